@@ -1,0 +1,72 @@
+"""ctypes binding of libplba.so (the C ABI of include/plba.h).  CUDA-only: there is no CPU fallback."""
+import ctypes as C
+import os
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_pd = C.POINTER(C.c_double)
+ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
+
+EXPORTS = ["plba_version", "plba_default_options", "plba_create", "plba_destroy", "plba_last_error", "plba_solve", "plba_solve_batch",
+           "plba_upload", "plba_reset_state", "plba_run", "plba_download", "plba_trial_assemble", "plba_trial_finish",
+           "plba_reduced_system", "plba_set_allreduce", "plba_get_timing", "plba_scene_preset", "plba_scene_create",
+           "plba_scene_problem", "plba_scene_truth", "plba_scene_destroy"]
+
+
+def declare(L):
+    abi.declare_common(L)
+    L.plba_version.restype = C.c_int
+    L.plba_default_options.argtypes = [C.c_int32, C.POINTER(abi.plba_options)]
+    L.plba_default_options.restype = None
+    L.plba_create.argtypes = [C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.plba_create.restype = C.c_int
+    L.plba_destroy.argtypes = [C.c_void_p]
+    L.plba_destroy.restype = None
+    L.plba_last_error.argtypes = [C.c_void_p]
+    L.plba_last_error.restype = C.c_char_p
+    L.plba_solve.argtypes = [C.c_void_p, C.POINTER(abi.plba_problem), C.POINTER(abi.plba_options), C.POINTER(abi.plba_result)]
+    L.plba_solve.restype = C.c_int
+    L.plba_solve_batch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.plba_problem), C.POINTER(abi.plba_options), C.POINTER(abi.plba_result)]
+    L.plba_solve_batch.restype = C.c_int
+    L.plba_upload.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.plba_problem), C.POINTER(abi.plba_options)]
+    L.plba_upload.restype = C.c_int
+    L.plba_reset_state.argtypes = [C.c_void_p]
+    L.plba_reset_state.restype = C.c_int
+    L.plba_run.argtypes = [C.c_void_p]
+    L.plba_run.restype = C.c_int
+    L.plba_download.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.plba_result)]
+    L.plba_download.restype = C.c_int
+    L.plba_trial_assemble.argtypes = [C.c_void_p, C.c_double]
+    L.plba_trial_assemble.restype = C.c_int
+    L.plba_trial_finish.argtypes = [C.c_void_p, C.c_double, _pd, _pd]
+    L.plba_trial_finish.restype = C.c_int
+    L.plba_reduced_system.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.plba_reduced_system.restype = C.c_int
+    L.plba_set_allreduce.argtypes = [C.c_void_p, ALLREDUCE_FN, C.c_void_p]
+    L.plba_set_allreduce.restype = C.c_int
+    L.plba_get_timing.argtypes = [C.c_void_p, C.POINTER(abi.plba_timing)]
+    L.plba_get_timing.restype = C.c_int
+    L.plba_set_detail_timing.argtypes = [C.c_void_p, C.c_int]
+    L.plba_set_detail_timing.restype = C.c_int
+    return L
+
+
+def library_path():
+    return os.path.join(_HERE, "libplba.so")
+
+
+def load(path=None):
+    """Load the CUDA library.  Raises (never falls back) if it has not been built."""
+    global _LIB
+    if path is not None:
+        return declare(C.CDLL(path))
+    if _LIB is None:
+        so = library_path()
+        if not os.path.exists(so):
+            raise RuntimeError("%s is missing: run `python -m pl_slam_plucker_b200.build` (nvcc, sm_100a). "
+                               "The LBA path is CUDA-only; there is no CPU fallback." % so)
+        _LIB = declare(C.CDLL(so))
+    return _LIB

@@ -1,0 +1,42 @@
+"""Builds pl_slam_plucker_b200/libplba.so (CUDA kernels + C ABI + scene generator) for sm_100a, in-tree."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SO = os.path.join(HERE, "libplba.so")
+SOURCES = ["plba_api.cu", "scene_gen.cpp"]
+HEADERS = ["plba_port.h", "plba_math.h", "plba_kernels.h", "plba_solver.h", os.path.join("..", "..", "include", "plba.h")]
+
+
+def nvcc_path():
+    for c in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found: the LBA library is CUDA-only and cannot be built without the CUDA toolkit")
+
+
+def is_stale():
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    if not force and not is_stale():
+        return SO
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "39", "-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    # the image exports CXX=/opt/gcc/bin/g++ which lacks parts of the toolchain; nvcc must use the system g++
+    env = dict(os.environ)
+    subprocess.check_call(cmd + ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else cmd, env=env)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

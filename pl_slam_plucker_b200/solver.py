@@ -1,0 +1,109 @@
+"""Python face of the C ABI: one `LBASolver` per GPU / stream (mirrors plba_handle)."""
+import ctypes as C
+import numpy as np
+
+from . import abi, _lib
+
+
+class LBAError(RuntimeError):
+    pass
+
+
+class LBASolver:
+    """B200 LBA solver handle.  `solve()` is the drop-in for the reference's three LBA functions (see include/plba.h)."""
+
+    def __init__(self, device=0, stream=None, lib=None):
+        self.L = lib or _lib.load()
+        self.h = C.c_void_p()
+        rc = self.L.plba_create(int(device), C.c_void_p(stream) if stream else None, C.byref(self.h))
+        if rc != 0 or not self.h:
+            raise LBAError("plba_create(device=%d) failed (%d): a CUDA device is required; there is no CPU fallback" % (device, rc))
+        self._cb = None
+        self._probs = None
+
+    def close(self):
+        if self.h:
+            self.L.plba_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, allow=(abi.OK, abi.DISCARDED)):
+        if rc not in allow:
+            raise LBAError("plba error %d: %s" % (rc, self.L.plba_last_error(self.h).decode()))
+        return rc
+
+    # ---- one-call interface (host buffers in, host buffers out) ----
+    def solve(self, prob, opt, trace_cap=256):
+        res = abi.Result(prob, trace_cap)
+        pc = prob.as_c()
+        res.rc = self._check(self.L.plba_solve(self.h, C.byref(pc), C.byref(opt.c), C.byref(res.c)))
+        return res
+
+    def solve_batch(self, probs, opt, trace_cap=64):
+        n = len(probs)
+        arr = (abi.plba_problem * n)(*[p.as_c() for p in probs])
+        results = [abi.Result(p, trace_cap) for p in probs]
+        rarr = (abi.plba_result * n)(*[r.c for r in results])
+        rc = self._check(self.L.plba_solve_batch(self.h, n, arr, C.byref(opt.c), rarr))
+        for i, r in enumerate(results):
+            r.c = rarr[i]
+            r.rc = rarr[i].status
+        return rc, results
+
+    # ---- staged interface (problem resident in HBM) ----
+    def upload(self, probs, opt):
+        if isinstance(probs, abi.Problem):
+            probs = [probs]
+        self._probs = list(probs)
+        n = len(self._probs)
+        arr = (abi.plba_problem * n)(*[p.as_c() for p in self._probs])
+        self._check(self.L.plba_upload(self.h, n, arr, C.byref(opt.c)))
+
+    def reset(self):
+        self._check(self.L.plba_reset_state(self.h))
+
+    def run(self):
+        self._check(self.L.plba_run(self.h))
+
+    def download(self, trace_cap=256):
+        n = len(self._probs)
+        results = [abi.Result(p, trace_cap) for p in self._probs]
+        rarr = (abi.plba_result * n)(*[r.c for r in results])
+        self._check(self.L.plba_download(self.h, n, rarr))
+        for i, r in enumerate(results):
+            r.c = rarr[i]
+            r.rc = rarr[i].status
+        return results
+
+    def trial_assemble(self, lam):
+        self._check(self.L.plba_trial_assemble(self.h, float(lam)))
+
+    def trial_finish(self, lam):
+        chi, sc = C.c_double(0), C.c_double(0)
+        self._check(self.L.plba_trial_finish(self.h, float(lam), C.byref(chi), C.byref(sc)))
+        return chi.value, sc.value
+
+    def reduced_system_ptr(self):
+        p, n = C.c_void_p(), C.c_int64()
+        self._check(self.L.plba_reduced_system(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def set_allreduce(self, fn):
+        """fn(ptr:int, n_doubles:int (negative => max-reduce of |n|), stream:int) sums the device buffer over ranks in place."""
+        def _cb(ptr, n, stream, user):
+            fn(ptr, n, stream)
+        self._cb = _lib.ALLREDUCE_FN(_cb)
+        self._check(self.L.plba_set_allreduce(self.h, self._cb, None))
+
+    def set_detail_timing(self, on=True):
+        self.L.plba_set_detail_timing(self.h, 1 if on else 0)
+
+    def timing(self):
+        t = abi.plba_timing()
+        self.L.plba_get_timing(self.h, C.byref(t))
+        return {k: getattr(t, k) for k, _ in abi.plba_timing._fields_}
