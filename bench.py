@@ -1,0 +1,261 @@
+#!/usr/bin/env python
+"""bench.py — LBA throughput of the CUDA path on B200, with roofline and CPU baseline (contract: task statement ④).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C1|C2|C4|C5] [--profile G|H_END|H_PLK] [--impl reference]
+
+A *step* is one complete local bundle adjustment (the drop-in call: full LM schedule of the chosen reference profile)
+over one synthetic window of the named workload.  Default workload = BASELINE config 2 (KITTI-shaped 20-KF window,
+8k points, 2k Plücker lines), default profile = G (what the reference runs in Plücker mode, SURVEY.md "Read this first").
+  value : observations/s = (point + line observations) x LM trials / device time, problem resident in HBM
+          (plba_reset_state + plba_run), CUDA events on the library's stream, L2 flushed between steps.
+  e2e   : the same metric through plba_solve() with HOST buffers in and out (H2D + D2H inside the timed region).
+  N > 1 : one rank per GPU, one independent window per rank (different seed), no data-path collective: weak scaling.
+--impl reference : the CPU restatement of the reference (oracle/, all host threads) on the same workload; rank 0 only.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+PROFILES = {"G": 0, "H_END": 1, "H_PLK": 2}
+WORKLOADS = {"C1": 1, "C2": 2, "C4": 4, "C5": 5}
+METRIC = "lba_observations_per_s"
+UNIT = "observations/s"
+
+
+def algorithmic_bytes(P, nnzb_S):
+    """every input read once + every output written once per LM trial (assembly + Schur stage)."""
+    nfix = P.n_kf - P.n_free
+    return (32 * P.n_pobs + 48 * P.n_lobs + 24 * P.n_pt + 32 * P.n_ls + 96 * (P.n_free + nfix)
+            + 288 * nnzb_S + 48 * P.n_free + 72 * P.n_pt + 112 * P.n_ls)
+
+
+def schur_nnz_blocks(P):
+    """Upper-triangular 6x6 blocks of S that are structurally non-zero (diag + co-visible free KF pairs)."""
+    nf = P.n_free
+    if nf > 400:            # banded estimate would need the pattern; count it exactly but vectorised per landmark run
+        pass
+    pat = np.zeros((nf, nf), bool)
+    np.fill_diagonal(pat, True)
+    for lm, kf in ((P.po_lm, P.po_kf), (P.lo_lm, P.lo_kf)):
+        if lm.size == 0:
+            continue
+        slot = P.kf_slot[kf]
+        ok = slot >= 0
+        lm, slot = lm[ok], slot[ok]
+        # first / last free slot per landmark: tracks are contiguous KF runs in the synthetic scenes and S is filled between
+        order = np.lexsort((slot, lm))
+        lm, slot = lm[order], slot[order]
+        start = np.r_[0, np.flatnonzero(lm[1:] != lm[:-1]) + 1]
+        end = np.r_[start[1:], lm.size]
+        for s, e in zip(start, end):
+            u = slot[s:e]
+            pat[np.ix_(u, u)] = True
+    return int(np.triu(pat).sum())
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons DURING the timed region (NVML; same fields as the nvidia-smi recipe line)."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons, self.stop_flag = index, period, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, str(e)
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def run_reference(args, rank):
+    """CPU arm: the oracle (restatement of the reference LBA; the reference itself is not buildable here) on all host threads."""
+    if rank != 0:
+        return
+    from oracle import loader as orc
+    from pl_slam_plucker_b200 import abi, scene
+    orc.build()
+    cores = orc.set_threads(os.cpu_count() or 1)
+    prof = PROFILES[args.profile]
+    P = scene.make_scene(WORKLOADS[args.workload], line_mode=1 if prof == abi.PROFILE_H_END else 0)
+    opt = abi.Options(prof, args.quirks)
+    for _ in range(min(args.warmup, 1)):
+        orc.solve(P, opt)
+    t0 = time.perf_counter(); trials = 0
+    steps = max(1, min(args.steps, 20))
+    for _ in range(steps):
+        r = orc.solve(P, opt); trials += r.n_trials
+    dt = time.perf_counter() - t0
+    val = P.n_obs * trials / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "lm_iters_per_s": trials / dt,
+            "config": {"workload": workload_name(args, P), "profile": args.profile, "quirks": args.quirks, "windows_per_gpu": 1},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d full LBA solves of the %s window (oracle/plba_oracle.cpp, OpenMP over landmarks)" % (steps, args.workload)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args, P):
+    return "%s: %d free + %d fixed KFs, %d points, %d lines, %d+%d observations" % (
+        args.workload, P.n_free, P.n_kf - P.n_free, P.n_pt, P.n_ls, P.n_pobs, P.n_lobs)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--profile", default="G", choices=sorted(PROFILES))
+    ap.add_argument("--quirks", type=int, default=0, help="0 = faithful (bug-for-bug), 1 = fixed")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from pl_slam_plucker_b200 import abi, scene, solver
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the LBA path is CUDA-only (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    prof = PROFILES[args.profile]
+    cfg = WORKLOADS[args.workload]
+    sp = scene.preset(cfg)
+    P = scene.make_scene(cfg, line_mode=1 if prof == abi.PROFILE_H_END else 0, seed=int(sp.seed) + 1000 * rank)
+    opt = abi.Options(prof, args.quirks)
+    stream = torch.cuda.Stream(device=dev)
+    s = solver.LBASolver(local, stream=stream.cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-problem throughput -------------------------------------------------------------------------
+    s.upload(P, opt)
+    s.set_detail_timing(True)
+    for _ in range(args.warmup):
+        s.reset(); s.run()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local); sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    trials = launches = 0
+    t_asm = t_sol = t_upd = 0.0; n_asm = 0
+    barrier()
+    for k in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()                                              # L2 flush between timed iterations (untimed)
+            s.reset()
+            ev[k][0].record(stream)
+            s.run()
+            ev[k][1].record(stream)
+        t = s.timing()
+        launches += t["n_launches_run"]; n_asm += t["n_assemble_run"]; trials += t["n_trials_run"]
+        t_asm += t["ms_assemble"]; t_sol += t["ms_solve"]; t_upd += t["ms_update"]
+    barrier()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    # ---- end to end through the drop-in call: host buffers in, host buffers out ----------------------------------
+    for _ in range(3):
+        s.solve(P, opt)
+    e2e_steps = max(3, args.steps // 4)
+    barrier()
+    t0 = time.perf_counter(); e2e_trials = 0; h2d = d2h = 0
+    for _ in range(e2e_steps):
+        r = s.solve(P, opt); e2e_trials += r.n_trials
+        t = s.timing(); h2d += t["h2d_bytes"]; d2h += t["d2h_bytes"]
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True; sampler.join()
+
+    tt = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float(P.n_obs * trials), float(P.n_obs * e2e_trials), float(trials)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_max, e2e_ms_max = tt.tolist(); obs_trials, e2e_obs_trials, trials_all = cnt.tolist()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
+        nnzb = schur_nnz_blocks(P)
+        A = algorithmic_bytes(P, nnzb)
+        asm_ms = t_asm / max(n_asm, 1)
+        line = {"metric": METRIC, "value": obs_trials / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "lm_iters_per_s": trials_all / (ms_max * 1e-3), "lm_trials_per_step": trials / args.steps,
+                "config": {"workload": workload_name(args, P), "profile": args.profile, "quirks": args.quirks, "windows_per_gpu": 1,
+                           "l2": "flushed between steps (256 MiB write)", "parallelism": "one independent window per GPU, no collective"},
+                "e2e": {"value": e2e_obs_trials / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
+                        "ms_per_step": e2e_ms_max / e2e_steps, "steps": e2e_steps},
+                "gpu_launches": int(launches),
+                "clocks": sampler.summary(),
+                "roofline": {"bound": "hbm", "kernel": "k_assemble (point + line launch pair of one LM trial)", "achieved": A / (asm_ms * 1e-3) / 1e9 if asm_ms > 0 else None,
+                             "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": (A / (asm_ms * 1e-3) / 1e9 / peak) if asm_ms > 0 else None,
+                             "traffic": None, "algorithmic_bytes": A, "ms_per_launch": asm_ms, "launches_timed": int(n_asm),
+                             "stage_ms_per_step": {"assemble": t_asm / args.steps, "solve": t_sol / args.steps, "update": t_upd / args.steps}}}
+        if not args.no_cpu_baseline:
+            from oracle import loader as orc
+            orc.build(); orc.set_threads(1)
+            t0 = time.perf_counter(); n = 0; ctr = 0
+            while time.perf_counter() - t0 < 10.0 or n < 1:
+                ro = orc.solve(P, opt); ctr += ro.n_trials; n += 1
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": P.n_obs * ctr / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": "%d full LBA solves of the same %s window by the oracle (single thread, as the reference: CMakeLists.txt:34 has no OpenMP), %.1f s" % (n, args.workload, dt),
+                                    "host_cores_available": os.cpu_count()}
+        print(json.dumps(line), flush=True)
+    s.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -183,6 +183,9 @@ int  plba_trial_finish(plba_handle h, double lambda, double *chi_new, double *sc
 /* Reduced camera system exposed for the cross-GPU reduction: device pointer + length in doubles of
  * [S blocks | g_red | cost scalars]; the caller all-reduces it in place between assemble and finish. */
 int  plba_reduced_system(plba_handle h, void **dev_ptr, int64_t *n_doubles);
+/* Host copy of one window's reduced camera system as left by plba_trial_assemble(): S_out[6 n_free][6 n_free] row-major
+ * (upper triangle of 6x6 blocks filled, undamped) and g_out[6 n_free].  Either pointer may be NULL. */
+int  plba_copy_reduced_system(plba_handle h, int32_t window, double *S_out, double *g_out);
 /* Optional all-reduce hook called on the handle's stream wherever the path has its exchange step
  * (SURVEY.md §8e).  fn(dev_ptr, n_doubles, stream, user) must sum the buffer in place over all ranks. */
 typedef void (*plba_allreduce_fn)(void *dev_ptr, int64_t n_doubles, void *stream, void *user);
@@ -193,9 +196,14 @@ typedef struct plba_timing {
     double  ms_total, ms_assemble, ms_solve, ms_update, ms_other;
     int64_t n_launches;      /* kernels launched by the library in the last plba_run / plba_solve  */
     int64_t n_assemble;      /* launches of the assembly kernel                                    */
-    int64_t h2d_bytes, d2h_bytes;
+    int64_t h2d_bytes, d2h_bytes;  /* host<->device bytes moved by the last plba_upload / plba_download (plba_solve = both) */
+    int64_t n_launches_run;  /* kernels launched by the last plba_run                              */
+    int64_t n_assemble_run;  /* assembly-kernel launches of the last plba_run                      */
+    int64_t n_trials_run;    /* LM trials (linear solves) of the last plba_run, summed over windows */
 } plba_timing;
 int  plba_get_timing(plba_handle h, plba_timing *t);
+/* on: record CUDA events around the assembly / solve / update kernels of every LM round (fills ms_assemble ...). */
+int  plba_set_detail_timing(plba_handle h, int on);
 
 /* ---- synthetic scenes: deterministic generator shared by tests, bench and oracle ---- */
 typedef struct plba_scene_spec {

@@ -284,7 +284,7 @@ int plba_reset_state(plba_handle h) {
     CK(cudaMemsetAsync(P.trace, 0, sizeof(plba_trace_rec) * (size_t)P.n_win * P.trace_cap, st));
     CK(cudaMemcpyAsync(P.ctrl, h->ctrl_init.data(), sizeof(WinCtrl) * (size_t)P.n_win, cudaMemcpyHostToDevice, st));
     int ndone = 0; for (const WinCtrl &c : h->ctrl_init) ndone += c.done;
-    h->h_counters[CNT_DONE] = ndone; h->h_counters[CNT_NEED_INIT] = P.n_win - ndone; h->h_counters[CNT_GATE] = 0; h->h_counters[3] = 0;
+    h->h_counters[CNT_DONE] = ndone; h->h_counters[CNT_NEED_INIT] = P.n_win - ndone; h->h_counters[CNT_GATE] = 0; h->h_counters[CNT_TRIALS] = 0;
     CK(cudaMemcpyAsync(P.counters, h->h_counters, sizeof(int) * CNT_N, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
     return PLBA_OK;
@@ -421,7 +421,7 @@ int plba_run(plba_handle h) {
     DevP &P = h->P; cudaStream_t st = h->stream;
     const bool G = (P.profile == PLBA_PROFILE_G);
     const int max_rounds = G ? (P.iters_stage1 + P.iters_stage2) * P.lm_max_trials + 2 : P.max_iters_lba + 1;
-    const int64_t launches0 = h->timing.n_launches;
+    const int64_t launches0 = h->timing.n_launches, assemble0 = h->timing.n_assemble;
     h->timing.ms_assemble = h->timing.ms_solve = h->timing.ms_update = 0;
     cudaEventRecord(h->ev[6], st);
     int rc;
@@ -451,7 +451,9 @@ int plba_run(plba_handle h) {
     float ms = 0; cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]);
     h->timing.ms_total = ms;
     h->timing.ms_other = ms - h->timing.ms_assemble - h->timing.ms_solve - h->timing.ms_update;
-    (void)launches0;
+    h->timing.n_launches_run = h->timing.n_launches - launches0;
+    h->timing.n_assemble_run = h->timing.n_assemble - assemble0;
+    h->timing.n_trials_run = h->h_counters[CNT_TRIALS];
     CK(cudaGetLastError());
     return PLBA_OK;
 }
@@ -585,6 +587,18 @@ int plba_reduced_system(plba_handle h, void **dev_ptr, int64_t *n_doubles) {
     if (!h || !h->uploaded) return PLBA_E_ARG;
     if (dev_ptr) *dev_ptr = h->sysbuf;
     if (n_doubles) *n_doubles = (int64_t)(h->S_doubles + (size_t)6 * h->P.n_free);
+    return PLBA_OK;
+}
+int plba_copy_reduced_system(plba_handle h, int32_t window, double *S_out, double *g_out) {
+    if (!h || !h->uploaded || window < 0 || window >= h->P.n_win) return PLBA_E_ARG;
+    const WinInfo &wi = h->wins[window];
+    const size_t n = (size_t)6 * wi.n_free;
+    std::vector<long long> off(1);
+    CK(cudaMemcpyAsync(off.data(), h->P.win_S_off + window, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (S_out && n) CK(cudaMemcpyAsync(S_out, h->P.S + off[0], sizeof(double) * n * n, cudaMemcpyDeviceToHost, h->stream));
+    if (g_out && n) CK(cudaMemcpyAsync(g_out, h->P.gs + (size_t)6 * wi.slot0, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return PLBA_OK;
 }
 int plba_get_timing(plba_handle h, plba_timing *t) { if (!h || !t) return PLBA_E_ARG; *t = h->timing; return PLBA_OK; }

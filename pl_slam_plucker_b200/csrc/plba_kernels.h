@@ -29,7 +29,7 @@ struct WinCtrl {
 // per-window accumulators that ARE summed over ranks (landmark-sharded multi-GPU): P.acc[8*w + ...]
 // assemble-phase sums live in P.acc[4*w + ...], update-phase sums in P.accB[4*w + ...] (two all-reduce ranges)
 enum { ACC_CHI_LIN = 0, ACC_ERR_PT = 1, ACC_ERR_LS = 2, ACC_CHI_NEW = 0, ACC_SCALE = 1, ACC_DX2 = 2, ACC_N = 8 };
-enum { CNT_DONE = 0, CNT_NEED_INIT = 1, CNT_GATE = 2, CNT_N = 4 };
+enum { CNT_DONE = 0, CNT_NEED_INIT = 1, CNT_GATE = 2, CNT_TRIALS = 3, CNT_N = 4 };
 
 struct DevP {
     Cam cam;
@@ -589,6 +589,7 @@ PLBA_KERNEL void k_control(DevP P) {
             WinCtrl &c = P.ctrl[w];
             if (!c.done) {
                 c.n_trials++;
+                plba_atomic_add_i(&P.counters[CNT_TRIALS], 1);
                 const double *acc = P.acc + (size_t)4 * w, *accB = P.accB + (size_t)4 * w;
                 if (P.profile == PLBA_PROFILE_G) {
                     if (c.trial == 0) c.chi_cur = acc[ACC_CHI_LIN];                // currentChi = activeRobustChi2()

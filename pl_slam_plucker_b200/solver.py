@@ -93,6 +93,13 @@ class LBASolver:
         self._check(self.L.plba_reduced_system(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def copy_reduced_system(self, window=0):
+        """(S, g) of one window after trial_assemble(): S dense [6nf, 6nf] with the upper block triangle filled, undamped."""
+        n = 6 * self._probs[window].n_free
+        S, g = np.zeros((n, n)), np.zeros(n)
+        self._check(self.L.plba_copy_reduced_system(self.h, int(window), S.ctypes.data_as(_lib._pd), g.ctypes.data_as(_lib._pd)))
+        return S, g
+
     def set_allreduce(self, fn):
         """fn(ptr:int, n_doubles:int (negative => max-reduce of |n|), stream:int) sums the device buffer over ranks in place."""
         def _cb(ptr, n, stream, user):

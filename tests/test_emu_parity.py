@@ -1,0 +1,25 @@
+"""CPU-side rehearsal of the GPU parity tests: the SAME kernel sources compiled with -DPLBA_HOST_EMU (tests/emu, test
+tooling only) run the small parity cases against the oracle, so that kernel logic is checked on a box without a GPU.
+The product library (libplba.so) is never replaced by this build; `-m gpu` runs the real thing."""
+import pytest
+
+import test_gpu_parity as g
+from pl_slam_plucker_b200 import solver
+
+
+@pytest.fixture(scope="module")
+def gpu_solver(emu):
+    s = solver.LBASolver(0, lib=emu)
+    yield s
+    s.close()
+
+
+test_small_window_all_profiles = g.test_small_window_all_profiles
+test_golden_fixtures = g.test_golden_fixtures
+test_large_window_tiled_solver = g.test_large_window_tiled_solver
+test_loop_closure_shaped_window = g.test_loop_closure_shaped_window
+test_batch_equals_individual_solves = g.test_batch_equals_individual_solves
+test_reduced_system_blocks_and_sparsity = g.test_reduced_system_blocks_and_sparsity
+test_edge_cases = g.test_edge_cases
+test_sigma_weights = g.test_sigma_weights
+test_map_handler_interface = g.test_map_handler_interface

@@ -1,0 +1,247 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (include/plba.h) exactly as the reference's host code
+would call it, against the CPU oracle on identical synthetic scenes.
+
+Tolerances are BASELINE.json's: per-iteration cost 1e-9 relative, final poses / landmarks 1e-8 absolute; observation
+gating, level flags and the Schur sparsity pattern are index work and must be bit-exact.
+Nothing here reads /root/reference (it does not exist on the GPU box).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import COST_RTOL, STATE_ATOL, assert_state_close, assert_trace_close
+from pl_slam_plucker_b200 import abi, scene
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+ALL = [(abi.PROFILE_G, 0), (abi.PROFILE_G, 1), (abi.PROFILE_H_END, 0), (abi.PROFILE_H_END, 1), (abi.PROFILE_H_PLK, 0), (abi.PROFILE_H_PLK, 1)]
+
+
+def _scene(cfg, prof, **kw):
+    return scene.make_scene(cfg, line_mode=1 if prof == abi.PROFILE_H_END else 0, **kw)
+
+
+def _check(gpu_solver, oracle, P, prof, q):
+    opt = abi.Options(prof, q)
+    r, o = gpu_solver.solve(P, opt), oracle.solve(P, opt)
+    assert r.rc == o.rc
+    assert gpu_solver.timing()["n_launches"] > 0            # the CUDA path ran (not a fallback)
+    n = assert_trace_close(o.trace, r.trace, prof)
+    assert_state_close(o, r, P, prof)
+    return r, o, n
+
+
+@pytest.mark.parametrize("prof,q", ALL)
+def test_small_window_all_profiles(gpu_solver, oracle, prof, q):
+    P = _scene(1, prof, n_kf_free=4, n_kf_fixed=2, n_pt=60, n_ls=20)
+    _check(gpu_solver, oracle, P, prof, q)
+
+
+@pytest.mark.parametrize("prof,q", ALL)
+def test_config1_euroc_window(gpu_solver, oracle, prof, q):
+    """BASELINE config 1: 10-KF window, 2k points, 500 lines."""
+    P = _scene(1, prof)
+    r, o, n = _check(gpu_solver, oracle, P, prof, q)
+    assert len(r.trace) == len(o.trace) or prof == abi.PROFILE_G
+
+
+@pytest.mark.parametrize("prof,q", [(abi.PROFILE_G, 0), (abi.PROFILE_G, 1), (abi.PROFILE_H_END, 0)])
+def test_config2_kitti_window(gpu_solver, oracle, prof, q):
+    """BASELINE config 2 (the bench workload): 20-KF window, 8k points, 2k lines."""
+    P = _scene(2, prof)
+    _check(gpu_solver, oracle, P, prof, q)
+
+
+@pytest.mark.parametrize("name", ["g_faithful", "g_fixed", "h_end_faithful", "h_plk_fixed"])
+def test_golden_fixtures(gpu_solver, name):
+    """Committed vectors (tests/golden/make_golden.py) — no oracle involved at run time."""
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    prob = abi.Problem(z["cam"], z["kf_T_wc"], z["kf_slot"], z["pt_xyz"], z["po_lm"], z["po_kf"], z["po_uv"], ls_plk=z["ls_plk"],
+                       ls_end=z["ls_end"], lo_lm=z["lo_lm"], lo_kf=z["lo_kf"], lo_ab=z["lo_ab"], x_pose=z["x_pose"])
+    r = gpu_solver.solve(prob, abi.Options(int(z["profile"]), int(z["quirks"])))
+    n = int(z["n_robust"])
+    fin = np.isfinite(z["trace_chi"][:n])
+    np.testing.assert_allclose(r.trace["chi"][:n][fin], z["trace_chi"][:n][fin], rtol=COST_RTOL)
+    np.testing.assert_allclose(r.trace["lambda"][:n], z["trace_lambda"][:n], rtol=COST_RTOL)
+    assert (r.trace["accepted"][:n] == z["trace_accepted"][:n]).all()
+    np.testing.assert_allclose(r.kf_T_wc, z["out_kf_T_wc"], atol=STATE_ATOL)
+    np.testing.assert_allclose(r.pt_xyz, z["out_pt_xyz"], atol=STATE_ATOL)
+    if int(z["profile"]) == abi.PROFILE_H_END:
+        np.testing.assert_allclose(r.ls_end, z["out_ls_end"], atol=STATE_ATOL)
+    else:
+        np.testing.assert_allclose(r.ls_orth, z["out_ls_orth"], atol=STATE_ATOL)
+        np.testing.assert_allclose(r.ls_plk, z["out_ls_plk"], atol=STATE_ATOL)
+    if int(z["profile"]) == abi.PROFILE_G:
+        assert (r.po_flags == z["out_po_flags"]).all() and (r.lo_flags == z["out_lo_flags"]).all()
+
+
+def test_large_window_tiled_solver(gpu_solver, oracle):
+    """6*Nkf = 180 > single-CTA limit: exercises the tiled Cholesky of the reduced camera system."""
+    P = scene.make_scene(1, n_kf_free=30, n_kf_fixed=2, n_pt=600, n_ls=150, seed=7)
+    _check(gpu_solver, oracle, P, abi.PROFILE_G, 1)
+
+
+def test_loop_closure_shaped_window(gpu_solver, oracle):
+    """Non-banded reduced camera system (KF i also sees landmarks of KF i-7)."""
+    P = scene.make_scene(1, n_kf_free=16, n_kf_fixed=2, n_pt=500, n_ls=120, loop_every=7, seed=11)
+    _check(gpu_solver, oracle, P, abi.PROFILE_G, 1)
+    _check(gpu_solver, oracle, P, abi.PROFILE_G, 0)
+
+
+def test_batch_equals_individual_solves(gpu_solver, oracle):
+    """BASELINE config 3 semantics: a batch of independent windows == the same windows solved one by one."""
+    probs = scene.make_batch(6, 3, n_pt=300, n_ls=80)
+    probs[2] = scene.make_scene(1, n_kf_free=6, n_kf_fixed=1, n_pt=150, n_ls=0, seed=5)          # ragged: different shape, no lines
+    opt = abi.Options(abi.PROFILE_G, 0)
+    rc, rs = gpu_solver.solve_batch(probs, opt)
+    assert rc == abi.OK
+    for P, r in zip(probs, rs):
+        o = oracle.solve(P, opt)
+        assert_trace_close(o.trace, r.trace, abi.PROFILE_G)
+        assert_state_close(o, r, P, abi.PROFILE_G)
+    opt = abi.Options(abi.PROFILE_H_PLK, 1)
+    rc, rs = gpu_solver.solve_batch(probs, opt)
+    for P, r in zip(probs, rs):
+        o = oracle.solve(P, opt)
+        assert_trace_close(o.trace, r.trace, abi.PROFILE_H_PLK)
+        assert_state_close(o, r, P, abi.PROFILE_H_PLK)
+
+
+def test_reduced_system_blocks_and_sparsity(gpu_solver, oracle):
+    """Subsystems 1-3 in isolation: S and g_red after one linearisation vs the oracle; block sparsity bit-exact."""
+    P = scene.make_scene(1, n_kf_free=12, n_kf_fixed=2, n_pt=400, n_ls=100, seed=3)
+    opt = abi.Options(abi.PROFILE_G, 0)
+    lam = 3.5
+    gpu_solver.upload(P, opt)
+    gpu_solver.trial_assemble(lam)
+    S, g = gpu_solver.copy_reduced_system(0)
+    So, go, chi = oracle.reduced_system_G(P, opt, lam)
+    nf = P.n_free
+    Sg = S.reshape(nf, 6, nf, 6).transpose(0, 2, 1, 3)
+    iu = np.triu_indices(nf)
+    for a, b in zip(*iu):
+        ref = So[a, b].copy()
+        if a == b:                                   # oracle exports the damped diagonal; the C ABI the undamped one
+            ref = ref - lam * np.eye(6)
+            got = np.triu(Sg[a, b]); ref = np.triu(ref)
+        else:
+            got = Sg[a, b]
+        np.testing.assert_allclose(got, ref, rtol=1e-10, atol=1e-7 * max(1.0, np.abs(ref).max()))
+    np.testing.assert_allclose(g, go, rtol=1e-10, atol=1e-8 * np.abs(go).max())
+    # sparsity: block (a,b) is structurally non-zero iff some landmark is seen by free KFs a and b
+    pat = np.zeros((nf, nf), bool)
+    for lm, kf in ((P.po_lm, P.po_kf), (P.lo_lm, P.lo_kf)):
+        slot = P.kf_slot[kf]
+        for l in np.unique(lm):
+            s = np.unique(slot[lm == l]); s = s[s >= 0]
+            pat[np.ix_(s, s)] = True
+    got_pat = np.abs(Sg).max(axis=(2, 3)) > 0
+    assert (np.triu(got_pat) == np.triu(pat)).all()
+
+
+def test_edge_cases(gpu_solver, oracle):
+    base = scene.make_scene(1, n_kf_free=3, n_kf_fixed=1, n_pt=40, n_ls=10, seed=21)
+    # empty problem: nothing to do (src/mapHandler.cpp:1499-1500)
+    E = abi.Problem(base.cam, base.kf_T_wc, base.kf_slot, np.zeros((0, 3)), None, None, None)
+    assert gpu_solver.solve(E, abi.Options(abi.PROFILE_H_END)).rc == abi.DISCARDED
+    # points only / lines only
+    Pp = abi.Problem(base.cam, base.kf_T_wc, base.kf_slot, base.pt_xyz, base.po_lm, base.po_kf, base.po_uv, ls_plk=np.zeros((0, 6)), x_pose=base.x_pose)
+    _check(gpu_solver, oracle, Pp, abi.PROFILE_G, 0)
+    Pl = abi.Problem(base.cam, base.kf_T_wc, base.kf_slot, np.zeros((0, 3)), None, None, None, ls_plk=base.ls_plk, lo_lm=base.lo_lm,
+                     lo_kf=base.lo_kf, lo_ab=base.lo_ab, x_pose=base.x_pose)
+    _check(gpu_solver, oracle, Pl, abi.PROFILE_G, 1)
+    # ragged tracks: single-observation landmarks, landmarks seen only by the fixed KF, a landmark without observations
+    keep = np.ones(base.n_pobs, bool)
+    first = np.r_[True, base.po_lm[1:] != base.po_lm[:-1]]
+    keep[(base.po_lm < 10) & ~first] = False                      # landmarks 0..9 keep one observation
+    keep[base.po_lm == 12] = False                                # landmark 12 has none
+    po_kf = base.po_kf.copy(); po_kf[base.po_lm == 15] = 0        # landmark 15 only in the fixed KF
+    Pr = abi.Problem(base.cam, base.kf_T_wc, base.kf_slot, base.pt_xyz, base.po_lm[keep], po_kf[keep], base.po_uv[keep], ls_plk=base.ls_plk,
+                     lo_lm=base.lo_lm, lo_kf=base.lo_kf, lo_ab=base.lo_ab, x_pose=base.x_pose)
+    for prof, q in ((abi.PROFILE_G, 0), (abi.PROFILE_H_PLK, 1)):
+        _check(gpu_solver, oracle, Pr, prof, q)
+    # malformed input is rejected, not executed
+    from pl_slam_plucker_b200.solver import LBAError
+    bad = abi.Problem(base.cam, base.kf_T_wc, base.kf_slot, base.pt_xyz, base.po_lm, base.po_kf + 100, base.po_uv)
+    with pytest.raises(LBAError):
+        gpu_solver.solve(bad, abi.Options(abi.PROFILE_G))
+    unsorted = abi.Problem(base.cam, base.kf_T_wc, base.kf_slot, base.pt_xyz, base.po_lm[::-1], base.po_kf[::-1], base.po_uv[::-1])
+    with pytest.raises(LBAError):
+        gpu_solver.solve(unsorted, abi.Options(abi.PROFILE_G))
+
+
+def test_sigma_weights(gpu_solver, oracle):
+    """Omega = I / sigma^2 rounded through float (src/mapHandler.cpp:6009-6010, Q13)."""
+    P = scene.make_scene(1, n_kf_free=4, n_kf_fixed=2, n_pt=80, n_ls=20, seed=8)
+    rng = np.random.default_rng(0)
+    P.po_sig2 = rng.uniform(0.5, 2.0, P.n_pobs); P.lo_sig2 = rng.uniform(0.5, 2.0, P.n_lobs)
+    _check(gpu_solver, oracle, P, abi.PROFILE_G, 0)
+
+
+def test_map_handler_interface(gpu_solver, oracle):
+    """The reference-named entry points (include/mapHandler.h:128-134) on a pointer-style map."""
+    from pl_slam_plucker_b200 import map_handler as mhm
+    P = scene.make_scene(1, n_kf_free=5, n_kf_fixed=2, n_pt=120, n_ls=30, seed=13)
+    mh = mhm.map_from_problem(P, gpu_solver, quirks=abi.QUIRKS_FAITHFUL)
+    n_before = sum(len(p.obs_list) for p in mh.map_points)
+    mh.localBundleAdjustmentForPlukerWithG2O()
+    o = oracle.solve(P, abi.Options(abi.PROFILE_G, 0))
+    for k in range(P.n_kf):
+        if P.kf_slot[k] >= 0:
+            np.testing.assert_allclose(mh.map_keyframes[k].T_kf_w[:3, :].reshape(12), o.kf_T_wc[k], atol=STATE_ATOL)
+    np.testing.assert_allclose(np.array([p.point3D for p in mh.map_points]), o.pt_xyz, atol=STATE_ATOL)
+    np.testing.assert_allclose(np.array([l.NDw for l in mh.map_lines]), o.ls_plk, atol=STATE_ATOL)
+    n_bad = int(((o.po_flags & abi.OBS_BAD) != 0).sum())
+    assert mh.bad_point_obs == n_bad
+    assert sum(len(p.obs_list) for p in mh.map_points) <= n_before
+    # hand-LM entry point with the reference's argument list
+    Pe = scene.make_scene(1, n_kf_free=5, n_kf_fixed=2, n_pt=120, n_ls=30, seed=13, line_mode=1)
+    mh = mhm.map_from_problem(Pe, gpu_solver, endpoint_lines=True)
+    # kf_idx 0 is never optimised by the reference driver (:1403); the scene's fixed KFs are rows 0..1 (local=False)
+    assert mh.localBundleAdjustment() == 0
+    o = oracle.solve(Pe, abi.Options(abi.PROFILE_H_END, 0))
+    for k in range(Pe.n_kf):
+        if Pe.kf_slot[k] >= 0:
+            np.testing.assert_allclose(mh.map_keyframes[k].T_kf_w[:3, :].reshape(12), o.kf_T_wc[k], atol=STATE_ATOL)
+    np.testing.assert_allclose(np.array([p.point3D for p in mh.map_points]), o.pt_xyz, atol=STATE_ATOL)
+    mh.vo_status = mhm.VO_INSERTING_KF
+    assert mh.localBundleAdjustment() == -1               # computed but discarded (:3011-3012)
+
+
+def test_config4_full_size_properties(gpu_solver):
+    """BASELINE config 4 at full size (200 KFs, 200k points, 50k lines): properties that need no oracle run."""
+    P, truth = scene.make_scene(4, with_truth=True)
+    opt = abi.Options(abi.PROFILE_G, 1)
+    r = gpu_solver.solve(P, opt)
+    assert r.rc == abi.OK
+    tr = r.trace
+    acc = tr[tr["accepted"] == 1]
+    assert len(acc) >= 5
+    assert (acc["chi_new"] < acc["chi"]).all()                       # every accepted LM step lowers the robust cost
+    s0 = tr[tr["stage"] == 0]
+    assert s0["chi"][-1] < 0.2 * s0["chi"][0]
+    free = P.kf_slot >= 0
+    e0 = np.abs(P.kf_T_wc[free] - truth["kf_T_wc"][free]).max(); e1 = np.abs(r.kf_T_wc[free] - truth["kf_T_wc"][free]).max()
+    assert e1 < 0.5 * e0                                             # moved towards the generating truth
+    np.testing.assert_array_equal(r.kf_T_wc[~free], P.kf_T_wc[~free])  # fixed observers untouched
+    # idempotence of the write-back representation: orth -> Plücker is unit norm (a8)
+    np.testing.assert_allclose(np.linalg.norm(r.ls_plk, axis=1), 1.0, atol=1e-12)
+    # gating is consistent with the returned chi2
+    assert ((r.po_chi2 > opt.chi2_gate) <= ((r.po_flags & abi.OBS_BAD) != 0)).all()
+    assert (((r.lo_flags & abi.OBS_BAD) != 0) == (r.lo_chi2 > opt.chi2_gate)).all()
+    # landmark-sharded assembly: sum of shard reduced systems == whole (linearity; the multi-GPU exchange step)
+    gpu_solver.upload(P, opt); gpu_solver.trial_assemble(1.0)
+    S, g = gpu_solver.copy_reduced_system(0)
+    home = np.zeros(P.n_pt, np.int64); home[P.po_lm[::-1]] = P.po_kf[::-1]
+    homel = np.zeros(P.n_ls, np.int64); homel[P.lo_lm[::-1]] = P.lo_kf[::-1]
+    cut = P.n_kf // 2
+    Ssum, gsum = np.zeros_like(S), np.zeros_like(g)
+    for m_p, m_l in ((home < cut, homel < cut), (home >= cut, homel >= cut)):
+        gpu_solver.upload(P.subset_landmarks(m_p, m_l), opt); gpu_solver.trial_assemble(1.0)
+        Si, gi = gpu_solver.copy_reduced_system(0)
+        Ssum += Si; gsum += gi
+    # H_pp of an observation travels with its landmark, so the sum is exact up to rounding
+    np.testing.assert_allclose(Ssum, S, rtol=1e-9, atol=1e-6 * np.abs(S).max())
+    np.testing.assert_allclose(gsum, g, rtol=1e-9, atol=1e-9 * np.abs(g).max())
