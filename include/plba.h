@@ -186,6 +186,10 @@ int  plba_reduced_system(plba_handle h, void **dev_ptr, int64_t *n_doubles);
 /* Host copy of one window's reduced camera system as left by plba_trial_assemble(): S_out[6 n_free][6 n_free] row-major
  * (upper triangle of 6x6 blocks filled, undamped) and g_out[6 n_free].  Either pointer may be NULL. */
 int  plba_copy_reduced_system(plba_handle h, int32_t window, double *S_out, double *g_out);
+/* Average device time (ms) of one launch of a stage kernel on the resident problem, `reps` back-to-back launches between
+ * two CUDA events on the handle's stream.  which: 0 = assembly (linearise + blocks + Schur), 1 = reduced-system solve,
+ * 2 = update (back-substitution + retraction + new cost).  The LM state is not advanced. */
+int  plba_time_kernel(plba_handle h, int32_t which, int32_t reps, double lambda, double *ms_avg);
 /* Optional all-reduce hook called on the handle's stream wherever the path has its exchange step
  * (SURVEY.md §8e).  fn(dev_ptr, n_doubles, stream, user) must sum the buffer in place over all ranks. */
 typedef void (*plba_allreduce_fn)(void *dev_ptr, int64_t n_doubles, void *stream, void *user);

@@ -25,18 +25,22 @@ def is_stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    if not force and not is_stale():
+def build(force=False, verbose=False, out=None, defines=()):
+    global SO
+    if out is None and not force and not is_stale():
         return SO
+    target = out or SO
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "39", "-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "39", "-o", target] + ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     # the image exports CXX=/opt/gcc/bin/g++ which lacks parts of the toolchain; nvcc must use the system g++
     env = dict(os.environ)
     subprocess.check_call(cmd + ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else cmd, env=env)
-    return SO
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=outs[0] if outs else None, defines=defs))

@@ -1,10 +1,22 @@
-// Host side of the C ABI (include/plba.h): flattening of one or many LBA windows into the resident SoA layout,
-// the round loop that drives the kernels (no per-observation work on the host), and the write-back.
+// Host side of the C ABI (include/plba.h).
+//   upload   : index bookkeeping only — landmarks of each window are sorted by keyframe signature, cut into chunks and
+//              segments, and flattened straight into ONE pinned staging buffer that reaches HBM with a single H2D copy;
+//              device memory is one arena per handle (no per-call cudaMalloc).
+//   run      : the whole LM schedule is a CUDA graph: WHILE(windows left){ IF(prep){gate, lambda init}; assemble; solve;
+//              update+controller }.  The controller runs on the device and steers both conditional nodes, so the host
+//              is not in the loop.  The graph is built once per (handle, profile): kernel parameters live at a fixed
+//              device address and the grids are persistent, so nothing in the graph depends on the problem.
+//              A host-driven loop over the same kernels remains for the tiled large-window solver, for the sharded
+//              multi-GPU exchange step (all-reduce hook) and for per-kernel event timing.
+//   download : one export kernel, one D2H copy, host-side un-permutation into the caller's buffers.
 // There is NO CPU fallback in this file: every numeric step is a kernel launch on the handle's stream.
 #include <vector>
 #include <string>
+#include <tuple>
+#include <utility>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include "plba_solver.h"
 
 using namespace plba;
@@ -13,36 +25,85 @@ using namespace plba;
 
 struct WinInfo { int n_kf, n_free, n_pt, n_ls, n_pobs, n_lobs, kf0, slot0, pt0, ls0, po0, lo0; };
 
+// bump allocator over a byte range (device arena or pinned staging): 256-byte aligned carve-outs
+struct Carver {
+    size_t off = 0;
+    template <typename T> size_t take(size_t n) { const size_t o = off; off += (std::max<size_t>(n, 1) * sizeof(T) + 255) & ~(size_t)255; return o; }
+};
+
 struct plba_handle_s {
-    int device = 0;
+    int device = 0, n_sm = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::string err;
-    std::vector<void *> allocs;
+    // memory
+    char *d_arena = nullptr; size_t d_cap = 0;
+    char *h_in = nullptr; size_t h_in_cap = 0;       // pinned: staged inputs
+    char *h_out = nullptr; size_t h_out_cap = 0;     // pinned: staged outputs
+    DevP *d_P = nullptr;                             // fixed address: kernel parameters
+    DevP *h_P = nullptr;                             // pinned copy
+    int *h_cnt = nullptr;                            // pinned counters
     DevP P{};
+    size_t in_bytes = 0, out_off = 0, out_bytes = 0;
+    // offsets inside the output region
+    size_t o_T = 0, o_x = 0, o_pt = 0, o_ls = 0, o_plk = 0, o_pchi = 0, o_lchi = 0, o_pf = 0, o_lf = 0, o_ctrl = 0, o_trace = 0, o_cnt = 0;
+    size_t i_pts0 = 0, i_lns0 = 0;
     plba_options opt{};
     std::vector<WinInfo> wins;
-    int n_chunks_pt = 0, n_chunks_ls = 0, ls_dim = 4, max_nf = 0;
-    bool uploaded = false;
-    // initial state kept on the device for plba_reset_state()
-    double *init_poseT = nullptr, *init_X = nullptr, *init_pts = nullptr, *init_lns = nullptr, *orth0 = nullptr;
-    int *pt_win = nullptr, *ls_win = nullptr;
+    std::vector<int> pt_perm, ls_perm, po_perm, lo_perm;    // internal index -> caller's (global, window-offset) index
+    int ls_dim = 4, max_nf = 0;
+    bool uploaded = false, small_path = true;
     double *sysbuf = nullptr; size_t sys_doubles = 0, S_doubles = 0;
     double *invbuf = nullptr;
-    int *h_counters = nullptr;              // pinned
-    WinCtrl *h_ctrl0 = nullptr;             // pinned, initial controller state
-    std::vector<WinCtrl> ctrl_init;
+    int h_counters[CNT_N] = {0};
     plba_allreduce_fn allreduce = nullptr; void *allreduce_user = nullptr;
     plba_timing timing{};
     cudaEvent_t ev[8]{};
-    bool detail_timing = false;
-    template <typename T> int dalloc(T **p, size_t n) {
-        void *q = nullptr;
-        if (cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) { err = "cudaMalloc failed"; return PLBA_E_CUDA; }
-        allocs.push_back(q); *p = (T *)q; return PLBA_OK;
+    bool detail_timing = false, no_graph = false;
+    int grid_chunks = 296, grid_solve = 148;
+#ifndef PLBA_HOST_EMU
+    cudaGraph_t graph[3] = {nullptr, nullptr, nullptr};
+    cudaGraphExec_t gexec[3] = {nullptr, nullptr, nullptr};
+    cudaGraphConditionalHandle cond_while[3]{}, cond_prep[3]{};
+#endif
+    void release() {
+        if (d_arena) cudaFree(d_arena);
+        if (h_in) cudaFreeHost(h_in);
+        if (h_out) cudaFreeHost(h_out);
+        d_arena = nullptr; h_in = nullptr; h_out = nullptr; d_cap = h_in_cap = h_out_cap = 0; uploaded = false;
     }
-    void free_all() { for (void *q : allocs) cudaFree(q); allocs.clear(); uploaded = false; }
 };
+
+static int ensure(plba_handle h, size_t dev_bytes, size_t in_bytes, size_t out_bytes) {
+    if (dev_bytes > h->d_cap) {
+        cudaStreamSynchronize(h->stream);
+        if (h->d_arena) cudaFree(h->d_arena);
+        h->d_arena = nullptr; h->d_cap = 0;
+        const size_t want = dev_bytes + dev_bytes / 4 + (1 << 20);
+        void *q = nullptr;
+        if (cudaMalloc(&q, want) != cudaSuccess) { h->err = "cudaMalloc of the device arena failed"; return PLBA_E_CUDA; }
+        h->d_arena = (char *)q; h->d_cap = want;
+    }
+    if (in_bytes > h->h_in_cap) {
+        cudaStreamSynchronize(h->stream);
+        if (h->h_in) cudaFreeHost(h->h_in);
+        h->h_in = nullptr; h->h_in_cap = 0;
+        const size_t want = in_bytes + in_bytes / 4 + (1 << 16);
+        void *q = nullptr;
+        if (cudaMallocHost(&q, want) != cudaSuccess) { h->err = "cudaMallocHost (input staging) failed"; return PLBA_E_CUDA; }
+        h->h_in = (char *)q; h->h_in_cap = want;
+    }
+    if (out_bytes > h->h_out_cap) {
+        cudaStreamSynchronize(h->stream);
+        if (h->h_out) cudaFreeHost(h->h_out);
+        h->h_out = nullptr; h->h_out_cap = 0;
+        const size_t want = out_bytes + out_bytes / 4 + (1 << 16);
+        void *q = nullptr;
+        if (cudaMallocHost(&q, want) != cudaSuccess) { h->err = "cudaMallocHost (output staging) failed"; return PLBA_E_CUDA; }
+        h->h_out = (char *)q; h->h_out_cap = want;
+    }
+    return PLBA_OK;
+}
 
 static int validate_problem(const plba_problem &p, const plba_options &o, std::string &err) {
     if (p.n_kf < 0 || p.n_free < 0 || p.n_pt < 0 || p.n_ls < 0 || p.n_pobs < 0 || p.n_lobs < 0) { err = "negative size"; return PLBA_E_ARG; }
@@ -70,26 +131,29 @@ static int validate_problem(const plba_problem &p, const plba_options &o, std::s
     return PLBA_OK;
 }
 
-static void build_chunks(const std::vector<int> &ptr, int lm0, int lm1, int win, std::vector<Chunk> &out, bool &too_long) {
-    int l = lm0;
-    while (l < lm1) {
-        Chunk c{}; c.lm0 = l; c.ob0 = ptr[l]; c.win = win;
-        int e = l;
-        while (e < lm1 && (e - l) < LC && (ptr[e + 1] - c.ob0) <= OC) e++;
-        if (e == l) { too_long = true; e = l + 1; }
-        c.lm1 = e; c.ob1 = ptr[e];
-        out.push_back(c);
-        l = e;
+// One landmark class of one window: signature sort.  Index work only.
+struct ClassLayout {
+    std::vector<int> perm;       // new local landmark -> old local landmark
+    std::vector<int> optr;       // CSR of the caller's order (local)
+};
+static void signature_order(int n_lm, int n_obs, const int32_t *lm, const int32_t *kf, bool permute, ClassLayout &L) {
+    L.optr.assign(n_lm + 1, 0);
+    for (int i = 0; i < n_obs; i++) L.optr[lm[i] + 1]++;
+    for (int l = 0; l < n_lm; l++) L.optr[l + 1] += L.optr[l];
+    L.perm.resize(n_lm);
+    for (int l = 0; l < n_lm; l++) L.perm[l] = l;
+    if (!permute || n_lm < 2) return;
+    std::vector<std::pair<uint64_t, int>> key(n_lm);
+    for (int l = 0; l < n_lm; l++) {
+        const int a = L.optr[l], b = L.optr[l + 1];
+        uint64_t hsh = 1469598103934665603ULL ^ (uint64_t)(b - a);
+        for (int i = a; i < b; i++) { hsh ^= (uint64_t)(uint32_t)kf[i] + 0x9e3779b97f4a7c15ULL + (hsh << 6) + (hsh >> 2); hsh *= 1099511628211ULL; }
+        const uint64_t first = (b > a) ? (uint64_t)(uint32_t)kf[a] : 0xffffffULL;
+        key[l] = std::make_pair((first << 40) | (hsh >> 24), l);
     }
+    std::sort(key.begin(), key.end());
+    for (int l = 0; l < n_lm; l++) L.perm[l] = key[l].second;
 }
-
-template <typename T> static int h2d(plba_handle h, T *dst, const std::vector<T> &src) {
-    if (src.empty()) return PLBA_OK;
-    CK(cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-    h->timing.h2d_bytes += (int64_t)(src.size() * sizeof(T));
-    return PLBA_OK;
-}
-#define UP(dptr, vec) do { int rc_ = h->dalloc(&dptr, (vec).size()); if (rc_) return rc_; rc_ = h2d(h, dptr, vec); if (rc_) return rc_; } while (0)
 
 extern "C" {
 
@@ -119,7 +183,22 @@ int plba_create(int32_t device, void *stream, plba_handle *out) {
     if (cudaSetDevice(device) != cudaSuccess) { delete h; *out = nullptr; return PLBA_E_CUDA; }
     if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
     else { if (cudaStreamCreate(&h->stream) != cudaSuccess) { delete h; *out = nullptr; return PLBA_E_CUDA; } h->own_stream = true; }
-    cudaMallocHost((void **)&h->h_counters, sizeof(int) * CNT_N);
+#ifndef PLBA_HOST_EMU
+    int nsm = 0;
+    if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && nsm > 0) h->n_sm = nsm;
+    const char *ng = std::getenv("PLBA_NO_GRAPH");
+    h->no_graph = ng && ng[0] == '1';
+#else
+    h->no_graph = true;
+#endif
+    h->grid_chunks = 2 * h->n_sm; h->grid_solve = h->n_sm;
+    void *q = nullptr;
+    if (cudaMalloc(&q, sizeof(DevP)) != cudaSuccess) { delete h; *out = nullptr; return PLBA_E_CUDA; }
+    h->d_P = (DevP *)q;
+    if (cudaMallocHost(&q, sizeof(DevP)) != cudaSuccess) { cudaFree(h->d_P); delete h; *out = nullptr; return PLBA_E_CUDA; }
+    h->h_P = (DevP *)q;
+    if (cudaMallocHost(&q, sizeof(int) * CNT_N) != cudaSuccess) { cudaFree(h->d_P); cudaFreeHost(h->h_P); delete h; *out = nullptr; return PLBA_E_CUDA; }
+    h->h_cnt = (int *)q;
     for (int i = 0; i < 8; i++) cudaEventCreate(&h->ev[i]);
     *out = h;
     return PLBA_OK;
@@ -128,8 +207,14 @@ int plba_create(int32_t device, void *stream, plba_handle *out) {
 void plba_destroy(plba_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    h->free_all();
-    if (h->h_counters) cudaFreeHost(h->h_counters);
+    cudaStreamSynchronize(h->stream);
+#ifndef PLBA_HOST_EMU
+    for (int i = 0; i < 3; i++) { if (h->gexec[i]) cudaGraphExecDestroy(h->gexec[i]); if (h->graph[i]) cudaGraphDestroy(h->graph[i]); }
+#endif
+    h->release();
+    if (h->d_P) cudaFree(h->d_P);
+    if (h->h_P) cudaFreeHost(h->h_P);
+    if (h->h_cnt) cudaFreeHost(h->h_cnt);
     for (int i = 0; i < 8; i++) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -139,11 +224,170 @@ const char *plba_last_error(plba_handle h) { return h ? h->err.c_str() : "null h
 
 int plba_set_allreduce(plba_handle h, plba_allreduce_fn fn, void *user) { if (!h) return PLBA_E_ARG; h->allreduce = fn; h->allreduce_user = user; return PLBA_OK; }
 
+}  // extern "C"
+
+// ---- launch helpers ------------------------------------------------------------------------------------------
+static inline dim3 grid1(int n, int b) { return dim3((unsigned)std::max(1, (n + b - 1) / b)); }
+template <int PROF> static void set_smem_attr() {
+#ifndef PLBA_HOST_EMU
+    static bool done = false;
+    if (!done) {
+        cudaFuncSetAttribute(k_assemble<PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemMax<PROF>::bytes());
+        cudaFuncSetAttribute(k_update<PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemMax<PROF>::bytes());
+        cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_small_smem());
+        done = true;
+    }
+#endif
+}
+static void set_all_attrs() { set_smem_attr<PLBA_PROFILE_G>(); set_smem_attr<PLBA_PROFILE_H_END>(); set_smem_attr<PLBA_PROFILE_H_PLK>(); }
+// persistent grid = SMs x resident CTAs per SM of the heavier of the two chunk kernels
+template <int PROF> static int chunk_occupancy() {
+#ifndef PLBA_HOST_EMU
+    int a = 1, b = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_assemble<PROF>, OC, SmemMax<PROF>::bytes());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_update<PROF>, OC, SmemMax<PROF>::bytes());
+    return std::max(1, std::min(a, b));
+#else
+    return 2;
+#endif
+}
+static int chunk_occupancy_for(int prof) {
+    return prof == PLBA_PROFILE_G ? chunk_occupancy<PLBA_PROFILE_G>() : prof == PLBA_PROFILE_H_END ? chunk_occupancy<PLBA_PROFILE_H_END>() : chunk_occupancy<PLBA_PROFILE_H_PLK>();
+}
+static size_t chunk_smem(int prof) {
+    return prof == PLBA_PROFILE_G ? SmemMax<PLBA_PROFILE_G>::bytes() : prof == PLBA_PROFILE_H_END ? SmemMax<PLBA_PROFILE_H_END>::bytes() : SmemMax<PLBA_PROFILE_H_PLK>::bytes();
+}
+static void launch_assemble(plba_handle h, int mode) {
+    const DevP *Pp = h->d_P; const dim3 g(h->grid_chunks), b(OC); const size_t sm = chunk_smem(h->opt.profile);
+    switch (h->opt.profile) {
+    case PLBA_PROFILE_G: PLBA_LAUNCH((k_assemble<PLBA_PROFILE_G>), g, b, sm, h->stream, Pp, mode); break;
+    case PLBA_PROFILE_H_END: PLBA_LAUNCH((k_assemble<PLBA_PROFILE_H_END>), g, b, sm, h->stream, Pp, mode); break;
+    default: PLBA_LAUNCH((k_assemble<PLBA_PROFILE_H_PLK>), g, b, sm, h->stream, Pp, mode); break;
+    }
+    h->timing.n_launches++; if (mode == 1) h->timing.n_assemble++;
+}
+static void launch_update(plba_handle h, int flags) {
+    const DevP *Pp = h->d_P; const dim3 g(h->grid_chunks), b(OC); const size_t sm = chunk_smem(h->opt.profile);
+    switch (h->opt.profile) {
+    case PLBA_PROFILE_G: PLBA_LAUNCH((k_update<PLBA_PROFILE_G>), g, b, sm, h->stream, Pp, flags); break;
+    case PLBA_PROFILE_H_END: PLBA_LAUNCH((k_update<PLBA_PROFILE_H_END>), g, b, sm, h->stream, Pp, flags); break;
+    default: PLBA_LAUNCH((k_update<PLBA_PROFILE_H_PLK>), g, b, sm, h->stream, Pp, flags); break;
+    }
+    h->timing.n_launches++;
+}
+static void launch_solve(plba_handle h) {
+    const DevP &P = h->P; const DevP *Pp = h->d_P;
+    if (P.n_free == 0) return;
+    if (h->small_path) {
+        PLBA_LAUNCH(k_solve_small, dim3(h->grid_solve), dim3(256), solve_small_smem(), h->stream, Pp);
+        h->timing.n_launches++;
+        return;
+    }
+    if (P.profile != PLBA_PROFILE_G) { PLBA_LAUNCH(k_control_h_pre, grid1(P.n_win, 128), dim3(128), 0, h->stream, Pp); h->timing.n_launches++; }
+    for (int w = 0; w < P.n_win; w++) {
+        const int n = 6 * h->wins[w].n_free;
+        if (n == 0 || h->wins[w].n_pobs + h->wins[w].n_lobs == 0) continue;
+        const int nt = (n + TB - 1) / TB;
+        for (int k = 0; k < nt; k++) {
+            PLBA_LAUNCH(k_potrf_tile, dim3(1), dim3(256), sizeof(double) * (2 * TB * (TB + 1) + TB), h->stream, Pp, w, k, h->invbuf);
+            h->timing.n_launches++;
+            const int m = nt - k - 1;
+            if (m > 0) {
+                PLBA_LAUNCH(k_trsm_tiles, dim3(m), dim3(256), sizeof(double) * 2 * TB * TB, h->stream, Pp, w, k, (const double *)h->invbuf);
+                PLBA_LAUNCH(k_syrk_tiles, dim3(m * (m + 1) / 2), dim3(256), sizeof(double) * 2 * TB * TB, h->stream, Pp, w, k, nt);
+                h->timing.n_launches += 2;
+            }
+        }
+        const int ntd = 1008;   // multiple of TB: G = 21 partial sums per row
+        PLBA_LAUNCH(k_trisolve_large, dim3(1), dim3(ntd), sizeof(double) * (TB + TB * (ntd / TB)), h->stream, Pp, w, nt, (const double *)h->invbuf);
+        h->timing.n_launches++;
+    }
+    PLBA_LAUNCH(k_pose_update, grid1(P.n_free, 128), dim3(128), 0, h->stream, Pp); h->timing.n_launches++;
+}
+static void allreduce(plba_handle h, double *p, size_t n, int op_max) {
+    if (!h->allreduce || !n) return;
+    // op is encoded in the sign of the count for the max reduction (only the lambda-init scalar uses it)
+    h->allreduce(p, op_max ? -(int64_t)n : (int64_t)n, (void *)h->stream, h->allreduce_user);
+}
+static int poll_counters(plba_handle h) {
+    CK(cudaMemcpyAsync(h->h_cnt, h->P.counters, sizeof(int) * CNT_N, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < CNT_N; i++) h->h_counters[i] = h->h_cnt[i];
+    return PLBA_OK;
+}
+PLBA_KERNEL void k_set_lambda(const DevP *Pp, double lambda) {
+    PLBA_PARAMS(P, Pp);
+    PHASE_BEGIN
+        for (int w = PLBA_BID * PLBA_NT + tid; w < P.n_win; w += PLBA_NB * PLBA_NT) { P.ctrl[w].lambda = lambda; P.ctrl[w].need_init = 0; }
+    PHASE_END
+}
+
+#ifndef PLBA_HOST_EMU
+// ---- the LM loop as a CUDA graph --------------------------------------------------------------------------------
+static cudaError_t add_kernel(cudaGraph_t g, cudaGraphNode_t *node, cudaGraphNode_t dep, void *fn, dim3 grid, dim3 block, size_t smem, void **args) {
+    cudaKernelNodeParams kp{};
+    kp.func = fn; kp.gridDim = grid; kp.blockDim = block; kp.sharedMemBytes = (unsigned)smem; kp.kernelParams = args; kp.extra = nullptr;
+    return cudaGraphAddKernelNode(node, g, dep ? &dep : nullptr, dep ? 1 : 0, &kp);
+}
+template <int PROF> static int build_graph(plba_handle h) {
+    const int pi = PROF;
+    if (h->gexec[pi]) return PLBA_OK;
+    set_all_attrs();
+    cudaGraph_t g = nullptr;
+    CK(cudaGraphCreate(&g, 0));
+    CK(cudaGraphConditionalHandleCreate(&h->cond_while[pi], g, 1, cudaGraphCondAssignDefault));
+    CK(cudaGraphConditionalHandleCreate(&h->cond_prep[pi], g, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams wp{}; wp.type = cudaGraphNodeTypeConditional;
+    wp.conditional.handle = h->cond_while[pi]; wp.conditional.type = cudaGraphCondTypeWhile; wp.conditional.size = 1;
+    cudaGraphNode_t wnode;
+    CK(cudaGraphAddNode(&wnode, g, nullptr, 0, &wp));
+    cudaGraph_t body = wp.conditional.phGraph_out[0];
+    cudaGraphNodeParams ip{}; ip.type = cudaGraphNodeTypeConditional;
+    ip.conditional.handle = h->cond_prep[pi]; ip.conditional.type = cudaGraphCondTypeIf; ip.conditional.size = 1;
+    cudaGraphNode_t inode;
+    CK(cudaGraphAddNode(&inode, body, nullptr, 0, &ip));
+    cudaGraph_t prep = ip.conditional.phGraph_out[0];
+    const DevP *Pp = h->d_P;
+    const dim3 gc(h->n_sm * chunk_occupancy<PROF>()), bc(OC); const size_t smc = SmemMax<PROF>::bytes();
+    int mode0 = 0, mode1 = 1, fl = KF_FUSE_CONTROL | KF_IN_GRAPH;
+    void *a_p[1] = {(void *)&Pp}, *a_m0[2] = {(void *)&Pp, (void *)&mode0}, *a_m1[2] = {(void *)&Pp, (void *)&mode1}, *a_fl[2] = {(void *)&Pp, (void *)&fl};
+    cudaGraphNode_t n1, n2, n3, m1, m2, m3;
+    CK(add_kernel(prep, &n1, nullptr, (void *)k_gate, dim3(h->grid_chunks), dim3(256), 0, a_p));
+    CK(add_kernel(prep, &n2, n1, (void *)k_assemble<PROF>, gc, bc, smc, a_m0));
+    CK(add_kernel(prep, &n3, n2, (void *)k_lambda_init, dim3(h->n_sm), dim3(128), 0, a_p));
+    CK(add_kernel(body, &m1, inode, (void *)k_assemble<PROF>, gc, bc, smc, a_m1));
+    CK(add_kernel(body, &m2, m1, (void *)k_solve_small, dim3(h->grid_solve), dim3(256), solve_small_smem(), a_p));
+    CK(add_kernel(body, &m3, m2, (void *)k_update<PROF>, gc, bc, smc, a_fl));
+    CK(cudaGraphInstantiate(&h->gexec[pi], g, 0));
+    h->graph[pi] = g;
+    return PLBA_OK;
+}
+static int build_graph_for(plba_handle h, int prof) {
+    return prof == PLBA_PROFILE_G ? build_graph<PLBA_PROFILE_G>(h) : prof == PLBA_PROFILE_H_END ? build_graph<PLBA_PROFILE_H_END>(h) : build_graph<PLBA_PROFILE_H_PLK>(h);
+}
+#endif
+
+static bool use_graph(plba_handle h) {
+#ifdef PLBA_HOST_EMU
+    (void)h; return false;
+#else
+    return h->small_path && !h->no_graph && !h->allreduce && !h->detail_timing;
+#endif
+}
+
+static int launch_reset(plba_handle h) {
+    PLBA_LAUNCH(k_reset, dim3(h->grid_chunks), dim3(256), 0, h->stream, (const DevP *)h->d_P, h->ls_dim, h->sys_doubles, h->sysbuf);
+    h->timing.n_launches++;
+    return PLBA_OK;
+}
+
+extern "C" {
+
 int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_options *opt) {
     if (!h || n <= 0 || !probs || !opt) return PLBA_E_ARG;
     if (opt->profile < PLBA_PROFILE_G || opt->profile > PLBA_PROFILE_H_PLK) { h->err = "unknown profile"; return PLBA_E_ARG; }
     CK(cudaSetDevice(h->device));
-    h->free_all();
+    h->uploaded = false;
     h->opt = *opt;
     h->timing = plba_timing{};
     const int prof = opt->profile;
@@ -151,6 +395,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     const int ld = h->ls_dim;
     h->wins.assign(n, WinInfo{});
     WinInfo tot{};
+    int max_nf = 0;
     for (int w = 0; w < n; w++) {
         const plba_problem &p = probs[w];
         int rc = validate_problem(p, *opt, h->err);
@@ -160,21 +405,125 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
         wi.kf0 = tot.n_kf; wi.slot0 = tot.n_free; wi.pt0 = tot.n_pt; wi.ls0 = tot.n_ls; wi.po0 = tot.n_pobs; wi.lo0 = tot.n_lobs;
         if ((int64_t)tot.n_pobs + p.n_pobs > 0x7fffffff || (int64_t)tot.n_lobs + p.n_lobs > 0x7fffffff) { h->err = "batch too large"; return PLBA_E_ARG; }
         tot.n_kf += p.n_kf; tot.n_free += p.n_free; tot.n_pt += p.n_pt; tot.n_ls += p.n_ls; tot.n_pobs += p.n_pobs; tot.n_lobs += p.n_lobs;
+        max_nf = std::max(max_nf, p.n_free);
+        for (int i = 0; i < 4; i++) if (p.cam[i] != probs[0].cam[i]) { h->err = "all windows of a batch must share the camera"; return PLBA_E_UNSUPPORTED; }
     }
-    // ---- flatten on the host (index arithmetic only) ----
-    std::vector<int> kf_slot(tot.n_kf), kf_win(tot.n_kf), slot_kf(tot.n_free), win_slot0(n), win_nfree(n), win_ls0(n), pt_win(tot.n_pt), ls_win(tot.n_ls);
-    std::vector<long long> win_S_off(n);
-    std::vector<double> Tmap((size_t)tot.n_kf * 12), X0((size_t)tot.n_free * 6), pts((size_t)tot.n_pt * 3), lns((size_t)tot.n_ls * ld), lns_map((size_t)tot.n_ls * 6);
-    std::vector<int> po_kf(tot.n_pobs), po_lm(tot.n_pobs), lo_kf(tot.n_lobs), lo_lm(tot.n_lobs), pt_ptr(tot.n_pt + 1, 0), ls_ptr(tot.n_ls + 1, 0);
-    std::vector<double> po_uv((size_t)tot.n_pobs * 2), lo_ab((size_t)tot.n_lobs * 4), po_om(tot.n_pobs), lo_om(tot.n_lobs);
-    std::vector<Chunk> ch_pt, ch_ls;
-    h->ctrl_init.assign(n, WinCtrl{});
-    long long S_off = 0; int max_nf = 0; bool too_long = false;
+    h->max_nf = max_nf;
+    h->small_path = (6 * max_nf <= SMALL_NMAX);
+    set_all_attrs();
+    h->grid_chunks = h->n_sm * chunk_occupancy_for(prof);
+
+    // ---- index work: signature order, chunks, segments --------------------------------------------------------
+    std::vector<Chunk> ch_pt, ch_ls; std::vector<Seg> sg_pt, sg_ls; std::vector<int> fp_pt, fp_ls;
+    h->pt_perm.resize(tot.n_pt); h->ls_perm.resize(tot.n_ls); h->po_perm.resize(tot.n_pobs); h->lo_perm.resize(tot.n_lobs);
+    std::vector<int> pt_ptr(tot.n_pt + 1, 0), ls_ptr(tot.n_ls + 1, 0);
+    bool too_long = false;
     for (int w = 0; w < n; w++) {
         const plba_problem &p = probs[w]; const WinInfo &wi = h->wins[w];
-        win_slot0[w] = wi.slot0; win_nfree[w] = wi.n_free; win_ls0[w] = wi.ls0; win_S_off[w] = S_off;
-        S_off += (long long)36 * wi.n_free * wi.n_free;
-        max_nf = std::max(max_nf, wi.n_free);
+        ClassLayout Lp, Ll;
+        signature_order(p.n_pt, p.n_pobs, p.po_lm, p.po_kf, true, Lp);
+        signature_order(p.n_ls, p.n_lobs, p.lo_lm, p.lo_kf, prof != PLBA_PROFILE_H_END, Ll);   // Q3 addresses endpoint lines by position
+        for (int cls = 0; cls < 2; cls++) {
+            const ClassLayout &L = cls ? Ll : Lp;
+            const int nl = cls ? p.n_ls : p.n_pt, lm0 = cls ? wi.ls0 : wi.pt0, ob0 = cls ? wi.lo0 : wi.po0;
+            const int32_t *kf = cls ? p.lo_kf : p.po_kf;
+            std::vector<int> &perm = cls ? h->ls_perm : h->pt_perm, &operm = cls ? h->lo_perm : h->po_perm, &ptr = cls ? ls_ptr : pt_ptr;
+            std::vector<Chunk> &chs = cls ? ch_ls : ch_pt; std::vector<Seg> &sgs = cls ? sg_ls : sg_pt; std::vector<int> &fps = cls ? fp_ls : fp_pt;
+            int chunk_tasks = 0, chunk_dtasks = 0;
+            int ob = ob0;
+            Chunk c{}; bool open = false; int seg_first_old = -1;
+            auto close_chunk = [&](int lm_end, int ob_end) { if (open) { c.lm1 = lm_end; c.ob1 = ob_end; c.seg1 = (int)sgs.size(); chs.push_back(c); open = false; seg_first_old = -1; } };
+            for (int nl_i = 0; nl_i < nl; nl_i++) {
+                const int old = L.perm[nl_i], a = L.optr[old], b = L.optr[old + 1], no = b - a;
+                if (no > OC) { too_long = true; break; }
+                const int g = lm0 + nl_i;
+                perm[g] = lm0 + old;
+                if (open && ((g - c.lm0) >= LC || (ob - c.ob0) + no > OC)) close_chunk(g, ob);
+                if (!open) { c = Chunk{}; c.lm0 = g; c.ob0 = ob; c.win = w; c.seg0 = (int)sgs.size(); open = true; seg_first_old = -1; chunk_tasks = 0; chunk_dtasks = 0; }
+                bool join = false;
+                if (seg_first_old >= 0) {
+                    Seg &s = sgs.back();
+                    const int fa = L.optr[seg_first_old];
+                    if (s.n_lm < SEG_MAX && s.nobs == no) { join = true; for (int i = 0; i < no; i++) if (kf[fa + i] != kf[a + i]) { join = false; break; } }
+                    if (join) s.n_lm++;
+                }
+                if (!join) {
+                    Seg s{}; s.lm0 = g; s.n_lm = 1; s.nobs = no; s.fp0 = (int)fps.size(); s.task0 = chunk_tasks; s.dtask0 = chunk_dtasks;
+                    for (int i = 0; i < no; i++) if (p.kf_slot[kf[a + i]] >= 0) { fps.push_back(i); s.nfree++; }
+                    chunk_tasks += s.nfree * (s.nfree - 1) / 2; chunk_dtasks += s.nfree;
+                    sgs.push_back(s); seg_first_old = old;
+                }
+                ptr[g] = ob;
+                for (int i = a; i < b; i++) operm[ob++] = ob0 + i;
+            }
+            if (too_long) break;
+            close_chunk(lm0 + nl, ob);
+            ptr[lm0 + nl] = ob;
+        }
+        if (too_long) break;
+    }
+    if (too_long) { h->err = "a landmark has more than 256 observations"; return PLBA_E_UNSUPPORTED; }
+
+    // ---- memory plan ----------------------------------------------------------------------------------------
+    Carver ci;   // staged inputs (same offsets in pinned host memory and at the start of the device arena)
+    const size_t i_kf_slot = ci.take<int>(tot.n_kf), i_kf_win = ci.take<int>(tot.n_kf), i_slot_kf = ci.take<int>(tot.n_free);
+    const size_t i_win_slot0 = ci.take<int>(n), i_win_nfree = ci.take<int>(n), i_win_ls0 = ci.take<int>(n), i_win_S = ci.take<long long>(n);
+    const size_t i_Tmap = ci.take<double>((size_t)12 * tot.n_kf), i_X0 = ci.take<double>((size_t)6 * tot.n_free);
+    const size_t i_pts0 = ci.take<double>((size_t)3 * tot.n_pt), i_lns0 = ci.take<double>((size_t)ld * tot.n_ls), i_lmap = ci.take<double>((size_t)6 * tot.n_ls);
+    const size_t i_pt_ptr = ci.take<int>(tot.n_pt + 1), i_ls_ptr = ci.take<int>(tot.n_ls + 1), i_pt_win = ci.take<int>(tot.n_pt), i_ls_win = ci.take<int>(tot.n_ls);
+    const size_t i_po_kf = ci.take<int>(tot.n_pobs), i_po_lm = ci.take<int>(tot.n_pobs), i_lo_kf = ci.take<int>(tot.n_lobs), i_lo_lm = ci.take<int>(tot.n_lobs);
+    const size_t i_po_uv = ci.take<double>((size_t)2 * tot.n_pobs), i_lo_ab = ci.take<double>((size_t)4 * tot.n_lobs);
+    const size_t i_po_om = ci.take<double>(tot.n_pobs), i_lo_om = ci.take<double>(tot.n_lobs);
+    const size_t i_ch_pt = ci.take<Chunk>(ch_pt.size()), i_ch_ls = ci.take<Chunk>(ch_ls.size()), i_sg_pt = ci.take<Seg>(sg_pt.size()), i_sg_ls = ci.take<Seg>(sg_ls.size());
+    const size_t i_fp_pt = ci.take<int>(fp_pt.size()), i_fp_ls = ci.take<int>(fp_ls.size());
+    const size_t i_ctrl0 = ci.take<WinCtrl>(n);
+    h->in_bytes = ci.off; h->i_pts0 = i_pts0; h->i_lns0 = i_lns0;
+    long long S_off = 0;
+    std::vector<long long> win_S_off(n);
+    for (int w = 0; w < n; w++) { win_S_off[w] = S_off; S_off += (long long)36 * h->wins[w].n_free * h->wins[w].n_free; }
+    h->S_doubles = (size_t)S_off;
+    h->sys_doubles = h->S_doubles + (size_t)18 * tot.n_free + (size_t)ACC_N * n + (size_t)n;
+    Carver cs = ci;   // device-only state follows the inputs
+    size_t s_poseT[2], s_X[2], s_pts[2], s_lns[2];
+    for (int b = 0; b < 2; b++) { s_poseT[b] = cs.take<double>((size_t)12 * tot.n_kf); s_X[b] = cs.take<double>((size_t)6 * tot.n_free); s_pts[b] = cs.take<double>((size_t)3 * tot.n_pt); s_lns[b] = cs.take<double>((size_t)ld * tot.n_ls); }
+    const size_t s_po_lvl = cs.take<unsigned char>(tot.n_pobs), s_lo_lvl = cs.take<unsigned char>(tot.n_lobs);
+    const size_t s_sys = cs.take<double>(h->sys_doubles), s_xp = cs.take<double>((size_t)6 * tot.n_free);
+    size_t s_inv = 0;
+    if (!h->small_path) { const int nt = (6 * max_nf + TB - 1) / TB; s_inv = cs.take<double>((size_t)nt * TB * TB); }
+    const int trace_cap = (prof == PLBA_PROFILE_G) ? (opt->iters_stage1 + opt->iters_stage2) * opt->lm_max_trials + 2 : opt->max_iters_lba + 2;
+    // output region (one D2H copy)
+    h->out_off = cs.off;
+    Carver co; co.off = cs.off;
+    h->o_T = co.take<double>((size_t)12 * tot.n_kf); h->o_x = co.take<double>((size_t)6 * tot.n_free); h->o_pt = co.take<double>((size_t)3 * tot.n_pt);
+    h->o_ls = co.take<double>((size_t)ld * tot.n_ls); h->o_plk = co.take<double>((size_t)6 * tot.n_ls);
+    h->o_pchi = co.take<double>(tot.n_pobs); h->o_lchi = co.take<double>(tot.n_lobs);
+    h->o_pf = co.take<unsigned char>(tot.n_pobs); h->o_lf = co.take<unsigned char>(tot.n_lobs);
+    h->o_ctrl = co.take<WinCtrl>(n); h->o_trace = co.take<plba_trace_rec>((size_t)n * trace_cap); h->o_cnt = co.take<int>(CNT_N);
+    h->out_bytes = co.off - h->out_off;
+    int rc = ensure(h, co.off, h->in_bytes, h->out_bytes);
+    if (rc) return rc;
+
+    // ---- flatten into the pinned staging buffer ------------------------------------------------------------------
+    char *hb = h->h_in;
+    int *kf_slot = (int *)(hb + i_kf_slot), *kf_win = (int *)(hb + i_kf_win), *slot_kf = (int *)(hb + i_slot_kf);
+    int *win_slot0 = (int *)(hb + i_win_slot0), *win_nfree = (int *)(hb + i_win_nfree), *win_ls0 = (int *)(hb + i_win_ls0);
+    long long *winS = (long long *)(hb + i_win_S);
+    double *Tmap = (double *)(hb + i_Tmap), *X0 = (double *)(hb + i_X0), *pts0 = (double *)(hb + i_pts0), *lns0 = (double *)(hb + i_lns0), *lmap = (double *)(hb + i_lmap);
+    int *d_pt_ptr = (int *)(hb + i_pt_ptr), *d_ls_ptr = (int *)(hb + i_ls_ptr), *pt_win = (int *)(hb + i_pt_win), *ls_win = (int *)(hb + i_ls_win);
+    int *po_kf = (int *)(hb + i_po_kf), *po_lm = (int *)(hb + i_po_lm), *lo_kf = (int *)(hb + i_lo_kf), *lo_lm = (int *)(hb + i_lo_lm);
+    double *po_uv = (double *)(hb + i_po_uv), *lo_ab = (double *)(hb + i_lo_ab), *po_om = (double *)(hb + i_po_om), *lo_om = (double *)(hb + i_lo_om);
+    WinCtrl *ctrl0 = (WinCtrl *)(hb + i_ctrl0);
+    std::memcpy(d_pt_ptr, pt_ptr.data(), sizeof(int) * pt_ptr.size());
+    std::memcpy(d_ls_ptr, ls_ptr.data(), sizeof(int) * ls_ptr.size());
+    if (!ch_pt.empty()) std::memcpy(hb + i_ch_pt, ch_pt.data(), sizeof(Chunk) * ch_pt.size());
+    if (!ch_ls.empty()) std::memcpy(hb + i_ch_ls, ch_ls.data(), sizeof(Chunk) * ch_ls.size());
+    if (!sg_pt.empty()) std::memcpy(hb + i_sg_pt, sg_pt.data(), sizeof(Seg) * sg_pt.size());
+    if (!sg_ls.empty()) std::memcpy(hb + i_sg_ls, sg_ls.data(), sizeof(Seg) * sg_ls.size());
+    if (!fp_pt.empty()) std::memcpy(hb + i_fp_pt, fp_pt.data(), sizeof(int) * fp_pt.size());
+    if (!fp_ls.empty()) std::memcpy(hb + i_fp_ls, fp_ls.data(), sizeof(int) * fp_ls.size());
+    for (int w = 0; w < n; w++) {
+        const plba_problem &p = probs[w]; const WinInfo &wi = h->wins[w];
+        win_slot0[w] = wi.slot0; win_nfree[w] = wi.n_free; win_ls0[w] = wi.ls0; winS[w] = win_S_off[w];
         for (int k = 0; k < p.n_kf; k++) {
             const int s = p.kf_slot[k];
             kf_slot[wi.kf0 + k] = s < 0 ? -1 : wi.slot0 + s; kf_win[wi.kf0 + k] = w;
@@ -185,253 +534,133 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
                 else log_se3(p.kf_T_wc + 12 * (size_t)k, &X0[(size_t)(wi.slot0 + s) * 6]);
             }
         }
-        for (int l = 0; l < p.n_pt; l++) { pt_win[wi.pt0 + l] = w; for (int i = 0; i < 3; i++) pts[(size_t)(wi.pt0 + l) * 3 + i] = p.pt_xyz[(size_t)3 * l + i]; }
-        for (int l = 0; l < p.n_ls; l++) {
-            ls_win[wi.ls0 + l] = w;
-            if (prof == PLBA_PROFILE_H_END) for (int i = 0; i < 6; i++) lns[(size_t)(wi.ls0 + l) * 6 + i] = p.ls_end[(size_t)6 * l + i];
+        for (int g = wi.pt0; g < wi.pt0 + p.n_pt; g++) {
+            const int old = h->pt_perm[g] - wi.pt0;
+            pt_win[g] = w;
+            for (int i = 0; i < 3; i++) pts0[(size_t)3 * g + i] = p.pt_xyz[(size_t)3 * old + i];
+        }
+        for (int g = wi.ls0; g < wi.ls0 + p.n_ls; g++) {
+            const int old = h->ls_perm[g] - wi.ls0;
+            ls_win[g] = w;
+            if (prof == PLBA_PROFILE_H_END) for (int i = 0; i < 6; i++) lns0[(size_t)6 * g + i] = p.ls_end[(size_t)6 * old + i];
             else {
-                plk_to_orth(p.ls_plk + (size_t)6 * l, &lns[(size_t)(wi.ls0 + l) * 4]);                // changePlukerToOrth (:6040, :1577)
-                for (int i = 0; i < 6; i++) lns_map[(size_t)(wi.ls0 + l) * 6 + i] = p.ls_plk[(size_t)6 * l + i];
+                plk_to_orth(p.ls_plk + (size_t)6 * old, &lns0[(size_t)4 * g]);                // changePlukerToOrth (:6040, :1577)
+                for (int i = 0; i < 6; i++) lmap[(size_t)6 * g + i] = p.ls_plk[(size_t)6 * old + i];
             }
         }
-        for (int i = 0; i < p.n_pobs; i++) {
-            const int o = wi.po0 + i;
-            po_kf[o] = wi.kf0 + p.po_kf[i]; po_lm[o] = wi.pt0 + p.po_lm[i]; pt_ptr[po_lm[o] + 1]++;
+        for (int g = wi.pt0; g < wi.pt0 + p.n_pt; g++) for (int o = pt_ptr[g]; o < pt_ptr[g + 1]; o++) {
+            const int i = h->po_perm[o] - wi.po0;
+            po_kf[o] = wi.kf0 + p.po_kf[i]; po_lm[o] = g;
             po_uv[(size_t)2 * o] = p.po_uv[(size_t)2 * i]; po_uv[(size_t)2 * o + 1] = p.po_uv[(size_t)2 * i + 1];
             po_om[o] = (double)(float)(1.0 / (p.po_sig2 ? p.po_sig2[i] : 1.0));                      // const float& invSigma2 (:6009, Q13)
         }
-        for (int i = 0; i < p.n_lobs; i++) {
-            const int o = wi.lo0 + i;
-            lo_kf[o] = wi.kf0 + p.lo_kf[i]; lo_lm[o] = wi.ls0 + p.lo_lm[i]; ls_ptr[lo_lm[o] + 1]++;
+        for (int g = wi.ls0; g < wi.ls0 + p.n_ls; g++) for (int o = ls_ptr[g]; o < ls_ptr[g + 1]; o++) {
+            const int i = h->lo_perm[o] - wi.lo0;
+            lo_kf[o] = wi.kf0 + p.lo_kf[i]; lo_lm[o] = g;
             for (int k = 0; k < 4; k++) lo_ab[(size_t)4 * o + k] = p.lo_ab[(size_t)4 * i + k];
             lo_om[o] = (double)(float)(1.0 / (p.lo_sig2 ? p.lo_sig2[i] : 1.0));
         }
-        WinCtrl &c = h->ctrl_init[w];
+        WinCtrl c{};
         c.need_init = 1; c.apply = 1; c.ni = 2.0; c.err_prev = 999999999.9; c.n_lm_pt = p.n_pt; c.n_lm_ls = p.n_ls;
         if (p.n_pobs + p.n_lobs == 0) c.done = 1;      // nothing to do (src/mapHandler.cpp:1496-1500)
+        ctrl0[w] = c;
     }
-    for (int l = 0; l < tot.n_pt; l++) pt_ptr[l + 1] += pt_ptr[l];
-    for (int l = 0; l < tot.n_ls; l++) ls_ptr[l + 1] += ls_ptr[l];
-    for (int w = 0; w < n; w++) {
-        const WinInfo &wi = h->wins[w];
-        build_chunks(pt_ptr, wi.pt0, wi.pt0 + wi.n_pt, w, ch_pt, too_long);
-        build_chunks(ls_ptr, wi.ls0, wi.ls0 + wi.n_ls, w, ch_ls, too_long);
-    }
-    if (too_long) { h->err = "a landmark has more than 256 observations"; return PLBA_E_UNSUPPORTED; }
-    h->n_chunks_pt = (int)ch_pt.size(); h->n_chunks_ls = (int)ch_ls.size(); h->max_nf = max_nf;
 
+    // ---- kernel parameters ------------------------------------------------------------------------------------
     DevP &P = h->P;
     P = DevP{};
+    char *db = h->d_arena;
     P.cam = Cam{probs[0].cam[0], probs[0].cam[1], probs[0].cam[2], probs[0].cam[3]};
-    for (int w = 1; w < n; w++) for (int i = 0; i < 4; i++) if (probs[w].cam[i] != probs[0].cam[i]) { h->err = "all windows of a batch must share the camera"; return PLBA_E_UNSUPPORTED; }
     P.profile = prof; P.fixed_quirks = (opt->quirks == PLBA_QUIRKS_FIXED);
     P.n_win = n; P.n_kf = tot.n_kf; P.n_free = tot.n_free; P.n_pt = tot.n_pt; P.n_ls = tot.n_ls; P.n_pobs = tot.n_pobs; P.n_lobs = tot.n_lobs;
+    P.n_chunks_pt = (int)ch_pt.size(); P.n_chunks_ls = (int)ch_ls.size();
     P.iters_stage1 = opt->iters_stage1; P.iters_stage2 = opt->iters_stage2; P.lm_max_trials = opt->lm_max_trials; P.max_iters_lba = opt->max_iters_lba;
+    P.max_rounds = (prof == PLBA_PROFILE_G) ? (opt->iters_stage1 + opt->iters_stage2) * opt->lm_max_trials + 2 : opt->max_iters_lba + 1;
     P.huber_delta = opt->huber_delta; P.chi2_gate = opt->chi2_gate; P.homog_th = opt->homog_th; P.min_error = opt->min_error;
     P.min_error_change = opt->min_error_change; P.lm_tau = opt->lm_tau; P.lambda_lba_lm = opt->lambda_lba_lm; P.lambda_lba_k = opt->lambda_lba_k;
-    int *d_i; double *d_d; long long *d_ll; Chunk *d_c;
-    UP(d_i, kf_slot); P.kf_slot = d_i; UP(d_i, kf_win); P.kf_win = d_i; UP(d_i, slot_kf); P.slot_kf = d_i;
-    UP(d_i, win_slot0); P.win_slot0 = d_i; UP(d_i, win_nfree); P.win_nfree = d_i; UP(d_i, win_ls0); P.win_ls0 = d_i;
-    UP(d_ll, win_S_off); P.win_S_off = d_ll;
-    UP(d_d, Tmap); P.kf_Tmap = d_d; h->init_poseT = d_d;
-    UP(d_d, X0); h->init_X = d_d; UP(d_d, pts); h->init_pts = d_d; UP(d_d, lns); h->init_lns = d_d; h->orth0 = d_d;
-    UP(d_d, lns_map); P.lns_map = d_d;
-    UP(d_i, pt_ptr); P.pt_ptr = d_i; UP(d_i, ls_ptr); P.ls_ptr = d_i;
-    UP(d_i, po_kf); P.po_kf = d_i; UP(d_i, po_lm); P.po_lm = d_i; UP(d_i, lo_kf); P.lo_kf = d_i; UP(d_i, lo_lm); P.lo_lm = d_i;
-    UP(d_d, po_uv); P.po_uv = d_d; UP(d_d, lo_ab); P.lo_ab = d_d; UP(d_d, po_om); P.po_om = d_d; UP(d_d, lo_om); P.lo_om = d_d;
-    UP(d_c, ch_pt); P.chunks_pt = d_c; UP(d_c, ch_ls); P.chunks_ls = d_c;
-    UP(h->pt_win, pt_win); UP(h->ls_win, ls_win);
-    int rc;
-    for (int b = 0; b < 2; b++) {
-        if ((rc = h->dalloc(&P.poseT[b], (size_t)tot.n_kf * 12))) return rc;
-        if ((rc = h->dalloc(&P.Xkf[b], (size_t)tot.n_free * 6))) return rc;
-        if ((rc = h->dalloc(&P.pts[b], (size_t)tot.n_pt * 3))) return rc;
-        if ((rc = h->dalloc(&P.lns[b], (size_t)tot.n_ls * ld))) return rc;
-    }
-    if ((rc = h->dalloc(&P.po_lvl, (size_t)tot.n_pobs))) return rc;
-    if ((rc = h->dalloc(&P.lo_lvl, (size_t)tot.n_lobs))) return rc;
-    if ((rc = h->dalloc(&P.po_chi2, (size_t)tot.n_pobs))) return rc;
-    if ((rc = h->dalloc(&P.lo_chi2, (size_t)tot.n_lobs))) return rc;
-    // reduced-system buffer: [S | g | hpp_diag | hpp_diag_init | acc | accmax]  (one memset, one all-reduce range)
-    h->S_doubles = (size_t)S_off;
-    h->sys_doubles = h->S_doubles + (size_t)18 * tot.n_free + (size_t)ACC_N * n + (size_t)n;
-    if ((rc = h->dalloc(&h->sysbuf, h->sys_doubles))) return rc;
+    P.kf_slot = (int *)(db + i_kf_slot); P.kf_win = (int *)(db + i_kf_win); P.slot_kf = (int *)(db + i_slot_kf);
+    P.win_slot0 = (int *)(db + i_win_slot0); P.win_nfree = (int *)(db + i_win_nfree); P.win_ls0 = (int *)(db + i_win_ls0); P.win_S_off = (long long *)(db + i_win_S);
+    P.kf_Tmap = (double *)(db + i_Tmap); P.X0 = (double *)(db + i_X0); P.pts0 = (double *)(db + i_pts0); P.lns0 = (double *)(db + i_lns0); P.lns_map = (double *)(db + i_lmap);
+    P.pt_ptr = (int *)(db + i_pt_ptr); P.ls_ptr = (int *)(db + i_ls_ptr); P.pt_win = (int *)(db + i_pt_win); P.ls_win = (int *)(db + i_ls_win);
+    P.po_kf = (int *)(db + i_po_kf); P.po_lm = (int *)(db + i_po_lm); P.lo_kf = (int *)(db + i_lo_kf); P.lo_lm = (int *)(db + i_lo_lm);
+    P.po_uv = (double *)(db + i_po_uv); P.lo_ab = (double *)(db + i_lo_ab); P.po_om = (double *)(db + i_po_om); P.lo_om = (double *)(db + i_lo_om);
+    P.chunks_pt = (Chunk *)(db + i_ch_pt); P.chunks_ls = (Chunk *)(db + i_ch_ls); P.segs_pt = (Seg *)(db + i_sg_pt); P.segs_ls = (Seg *)(db + i_sg_ls);
+    P.freepos_pt = (int *)(db + i_fp_pt); P.freepos_ls = (int *)(db + i_fp_ls);
+    P.ctrl0 = (WinCtrl *)(db + i_ctrl0);
+    for (int b = 0; b < 2; b++) { P.poseT[b] = (double *)(db + s_poseT[b]); P.Xkf[b] = (double *)(db + s_X[b]); P.pts[b] = (double *)(db + s_pts[b]); P.lns[b] = (double *)(db + s_lns[b]); }
+    P.po_lvl = (unsigned char *)(db + s_po_lvl); P.lo_lvl = (unsigned char *)(db + s_lo_lvl);
+    P.po_chi2 = (double *)(db + h->o_pchi); P.lo_chi2 = (double *)(db + h->o_lchi);
+    h->sysbuf = (double *)(db + s_sys);
     P.S = h->sysbuf; P.gs = P.S + h->S_doubles; P.hpp_diag = P.gs + (size_t)6 * tot.n_free; P.hpp_diag_init = P.hpp_diag + (size_t)6 * tot.n_free;
     P.acc = P.hpp_diag_init + (size_t)6 * tot.n_free; P.accB = P.acc + (size_t)4 * n; P.accmax = P.acc + (size_t)ACC_N * n;
-    if ((rc = h->dalloc(&P.xp, (size_t)6 * tot.n_free))) return rc;
-    if ((rc = h->dalloc(&P.ctrl, (size_t)n))) return rc;
-    P.trace_cap = (prof == PLBA_PROFILE_G) ? (opt->iters_stage1 + opt->iters_stage2) * opt->lm_max_trials + 2 : opt->max_iters_lba + 2;
-    if ((rc = h->dalloc(&P.trace, (size_t)n * P.trace_cap))) return rc;
-    if ((rc = h->dalloc(&P.counters, (size_t)CNT_N))) return rc;
-    if (6 * max_nf > SMALL_NMAX) { const int nt = (6 * max_nf + TB - 1) / TB; if ((rc = h->dalloc(&h->invbuf, (size_t)nt * TB * TB))) return rc; }
+    P.xp = (double *)(db + s_xp);
+    h->invbuf = h->small_path ? nullptr : (double *)(db + s_inv);
+    P.ctrl = (WinCtrl *)(db + h->o_ctrl); P.trace = (plba_trace_rec *)(db + h->o_trace); P.trace_cap = trace_cap; P.counters = (int *)(db + h->o_cnt);
+    set_all_attrs();
+#ifndef PLBA_HOST_EMU
+    if (h->small_path && !h->no_graph) {
+        if ((rc = build_graph_for(h, prof))) return rc;
+        P.cond_while = (unsigned long long)h->cond_while[prof]; P.cond_prep = (unsigned long long)h->cond_prep[prof];
+    }
+#endif
+    *h->h_P = P;
+    CK(cudaMemcpyAsync(h->d_P, h->h_P, sizeof(DevP), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_arena, h->h_in, h->in_bytes, cudaMemcpyHostToDevice, h->stream));
+    h->timing.h2d_bytes += (int64_t)(h->in_bytes + sizeof(DevP));
     h->uploaded = true;
-    return plba_reset_state(h);
+    return launch_reset(h);
 }
 
 int plba_reset_state(plba_handle h) {
     if (!h || !h->uploaded) return PLBA_E_ARG;
-    DevP &P = h->P; cudaStream_t st = h->stream;
-    for (int b = 0; b < 2; b++) {
-        CK(cudaMemcpyAsync(P.poseT[b], h->init_poseT, sizeof(double) * 12 * (size_t)P.n_kf, cudaMemcpyDeviceToDevice, st));
-        CK(cudaMemcpyAsync(P.Xkf[b], h->init_X, sizeof(double) * 6 * (size_t)P.n_free, cudaMemcpyDeviceToDevice, st));
-        CK(cudaMemcpyAsync(P.pts[b], h->init_pts, sizeof(double) * 3 * (size_t)P.n_pt, cudaMemcpyDeviceToDevice, st));
-        CK(cudaMemcpyAsync(P.lns[b], h->init_lns, sizeof(double) * h->ls_dim * (size_t)P.n_ls, cudaMemcpyDeviceToDevice, st));
-    }
-    CK(cudaMemsetAsync(P.po_lvl, 0, (size_t)P.n_pobs, st));
-    CK(cudaMemsetAsync(P.lo_lvl, 0, (size_t)P.n_lobs, st));
-    CK(cudaMemsetAsync(P.po_chi2, 0, sizeof(double) * (size_t)P.n_pobs, st));
-    CK(cudaMemsetAsync(P.lo_chi2, 0, sizeof(double) * (size_t)P.n_lobs, st));
-    CK(cudaMemsetAsync(P.trace, 0, sizeof(plba_trace_rec) * (size_t)P.n_win * P.trace_cap, st));
-    CK(cudaMemcpyAsync(P.ctrl, h->ctrl_init.data(), sizeof(WinCtrl) * (size_t)P.n_win, cudaMemcpyHostToDevice, st));
-    int ndone = 0; for (const WinCtrl &c : h->ctrl_init) ndone += c.done;
-    h->h_counters[CNT_DONE] = ndone; h->h_counters[CNT_NEED_INIT] = P.n_win - ndone; h->h_counters[CNT_GATE] = 0; h->h_counters[CNT_TRIALS] = 0;
-    CK(cudaMemcpyAsync(P.counters, h->h_counters, sizeof(int) * CNT_N, cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));
+    CK(cudaSetDevice(h->device));
+    launch_reset(h);
+    CK(cudaGetLastError());
     return PLBA_OK;
 }
 
 }  // extern "C"
 
-// ---- launch helpers ------------------------------------------------------------------------------------------
-template <int PROF, int LT> static void set_smem_attr() {
-#ifndef PLBA_HOST_EMU
-    static bool done = false;
-    if (!done) {
-        cudaFuncSetAttribute(k_assemble<PROF, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<PROF, LT>::bytes());
-        cudaFuncSetAttribute(k_update<PROF, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<PROF, LT>::bytes());
-        done = true;
-    }
-#endif
-}
-template <int PROF, int LT> static void launch_assemble(plba_handle h, int nchunks, int mode) {
-    if (!nchunks) return;
-    set_smem_attr<PROF, LT>();
-    const size_t smem = Smem<PROF, LT>::bytes();
-    PLBA_LAUNCH((k_assemble<PROF, LT>), dim3(nchunks), dim3(OC), smem, h->stream, h->P, mode);
-    h->timing.n_launches++; if (mode == 1) h->timing.n_assemble++;
-}
-template <int PROF, int LT> static void launch_update(plba_handle h, int nchunks) {
-    if (!nchunks) return;
-    set_smem_attr<PROF, LT>();
-    const size_t smem = Smem<PROF, LT>::bytes();
-    PLBA_LAUNCH((k_update<PROF, LT>), dim3(nchunks), dim3(OC), smem, h->stream, h->P);
-    h->timing.n_launches++;
-}
-static void do_assemble(plba_handle h, int mode) {
-    switch (h->opt.profile) {
-    case PLBA_PROFILE_G: launch_assemble<PLBA_PROFILE_G, LT_POINT>(h, h->n_chunks_pt, mode); launch_assemble<PLBA_PROFILE_G, LT_LINE_ORTH>(h, h->n_chunks_ls, mode); break;
-    case PLBA_PROFILE_H_END: launch_assemble<PLBA_PROFILE_H_END, LT_POINT>(h, h->n_chunks_pt, mode); launch_assemble<PLBA_PROFILE_H_END, LT_LINE_END>(h, h->n_chunks_ls, mode); break;
-    default: launch_assemble<PLBA_PROFILE_H_PLK, LT_POINT>(h, h->n_chunks_pt, mode); launch_assemble<PLBA_PROFILE_H_PLK, LT_LINE_ORTH>(h, h->n_chunks_ls, mode); break;
-    }
-}
-static void do_update(plba_handle h) {
-    switch (h->opt.profile) {
-    case PLBA_PROFILE_G: launch_update<PLBA_PROFILE_G, LT_POINT>(h, h->n_chunks_pt); launch_update<PLBA_PROFILE_G, LT_LINE_ORTH>(h, h->n_chunks_ls); break;
-    case PLBA_PROFILE_H_END: launch_update<PLBA_PROFILE_H_END, LT_POINT>(h, h->n_chunks_pt); launch_update<PLBA_PROFILE_H_END, LT_LINE_END>(h, h->n_chunks_ls); break;
-    default: launch_update<PLBA_PROFILE_H_PLK, LT_POINT>(h, h->n_chunks_pt); launch_update<PLBA_PROFILE_H_PLK, LT_LINE_ORTH>(h, h->n_chunks_ls); break;
-    }
-}
-static void do_solve(plba_handle h) {
-    DevP &P = h->P;
-    if (P.n_free == 0) return;
-    if (6 * h->max_nf <= SMALL_NMAX) {
-        const int n = 6 * h->max_nf, ldm = n + 1;
-        const size_t sm = solve_small_smem(n, ldm);
-#ifndef PLBA_HOST_EMU
-        static size_t attr_set = 0;
-        if (sm > attr_set) { cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); attr_set = sm; }
-#endif
-        PLBA_LAUNCH(k_solve_small, dim3(P.n_win), dim3(256), sm, h->stream, P, ldm);
-        h->timing.n_launches++;
-        return;
-    }
-    for (int w = 0; w < P.n_win; w++) {
-        const int n = 6 * h->wins[w].n_free;
-        if (n == 0 || h->ctrl_init[w].done) continue;
-        const int nt = (n + TB - 1) / TB;
-        for (int k = 0; k < nt; k++) {
-            PLBA_LAUNCH(k_potrf_tile, dim3(1), dim3(256), sizeof(double) * (2 * TB * (TB + 1) + TB), h->stream, P, w, k, h->invbuf);
-            h->timing.n_launches++;
-            const int m = nt - k - 1;
-            if (m > 0) {
-                PLBA_LAUNCH(k_trsm_tiles, dim3(m), dim3(256), sizeof(double) * 2 * TB * TB, h->stream, P, w, k, (const double *)h->invbuf);
-                PLBA_LAUNCH(k_syrk_tiles, dim3(m * (m + 1) / 2), dim3(256), sizeof(double) * 2 * TB * TB, h->stream, P, w, k, nt);
-                h->timing.n_launches += 2;
-            }
-        }
-        const int ntd = 1008;   // multiple of TB: G = 21 partial sums per row
-        PLBA_LAUNCH(k_trisolve_large, dim3(1), dim3(ntd), sizeof(double) * (TB + TB * (ntd / TB)), h->stream, P, w, nt, (const double *)h->invbuf);
-        h->timing.n_launches++;
-    }
-}
-static void allreduce(plba_handle h, double *p, size_t n, int op_max) {
-    if (!h->allreduce || !n) return;
-    // op is encoded in the sign of the count for the max reduction (only the lambda-init scalar uses it)
-    h->allreduce(p, op_max ? -(int64_t)n : (int64_t)n, (void *)h->stream, h->allreduce_user);
-}
-static int poll_counters(plba_handle h) {
-    CK(cudaMemcpyAsync(h->h_counters, h->P.counters, sizeof(int) * CNT_N, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    return PLBA_OK;
-}
-PLBA_KERNEL void k_set_lambda(DevP P, double lambda) {
-    PHASE_BEGIN
-        const int w = PLBA_BID * PLBA_NT + tid;
-        if (w < P.n_win) { P.ctrl[w].lambda = lambda; P.ctrl[w].need_init = 0; }
-    PHASE_END
-}
-static inline dim3 grid1(int n, int b) { return dim3((unsigned)std::max(1, (n + b - 1) / b)); }
-
-// one LM round for every window that is not finished: (gate) -> (lambda init) -> assemble -> solve -> update -> control
-static int run_round(plba_handle h, bool need_init, bool need_gate) {
-    DevP &P = h->P; cudaStream_t st = h->stream;
-    const bool G = (P.profile == PLBA_PROFILE_G);
-    if (need_gate) {
-        if (P.n_pobs) { PLBA_LAUNCH(k_gate<LT_POINT>, grid1(P.n_pobs, 256), dim3(256), 0, st, P, P.n_pobs); h->timing.n_launches++; }
-        if (P.n_lobs) { PLBA_LAUNCH(k_gate<LT_LINE_ORTH>, grid1(P.n_lobs, 256), dim3(256), 0, st, P, P.n_lobs); h->timing.n_launches++; }
-    }
-    CK(cudaMemsetAsync(h->sysbuf, 0, sizeof(double) * h->sys_doubles, st));
-    if (need_init || need_gate) {
-        if (need_init) {
-            do_assemble(h, 0);
-            allreduce(h, P.hpp_diag_init, (size_t)6 * P.n_free, 0);
-            allreduce(h, P.accmax, (size_t)P.n_win, 1);
-        }
-        PLBA_LAUNCH(k_lambda_init, grid1(P.n_win, 128), dim3(128), 0, st, P); h->timing.n_launches++;
+// one LM round, host driven: (gate + lambda init) -> assemble -> [exchange] -> solve -> update -> [exchange] -> control
+static int run_round(plba_handle h, bool need_prep) {
+    DevP &P = h->P; cudaStream_t st = h->stream; const DevP *Pp = h->d_P;
+    if (!h->small_path) CK(cudaMemsetAsync(h->sysbuf, 0, sizeof(double) * (h->S_doubles + (size_t)12 * P.n_free), st));
+    if (need_prep) {
+        PLBA_LAUNCH(k_gate, dim3(h->grid_chunks), dim3(256), 0, st, Pp); h->timing.n_launches++;
+        launch_assemble(h, 0);
+        allreduce(h, P.hpp_diag_init, (size_t)6 * P.n_free, 0);
+        allreduce(h, P.accmax, (size_t)P.n_win, 1);
+        PLBA_LAUNCH(k_lambda_init, dim3(h->n_sm), dim3(128), 0, st, Pp); h->timing.n_launches++;
     }
     if (h->detail_timing) cudaEventRecord(h->ev[0], st);
-    do_assemble(h, 1);
+    launch_assemble(h, 1);
     if (h->detail_timing) cudaEventRecord(h->ev[1], st);
     allreduce(h, h->sysbuf, h->S_doubles + (size_t)12 * P.n_free, 0);            // the exchange step: S, g, hpp_diag
     allreduce(h, P.acc, (size_t)4 * P.n_win, 0);                                 // assemble-phase cost sums
-    if (!G) { PLBA_LAUNCH(k_control_h_pre, grid1(P.n_win, 128), dim3(128), 0, st, P); h->timing.n_launches++; }
-    do_solve(h);
+    launch_solve(h);
     if (h->detail_timing) cudaEventRecord(h->ev[2], st);
-    if (P.n_free) { PLBA_LAUNCH(k_pose_update, grid1(P.n_free, 128), dim3(128), 0, st, P); h->timing.n_launches++; }
-    do_update(h);
+    launch_update(h, 0);
     if (h->detail_timing) cudaEventRecord(h->ev[3], st);
+    allreduce(h, P.accB, (size_t)4 * P.n_win, 0);                                // update-phase sums (new cost, scale, |dx|^2)
+    PLBA_LAUNCH(k_control, dim3(1), dim3(256), 0, st, Pp, 0); h->timing.n_launches++;
     return PLBA_OK;
 }
 
-extern "C" {
-
-int plba_run(plba_handle h) {
-    if (!h || !h->uploaded) return PLBA_E_ARG;
-    CK(cudaSetDevice(h->device));
+static int run_async(plba_handle h) {
     DevP &P = h->P; cudaStream_t st = h->stream;
-    const bool G = (P.profile == PLBA_PROFILE_G);
-    const int max_rounds = G ? (P.iters_stage1 + P.iters_stage2) * P.lm_max_trials + 2 : P.max_iters_lba + 1;
-    const int64_t launches0 = h->timing.n_launches, assemble0 = h->timing.n_assemble;
     h->timing.ms_assemble = h->timing.ms_solve = h->timing.ms_update = 0;
-    cudaEventRecord(h->ev[6], st);
+#ifndef PLBA_HOST_EMU
+    if (use_graph(h)) {
+        CK(cudaGraphLaunch(h->gexec[P.profile], st));
+        return PLBA_OK;
+    }
+#endif
     int rc;
-    // h_counters holds the state left by plba_reset_state()
-    for (int round = 0; round < max_rounds; round++) {
+    if ((rc = poll_counters(h))) return rc;
+    for (int round = 0; round < P.max_rounds; round++) {
         if (h->h_counters[CNT_DONE] >= P.n_win) break;
-        const bool need_init = h->h_counters[CNT_NEED_INIT] > 0, need_gate = h->h_counters[CNT_GATE] > 0;
-        if ((rc = run_round(h, need_init, need_gate))) return rc;
-        allreduce(h, P.accB, (size_t)4 * P.n_win, 0);                            // update-phase sums (new cost, scale, |dx|^2)
-        PLBA_LAUNCH(k_control, grid1(P.n_win, 128), dim3(128), 0, st, P); h->timing.n_launches++;
+        const bool need_prep = h->h_counters[CNT_NEED_INIT] > 0 || h->h_counters[CNT_GATE] > 0;
+        if ((rc = run_round(h, need_prep))) return rc;
         if ((rc = poll_counters(h))) return rc;
         if (h->detail_timing) {
             float a = 0, b = 0, c = 0;
@@ -439,15 +668,39 @@ int plba_run(plba_handle h) {
             h->timing.ms_assemble += a; h->timing.ms_solve += b; h->timing.ms_update += c;
         }
     }
-    if (G) {   // pending gate of windows that stopped right after stage 0, then the final per-edge test
-        if (h->h_counters[CNT_GATE] > 0) {
-            if (P.n_pobs) { PLBA_LAUNCH(k_gate<LT_POINT>, grid1(P.n_pobs, 256), dim3(256), 0, st, P, P.n_pobs); h->timing.n_launches++; }
-            if (P.n_lobs) { PLBA_LAUNCH(k_gate<LT_LINE_ORTH>, grid1(P.n_lobs, 256), dim3(256), 0, st, P, P.n_lobs); h->timing.n_launches++; }
-            PLBA_LAUNCH(k_lambda_init, grid1(P.n_win, 128), dim3(128), 0, st, P); h->timing.n_launches++;
-        }
-    }
+    return PLBA_OK;
+}
+
+// the chi2 gate of windows that left stage 0 in the very last round is still pending (src/mapHandler.cpp:6125-6147)
+static int finish_pending_gate(plba_handle h) {
+    if (h->P.profile != PLBA_PROFILE_G) return PLBA_OK;
+    PLBA_LAUNCH(k_gate, dim3(h->grid_chunks), dim3(256), 0, h->stream, (const DevP *)h->d_P); h->timing.n_launches++;
+    PLBA_LAUNCH(k_lambda_init, dim3(h->n_sm), dim3(128), 0, h->stream, (const DevP *)h->d_P); h->timing.n_launches++;
+    return PLBA_OK;
+}
+
+static void account_graph_launches(plba_handle h) {
+    // kernels executed inside the graph, reconstructed from the device-side round / prep counters
+    const int rounds = h->h_counters[CNT_ROUNDS], preps = h->h_counters[CNT_PREPS];
+    h->timing.n_launches += (int64_t)3 * rounds + (int64_t)3 * preps;
+    h->timing.n_assemble += rounds;
+}
+
+extern "C" {
+
+int plba_run(plba_handle h) {
+    if (!h || !h->uploaded) return PLBA_E_ARG;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int64_t launches0 = h->timing.n_launches, assemble0 = h->timing.n_assemble;
+    const bool graph = use_graph(h);
+    cudaEventRecord(h->ev[6], st);
+    int rc;
+    if ((rc = run_async(h))) return rc;
+    if ((rc = finish_pending_gate(h))) return rc;
     cudaEventRecord(h->ev[7], st);
-    CK(cudaStreamSynchronize(st));
+    if ((rc = poll_counters(h))) return rc;
+    if (graph) account_graph_launches(h);
     float ms = 0; cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]);
     h->timing.ms_total = ms;
     h->timing.ms_other = ms - h->timing.ms_assemble - h->timing.ms_solve - h->timing.ms_update;
@@ -464,77 +717,59 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
     DevP &P = h->P; cudaStream_t st = h->stream;
     const bool G = (P.profile == PLBA_PROFILE_G);
     const int ld = h->ls_dim;
-    // device-side write-back into staging buffers
-    double *d_T, *d_x, *d_pt, *d_ls, *d_plk; unsigned char *d_pf, *d_lf;
-    int rc;
-    if ((rc = h->dalloc(&d_T, (size_t)12 * P.n_kf))) return rc;
-    if ((rc = h->dalloc(&d_x, (size_t)6 * P.n_free))) return rc;
-    if ((rc = h->dalloc(&d_pt, (size_t)3 * P.n_pt))) return rc;
-    if ((rc = h->dalloc(&d_ls, (size_t)ld * P.n_ls))) return rc;
-    if ((rc = h->dalloc(&d_plk, (size_t)6 * P.n_ls))) return rc;
-    if ((rc = h->dalloc(&d_pf, (size_t)P.n_pobs))) return rc;
-    if ((rc = h->dalloc(&d_lf, (size_t)P.n_lobs))) return rc;
-    if (G) {
-        if (P.n_pobs) { PLBA_LAUNCH(k_final<LT_POINT>, grid1(P.n_pobs, 256), dim3(256), 0, st, P, P.n_pobs, d_pf); h->timing.n_launches++; }
-        if (P.n_lobs) { PLBA_LAUNCH(k_final<LT_LINE_ORTH>, grid1(P.n_lobs, 256), dim3(256), 0, st, P, P.n_lobs, d_lf); h->timing.n_launches++; }
-    }
-    if (P.n_kf) { PLBA_LAUNCH(k_export_poses, grid1(P.n_kf, 128), dim3(128), 0, st, P, d_T, d_x); h->timing.n_launches++; }
-    const int nl = std::max(P.n_pt, P.n_ls);
-    if (nl) {
-        const int q9 = (P.profile == PLBA_PROFILE_H_PLK && !P.fixed_quirks) ? 1 : 0;
-        PLBA_LAUNCH(k_export_landmarks, grid1(nl, 256), dim3(256), 0, st, P, (const int *)h->pt_win, (const int *)h->ls_win, d_pt, d_ls, d_plk, ld, (const double *)h->orth0, q9);
-        h->timing.n_launches++;
-    }
-    std::vector<double> T((size_t)12 * P.n_kf), X((size_t)6 * P.n_free), pt((size_t)3 * P.n_pt), ls((size_t)ld * P.n_ls), plk((size_t)6 * P.n_ls), pchi(P.n_pobs), lchi(P.n_lobs);
-    std::vector<double> pt0((size_t)3 * P.n_pt), ls0((size_t)ld * P.n_ls);
-    std::vector<unsigned char> pf(P.n_pobs), lf(P.n_lobs);
-    std::vector<WinCtrl> ctrl(P.n_win);
-    std::vector<plba_trace_rec> trace((size_t)P.n_win * P.trace_cap);
-    auto d2h = [&](void *dst, const void *src, size_t bytes) -> int { if (!bytes) return 0; h->timing.d2h_bytes += (int64_t)bytes; return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st) == cudaSuccess ? 0 : 1; };
-    int bad = 0;
-    bad |= d2h(T.data(), d_T, T.size() * 8); bad |= d2h(X.data(), d_x, X.size() * 8); bad |= d2h(pt.data(), d_pt, pt.size() * 8);
-    bad |= d2h(ls.data(), d_ls, ls.size() * 8); bad |= d2h(plk.data(), d_plk, plk.size() * 8);
-    bad |= d2h(pt0.data(), h->init_pts, pt0.size() * 8); bad |= d2h(ls0.data(), h->init_lns, ls0.size() * 8);
-    if (G) { bad |= d2h(pchi.data(), P.po_chi2, pchi.size() * 8); bad |= d2h(lchi.data(), P.lo_chi2, lchi.size() * 8); bad |= d2h(pf.data(), d_pf, pf.size()); bad |= d2h(lf.data(), d_lf, lf.size()); }
-    bad |= d2h(ctrl.data(), P.ctrl, ctrl.size() * sizeof(WinCtrl)); bad |= d2h(trace.data(), P.trace, trace.size() * sizeof(plba_trace_rec));
-    if (bad) { h->err = "device to host copy failed"; return PLBA_E_CUDA; }
+    char *db = h->d_arena;
+    ExportP E{};
+    E.T_wc = (double *)(db + h->o_T); E.x = (double *)(db + h->o_x); E.pt = (double *)(db + h->o_pt); E.ls = (double *)(db + h->o_ls); E.plk = (double *)(db + h->o_plk);
+    E.pf = (unsigned char *)(db + h->o_pf); E.lf = (unsigned char *)(db + h->o_lf);
+    E.ls_dim = ld; E.q9 = (P.profile == PLBA_PROFILE_H_PLK && !P.fixed_quirks) ? 1 : 0; E.do_final = G ? 1 : 0;
+    PLBA_LAUNCH(k_export, dim3(h->grid_chunks), dim3(256), 0, st, (const DevP *)h->d_P, E); h->timing.n_launches++;
+    CK(cudaMemcpyAsync(h->h_out, db + h->out_off, h->out_bytes, cudaMemcpyDeviceToHost, st));
+    h->timing.d2h_bytes += (int64_t)h->out_bytes;
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    // staging buffers were the last 7 allocations
-    for (int i = 0; i < 7; i++) { cudaFree(h->allocs.back()); h->allocs.pop_back(); }
+    const char *ob = h->h_out - h->out_off;      // so that ob + o_xxx addresses the host copy
+    const double *T = (const double *)(ob + h->o_T), *X = (const double *)(ob + h->o_x), *pt = (const double *)(ob + h->o_pt), *ls = (const double *)(ob + h->o_ls);
+    const double *plk = (const double *)(ob + h->o_plk), *pchi = (const double *)(ob + h->o_pchi), *lchi = (const double *)(ob + h->o_lchi);
+    const unsigned char *pf = (const unsigned char *)(ob + h->o_pf), *lf = (const unsigned char *)(ob + h->o_lf);
+    const WinCtrl *ctrl = (const WinCtrl *)(ob + h->o_ctrl); const plba_trace_rec *trace = (const plba_trace_rec *)(ob + h->o_trace);
+    const int *cnt = (const int *)(ob + h->o_cnt);
+    for (int i = 0; i < CNT_N; i++) h->h_counters[i] = cnt[i];
+    const double *pt0 = (const double *)(h->h_in + h->i_pts0), *ls0 = (const double *)(h->h_in + h->i_lns0);
     int rc_all = PLBA_OK;
     for (int w = 0; w < n; w++) {
         const WinInfo &wi = h->wins[w]; plba_result &r = res[w];
         r.n_trace = ctrl[w].n_trace; r.n_trials = ctrl[w].n_trials;
         r.status = (wi.n_pobs + wi.n_lobs == 0) ? PLBA_DISCARDED : PLBA_OK;
         if (r.trace) for (int i = 0; i < std::min(r.n_trace, std::min(r.trace_cap, P.trace_cap)); i++) r.trace[i] = trace[(size_t)w * P.trace_cap + i];
+        if (r.kf_T_wc) for (int i = 0; i < 12 * wi.n_kf; i++) r.kf_T_wc[i] = T[(size_t)12 * wi.kf0 + i];
         if (r.x_pose) for (int i = 0; i < 6 * wi.n_free; i++) r.x_pose[i] = X[(size_t)6 * wi.slot0 + i];
-        if (r.pt_xyz) for (int i = 0; i < 3 * wi.n_pt; i++) r.pt_xyz[i] = pt[(size_t)3 * wi.pt0 + i];
-        if (ld == 4) {
-            if (r.ls_orth) for (int i = 0; i < 4 * wi.n_ls; i++) r.ls_orth[i] = ls[(size_t)4 * wi.ls0 + i];
-            if (r.ls_plk) for (int i = 0; i < 6 * wi.n_ls; i++) r.ls_plk[i] = plk[(size_t)6 * wi.ls0 + i];
-        } else if (r.ls_end) for (int i = 0; i < 6 * wi.n_ls; i++) r.ls_end[i] = ls[(size_t)6 * wi.ls0 + i];
-        // inlier rule of the hand-LM write-back (src/mapHandler.cpp:2858-2860, 2871-2873); profile G leaves it to the final chi2 test
-        if (r.pt_inlier) for (int l = 0; l < wi.n_pt; l++) {
-            double d2 = 0; for (int i = 0; i < 3; i++) { const double d = pt[(size_t)3 * (wi.pt0 + l) + i] - pt0[(size_t)3 * (wi.pt0 + l) + i]; d2 += d * d; }
-            r.pt_inlier[l] = (!G && std::sqrt(d2) > 0.01) ? 0 : 1;
+        for (int g = wi.pt0; g < wi.pt0 + wi.n_pt; g++) {
+            const int old = h->pt_perm[g] - wi.pt0;
+            if (r.pt_xyz) for (int i = 0; i < 3; i++) r.pt_xyz[(size_t)3 * old + i] = pt[(size_t)3 * g + i];
+            // inlier rule of the hand-LM write-back (src/mapHandler.cpp:2858-2860, 2871-2873); profile G leaves it to the final chi2 test
+            if (r.pt_inlier) { double d2 = 0; for (int i = 0; i < 3; i++) { const double d = pt[(size_t)3 * g + i] - pt0[(size_t)3 * g + i]; d2 += d * d; } r.pt_inlier[old] = (!G && std::sqrt(d2) > 0.01) ? 0 : 1; }
         }
-        if (r.ls_inlier) for (int l = 0; l < wi.n_ls; l++) {
-            double d2 = 0; for (int i = 0; i < ld; i++) { const double d = ls[(size_t)ld * (wi.ls0 + l) + i] - ls0[(size_t)ld * (wi.ls0 + l) + i]; d2 += d * d; }
-            r.ls_inlier[l] = (!G && std::sqrt(d2) > 0.01) ? 0 : 1;
+        for (int g = wi.ls0; g < wi.ls0 + wi.n_ls; g++) {
+            const int old = h->ls_perm[g] - wi.ls0;
+            if (ld == 4) {
+                if (r.ls_orth) for (int i = 0; i < 4; i++) r.ls_orth[(size_t)4 * old + i] = ls[(size_t)4 * g + i];
+                if (r.ls_plk) for (int i = 0; i < 6; i++) r.ls_plk[(size_t)6 * old + i] = plk[(size_t)6 * g + i];
+            } else if (r.ls_end) for (int i = 0; i < 6; i++) r.ls_end[(size_t)6 * old + i] = ls[(size_t)6 * g + i];
+            if (r.ls_inlier) { double d2 = 0; for (int i = 0; i < ld; i++) { const double d = ls[(size_t)ld * g + i] - ls0[(size_t)ld * g + i]; d2 += d * d; } r.ls_inlier[old] = (!G && std::sqrt(d2) > 0.01) ? 0 : 1; }
         }
         if (G) {
-            if (r.po_chi2) for (int i = 0; i < wi.n_pobs; i++) r.po_chi2[i] = pchi[(size_t)wi.po0 + i];
-            if (r.lo_chi2) for (int i = 0; i < wi.n_lobs; i++) r.lo_chi2[i] = lchi[(size_t)wi.lo0 + i];
-            if (r.po_flags) for (int i = 0; i < wi.n_pobs; i++) r.po_flags[i] = pf[(size_t)wi.po0 + i];
-            if (r.lo_flags) for (int i = 0; i < wi.n_lobs; i++) r.lo_flags[i] = lf[(size_t)wi.lo0 + i];
+            for (int o = wi.po0; o < wi.po0 + wi.n_pobs; o++) {
+                const int i = h->po_perm[o] - wi.po0;
+                if (r.po_chi2) r.po_chi2[i] = pchi[o];
+                if (r.po_flags) r.po_flags[i] = pf[o];
+            }
+            for (int o = wi.lo0; o < wi.lo0 + wi.n_lobs; o++) {
+                const int i = h->lo_perm[o] - wi.lo0;
+                if (r.lo_chi2) r.lo_chi2[i] = lchi[o];
+                if (r.lo_flags) r.lo_flags[i] = lf[o];
+            }
         }
         if (r.status < PLBA_DISCARDED) rc_all = r.status;
-    }
-    for (int w = 0; w < n; w++) {
-        const WinInfo &wi = h->wins[w]; plba_result &r = res[w];
-        if (!r.kf_T_wc) continue;
-        for (int k = 0; k < wi.n_kf; k++) for (int i = 0; i < 12; i++) r.kf_T_wc[(size_t)12 * k + i] = T[(size_t)12 * (wi.kf0 + k) + i];
     }
     return rc_all;
 }
@@ -543,9 +778,20 @@ int plba_solve_batch(plba_handle h, int32_t n, const plba_problem *probs, const 
     if (!h || !res) return PLBA_E_ARG;
     int rc = plba_upload(h, n, probs, opt);
     if (rc) { for (int w = 0; w < n; w++) { res[w].status = rc; res[w].n_trace = 0; res[w].n_trials = 0; } return rc; }
-    if ((rc = plba_run(h))) return rc;
-    rc = plba_download(h, n, res);
-    // fixed KFs: the exported buffer only holds free KFs; copy the caller's rows through
+    const bool graph = use_graph(h);
+    const int64_t launches0 = h->timing.n_launches, assemble0 = h->timing.n_assemble;
+    cudaEventRecord(h->ev[6], h->stream);
+    if ((rc = run_async(h))) return rc;
+    if ((rc = finish_pending_gate(h))) return rc;
+    cudaEventRecord(h->ev[7], h->stream);
+    rc = plba_download(h, n, res);              // one synchronisation for the whole call
+    if (graph) account_graph_launches(h);
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]);
+    h->timing.ms_total = ms; h->timing.ms_other = ms - h->timing.ms_assemble - h->timing.ms_solve - h->timing.ms_update;
+    h->timing.n_launches_run = h->timing.n_launches - launches0;
+    h->timing.n_assemble_run = h->timing.n_assemble - assemble0;
+    h->timing.n_trials_run = h->h_counters[CNT_TRIALS];
+    // fixed KFs: copy the caller's rows through untouched
     for (int w = 0; w < n; w++) if (res[w].kf_T_wc) for (int k = 0; k < probs[w].n_kf; k++) if (probs[w].kf_slot[k] < 0) for (int i = 0; i < 12; i++) res[w].kf_T_wc[(size_t)12 * k + i] = probs[w].kf_T_wc[(size_t)12 * k + i];
     return rc;
 }
@@ -561,9 +807,9 @@ int plba_solve(plba_handle h, const plba_problem *prob, const plba_options *opt,
 int plba_trial_assemble(plba_handle h, double lambda) {
     if (!h || !h->uploaded) return PLBA_E_ARG;
     DevP &P = h->P; cudaStream_t st = h->stream;
-    PLBA_LAUNCH(k_set_lambda, grid1(P.n_win, 128), dim3(128), 0, st, P, lambda);
+    PLBA_LAUNCH(k_set_lambda, grid1(P.n_win, 128), dim3(128), 0, st, (const DevP *)h->d_P, lambda);
     CK(cudaMemsetAsync(h->sysbuf, 0, sizeof(double) * h->sys_doubles, st));
-    do_assemble(h, 1);
+    launch_assemble(h, 1);
     CK(cudaGetLastError());
     return PLBA_OK;
 }
@@ -571,10 +817,8 @@ int plba_trial_finish(plba_handle h, double lambda, double *chi_new, double *sca
     if (!h || !h->uploaded) return PLBA_E_ARG;
     DevP &P = h->P; cudaStream_t st = h->stream;
     (void)lambda;
-    if (P.profile != PLBA_PROFILE_G) { PLBA_LAUNCH(k_control_h_pre, grid1(P.n_win, 128), dim3(128), 0, st, P); }
-    do_solve(h);
-    if (P.n_free) PLBA_LAUNCH(k_pose_update, grid1(P.n_free, 128), dim3(128), 0, st, P);
-    do_update(h);
+    launch_solve(h);
+    launch_update(h, 0);
     double acc[4];
     CK(cudaMemcpyAsync(acc, P.accB, sizeof(acc), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -593,14 +837,38 @@ int plba_copy_reduced_system(plba_handle h, int32_t window, double *S_out, doubl
     if (!h || !h->uploaded || window < 0 || window >= h->P.n_win) return PLBA_E_ARG;
     const WinInfo &wi = h->wins[window];
     const size_t n = (size_t)6 * wi.n_free;
-    std::vector<long long> off(1);
-    CK(cudaMemcpyAsync(off.data(), h->P.win_S_off + window, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    if (S_out && n) CK(cudaMemcpyAsync(S_out, h->P.S + off[0], sizeof(double) * n * n, cudaMemcpyDeviceToHost, h->stream));
+    size_t off = 0;
+    for (int w = 0; w < window; w++) off += (size_t)36 * h->wins[w].n_free * h->wins[w].n_free;
+    if (S_out && n) CK(cudaMemcpyAsync(S_out, h->P.S + off, sizeof(double) * n * n, cudaMemcpyDeviceToHost, h->stream));
     if (g_out && n) CK(cudaMemcpyAsync(g_out, h->P.gs + (size_t)6 * wi.slot0, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return PLBA_OK;
 }
+// Average device time of one launch of a stage kernel on the resident problem: `reps` back-to-back launches bracketed by
+// CUDA events on the handle's stream.  which: 0 assemble (mode 1), 1 reduced-system solve, 2 update.  State is not advanced.
+int plba_time_kernel(plba_handle h, int32_t which, int32_t reps, double lambda, double *ms_avg) {
+    if (!h || !h->uploaded || reps <= 0 || !ms_avg) return PLBA_E_ARG;
+    cudaStream_t st = h->stream;
+    PLBA_LAUNCH(k_set_lambda, grid1(h->P.n_win, 128), dim3(128), 0, st, (const DevP *)h->d_P, lambda);
+    CK(cudaMemsetAsync(h->sysbuf, 0, sizeof(double) * h->sys_doubles, st));
+    for (int w = 0; w < 2; w++) { if (which == 0) launch_assemble(h, 1); else if (which == 1) launch_solve(h); else launch_update(h, 0); }
+    cudaEventRecord(h->ev[4], st);
+    for (int r = 0; r < reps; r++) { if (which == 0) launch_assemble(h, 1); else if (which == 1) launch_solve(h); else launch_update(h, 0); }
+    cudaEventRecord(h->ev[5], st);
+    CK(cudaStreamSynchronize(st));
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]);
+    *ms_avg = (double)ms / reps;
+    CK(cudaMemsetAsync(h->sysbuf, 0, sizeof(double) * h->sys_doubles, st));
+    CK(cudaGetLastError());
+    return PLBA_OK;
+}
+#ifdef PLBA_PROF
+int plba_debug_prof(unsigned long long *out64, int reset) {
+    if (out64) cudaMemcpyFromSymbol(out64, plba_prof_table, sizeof(unsigned long long) * 64);
+    if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(plba_prof_table, z, sizeof(z)); }
+    return 0;
+}
+#endif
 int plba_get_timing(plba_handle h, plba_timing *t) { if (!h || !t) return PLBA_E_ARG; *t = h->timing; return PLBA_OK; }
 int plba_set_detail_timing(plba_handle h, int on) { if (!h) return PLBA_E_ARG; h->detail_timing = on != 0; return PLBA_OK; }
 

@@ -365,7 +365,7 @@ PLBA_HD bool spd_inverse(double *M) {
     return true;
 }
 template <int D>
-PLBA_HD void gj_inverse(double *M) {   // pivoted Gauss-Jordan, any non-singular matrix
+PLBA_COLD void gj_inverse(double *M) {   // pivoted Gauss-Jordan, any non-singular matrix
     double a[D][2 * D];
     for (int r = 0; r < D; r++) for (int c = 0; c < D; c++) { a[r][c] = M[r * D + c]; a[r][D + c] = (r == c) ? 1.0 : 0.0; }
     for (int k = 0; k < D; k++) {

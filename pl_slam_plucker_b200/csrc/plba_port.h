@@ -12,12 +12,16 @@
 #include <cstring>
 #include <cmath>
 
+struct alignas(16) plba_d2 { double x, y; };   // 128-bit load unit of the SoA observation arrays
+
 #ifndef PLBA_HOST_EMU
 // ------------------------------------------------------------------ CUDA
 #include <cuda_runtime.h>
 #define PLBA_HD __host__ __device__ __forceinline__
 #define PLBA_D __device__ __forceinline__
 #define PLBA_KERNEL __global__
+#define PLBA_COLD __host__ __device__ __noinline__
+#define PLBA_BOUNDS(t, b) __launch_bounds__(t, b)
 #define PLBA_SMEM(ptr) extern __shared__ __align__(16) unsigned char plba_smem_raw[]; unsigned char *ptr = plba_smem_raw
 #define PHASE_BEGIN { const int tid = (int)threadIdx.x; (void)tid;
 #define PHASE_END } __syncthreads();
@@ -27,7 +31,9 @@
 #define PLBA_NB ((int)gridDim.x)
 #define PLBA_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #define plba_isfinite(x) isfinite(x)
-PLBA_D void plba_atomic_add(double *p, double v) { atomicAdd(p, v); }
+// accumulation into HBM/L2-resident sums: red.global.add.f64 (fire and forget).  Written as PTX so that the compiler can
+// not fall back to a generic-address atomic (QSPC + branch + CAS loop for the shared window) when it loses the address space.
+PLBA_D void plba_atomic_add(double *p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 PLBA_D void plba_atomic_add_i(int *p, int v) { atomicAdd(p, v); }
 // max over non-negative doubles (bit pattern order == value order)
 PLBA_D void plba_atomic_max_pos(double *p, double v) { atomicMax((unsigned long long *)p, (unsigned long long)__double_as_longlong(v)); }
@@ -35,8 +41,35 @@ PLBA_D void plba_atomic_max_pos(double *p, double v) { atomicMax((unsigned long 
 // Must be reached by every thread of the CTA (blockDim is a multiple of 32).
 PLBA_D void plba_block_add(double *smem_dst, double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(smem_dst, v);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(smem_dst, v);     // <= 8 adds per call: the shared-memory CAS loop is fine here
 }
+// optional per-phase cycle accounting (development builds only: -DPLBA_PROF): thread 0 of every CTA adds the cycles between
+// two marks to a global table that tools read back through plba_debug_prof()
+#ifdef PLBA_PROF
+__device__ unsigned long long plba_prof_table[64];
+#define PROF_DECL long long prof_t0_ = clock64()
+#define PROF_MARK(id) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&plba_prof_table[id], (unsigned long long)(t_ - prof_t0_)); prof_t0_ = t_; } } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(id)
+#endif
+// kernel parameters live in device memory (one fixed address per handle, so that the CUDA graph of the LM loop never
+// has to be rebuilt); every CTA stages them into shared memory once.
+#define PLBA_PARAMS(P, Pp)                                                                                   \
+    for (int i_ = (int)threadIdx.x; i_ < (int)(sizeof(DevP) / 4); i_ += (int)blockDim.x)                       \
+        ((int *)&plba_params_smem)[i_] = ((const int *)(Pp))[i_];                                            \
+    __syncthreads();                                                                                         \
+    const DevP &P = plba_params_smem
+// inside device functions: bind to the shared copy directly so that parameter reads stay shared-space loads
+#define PLBA_PARAMS_REF(P, Pin) const DevP &P = plba_params_smem; (void)Pin
+// reads of values that other CTAs of the SAME launch produced with atomics (L2 is the point of coherence)
+PLBA_D double plba_ld_l2(const double *p) { return __ldcg(p); }
+PLBA_D int plba_ld_l2(const int *p) { return __ldcg(p); }
+PLBA_D void plba_fence() { __threadfence(); }
+PLBA_D int plba_atomic_fetch_add_i(int *p, int v) { return atomicAdd(p, v); }
+PLBA_D double plba_rsqrt(double x) { return rsqrt(x); }
+// WHILE / IF nodes of the LM-loop graph are steered from the controller (cudaGraphSetConditional is a device runtime builtin)
+PLBA_D void plba_graph_set(unsigned long long handle, unsigned int v) { cudaGraphSetConditional((cudaGraphConditionalHandle)handle, v); }
 #else
 // ------------------------------------------------------------------ host emulation
 #include <cstdlib>
@@ -44,6 +77,8 @@ PLBA_D void plba_block_add(double *smem_dst, double v) {
 #define PLBA_HD inline
 #define PLBA_D inline
 #define PLBA_KERNEL static
+#define PLBA_COLD inline
+#define PLBA_BOUNDS(t, b)
 struct plba_dim3 { unsigned x, y, z; plba_dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 typedef plba_dim3 dim3;
 struct PlbaEmuCtx { int nt = 1, bid = 0, bidy = 0, nb = 1; unsigned char *smem = nullptr; };
@@ -70,6 +105,16 @@ inline void plba_atomic_add(double *p, double v) { *p += v; }
 inline void plba_atomic_add_i(int *p, int v) { *p += v; }
 inline void plba_atomic_max_pos(double *p, double v) { if (v > *p) *p = v; }
 inline void plba_block_add(double *d, double v) { *d += v; }
+#define PLBA_PARAMS(P, Pp) const DevP &P = *(Pp)
+#define PLBA_PARAMS_REF(P, Pin) const DevP &P = Pin
+#define PROF_DECL
+#define PROF_MARK(id)
+inline double plba_ld_l2(const double *p) { return *p; }
+inline int plba_ld_l2(const int *p) { return *p; }
+inline void plba_fence() {}
+inline int plba_atomic_fetch_add_i(int *p, int v) { int o = *p; *p += v; return o; }
+inline double plba_rsqrt(double x) { return 1.0 / std::sqrt(x); }
+inline void plba_graph_set(unsigned long long, unsigned int) {}
 // minimal CUDA runtime stand-ins
 typedef int cudaError_t; typedef void *cudaStream_t; typedef void *cudaEvent_t;
 enum { cudaSuccess = 0 };

@@ -1,8 +1,12 @@
 // Damped solve of the reduced camera system  (S + damping) x_p = g_red   (subsystem 4; replaces
 // Eigen::SimplicialLDLT of src/mapHandler.cpp:2566-2568 and g2o LinearSolverEigen, src/mapHandler.cpp:5925).
-// S is symmetric positive definite after damping: Cholesky S = U^T U in FP64 on the vector pipe (tcgen05 has no
+// S is symmetric positive definite after damping: Cholesky S = L L^T in FP64 on the vector pipe (tcgen05 has no
 // f64 kind; DMMA is considered only for the large-window GEMM update).
-//   k_solve_small : one CTA per window, whole system in shared memory (n = 6 Nkf <= 144: configs 1-3)
+//   k_solve_small : one CTA per window, whole system in shared memory (n = 6 Nkf <= 144: configs 1-3).  Right-looking
+//                   Cholesky in panels of one pose block (6 columns): the 6x6 diagonal block is factored redundantly
+//                   in the registers of every thread that owns a row below it, so a panel costs two block barriers
+//                   instead of twelve; the right-hand side rides along as row n (L y = g for free).  The kernel also
+//                   runs the hand-LM pre-solve controller, clears the accumulators it consumed and applies the pose step.
 //   k_potrf_tile / k_trsm_tiles / k_syrk_tiles / k_trisolve_large : tiled right-looking factorisation in HBM/L2
 //                   for large windows (configs 4-5), 48 x 48 tiles, many CTAs per step.
 #pragma once
@@ -12,69 +16,195 @@ namespace plba {
 
 enum { SMALL_NMAX = 144, TB = 48 };
 
-PLBA_KERNEL void k_solve_small(DevP P, int ldm) {
+static inline size_t solve_small_smem() { return sizeof(double) * ((size_t)(SMALL_NMAX + 1) * (SMALL_NMAX + 1) + 2 * SMALL_NMAX + 24 + 16) + 64; }
+
+PLBA_KERNEL void k_solve_small(const DevP *Pp) {
     PLBA_SMEM(raw);
-    const int w = PLBA_BID;
-    WinCtrl &ctl = P.ctrl[w];
-    if (ctl.done) return;
-    const int nf = P.win_nfree[w], n = 6 * nf, slot0 = P.win_slot0[w];
-    double *M = (double *)raw;                 // n x ldm, lower triangle used
-    double *dg = M + (size_t)n * ldm, *b = dg + n, *y = b + n, *x = y + n;
-    int *fail = (int *)(x + n);
-    const double *Sw = P.S + P.win_S_off[w];
-    PHASE_BEGIN
-        if (tid == 0) *fail = 0;
-        for (int idx = tid; idx < n * n; idx += PLBA_NT) {
-            const int r = idx / n, c = idx % n;
-            if (c > r) continue;
-            double v = Sw[(size_t)c * n + r];      // upper entry (c,r) mirrored into lower (r,c)
-            if (r == c) v += (P.profile == PLBA_PROFILE_G) ? ctl.lambda : ctl.lambda * P.hpp_diag[(size_t)6 * slot0 + r];
-            M[(size_t)r * ldm + c] = v;
-        }
-        for (int i = tid; i < n; i += PLBA_NT) b[i] = P.gs[(size_t)6 * slot0 + i];
-    PHASE_END
-    for (int k = 0; k < n; k++) {
+    PLBA_PARAMS(P, Pp);
+    PROF_DECL;
+    for (int w = PLBA_BID; w < P.n_win; w += PLBA_NB) {
+        WinCtrl &ctl = P.ctrl[w];
+        const int nf = P.win_nfree[w], n = 6 * nf, slot0 = P.win_slot0[w], ldm = n + 1;     // n even => ldm odd: conflict-free columns
+        double *M = (double *)raw;                 // (n+1) x ldm lower triangle; row n = right-hand side
+        double *dinv = M + (size_t)(n + 1) * ldm, *xs = dinv + n, *Ls = xs + n, *red = Ls + 24;
+        int *flag = (int *)(red + 4);              // [0] skip, [1] fail
+        double *Sw = P.S + P.win_S_off[w];
         PHASE_BEGIN
-            const double p = M[(size_t)k * ldm + k];
-            const bool bad = !(p > 0.0) || !plba_isfinite(p);
-            const double d = bad ? 1.0 : sqrt(p);
-            if (tid == 0) { dg[k] = d; if (bad) *fail = 1; }
-            for (int i = k + 1 + tid; i < n; i += PLBA_NT) M[(size_t)i * ldm + k] /= d;
-        PHASE_END
-        PHASE_BEGIN
-            const int ti = tid >> 4, tj = tid & 15;
-            for (int i = k + 1 + ti; i < n; i += PLBA_NT >> 4) {
-                const double lik = M[(size_t)i * ldm + k];
-                for (int j = k + 1 + tj; j <= i; j += 16) M[(size_t)i * ldm + j] -= lik * M[(size_t)j * ldm + k];
+            if (tid == 0) {
+                if (!ctl.done && P.profile != PLBA_PROFILE_G) control_h_pre_window(P, w);
+                flag[0] = ctl.done; flag[1] = 0; red[0] = 0.0; red[1] = 0.0;
             }
         PHASE_END
-    }
-    for (int k = 0; k < n; k++) {              // L y = b
+    PROF_MARK(41);
+        const int skip = flag[0];
         PHASE_BEGIN
-            const double yk = b[k] / dg[k];
-            if (tid == 0) y[k] = yk;
-            for (int i = k + 1 + tid; i < n; i += PLBA_NT) b[i] -= M[(size_t)i * ldm + k] * yk;
         PHASE_END
-    }
-    for (int k = n - 1; k >= 0; k--) {         // L^T x = y
+    PROF_MARK(42);
+        if (skip || n == 0) continue;
+        const double lambda = ctl.lambda;
         PHASE_BEGIN
-            const double xk = y[k] / dg[k];
-            if (tid == 0) x[k] = xk;
-            for (int i = tid; i < k; i += PLBA_NT) y[i] -= M[(size_t)k * ldm + i] * xk;
+            // upper triangle of S, one warp per row (coalesced), four loads in flight per thread; stored transposed as lower (cg,rg)
+            const int warp = tid >> 5, lane = tid & 31, nwarp = PLBA_NT >> 5;
+            for (int rg = warp; rg < n; rg += nwarp) {
+                double *row = Sw + (size_t)rg * n;
+                const double dmp = (P.profile == PLBA_PROFILE_G) ? lambda : lambda * P.hpp_diag[(size_t)6 * slot0 + rg];
+                for (int c0 = rg + lane; c0 < n; c0 += 128) {
+                    double v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { const int cg = c0 + 32 * u; v[u] = cg < n ? row[cg] : 0.0; }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int cg = c0 + 32 * u;
+                        if (cg < n) { row[cg] = 0.0; M[(size_t)cg * ldm + rg] = (cg == rg) ? v[u] + dmp : v[u]; }   // consumed: the next assembly accumulates into a clean S
+                    }
+                }
+            }
+            for (int i = tid; i < n; i += PLBA_NT) { M[(size_t)n * ldm + i] = P.gs[(size_t)6 * slot0 + i]; P.gs[(size_t)6 * slot0 + i] = 0.0; }
         PHASE_END
+    PROF_MARK(43);
+        PHASE_BEGIN
+            for (int i = tid; i < n; i += PLBA_NT) P.hpp_diag[(size_t)6 * slot0 + i] = 0.0;
+        PHASE_END
+    PROF_MARK(44);
+        for (int kb = 0; kb < nf; kb++) {
+            const int k0 = 6 * kb;
+            PHASE_BEGIN
+                const int r = k0 + 6 + tid;
+                if (r <= n) {
+                    double L[21], inv[6];
+#pragma unroll
+                    for (int i = 0; i < 6; i++) {
+#pragma unroll
+                        for (int j = 0; j <= i; j++) L[i * (i + 1) / 2 + j] = M[(size_t)(k0 + i) * ldm + k0 + j];
+                    }
+                    bool bad = false;
+#pragma unroll
+                    for (int j = 0; j < 6; j++) {
+                        double s = L[j * (j + 1) / 2 + j];
+#pragma unroll
+                        for (int k = 0; k < j; k++) s -= L[j * (j + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+                        if (!(s > 0.0) || !plba_isfinite(s)) { bad = true; s = 1.0; }
+                        inv[j] = plba_rsqrt(s);
+                        L[j * (j + 1) / 2 + j] = s * inv[j];
+#pragma unroll
+                        for (int i = j + 1; i < 6; i++) {
+                            double v = L[i * (i + 1) / 2 + j];
+#pragma unroll
+                            for (int k = 0; k < j; k++) v -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+                            L[i * (i + 1) / 2 + j] = v * inv[j];
+                        }
+                    }
+                    double x[6];
+#pragma unroll
+                    for (int c = 0; c < 6; c++) {
+                        double v = M[(size_t)r * ldm + k0 + c];
+#pragma unroll
+                        for (int k = 0; k < c; k++) v -= x[k] * L[c * (c + 1) / 2 + k];
+                        x[c] = v * inv[c];
+                    }
+#pragma unroll
+                    for (int c = 0; c < 6; c++) M[(size_t)r * ldm + k0 + c] = x[c];
+                    if (tid == 0) {
+                        if (bad) flag[1] = 1;
+#pragma unroll
+                        for (int c = 0; c < 6; c++) dinv[k0 + c] = inv[c];
+                    }
+                    // the diagonal block is only read in this phase: thread 0 parks L_kk and writes it back in the next one
+                    if (tid == 0) {
+#pragma unroll
+                        for (int i = 0; i < 21; i++) Ls[i] = L[i];
+                    }
+                }
+            PHASE_END
+    PROF_MARK(45);
+            PHASE_BEGIN
+                if (tid == 0) {
+                    for (int i = 0; i < 6; i++) for (int j = 0; j <= i; j++) M[(size_t)(k0 + i) * ldm + k0 + j] = Ls[i * (i + 1) / 2 + j];
+                }
+                // trailing update M[i][j] -= sum_c L[i][c] L[j][c] on 4 x 4 register tiles whose rows / columns are strided by T,
+                // so that neighbouring lanes read neighbouring rows of L (ldm is odd: conflict-free) and share the Li loads
+                const int base = k0 + 6, m = n - base + 1;      // rows base..n (row n = right-hand side), columns base..n-1
+                const int T = (m + 3) >> 2;
+                for (int p = tid; p < T * T; p += PLBA_NT) {
+                    const int ti = p / T, tj = p - ti * T;
+                    double Li[4][6], Lj[4][6];
+#pragma unroll
+                    for (int a = 0; a < 4; a++) {
+                        const int i = base + ti + T * a, j = base + tj + T * a;
+#pragma unroll
+                        for (int c = 0; c < 6; c++) {
+                            Li[a][c] = (i <= n) ? M[(size_t)i * ldm + k0 + c] : 0.0;
+                            Lj[a][c] = (j < n) ? M[(size_t)j * ldm + k0 + c] : 0.0;
+                        }
+                    }
+#pragma unroll
+                    for (int a = 0; a < 4; a++) {
+#pragma unroll
+                        for (int bb = 0; bb <= a; bb++) {
+                            const int i = base + ti + T * a, j = base + tj + T * bb;
+                            if (i <= n && j < n && j <= i && (a > bb || tj <= ti)) {
+                                double sdot = 0.0;
+#pragma unroll
+                                for (int c = 0; c < 6; c++) sdot += Li[a][c] * Lj[bb][c];
+                                M[(size_t)i * ldm + j] -= sdot;
+                            }
+                        }
+                    }
+                }
+            PHASE_END
+    PROF_MARK(46);
+        }
+        // backward substitution L^T x = y, y = row n; column-oriented so that every step reads rows of L
+        for (int kb = nf - 1; kb >= 0; kb--) {
+            const int k0 = 6 * kb;
+            PHASE_BEGIN
+                if (tid <= k0) {       // threads 0..k0-1 own y[j]; thread k0 (or 0 when k0 == 0) records x
+                    double x[6];
+#pragma unroll
+                    for (int c = 5; c >= 0; c--) {
+                        double v = M[(size_t)n * ldm + k0 + c];
+#pragma unroll
+                        for (int m = c + 1; m < 6; m++) v -= M[(size_t)(k0 + m) * ldm + k0 + c] * x[m];
+                        x[c] = v * dinv[k0 + c];
+                    }
+                    if (tid < k0) {
+                        double y = M[(size_t)n * ldm + tid];
+#pragma unroll
+                        for (int c = 0; c < 6; c++) y -= M[(size_t)(k0 + c) * ldm + tid] * x[c];
+                        M[(size_t)n * ldm + tid] = y;
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 6; c++) xs[k0 + c] = x[c];
+                    }
+                }
+            PHASE_END
+    PROF_MARK(47);
+        }
+        PHASE_BEGIN
+            const int f = flag[1];
+            for (int i = tid; i < n; i += PLBA_NT) P.xp[(size_t)6 * slot0 + i] = f ? 0.0 : xs[i];
+            if (tid == 0 && f) ctl.solve_fail = 1;
+        PHASE_END
+    PROF_MARK(48);
+        PHASE_BEGIN
+            double sc = 0.0, d2 = 0.0;
+            if (tid < nf) pose_update_slot(P, slot0 + tid, sc, d2);
+            plba_block_add(&red[0], sc);
+            plba_block_add(&red[1], d2);
+        PHASE_END
+    PROF_MARK(49);
+        PHASE_BEGIN
+            if (tid == 0) { ctl.scale_pose = red[0]; ctl.dx2_pose = red[1]; }
+        PHASE_END
+    PROF_MARK(50);
     }
-    PHASE_BEGIN
-        const int f = *fail;
-        for (int i = tid; i < n; i += PLBA_NT) P.xp[(size_t)6 * slot0 + i] = f ? 0.0 : x[i];
-        if (tid == 0 && f) ctl.solve_fail = 1;
-    PHASE_END
 }
-static inline size_t solve_small_smem(int n, int ldm) { return sizeof(double) * ((size_t)n * ldm + 4 * (size_t)n) + 16; }
 
 // ---- tiled path -----------------------------------------------------------------------------------------------
 // Factor the diagonal tile k (damping added here: later tiles only receive additive updates) and store inv(U_kk).
-PLBA_KERNEL void k_potrf_tile(DevP P, int w, int k, double *invbuf) {
+PLBA_KERNEL void k_potrf_tile(const DevP *Pp, int w, int k, double *invbuf) {
     PLBA_SMEM(raw);
+    PLBA_PARAMS(P, Pp);
     WinCtrl &ctl = P.ctrl[w];
     const int n = 6 * P.win_nfree[w], slot0 = P.win_slot0[w];
     double *Sw = P.S + P.win_S_off[w];
@@ -131,8 +261,9 @@ PLBA_KERNEL void k_potrf_tile(DevP P, int w, int k, double *invbuf) {
 }
 
 // U_kj = inv(U_kk)^T A_kj for every tile j > k  (one CTA per tile)
-PLBA_KERNEL void k_trsm_tiles(DevP P, int w, int k, const double *invbuf) {
+PLBA_KERNEL void k_trsm_tiles(const DevP *Pp, int w, int k, const double *invbuf) {
     PLBA_SMEM(raw);
+    PLBA_PARAMS(P, Pp);
     const int n = 6 * P.win_nfree[w];
     double *Sw = P.S + P.win_S_off[w];
     const int j = k + 1 + PLBA_BID;
@@ -162,8 +293,9 @@ PLBA_KERNEL void k_trsm_tiles(DevP P, int w, int k, const double *invbuf) {
 }
 
 // A_ij -= U_ki^T U_kj for k < i <= j  (one CTA per tile pair; grid.x enumerates the upper-triangular pairs)
-PLBA_KERNEL void k_syrk_tiles(DevP P, int w, int k, int nt) {
+PLBA_KERNEL void k_syrk_tiles(const DevP *Pp, int w, int k, int nt) {
     PLBA_SMEM(raw);
+    PLBA_PARAMS(P, Pp);
     const int n = 6 * P.win_nfree[w];
     double *Sw = P.S + P.win_S_off[w];
     const int m = nt - k - 1;
@@ -197,8 +329,9 @@ PLBA_KERNEL void k_syrk_tiles(DevP P, int w, int k, int nt) {
 }
 
 // U^T y = g ; U x = y with the stored inverse diagonal tiles (single CTA, 1024 threads)
-PLBA_KERNEL void k_trisolve_large(DevP P, int w, int nt, const double *invbuf) {
+PLBA_KERNEL void k_trisolve_large(const DevP *Pp, int w, int nt, const double *invbuf) {
     PLBA_SMEM(raw);
+    PLBA_PARAMS(P, Pp);
     WinCtrl &ctl = P.ctrl[w];
     const int n = 6 * P.win_nfree[w], slot0 = P.win_slot0[w];
     const double *Sw = P.S + P.win_S_off[w];

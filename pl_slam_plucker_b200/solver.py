@@ -100,6 +100,12 @@ class LBASolver:
         self._check(self.L.plba_copy_reduced_system(self.h, int(window), S.ctypes.data_as(_lib._pd), g.ctypes.data_as(_lib._pd)))
         return S, g
 
+    def time_kernel(self, which, reps=20, lam=1.0):
+        """Average ms of one launch of a stage kernel (0 assemble, 1 solve, 2 update) on the resident problem."""
+        ms = C.c_double(0)
+        self._check(self.L.plba_time_kernel(self.h, int(which), int(reps), float(lam), C.byref(ms)))
+        return ms.value
+
     def set_allreduce(self, fn):
         """fn(ptr:int, n_doubles:int (negative => max-reduce of |n|), stream:int) sums the device buffer over ranks in place."""
         def _cb(ptr, n, stream, user):
