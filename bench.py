@@ -38,28 +38,11 @@ def algorithmic_bytes(P, nnzb_S):
             + 288 * nnzb_S + 48 * P.n_free + 72 * P.n_pt + 112 * P.n_ls)
 
 
-def schur_nnz_blocks(P):
-    """Upper-triangular 6x6 blocks of S that are structurally non-zero (diag + co-visible free KF pairs)."""
-    nf = P.n_free
-    if nf > 400:            # banded estimate would need the pattern; count it exactly but vectorised per landmark run
-        pass
-    pat = np.zeros((nf, nf), bool)
-    np.fill_diagonal(pat, True)
-    for lm, kf in ((P.po_lm, P.po_kf), (P.lo_lm, P.lo_kf)):
-        if lm.size == 0:
-            continue
-        slot = P.kf_slot[kf]
-        ok = slot >= 0
-        lm, slot = lm[ok], slot[ok]
-        # first / last free slot per landmark: tracks are contiguous KF runs in the synthetic scenes and S is filled between
-        order = np.lexsort((slot, lm))
-        lm, slot = lm[order], slot[order]
-        start = np.r_[0, np.flatnonzero(lm[1:] != lm[:-1]) + 1]
-        end = np.r_[start[1:], lm.size]
-        for s, e in zip(start, end):
-            u = slot[s:e]
-            pat[np.ix_(u, u)] = True
-    return int(np.triu(pat).sum())
+def algorithmic_flops(P):
+    """SURVEY.md §8(d) profile-G estimate, evaluated per landmark track length."""
+    kp = np.bincount(P.po_lm, minlength=P.n_pt).astype(np.float64) if P.n_pobs else np.zeros(P.n_pt)
+    kl = np.bincount(P.lo_lm, minlength=P.n_ls).astype(np.float64) if P.n_lobs else np.zeros(P.n_ls)
+    return float(313.0 * P.n_pobs + 620.0 * P.n_lobs + np.sum(50 + 144 * kp + 108 * kp * (kp + 1)) + np.sum(150 + 240 * kl + 144 * kl * (kl + 1)))
 
 
 class ClockSampler(threading.Thread):
@@ -131,6 +114,55 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def _peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s"
+
+
+def largest_config_roofline(s, abi, scene, args):
+    """Assembly kernel on BASELINE config 5 (2 000 KFs, 2M points, 500k lines; inputs 0.45 GB >> L2, so every launch is cold)."""
+    P5 = scene.make_scene(5)
+    s.upload(P5, abi.Options(PROFILES[args.profile] if args.profile != "H_END" else 0, args.quirks))
+    st = s.layout_stats()
+    A = algorithmic_bytes(P5, st["nnzb_S"]); F = algorithmic_flops(P5)
+    ms_a = s.time_kernel(0, 5); ms_u = s.time_kernel(2, 5)
+    peak, src = _peak()
+    return {"workload": "C5: %d free KFs, %d points, %d lines, %d+%d observations" % (P5.n_free, P5.n_pt, P5.n_ls, P5.n_pobs, P5.n_lobs),
+            "kernel": "k_assemble", "bound": "hbm", "algorithmic_bytes": A, "ms_per_launch": ms_a, "achieved": A / (ms_a * 1e-3) / 1e9, "peak": peak,
+            "peak_source": src, "unit": "GB/s", "frac": A / (ms_a * 1e-3) / 1e9 / peak, "algorithmic_flops": F, "achieved_fp64_tflops": F / (ms_a * 1e-3) / 1e12,
+            "update_kernel_ms_per_launch": ms_u, "nnzb_S": st["nnzb_S"], "launches_timed": 5,
+            "note": "FP64 work (about %.1f GFLOP) bounds this kernel before HBM does: at the 37 TFLOP/s vector peak it needs %.0f us, the HBM roofline %.0f us" % (F / 1e9, F / 37e12 * 1e6, A / (peak * 1e9) * 1e6)}
+
+
+def sharded_run(s, abi, scene, args, rank, world, dev, stream, barrier):
+    """BASELINE config 4 sharded by base keyframe over the ranks, reduced camera system all-reduced with NCCL every LM trial."""
+    import torch
+    import torch.distributed as dist
+    from pl_slam_plucker_b200 import sharded, solver
+    P4 = scene.make_scene(4)
+    s2 = solver.LBASolver(dev.index, stream=stream.cuda_stream)
+    sh = sharded.ShardedLBA(s2, rank, world, device=dev)
+    opt = abi.Options(abi.PROFILE_G, 1)
+    with torch.cuda.stream(stream):
+        sh.upload(P4, opt)
+        s2.run()                                   # warm-up (NCCL communicator, allocator)
+        reps, t_ms, trials = 3, 0.0, 0
+        for _ in range(reps):
+            s2.reset()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier(); e0.record(stream); s2.run(); e1.record(stream); torch.cuda.synchronize()
+            t_ms += e0.elapsed_time(e1); trials += s2.timing()["n_trials_run"]
+    t = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    n_dbl = s2.reduced_system_ptr()[1]
+    s2.close()
+    return {"workload": "C4: %d free KFs, %d points, %d lines sharded by base keyframe over %d GPUs" % (P4.n_free, P4.n_pt, P4.n_ls, world),
+            "lm_trials": trials // reps, "ms_per_lba": float(t.item()) / reps, "observations_per_s": P4.n_obs * trials / (float(t.item()) * 1e-3),
+            "allreduce_bytes_per_trial": int(8 * n_dbl), "collective": "NCCL all-reduce of [S | g] per LM trial (torch.distributed)"}
+
+
 def workload_name(args, P):
     return "%s: %d free + %d fixed KFs, %d points, %d lines, %d+%d observations" % (
         args.workload, P.n_free, P.n_kf - P.n_free, P.n_pt, P.n_ls, P.n_pobs, P.n_lobs)
@@ -146,6 +178,8 @@ def main():
     ap.add_argument("--profile", default="G", choices=sorted(PROFILES))
     ap.add_argument("--quirks", type=int, default=0, help="0 = faithful (bug-for-bug), 1 = fixed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-largest", action="store_true", help="skip the C5 assembly roofline measurement")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the landmark-sharded C4 run")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
@@ -178,6 +212,7 @@ def main():
 
     # ---- resident-problem throughput -------------------------------------------------------------------------
     s.upload(P, opt)
+    nnzb = s.layout_stats()["nnzb_S"]
     for _ in range(args.warmup):
         s.reset(); s.run()
     torch.cuda.synchronize()
@@ -219,6 +254,11 @@ def main():
     e2e_s = time.perf_counter() - t0
     sampler.stop_flag = True; sampler.join()
 
+    extras = {}
+    if rank == 0 and not args.no_largest:
+        extras["roofline_largest"] = largest_config_roofline(s, abi, scene, args)
+    if world > 1 and not args.no_sharded:
+        extras["sharded"] = sharded_run(s, abi, scene, args, rank, world, dev, stream, barrier)
     tt = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(P.n_obs * trials), float(P.n_obs * e2e_trials), float(trials)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -226,13 +266,7 @@ def main():
     ms_max, e2e_ms_max = tt.tolist(); obs_trials, e2e_obs_trials, trials_all = cnt.tolist()
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
-        nnzb = schur_nnz_blocks(P)
+        peak, peak_src = _peak()
         A = algorithmic_bytes(P, nnzb)
         asm_ms = t_asm / max(n_asm, 1)
         line = {"metric": METRIC, "value": obs_trials / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -249,6 +283,7 @@ def main():
                              "traffic": None, "algorithmic_bytes": A, "ms_per_launch": asm_ms, "launches_timed": int(n_asm),
                              "stage_ms_per_step": {"assemble": t_asm / det_steps, "solve": t_sol / det_steps, "update": t_upd / det_steps},
                              "how": "CUDA events around each stage in a host-driven replay of the same steps (the headline steps run as one CUDA graph)"}}
+        line.update(extras)
         if not args.no_cpu_baseline:
             from oracle import loader as orc
             orc.build(); orc.set_threads(1)

@@ -190,6 +190,9 @@ int  plba_copy_reduced_system(plba_handle h, int32_t window, double *S_out, doub
  * two CUDA events on the handle's stream.  which: 0 = assembly (linearise + blocks + Schur), 1 = reduced-system solve,
  * 2 = update (back-substitution + retraction + new cost).  The LM state is not advanced. */
 int  plba_time_kernel(plba_handle h, int32_t which, int32_t reps, double lambda, double *ms_avg);
+/* Layout of the resident problem, for roofline accounting: out8 = { point chunks, line chunks, point segments, line segments,
+ * off-diagonal Schur tasks, diagonal Schur tasks, structurally non-zero upper 6x6 blocks of S (nnzb), device arena bytes }. */
+int  plba_layout_stats(plba_handle h, int64_t *out8);
 /* Optional all-reduce hook called on the handle's stream wherever the path has its exchange step
  * (SURVEY.md §8e).  fn(dev_ptr, n_doubles, stream, user) must sum the buffer in place over all ranks. */
 typedef void (*plba_allreduce_fn)(void *dev_ptr, int64_t n_doubles, void *stream, void *user);
@@ -204,6 +207,8 @@ typedef struct plba_timing {
     int64_t n_launches_run;  /* kernels launched by the last plba_run                              */
     int64_t n_assemble_run;  /* assembly-kernel launches of the last plba_run                      */
     int64_t n_trials_run;    /* LM trials (linear solves) of the last plba_run, summed over windows */
+    double  ms_host_prep;    /* host wall time of the last plba_upload before its H2D copy (validation, signature sort, flattening) */
+    double  ms_host_unpack;  /* host wall time of the last plba_download after its D2H copy (un-permutation into caller buffers)  */
 } plba_timing;
 int  plba_get_timing(plba_handle h, plba_timing *t);
 /* on: record CUDA events around the assembly / solve / update kernels of every LM round (fills ms_assemble ...). */

@@ -56,7 +56,8 @@ class plba_timing(C.Structure):
     _fields_ = [("ms_total", C.c_double), ("ms_assemble", C.c_double), ("ms_solve", C.c_double), ("ms_update", C.c_double),
                 ("ms_other", C.c_double), ("n_launches", C.c_int64), ("n_assemble", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("n_launches_run", C.c_int64), ("n_assemble_run", C.c_int64), ("n_trials_run", C.c_int64)]
+                ("n_launches_run", C.c_int64), ("n_assemble_run", C.c_int64), ("n_trials_run", C.c_int64),
+                ("ms_host_prep", C.c_double), ("ms_host_unpack", C.c_double)]
 
 
 class plba_scene_spec(C.Structure):

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include "plba_solver.h"
 
 using namespace plba;
@@ -56,6 +57,7 @@ struct plba_handle_s {
     double *sysbuf = nullptr; size_t sys_doubles = 0, S_doubles = 0;
     double *invbuf = nullptr;
     int h_counters[CNT_N] = {0};
+    int64_t layout[8] = {0};
     plba_allreduce_fn allreduce = nullptr; void *allreduce_user = nullptr;
     plba_timing timing{};
     cudaEvent_t ev[8]{};
@@ -143,16 +145,49 @@ static void signature_order(int n_lm, int n_obs, const int32_t *lm, const int32_
     L.perm.resize(n_lm);
     for (int l = 0; l < n_lm; l++) L.perm[l] = l;
     if (!permute || n_lm < 2) return;
-    std::vector<std::pair<uint64_t, int>> key(n_lm);
+    // group landmarks by exact signature with an open-addressing table (hash -> group), then order the groups by
+    // (first keyframe, first appearance) and counting-sort the landmarks by group: O(n) instead of a comparison sort
+    struct Slot { uint64_t hsh; int group, rep; };
+    size_t cap = 1024;
+    std::vector<Slot> table(cap, Slot{0, -1, -1});
+    std::vector<int> group_of(n_lm), g_first, g_rep, g_count;
+    auto same_sig = [&](int l, int r) {
+        const int a = L.optr[l], b = L.optr[l + 1], c = L.optr[r];
+        if (b - a != L.optr[r + 1] - c) return false;
+        for (int i = 0; i < b - a; i++) if (kf[a + i] != kf[c + i]) return false;
+        return true;
+    };
     for (int l = 0; l < n_lm; l++) {
         const int a = L.optr[l], b = L.optr[l + 1];
         uint64_t hsh = 1469598103934665603ULL ^ (uint64_t)(b - a);
         for (int i = a; i < b; i++) { hsh ^= (uint64_t)(uint32_t)kf[i] + 0x9e3779b97f4a7c15ULL + (hsh << 6) + (hsh >> 2); hsh *= 1099511628211ULL; }
-        const uint64_t first = (b > a) ? (uint64_t)(uint32_t)kf[a] : 0xffffffULL;
-        key[l] = std::make_pair((first << 40) | (hsh >> 24), l);
+        size_t pos = (size_t)(hsh >> 17) & (cap - 1);
+        int g = -1;
+        while (table[pos].group >= 0) {
+            if (table[pos].hsh == hsh && same_sig(l, table[pos].rep)) { g = table[pos].group; break; }
+            pos = (pos + 1) & (cap - 1);
+        }
+        if (g < 0) {
+            g = (int)g_rep.size();
+            g_rep.push_back(l); g_count.push_back(0); g_first.push_back(b > a ? kf[a] : 0x7fffffff);
+            table[pos] = Slot{hsh, g, l};
+            if (2 * g_rep.size() > cap) {      // grow: re-insert the representatives
+                cap *= 4;
+                std::vector<Slot> bigger(cap, Slot{0, -1, -1});
+                for (const Slot &sl : table) if (sl.group >= 0) { size_t q = (size_t)(sl.hsh >> 17) & (cap - 1); while (bigger[q].group >= 0) q = (q + 1) & (cap - 1); bigger[q] = sl; }
+                table.swap(bigger);
+            }
+        }
+        group_of[l] = g; g_count[g]++;
     }
-    std::sort(key.begin(), key.end());
-    for (int l = 0; l < n_lm; l++) L.perm[l] = key[l].second;
+    const int ng = (int)g_rep.size();
+    std::vector<int> order(ng);
+    for (int g = 0; g < ng; g++) order[g] = g;
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return g_first[x] != g_first[y] ? g_first[x] < g_first[y] : x < y; });
+    std::vector<int> start(ng, 0);
+    int acc = 0;
+    for (int r = 0; r < ng; r++) { start[order[r]] = acc; acc += g_count[order[r]]; }
+    for (int l = 0; l < n_lm; l++) L.perm[start[group_of[l]]++] = l;       // stable inside a group
 }
 
 extern "C" {
@@ -252,7 +287,9 @@ template <int PROF> static int chunk_occupancy() {
 #endif
 }
 static int chunk_occupancy_for(int prof) {
-    return prof == PLBA_PROFILE_G ? chunk_occupancy<PLBA_PROFILE_G>() : prof == PLBA_PROFILE_H_END ? chunk_occupancy<PLBA_PROFILE_H_END>() : chunk_occupancy<PLBA_PROFILE_H_PLK>();
+    static int cache[3] = {0, 0, 0};
+    if (cache[prof]) return cache[prof];
+    return cache[prof] = prof == PLBA_PROFILE_G ? chunk_occupancy<PLBA_PROFILE_G>() : prof == PLBA_PROFILE_H_END ? chunk_occupancy<PLBA_PROFILE_H_END>() : chunk_occupancy<PLBA_PROFILE_H_PLK>();
 }
 static size_t chunk_smem(int prof) {
     return prof == PLBA_PROFILE_G ? SmemMax<PLBA_PROFILE_G>::bytes() : prof == PLBA_PROFILE_H_END ? SmemMax<PLBA_PROFILE_H_END>::bytes() : SmemMax<PLBA_PROFILE_H_PLK>::bytes();
@@ -387,6 +424,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     if (!h || n <= 0 || !probs || !opt) return PLBA_E_ARG;
     if (opt->profile < PLBA_PROFILE_G || opt->profile > PLBA_PROFILE_H_PLK) { h->err = "unknown profile"; return PLBA_E_ARG; }
     CK(cudaSetDevice(h->device));
+    const auto t_host0 = std::chrono::steady_clock::now();
     h->uploaded = false;
     h->opt = *opt;
     h->timing = plba_timing{};
@@ -464,6 +502,32 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     }
     if (too_long) { h->err = "a landmark has more than 256 observations"; return PLBA_E_UNSUPPORTED; }
 
+    {   // layout statistics (plba_layout_stats): structural non-zero 6x6 blocks of S = union over segments of their pose pairs
+        std::vector<size_t> wbase(n + 1, 0);
+        for (int w = 0; w < n; w++) wbase[w + 1] = wbase[w] + (size_t)h->wins[w].n_free * h->wins[w].n_free;
+        std::vector<unsigned char> mark(wbase[n], 0);
+        int64_t n_off = 0, n_diag = 0, nnzb = 0;
+        for (int cls = 0; cls < 2; cls++) {
+            const std::vector<Seg> &sgs = cls ? sg_ls : sg_pt; const std::vector<int> &fps = cls ? fp_ls : fp_pt;
+            const std::vector<int> &ptr = cls ? ls_ptr : pt_ptr; const std::vector<int> &operm = cls ? h->lo_perm : h->po_perm;
+            int w = 0;
+            for (const Seg &sg : sgs) {
+                n_off += (int64_t)sg.nfree * (sg.nfree - 1) / 2; n_diag += sg.nfree;
+                while (w + 1 < n && (cls ? h->wins[w + 1].ls0 : h->wins[w + 1].pt0) <= sg.lm0) w++;     // segments are emitted window by window
+                const plba_problem &p = probs[w]; const WinInfo &wi = h->wins[w];
+                const int32_t *kf = cls ? p.lo_kf : p.po_kf; const int ob0 = cls ? wi.lo0 : wi.po0, o0 = ptr[sg.lm0];
+                for (int i = 0; i < sg.nfree; i++) for (int j = i; j < sg.nfree; j++) {
+                    int a = p.kf_slot[kf[operm[o0 + fps[sg.fp0 + i]] - ob0]], b = p.kf_slot[kf[operm[o0 + fps[sg.fp0 + j]] - ob0]];
+                    if (a > b) std::swap(a, b);
+                    unsigned char &m = mark[wbase[w] + (size_t)a * wi.n_free + b];
+                    if (!m) { m = 1; nnzb++; }
+                }
+            }
+        }
+        h->layout[0] = (int64_t)ch_pt.size(); h->layout[1] = (int64_t)ch_ls.size(); h->layout[2] = (int64_t)sg_pt.size(); h->layout[3] = (int64_t)sg_ls.size();
+        h->layout[4] = n_off; h->layout[5] = n_diag; h->layout[6] = nnzb;
+    }
+
     // ---- memory plan ----------------------------------------------------------------------------------------
     Carver ci;   // staged inputs (same offsets in pinned host memory and at the start of the device arena)
     const size_t i_kf_slot = ci.take<int>(tot.n_kf), i_kf_win = ci.take<int>(tot.n_kf), i_slot_kf = ci.take<int>(tot.n_free);
@@ -502,6 +566,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     h->out_bytes = co.off - h->out_off;
     int rc = ensure(h, co.off, h->in_bytes, h->out_bytes);
     if (rc) return rc;
+    h->layout[7] = (int64_t)co.off;
 
     // ---- flatten into the pinned staging buffer ------------------------------------------------------------------
     char *hb = h->h_in;
@@ -552,13 +617,13 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
             const int i = h->po_perm[o] - wi.po0;
             po_kf[o] = wi.kf0 + p.po_kf[i]; po_lm[o] = g;
             po_uv[(size_t)2 * o] = p.po_uv[(size_t)2 * i]; po_uv[(size_t)2 * o + 1] = p.po_uv[(size_t)2 * i + 1];
-            po_om[o] = (double)(float)(1.0 / (p.po_sig2 ? p.po_sig2[i] : 1.0));                      // const float& invSigma2 (:6009, Q13)
+            po_om[o] = p.po_sig2 ? (double)(float)(1.0 / p.po_sig2[i]) : 1.0;                        // const float& invSigma2 (:6009, Q13)
         }
         for (int g = wi.ls0; g < wi.ls0 + p.n_ls; g++) for (int o = ls_ptr[g]; o < ls_ptr[g + 1]; o++) {
             const int i = h->lo_perm[o] - wi.lo0;
             lo_kf[o] = wi.kf0 + p.lo_kf[i]; lo_lm[o] = g;
             for (int k = 0; k < 4; k++) lo_ab[(size_t)4 * o + k] = p.lo_ab[(size_t)4 * i + k];
-            lo_om[o] = (double)(float)(1.0 / (p.lo_sig2 ? p.lo_sig2[i] : 1.0));
+            lo_om[o] = p.lo_sig2 ? (double)(float)(1.0 / p.lo_sig2[i]) : 1.0;
         }
         WinCtrl c{};
         c.need_init = 1; c.apply = 1; c.ni = 2.0; c.err_prev = 999999999.9; c.n_lm_pt = p.n_pt; c.n_lm_ls = p.n_ls;
@@ -604,6 +669,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     }
 #endif
     *h->h_P = P;
+    h->timing.ms_host_prep = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
     CK(cudaMemcpyAsync(h->d_P, h->h_P, sizeof(DevP), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_arena, h->h_in, h->in_bytes, cudaMemcpyHostToDevice, h->stream));
     h->timing.h2d_bytes += (int64_t)(h->in_bytes + sizeof(DevP));
@@ -727,6 +793,7 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
     h->timing.d2h_bytes += (int64_t)h->out_bytes;
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    const auto t_host0 = std::chrono::steady_clock::now();
     const char *ob = h->h_out - h->out_off;      // so that ob + o_xxx addresses the host copy
     const double *T = (const double *)(ob + h->o_T), *X = (const double *)(ob + h->o_x), *pt = (const double *)(ob + h->o_pt), *ls = (const double *)(ob + h->o_ls);
     const double *plk = (const double *)(ob + h->o_plk), *pchi = (const double *)(ob + h->o_pchi), *lchi = (const double *)(ob + h->o_lchi);
@@ -771,6 +838,7 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
         }
         if (r.status < PLBA_DISCARDED) rc_all = r.status;
     }
+    h->timing.ms_host_unpack = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
     return rc_all;
 }
 
@@ -869,6 +937,7 @@ int plba_debug_prof(unsigned long long *out64, int reset) {
     return 0;
 }
 #endif
+int plba_layout_stats(plba_handle h, int64_t *out8) { if (!h || !h->uploaded || !out8) return PLBA_E_ARG; for (int i = 0; i < 8; i++) out8[i] = h->layout[i]; return PLBA_OK; }
 int plba_get_timing(plba_handle h, plba_timing *t) { if (!h || !t) return PLBA_E_ARG; *t = h->timing; return PLBA_OK; }
 int plba_set_detail_timing(plba_handle h, int on) { if (!h) return PLBA_E_ARG; h->detail_timing = on != 0; return PLBA_OK; }
 

@@ -106,6 +106,12 @@ class LBASolver:
         self._check(self.L.plba_time_kernel(self.h, int(which), int(reps), float(lam), C.byref(ms)))
         return ms.value
 
+    def layout_stats(self):
+        out = (C.c_int64 * 8)()
+        self._check(self.L.plba_layout_stats(self.h, out))
+        keys = ("chunks_pt", "chunks_ls", "segments_pt", "segments_ls", "tasks_offdiag", "tasks_diag", "nnzb_S", "arena_bytes")
+        return dict(zip(keys, [int(v) for v in out]))
+
     def set_allreduce(self, fn):
         """fn(ptr:int, n_doubles:int (negative => max-reduce of |n|), stream:int) sums the device buffer over ranks in place."""
         def _cb(ptr, n, stream, user):
