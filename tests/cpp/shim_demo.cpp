@@ -1,0 +1,42 @@
+// Builds a pointer-style map from a synthetic scene and runs the reference-named LBA entry points of the C++ host shim.
+// Usage: shim_demo [n_pt n_ls]   (prints one line of key=value pairs; exit code 0 on success)
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include "../../pl_slam_plucker_b200/csrc/shim/map_handler_shim.h"
+using namespace plba_shim;
+
+int main(int argc, char **argv) {
+    plba_scene_spec sp; plba_scene_preset(1, &sp);
+    sp.n_kf_free = 5; sp.n_kf_fixed = 2; sp.n_pt = argc > 1 ? std::atoi(argv[1]) : 120; sp.n_ls = argc > 2 ? std::atoi(argv[2]) : 30; sp.seed = 13;
+    plba_scene sc; if (plba_scene_create(&sp, &sc) != 0) return 2;
+    plba_problem P; plba_scene_problem(sc, &P);
+    PinholeStereoCamera cam{P.cam[0], P.cam[1], P.cam[2], P.cam[3]};
+    std::vector<std::unique_ptr<KeyFrame>> kfs; std::vector<std::unique_ptr<MapPoint>> pts; std::vector<std::unique_ptr<MapLine>> lns;
+    try {
+        MapHandlerShim mh(0);
+        mh.cam = &cam;
+        for (int k = 0; k < P.n_kf; k++) {
+            kfs.emplace_back(new KeyFrame()); KeyFrame *kf = kfs.back().get();
+            kf->kf_idx = k; kf->local = P.kf_slot[k] >= 0;
+            for (int i = 0; i < 12; i++) kf->T_kf_w[i] = P.kf_T_wc[12 * k + i];
+            kf->T_kf_w[15] = 1.0;
+            if (P.kf_slot[k] >= 0 && P.x_pose) for (int i = 0; i < 6; i++) kf->x_kf_w[i] = P.x_pose[6 * P.kf_slot[k] + i];
+            mh.map_keyframes.push_back(kf);
+        }
+        for (int l = 0; l < P.n_pt; l++) { pts.emplace_back(new MapPoint()); pts.back()->idx = l; for (int i = 0; i < 3; i++) pts.back()->point3D[i] = P.pt_xyz[3 * l + i]; mh.map_points.push_back(pts.back().get()); }
+        for (int i = 0; i < P.n_pobs; i++) mh.map_points[P.po_lm[i]]->addMapPointObservation(P.po_kf[i], {P.po_uv[2 * i], P.po_uv[2 * i + 1]});
+        for (int l = 0; l < P.n_ls; l++) { lns.emplace_back(new MapLine()); lns.back()->idx = l; for (int i = 0; i < 6; i++) lns.back()->NDw[i] = P.ls_plk[6 * l + i]; mh.map_lines.push_back(lns.back().get()); }
+        for (int i = 0; i < P.n_lobs; i++) { MapLine *l = mh.map_lines[P.lo_lm[i]]; l->NDw_obs_list.push_back({P.lo_ab[4 * i], P.lo_ab[4 * i + 1], P.lo_ab[4 * i + 2], P.lo_ab[4 * i + 3]}); l->kf_obs_list.push_back(P.lo_kf[i]); l->sigma_list.push_back(1.0); }
+        mh.localBundleAdjustmentForPlukerWithG2O();
+        const double chi0 = mh.last_trace.empty() ? -1 : mh.last_trace.front().chi, chi1 = mh.last_trace.empty() ? -1 : mh.last_trace.back().chi_new;
+        std::printf("g2o_path trials=%zu chi_first=%.9e chi_last=%.9e bad_pt_obs=%d bad_ls_obs=%d T2=%.12f,%.12f,%.12f\n", mh.last_trace.size(), chi0, chi1,
+                    mh.n_bad_point_obs, mh.n_bad_line_obs, mh.map_keyframes[2]->T_kf_w[3], mh.map_keyframes[2]->T_kf_w[7], mh.map_keyframes[2]->T_kf_w[11]);
+        const int rc = mh.localBundleAdjustmentForPluker();          // hand LM on the (now optimised) map: faithful Q10 => lines carry no observations
+        std::printf("hand_lm rc=%d iters=%zu\n", rc, mh.last_trace.size());
+        mh.vo_status = VO_INSERTING_KF;
+        std::printf("discarded rc=%d\n", mh.localBundleAdjustmentForPluker());
+    } catch (const std::exception &e) { std::fprintf(stderr, "error: %s\n", e.what()); plba_scene_destroy(sc); return 1; }
+    plba_scene_destroy(sc);
+    return 0;
+}
