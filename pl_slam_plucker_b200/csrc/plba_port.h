@@ -67,7 +67,7 @@ PLBA_D double plba_ld_l2(const double *p) { return __ldcg(p); }
 PLBA_D int plba_ld_l2(const int *p) { return __ldcg(p); }
 PLBA_D void plba_fence() { __threadfence(); }
 PLBA_D int plba_atomic_fetch_add_i(int *p, int v) { return atomicAdd(p, v); }
-PLBA_D double plba_rsqrt(double x) { return rsqrt(x); }
+PLBA_D double plba_rsqrt(double x) { return rsqrt(x); }   // (an FP32-seeded Newton variant measured slower: profiles/README.md)
 // WHILE / IF nodes of the LM-loop graph are steered from the controller (cudaGraphSetConditional is a device runtime builtin)
 PLBA_D void plba_graph_set(unsigned long long handle, unsigned int v) { cudaGraphSetConditional((cudaGraphConditionalHandle)handle, v); }
 #else

@@ -16,7 +16,7 @@ namespace plba {
 
 enum { SMALL_NMAX = 144, TB = 48 };
 
-static inline size_t solve_small_smem() { return sizeof(double) * ((size_t)(SMALL_NMAX + 1) * (SMALL_NMAX + 1) + 2 * SMALL_NMAX + 24 + 16) + 64; }
+static inline size_t solve_small_smem() { return sizeof(double) * ((size_t)(SMALL_NMAX + 1) * (SMALL_NMAX + 1) + 2 * SMALL_NMAX + 24 + 16 + 6 * 264 + 21 * (SMALL_NMAX / 6)) + 64; }
 
 PLBA_KERNEL void k_solve_small(const DevP *Pp) {
     PLBA_SMEM(raw);
@@ -27,7 +27,8 @@ PLBA_KERNEL void k_solve_small(const DevP *Pp) {
         const int nf = P.win_nfree[w], n = 6 * nf, slot0 = P.win_slot0[w], ldm = n + 1;     // n even => ldm odd: conflict-free columns
         double *M = (double *)raw;                 // (n+1) x ldm lower triangle; row n = right-hand side
         double *dinv = M + (size_t)(n + 1) * ldm, *xs = dinv + n, *Ls = xs + n, *red = Ls + 24;
-        int *flag = (int *)(red + 4);              // [0] skip, [1] fail
+        int *flag = (int *)(red + 4);   // (red: 4 doubles, flag: 2 ints, then the partial-sum buffer)
+        (void)0;              // [0] skip, [1] fail
         double *Sw = P.S + P.win_S_off[w];
         PHASE_BEGIN
             if (tid == 0) {
@@ -45,19 +46,29 @@ PLBA_KERNEL void k_solve_small(const DevP *Pp) {
         PHASE_BEGIN
             // upper triangle of S, one warp per row (coalesced), four loads in flight per thread; stored transposed as lower (cg,rg)
             const int warp = tid >> 5, lane = tid & 31, nwarp = PLBA_NT >> 5;
-            for (int rg = warp; rg < n; rg += nwarp) {
-                double *row = Sw + (size_t)rg * n;
-                const double dmp = (P.profile == PLBA_PROFILE_G) ? lambda : lambda * P.hpp_diag[(size_t)6 * slot0 + rg];
-                for (int c0 = rg + lane; c0 < n; c0 += 128) {
-                    double v[4];
+            for (int rg0 = warp; rg0 < n; rg0 += 2 * nwarp) {
+                double v[2][4];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) { const int cg = c0 + 32 * u; v[u] = cg < n ? row[cg] : 0.0; }
+                for (int rr = 0; rr < 2; rr++) {
+                    const int rg = rg0 + rr * nwarp;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { const int cg = lane + 32 * u; v[rr][u] = (rg < n && cg >= rg && cg < n) ? Sw[(size_t)rg * n + cg] : 0.0; }
+                }
+#pragma unroll
+                for (int rr = 0; rr < 2; rr++) {
+                    const int rg = rg0 + rr * nwarp;
+                    if (rg >= n) continue;
+                    const double dmp = (P.profile == PLBA_PROFILE_G) ? lambda : lambda * P.hpp_diag[(size_t)6 * slot0 + rg];
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
-                        const int cg = c0 + 32 * u;
-                        if (cg < n) { row[cg] = 0.0; M[(size_t)cg * ldm + rg] = (cg == rg) ? v[u] + dmp : v[u]; }   // consumed: the next assembly accumulates into a clean S
+                        const int cg = lane + 32 * u;
+                        if (cg >= rg && cg < n) { Sw[(size_t)rg * n + cg] = 0.0; M[(size_t)cg * ldm + rg] = (cg == rg) ? v[rr][u] + dmp : v[rr][u]; }   // consumed: the next assembly accumulates into a clean S
                     }
                 }
+            }
+            for (int rg = warp; rg < n && n > 128; rg += nwarp) {      // columns beyond 128 (n <= 144)
+                const int cg = 128 + lane;
+                if (cg < n && cg >= rg) { const double x = Sw[(size_t)rg * n + cg]; Sw[(size_t)rg * n + cg] = 0.0; M[(size_t)cg * ldm + rg] = (cg == rg) ? x + ((P.profile == PLBA_PROFILE_G) ? lambda : lambda * P.hpp_diag[(size_t)6 * slot0 + rg]) : x; }
             }
             for (int i = tid; i < n; i += PLBA_NT) { M[(size_t)n * ldm + i] = P.gs[(size_t)6 * slot0 + i]; P.gs[(size_t)6 * slot0 + i] = 0.0; }
         PHASE_END
@@ -66,26 +77,66 @@ PLBA_KERNEL void k_solve_small(const DevP *Pp) {
             for (int i = tid; i < n; i += PLBA_NT) P.hpp_diag[(size_t)6 * slot0 + i] = 0.0;
         PHASE_END
     PROF_MARK(44);
+        // Left-looking Cholesky in panels of one pose block (6 columns).  Per panel two phases:
+        //  U: every row r >= k0 (row n = right-hand side) accumulates sum_{q<k0} L[r][q] L[k0+c][q] for the panel's 6 columns.  One
+        //     thread per (row, half of the q range): its own row is read once per q (stride ldm, odd: conflict-free) and the six
+        //     rows k0..k0+5 are BROADCAST loads shared by the whole warp, so the phase is FMA-bound, not shared-memory-bound,
+        //     and no trailing matrix is ever re-written;
+        //  A: every row folds the partial sums in, the 6x6 diagonal block is factored redundantly in the registers of each row's
+        //     thread (no extra barrier), then the row is solved against it.
+        double *part = Ls + 24 + 8;               // [nsplit][n+1][6] partial sums of phase U (nsplit * rows <= 256)
+        double *Lblk = part + 6 * 264;            // [nf][21] factored diagonal blocks (M keeps their un-factored values)
         for (int kb = 0; kb < nf; kb++) {
-            const int k0 = 6 * kb;
+            const int k0 = 6 * kb, m = n - k0 + 1;
+            // the q range of a row is split over as many threads as the 256-thread CTA allows: late panels have few rows but long rows
+            const int mpad = (m + 31) & ~31, nsplit = (mpad <= 32) ? 8 : (mpad <= 64) ? 4 : (mpad <= 128) ? 2 : 1;
             PHASE_BEGIN
-                const int r = k0 + 6 + tid;
+                const int sp = tid / mpad, rr = tid - sp * mpad;
+                if (k0 > 0 && sp < nsplit && rr < m) {
+                    const int r = k0 + rr;
+                    const int qs = (k0 + nsplit - 1) / nsplit, q0 = sp * qs, q1 = (q0 + qs < k0) ? q0 + qs : k0;
+                    double acc[6] = {0, 0, 0, 0, 0, 0};
+                    const double *Mr = M + (size_t)r * ldm, *Mk = M + (size_t)k0 * ldm;
+#pragma unroll 4
+                    for (int q = q0; q < q1; q++) {
+                        const double v = Mr[q];
+#pragma unroll
+                        for (int c = 0; c < 6; c++) acc[c] += v * Mk[(size_t)c * ldm + q];
+                    }
+#pragma unroll
+                    for (int c = 0; c < 6; c++) part[((size_t)sp * mpad + rr) * 6 + c] = acc[c];
+                }
+            PHASE_END
+            PROF_MARK(45);
+            PHASE_BEGIN
+                if (k0 > 0) for (int idx = tid; idx < 6 * m; idx += PLBA_NT) {       // fold the partial sums into the panel, one thread per entry
+                    const int rr = idx / 6, c = idx - 6 * rr;
+                    double sum = 0.0;
+                    for (int sp = 0; sp < nsplit; sp++) sum += part[((size_t)sp * mpad + rr) * 6 + c];
+                    M[(size_t)(k0 + rr) * ldm + k0 + c] -= sum;
+                }
+            PHASE_END
+            PROF_MARK(51);
+            PHASE_BEGIN
+                const int r = k0 + 6 + tid;              // rows below the diagonal block
                 if (r <= n) {
                     double L[21], inv[6];
 #pragma unroll
                     for (int i = 0; i < 6; i++) {
 #pragma unroll
-                        for (int j = 0; j <= i; j++) L[i * (i + 1) / 2 + j] = M[(size_t)(k0 + i) * ldm + k0 + j];
+                        for (int j = 0; j <= i; j++) {
+                            L[i * (i + 1) / 2 + j] = M[(size_t)(k0 + i) * ldm + k0 + j];
+                        }
                     }
                     bool bad = false;
 #pragma unroll
                     for (int j = 0; j < 6; j++) {
-                        double s = L[j * (j + 1) / 2 + j];
+                        double sd = L[j * (j + 1) / 2 + j];
 #pragma unroll
-                        for (int k = 0; k < j; k++) s -= L[j * (j + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
-                        if (!(s > 0.0) || !plba_isfinite(s)) { bad = true; s = 1.0; }
-                        inv[j] = plba_rsqrt(s);
-                        L[j * (j + 1) / 2 + j] = s * inv[j];
+                        for (int k = 0; k < j; k++) sd -= L[j * (j + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+                        if (!(sd > 0.0) || !plba_isfinite(sd)) { bad = true; sd = 1.0; }
+                        inv[j] = plba_rsqrt(sd);
+                        L[j * (j + 1) / 2 + j] = sd * inv[j];
 #pragma unroll
                         for (int i = j + 1; i < 6; i++) {
                             double v = L[i * (i + 1) / 2 + j];
@@ -108,51 +159,12 @@ PLBA_KERNEL void k_solve_small(const DevP *Pp) {
                         if (bad) flag[1] = 1;
 #pragma unroll
                         for (int c = 0; c < 6; c++) dinv[k0 + c] = inv[c];
-                    }
-                    // the diagonal block is only read in this phase: thread 0 parks L_kk and writes it back in the next one
-                    if (tid == 0) {
 #pragma unroll
-                        for (int i = 0; i < 21; i++) Ls[i] = L[i];
+                        for (int i = 0; i < 21; i++) Lblk[kb * 21 + i] = L[i];
                     }
                 }
             PHASE_END
-    PROF_MARK(45);
-            PHASE_BEGIN
-                if (tid == 0) {
-                    for (int i = 0; i < 6; i++) for (int j = 0; j <= i; j++) M[(size_t)(k0 + i) * ldm + k0 + j] = Ls[i * (i + 1) / 2 + j];
-                }
-                // trailing update M[i][j] -= sum_c L[i][c] L[j][c] on 4 x 4 register tiles whose rows / columns are strided by T,
-                // so that neighbouring lanes read neighbouring rows of L (ldm is odd: conflict-free) and share the Li loads
-                const int base = k0 + 6, m = n - base + 1;      // rows base..n (row n = right-hand side), columns base..n-1
-                const int T = (m + 3) >> 2;
-                for (int p = tid; p < T * T; p += PLBA_NT) {
-                    const int ti = p / T, tj = p - ti * T;
-                    double Li[4][6], Lj[4][6];
-#pragma unroll
-                    for (int a = 0; a < 4; a++) {
-                        const int i = base + ti + T * a, j = base + tj + T * a;
-#pragma unroll
-                        for (int c = 0; c < 6; c++) {
-                            Li[a][c] = (i <= n) ? M[(size_t)i * ldm + k0 + c] : 0.0;
-                            Lj[a][c] = (j < n) ? M[(size_t)j * ldm + k0 + c] : 0.0;
-                        }
-                    }
-#pragma unroll
-                    for (int a = 0; a < 4; a++) {
-#pragma unroll
-                        for (int bb = 0; bb <= a; bb++) {
-                            const int i = base + ti + T * a, j = base + tj + T * bb;
-                            if (i <= n && j < n && j <= i && (a > bb || tj <= ti)) {
-                                double sdot = 0.0;
-#pragma unroll
-                                for (int c = 0; c < 6; c++) sdot += Li[a][c] * Lj[bb][c];
-                                M[(size_t)i * ldm + j] -= sdot;
-                            }
-                        }
-                    }
-                }
-            PHASE_END
-    PROF_MARK(46);
+            PROF_MARK(46);
         }
         // backward substitution L^T x = y, y = row n; column-oriented so that every step reads rows of L
         for (int kb = nf - 1; kb >= 0; kb--) {
@@ -164,7 +176,7 @@ PLBA_KERNEL void k_solve_small(const DevP *Pp) {
                     for (int c = 5; c >= 0; c--) {
                         double v = M[(size_t)n * ldm + k0 + c];
 #pragma unroll
-                        for (int m = c + 1; m < 6; m++) v -= M[(size_t)(k0 + m) * ldm + k0 + c] * x[m];
+                        for (int m = c + 1; m < 6; m++) v -= Lblk[kb * 21 + m * (m + 1) / 2 + c] * x[m];
                         x[c] = v * dinv[k0 + c];
                     }
                     if (tid < k0) {

@@ -83,6 +83,13 @@ def test_large_window_tiled_solver(gpu_solver, oracle):
     _check(gpu_solver, oracle, P, abi.PROFILE_G, 1)
 
 
+def test_largest_single_cta_window(gpu_solver, oracle):
+    """6*Nkf = 144: the largest reduced camera system the shared-memory Cholesky takes (one thread per row, no q split)."""
+    P = scene.make_scene(1, n_kf_free=24, n_kf_fixed=2, n_pt=2400, n_ls=600, seed=17)      # ~100 landmarks per KF: well conditioned
+    _check(gpu_solver, oracle, P, abi.PROFILE_G, 1)
+    _check(gpu_solver, oracle, P, abi.PROFILE_H_PLK, 1)
+
+
 def test_loop_closure_shaped_window(gpu_solver, oracle):
     """Non-banded reduced camera system (KF i also sees landmarks of KF i-7)."""
     P = scene.make_scene(1, n_kf_free=16, n_kf_fixed=2, n_pt=500, n_ls=120, loop_every=7, seed=11)
@@ -208,6 +215,29 @@ def test_map_handler_interface(gpu_solver, oracle):
     np.testing.assert_allclose(np.array([p.point3D for p in mh.map_points]), o.pt_xyz, atol=STATE_ATOL)
     mh.vo_status = mhm.VO_INSERTING_KF
     assert mh.localBundleAdjustment() == -1               # computed but discarded (:3011-3012)
+
+
+def test_config3_full_batch(gpu_solver, oracle):
+    """BASELINE config 3 at full size: 1024 independent 10-KF windows in ONE call; sampled windows against the oracle,
+    all windows against batch-wide invariants."""
+    probs = scene.make_batch(1024, 3)
+    opt = abi.Options(abi.PROFILE_G, 0)
+    rc, rs = gpu_solver.solve_batch(probs, opt)
+    assert rc == abi.OK
+    assert gpu_solver.timing()["n_trials_run"] == sum(r.n_trials for r in rs)
+    for w in (0, 1, 511, 1023):
+        o = oracle.solve(probs[w], opt)
+        assert_trace_close(o.trace, rs[w].trace, abi.PROFILE_G)
+        assert_state_close(o, rs[w], probs[w], abi.PROFILE_G)
+    for P, r in zip(probs, rs):
+        assert r.rc == abi.OK and 15 <= r.n_trials <= 150
+        tr = r.trace
+        acc = tr[tr["accepted"] == 1]
+        assert len(acc) >= 3 and (acc["chi_new"] < acc["chi"]).all()
+        assert (tr["window"] == tr["window"][0]).all()
+        fixed = P.kf_slot < 0
+        np.testing.assert_array_equal(r.kf_T_wc[fixed], P.kf_T_wc[fixed])
+        assert np.isfinite(r.pt_xyz).all() and np.isfinite(r.ls_orth).all()
 
 
 def test_config4_full_size_properties(gpu_solver):
