@@ -270,6 +270,10 @@ template <int PROF> static void set_smem_attr() {
         cudaFuncSetAttribute(k_assemble<PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemMax<PROF>::bytes());
         cudaFuncSetAttribute(k_update<PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemMax<PROF>::bytes());
         cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_small_smem());
+        cudaFuncSetAttribute(k_potrf_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_block_smem());
+        cudaFuncSetAttribute(k_trsm_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_block_smem());
+        cudaFuncSetAttribute(k_syrk_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_dmma_smem());
+        cudaFuncSetAttribute(k_back_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)back_block_smem());
         done = true;
     }
 #endif
@@ -324,20 +328,25 @@ static void launch_solve(plba_handle h) {
     for (int w = 0; w < P.n_win; w++) {
         const int n = 6 * h->wins[w].n_free;
         if (n == 0 || h->wins[w].n_pobs + h->wins[w].n_lobs == 0) continue;
-        const int nt = (n + TB - 1) / TB;
-        for (int k = 0; k < nt; k++) {
-            PLBA_LAUNCH(k_potrf_tile, dim3(1), dim3(256), sizeof(double) * (2 * TB * (TB + 1) + TB), h->stream, Pp, w, k, h->invbuf);
-            h->timing.n_launches++;
-            const int m = nt - k - 1;
-            if (m > 0) {
-                PLBA_LAUNCH(k_trsm_tiles, dim3(m), dim3(256), sizeof(double) * 2 * TB * TB, h->stream, Pp, w, k, (const double *)h->invbuf);
-                PLBA_LAUNCH(k_syrk_tiles, dim3(m * (m + 1) / 2), dim3(256), sizeof(double) * 2 * TB * TB, h->stream, Pp, w, k, nt);
+        PLBA_LAUNCH(k_rhs_init, grid1(n, 256), dim3(256), 0, h->stream, Pp, w); h->timing.n_launches++;
+        for (int k0 = 0; k0 < n; k0 += NBK) {
+            const int nb = std::min((int)NBK, n - k0), lo = k0 + nb;
+            PLBA_LAUNCH(k_potrf_block, dim3(1), dim3(256), potrf_block_smem(), h->stream, Pp, w, k0, nb);
+            // columns right of the block + the right-hand side column
+            PLBA_LAUNCH(k_trsm_block, dim3((n - lo + 1 + TRSM_COLS - 1) / TRSM_COLS), dim3(256), trsm_block_smem(), h->stream, Pp, w, k0, nb);
+            h->timing.n_launches += 2;
+            if (lo < n) {
+                PLBA_LAUNCH(k_rhs_update, grid1(n - lo, 256), dim3(256), 0, h->stream, Pp, w, k0, nb);
+                const int T = (n - lo + ST - 1) / ST;
+                PLBA_LAUNCH(k_syrk_dmma, dim3(T * (T + 1) / 2), dim3(256), syrk_dmma_smem(), h->stream, Pp, w, k0, nb, lo);
                 h->timing.n_launches += 2;
             }
         }
-        const int ntd = 1008;   // multiple of TB: G = 21 partial sums per row
-        PLBA_LAUNCH(k_trisolve_large, dim3(1), dim3(ntd), sizeof(double) * (TB + TB * (ntd / TB)), h->stream, Pp, w, nt, (const double *)h->invbuf);
-        h->timing.n_launches++;
+        for (int k0 = ((n - 1) / NBK) * NBK; k0 >= 0; k0 -= NBK) {
+            const int nb = std::min((int)NBK, n - k0);
+            PLBA_LAUNCH(k_back_block, dim3(1), dim3(512), back_block_smem(), h->stream, Pp, w, k0, nb);
+            h->timing.n_launches++;
+        }
     }
     PLBA_LAUNCH(k_pose_update, grid1(P.n_free, 128), dim3(128), 0, h->stream, Pp); h->timing.n_launches++;
 }
@@ -553,7 +562,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     const size_t s_po_lvl = cs.take<unsigned char>(tot.n_pobs), s_lo_lvl = cs.take<unsigned char>(tot.n_lobs);
     const size_t s_sys = cs.take<double>(h->sys_doubles), s_xp = cs.take<double>((size_t)6 * tot.n_free);
     size_t s_inv = 0;
-    if (!h->small_path) { const int nt = (6 * max_nf + TB - 1) / TB; s_inv = cs.take<double>((size_t)nt * TB * TB); }
+    (void)s_inv;
     const int trace_cap = (prof == PLBA_PROFILE_G) ? (opt->iters_stage1 + opt->iters_stage2) * opt->lm_max_trials + 2 : opt->max_iters_lba + 2;
     // output region (one D2H copy)
     h->out_off = cs.off;
@@ -659,7 +668,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     P.S = h->sysbuf; P.gs = P.S + h->S_doubles; P.hpp_diag = P.gs + (size_t)6 * tot.n_free; P.hpp_diag_init = P.hpp_diag + (size_t)6 * tot.n_free;
     P.acc = P.hpp_diag_init + (size_t)6 * tot.n_free; P.accB = P.acc + (size_t)4 * n; P.accmax = P.acc + (size_t)ACC_N * n;
     P.xp = (double *)(db + s_xp);
-    h->invbuf = h->small_path ? nullptr : (double *)(db + s_inv);
+    h->invbuf = nullptr;
     P.ctrl = (WinCtrl *)(db + h->o_ctrl); P.trace = (plba_trace_rec *)(db + h->o_trace); P.trace_cap = trace_cap; P.counters = (int *)(db + h->o_cnt);
     set_all_attrs();
 #ifndef PLBA_HOST_EMU

@@ -14,9 +14,104 @@
 
 namespace plba {
 
-enum { SMALL_NMAX = 144, TB = 48 };
+enum { SMALL_NMAX = 144 };
 
 static inline size_t solve_small_smem() { return sizeof(double) * ((size_t)(SMALL_NMAX + 1) * (SMALL_NMAX + 1) + 2 * SMALL_NMAX + 24 + 16 + 6 * 264 + 21 * (SMALL_NMAX / 6)) + 64; }
+
+// Left-looking Cholesky of a symmetric positive definite matrix held as a LOWER triangle in shared memory (row stride ldm, odd),
+// in panels of one pose block (6 columns).  nd = dimension (multiple of 6); rows nd..nr (if any) are extra rows that ride along
+// (the right-hand side of k_solve_small: L y = g comes for free).  The factored 6x6 diagonal blocks are returned in Lblk (M keeps
+// their un-factored values), 1/L_jj in dinv.  Per panel three phases:
+//  U: every row r >= k0 (row n = right-hand side) accumulates sum_{q<k0} L[r][q] L[k0+c][q] for the panel's 6 columns.  One
+//     thread per (row, half of the q range): its own row is read once per q (stride ldm, odd: conflict-free) and the six
+//     rows k0..k0+5 are BROADCAST loads shared by the whole warp, so the phase is FMA-bound, not shared-memory-bound,
+//     and no trailing matrix is ever re-written;
+//  A: every row folds the partial sums in, the 6x6 diagonal block is factored redundantly in the registers of each row's
+//     thread (no extra barrier), then the row is solved against it.
+//  F: the partial sums are folded into the panel, one thread per entry.
+// Must be called by all 256 threads of the CTA.
+PLBA_D void chol_lower_panels(double *M, int ldm, int nd, int nr, double *dinv, double *Lblk, double *part, int *fail) {
+    const int nf = nd / 6, n = nr;
+for (int kb = 0; kb < nf; kb++) {
+    const int k0 = 6 * kb, m = n - k0 + 1;
+    // the q range of a row is split over as many threads as the 256-thread CTA allows: late panels have few rows but long rows
+    const int mpad = (m + 31) & ~31, nsplit = (mpad <= 32) ? 8 : (mpad <= 64) ? 4 : (mpad <= 128) ? 2 : 1;
+    PHASE_BEGIN
+        const int sp = tid / mpad, rr = tid - sp * mpad;
+        if (k0 > 0 && sp < nsplit && rr < m) {
+            const int r = k0 + rr;
+            const int qs = (k0 + nsplit - 1) / nsplit, q0 = sp * qs, q1 = (q0 + qs < k0) ? q0 + qs : k0;
+            double acc[6] = {0, 0, 0, 0, 0, 0};
+            const double *Mr = M + (size_t)r * ldm, *Mk = M + (size_t)k0 * ldm;
+#pragma unroll 4
+            for (int q = q0; q < q1; q++) {
+                const double v = Mr[q];
+#pragma unroll
+                for (int c = 0; c < 6; c++) acc[c] += v * Mk[(size_t)c * ldm + q];
+            }
+#pragma unroll
+            for (int c = 0; c < 6; c++) part[((size_t)sp * mpad + rr) * 6 + c] = acc[c];
+        }
+    PHASE_END
+    PHASE_BEGIN
+        if (k0 > 0) for (int idx = tid; idx < 6 * m; idx += PLBA_NT) {       // fold the partial sums into the panel, one thread per entry
+            const int rr = idx / 6, c = idx - 6 * rr;
+            double sum = 0.0;
+            for (int sp = 0; sp < nsplit; sp++) sum += part[((size_t)sp * mpad + rr) * 6 + c];
+            M[(size_t)(k0 + rr) * ldm + k0 + c] -= sum;
+        }
+    PHASE_END
+    PHASE_BEGIN
+        const int r = k0 + 6 + tid;              // rows below the diagonal block; thread 0 factors the block even when no row is left
+        if (r <= n || tid == 0) {
+            double L[21], inv[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+#pragma unroll
+                for (int j = 0; j <= i; j++) {
+                    L[i * (i + 1) / 2 + j] = M[(size_t)(k0 + i) * ldm + k0 + j];
+                }
+            }
+            bool bad = false;
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+                double sd = L[j * (j + 1) / 2 + j];
+#pragma unroll
+                for (int k = 0; k < j; k++) sd -= L[j * (j + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+                if (!(sd > 0.0) || !plba_isfinite(sd)) { bad = true; sd = 1.0; }
+                inv[j] = plba_rsqrt(sd);
+                L[j * (j + 1) / 2 + j] = sd * inv[j];
+#pragma unroll
+                for (int i = j + 1; i < 6; i++) {
+                    double v = L[i * (i + 1) / 2 + j];
+#pragma unroll
+                    for (int k = 0; k < j; k++) v -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+                    L[i * (i + 1) / 2 + j] = v * inv[j];
+                }
+            }
+            if (r <= n) {
+                double x[6];
+#pragma unroll
+                for (int c = 0; c < 6; c++) {
+                    double v = M[(size_t)r * ldm + k0 + c];
+#pragma unroll
+                    for (int k = 0; k < c; k++) v -= x[k] * L[c * (c + 1) / 2 + k];
+                    x[c] = v * inv[c];
+                }
+#pragma unroll
+                for (int c = 0; c < 6; c++) M[(size_t)r * ldm + k0 + c] = x[c];
+            }
+            if (tid == 0) {
+                if (bad) *fail = 1;
+#pragma unroll
+                for (int c = 0; c < 6; c++) dinv[k0 + c] = inv[c];
+#pragma unroll
+                for (int i = 0; i < 21; i++) Lblk[kb * 21 + i] = L[i];
+            }
+        }
+    PHASE_END
+}
+}
 
 PLBA_KERNEL void k_solve_small(const DevP *Pp) {
     PLBA_SMEM(raw);
@@ -77,95 +172,9 @@ PLBA_KERNEL void k_solve_small(const DevP *Pp) {
             for (int i = tid; i < n; i += PLBA_NT) P.hpp_diag[(size_t)6 * slot0 + i] = 0.0;
         PHASE_END
     PROF_MARK(44);
-        // Left-looking Cholesky in panels of one pose block (6 columns).  Per panel two phases:
-        //  U: every row r >= k0 (row n = right-hand side) accumulates sum_{q<k0} L[r][q] L[k0+c][q] for the panel's 6 columns.  One
-        //     thread per (row, half of the q range): its own row is read once per q (stride ldm, odd: conflict-free) and the six
-        //     rows k0..k0+5 are BROADCAST loads shared by the whole warp, so the phase is FMA-bound, not shared-memory-bound,
-        //     and no trailing matrix is ever re-written;
-        //  A: every row folds the partial sums in, the 6x6 diagonal block is factored redundantly in the registers of each row's
-        //     thread (no extra barrier), then the row is solved against it.
         double *part = Ls + 24 + 8;               // [nsplit][n+1][6] partial sums of phase U (nsplit * rows <= 256)
         double *Lblk = part + 6 * 264;            // [nf][21] factored diagonal blocks (M keeps their un-factored values)
-        for (int kb = 0; kb < nf; kb++) {
-            const int k0 = 6 * kb, m = n - k0 + 1;
-            // the q range of a row is split over as many threads as the 256-thread CTA allows: late panels have few rows but long rows
-            const int mpad = (m + 31) & ~31, nsplit = (mpad <= 32) ? 8 : (mpad <= 64) ? 4 : (mpad <= 128) ? 2 : 1;
-            PHASE_BEGIN
-                const int sp = tid / mpad, rr = tid - sp * mpad;
-                if (k0 > 0 && sp < nsplit && rr < m) {
-                    const int r = k0 + rr;
-                    const int qs = (k0 + nsplit - 1) / nsplit, q0 = sp * qs, q1 = (q0 + qs < k0) ? q0 + qs : k0;
-                    double acc[6] = {0, 0, 0, 0, 0, 0};
-                    const double *Mr = M + (size_t)r * ldm, *Mk = M + (size_t)k0 * ldm;
-#pragma unroll 4
-                    for (int q = q0; q < q1; q++) {
-                        const double v = Mr[q];
-#pragma unroll
-                        for (int c = 0; c < 6; c++) acc[c] += v * Mk[(size_t)c * ldm + q];
-                    }
-#pragma unroll
-                    for (int c = 0; c < 6; c++) part[((size_t)sp * mpad + rr) * 6 + c] = acc[c];
-                }
-            PHASE_END
-            PROF_MARK(45);
-            PHASE_BEGIN
-                if (k0 > 0) for (int idx = tid; idx < 6 * m; idx += PLBA_NT) {       // fold the partial sums into the panel, one thread per entry
-                    const int rr = idx / 6, c = idx - 6 * rr;
-                    double sum = 0.0;
-                    for (int sp = 0; sp < nsplit; sp++) sum += part[((size_t)sp * mpad + rr) * 6 + c];
-                    M[(size_t)(k0 + rr) * ldm + k0 + c] -= sum;
-                }
-            PHASE_END
-            PROF_MARK(51);
-            PHASE_BEGIN
-                const int r = k0 + 6 + tid;              // rows below the diagonal block
-                if (r <= n) {
-                    double L[21], inv[6];
-#pragma unroll
-                    for (int i = 0; i < 6; i++) {
-#pragma unroll
-                        for (int j = 0; j <= i; j++) {
-                            L[i * (i + 1) / 2 + j] = M[(size_t)(k0 + i) * ldm + k0 + j];
-                        }
-                    }
-                    bool bad = false;
-#pragma unroll
-                    for (int j = 0; j < 6; j++) {
-                        double sd = L[j * (j + 1) / 2 + j];
-#pragma unroll
-                        for (int k = 0; k < j; k++) sd -= L[j * (j + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
-                        if (!(sd > 0.0) || !plba_isfinite(sd)) { bad = true; sd = 1.0; }
-                        inv[j] = plba_rsqrt(sd);
-                        L[j * (j + 1) / 2 + j] = sd * inv[j];
-#pragma unroll
-                        for (int i = j + 1; i < 6; i++) {
-                            double v = L[i * (i + 1) / 2 + j];
-#pragma unroll
-                            for (int k = 0; k < j; k++) v -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
-                            L[i * (i + 1) / 2 + j] = v * inv[j];
-                        }
-                    }
-                    double x[6];
-#pragma unroll
-                    for (int c = 0; c < 6; c++) {
-                        double v = M[(size_t)r * ldm + k0 + c];
-#pragma unroll
-                        for (int k = 0; k < c; k++) v -= x[k] * L[c * (c + 1) / 2 + k];
-                        x[c] = v * inv[c];
-                    }
-#pragma unroll
-                    for (int c = 0; c < 6; c++) M[(size_t)r * ldm + k0 + c] = x[c];
-                    if (tid == 0) {
-                        if (bad) flag[1] = 1;
-#pragma unroll
-                        for (int c = 0; c < 6; c++) dinv[k0 + c] = inv[c];
-#pragma unroll
-                        for (int i = 0; i < 21; i++) Lblk[kb * 21 + i] = L[i];
-                    }
-                }
-            PHASE_END
-            PROF_MARK(46);
-        }
+        chol_lower_panels(M, ldm, n, n, dinv, Lblk, part, flag + 1);
         // backward substitution L^T x = y, y = row n; column-oriented so that every step reads rows of L
         for (int kb = nf - 1; kb >= 0; kb--) {
             const int k0 = 6 * kb;
@@ -212,177 +221,291 @@ PLBA_KERNEL void k_solve_small(const DevP *Pp) {
     }
 }
 
-// ---- tiled path -----------------------------------------------------------------------------------------------
-// Factor the diagonal tile k (damping added here: later tiles only receive additive updates) and store inv(U_kk).
-PLBA_KERNEL void k_potrf_tile(const DevP *Pp, int w, int k, double *invbuf) {
+// ---- tiled path (6 Nkf > 144: BASELINE configs 4-5) ---------------------------------------------------------------------
+// Right-looking block Cholesky S = U^T U on the dense upper-triangular storage in HBM, factor block NBK = 96 (16 pose blocks):
+//   k_potrf_block : diagonal block (k0,k0) -> shared memory, panel Cholesky above, U_kk written back
+//   k_trsm_block  : U_kj = U_kk^-T A_kj for every column right of the block, and y_k = U_kk^-T g_k; one thread per column,
+//                   six accumulators per thread against broadcast rows of U_kk^T (same inner loop as the panel update)
+//   k_rhs_update  : g_j -= U_kj^T y_k  (the right-hand side rides along the factorisation: forward substitution for free)
+//   k_syrk_dmma   : trailing update A_ij -= U_ki^T U_kj on 128 x 128 tiles with FP64 tensor-core MMAs
+//                   (mma.sync.m8n8k4.f64: the only dense contraction of the path — north star: "FP64 DMMA only for the dense
+//                   reduced-camera-system Cholesky"); K = 96 streamed through shared memory in cp.async double-buffered chunks of 32
+//   k_back_block  : backward substitution U x = y, one block row at a time
+enum { NBK = 96, ST = 128 /* SYRK tile */, SKC = 32 /* K chunk */, SLD = ST + 4 /* row stride: fragment loads conflict-free */ };
+
+static inline size_t potrf_block_smem() { return sizeof(double) * ((size_t)NBK * (NBK + 1) + NBK + 21 * (NBK / 6) + 6 * 264 + 16); }
+PLBA_KERNEL void k_potrf_block(const DevP *Pp, int w, int k0, int nb) {
     PLBA_SMEM(raw);
     PLBA_PARAMS(P, Pp);
     WinCtrl &ctl = P.ctrl[w];
-    const int n = 6 * P.win_nfree[w], slot0 = P.win_slot0[w];
+    const int n = 6 * P.win_nfree[w], slot0 = P.win_slot0[w], ldm = nb + 1;
     double *Sw = P.S + P.win_S_off[w];
-    const int k0 = k * TB, tb = (n - k0 < TB) ? n - k0 : TB;
-    double *M = (double *)raw;                 // tb x (TB+1), holds U (upper) row-major
-    double *Inv = M + TB * (TB + 1);
-    double *dgt = Inv + TB * (TB + 1);         // diagonal of U (kept apart: the pivot row is read by every thread)
-    const int ldm = TB + 1;
+    double *M = (double *)raw, *dinv = M + (size_t)NBK * (NBK + 1), *Lblk = dinv + NBK, *part = Lblk + 21 * (NBK / 6);
+    int *fail = (int *)(part + 6 * 264);
     PHASE_BEGIN
-        for (int idx = tid; idx < tb * tb; idx += PLBA_NT) {
-            const int r = idx / tb, c = idx % tb;
-            double v = 0.0;
-            if (c >= r) {
-                v = Sw[(size_t)(k0 + r) * n + k0 + c];
-                if (r == c) v += (P.profile == PLBA_PROFILE_G) ? ctl.lambda : ctl.lambda * P.hpp_diag[(size_t)6 * slot0 + k0 + r];
-            }
-            M[r * ldm + c] = v; Inv[r * ldm + c] = 0.0;
+        if (tid == 0) *fail = 0;
+        for (int idx = tid; idx < nb * nb; idx += PLBA_NT) {
+            const int r = idx / nb, c = idx - r * nb;
+            if (c < r) continue;
+            double v = Sw[(size_t)(k0 + r) * n + k0 + c];
+            if (r == c) v += (P.profile == PLBA_PROFILE_G) ? ctl.lambda : ctl.lambda * P.hpp_diag[(size_t)6 * slot0 + k0 + r];
+            M[(size_t)c * ldm + r] = v;                 // lower (c,r)
         }
     PHASE_END
-    for (int q = 0; q < tb; q++) {             // row-oriented Cholesky of the upper triangle: U^T U
+    chol_lower_panels(M, ldm, nb, nb - 1, dinv, Lblk, part, fail);
+    PHASE_BEGIN
+        for (int idx = tid; idx < nb * nb; idx += PLBA_NT) {
+            const int r = idx / nb, c = idx - r * nb;     // U[r][c] = L[c][r], c >= r
+            if (c < r) continue;
+            double v;
+            if (c / 6 == r / 6) { const int kb = r / 6, i = c - 6 * kb, j = r - 6 * kb; v = Lblk[kb * 21 + i * (i + 1) / 2 + j]; }
+            else v = M[(size_t)c * ldm + r];
+            Sw[(size_t)(k0 + r) * n + k0 + c] = v;
+        }
+        if (tid == 0 && *fail) ctl.solve_fail = 1;
+    PHASE_END
+}
+
+// columns k0+nb .. n-1 of block row k, plus the right-hand side as one more column (handled by the last CTA)
+enum { TRSM_COLS = 128 };
+static inline size_t trsm_block_smem() { return sizeof(double) * ((size_t)NBK * (NBK + 1) + (size_t)NBK * (TRSM_COLS + 1) + NBK); }
+PLBA_KERNEL void k_trsm_block(const DevP *Pp, int w, int k0, int nb) {
+    PLBA_SMEM(raw);
+    PLBA_PARAMS(P, Pp);
+    const int n = 6 * P.win_nfree[w], slot0 = P.win_slot0[w], ldl = nb + 1, ldx = TRSM_COLS + 1;
+    double *Sw = P.S + P.win_S_off[w];
+    double *Lk = (double *)raw, *X = Lk + (size_t)NBK * (NBK + 1), *Dk = X + (size_t)NBK * (TRSM_COLS + 1);      // Lk = U_kk^T (lower), X = the CTA's columns, Dk = 1 / diag
+    const int c0 = k0 + nb + PLBA_BID * TRSM_COLS;                     // first column of this CTA; column index n = right-hand side
+    double *g = P.xp + (size_t)6 * slot0;                              // y is built in xp (copied from gs by the first block)
+    PHASE_BEGIN
+        for (int idx = tid; idx < nb * nb; idx += PLBA_NT) {
+            const int r = idx / nb, c = idx - r * nb;
+            if (c >= r) { const double v = Sw[(size_t)(k0 + r) * n + k0 + c]; Lk[(size_t)c * ldl + r] = v; if (c == r) Dk[r] = 1.0 / v; }
+        }
+        for (int idx = tid; idx < nb * TRSM_COLS; idx += PLBA_NT) {
+            const int r = idx / TRSM_COLS, cc = idx - r * TRSM_COLS, c = c0 + cc;
+            X[(size_t)r * ldx + cc] = (c < n) ? Sw[(size_t)(k0 + r) * n + c] : (c == n ? g[k0 + r] : 0.0);
+        }
+    PHASE_END
+    // forward substitution L X = A in panels of 6 rows: (1) all 256 threads subtract the contribution of the rows already
+    // solved (thread = column x half of the panel's rows, three accumulators against broadcast rows of L), (2) one thread per
+    // column solves the 6 x 6 triangle
+    for (int p0 = 0; p0 < nb; p0 += 6) {
         PHASE_BEGIN
-            const double p = M[q * ldm + q];
-            const bool bad = !(p > 0.0) || !plba_isfinite(p);
-            const double d = bad ? 1.0 : sqrt(p);
-            if (tid == 0) { dgt[q] = d; if (bad) ctl.solve_fail = 1; }
-            for (int c = q + 1 + tid; c < tb; c += PLBA_NT) M[q * ldm + c] /= d;
+            const int cc = tid & (TRSM_COLS - 1), hf = tid >> 7;
+            if (p0 > 0 && c0 + cc <= n) {
+                double acc[3] = {0, 0, 0};
+                const double *L0 = Lk + (size_t)(p0 + 3 * hf) * ldl;
+#pragma unroll 4
+                for (int q = 0; q < p0; q++) {
+                    const double v = X[(size_t)q * ldx + cc];
+                    acc[0] += v * L0[q]; acc[1] += v * L0[ldl + q]; acc[2] += v * L0[2 * ldl + q];
+                }
+#pragma unroll
+                for (int c = 0; c < 3; c++) X[(size_t)(p0 + 3 * hf + c) * ldx + cc] -= acc[c];
+            }
         PHASE_END
         PHASE_BEGIN
-            const int ti = tid >> 4, tj = tid & 15;
-            for (int r = q + 1 + ti; r < tb; r += PLBA_NT >> 4) {
-                const double uqr = M[q * ldm + r];
-                for (int c = r + tj; c < tb; c += 16) M[r * ldm + c] -= uqr * M[q * ldm + c];
+            if (tid < TRSM_COLS && c0 + tid <= n) {
+                const int cc = tid;
+                double x[6];
+#pragma unroll
+                for (int c = 0; c < 6; c++) {
+                    double v = X[(size_t)(p0 + c) * ldx + cc];
+#pragma unroll
+                    for (int k = 0; k < c; k++) v -= x[k] * Lk[(size_t)(p0 + c) * ldl + p0 + k];
+                    x[c] = v * Dk[p0 + c];
+                }
+#pragma unroll
+                for (int c = 0; c < 6; c++) X[(size_t)(p0 + c) * ldx + cc] = x[c];
             }
         PHASE_END
     }
-    // inverse of the upper-triangular tile, column by column: U X = I
     PHASE_BEGIN
-        if (tid < tb) {
-            const int c = tid;
-            for (int r = c; r >= 0; r--) {
-                double s = (r == c) ? 1.0 : 0.0;
-                for (int m = r + 1; m <= c; m++) s -= M[r * ldm + m] * Inv[m * ldm + c];
-                Inv[r * ldm + c] = s / dgt[r];
-            }
-        }
-    PHASE_END
-    PHASE_BEGIN
-        for (int idx = tid; idx < tb * tb; idx += PLBA_NT) {
-            const int r = idx / tb, c = idx % tb;
-            if (c >= r) Sw[(size_t)(k0 + r) * n + k0 + c] = (c == r) ? dgt[r] : M[r * ldm + c];
-            invbuf[(size_t)k * TB * TB + r * TB + c] = (c >= r) ? Inv[r * ldm + c] : 0.0;
+        for (int idx = tid; idx < nb * TRSM_COLS; idx += PLBA_NT) {
+            const int r = idx / TRSM_COLS, cc = idx - r * TRSM_COLS, c = c0 + cc;
+            if (c < n) Sw[(size_t)(k0 + r) * n + c] = X[(size_t)r * ldx + cc];
+            else if (c == n) g[k0 + r] = X[(size_t)r * ldx + cc];
         }
     PHASE_END
 }
 
-// U_kj = inv(U_kk)^T A_kj for every tile j > k  (one CTA per tile)
-PLBA_KERNEL void k_trsm_tiles(const DevP *Pp, int w, int k, const double *invbuf) {
-    PLBA_SMEM(raw);
+// g_j -= sum_r U[k0+r][j] y[k0+r]   for every column j right of the block
+PLBA_KERNEL void k_rhs_update(const DevP *Pp, int w, int k0, int nb) {
     PLBA_PARAMS(P, Pp);
-    const int n = 6 * P.win_nfree[w];
-    double *Sw = P.S + P.win_S_off[w];
-    const int j = k + 1 + PLBA_BID;
-    const int k0 = k * TB, tbk = (n - k0 < TB) ? n - k0 : TB;
-    const int j0 = j * TB, tbj = (n - j0 < TB) ? n - j0 : TB;
-    double *Inv = (double *)raw, *Aj = Inv + TB * TB;     // Inv[q][r], Aj[q][c]
-    PHASE_BEGIN
-        for (int idx = tid; idx < TB * TB; idx += PLBA_NT) {
-            const int q = idx / TB, c = idx % TB;
-            Inv[idx] = (q < tbk && c < tbk) ? invbuf[(size_t)k * TB * TB + idx] : 0.0;
-            Aj[idx] = (q < tbk && c < tbj) ? Sw[(size_t)(k0 + q) * n + j0 + c] : 0.0;
-        }
-    PHASE_END
-    PHASE_BEGIN
-        const int ty = tid >> 4, tx = tid & 15;
-        double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-        for (int q = 0; q < tbk; q++) {
-            double a[3], bb[3];
-            for (int u = 0; u < 3; u++) { a[u] = Inv[q * TB + ty * 3 + u]; bb[u] = Aj[q * TB + tx * 3 + u]; }   // (Inv^T)[r][q] = Inv[q][r]
-            for (int u = 0; u < 3; u++) for (int v = 0; v < 3; v++) acc[u][v] += a[u] * bb[v];
-        }
-        for (int u = 0; u < 3; u++) for (int v = 0; v < 3; v++) {
-            const int r = ty * 3 + u, c = tx * 3 + v;
-            if (r < tbk && c < tbj) Sw[(size_t)(k0 + r) * n + j0 + c] = acc[u][v];
-        }
-    PHASE_END
-}
-
-// A_ij -= U_ki^T U_kj for k < i <= j  (one CTA per tile pair; grid.x enumerates the upper-triangular pairs)
-PLBA_KERNEL void k_syrk_tiles(const DevP *Pp, int w, int k, int nt) {
-    PLBA_SMEM(raw);
-    PLBA_PARAMS(P, Pp);
-    const int n = 6 * P.win_nfree[w];
-    double *Sw = P.S + P.win_S_off[w];
-    const int m = nt - k - 1;
-    int p = PLBA_BID, a = 0;
-    while (p >= m - a) { p -= m - a; a++; }
-    const int i = k + 1 + a, j = i + p;
-    const int k0 = k * TB, tbk = (n - k0 < TB) ? n - k0 : TB;
-    const int i0 = i * TB, tbi = (n - i0 < TB) ? n - i0 : TB;
-    const int j0 = j * TB, tbj = (n - j0 < TB) ? n - j0 : TB;
-    double *Ui = (double *)raw, *Uj = Ui + TB * TB;
-    PHASE_BEGIN
-        for (int idx = tid; idx < TB * TB; idx += PLBA_NT) {
-            const int q = idx / TB, c = idx % TB;
-            Ui[idx] = (q < tbk && c < tbi) ? Sw[(size_t)(k0 + q) * n + i0 + c] : 0.0;
-            Uj[idx] = (q < tbk && c < tbj) ? Sw[(size_t)(k0 + q) * n + j0 + c] : 0.0;
-        }
-    PHASE_END
-    PHASE_BEGIN
-        const int ty = tid >> 4, tx = tid & 15;
-        double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-        for (int q = 0; q < tbk; q++) {
-            double av[3], bv[3];
-            for (int u = 0; u < 3; u++) { av[u] = Ui[q * TB + ty * 3 + u]; bv[u] = Uj[q * TB + tx * 3 + u]; }
-            for (int u = 0; u < 3; u++) for (int v = 0; v < 3; v++) acc[u][v] += av[u] * bv[v];
-        }
-        for (int u = 0; u < 3; u++) for (int v = 0; v < 3; v++) {
-            const int r = ty * 3 + u, c = tx * 3 + v;
-            if (r < tbi && c < tbj && (i != j || c >= r)) Sw[(size_t)(i0 + r) * n + j0 + c] -= acc[u][v];
-        }
-    PHASE_END
-}
-
-// U^T y = g ; U x = y with the stored inverse diagonal tiles (single CTA, 1024 threads)
-PLBA_KERNEL void k_trisolve_large(const DevP *Pp, int w, int nt, const double *invbuf) {
-    PLBA_SMEM(raw);
-    PLBA_PARAMS(P, Pp);
-    WinCtrl &ctl = P.ctrl[w];
     const int n = 6 * P.win_nfree[w], slot0 = P.win_slot0[w];
     const double *Sw = P.S + P.win_S_off[w];
-    double *g = P.xp + (size_t)6 * slot0;       // solved in place in xp
-    double *yt = (double *)raw, *part = yt + TB;   // part[TB][G]
-    const int G = PLBA_NT / TB;
+    double *g = P.xp + (size_t)6 * slot0;
     PHASE_BEGIN
-        for (int i = tid; i < n; i += PLBA_NT) g[i] = P.gs[(size_t)6 * slot0 + i];
+        for (int j = k0 + nb + PLBA_BID * PLBA_NT + tid; j < n; j += PLBA_NB * PLBA_NT) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;          // nb is a multiple of 6: three independent chains, loads issued ahead
+#pragma unroll 2
+            for (int r = 0; r < nb; r += 3) {
+                s0 += Sw[(size_t)(k0 + r) * n + j] * g[k0 + r]; s1 += Sw[(size_t)(k0 + r + 1) * n + j] * g[k0 + r + 1]; s2 += Sw[(size_t)(k0 + r + 2) * n + j] * g[k0 + r + 2];
+            }
+            g[j] -= (s0 + s1) + s2;
+        }
     PHASE_END
-    for (int k = 0; k < nt; k++) {
-        const int k0 = k * TB, tb = (n - k0 < TB) ? n - k0 : TB;
-        const double *Inv = invbuf + (size_t)k * TB * TB;
-        PHASE_BEGIN
-            if (tid < tb) { double s = 0; for (int q = 0; q <= tid; q++) s += Inv[q * TB + tid] * g[k0 + q]; yt[tid] = s; }
-        PHASE_END
-        PHASE_BEGIN
-            if (tid < tb) g[k0 + tid] = yt[tid];
-            for (int j = k0 + tb + tid; j < n; j += PLBA_NT) {
-                double s = 0; for (int r = 0; r < tb; r++) s += Sw[(size_t)(k0 + r) * n + j] * yt[r];
-                g[j] -= s;
+}
+PLBA_KERNEL void k_rhs_init(const DevP *Pp, int w) {
+    PLBA_PARAMS(P, Pp);
+    const int n = 6 * P.win_nfree[w], slot0 = P.win_slot0[w];
+    PHASE_BEGIN
+        for (int i = PLBA_BID * PLBA_NT + tid; i < n; i += PLBA_NB * PLBA_NT) P.xp[(size_t)6 * slot0 + i] = P.gs[(size_t)6 * slot0 + i];
+    PHASE_END
+}
+
+#ifndef PLBA_HOST_EMU
+PLBA_D void plba_dmma(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+PLBA_D void plba_cp_async16(void *smem_dst, const void *gsrc, bool valid) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 16 : 0;                    // src-size 0: the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
+}
+PLBA_D void plba_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> PLBA_D void plba_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
+
+static inline size_t syrk_dmma_smem() { return sizeof(double) * (size_t)(2 * 2 * SKC * SLD); }
+// A_ij -= U_ki^T U_kj for the trailing tiles (ti <= tj) of step k; lo = first trailing row / column
+PLBA_KERNEL void PLBA_BOUNDS(256, 1) k_syrk_dmma(const DevP *Pp, int w, int k0, int nb, int lo) {
+    PLBA_SMEM(raw);
+    PLBA_PARAMS(P, Pp);
+    const int n = 6 * P.win_nfree[w];
+    double *Sw = P.S + P.win_S_off[w];
+    const int T = (n - lo + ST - 1) / ST;
+    int p = PLBA_BID, ti = 0;
+    while (p >= T - ti) { p -= T - ti; ti++; }
+    const int tj = ti + p;
+    const int i0 = lo + ti * ST, j0 = lo + tj * ST;
+#ifdef PLBA_HOST_EMU
+    (void)raw;
+    PHASE_BEGIN     // plain loops on the host (the MMA fragments exist only on the GPU)
+        for (int idx = tid; idx < ST * ST; idx += PLBA_NT) {
+            const int r = i0 + idx / ST, c = j0 + idx % ST;
+            if (r >= n || c >= n || c < r) continue;
+            double sum = 0.0;
+            for (int q = 0; q < nb; q++) sum += Sw[(size_t)(k0 + q) * n + r] * Sw[(size_t)(k0 + q) * n + c];
+            Sw[(size_t)r * n + c] -= sum;
+        }
+    PHASE_END
+#else
+    double *As = (double *)raw, *Bs = As + 2 * SKC * SLD;     // [2 stages][SKC][SLD] each
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 1, wn = warp >> 1;                   // 2 x 4 warps: 64 x 32 per warp
+    const bool diag = (ti == tj);
+    double acc[8][4][2];
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+    const int nchunk = (nb + SKC - 1) / SKC;
+    auto load_chunk = [&](int ch, int stage) {
+        // SKC rows x 128 doubles per operand = 2048 x 16-byte copies; 256 threads -> 8 each per operand
+        for (int it = 0; it < 8; it++) {
+            const int e = tid + it * 256, r = e >> 6, c2 = (e & 63) * 2;
+            const int kr = ch * SKC + r;
+            const bool okr = kr < nb;
+            const size_t row = (size_t)(k0 + (okr ? kr : 0)) * n;
+            { const int c = i0 + c2; const bool ok = okr && c < n; plba_cp_async16(As + (size_t)(stage * SKC + r) * SLD + c2, Sw + row + (ok ? c : 0), ok); }
+            if (!diag) { const int c = j0 + c2; const bool ok = okr && c < n; plba_cp_async16(Bs + (size_t)(stage * SKC + r) * SLD + c2, Sw + row + (ok ? c : 0), ok); }
+        }
+        plba_cp_async_commit();
+    };
+    load_chunk(0, 0);
+    for (int ch = 0; ch < nchunk; ch++) {
+        const int stage = ch & 1;
+        if (ch + 1 < nchunk) { load_chunk(ch + 1, stage ^ 1); plba_cp_async_wait<1>(); } else plba_cp_async_wait<0>();
+        __syncthreads();
+        const double *Ac = As + (size_t)stage * SKC * SLD, *Bc = diag ? Ac : Bs + (size_t)stage * SKC * SLD;
+#pragma unroll
+        for (int kk = 0; kk < SKC; kk += 4) {
+            double af[8], bf[4];
+            const double *ar = Ac + (size_t)(kk + (lane & 3)) * SLD + wm * 64 + (lane >> 2);
+            const double *br = Bc + (size_t)(kk + (lane & 3)) * SLD + wn * 32 + (lane >> 2);
+#pragma unroll
+            for (int a = 0; a < 8; a++) af[a] = ar[a * 8];
+#pragma unroll
+            for (int b = 0; b < 4; b++) bf[b] = br[b * 8];
+#pragma unroll
+            for (int a = 0; a < 8; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) plba_dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+        const int r = i0 + wm * 64 + a * 8 + (lane >> 2);
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int c = j0 + wn * 32 + b * 8 + 2 * (lane & 3);
+            if (r < n && c + 1 < n && c >= r) {
+                plba_d2 *dst = (plba_d2 *)(Sw + (size_t)r * n + c);
+                plba_d2 v = *dst; v.x -= acc[a][b][0]; v.y -= acc[a][b][1]; *dst = v;
+            } else if (r < n) {
+                if (c < n && c >= r) Sw[(size_t)r * n + c] -= acc[a][b][0];
+                if (c + 1 < n && c + 1 >= r) Sw[(size_t)r * n + c + 1] -= acc[a][b][1];
+            }
+        }
+    }
+#endif
+}
+
+// backward substitution U x = y for block row k (blocks are visited last to first; x overwrites y in xp)
+static inline size_t back_block_smem() { return sizeof(double) * ((size_t)NBK * (NBK + 1) + (size_t)NBK * 33 + 2 * NBK); }
+PLBA_KERNEL void k_back_block(const DevP *Pp, int w, int k0, int nb) {
+    PLBA_SMEM(raw);
+    PLBA_PARAMS(P, Pp);
+    WinCtrl &ctl = P.ctrl[w];
+    const int n = 6 * P.win_nfree[w], slot0 = P.win_slot0[w], ldu = nb + 1;
+    const double *Sw = P.S + P.win_S_off[w];
+    double *x = P.xp + (size_t)6 * slot0;
+    double *Uk = (double *)raw, *part = Uk + (size_t)NBK * (NBK + 1), *yk = part + (size_t)NBK * 33;
+    PHASE_BEGIN
+        for (int idx = tid; idx < nb * nb; idx += PLBA_NT) {
+            const int r = idx / nb, c = idx - r * nb;
+            if (c >= r) Uk[(size_t)r * ldu + c] = Sw[(size_t)(k0 + r) * n + k0 + c];
+        }
+        // partial dot products of row r with the already solved x_j, j right of the block: 32 lanes per row, coalesced
+        const int lane = tid & 31, wrp = tid >> 5, nw = PLBA_NT >> 5;
+        for (int r = wrp; r < nb; r += nw) {
+            double sum = 0.0;
+            const double *row = Sw + (size_t)(k0 + r) * n;
+            for (int j = k0 + nb + lane; j < n; j += 32) sum += row[j] * x[j];
+            part[(size_t)r * 33 + lane] = sum;
+        }
+    PHASE_END
+    PHASE_BEGIN
+        if (tid < nb) { double sum = x[k0 + tid]; for (int l = 0; l < 32; l++) sum -= part[(size_t)tid * 33 + l]; yk[tid] = sum; }
+    PHASE_END
+    for (int p0 = nb - 6; p0 >= 0; p0 -= 6) {   // back substitution in panels of 6: every thread solves the 6 x 6 triangle redundantly,
+        PHASE_BEGIN                             // thread t < p0 then removes the panel from its own y[t] (reads a row segment of U)
+            if (tid <= p0) {
+                double xs[6];
+#pragma unroll
+                for (int c = 5; c >= 0; c--) {
+                    double v = yk[p0 + c];
+#pragma unroll
+                    for (int m = c + 1; m < 6; m++) v -= Uk[(size_t)(p0 + c) * ldu + p0 + m] * xs[m];
+                    xs[c] = v / Uk[(size_t)(p0 + c) * ldu + p0 + c];
+                }
+                if (tid < p0) {
+                    double y = yk[tid];
+#pragma unroll
+                    for (int c = 0; c < 6; c++) y -= Uk[(size_t)tid * ldu + p0 + c] * xs[c];
+                    yk[tid] = y;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 6; c++) yk[NBK + p0 + c] = xs[c];
+                }
             }
         PHASE_END
     }
-    for (int k = nt - 1; k >= 0; k--) {
-        const int k0 = k * TB, tb = (n - k0 < TB) ? n - k0 : TB;
-        const double *Inv = invbuf + (size_t)k * TB * TB;
-        PHASE_BEGIN
-            const int r = tid / G, q = tid % G;
-            if (r < tb) { double s = 0; for (int j = k0 + tb + q; j < n; j += G) s += Sw[(size_t)(k0 + r) * n + j] * g[j]; part[r * G + q] = s; }
-        PHASE_END
-        PHASE_BEGIN
-            if (tid < tb) { double s = g[k0 + tid]; for (int q = 0; q < G; q++) s -= part[tid * G + q]; yt[tid] = s; }
-        PHASE_END
-        PHASE_BEGIN
-            if (tid < tb) { double s = 0; for (int q = tid; q < tb; q++) s += Inv[tid * TB + q] * yt[q]; g[k0 + tid] = s; }
-        PHASE_END
-    }
     PHASE_BEGIN
-        if (ctl.solve_fail) for (int i = tid; i < n; i += PLBA_NT) g[i] = 0.0;
+        if (tid < nb) x[k0 + tid] = ctl.solve_fail ? 0.0 : yk[NBK + tid];
     PHASE_END
 }
 
