@@ -121,6 +121,14 @@ def _peak():
         return 6650.0, "fallback 6650 GB/s"
 
 
+def _traffic(workload):
+    """Measured DRAM bytes per k_assemble launch from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        return int(json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[workload]["k_assemble"])
+    except Exception:
+        return None
+
+
 def largest_config_roofline(s, abi, scene, args):
     """Assembly kernel on BASELINE config 5 (2 000 KFs, 2M points, 500k lines; inputs 0.45 GB >> L2, so every launch is cold)."""
     P5 = scene.make_scene(5)
@@ -131,7 +139,7 @@ def largest_config_roofline(s, abi, scene, args):
     peak, src = _peak()
     return {"workload": "C5: %d free KFs, %d points, %d lines, %d+%d observations" % (P5.n_free, P5.n_pt, P5.n_ls, P5.n_pobs, P5.n_lobs),
             "kernel": "k_assemble", "bound": "hbm", "algorithmic_bytes": A, "ms_per_launch": ms_a, "achieved": A / (ms_a * 1e-3) / 1e9, "peak": peak,
-            "peak_source": src, "unit": "GB/s", "frac": A / (ms_a * 1e-3) / 1e9 / peak, "algorithmic_flops": F, "achieved_fp64_tflops": F / (ms_a * 1e-3) / 1e12,
+            "peak_source": src, "unit": "GB/s", "frac": A / (ms_a * 1e-3) / 1e9 / peak, "traffic": _traffic("C5"), "algorithmic_flops": F, "achieved_fp64_tflops": F / (ms_a * 1e-3) / 1e12,
             "update_kernel_ms_per_launch": ms_u, "nnzb_S": st["nnzb_S"], "launches_timed": 5,
             "note": "FP64 work (about %.1f GFLOP) bounds this kernel before HBM does: at the 37 TFLOP/s vector peak it needs %.0f us, the HBM roofline %.0f us" % (F / 1e9, F / 37e12 * 1e6, A / (peak * 1e9) * 1e6)}
 
@@ -280,7 +288,7 @@ def main():
                 "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "kernel": "k_assemble (one launch per LM trial: points + lines)", "achieved": A / (asm_ms * 1e-3) / 1e9 if asm_ms > 0 else None,
                              "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": (A / (asm_ms * 1e-3) / 1e9 / peak) if asm_ms > 0 else None,
-                             "traffic": None, "algorithmic_bytes": A, "ms_per_launch": asm_ms, "launches_timed": int(n_asm),
+                             "traffic": _traffic(args.workload) if args.profile == "G" else None, "algorithmic_bytes": A, "ms_per_launch": asm_ms, "launches_timed": int(n_asm),
                              "stage_ms_per_step": {"assemble": t_asm / det_steps, "solve": t_sol / det_steps, "update": t_upd / det_steps},
                              "how": "CUDA events around each stage in a host-driven replay of the same steps (the headline steps run as one CUDA graph)"}}
         line.update(extras)
