@@ -52,7 +52,7 @@ struct plba_handle_s {
     plba_options opt{};
     std::vector<WinInfo> wins;
     std::vector<int> pt_perm, ls_perm, po_perm, lo_perm;    // internal index -> caller's (global, window-offset) index
-    int ls_dim = 4, max_nf = 0;
+    int ls_dim = 4, max_nf = 0, solve_class = 1;
     bool uploaded = false, small_path = true;
     double *sysbuf = nullptr; size_t sys_doubles = 0, S_doubles = 0;
     double *invbuf = nullptr;
@@ -64,9 +64,9 @@ struct plba_handle_s {
     bool detail_timing = false, no_graph = false;
     int grid_chunks = 296, grid_solve = 148;
 #ifndef PLBA_HOST_EMU
-    cudaGraph_t graph[3] = {nullptr, nullptr, nullptr};
-    cudaGraphExec_t gexec[3] = {nullptr, nullptr, nullptr};
-    cudaGraphConditionalHandle cond_while[3]{}, cond_prep[3]{};
+    cudaGraph_t graph[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};       // [profile * 2 + size class of the reduced system]
+    cudaGraphExec_t gexec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaGraphConditionalHandle cond_while[6]{}, cond_prep[6]{};
 #endif
     void release() {
         if (d_arena) cudaFree(d_arena);
@@ -244,7 +244,7 @@ void plba_destroy(plba_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
 #ifndef PLBA_HOST_EMU
-    for (int i = 0; i < 3; i++) { if (h->gexec[i]) cudaGraphExecDestroy(h->gexec[i]); if (h->graph[i]) cudaGraphDestroy(h->graph[i]); }
+    for (int i = 0; i < 6; i++) { if (h->gexec[i]) cudaGraphExecDestroy(h->gexec[i]); if (h->graph[i]) cudaGraphDestroy(h->graph[i]); }
 #endif
     h->release();
     if (h->d_P) cudaFree(h->d_P);
@@ -269,7 +269,7 @@ template <int PROF> static void set_smem_attr() {
     if (!done) {
         cudaFuncSetAttribute(k_assemble<PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemMax<PROF>::bytes());
         cudaFuncSetAttribute(k_update<PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemMax<PROF>::bytes());
-        cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_small_smem());
+        cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_small_smem(1));
         cudaFuncSetAttribute(k_potrf_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_block_smem());
         cudaFuncSetAttribute(k_trsm_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_block_smem());
         cudaFuncSetAttribute(k_syrk_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_dmma_smem());
@@ -320,7 +320,7 @@ static void launch_solve(plba_handle h) {
     const DevP &P = h->P; const DevP *Pp = h->d_P;
     if (P.n_free == 0) return;
     if (h->small_path) {
-        PLBA_LAUNCH(k_solve_small, dim3(h->grid_solve), dim3(256), solve_small_smem(), h->stream, Pp);
+        PLBA_LAUNCH(k_solve_small, dim3(h->grid_solve), dim3(256), solve_small_smem(h->solve_class), h->stream, Pp);
         h->timing.n_launches++;
         return;
     }
@@ -376,7 +376,7 @@ static cudaError_t add_kernel(cudaGraph_t g, cudaGraphNode_t *node, cudaGraphNod
     return cudaGraphAddKernelNode(node, g, dep ? &dep : nullptr, dep ? 1 : 0, &kp);
 }
 template <int PROF> static int build_graph(plba_handle h) {
-    const int pi = PROF;
+    const int pi = PROF * 2 + h->solve_class;
     if (h->gexec[pi]) return PLBA_OK;
     set_all_attrs();
     cudaGraph_t g = nullptr;
@@ -402,7 +402,7 @@ template <int PROF> static int build_graph(plba_handle h) {
     CK(add_kernel(prep, &n2, n1, (void *)k_assemble<PROF>, gc, bc, smc, a_m0));
     CK(add_kernel(prep, &n3, n2, (void *)k_lambda_init, dim3(h->n_sm), dim3(128), 0, a_p));
     CK(add_kernel(body, &m1, inode, (void *)k_assemble<PROF>, gc, bc, smc, a_m1));
-    CK(add_kernel(body, &m2, m1, (void *)k_solve_small, dim3(h->grid_solve), dim3(256), solve_small_smem(), a_p));
+    CK(add_kernel(body, &m2, m1, (void *)k_solve_small, dim3(h->grid_solve), dim3(256), solve_small_smem(h->solve_class), a_p));
     CK(add_kernel(body, &m3, m2, (void *)k_update<PROF>, gc, bc, smc, a_fl));
     CK(cudaGraphInstantiate(&h->gexec[pi], g, 0));
     h->graph[pi] = g;
@@ -457,6 +457,9 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     }
     h->max_nf = max_nf;
     h->small_path = (6 * max_nf <= SMALL_NMAX);
+    h->solve_class = solve_small_class(6 * max_nf);
+    // persistent solver grid: as many CTAs as fit (4 per SM in the small class); fixed per class so that the cached graph stays valid
+    h->grid_solve = h->n_sm * (h->solve_class == 0 ? 4 : 1);
     set_all_attrs();
     h->grid_chunks = h->n_sm * chunk_occupancy_for(prof);
 
@@ -674,7 +677,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
 #ifndef PLBA_HOST_EMU
     if (h->small_path && !h->no_graph) {
         if ((rc = build_graph_for(h, prof))) return rc;
-        P.cond_while = (unsigned long long)h->cond_while[prof]; P.cond_prep = (unsigned long long)h->cond_prep[prof];
+        P.cond_while = (unsigned long long)h->cond_while[prof * 2 + h->solve_class]; P.cond_prep = (unsigned long long)h->cond_prep[prof * 2 + h->solve_class];
     }
 #endif
     *h->h_P = P;
@@ -726,7 +729,7 @@ static int run_async(plba_handle h) {
     h->timing.ms_assemble = h->timing.ms_solve = h->timing.ms_update = 0;
 #ifndef PLBA_HOST_EMU
     if (use_graph(h)) {
-        CK(cudaGraphLaunch(h->gexec[P.profile], st));
+        CK(cudaGraphLaunch(h->gexec[P.profile * 2 + h->solve_class], st));
         return PLBA_OK;
     }
 #endif

@@ -16,7 +16,10 @@ namespace plba {
 
 enum { SMALL_NMAX = 144 };
 
-static inline size_t solve_small_smem() { return sizeof(double) * ((size_t)(SMALL_NMAX + 1) * (SMALL_NMAX + 1) + 2 * SMALL_NMAX + 24 + 16 + 6 * 264 + 21 * (SMALL_NMAX / 6)) + 64; }
+// shared memory of k_solve_small for reduced systems up to nmax unknowns; two size classes (<= 72 and <= 144) so that batches of
+// small windows (BASELINE config 3: n = 60) get four resident CTAs per SM instead of one
+static inline int solve_small_class(int n) { return n <= 72 ? 0 : 1; }
+static inline size_t solve_small_smem(int cls) { const size_t nmax = cls == 0 ? 72 : SMALL_NMAX; return sizeof(double) * ((nmax + 1) * (nmax + 1) + 2 * nmax + 24 + 16 + 6 * 264 + 21 * (nmax / 6)) + 64; }
 
 // Left-looking Cholesky of a symmetric positive definite matrix held as a LOWER triangle in shared memory (row stride ldm, odd),
 // in panels of one pose block (6 columns).  nd = dimension (multiple of 6); rows nd..nr (if any) are extra rows that ride along
