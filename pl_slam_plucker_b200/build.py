@@ -31,7 +31,7 @@ def build(force=False, verbose=False, out=None, defines=()):
         return SO
     target = out or SO
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "39", "-o", target] + ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared", "-diag-suppress", "39", "-o", target] + ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lgomp"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     # the image exports CXX=/opt/gcc/bin/g++ which lacks parts of the toolchain; nvcc must use the system g++

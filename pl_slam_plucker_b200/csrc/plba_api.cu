@@ -52,6 +52,8 @@ struct plba_handle_s {
     plba_options opt{};
     std::vector<WinInfo> wins;
     std::vector<int> pt_perm, ls_perm, po_perm, lo_perm;    // internal index -> caller's (global, window-offset) index
+    std::vector<Chunk> ch_pt, ch_ls; std::vector<Seg> sg_pt, sg_ls; std::vector<int> fp_pt, fp_ls, pt_ptr, ls_ptr;   // upload scratch, capacity re-used
+    std::vector<unsigned char> mark;
     int ls_dim = 4, max_nf = 0, solve_class = 1;
     bool uploaded = false, small_path = true;
     double *sysbuf = nullptr; size_t sys_doubles = 0, S_doubles = 0;
@@ -464,15 +466,22 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     h->grid_chunks = h->n_sm * chunk_occupancy_for(prof);
 
     // ---- index work: signature order, chunks, segments --------------------------------------------------------
-    std::vector<Chunk> ch_pt, ch_ls; std::vector<Seg> sg_pt, sg_ls; std::vector<int> fp_pt, fp_ls;
+    std::vector<Chunk> &ch_pt = h->ch_pt, &ch_ls = h->ch_ls; std::vector<Seg> &sg_pt = h->sg_pt, &sg_ls = h->sg_ls; std::vector<int> &fp_pt = h->fp_pt, &fp_ls = h->fp_ls;
+    ch_pt.clear(); ch_ls.clear(); sg_pt.clear(); sg_ls.clear(); fp_pt.clear(); fp_ls.clear();
     h->pt_perm.resize(tot.n_pt); h->ls_perm.resize(tot.n_ls); h->po_perm.resize(tot.n_pobs); h->lo_perm.resize(tot.n_lobs);
-    std::vector<int> pt_ptr(tot.n_pt + 1, 0), ls_ptr(tot.n_ls + 1, 0);
+    std::vector<int> &pt_ptr = h->pt_ptr, &ls_ptr = h->ls_ptr;
+    pt_ptr.assign(tot.n_pt + 1, 0); ls_ptr.assign(tot.n_ls + 1, 0);
     bool too_long = false;
+    std::vector<ClassLayout> Lps(n), Lls(n);
+#pragma omp parallel for schedule(dynamic, 4) if (n > 8)
+    for (int w = 0; w < n; w++) {
+        const plba_problem &p = probs[w];
+        signature_order(p.n_pt, p.n_pobs, p.po_lm, p.po_kf, true, Lps[w]);
+        signature_order(p.n_ls, p.n_lobs, p.lo_lm, p.lo_kf, prof != PLBA_PROFILE_H_END, Lls[w]);   // Q3 addresses endpoint lines by position
+    }
     for (int w = 0; w < n; w++) {
         const plba_problem &p = probs[w]; const WinInfo &wi = h->wins[w];
-        ClassLayout Lp, Ll;
-        signature_order(p.n_pt, p.n_pobs, p.po_lm, p.po_kf, true, Lp);
-        signature_order(p.n_ls, p.n_lobs, p.lo_lm, p.lo_kf, prof != PLBA_PROFILE_H_END, Ll);   // Q3 addresses endpoint lines by position
+        const ClassLayout &Lp = Lps[w], &Ll = Lls[w];
         for (int cls = 0; cls < 2; cls++) {
             const ClassLayout &L = cls ? Ll : Lp;
             const int nl = cls ? p.n_ls : p.n_pt, lm0 = cls ? wi.ls0 : wi.pt0, ob0 = cls ? wi.lo0 : wi.po0;
@@ -517,7 +526,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     {   // layout statistics (plba_layout_stats): structural non-zero 6x6 blocks of S = union over segments of their pose pairs
         std::vector<size_t> wbase(n + 1, 0);
         for (int w = 0; w < n; w++) wbase[w + 1] = wbase[w] + (size_t)h->wins[w].n_free * h->wins[w].n_free;
-        std::vector<unsigned char> mark(wbase[n], 0);
+        std::vector<unsigned char> &mark = h->mark; mark.assign(wbase[n], 0);
         int64_t n_off = 0, n_diag = 0, nnzb = 0;
         for (int cls = 0; cls < 2; cls++) {
             const std::vector<Seg> &sgs = cls ? sg_ls : sg_pt; const std::vector<int> &fps = cls ? fp_ls : fp_pt;
@@ -598,6 +607,8 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     if (!sg_ls.empty()) std::memcpy(hb + i_sg_ls, sg_ls.data(), sizeof(Seg) * sg_ls.size());
     if (!fp_pt.empty()) std::memcpy(hb + i_fp_pt, fp_pt.data(), sizeof(int) * fp_pt.size());
     if (!fp_ls.empty()) std::memcpy(hb + i_fp_ls, fp_ls.data(), sizeof(int) * fp_ls.size());
+    const bool par_lm = (n <= 8);       // one (or few) big windows: parallel over landmarks; batches: parallel over windows
+#pragma omp parallel for schedule(dynamic, 4) if (!par_lm)
     for (int w = 0; w < n; w++) {
         const plba_problem &p = probs[w]; const WinInfo &wi = h->wins[w];
         win_slot0[w] = wi.slot0; win_nfree[w] = wi.n_free; win_ls0[w] = wi.ls0; winS[w] = win_S_off[w];
@@ -611,11 +622,13 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
                 else log_se3(p.kf_T_wc + 12 * (size_t)k, &X0[(size_t)(wi.slot0 + s) * 6]);
             }
         }
+#pragma omp parallel for schedule(static) if (par_lm && p.n_pt > 2048)
         for (int g = wi.pt0; g < wi.pt0 + p.n_pt; g++) {
             const int old = h->pt_perm[g] - wi.pt0;
             pt_win[g] = w;
             for (int i = 0; i < 3; i++) pts0[(size_t)3 * g + i] = p.pt_xyz[(size_t)3 * old + i];
         }
+#pragma omp parallel for schedule(static) if (par_lm && p.n_ls > 2048)
         for (int g = wi.ls0; g < wi.ls0 + p.n_ls; g++) {
             const int old = h->ls_perm[g] - wi.ls0;
             ls_win[g] = w;
@@ -625,12 +638,14 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
                 for (int i = 0; i < 6; i++) lmap[(size_t)6 * g + i] = p.ls_plk[(size_t)6 * old + i];
             }
         }
+#pragma omp parallel for schedule(static) if (par_lm && p.n_pt > 2048)
         for (int g = wi.pt0; g < wi.pt0 + p.n_pt; g++) for (int o = pt_ptr[g]; o < pt_ptr[g + 1]; o++) {
             const int i = h->po_perm[o] - wi.po0;
             po_kf[o] = wi.kf0 + p.po_kf[i]; po_lm[o] = g;
             po_uv[(size_t)2 * o] = p.po_uv[(size_t)2 * i]; po_uv[(size_t)2 * o + 1] = p.po_uv[(size_t)2 * i + 1];
             po_om[o] = p.po_sig2 ? (double)(float)(1.0 / p.po_sig2[i]) : 1.0;                        // const float& invSigma2 (:6009, Q13)
         }
+#pragma omp parallel for schedule(static) if (par_lm && p.n_ls > 2048)
         for (int g = wi.ls0; g < wi.ls0 + p.n_ls; g++) for (int o = ls_ptr[g]; o < ls_ptr[g + 1]; o++) {
             const int i = h->lo_perm[o] - wi.lo0;
             lo_kf[o] = wi.kf0 + p.lo_kf[i]; lo_lm[o] = g;
@@ -815,6 +830,7 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
     for (int i = 0; i < CNT_N; i++) h->h_counters[i] = cnt[i];
     const double *pt0 = (const double *)(h->h_in + h->i_pts0), *ls0 = (const double *)(h->h_in + h->i_lns0);
     int rc_all = PLBA_OK;
+#pragma omp parallel for schedule(dynamic, 4) if (n > 8)
     for (int w = 0; w < n; w++) {
         const WinInfo &wi = h->wins[w]; plba_result &r = res[w];
         r.n_trace = ctrl[w].n_trace; r.n_trials = ctrl[w].n_trials;
@@ -848,8 +864,8 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
                 if (r.lo_flags) r.lo_flags[i] = lf[o];
             }
         }
-        if (r.status < PLBA_DISCARDED) rc_all = r.status;
     }
+    for (int w = 0; w < n; w++) if (res[w].status < PLBA_DISCARDED) rc_all = res[w].status;
     h->timing.ms_host_unpack = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
     return rc_all;
 }

@@ -405,7 +405,10 @@ PLBA_D void assemble_chunk(const DevP &Pin, const Chunk &ch, int mode) {
 #else
         const int ntasks = (nseg && mode == 1) ? sm.seg_task0[nseg] : 0;
 #endif
-        for (int p = tid; p < ntasks; p += PLBA_NT) {
+        // every (segment, pose pair) is split into two tasks of three block rows each: twice the threads busy in this latency-bound
+        // phase and half the accumulators per thread (18: no spills at 128 registers); the 2x2 / 2x6 inner products are recomputed
+        for (int p2 = tid; p2 < 2 * ntasks; p2 += PLBA_NT) {
+            const int p = p2 >> 1, hrow = 3 * (p2 & 1);
             int lo = 0, hi = nseg;                     // largest s with seg_task0[s] <= p
             while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sm.seg_task0[mid] <= p) lo = mid; else hi = mid; }
             const int s = lo, nf = sm.seg_nfree[s];
@@ -416,9 +419,9 @@ PLBA_D void assemble_chunk(const DevP &Pin, const Chunk &ch, int mode) {
             const int t0 = ptr[ch.lm0 + l0] - ch.ob0;
             const int pa = sm.freepos[t0 + i], pb = sm.freepos[t0 + j];
             const int sa = sm.slot[t0 + pa] - slot0, sb = sm.slot[t0 + pb] - slot0;
-            double blk[36];
+            double blk[18];
 #pragma unroll
-            for (int k = 0; k < 36; k++) blk[k] = 0.0;
+            for (int k = 0; k < 18; k++) blk[k] = 0.0;
             for (int m = 0; m < nl; m++) {
                 const int ta = t0 + m * no + pa, tb = t0 + m * no + pb;
                 double M[RANK * RANK], MA[RANK * 6];
@@ -451,10 +454,10 @@ PLBA_D void assemble_chunk(const DevP &Pin, const Chunk &ch, int mode) {
                     }
                 }
 #pragma unroll
-                for (int r = 0; r < 6; r++) {
+                for (int r = 0; r < 3; r++) {
 #pragma unroll
                     for (int k = 0; k < RANK; k++) {
-                        const double av = sm.A[(k * 6 + r) * OC + ta];
+                        const double av = sm.A[(k * 6 + hrow + r) * OC + ta];
 #pragma unroll
                         for (int c = 0; c < 6; c++) blk[r * 6 + c] += av * MA[k * 6 + c];
                     }
@@ -470,11 +473,12 @@ PLBA_D void assemble_chunk(const DevP &Pin, const Chunk &ch, int mode) {
                 double *base = Sw + (size_t)(6 * ra) * ld + 6 * cb;
                 const int sr = tr ? 1 : ld, sc = tr ? ld : 1;
 #pragma unroll
-                for (int r = 0; r < 6; r++) {
+                for (int r = 0; r < 3; r++) {
 #pragma unroll
                     for (int c = 0; c < 6; c++) {
-                        const bool on = !same || (pass == 0 ? (r <= c) : (c <= r));
-                        if (on) plba_atomic_add(base + r * sr + c * sc, -blk[r * 6 + c]);
+                        const int rr = hrow + r;
+                        const bool on = !same || (pass == 0 ? (rr <= c) : (c <= rr));
+                        if (on) plba_atomic_add(base + rr * sr + c * sc, -blk[r * 6 + c]);
                     }
                 }
             }

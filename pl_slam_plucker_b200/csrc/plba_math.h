@@ -332,29 +332,31 @@ PLBA_HD void h_plkline(const Cam &cam, const double *T, const LinePre &L, const 
 // ---------------------------------------------------------------------------------------------------
 template <int D>
 PLBA_HD bool spd_inverse(double *M) {
-    double Lm[D * D];
+    // Cholesky M = L L^T with ONE reciprocal square root per pivot (no sqrt followed by divisions: this sits on the latency
+    // path of the per-landmark phase), then L^-1 and M^-1 = L^-T L^-1
+    double Lm[D * D], ri[D];
     for (int i = 0; i < D * D; i++) Lm[i] = 0.0;
     for (int j = 0; j < D; j++) {
         double s = M[j * D + j];
         for (int k = 0; k < j; k++) s -= Lm[j * D + k] * Lm[j * D + k];
         if (!(s > 0.0)) return false;
-        const double ljj = sqrt(s);
-        Lm[j * D + j] = ljj;
+        ri[j] = plba_rsqrt_hd(s);
+        Lm[j * D + j] = s * ri[j];
         for (int i = j + 1; i < D; i++) {
             double v = M[i * D + j];
             for (int k = 0; k < j; k++) v -= Lm[i * D + k] * Lm[j * D + k];
-            Lm[i * D + j] = v / ljj;
+            Lm[i * D + j] = v * ri[j];
         }
     }
     // Linv (lower)
     double Li[D * D];
     for (int i = 0; i < D * D; i++) Li[i] = 0.0;
     for (int j = 0; j < D; j++) {
-        Li[j * D + j] = 1.0 / Lm[j * D + j];
+        Li[j * D + j] = ri[j];
         for (int i = j + 1; i < D; i++) {
             double s = 0.0;
             for (int k = j; k < i; k++) s -= Lm[i * D + k] * Li[k * D + j];
-            Li[i * D + j] = s / Lm[i * D + i];
+            Li[i * D + j] = s * ri[i];
         }
     }
     for (int r = 0; r < D; r++) for (int c = 0; c <= r; c++) {

@@ -12,7 +12,12 @@
 #include <cstring>
 #include <cmath>
 
-struct alignas(16) plba_d2 { double x, y; };   // 128-bit load unit of the SoA observation arrays
+struct alignas(16) plba_d2 { double x, y; };
+#if defined(__CUDA_ARCH__)
+#define plba_rsqrt_hd(x) rsqrt(x)
+#else
+#define plba_rsqrt_hd(x) (1.0 / std::sqrt(x))
+#endif   // 128-bit load unit of the SoA observation arrays
 
 #ifndef PLBA_HOST_EMU
 // ------------------------------------------------------------------ CUDA

@@ -38,8 +38,9 @@ class LBASolver:
         return rc
 
     # ---- one-call interface (host buffers in, host buffers out) ----
-    def solve(self, prob, opt, trace_cap=256):
-        res = abi.Result(prob, trace_cap)
+    def solve(self, prob, opt, trace_cap=256, out=None):
+        """The drop-in call.  `out`: a Result of matching shape to write into (a steady-state caller re-uses its buffers)."""
+        res = out if out is not None else abi.Result(prob, trace_cap)
         pc = prob.as_c()
         res.rc = self._check(self.L.plba_solve(self.h, C.byref(pc), C.byref(opt.c), C.byref(res.c)))
         return res

@@ -18,7 +18,7 @@ _L = None
 def build(force=False):
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "plba.h")]
     if force or not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
-        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DPLBA_HOST_EMU", "-x", "c++",
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-fopenmp", "-shared", "-DPLBA_HOST_EMU", "-x", "c++",
                                os.path.join(CSRC, "plba_api.cu"), os.path.join(CSRC, "scene_gen.cpp"), "-o", SO])
     return SO
 
