@@ -114,10 +114,10 @@ struct Smem {
     typedef KT<PROF, LT> K;
     enum { NSYM = K::D * (K::D + 1) / 2 };
     double *A, *B, *E, *U, *TA, *Hinv, *V, *Pre, *Xl, *red;
-    int *slot, *lmof, *act, *freepos, *seg_lm0, *seg_nlm, *seg_nobs, *seg_nfree, *seg_task0, *seg_dtask0, *seg_fp0;
+    int *slot, *lmof, *act, *freepos, *seg_lm0, *seg_nlm, *seg_nobs, *seg_nfree, *seg_task0, *seg_dtask0, *seg_fp0, *lm_t0;
     static size_t bytes() {
         return sizeof(double) * ((size_t)(K::RANK * 6 + 2 * K::RANK * K::D + 2 * K::RANK) * OC + (size_t)(NSYM + 2 * K::D + K::NPRE) * LC + 8)
-             + sizeof(int) * (4 * OC + 7 * LC + 32);
+             + sizeof(int) * (4 * OC + 8 * LC + 48);
     }
     PLBA_HD explicit Smem(unsigned char *raw) {
         double *p = (double *)raw;
@@ -133,7 +133,7 @@ struct Smem {
         red = p; p += 8;
         int *q = (int *)p;
         slot = q; q += OC; lmof = q; q += OC; act = q; q += OC; freepos = q; q += OC;
-        seg_lm0 = q; q += LC; seg_nlm = q; q += LC; seg_nobs = q; q += LC; seg_nfree = q; q += LC; seg_fp0 = q; q += LC; seg_task0 = q; q += LC + 16; seg_dtask0 = q; q += LC + 16;
+        seg_lm0 = q; q += LC; seg_nlm = q; q += LC; seg_nobs = q; q += LC; seg_nfree = q; q += LC; seg_fp0 = q; q += LC; seg_task0 = q; q += LC + 16; seg_dtask0 = q; q += LC + 16; lm_t0 = q; q += LC + 16;
     }
 };
 template <int PROF> struct SmemMax {
@@ -329,6 +329,7 @@ PLBA_D void assemble_chunk(const DevP &Pin, const Chunk &ch, int mode) {
     PHASE_BEGIN
         if (tid < 8) sm.red[tid] = 0.0;
         if (tid < nlm) lm_precompute<PROF, LT>(P, ctl, ch.win, ch.lm0 + tid, tid, sm, state);
+        if (tid <= nlm) sm.lm_t0[tid] = ptr[ch.lm0 + tid] - ch.ob0;      // CSR offsets of the chunk's landmarks, once, in shared memory
         if (tid < nseg) {
             const Seg sg = OA::segs(P)[ch.seg0 + tid];
             sm.seg_lm0[tid] = sg.lm0 - ch.lm0; sm.seg_nlm[tid] = sg.n_lm; sm.seg_nobs[tid] = sg.nobs;
@@ -353,8 +354,8 @@ PLBA_D void assemble_chunk(const DevP &Pin, const Chunk &ch, int mode) {
     PROF_MARK(2);
     PHASE_BEGIN
         if (tid < nlm) {
-            const int lm = ch.lm0 + tid;
-            const int t0 = ptr[lm] - ch.ob0, t1 = ptr[lm + 1] - ch.ob0;
+
+            const int t0 = sm.lm_t0[tid], t1 = sm.lm_t0[tid + 1];
             double H[D * D], bl[D], maxd;
             lm_blocks<PROF, LT>(t0, t1, sm, H, bl, maxd);
             if (mode == 0) plba_atomic_max_pos(&P.accmax[ch.win], maxd);
@@ -416,7 +417,7 @@ PLBA_D void assemble_chunk(const DevP &Pin, const Chunk &ch, int mode) {
             while (q >= nf - 1 - i) { q -= nf - 1 - i; i++; }
             const int j = i + 1 + q;
             const int l0 = sm.seg_lm0[s], nl = sm.seg_nlm[s], no = sm.seg_nobs[s];
-            const int t0 = ptr[ch.lm0 + l0] - ch.ob0;
+            const int t0 = sm.lm_t0[l0];
             const int pa = sm.freepos[t0 + i], pb = sm.freepos[t0 + j];
             const int sa = sm.slot[t0 + pa] - slot0, sb = sm.slot[t0 + pb] - slot0;
             double blk[18];
@@ -493,7 +494,7 @@ PLBA_D void assemble_chunk(const DevP &Pin, const Chunk &ch, int mode) {
             while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sm.seg_dtask0[mid] <= p) lo = mid; else hi = mid; }
             const int s = lo, i = p - sm.seg_dtask0[s];
             const int l0 = sm.seg_lm0[s], nl = sm.seg_nlm[s], no = sm.seg_nobs[s];
-            const int t0 = ptr[ch.lm0 + l0] - ch.ob0;
+            const int t0 = sm.lm_t0[l0];
             const int pa = sm.freepos[t0 + i];
             const int sa = sm.slot[t0 + pa] - slot0;
             double Sd[21], gv[6], hd[6];
@@ -609,6 +610,7 @@ PLBA_D void update_chunk(const DevP &Pin, const Chunk &ch) {
     PHASE_BEGIN
         if (tid < 8) sm.red[tid] = 0.0;
         if (tid < nlm) lm_precompute<PROF, LT>(P, ctl, ch.win, ch.lm0 + tid, tid, sm, state);
+        if (tid <= nlm) sm.lm_t0[tid] = ptr[ch.lm0 + tid] - ch.ob0;
     PHASE_END
     PROF_MARK(21);
     PHASE_BEGIN
@@ -634,7 +636,7 @@ PLBA_D void update_chunk(const DevP &Pin, const Chunk &ch) {
         double sc = 0.0, d2 = 0.0;
         if (tid < nlm) {
             const int lm = ch.lm0 + tid;
-            const int t0 = ptr[lm] - ch.ob0, t1 = ptr[lm + 1] - ch.ob0;
+            const int t0 = sm.lm_t0[tid], t1 = sm.lm_t0[tid + 1];
             double H[D * D], bl[D], maxd;
             lm_blocks<PROF, LT>(t0, t1, sm, H, bl, maxd);
             damp_invert<PROF, D>(ctl, H);
