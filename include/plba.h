@@ -190,6 +190,10 @@ int  plba_copy_reduced_system(plba_handle h, int32_t window, double *S_out, doub
  * two CUDA events on the handle's stream.  which: 0 = assembly (linearise + blocks + Schur), 1 = reduced-system solve,
  * 2 = update (back-substitution + retraction + new cost).  The LM state is not advanced. */
 int  plba_time_kernel(plba_handle h, int32_t which, int32_t reps, double lambda, double *ms_avg);
+/* Large windows (6 n_free > 144): the reduced camera system is solved by a banded Cholesky when no landmark track spans more
+ * than 15 free keyframes (sliding-window shape), by the dense tensor-core (FP64 DMMA) Cholesky otherwise.  on != 0 forces the
+ * dense path (benchmarks, tests). */
+int  plba_set_force_dense(plba_handle h, int on);
 /* Layout of the resident problem, for roofline accounting: out8 = { point chunks, line chunks, point segments, line segments,
  * off-diagonal Schur tasks, diagonal Schur tasks, structurally non-zero upper 6x6 blocks of S (nnzb), device arena bytes }. */
 int  plba_layout_stats(plba_handle h, int64_t *out8);

@@ -54,7 +54,8 @@ struct plba_handle_s {
     std::vector<int> pt_perm, ls_perm, po_perm, lo_perm;    // internal index -> caller's (global, window-offset) index
     std::vector<Chunk> ch_pt, ch_ls; std::vector<Seg> sg_pt, sg_ls; std::vector<int> fp_pt, fp_ls, pt_ptr, ls_ptr;   // upload scratch, capacity re-used
     std::vector<unsigned char> mark;
-    int ls_dim = 4, max_nf = 0, solve_class = 1;
+    int ls_dim = 4, max_nf = 0, solve_class = 1, band_blocks = 0;
+    bool force_dense = false;
     bool uploaded = false, small_path = true;
     double *sysbuf = nullptr; size_t sys_doubles = 0, S_doubles = 0;
     double *invbuf = nullptr;
@@ -225,6 +226,8 @@ int plba_create(int32_t device, void *stream, plba_handle *out) {
     if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && nsm > 0) h->n_sm = nsm;
     const char *ng = std::getenv("PLBA_NO_GRAPH");
     h->no_graph = ng && ng[0] == '1';
+    const char *fd = std::getenv("PLBA_FORCE_DENSE");        // large windows: always take the dense DMMA Cholesky (tests, benchmarks)
+    h->force_dense = fd && fd[0] == '1';
 #else
     h->no_graph = true;
 #endif
@@ -272,6 +275,7 @@ template <int PROF> static void set_smem_attr() {
         cudaFuncSetAttribute(k_assemble<PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemMax<PROF>::bytes());
         cudaFuncSetAttribute(k_update<PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemMax<PROF>::bytes());
         cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_small_smem(1));
+        cudaFuncSetAttribute(k_solve_banded, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_banded_smem());
         cudaFuncSetAttribute(k_potrf_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_block_smem());
         cudaFuncSetAttribute(k_trsm_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_block_smem());
         cudaFuncSetAttribute(k_syrk_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_dmma_smem());
@@ -327,6 +331,12 @@ static void launch_solve(plba_handle h) {
         return;
     }
     if (P.profile != PLBA_PROFILE_G) { PLBA_LAUNCH(k_control_h_pre, grid1(P.n_win, 128), dim3(128), 0, h->stream, Pp); h->timing.n_launches++; }
+    if (h->band_blocks <= BAND_MAX && !h->force_dense) {
+        // block-banded reduced camera system (no loop closure in the window): banded left-looking Cholesky, one CTA per window
+        PLBA_LAUNCH(k_solve_banded, dim3(std::min(P.n_win, h->n_sm)), dim3(256), solve_banded_smem(), h->stream, Pp, h->band_blocks);
+        PLBA_LAUNCH(k_pose_update, grid1(P.n_free, 128), dim3(128), 0, h->stream, Pp); h->timing.n_launches += 2;
+        return;
+    }
     for (int w = 0; w < P.n_win; w++) {
         const int n = 6 * h->wins[w].n_free;
         if (n == 0 || h->wins[w].n_pobs + h->wins[w].n_lobs == 0) continue;
@@ -527,7 +537,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
         std::vector<size_t> wbase(n + 1, 0);
         for (int w = 0; w < n; w++) wbase[w + 1] = wbase[w] + (size_t)h->wins[w].n_free * h->wins[w].n_free;
         std::vector<unsigned char> &mark = h->mark; mark.assign(wbase[n], 0);
-        int64_t n_off = 0, n_diag = 0, nnzb = 0;
+        int64_t n_off = 0, n_diag = 0, nnzb = 0; int band = 0;
         for (int cls = 0; cls < 2; cls++) {
             const std::vector<Seg> &sgs = cls ? sg_ls : sg_pt; const std::vector<int> &fps = cls ? fp_ls : fp_pt;
             const std::vector<int> &ptr = cls ? ls_ptr : pt_ptr; const std::vector<int> &operm = cls ? h->lo_perm : h->po_perm;
@@ -540,13 +550,14 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
                 for (int i = 0; i < sg.nfree; i++) for (int j = i; j < sg.nfree; j++) {
                     int a = p.kf_slot[kf[operm[o0 + fps[sg.fp0 + i]] - ob0]], b = p.kf_slot[kf[operm[o0 + fps[sg.fp0 + j]] - ob0]];
                     if (a > b) std::swap(a, b);
+                    if (b - a > band) band = b - a;
                     unsigned char &m = mark[wbase[w] + (size_t)a * wi.n_free + b];
                     if (!m) { m = 1; nnzb++; }
                 }
             }
         }
         h->layout[0] = (int64_t)ch_pt.size(); h->layout[1] = (int64_t)ch_ls.size(); h->layout[2] = (int64_t)sg_pt.size(); h->layout[3] = (int64_t)sg_ls.size();
-        h->layout[4] = n_off; h->layout[5] = n_diag; h->layout[6] = nnzb;
+        h->layout[4] = n_off; h->layout[5] = n_diag; h->layout[6] = nnzb; h->band_blocks = band;
     }
 
     // ---- memory plan ----------------------------------------------------------------------------------------
@@ -965,6 +976,7 @@ int plba_debug_prof(unsigned long long *out64, int reset) {
     return 0;
 }
 #endif
+int plba_set_force_dense(plba_handle h, int on) { if (!h) return PLBA_E_ARG; h->force_dense = on != 0; return PLBA_OK; }
 int plba_layout_stats(plba_handle h, int64_t *out8) { if (!h || !h->uploaded || !out8) return PLBA_E_ARG; for (int i = 0; i < 8; i++) out8[i] = h->layout[i]; return PLBA_OK; }
 int plba_get_timing(plba_handle h, plba_timing *t) { if (!h || !t) return PLBA_E_ARG; *t = h->timing; return PLBA_OK; }
 int plba_set_detail_timing(plba_handle h, int on) { if (!h) return PLBA_E_ARG; h->detail_timing = on != 0; return PLBA_OK; }

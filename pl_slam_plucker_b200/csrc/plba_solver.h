@@ -512,4 +512,198 @@ PLBA_KERNEL void k_back_block(const DevP *Pp, int w, int k0, int nb) {
     PHASE_END
 }
 
+// ---- banded path (6 Nkf > 144 and every landmark track shorter than BAND_MAX keyframes: the sliding-window shape of configs 4-5) ----
+// The reduced camera system of a window without loop closures is block-banded (block (a,b) is non-zero only if some landmark is
+// seen by free keyframes a and b), and Cholesky preserves the band.  One CTA per window walks the 6-column panels left-looking,
+// exactly like chol_lower_panels, but every row only looks back over its band and the factor lives in a shared-memory RING of the
+// last QB columns x RB rows; S is read once (band only), L is written back in place for the backward substitution.
+// O(n * band^2) instead of O(n^3 / 3): n = 12 000, band 14 blocks -> 0.1 GFLOP instead of 576.
+enum { BAND_MAX = 15 /* blocks */, BAND_RB = 6 * (BAND_MAX + 1), BAND_QB = 6 * BAND_MAX, BAND_LDR = BAND_RB + 1 };
+static inline size_t solve_banded_smem() { return sizeof(double) * ((size_t)BAND_QB * BAND_LDR + BAND_QB + BAND_RB + (BAND_RB + 2) * 6 + 8 * (BAND_RB + 2) * 6 + 64) + 64; }
+
+PLBA_KERNEL void k_solve_banded(const DevP *Pp, int bwb) {
+    PLBA_SMEM(raw);
+    PLBA_PARAMS(P, Pp);
+    for (int w = PLBA_BID; w < P.n_win; w += PLBA_NB) {
+        WinCtrl &ctl = P.ctrl[w];
+        const int nf = P.win_nfree[w], n = 6 * nf, slot0 = P.win_slot0[w];
+        if (ctl.done || n == 0) continue;                     // (profile H: k_control_h_pre has already run)
+        const int RB = 6 * (bwb + 1), QB = 6 * bwb, ldr = BAND_LDR;
+        double *ring = (double *)raw;                          // ring[(q % QB) * ldr + (r % RB)] = L[r][q]
+        double *yring = ring + (size_t)BAND_QB * BAND_LDR;     // y[q % QB]   (the right-hand side rides along as one more row)
+        double *xring = yring + BAND_QB;                       // backward substitution: x[r % RB]
+        double *Pn = xring + BAND_RB;                          // [RB + 1][6] the panel being built (row RB = right-hand side)
+        double *part = Pn + (BAND_RB + 2) * 6;                 // [<= 256][6] partial sums
+        double *Lb = part + 8 * (BAND_RB + 2) * 6;             // [0..20] diagonal block staged for the backward pass, [40] fail flag
+        double *Sw = P.S + P.win_S_off[w];
+        double *x = P.xp + (size_t)6 * slot0;
+        const double lambda = ctl.lambda;
+        // raw (un-factored) entries of one panel: rows k0 .. k0+nr-1 of its six columns (upper storage: contiguous in the row index)
+        // plus the right-hand side; staged into Pn one panel ahead by threads that are idle in the factor phase
+        PHASE_BEGIN
+            if (tid == 0) Lb[40] = 0.0;
+            const int nr0 = (n < RB) ? n : RB;
+            for (int idx = tid; idx < 6 * (nr0 + 1); idx += PLBA_NT) {
+                const int c = idx / (nr0 + 1), rr = idx - c * (nr0 + 1);
+                double v;
+                if (rr == nr0) v = P.gs[(size_t)6 * slot0 + c];
+                else if (rr >= c) { v = Sw[(size_t)c * n + rr]; if (rr == c) v += (P.profile == PLBA_PROFILE_G) ? lambda : lambda * P.hpp_diag[(size_t)6 * slot0 + rr]; }
+                else v = 0.0;
+                Pn[rr * 6 + c] = v;
+            }
+        PHASE_END
+        for (int kb = 0; kb < nf; kb++) {
+            const int k0 = 6 * kb;
+            const int nr = (n - k0 < RB) ? n - k0 : RB;       // band rows of this panel: r = k0 + rr, rr < nr; rr == nr is the rhs row
+            const int m = nr + 1;
+            const int mpad = (m + 31) & ~31, nsplit = (mpad <= 32) ? 8 : (mpad <= 64) ? 4 : (mpad <= 128) ? 2 : 1;
+            const int qlo_panel = (kb > bwb) ? 6 * (kb - bwb) : 0;
+            const int kslot = k0 % RB;                         // RB and k0 are multiples of 6: rows k0 .. k0+5 sit at kslot .. kslot+5
+            PHASE_BEGIN
+                const int sp = tid / mpad, rr = tid - sp * mpad;
+                if (k0 > 0 && sp < nsplit && rr < m) {
+                    const bool rhs = (rr == nr);
+                    const int r = k0 + rr;
+                    const int rblk = r / 6;
+                    const int qlo = rhs ? qlo_panel : ((rblk > bwb) ? 6 * (rblk - bwb) : 0);      // first column of row r's band
+                    const int len = k0 - qlo, qs = (len + nsplit - 1) / nsplit;
+                    const int q0 = qlo + sp * qs, q1 = (q0 + qs < k0) ? q0 + qs : k0;
+                    double acc[6] = {0, 0, 0, 0, 0, 0};
+                    int rslot = kslot + rr; if (rslot >= RB) rslot -= RB;
+                    int qc = (q0 < q1) ? q0 % QB : 0;
+                    for (int q = q0; q < q1; q++) {
+                        const double *col = ring + (size_t)qc * ldr;
+                        const double v = rhs ? yring[qc] : col[rslot];
+#pragma unroll
+                        for (int c = 0; c < 6; c++) acc[c] += v * col[kslot + c];
+                        if (++qc == QB) qc = 0;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 6; c++) part[((size_t)sp * mpad + rr) * 6 + c] = acc[c];
+                }
+            PHASE_END
+            PHASE_BEGIN
+                if (k0 > 0) for (int idx = tid; idx < 6 * m; idx += PLBA_NT) {       // fold the partial sums into the staged raw entries
+                    const int rr = idx / 6, c = idx - 6 * rr;
+                    double sum = 0.0;
+                    for (int sp = 0; sp < nsplit; sp++) sum += part[((size_t)sp * mpad + rr) * 6 + c];
+                    Pn[rr * 6 + c] -= sum;
+                }
+            PHASE_END
+            PHASE_BEGIN
+                const int rr = 6 + tid;                        // rows below the diagonal block (incl. the rhs row at rr == nr)
+                if (rr <= nr || tid == 0) {
+                    double L[21], inv[6];
+#pragma unroll
+                    for (int i = 0; i < 6; i++) {
+#pragma unroll
+                        for (int j = 0; j <= i; j++) L[i * (i + 1) / 2 + j] = Pn[i * 6 + j];
+                    }
+                    bool bad = false;
+#pragma unroll
+                    for (int j = 0; j < 6; j++) {
+                        double sd = L[j * (j + 1) / 2 + j];
+#pragma unroll
+                        for (int k = 0; k < j; k++) sd -= L[j * (j + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+                        if (!(sd > 0.0) || !plba_isfinite(sd)) { bad = true; sd = 1.0; }
+                        inv[j] = plba_rsqrt(sd);
+                        L[j * (j + 1) / 2 + j] = sd * inv[j];
+#pragma unroll
+                        for (int i = j + 1; i < 6; i++) {
+                            double v = L[i * (i + 1) / 2 + j];
+#pragma unroll
+                            for (int k = 0; k < j; k++) v -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+                            L[i * (i + 1) / 2 + j] = v * inv[j];
+                        }
+                    }
+                    if (rr <= nr) {
+                        double xr[6];
+#pragma unroll
+                        for (int c = 0; c < 6; c++) {
+                            double v = Pn[rr * 6 + c];
+#pragma unroll
+                            for (int k = 0; k < c; k++) v -= xr[k] * L[c * (c + 1) / 2 + k];
+                            xr[c] = v * inv[c];
+                        }
+                        // publish: ring for the panels to come, global (in place, upper storage) for the backward substitution
+                        const int qc0 = (QB > 0) ? k0 % QB : 0;         // QB is a multiple of 6: columns k0 .. k0+5 sit at qc0 .. qc0+5
+                        if (rr == nr) {
+#pragma unroll
+                            for (int c = 0; c < 6; c++) { if (QB > 0) yring[qc0 + c] = xr[c]; x[k0 + c] = xr[c]; }
+                        } else {
+                            int rslot = kslot + rr; if (rslot >= RB) rslot -= RB;
+#pragma unroll
+                            for (int c = 0; c < 6; c++) { if (QB > 0) ring[(size_t)(qc0 + c) * ldr + rslot] = xr[c]; Sw[(size_t)(k0 + c) * n + k0 + rr] = xr[c]; }
+                        }
+                    }
+                    if (tid == 0) {
+                        if (bad) Lb[40] = 1.0;
+#pragma unroll
+                        for (int i = 0; i < 6; i++) {
+#pragma unroll
+                            for (int j = 0; j <= i; j++) Sw[(size_t)(k0 + j) * n + k0 + i] = L[i * (i + 1) / 2 + j];     // factored diagonal block, upper storage
+                        }
+                    }
+                }
+            PHASE_END
+            PHASE_BEGIN
+                // stage the raw entries of the NEXT panel (Pn is free again): global loads issued by all threads at once
+                if (kb + 1 < nf) {
+                    const int k1 = k0 + 6, nr1 = (n - k1 < RB) ? n - k1 : RB;
+                    for (int idx = tid; idx < 6 * (nr1 + 1); idx += PLBA_NT) {
+                        const int c = idx / (nr1 + 1), rr = idx - c * (nr1 + 1);
+                        double v;
+                        if (rr == nr1) v = P.gs[(size_t)6 * slot0 + k1 + c];
+                        else if (rr >= c) { v = Sw[(size_t)(k1 + c) * n + k1 + rr]; if (rr == c) v += (P.profile == PLBA_PROFILE_G) ? lambda : lambda * P.hpp_diag[(size_t)6 * slot0 + k1 + rr]; }
+                        else v = 0.0;
+                        Pn[rr * 6 + c] = v;
+                    }
+                }
+            PHASE_END
+        }
+        // backward substitution L^T x = y, last panel first: x_k = L_kk^-T (y_k - sum over the band rows below of L[r][k-cols] x_r)
+        for (int kb = nf - 1; kb >= 0; kb--) {
+            const int k0 = 6 * kb;
+            const int nr = (n - k0 < RB) ? n - k0 : RB;
+            const int kslot = k0 % RB;
+            PHASE_BEGIN
+                // 6 columns x 32 lanes: lane-strided partial dot products over the rows below the diagonal block (contiguous in memory);
+                // the seventh warp stages the factored diagonal block
+                const int c = tid >> 5, lane = tid & 31;
+                if (c < 6) {
+                    double sum = 0.0;
+                    const double *col = Sw + (size_t)(k0 + c) * n + k0;
+                    for (int rr = 6 + lane; rr < nr; rr += 32) { int xs_ = kslot + rr; if (xs_ >= RB) xs_ -= RB; sum += col[rr] * xring[xs_]; }
+                    part[c * 33 + lane] = sum;
+                } else if (c == 6 && lane < 21) {
+                    int i = 0; while ((i + 1) * (i + 2) / 2 <= lane) i++;
+                    const int j = lane - i * (i + 1) / 2;
+                    Lb[lane] = Sw[(size_t)(k0 + j) * n + k0 + i];
+                }
+            PHASE_END
+            PHASE_BEGIN
+                if (tid < 6) { double sum = x[k0 + tid]; for (int l = 0; l < 32; l++) sum -= part[tid * 33 + l]; Lb[24 + tid] = sum; }
+            PHASE_END
+            PHASE_BEGIN
+                if (tid == 0) {
+                    double xs[6];
+#pragma unroll
+                    for (int c = 5; c >= 0; c--) {
+                        double v = Lb[24 + c];
+#pragma unroll
+                        for (int mm = c + 1; mm < 6; mm++) v -= Lb[mm * (mm + 1) / 2 + c] * xs[mm];
+                        xs[c] = v / Lb[c * (c + 1) / 2 + c];
+                    }
+                    const bool fail = (Lb[40] != 0.0);
+#pragma unroll
+                    for (int c = 0; c < 6; c++) { xring[kslot + c] = xs[c]; x[k0 + c] = fail ? 0.0 : xs[c]; }
+                }
+            PHASE_END
+        }
+        PHASE_BEGIN
+            if (tid == 0 && Lb[40] != 0.0) ctl.solve_fail = 1;
+        PHASE_END
+    }
+}
+
 }  // namespace plba

@@ -107,6 +107,10 @@ class LBASolver:
         self._check(self.L.plba_time_kernel(self.h, int(which), int(reps), float(lam), C.byref(ms)))
         return ms.value
 
+    def set_force_dense(self, on=True):
+        """Large windows: always use the dense DMMA Cholesky instead of the banded one."""
+        self._check(self.L.plba_set_force_dense(self.h, 1 if on else 0))
+
     def layout_stats(self):
         out = (C.c_int64 * 8)()
         self._check(self.L.plba_layout_stats(self.h, out))

@@ -16,7 +16,7 @@ def gpu_solver(emu):
 
 test_small_window_all_profiles = g.test_small_window_all_profiles
 test_golden_fixtures = g.test_golden_fixtures
-test_large_window_tiled_solver = g.test_large_window_tiled_solver
+test_large_window_solvers = g.test_large_window_solvers
 test_largest_single_cta_window = g.test_largest_single_cta_window
 test_loop_closure_shaped_window = g.test_loop_closure_shaped_window
 test_batch_equals_individual_solves = g.test_batch_equals_individual_solves

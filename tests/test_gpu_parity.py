@@ -77,9 +77,22 @@ def test_golden_fixtures(gpu_solver, name):
         assert (r.po_flags == z["out_po_flags"]).all() and (r.lo_flags == z["out_lo_flags"]).all()
 
 
-def test_large_window_tiled_solver(gpu_solver, oracle):
-    """6*Nkf = 180 > single-CTA limit: exercises the tiled Cholesky of the reduced camera system."""
+@pytest.mark.parametrize("dense", [False, True])
+def test_large_window_solvers(gpu_solver, oracle, dense):
+    """6*Nkf = 180 > single-CTA limit.  Sliding-window shape => banded Cholesky; dense=True forces the tiled tensor-core
+    (FP64 DMMA) Cholesky of the dense reduced camera system on the same window."""
     P = scene.make_scene(1, n_kf_free=30, n_kf_fixed=2, n_pt=600, n_ls=150, seed=7)
+    gpu_solver.set_force_dense(dense)
+    try:
+        _check(gpu_solver, oracle, P, abi.PROFILE_G, 1)
+        _check(gpu_solver, oracle, P, abi.PROFILE_H_PLK, 1)
+    finally:
+        gpu_solver.set_force_dense(False)
+
+
+def test_large_window_with_loop_closure_takes_the_dense_path(gpu_solver, oracle):
+    """KF i also observes landmarks of KF i-20: the reduced camera system is no longer banded within 15 blocks."""
+    P = scene.make_scene(1, n_kf_free=40, n_kf_fixed=2, n_pt=1600, n_ls=400, loop_every=20, seed=9)
     _check(gpu_solver, oracle, P, abi.PROFILE_G, 1)
 
 
@@ -245,8 +258,16 @@ def test_config5_full_size_properties(gpu_solver):
     DMMA Cholesky): the invariants that need no oracle run."""
     P, truth = scene.make_scene(5, with_truth=True)
     opt = abi.Options(abi.PROFILE_G, 1, iters_stage1=3, iters_stage2=2)          # 5 outer iterations keep the test short
-    r = gpu_solver.solve(P, opt)
-    assert r.rc == abi.OK
+    gpu_solver.set_force_dense(True)                                             # the dense 12 000^2 DMMA Cholesky
+    try:
+        r = gpu_solver.solve(P, opt)
+    finally:
+        gpu_solver.set_force_dense(False)
+    rb = gpu_solver.solve(P, opt)                                                # banded Cholesky on the same window
+    assert r.rc == abi.OK and rb.rc == abi.OK
+    nb_ = min(len(r.trace), len(rb.trace))
+    np.testing.assert_allclose(rb.trace["chi"][:nb_], r.trace["chi"][:nb_], rtol=1e-7)     # two factorisations of one system
+    np.testing.assert_allclose(rb.kf_T_wc, r.kf_T_wc, atol=1e-6)
     tr = r.trace
     acc = tr[tr["accepted"] == 1]
     assert len(acc) >= 4 and (acc["chi_new"] < acc["chi"]).all() and (acc["rho"] > 0).all()

@@ -5,7 +5,7 @@ import numpy as np
 from pl_slam_plucker_b200 import abi, scene, solver
 from oracle import loader as orc
 s = solver.LBASolver(0)
-for nkf, npt, nls in ((30, 600, 150), (100, 6000, 1500)):
+for nkf, npt, nls in ((30, 600, 150), (100, 6000, 1500), (200, 12000, 3000)):
     P = scene.make_scene(1, n_kf_free=nkf, n_kf_fixed=2, n_pt=npt, n_ls=nls, seed=7)
     opt = abi.Options(abi.PROFILE_G, 1)
     r = s.solve(P, opt); o = orc.solve(P, opt)
