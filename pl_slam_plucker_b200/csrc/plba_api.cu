@@ -48,7 +48,7 @@ struct plba_handle_s {
     size_t in_bytes = 0, out_off = 0, out_bytes = 0;
     // offsets inside the output region
     size_t o_T = 0, o_x = 0, o_pt = 0, o_ls = 0, o_plk = 0, o_pchi = 0, o_lchi = 0, o_pf = 0, o_lf = 0, o_ctrl = 0, o_trace = 0, o_cnt = 0;
-    size_t i_pts0 = 0, i_lns0 = 0;
+    size_t i_pts0 = 0, i_lns0 = 0, i_lmap = 0;
     plba_options opt{};
     std::vector<WinInfo> wins;
     std::vector<int> pt_perm, ls_perm, po_perm, lo_perm;    // internal index -> caller's (global, window-offset) index
@@ -140,6 +140,7 @@ static int validate_problem(const plba_problem &p, const plba_options &o, std::s
 struct ClassLayout {
     std::vector<int> perm;       // new local landmark -> old local landmark
     std::vector<int> optr;       // CSR of the caller's order (local)
+    std::vector<int> group;      // signature group of each OLD landmark (equal group <=> identical keyframe sequence); empty = not grouped
 };
 static void signature_order(int n_lm, int n_obs, const int32_t *lm, const int32_t *kf, bool permute, ClassLayout &L) {
     L.optr.assign(n_lm + 1, 0);
@@ -148,6 +149,29 @@ static void signature_order(int n_lm, int n_obs, const int32_t *lm, const int32_
     L.perm.resize(n_lm);
     for (int l = 0; l < n_lm; l++) L.perm[l] = l;
     if (!permute || n_lm < 2) return;
+    {   // fast path: every track is a contiguous keyframe run (the usual sliding-window case) => the signature IS (first KF, length):
+        // one pass over the observations and a counting sort, no hashing
+        int maxlen = 0, maxkf = 0; bool contiguous = true;
+        for (int l = 0; l < n_lm && contiguous; l++) {
+            const int a = L.optr[l], b = L.optr[l + 1];
+            if (b - a > maxlen) maxlen = b - a;
+            if (b > a && kf[a] > maxkf) maxkf = kf[a];
+            for (int i = a + 1; i < b; i++) if (kf[i] != kf[i - 1] + 1) { contiguous = false; break; }
+        }
+        if (contiguous && (int64_t)(maxkf + 2) * (maxlen + 1) <= 4 * (int64_t)n_lm + 4096) {
+            const int W = maxlen + 1, nkeys = (maxkf + 2) * W;
+            std::vector<int> cnt(nkeys + 1, 0);
+            L.group.resize(n_lm);
+            for (int l = 0; l < n_lm; l++) {
+                const int a = L.optr[l], b = L.optr[l + 1];
+                const int key = (b > a ? kf[a] : maxkf + 1) * W + (b - a);      // landmarks without observations go last
+                L.group[l] = key; cnt[key + 1]++;
+            }
+            for (int k = 0; k < nkeys; k++) cnt[k + 1] += cnt[k];
+            for (int l = 0; l < n_lm; l++) L.perm[cnt[L.group[l]]++] = l;
+            return;
+        }
+    }
     // group landmarks by exact signature with an open-addressing table (hash -> group), then order the groups by
     // (first keyframe, first appearance) and counting-sort the landmarks by group: O(n) instead of a comparison sort
     struct Slot { uint64_t hsh; int group, rep; };
@@ -191,6 +215,7 @@ static void signature_order(int n_lm, int n_obs, const int32_t *lm, const int32_
     int acc = 0;
     for (int r = 0; r < ng; r++) { start[order[r]] = acc; acc += g_count[order[r]]; }
     for (int l = 0; l < n_lm; l++) L.perm[start[group_of[l]]++] = l;       // stable inside a group
+    L.group.swap(group_of);
 }
 
 extern "C" {
@@ -513,7 +538,10 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
                 if (seg_first_old >= 0) {
                     Seg &s = sgs.back();
                     const int fa = L.optr[seg_first_old];
-                    if (s.n_lm < SEG_MAX && s.nobs == no) { join = true; for (int i = 0; i < no; i++) if (kf[fa + i] != kf[a + i]) { join = false; break; } }
+                    if (s.n_lm < SEG_MAX && s.nobs == no) {
+                        if (!L.group.empty()) join = (L.group[seg_first_old] == L.group[old]);
+                        else { join = true; for (int i = 0; i < no; i++) if (kf[fa + i] != kf[a + i]) { join = false; break; } }
+                    }
                     if (join) s.n_lm++;
                 }
                 if (!join) {
@@ -573,7 +601,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     const size_t i_ch_pt = ci.take<Chunk>(ch_pt.size()), i_ch_ls = ci.take<Chunk>(ch_ls.size()), i_sg_pt = ci.take<Seg>(sg_pt.size()), i_sg_ls = ci.take<Seg>(sg_ls.size());
     const size_t i_fp_pt = ci.take<int>(fp_pt.size()), i_fp_ls = ci.take<int>(fp_ls.size());
     const size_t i_ctrl0 = ci.take<WinCtrl>(n);
-    h->in_bytes = ci.off; h->i_pts0 = i_pts0; h->i_lns0 = i_lns0;
+    h->in_bytes = ci.off; h->i_pts0 = i_pts0; h->i_lns0 = i_lns0; h->i_lmap = i_lmap;
     long long S_off = 0;
     std::vector<long long> win_S_off(n);
     for (int w = 0; w < n; w++) { win_S_off[w] = S_off; S_off += (long long)36 * h->wins[w].n_free * h->wins[w].n_free; }
@@ -633,30 +661,30 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
                 else log_se3(p.kf_T_wc + 12 * (size_t)k, &X0[(size_t)(wi.slot0 + s) * 6]);
             }
         }
-#pragma omp parallel for schedule(static) if (par_lm && p.n_pt > 2048)
+#pragma omp parallel for schedule(static) if (par_lm && p.n_pt > 200000)
         for (int g = wi.pt0; g < wi.pt0 + p.n_pt; g++) {
             const int old = h->pt_perm[g] - wi.pt0;
             pt_win[g] = w;
             for (int i = 0; i < 3; i++) pts0[(size_t)3 * g + i] = p.pt_xyz[(size_t)3 * old + i];
         }
-#pragma omp parallel for schedule(static) if (par_lm && p.n_ls > 2048)
+#pragma omp parallel for schedule(static) if (par_lm && p.n_ls > 200000)
         for (int g = wi.ls0; g < wi.ls0 + p.n_ls; g++) {
             const int old = h->ls_perm[g] - wi.ls0;
             ls_win[g] = w;
             if (prof == PLBA_PROFILE_H_END) for (int i = 0; i < 6; i++) lns0[(size_t)6 * g + i] = p.ls_end[(size_t)6 * old + i];
             else {
-                plk_to_orth(p.ls_plk + (size_t)6 * old, &lns0[(size_t)4 * g]);                // changePlukerToOrth (:6040, :1577)
+                // changePlukerToOrth (:6040, :1577) runs on the device (k_reset): four inverse trig calls per line are not host work
                 for (int i = 0; i < 6; i++) lmap[(size_t)6 * g + i] = p.ls_plk[(size_t)6 * old + i];
             }
         }
-#pragma omp parallel for schedule(static) if (par_lm && p.n_pt > 2048)
+#pragma omp parallel for schedule(static) if (par_lm && p.n_pt > 200000)
         for (int g = wi.pt0; g < wi.pt0 + p.n_pt; g++) for (int o = pt_ptr[g]; o < pt_ptr[g + 1]; o++) {
             const int i = h->po_perm[o] - wi.po0;
             po_kf[o] = wi.kf0 + p.po_kf[i]; po_lm[o] = g;
             po_uv[(size_t)2 * o] = p.po_uv[(size_t)2 * i]; po_uv[(size_t)2 * o + 1] = p.po_uv[(size_t)2 * i + 1];
             po_om[o] = p.po_sig2 ? (double)(float)(1.0 / p.po_sig2[i]) : 1.0;                        // const float& invSigma2 (:6009, Q13)
         }
-#pragma omp parallel for schedule(static) if (par_lm && p.n_ls > 2048)
+#pragma omp parallel for schedule(static) if (par_lm && p.n_ls > 200000)
         for (int g = wi.ls0; g < wi.ls0 + p.n_ls; g++) for (int o = ls_ptr[g]; o < ls_ptr[g + 1]; o++) {
             const int i = h->lo_perm[o] - wi.lo0;
             lo_kf[o] = wi.kf0 + p.lo_kf[i]; lo_lm[o] = g;
@@ -861,7 +889,14 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
                 if (r.ls_orth) for (int i = 0; i < 4; i++) r.ls_orth[(size_t)4 * old + i] = ls[(size_t)4 * g + i];
                 if (r.ls_plk) for (int i = 0; i < 6; i++) r.ls_plk[(size_t)6 * old + i] = plk[(size_t)6 * g + i];
             } else if (r.ls_end) for (int i = 0; i < 6; i++) r.ls_end[(size_t)6 * old + i] = ls[(size_t)6 * g + i];
-            if (r.ls_inlier) { double d2 = 0; for (int i = 0; i < ld; i++) { const double d = ls[(size_t)ld * g + i] - ls0[(size_t)ld * g + i]; d2 += d * d; } r.ls_inlier[old] = (!G && std::sqrt(d2) > 0.01) ? 0 : 1; }
+            if (r.ls_inlier) {
+                double d2 = 0, o0[6];
+                if (G) o0[0] = 0;
+                else if (ld == 4) plk_to_orth((const double *)(h->h_in + h->i_lmap) + (size_t)6 * g, o0);     // initial orthonormal coordinates (computed on the device for the solve)
+                else for (int i = 0; i < 6; i++) o0[i] = ls0[(size_t)6 * g + i];
+                if (!G) for (int i = 0; i < ld; i++) { const double d = ls[(size_t)ld * g + i] - o0[i]; d2 += d * d; }
+                r.ls_inlier[old] = (!G && std::sqrt(d2) > 0.01) ? 0 : 1;
+            }
         }
         if (G) {
             for (int o = wi.po0; o < wi.po0 + wi.n_pobs; o++) {

@@ -1014,6 +1014,13 @@ PLBA_KERNEL void k_reset(const DevP *Pp, int ls_dim, size_t sys_doubles, double 
         for (size_t i = g0; i < (size_t)12 * P.n_kf; i += gs) { const double v = P.kf_Tmap[i]; P.poseT[0][i] = v; P.poseT[1][i] = v; }
         for (size_t i = g0; i < (size_t)6 * P.n_free; i += gs) { const double v = P.X0[i]; P.Xkf[0][i] = v; P.Xkf[1][i] = v; P.xp[i] = 0.0; }
         for (size_t i = g0; i < (size_t)3 * P.n_pt; i += gs) { const double v = P.pts0[i]; P.pts[0][i] = v; P.pts[1][i] = v; }
+        if (ls_dim == 4) {      // initial orthonormal coordinates from the map's Plücker vectors (MapLine::changePlukerToOrth, src/mapFeatures.cpp:186-201)
+            double *lns0 = const_cast<double *>(P.lns0);
+            for (size_t l = g0; l < (size_t)P.n_ls; l += gs) {
+                double o[4]; plk_to_orth(P.lns_map + 6 * l, o);
+                for (int i = 0; i < 4; i++) { lns0[4 * l + i] = o[i]; P.lns[0][4 * l + i] = o[i]; P.lns[1][4 * l + i] = o[i]; }
+            }
+        } else
         for (size_t i = g0; i < (size_t)ls_dim * P.n_ls; i += gs) { const double v = P.lns0[i]; P.lns[0][i] = v; P.lns[1][i] = v; }
         for (size_t i = g0; i < (size_t)P.n_pobs; i += gs) { P.po_lvl[i] = 0; P.po_chi2[i] = 0.0; }
         for (size_t i = g0; i < (size_t)P.n_lobs; i += gs) { P.lo_lvl[i] = 0; P.lo_chi2[i] = 0.0; }
