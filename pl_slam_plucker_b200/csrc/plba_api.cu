@@ -58,7 +58,6 @@ struct plba_handle_s {
     bool force_dense = false;
     bool uploaded = false, small_path = true;
     double *sysbuf = nullptr; size_t sys_doubles = 0, S_doubles = 0;
-    double *invbuf = nullptr;
     int h_counters[CNT_N] = {0};
     int64_t layout[8] = {0};
     plba_allreduce_fn allreduce = nullptr; void *allreduce_user = nullptr;
@@ -612,8 +611,6 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     for (int b = 0; b < 2; b++) { s_poseT[b] = cs.take<double>((size_t)12 * tot.n_kf); s_X[b] = cs.take<double>((size_t)6 * tot.n_free); s_pts[b] = cs.take<double>((size_t)3 * tot.n_pt); s_lns[b] = cs.take<double>((size_t)ld * tot.n_ls); }
     const size_t s_po_lvl = cs.take<unsigned char>(tot.n_pobs), s_lo_lvl = cs.take<unsigned char>(tot.n_lobs);
     const size_t s_sys = cs.take<double>(h->sys_doubles), s_xp = cs.take<double>((size_t)6 * tot.n_free);
-    size_t s_inv = 0;
-    (void)s_inv;
     const int trace_cap = (prof == PLBA_PROFILE_G) ? (opt->iters_stage1 + opt->iters_stage2) * opt->lm_max_trials + 2 : opt->max_iters_lba + 2;
     // output region (one D2H copy)
     h->out_off = cs.off;
@@ -725,7 +722,6 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     P.S = h->sysbuf; P.gs = P.S + h->S_doubles; P.hpp_diag = P.gs + (size_t)6 * tot.n_free; P.hpp_diag_init = P.hpp_diag + (size_t)6 * tot.n_free;
     P.acc = P.hpp_diag_init + (size_t)6 * tot.n_free; P.accB = P.acc + (size_t)4 * n; P.accmax = P.acc + (size_t)ACC_N * n;
     P.xp = (double *)(db + s_xp);
-    h->invbuf = nullptr;
     P.ctrl = (WinCtrl *)(db + h->o_ctrl); P.trace = (plba_trace_rec *)(db + h->o_trace); P.trace_cap = trace_cap; P.counters = (int *)(db + h->o_cnt);
     set_all_attrs();
 #ifndef PLBA_HOST_EMU

@@ -401,11 +401,7 @@ PLBA_D void assemble_chunk(const DevP &Pin, const Chunk &ch, int mode) {
     double *Sw = P.S + P.win_S_off[ch.win];
     // ---- off-diagonal pose pairs (a,b), a before b in the landmark's track: S_ab -= At_a^T (Ta_a Bt_b^T) At_b ----
     PHASE_BEGIN
-#ifdef PLBA_EXP_NO_TASKS
-        const int ntasks = 0;
-#else
         const int ntasks = (nseg && mode == 1) ? sm.seg_task0[nseg] : 0;
-#endif
         // every (segment, pose pair) is split into two tasks of three block rows each: twice the threads busy in this latency-bound
         // phase and half the accumulators per thread (18: no spills at 128 registers); the 2x2 / 2x6 inner products are recomputed
         for (int p2 = tid; p2 < 2 * ntasks; p2 += PLBA_NT) {

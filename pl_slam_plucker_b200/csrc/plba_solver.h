@@ -38,7 +38,8 @@ PLBA_D void chol_lower_panels(double *M, int ldm, int nd, int nr, double *dinv, 
 for (int kb = 0; kb < nf; kb++) {
     const int k0 = 6 * kb, m = n - k0 + 1;
     // the q range of a row is split over as many threads as the 256-thread CTA allows: late panels have few rows but long rows
-    const int mpad = (m + 31) & ~31, nsplit = (mpad <= 32) ? 8 : (mpad <= 64) ? 4 : (mpad <= 128) ? 2 : 1;
+    // short look-back (first panels): one thread per row updates the panel in place and the fold phase is skipped
+    const int mpad = (m + 31) & ~31, nsplit = (k0 <= 36) ? 1 : (mpad <= 32) ? 8 : (mpad <= 64) ? 4 : (mpad <= 128) ? 2 : 1;
     PHASE_BEGIN
         const int sp = tid / mpad, rr = tid - sp * mpad;
         if (k0 > 0 && sp < nsplit && rr < m) {
@@ -52,10 +53,16 @@ for (int kb = 0; kb < nf; kb++) {
 #pragma unroll
                 for (int c = 0; c < 6; c++) acc[c] += v * Mk[(size_t)c * ldm + q];
             }
+            if (nsplit == 1) {
 #pragma unroll
-            for (int c = 0; c < 6; c++) part[((size_t)sp * mpad + rr) * 6 + c] = acc[c];
+                for (int c = 0; c < 6; c++) M[(size_t)r * ldm + k0 + c] -= acc[c];
+            } else {
+#pragma unroll
+                for (int c = 0; c < 6; c++) part[((size_t)sp * mpad + rr) * 6 + c] = acc[c];
+            }
         }
     PHASE_END
+    if (nsplit > 1) {
     PHASE_BEGIN
         if (k0 > 0) for (int idx = tid; idx < 6 * m; idx += PLBA_NT) {       // fold the partial sums into the panel, one thread per entry
             const int rr = idx / 6, c = idx - 6 * rr;
@@ -64,6 +71,7 @@ for (int kb = 0; kb < nf; kb++) {
             M[(size_t)(k0 + rr) * ldm + k0 + c] -= sum;
         }
     PHASE_END
+    }
     PHASE_BEGIN
         const int r = k0 + 6 + tid;              // rows below the diagonal block; thread 0 factors the block even when no row is left
         if (r <= n || tid == 0) {
@@ -144,16 +152,16 @@ PLBA_KERNEL void k_solve_small(const DevP *Pp) {
         PHASE_BEGIN
             // upper triangle of S, one warp per row (coalesced), four loads in flight per thread; stored transposed as lower (cg,rg)
             const int warp = tid >> 5, lane = tid & 31, nwarp = PLBA_NT >> 5;
-            for (int rg0 = warp; rg0 < n; rg0 += 2 * nwarp) {
-                double v[2][4];
+            for (int rg0 = warp; rg0 < n; rg0 += 4 * nwarp) {
+                double v[4][4];
 #pragma unroll
-                for (int rr = 0; rr < 2; rr++) {
+                for (int rr = 0; rr < 4; rr++) {
                     const int rg = rg0 + rr * nwarp;
 #pragma unroll
                     for (int u = 0; u < 4; u++) { const int cg = lane + 32 * u; v[rr][u] = (rg < n && cg >= rg && cg < n) ? Sw[(size_t)rg * n + cg] : 0.0; }
                 }
 #pragma unroll
-                for (int rr = 0; rr < 2; rr++) {
+                for (int rr = 0; rr < 4; rr++) {
                     const int rg = rg0 + rr * nwarp;
                     if (rg >= n) continue;
                     const double dmp = (P.profile == PLBA_PROFILE_G) ? lambda : lambda * P.hpp_diag[(size_t)6 * slot0 + rg];
