@@ -34,6 +34,13 @@ enum {
     PLBA_PROFILE_H_PLK = 2  /* hand LM, orthonormal Plücker lines (dead + buggy in reference) (src/mapHandler.cpp:1618)  */
 };
 
+/* Profile H_END only: the LM shell around the per-observation arithmetic.  GBA = MapHandler::levMarquardtOptimizationGBA
+ * (include/mapHandler.h:137, src/mapHandler.cpp:3128-3728; the "next" row 1 of SURVEY.md §8f): identical observation terms (incl.
+ * Q3 / Q4, :3547-3550), every keyframe but KF 0 free, and a shell that differs in: lambda0 scaled by an `int Hmax` (truncated,
+ * :3386-3392), all three stop tests against numeric_limits<double>::epsilon() (:3664, :3694), err /= 0 in EVERY iteration
+ * (Npt_obs, Nls_obs are never counted, :3383, :3662), no `inlier` rule on write-back (:3705-3726), void return. */
+enum { PLBA_SHELL_LBA = 0, PLBA_SHELL_GBA = 1 };
+
 /* Bug-for-bug (FAITHFUL) or intended maths (FIXED); every difference is listed in SURVEY.md §8.Q. */
 enum { PLBA_QUIRKS_FAITHFUL = 0, PLBA_QUIRKS_FIXED = 1 };
 
@@ -92,7 +99,7 @@ typedef struct plba_options {
     double  lambda_lba_lm;    /* 1e-5  SlamConfig::lambdaLbaLM                                     */
     double  lambda_lba_k;     /* 10    SlamConfig::lambdaLbaK                                      */
     int32_t max_iters_lba;    /* 15    SlamConfig::maxItersLba                                     */
-    int32_t reserved0;
+    int32_t shell;            /* PLBA_SHELL_LBA (0) or PLBA_SHELL_GBA (1): which hand-LM shell wraps profile H_END */
     double  homog_th;         /* 1e-7  Config::homogTh                                             */
     double  min_error;        /* 1e-7  Config::minError                                            */
     double  min_error_change; /* 1e-7  Config::minErrorChange                                      */

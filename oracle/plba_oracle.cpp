@@ -749,11 +749,20 @@ struct HRun {
         const int max_iters = O.max_iters_lba;
         const int Npt = P.n_pt, Nls = P.n_ls;
         std::vector<double> xp, xlp, xll;
+        // Global BA shell (levMarquardtOptimizationGBA, src/mapHandler.cpp:3128-3728): same terms as H_END, different shell
+        const bool gba = (O.shell == PLBA_SHELL_GBA);
+        const double eps = std::numeric_limits<double>::epsilon();
+        const double th_err_change = gba ? eps : O.min_error_change, th_err = gba ? eps : O.min_error, th_dx = gba ? eps : O.min_error_change;   // :3664, :3694
+        const double norm_fixed = gba ? (double)(P.n_pobs + P.n_lobs) : (double)(Npt + Nls);
 
         linearize(true);
         // Q1: err /= (Npt_obs + Nls_obs) with both counters left at 0  (:2551)
-        if (!fixed) err /= (double)0; else err /= (double)(Npt + Nls);
-        lambda *= Hmax();                                         // :2555-2561
+        if (!fixed) err /= (double)0; else err /= norm_fixed;     // (GBA: `err` is not even initialised, :3142; restated as 0 + sum)
+        {
+            double hm = Hmax();                                   // :2555-2561
+            if (gba && !fixed) hm = (double)(long long)hm;        // `int Hmax` (:3386-3391): the scale is truncated to an integer
+            lambda *= hm;
+        }
         solve(lambda, xp, xlp, xll);                              // :2564-2568
         retract(xp, xlp, xll);                                    // :2571-2586
         {
@@ -764,14 +773,14 @@ struct HRun {
         for (int iters = 1; iters < max_iters; iters++) {         // :2594
             linearize(false);
             // :2796 ; H_PLK divides by zero in every iteration (:2108, Q1)
-            if (plk && !fixed) err /= (double)0; else err /= (double)(Npt + Nls);
+            if ((plk || gba) && !fixed) err /= (double)0; else err /= norm_fixed;      // GBA: err /= (Npt_obs+Nls_obs) = 0 every iteration (:3662)
             plba_trace_rec tr{}; tr.window = window; tr.iter = iters; tr.chi = err; tr.lambda = lambda; tr.err_pt = point_error; tr.err_ls = line_error;
-            if (std::fabs(err - err_prev) < O.min_error_change || err < O.min_error) { tr.stop = 1; push_trace(res, tr); break; }   // :2798
+            if (std::fabs(err - err_prev) < th_err_change || err < th_err) { tr.stop = 1; push_trace(res, tr); break; }   // :2798 / :3664
             solve(lambda, xp, xlp, xll);                          // :2801-2806
             if (err > err_prev) lambda /= lambda_k;               // :2809-2811 (Q2)
             else { lambda *= lambda_k; retract(xp, xlp, xll); tr.accepted = 1; }
             tr.dx_norm = vnorm(xp, xlp, xll);
-            if (tr.dx_norm < O.min_error_change) { tr.stop = 2; push_trace(res, tr); break; }   // :2834
+            if (tr.dx_norm < th_dx) { tr.stop = 2; push_trace(res, tr); break; }   // :2834 / :3694
             push_trace(res, tr);
             err_prev = err;
         }
@@ -784,13 +793,13 @@ struct HRun {
         if (res->x_pose) for (int s = 0; s < P.n_free; s++) for (int i = 0; i < 6; i++) res->x_pose[6 * s + i] = Xkf[s][i];
         for (int l = 0; l < Npt; l++) {
             double d2 = 0; for (int i = 0; i < 3; i++) { double d = Xpt[l][i] - P.pt_xyz[3 * l + i]; d2 += d * d; }
-            if (res->pt_inlier) res->pt_inlier[l] = (std::sqrt(d2) > 0.01) ? 0 : 1;
+            if (res->pt_inlier) res->pt_inlier[l] = (!gba && std::sqrt(d2) > 0.01) ? 0 : 1;      // GBA has no inlier rule (:3705-3726)
             if (res->pt_xyz) for (int i = 0; i < 3; i++) res->pt_xyz[3 * l + i] = Xpt[l][i];
         }
         for (int l = 0; l < Nls; l++) {
             if (!plk) {
                 double d2 = 0; for (int i = 0; i < 6; i++) { double d = Xls[6 * l + i] - P.ls_end[6 * l + i]; d2 += d * d; }
-                if (res->ls_inlier) res->ls_inlier[l] = (std::sqrt(d2) > 0.01) ? 0 : 1;
+                if (res->ls_inlier) res->ls_inlier[l] = (!gba && std::sqrt(d2) > 0.01) ? 0 : 1;
                 if (res->ls_end) for (int i = 0; i < 6; i++) res->ls_end[6 * l + i] = Xls[6 * l + i];
             } else {
                 // :2185-2196: DX = X_line - orthNDw ; inlier rule on ||DX|| ; Q9: NDw = changeOrthToPluker(DX)

@@ -8,6 +8,7 @@ import numpy as np
 
 PROFILE_G, PROFILE_H_END, PROFILE_H_PLK = 0, 1, 2
 QUIRKS_FAITHFUL, QUIRKS_FIXED = 0, 1
+SHELL_LBA, SHELL_GBA = 0, 1
 OK, DISCARDED, E_ARG, E_CUDA, E_NUMERIC, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 OBS_LEVEL1, OBS_BAD, OBS_NEGDEPTH = 1, 2, 4
 
@@ -26,7 +27,7 @@ class plba_problem(C.Structure):
 
 class plba_options(C.Structure):
     _fields_ = [("profile", C.c_int32), ("quirks", C.c_int32),
-                ("lambda_lba_lm", C.c_double), ("lambda_lba_k", C.c_double), ("max_iters_lba", C.c_int32), ("reserved0", C.c_int32),
+                ("lambda_lba_lm", C.c_double), ("lambda_lba_k", C.c_double), ("max_iters_lba", C.c_int32), ("shell", C.c_int32),
                 ("homog_th", C.c_double), ("min_error", C.c_double), ("min_error_change", C.c_double),
                 ("huber_delta", C.c_double), ("chi2_gate", C.c_double), ("iters_stage1", C.c_int32), ("iters_stage2", C.c_int32),
                 ("lm_tau", C.c_double), ("lm_max_trials", C.c_int32), ("reserved1", C.c_int32)]

@@ -468,6 +468,7 @@ extern "C" {
 int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_options *opt) {
     if (!h || n <= 0 || !probs || !opt) return PLBA_E_ARG;
     if (opt->profile < PLBA_PROFILE_G || opt->profile > PLBA_PROFILE_H_PLK) { h->err = "unknown profile"; return PLBA_E_ARG; }
+    if (opt->shell != PLBA_SHELL_LBA && !(opt->shell == PLBA_SHELL_GBA && opt->profile == PLBA_PROFILE_H_END)) { h->err = "the GBA shell exists for profile H_END only"; return PLBA_E_ARG; }
     CK(cudaSetDevice(h->device));
     const auto t_host0 = std::chrono::steady_clock::now();
     h->uploaded = false;
@@ -689,7 +690,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
             lo_om[o] = p.lo_sig2 ? (double)(float)(1.0 / p.lo_sig2[i]) : 1.0;
         }
         WinCtrl c{};
-        c.need_init = 1; c.apply = 1; c.ni = 2.0; c.err_prev = 999999999.9; c.n_lm_pt = p.n_pt; c.n_lm_ls = p.n_ls;
+        c.need_init = 1; c.apply = 1; c.ni = 2.0; c.err_prev = 999999999.9; c.n_lm_pt = p.n_pt; c.n_lm_ls = p.n_ls; c.n_obs = p.n_pobs + p.n_lobs;
         if (p.n_pobs + p.n_lobs == 0) c.done = 1;      // nothing to do (src/mapHandler.cpp:1496-1500)
         ctrl0[w] = c;
     }
@@ -705,7 +706,10 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     P.iters_stage1 = opt->iters_stage1; P.iters_stage2 = opt->iters_stage2; P.lm_max_trials = opt->lm_max_trials; P.max_iters_lba = opt->max_iters_lba;
     P.max_rounds = (prof == PLBA_PROFILE_G) ? (opt->iters_stage1 + opt->iters_stage2) * opt->lm_max_trials + 2 : opt->max_iters_lba + 1;
     P.huber_delta = opt->huber_delta; P.chi2_gate = opt->chi2_gate; P.homog_th = opt->homog_th; P.min_error = opt->min_error;
-    P.min_error_change = opt->min_error_change; P.lm_tau = opt->lm_tau; P.lambda_lba_lm = opt->lambda_lba_lm; P.lambda_lba_k = opt->lambda_lba_k;
+    P.min_error_change = opt->min_error_change; P.lm_tau = opt->lm_tau;
+    P.gba = (prof == PLBA_PROFILE_H_END && opt->shell == PLBA_SHELL_GBA) ? 1 : 0;
+    if (P.gba) { P.min_error = P.min_error_change = 2.220446049250313e-16; }      // numeric_limits<double>::epsilon() (src/mapHandler.cpp:3664, :3694)
+    P.lambda_lba_lm = opt->lambda_lba_lm; P.lambda_lba_k = opt->lambda_lba_k;
     P.kf_slot = (int *)(db + i_kf_slot); P.kf_win = (int *)(db + i_kf_win); P.slot_kf = (int *)(db + i_slot_kf);
     P.win_slot0 = (int *)(db + i_win_slot0); P.win_nfree = (int *)(db + i_win_nfree); P.win_ls0 = (int *)(db + i_win_ls0); P.win_S_off = (long long *)(db + i_win_S);
     P.kf_Tmap = (double *)(db + i_Tmap); P.X0 = (double *)(db + i_X0); P.pts0 = (double *)(db + i_pts0); P.lns0 = (double *)(db + i_lns0); P.lns_map = (double *)(db + i_lmap);
@@ -877,7 +881,7 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
             const int old = h->pt_perm[g] - wi.pt0;
             if (r.pt_xyz) for (int i = 0; i < 3; i++) r.pt_xyz[(size_t)3 * old + i] = pt[(size_t)3 * g + i];
             // inlier rule of the hand-LM write-back (src/mapHandler.cpp:2858-2860, 2871-2873); profile G leaves it to the final chi2 test
-            if (r.pt_inlier) { double d2 = 0; for (int i = 0; i < 3; i++) { const double d = pt[(size_t)3 * g + i] - pt0[(size_t)3 * g + i]; d2 += d * d; } r.pt_inlier[old] = (!G && std::sqrt(d2) > 0.01) ? 0 : 1; }
+            if (r.pt_inlier) { double d2 = 0; for (int i = 0; i < 3; i++) { const double d = pt[(size_t)3 * g + i] - pt0[(size_t)3 * g + i]; d2 += d * d; } r.pt_inlier[old] = (!G && !P.gba && std::sqrt(d2) > 0.01) ? 0 : 1; }
         }
         for (int g = wi.ls0; g < wi.ls0 + wi.n_ls; g++) {
             const int old = h->ls_perm[g] - wi.ls0;
@@ -891,7 +895,7 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
                 else if (ld == 4) plk_to_orth((const double *)(h->h_in + h->i_lmap) + (size_t)6 * g, o0);     // initial orthonormal coordinates (computed on the device for the solve)
                 else for (int i = 0; i < 6; i++) o0[i] = ls0[(size_t)6 * g + i];
                 if (!G) for (int i = 0; i < ld; i++) { const double d = ls[(size_t)ld * g + i] - o0[i]; d2 += d * d; }
-                r.ls_inlier[old] = (!G && std::sqrt(d2) > 0.01) ? 0 : 1;
+                r.ls_inlier[old] = (!G && !P.gba && std::sqrt(d2) > 0.01) ? 0 : 1;
             }
         }
         if (G) {

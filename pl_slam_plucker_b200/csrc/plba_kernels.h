@@ -47,7 +47,7 @@ struct WinCtrl {
     int n_lm_pt, n_lm_ls;            // landmark counts of the window (profile H normalisation)
     double lambda, ni, chi_cur, err_prev;
     double scale_pose, dx2_pose;     // pose part of computeScale() / ||DX||^2 (replicated on every rank, never all-reduced)
-    int n_trials, pad2;
+    int n_trials, n_obs;             // n_obs: observations of the window (GBA normalisation in FIXED mode)
 };
 // per-window accumulators that ARE summed over ranks (landmark-sharded multi-GPU):
 // assemble-phase sums live in P.acc[4*w + ...], update-phase sums in P.accB[4*w + ...] (two all-reduce ranges)
@@ -58,7 +58,7 @@ struct DevP {
     Cam cam;
     int profile, fixed_quirks;
     int n_win, n_kf, n_free, n_pt, n_ls, n_pobs, n_lobs;
-    int n_chunks_pt, n_chunks_ls, max_rounds, pad0;
+    int n_chunks_pt, n_chunks_ls, max_rounds, gba;   // gba: Global BA shell around profile H_END (PLBA_SHELL_GBA)
     int iters_stage1, iters_stage2, lm_max_trials, max_iters_lba;
     double huber_delta, chi2_gate, homog_th, min_error, min_error_change, lm_tau, lambda_lba_lm, lambda_lba_k;
     // keyframes
@@ -716,7 +716,10 @@ PLBA_D void lambda_init_window(const DevP &P, int w) {
         for (int i = 0; i < 6 * nf; i++) { const double h = fabs(plba_ld_l2(&P.hpp_diag_init[(size_t)6 * s0 + i])); if (h > m) m = h; P.hpp_diag_init[(size_t)6 * s0 + i] = 0.0; }
         P.accmax[w] = 0.0;
         if (P.profile == PLBA_PROFILE_G) { c.lambda = P.lm_tau * m; c.ni = 2.0; }
-        else c.lambda = P.lambda_lba_lm * m;
+        else {
+            if (P.gba && !P.fixed_quirks) m = (double)(long long)m;      // `int Hmax` of the GBA shell (src/mapHandler.cpp:3386-3391)
+            c.lambda = P.lambda_lba_lm * m;
+        }
         c.need_init = 0;
         plba_atomic_add_i(&P.counters[CNT_NEED_INIT], -1);
     }
@@ -730,8 +733,8 @@ PLBA_D void control_h_pre_window(const DevP &P, int w) {
     const double err_pt = plba_ld_l2(&P.acc[(size_t)4 * w + ACC_ERR_PT]), err_ls = plba_ld_l2(&P.acc[(size_t)4 * w + ACC_ERR_LS]);
     double err = err_pt + err_ls;
     const double zero = 0.0;
-    const bool div0 = !P.fixed_quirks && (c.iter == 0 || P.profile == PLBA_PROFILE_H_PLK);    // Q1
-    err = div0 ? err / zero : err / (double)(c.n_lm_pt + c.n_lm_ls);
+    const bool div0 = !P.fixed_quirks && (c.iter == 0 || P.profile == PLBA_PROFILE_H_PLK || P.gba);    // Q1 (GBA: every iteration, :3662)
+    err = div0 ? err / zero : err / (P.gba ? (double)c.n_obs : (double)(c.n_lm_pt + c.n_lm_ls));
     c.chi_cur = err;
     c.apply = 1; c.stop_code = 0;
     if (c.iter > 0) {

@@ -527,7 +527,7 @@ PLBA_KERNEL void k_back_block(const DevP *Pp, int w, int k0, int nb) {
 // last QB columns x RB rows; S is read once (band only), L is written back in place for the backward substitution.
 // O(n * band^2) instead of O(n^3 / 3): n = 12 000, band 14 blocks -> 0.1 GFLOP instead of 576.
 enum { BAND_MAX = 15 /* blocks */, BAND_RB = 6 * (BAND_MAX + 1), BAND_QB = 6 * BAND_MAX, BAND_LDR = BAND_RB + 1 };
-static inline size_t solve_banded_smem() { return sizeof(double) * ((size_t)BAND_QB * BAND_LDR + BAND_QB + BAND_RB + (BAND_RB + 2) * 6 + 8 * (BAND_RB + 2) * 6 + 64) + 64; }
+static inline size_t solve_banded_smem() { return sizeof(double) * ((size_t)BAND_QB * BAND_LDR + BAND_QB + BAND_RB + 2 * (BAND_RB + 2) * 6 + 256 * 6 + 64) + 64; }
 
 PLBA_KERNEL void k_solve_banded(const DevP *Pp, int bwb) {
     PLBA_SMEM(raw);
@@ -540,14 +540,13 @@ PLBA_KERNEL void k_solve_banded(const DevP *Pp, int bwb) {
         double *ring = (double *)raw;                          // ring[(q % QB) * ldr + (r % RB)] = L[r][q]
         double *yring = ring + (size_t)BAND_QB * BAND_LDR;     // y[q % QB]   (the right-hand side rides along as one more row)
         double *xring = yring + BAND_QB;                       // backward substitution: x[r % RB]
-        double *Pn = xring + BAND_RB;                          // [RB + 1][6] the panel being built (row RB = right-hand side)
-        double *part = Pn + (BAND_RB + 2) * 6;                 // [<= 256][6] partial sums
-        double *Lb = part + 8 * (BAND_RB + 2) * 6;             // [0..20] diagonal block staged for the backward pass, [40] fail flag
+        double *Pn0 = xring + BAND_RB;                         // two panel buffers [RB + 1][6] (row nr = right-hand side): the raw entries of
+        double *Pn1 = Pn0 + (BAND_RB + 2) * 6;                 //   panel kb+1 are staged while panel kb is factored
+        double *part = Pn1 + (BAND_RB + 2) * 6;                // [<= 256][6] partial sums
+        double *Lb = part + 256 * 6;                           // [0..20] diagonal block staged for the backward pass, [24..29] rhs, [40] fail flag
         double *Sw = P.S + P.win_S_off[w];
         double *x = P.xp + (size_t)6 * slot0;
         const double lambda = ctl.lambda;
-        // raw (un-factored) entries of one panel: rows k0 .. k0+nr-1 of its six columns (upper storage: contiguous in the row index)
-        // plus the right-hand side; staged into Pn one panel ahead by threads that are idle in the factor phase
         PHASE_BEGIN
             if (tid == 0) Lb[40] = 0.0;
             const int nr0 = (n < RB) ? n : RB;
@@ -557,10 +556,11 @@ PLBA_KERNEL void k_solve_banded(const DevP *Pp, int bwb) {
                 if (rr == nr0) v = P.gs[(size_t)6 * slot0 + c];
                 else if (rr >= c) { v = Sw[(size_t)c * n + rr]; if (rr == c) v += (P.profile == PLBA_PROFILE_G) ? lambda : lambda * P.hpp_diag[(size_t)6 * slot0 + rr]; }
                 else v = 0.0;
-                Pn[rr * 6 + c] = v;
+                Pn0[rr * 6 + c] = v;
             }
         PHASE_END
         for (int kb = 0; kb < nf; kb++) {
+            double *Pn = (kb & 1) ? Pn1 : Pn0, *Pnext = (kb & 1) ? Pn0 : Pn1;
             const int k0 = 6 * kb;
             const int nr = (n - k0 < RB) ? n - k0 : RB;       // band rows of this panel: r = k0 + rr, rr < nr; rr == nr is the rhs row
             const int m = nr + 1;
@@ -578,13 +578,20 @@ PLBA_KERNEL void k_solve_banded(const DevP *Pp, int bwb) {
                     const int q0 = qlo + sp * qs, q1 = (q0 + qs < k0) ? q0 + qs : k0;
                     double acc[6] = {0, 0, 0, 0, 0, 0};
                     int rslot = kslot + rr; if (rslot >= RB) rslot -= RB;
-                    int qc = (q0 < q1) ? q0 % QB : 0;
-                    for (int q = q0; q < q1; q++) {
+                    // the ring wraps at most once inside [q0, q1): two straight runs, each unrollable
+                    int qc = (q0 < q1) ? q0 % QB : 0, left = q1 - q0;
+                    while (left > 0) {
+                        const int run = (QB - qc < left) ? QB - qc : left;
                         const double *col = ring + (size_t)qc * ldr;
-                        const double v = rhs ? yring[qc] : col[rslot];
+                        const double *src = rhs ? yring + qc : col + rslot;
+                        const int sstride = rhs ? 1 : ldr;
+#pragma unroll 4
+                        for (int t = 0; t < run; t++) {
+                            const double v = src[(size_t)t * sstride];
 #pragma unroll
-                        for (int c = 0; c < 6; c++) acc[c] += v * col[kslot + c];
-                        if (++qc == QB) qc = 0;
+                            for (int c = 0; c < 6; c++) acc[c] += v * col[(size_t)t * ldr + kslot + c];
+                        }
+                        left -= run; qc = 0;
                     }
 #pragma unroll
                     for (int c = 0; c < 6; c++) part[((size_t)sp * mpad + rr) * 6 + c] = acc[c];
@@ -600,7 +607,20 @@ PLBA_KERNEL void k_solve_banded(const DevP *Pp, int bwb) {
             PHASE_END
             PHASE_BEGIN
                 const int rr = 6 + tid;                        // rows below the diagonal block (incl. the rhs row at rr == nr)
-                if (rr <= nr || tid == 0) {
+                if (tid >= 128) {
+                    // the upper half of the CTA is idle while the lower half factors: it stages the raw entries of the NEXT panel
+                    if (kb + 1 < nf) {
+                        const int k1 = k0 + 6, nr1 = (n - k1 < RB) ? n - k1 : RB;
+                        for (int idx = tid - 128; idx < 6 * (nr1 + 1); idx += PLBA_NT - 128) {
+                            const int c = idx / (nr1 + 1), r1 = idx - c * (nr1 + 1);
+                            double v;
+                            if (r1 == nr1) v = P.gs[(size_t)6 * slot0 + k1 + c];
+                            else if (r1 >= c) { v = Sw[(size_t)(k1 + c) * n + k1 + r1]; if (r1 == c) v += (P.profile == PLBA_PROFILE_G) ? lambda : lambda * P.hpp_diag[(size_t)6 * slot0 + k1 + r1]; }
+                            else v = 0.0;
+                            Pnext[r1 * 6 + c] = v;
+                        }
+                    }
+                } else if (rr <= nr || tid == 0) {
                     double L[21], inv[6];
 #pragma unroll
                     for (int i = 0; i < 6; i++) {
@@ -654,20 +674,6 @@ PLBA_KERNEL void k_solve_banded(const DevP *Pp, int bwb) {
                     }
                 }
             PHASE_END
-            PHASE_BEGIN
-                // stage the raw entries of the NEXT panel (Pn is free again): global loads issued by all threads at once
-                if (kb + 1 < nf) {
-                    const int k1 = k0 + 6, nr1 = (n - k1 < RB) ? n - k1 : RB;
-                    for (int idx = tid; idx < 6 * (nr1 + 1); idx += PLBA_NT) {
-                        const int c = idx / (nr1 + 1), rr = idx - c * (nr1 + 1);
-                        double v;
-                        if (rr == nr1) v = P.gs[(size_t)6 * slot0 + k1 + c];
-                        else if (rr >= c) { v = Sw[(size_t)(k1 + c) * n + k1 + rr]; if (rr == c) v += (P.profile == PLBA_PROFILE_G) ? lambda : lambda * P.hpp_diag[(size_t)6 * slot0 + k1 + rr]; }
-                        else v = 0.0;
-                        Pn[rr * 6 + c] = v;
-                    }
-                }
-            PHASE_END
         }
         // backward substitution L^T x = y, last panel first: x_k = L_kk^-T (y_k - sum over the band rows below of L[r][k-cols] x_r)
         for (int kb = nf - 1; kb >= 0; kb--) {
@@ -676,21 +682,25 @@ PLBA_KERNEL void k_solve_banded(const DevP *Pp, int bwb) {
             const int kslot = k0 % RB;
             PHASE_BEGIN
                 // 6 columns x 32 lanes: lane-strided partial dot products over the rows below the diagonal block (contiguous in memory);
-                // the seventh warp stages the factored diagonal block
+                // the seventh warp stages the factored diagonal block and the right-hand side
                 const int c = tid >> 5, lane = tid & 31;
                 if (c < 6) {
                     double sum = 0.0;
                     const double *col = Sw + (size_t)(k0 + c) * n + k0;
                     for (int rr = 6 + lane; rr < nr; rr += 32) { int xs_ = kslot + rr; if (xs_ >= RB) xs_ -= RB; sum += col[rr] * xring[xs_]; }
+#ifndef PLBA_HOST_EMU
+                    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+                    if (lane == 0) part[c * 33] = sum;
+#else
                     part[c * 33 + lane] = sum;
-                } else if (c == 6 && lane < 21) {
-                    int i = 0; while ((i + 1) * (i + 2) / 2 <= lane) i++;
-                    const int j = lane - i * (i + 1) / 2;
-                    Lb[lane] = Sw[(size_t)(k0 + j) * n + k0 + i];
+#endif
+                } else if (c == 6) {
+                    if (lane < 21) {
+                        int i = 0; while ((i + 1) * (i + 2) / 2 <= lane) i++;
+                        const int j = lane - i * (i + 1) / 2;
+                        Lb[lane] = Sw[(size_t)(k0 + j) * n + k0 + i];
+                    } else if (lane < 27) Lb[24 + lane - 21] = x[k0 + lane - 21];
                 }
-            PHASE_END
-            PHASE_BEGIN
-                if (tid < 6) { double sum = x[k0 + tid]; for (int l = 0; l < 32; l++) sum -= part[tid * 33 + l]; Lb[24 + tid] = sum; }
             PHASE_END
             PHASE_BEGIN
                 if (tid == 0) {
@@ -698,6 +708,11 @@ PLBA_KERNEL void k_solve_banded(const DevP *Pp, int bwb) {
 #pragma unroll
                     for (int c = 5; c >= 0; c--) {
                         double v = Lb[24 + c];
+#ifndef PLBA_HOST_EMU
+                        v -= part[c * 33];
+#else
+                        for (int l = 0; l < 32; l++) v -= part[c * 33 + l];
+#endif
 #pragma unroll
                         for (int mm = c + 1; mm < 6; mm++) v -= Lb[mm * (mm + 1) / 2 + c] * xs[mm];
                         xs[c] = v / Lb[c * (c + 1) / 2 + c];

@@ -10,6 +10,8 @@
 //   int  localBundleAdjustmentForPluker()                      src/mapHandler.cpp:1505-1615
 //   int  levMarquardtOptimizationLBAForPluker(...)             src/mapHandler.cpp:1618-2332   -> PLBA_PROFILE_H_PLK
 //   void localBundleAdjustmentForPlukerWithG2O()               src/mapHandler.cpp:5851-6323   -> PLBA_PROFILE_G
+//   void globalBundleAdjustment()                              src/mapHandler.cpp:3022-3126
+//   void levMarquardtOptimizationGBA(X_aux, kf_list, ...)      src/mapHandler.cpp:3128-3728   -> PLBA_PROFILE_H_END + PLBA_SHELL_GBA
 //
 // Only index bookkeeping (flattening, write-back, observation erasure) happens here; every FP64 operation of the path
 // runs in the CUDA library.  If the library reports an error the shim throws: there is no CPU fallback.
@@ -88,6 +90,14 @@ public:
         return hand_lm(PLBA_PROFILE_H_PLK, X_aux, kf_list, pt_list, ls_list, pt_obs_list, ls_obs_list);
     }
 
+    // ---- global BA, run once at shutdown (app/plslam_dataset.cpp:174): every non-NULL KF but KF 0, every non-NULL landmark ----
+    void globalBundleAdjustment() { Gathered g = gather(false, true); levMarquardtOptimizationGBA(g.X, g.kfs, g.pts, g.lss, g.pt_obs, g.ls_obs); }   // no emptiness test (:3120)
+    void levMarquardtOptimizationGBA(std::vector<double> X_aux, std::vector<int> kf_list, std::vector<int> pt_list, std::vector<int> ls_list,
+                                     std::vector<Vector6i> pt_obs_list, std::vector<Vector6i> ls_obs_list) {
+        if (pt_obs_list.size() + ls_obs_list.size() == 0) return;      // the reference would factor an empty system; nothing to write back
+        hand_lm(PLBA_PROFILE_H_END, X_aux, kf_list, pt_list, ls_list, pt_obs_list, ls_obs_list, PLBA_SHELL_GBA);
+    }
+
     // ---- the Plücker-mode LBA that actually runs in the reference (src/mapHandler.cpp:5851-6323) ----
     void localBundleAdjustmentForPlukerWithG2O() {
         std::vector<MapPoint *> lpt; std::vector<MapLine *> lls;
@@ -159,19 +169,19 @@ private:
         return {std::atan2(u2[2], c[2] / cn), std::asin(-u1[2]), std::atan2(u1[1], u1[0]), std::asin(dn / std::sqrt(nn * nn + dn * dn))};
     }
 
-    Gathered gather(bool pluker) {
+    Gathered gather(bool pluker, bool global = false) {
         Gathered g;
-        for (KeyFrame *kf : map_keyframes) if (kf && kf->local && kf->kf_idx != 0) { for (double v : kf->x_kf_w) g.X.push_back(v); g.kfs.push_back(kf->kf_idx); }
+        for (KeyFrame *kf : map_keyframes) if (kf && (global || kf->local) && kf->kf_idx != 0) { for (double v : kf->x_kf_w) g.X.push_back(v); g.kfs.push_back(kf->kf_idx); }
         std::unordered_map<int, int> pos;                                                    // replaces the O(Nobs*Nkf) search (:1437-1444)
         for (size_t j = 0; j < g.kfs.size(); j++) pos[g.kfs[j]] = (int)j;
         int loc = 0;
-        for (MapPoint *p : map_points) if (p && p->local) {
+        for (MapPoint *p : map_points) if (p && (global || p->local)) {
             for (double v : p->point3D) g.X.push_back(v);
             for (size_t i = 0; i < p->obs_list.size(); i++) { const int k = p->kf_obs_list[i]; g.pt_obs.push_back({p->idx, loc, (int)i, k, pos.count(k) ? pos[k] : -1, 1}); }
             g.pts.push_back(p->idx); loc++;
         }
         loc = 0;
-        for (MapLine *l : map_lines) if (l && l->local) {
+        for (MapLine *l : map_lines) if (l && (global || l->local)) {
             size_t n_obs;
             if (pluker) { const Vector4d o = pluker_to_orth(l->NDw); for (double v : o) g.X.push_back(v); n_obs = (quirks == PLBA_QUIRKS_FAITHFUL) ? l->obs_list.size() : l->NDw_obs_list.size(); }   // Q10 (:1582)
             else { for (double v : l->line3D) g.X.push_back(v); n_obs = l->obs_list.size(); }
@@ -181,7 +191,7 @@ private:
         return g;
     }
 
-    Out run(Flat &f, int profile, int n_pt, int n_ls) {
+    Out run(Flat &f, int profile, int n_pt, int n_ls, int shell = PLBA_SHELL_LBA) {
         plba_problem P{};
         P.n_kf = (int)f.kf_slot.size(); P.n_free = 0; for (int s : f.kf_slot) if (s >= 0) P.n_free++;
         P.n_pt = n_pt; P.n_ls = n_ls; P.n_pobs = (int)f.po_lm.size(); P.n_lobs = (int)f.lo_lm.size();
@@ -191,7 +201,7 @@ private:
         P.po_lm = f.po_lm.data(); P.po_kf = f.po_kf.data(); P.po_uv = f.po_uv.data(); P.po_sig2 = f.po_sig2.empty() ? nullptr : f.po_sig2.data();
         P.lo_lm = f.lo_lm.data(); P.lo_kf = f.lo_kf.data(); P.lo_ab = f.lo_ab.data(); P.lo_sig2 = f.lo_sig2.empty() ? nullptr : f.lo_sig2.data();
         plba_options opt; plba_default_options(profile, &opt);
-        opt.quirks = quirks; opt.lambda_lba_lm = config.lambda_lba_lm; opt.lambda_lba_k = config.lambda_lba_k; opt.max_iters_lba = config.max_iters_lba;
+        opt.quirks = quirks; opt.shell = shell; opt.lambda_lba_lm = config.lambda_lba_lm; opt.lambda_lba_k = config.lambda_lba_k; opt.max_iters_lba = config.max_iters_lba;
         opt.homog_th = config.homog_th; opt.min_error = config.min_error; opt.min_error_change = config.min_error_change;
         Out o;
         o.kf_T.resize(12 * (size_t)P.n_kf); o.pt_xyz.resize(3 * (size_t)n_pt); o.ls_plk.resize(6 * (size_t)n_ls); o.ls_end.resize(6 * (size_t)n_ls);
@@ -208,7 +218,7 @@ private:
     }
 
     int hand_lm(int profile, const std::vector<double> &X, const std::vector<int> &kf_list, const std::vector<int> &pt_list, const std::vector<int> &ls_list,
-                const std::vector<Vector6i> &pt_obs_list, const std::vector<Vector6i> &ls_obs_list) {
+                const std::vector<Vector6i> &pt_obs_list, const std::vector<Vector6i> &ls_obs_list, int shell = PLBA_SHELL_LBA) {
         const int Nkf = (int)kf_list.size();
         const int Npt = pt_obs_list.empty() ? 0 : pt_obs_list.back()[1] + 1;                 // :2359-2360
         const int Nls = ls_obs_list.empty() ? 0 : ls_obs_list.back()[1] + 1;                 // :2441-2442
@@ -236,8 +246,8 @@ private:
         if (profile == PLBA_PROFILE_H_END) f.ls_end.assign(lx, lx + 6 * Nls);
         else for (int i = 0; i < Nls; i++) for (double v : map_lines.at(ls_list[i])->NDw) f.ls_plk.push_back(v);   // pass 0 reads the MAP Plücker vector (:1744)
         (void)dl;
-        Out o = run(f, profile, Npt, Nls);
-        if (vo_status == VO_INSERTING_KF) return -1;                                         // computed but discarded (:2841, :3011-3012)
+        Out o = run(f, profile, Npt, Nls, shell);
+        if (shell == PLBA_SHELL_LBA && vo_status == VO_INSERTING_KF) return -1;                                         // computed but discarded (:2841, :3011-3012)
         for (int i = 0; i < Nkf; i++) pull_T(o.kf_T, i, map_keyframes[kf_list[i]]->T_kf_w);   // write-back under m_insert_kf (:2844-2882)
         for (int i = 0; i < Npt; i++) { MapPoint *p = map_points[pt_list[i]]; if (!o.pt_inlier[i]) p->inlier = false; for (int k = 0; k < 3; k++) p->point3D[k] = o.pt_xyz[3 * i + k]; }
         for (int i = 0; i < Nls; i++) {

@@ -84,22 +84,23 @@ class MapHandler:
         self.last_result = None
 
     # ------------------------------------------------------------------ drivers (flattening) -----------------
-    def _gather(self, pluker):
-        """src/mapHandler.cpp:1396-1493 (and the Plücker twin :1509-1607): X_aux, id lists and Vector6i observation tuples."""
+    def _gather(self, pluker, global_ba=False):
+        """src/mapHandler.cpp:1396-1493 (and the Plücker twin :1509-1607): X_aux, id lists and Vector6i observation tuples.
+        global_ba: the flattening of globalBundleAdjustment (:3022-3117), which ignores the `local` flags."""
         X_aux, kf_list = [], []
         for kf in self.map_keyframes:
-            if kf is not None and kf.local and kf.kf_idx != 0:
+            if kf is not None and (global_ba or kf.local) and kf.kf_idx != 0:
                 X_aux.extend(kf.x_kf_w.tolist()); kf_list.append(kf.kf_idx)
         kf_pos = {k: j for j, k in enumerate(kf_list)}     # replaces the O(Nobs*Nkf) linear search (:1437-1444)
         pt_obs_list, pt_list = [], []
-        for loc, pt in enumerate(p for p in self.map_points if p is not None and p.local):
+        for loc, pt in enumerate(p for p in self.map_points if p is not None and (global_ba or p.local)):
             X_aux.extend(pt.point3D.tolist())
             for i in range(len(pt.obs_list)):
                 kfo = pt.kf_obs_list[i]
                 pt_obs_list.append((pt.idx, loc, i, kfo, kf_pos.get(kfo, -1), 1))
             pt_list.append(pt.idx)
         ls_obs_list, ls_list = [], []
-        for loc, ls in enumerate(l for l in self.map_lines if l is not None and l.local):
+        for loc, ls in enumerate(l for l in self.map_lines if l is not None and (global_ba or l.local)):
             if pluker:
                 X_aux.extend(_pluker_to_orth(ls.NDw).tolist())       # :1577
                 n_obs = len(ls.obs_list) if self.quirks == abi.QUIRKS_FAITHFUL else len(ls.NDw_obs_list)   # Q10 (:1582)
@@ -124,14 +125,23 @@ class MapHandler:
             return self.levMarquardtOptimizationLBAForPluker(*a)
         return -1
 
+    def globalBundleAdjustment(self):
+        """src/mapHandler.cpp:3022-3126: every non-NULL KF but KF 0 and every non-NULL landmark; void, no emptiness test."""
+        self.levMarquardtOptimizationGBA(*self._gather(False, global_ba=True))
+
     # ------------------------------------------------------------------ hand-LM entry points -----------------
+    def levMarquardtOptimizationGBA(self, X_aux, kf_list, pt_list, ls_list, pt_obs_list, ls_obs_list):
+        """src/mapHandler.cpp:3128-3728 (include/mapHandler.h:137): H_END arithmetic inside the GBA shell; returns nothing."""
+        if len(pt_obs_list) + len(ls_obs_list) != 0:
+            self._hand_lm(abi.PROFILE_H_END, X_aux, kf_list, pt_list, ls_list, pt_obs_list, ls_obs_list, shell=abi.SHELL_GBA)
+
     def levMarquardtOptimizationLBA(self, X_aux, kf_list, pt_list, ls_list, pt_obs_list, ls_obs_list):
         return self._hand_lm(abi.PROFILE_H_END, X_aux, kf_list, pt_list, ls_list, pt_obs_list, ls_obs_list)
 
     def levMarquardtOptimizationLBAForPluker(self, X_aux, kf_list, pt_list, ls_list, pt_obs_list, ls_obs_list):
         return self._hand_lm(abi.PROFILE_H_PLK, X_aux, kf_list, pt_list, ls_list, pt_obs_list, ls_obs_list)
 
-    def _hand_lm(self, profile, X_aux, kf_list, pt_list, ls_list, pt_obs_list, ls_obs_list):
+    def _hand_lm(self, profile, X_aux, kf_list, pt_list, ls_list, pt_obs_list, ls_obs_list, shell=abi.SHELL_LBA):
         X = np.asarray(X_aux, dtype=np.float64)
         Nkf = len(kf_list)
         Npt = (pt_obs_list[-1][1] + 1) if len(pt_obs_list) else 0          # :2359-2360
@@ -163,12 +173,12 @@ class MapHandler:
                            np.array([ob[1] for ob in po], np.int32), np.array([row_of[ob[3]] for ob in po], np.int32), po_uv,
                            ls_plk=ls_plk, ls_end=ls_end, lo_lm=np.array([ob[1] for ob in lo], np.int32),
                            lo_kf=np.array([row_of[ob[3]] for ob in lo], np.int32), lo_ab=lo_ab, x_pose=X[:6 * Nkf].reshape(-1, 6))
-        opt = abi.Options(profile, self.quirks, lambda_lba_lm=self.cfg.lambda_lba_lm, lambda_lba_k=self.cfg.lambda_lba_k,
+        opt = abi.Options(profile, self.quirks, shell=shell, lambda_lba_lm=self.cfg.lambda_lba_lm, lambda_lba_k=self.cfg.lambda_lba_k,
                           max_iters_lba=self.cfg.max_iters_lba, homog_th=self.cfg.homog_th, min_error=self.cfg.min_error,
                           min_error_change=self.cfg.min_error_change)
         res = self.solver.solve(prob, opt)
         self.last_result = res
-        if self.vo_status == VO_INSERTING_KF:               # :2841 / :3011-3012 : computed but discarded
+        if shell == abi.SHELL_LBA and self.vo_status == VO_INSERTING_KF:               # :2841 / :3011-3012 : computed but discarded
             return -1
         # write-back under m_insert_kf (:2844-2882)
         for i in range(Nkf):

@@ -36,6 +36,8 @@ int main(int argc, char **argv) {
         std::printf("hand_lm rc=%d iters=%zu\n", rc, mh.last_trace.size());
         mh.vo_status = VO_INSERTING_KF;
         std::printf("discarded rc=%d\n", mh.localBundleAdjustmentForPluker());
+        mh.globalBundleAdjustment();                                  // shutdown-time global BA: ignores vo_status and the `local` flags, returns nothing
+        std::printf("gba iters=%zu\n", mh.last_trace.size());
     } catch (const std::exception &e) { std::fprintf(stderr, "error: %s\n", e.what()); plba_scene_destroy(sc); return 1; }
     plba_scene_destroy(sc);
     return 0;

@@ -23,4 +23,5 @@ test_batch_equals_individual_solves = g.test_batch_equals_individual_solves
 test_reduced_system_blocks_and_sparsity = g.test_reduced_system_blocks_and_sparsity
 test_edge_cases = g.test_edge_cases
 test_sigma_weights = g.test_sigma_weights
+test_global_ba_shell = g.test_global_ba_shell
 test_map_handler_interface = g.test_map_handler_interface

@@ -54,13 +54,13 @@ def test_config2_kitti_window(gpu_solver, oracle, prof, q):
     _check(gpu_solver, oracle, P, prof, q)
 
 
-@pytest.mark.parametrize("name", ["g_faithful", "g_fixed", "h_end_faithful", "h_plk_fixed"])
+@pytest.mark.parametrize("name", ["g_faithful", "g_fixed", "h_end_faithful", "h_plk_fixed", "gba_faithful", "gba_fixed"])
 def test_golden_fixtures(gpu_solver, name):
     """Committed vectors (tests/golden/make_golden.py) — no oracle involved at run time."""
     z = np.load(os.path.join(GOLD, name + ".npz"))
     prob = abi.Problem(z["cam"], z["kf_T_wc"], z["kf_slot"], z["pt_xyz"], z["po_lm"], z["po_kf"], z["po_uv"], ls_plk=z["ls_plk"],
                        ls_end=z["ls_end"], lo_lm=z["lo_lm"], lo_kf=z["lo_kf"], lo_ab=z["lo_ab"], x_pose=z["x_pose"])
-    r = gpu_solver.solve(prob, abi.Options(int(z["profile"]), int(z["quirks"])))
+    r = gpu_solver.solve(prob, abi.Options(int(z["profile"]), int(z["quirks"]), shell=int(z["shell"]) if "shell" in z else abi.SHELL_LBA))
     n = int(z["n_robust"])
     fin = np.isfinite(z["trace_chi"][:n])
     np.testing.assert_allclose(r.trace["chi"][:n][fin], z["trace_chi"][:n][fin], rtol=COST_RTOL)
@@ -192,6 +192,29 @@ def test_edge_cases(gpu_solver, oracle):
         gpu_solver.solve(unsorted, abi.Options(abi.PROFILE_G))
 
 
+@pytest.mark.parametrize("q", [0, 1])
+def test_global_ba_shell(gpu_solver, oracle, q):
+    """levMarquardtOptimizationGBA (src/mapHandler.cpp:3128-3728) = the H_END observation terms inside a
+    different LM shell (truncated `int Hmax`, epsilon() stop tests, err /= 0 in every iteration, no inlier rule);
+    every keyframe but KF 0 is free."""
+    P = scene.make_scene(1, n_kf_free=12, n_kf_fixed=1, n_pt=400, n_ls=100, line_mode=1, seed=31)
+    opt = abi.Options(abi.PROFILE_H_END, q, shell=abi.SHELL_GBA)
+    r, o = gpu_solver.solve(P, opt), oracle.solve(P, opt)
+    assert r.rc == o.rc == abi.OK
+    assert_trace_close(o.trace, r.trace, abi.PROFILE_H_END)
+    assert_state_close(o, r, P, abi.PROFILE_H_END)
+    assert r.pt_inlier.all() and r.ls_inlier.all()                     # no `inlier` rule on the GBA write-back (:3705-3726)
+    lba = oracle.solve(P, abi.Options(abi.PROFILE_H_END, q))
+    if q == 0:
+        # faithful: the cost is x/0 in EVERY iteration, so no stop test ever fires and all max_iters_lba passes run
+        assert len(r.trace) == opt.max_iters_lba and not np.isfinite(r.trace["chi"][1:]).any()
+        assert r.trace["lambda"][0] <= lba.trace["lambda"][0] and r.trace["lambda"][0] > lba.trace["lambda"][0] - 1e-5 * 1.0000001   # lambda0 = 1e-5 * trunc(Hmax)
+    # the shell is rejected for the other profiles
+    from pl_slam_plucker_b200.solver import LBAError
+    with pytest.raises(LBAError):
+        gpu_solver.solve(P, abi.Options(abi.PROFILE_G, q, shell=abi.SHELL_GBA))
+
+
 def test_sigma_weights(gpu_solver, oracle):
     """Omega = I / sigma^2 rounded through float (src/mapHandler.cpp:6009-6010, Q13)."""
     P = scene.make_scene(1, n_kf_free=4, n_kf_fixed=2, n_pt=80, n_ls=20, seed=8)
@@ -228,6 +251,17 @@ def test_map_handler_interface(gpu_solver, oracle):
     np.testing.assert_allclose(np.array([p.point3D for p in mh.map_points]), o.pt_xyz, atol=STATE_ATOL)
     mh.vo_status = mhm.VO_INSERTING_KF
     assert mh.localBundleAdjustment() == -1               # computed but discarded (:3011-3012)
+    # global BA entry point (:3022-3126): ignores the `local` flags, frees every KF but kf_idx 0, returns nothing
+    Pg = scene.make_scene(1, n_kf_free=6, n_kf_fixed=1, n_pt=150, n_ls=40, seed=14, line_mode=1)
+    mh = mhm.map_from_problem(Pg, gpu_solver, endpoint_lines=True)
+    for lm in mh.map_points + mh.map_lines:
+        lm.local = False
+    assert mh.globalBundleAdjustment() is None
+    o = oracle.solve(Pg, abi.Options(abi.PROFILE_H_END, 0, shell=abi.SHELL_GBA))
+    for k in range(Pg.n_kf):
+        np.testing.assert_allclose(mh.map_keyframes[k].T_kf_w[:3, :].reshape(12), o.kf_T_wc[k], atol=STATE_ATOL)
+    np.testing.assert_allclose(np.array([p.point3D for p in mh.map_points]), o.pt_xyz, atol=STATE_ATOL)
+    np.testing.assert_allclose(np.array([l.line3D for l in mh.map_lines]), o.ls_end, atol=STATE_ATOL)
 
 
 def test_config3_full_batch(gpu_solver, oracle):

@@ -141,13 +141,36 @@ def test_h_faithful_first_error_is_infinite(oracle, emu):
     assert r.trace["accepted"][1] == 1                                              # inf as err_prev => first loop step applied
 
 
-@pytest.mark.parametrize("name", ["g_faithful", "g_fixed", "h_end_faithful", "h_plk_fixed"])
+@pytest.mark.parametrize("quirks", [0, 1])
+def test_global_ba_shell(oracle, emu, quirks):
+    """levMarquardtOptimizationGBA (src/mapHandler.cpp:3128-3728): Schur == literal dense solve inside the GBA shell too;
+    faithful: lambda0 = 1e-5 * trunc(Hmax) (`int Hmax`, :3386-3392), cost x/0 in every pass => all passes run, all applied."""
+    P = scene.make_scene(1, lib=emu, n_kf_free=6, n_kf_fixed=1, n_pt=80, n_ls=20, line_mode=1, seed=77)
+    opt = abi.Options(abi.PROFILE_H_END, quirks, shell=abi.SHELL_GBA)
+    a, b = oracle.solve(P, opt), oracle.solve(P, opt, dense=True)
+    assert len(a.trace) == len(b.trace)
+    np.testing.assert_allclose(a.kf_T_wc, b.kf_T_wc, atol=1e-10)
+    np.testing.assert_allclose(a.pt_xyz, b.pt_xyz, atol=1e-9)
+    assert a.pt_inlier.all() and a.ls_inlier.all()                     # no `inlier` rule (:3705-3726)
+    lba = oracle.solve(P, abi.Options(abi.PROFILE_H_END, quirks))
+    if quirks == 0:
+        assert len(a.trace) == opt.max_iters_lba and np.isinf(a.trace["chi"]).all() and (a.trace["accepted"][1:] == 1).all()
+        lam_g, lam_l = a.trace["lambda"][1], lba.trace["lambda"][1]      # lambda in force for the first loop pass
+        hmax = lam_l / 1e-5
+        np.testing.assert_allclose(lam_g, 1e-5 * np.floor(hmax), rtol=1e-12)
+    else:
+        # intended maths: finite cost normalised by the observation count; epsilon() thresholds => runs longer than the LBA shell
+        assert np.isfinite(a.trace["chi"]).all() and len(a.trace) >= len(lba.trace)
+        np.testing.assert_allclose(a.trace["chi"][0] * P.n_obs, lba.trace["chi"][0] * (P.n_pt + P.n_ls), rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["g_faithful", "g_fixed", "h_end_faithful", "h_plk_fixed", "gba_faithful", "gba_fixed"])
 def test_golden_fixtures(oracle, name):
     """Committed oracle outputs (tests/golden/make_golden.py): guards the oracle against silent drift."""
     z = np.load(os.path.join(GOLD, name + ".npz"))
     prob = abi.Problem(z["cam"], z["kf_T_wc"], z["kf_slot"], z["pt_xyz"], z["po_lm"], z["po_kf"], z["po_uv"], ls_plk=z["ls_plk"],
                        ls_end=z["ls_end"], lo_lm=z["lo_lm"], lo_kf=z["lo_kf"], lo_ab=z["lo_ab"], x_pose=z["x_pose"])
-    r = oracle.solve(prob, abi.Options(int(z["profile"]), int(z["quirks"])))
+    r = oracle.solve(prob, abi.Options(int(z["profile"]), int(z["quirks"]), shell=int(z["shell"]) if "shell" in z else abi.SHELL_LBA))
     n = int(z["n_robust"])
     fin = np.isfinite(z["trace_chi"][:n])
     np.testing.assert_allclose(r.trace["chi"][:n][fin], z["trace_chi"][:n][fin], rtol=1e-9)
