@@ -201,6 +201,11 @@ int  plba_time_kernel(plba_handle h, int32_t which, int32_t reps, double lambda,
  * than 15 free keyframes (sliding-window shape), by the dense tensor-core (FP64 DMMA) Cholesky otherwise.  on != 0 forces the
  * dense path (benchmarks, tests). */
 int  plba_set_force_dense(plba_handle h, int on);
+/* Assembly / update have two implementations: warp-autonomous kernels (one warp per run of landmarks with identical keyframe
+ * sequence; large uploads whose longest track has at most 32 observations) and CTA-chunk kernels (everything else).
+ * mode 0 = route by size (default), 1 = always the CTA-chunk kernels, 2 = the warp kernels whenever the tracks allow
+ * (tests, A/B measurements; also the PLBA_FORCE_CHUNK environment variable). */
+int  plba_set_force_chunk(plba_handle h, int mode);
 /* Layout of the resident problem, for roofline accounting: out8 = { point chunks, line chunks, point segments, line segments,
  * off-diagonal Schur tasks, diagonal Schur tasks, structurally non-zero upper 6x6 blocks of S (nnzb), device arena bytes }. */
 int  plba_layout_stats(plba_handle h, int64_t *out8);

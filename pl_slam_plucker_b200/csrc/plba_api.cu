@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <chrono>
 #include "plba_solver.h"
+#include "plba_warp.h"
 
 using namespace plba;
 
@@ -56,6 +57,10 @@ struct plba_handle_s {
     std::vector<unsigned char> mark;
     int ls_dim = 4, max_nf = 0, solve_class = 1, band_blocks = 0;
     bool force_dense = false;
+    int force_chunk = 0;             // 0 = route by size, 1 = always the CTA-chunk kernels, 2 = the warp kernels whenever every track fits a warp
+    bool warp_path = true;           // this upload runs on the warp-autonomous kernels (plba_warp.h)
+    std::vector<WItem> wi_pt, wi_ls;
+    int grid_warp = 592;
     bool uploaded = false, small_path = true;
     double *sysbuf = nullptr; size_t sys_doubles = 0, S_doubles = 0;
     int h_counters[CNT_N] = {0};
@@ -66,9 +71,9 @@ struct plba_handle_s {
     bool detail_timing = false, no_graph = false;
     int grid_chunks = 296, grid_solve = 148;
 #ifndef PLBA_HOST_EMU
-    cudaGraph_t graph[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};       // [profile * 2 + size class of the reduced system]
-    cudaGraphExec_t gexec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaGraphConditionalHandle cond_while[6]{}, cond_prep[6]{};
+    cudaGraph_t graph[12]{};       // [(profile * 2 + size class of the reduced system) * 2 + warp path]
+    cudaGraphExec_t gexec[12]{};
+    cudaGraphConditionalHandle cond_while[12]{}, cond_prep[12]{};
 #endif
     void release() {
         if (d_arena) cudaFree(d_arena);
@@ -252,6 +257,8 @@ int plba_create(int32_t device, void *stream, plba_handle *out) {
     h->no_graph = ng && ng[0] == '1';
     const char *fd = std::getenv("PLBA_FORCE_DENSE");        // large windows: always take the dense DMMA Cholesky (tests, benchmarks)
     h->force_dense = fd && fd[0] == '1';
+    const char *fc = std::getenv("PLBA_FORCE_CHUNK");        // always take the CTA-chunk assembly / update kernels (tests, A/B runs)
+    h->force_chunk = fc ? std::atoi(fc) : 0;
 #else
     h->no_graph = true;
 #endif
@@ -273,7 +280,7 @@ void plba_destroy(plba_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
 #ifndef PLBA_HOST_EMU
-    for (int i = 0; i < 6; i++) { if (h->gexec[i]) cudaGraphExecDestroy(h->gexec[i]); if (h->graph[i]) cudaGraphDestroy(h->graph[i]); }
+    for (int i = 0; i < 12; i++) { if (h->gexec[i]) cudaGraphExecDestroy(h->gexec[i]); if (h->graph[i]) cudaGraphDestroy(h->graph[i]); }
 #endif
     h->release();
     if (h->d_P) cudaFree(h->d_P);
@@ -298,6 +305,8 @@ template <int PROF> static void set_smem_attr() {
     if (!done) {
         cudaFuncSetAttribute(k_assemble<PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemMax<PROF>::bytes());
         cudaFuncSetAttribute(k_update<PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemMax<PROF>::bytes());
+        cudaFuncSetAttribute(k_assemble_w<PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WARPS_PER_CTA * WSmemMax<PROF>::bytes()));
+        cudaFuncSetAttribute(k_update_w<PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WARPS_PER_CTA * WSmemMax<PROF>::bytes()));
         cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_small_smem(1));
         cudaFuncSetAttribute(k_solve_banded, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_banded_smem());
         cudaFuncSetAttribute(k_potrf_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_block_smem());
@@ -325,11 +334,51 @@ static int chunk_occupancy_for(int prof) {
     if (cache[prof]) return cache[prof];
     return cache[prof] = prof == PLBA_PROFILE_G ? chunk_occupancy<PLBA_PROFILE_G>() : prof == PLBA_PROFILE_H_END ? chunk_occupancy<PLBA_PROFILE_H_END>() : chunk_occupancy<PLBA_PROFILE_H_PLK>();
 }
+// warp path: persistent grid of WARPS_PER_CTA-warp CTAs (emulation: one warp per "CTA")
+template <int PROF> static int warp_occupancy() {
+#ifndef PLBA_HOST_EMU
+    int a = 1, b = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_assemble_w<PROF>, WNT, WARPS_PER_CTA * WSmemMax<PROF>::bytes());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_update_w<PROF>, WNT, WARPS_PER_CTA * WSmemMax<PROF>::bytes());
+    return std::max(1, std::min(a, b));
+#else
+    return 1;
+#endif
+}
+static int warp_occupancy_for(int prof) {
+    static int cache[3] = {0, 0, 0};
+    if (cache[prof]) return cache[prof];
+    return cache[prof] = prof == PLBA_PROFILE_G ? warp_occupancy<PLBA_PROFILE_G>() : prof == PLBA_PROFILE_H_END ? warp_occupancy<PLBA_PROFILE_H_END>() : warp_occupancy<PLBA_PROFILE_H_PLK>();
+}
+static size_t warp_smem(int prof) {
+    const size_t w = prof == PLBA_PROFILE_G ? WSmemMax<PLBA_PROFILE_G>::bytes() : prof == PLBA_PROFILE_H_END ? WSmemMax<PLBA_PROFILE_H_END>::bytes() : WSmemMax<PLBA_PROFILE_H_PLK>::bytes();
+#ifndef PLBA_HOST_EMU
+    return WARPS_PER_CTA * w;
+#else
+    return w;
+#endif
+}
+#ifndef PLBA_HOST_EMU
+static inline dim3 warp_block() { return dim3(WNT); }
+#else
+static inline dim3 warp_block() { return dim3(32); }
+#endif
 static size_t chunk_smem(int prof) {
     return prof == PLBA_PROFILE_G ? SmemMax<PLBA_PROFILE_G>::bytes() : prof == PLBA_PROFILE_H_END ? SmemMax<PLBA_PROFILE_H_END>::bytes() : SmemMax<PLBA_PROFILE_H_PLK>::bytes();
 }
 static void launch_assemble(plba_handle h, int mode) {
-    const DevP *Pp = h->d_P; const dim3 g(h->grid_chunks), b(OC); const size_t sm = chunk_smem(h->opt.profile);
+    const DevP *Pp = h->d_P;
+    if (h->warp_path) {
+        const dim3 g(h->grid_warp), b = warp_block(); const size_t sm = warp_smem(h->opt.profile);
+        switch (h->opt.profile) {
+        case PLBA_PROFILE_G: PLBA_LAUNCH((k_assemble_w<PLBA_PROFILE_G>), g, b, sm, h->stream, Pp, mode); break;
+        case PLBA_PROFILE_H_END: PLBA_LAUNCH((k_assemble_w<PLBA_PROFILE_H_END>), g, b, sm, h->stream, Pp, mode); break;
+        default: PLBA_LAUNCH((k_assemble_w<PLBA_PROFILE_H_PLK>), g, b, sm, h->stream, Pp, mode); break;
+        }
+        h->timing.n_launches++; if (mode == 1) h->timing.n_assemble++;
+        return;
+    }
+    const dim3 g(h->grid_chunks), b(OC); const size_t sm = chunk_smem(h->opt.profile);
     switch (h->opt.profile) {
     case PLBA_PROFILE_G: PLBA_LAUNCH((k_assemble<PLBA_PROFILE_G>), g, b, sm, h->stream, Pp, mode); break;
     case PLBA_PROFILE_H_END: PLBA_LAUNCH((k_assemble<PLBA_PROFILE_H_END>), g, b, sm, h->stream, Pp, mode); break;
@@ -338,7 +387,18 @@ static void launch_assemble(plba_handle h, int mode) {
     h->timing.n_launches++; if (mode == 1) h->timing.n_assemble++;
 }
 static void launch_update(plba_handle h, int flags) {
-    const DevP *Pp = h->d_P; const dim3 g(h->grid_chunks), b(OC); const size_t sm = chunk_smem(h->opt.profile);
+    const DevP *Pp = h->d_P;
+    if (h->warp_path) {
+        const dim3 g(h->grid_warp), b = warp_block(); const size_t sm = warp_smem(h->opt.profile);
+        switch (h->opt.profile) {
+        case PLBA_PROFILE_G: PLBA_LAUNCH((k_update_w<PLBA_PROFILE_G>), g, b, sm, h->stream, Pp, flags); break;
+        case PLBA_PROFILE_H_END: PLBA_LAUNCH((k_update_w<PLBA_PROFILE_H_END>), g, b, sm, h->stream, Pp, flags); break;
+        default: PLBA_LAUNCH((k_update_w<PLBA_PROFILE_H_PLK>), g, b, sm, h->stream, Pp, flags); break;
+        }
+        h->timing.n_launches++;
+        return;
+    }
+    const dim3 g(h->grid_chunks), b(OC); const size_t sm = chunk_smem(h->opt.profile);
     switch (h->opt.profile) {
     case PLBA_PROFILE_G: PLBA_LAUNCH((k_update<PLBA_PROFILE_G>), g, b, sm, h->stream, Pp, flags); break;
     case PLBA_PROFILE_H_END: PLBA_LAUNCH((k_update<PLBA_PROFILE_H_END>), g, b, sm, h->stream, Pp, flags); break;
@@ -412,7 +472,7 @@ static cudaError_t add_kernel(cudaGraph_t g, cudaGraphNode_t *node, cudaGraphNod
     return cudaGraphAddKernelNode(node, g, dep ? &dep : nullptr, dep ? 1 : 0, &kp);
 }
 template <int PROF> static int build_graph(plba_handle h) {
-    const int pi = PROF * 2 + h->solve_class;
+    const int pi = (PROF * 2 + h->solve_class) * 2 + (h->warp_path ? 1 : 0);
     if (h->gexec[pi]) return PLBA_OK;
     set_all_attrs();
     cudaGraph_t g = nullptr;
@@ -430,16 +490,18 @@ template <int PROF> static int build_graph(plba_handle h) {
     CK(cudaGraphAddNode(&inode, body, nullptr, 0, &ip));
     cudaGraph_t prep = ip.conditional.phGraph_out[0];
     const DevP *Pp = h->d_P;
-    const dim3 gc(h->n_sm * chunk_occupancy<PROF>()), bc(OC); const size_t smc = SmemMax<PROF>::bytes();
+    const dim3 gc(h->warp_path ? h->n_sm * warp_occupancy<PROF>() : h->n_sm * chunk_occupancy<PROF>()), bc(h->warp_path ? (int)WNT : (int)OC);
+    const size_t smc = h->warp_path ? WARPS_PER_CTA * WSmemMax<PROF>::bytes() : SmemMax<PROF>::bytes();
+    void *f_asm = h->warp_path ? (void *)k_assemble_w<PROF> : (void *)k_assemble<PROF>, *f_upd = h->warp_path ? (void *)k_update_w<PROF> : (void *)k_update<PROF>;
     int mode0 = 0, mode1 = 1, fl = KF_FUSE_CONTROL | KF_IN_GRAPH;
     void *a_p[1] = {(void *)&Pp}, *a_m0[2] = {(void *)&Pp, (void *)&mode0}, *a_m1[2] = {(void *)&Pp, (void *)&mode1}, *a_fl[2] = {(void *)&Pp, (void *)&fl};
     cudaGraphNode_t n1, n2, n3, m1, m2, m3;
     CK(add_kernel(prep, &n1, nullptr, (void *)k_gate, dim3(h->grid_chunks), dim3(256), 0, a_p));
-    CK(add_kernel(prep, &n2, n1, (void *)k_assemble<PROF>, gc, bc, smc, a_m0));
+    CK(add_kernel(prep, &n2, n1, f_asm, gc, bc, smc, a_m0));
     CK(add_kernel(prep, &n3, n2, (void *)k_lambda_init, dim3(h->n_sm), dim3(128), 0, a_p));
-    CK(add_kernel(body, &m1, inode, (void *)k_assemble<PROF>, gc, bc, smc, a_m1));
+    CK(add_kernel(body, &m1, inode, f_asm, gc, bc, smc, a_m1));
     CK(add_kernel(body, &m2, m1, (void *)k_solve_small, dim3(h->grid_solve), dim3(256), solve_small_smem(h->solve_class), a_p));
-    CK(add_kernel(body, &m3, m2, (void *)k_update<PROF>, gc, bc, smc, a_fl));
+    CK(add_kernel(body, &m3, m2, f_upd, gc, bc, smc, a_fl));
     CK(cudaGraphInstantiate(&h->gexec[pi], g, 0));
     h->graph[pi] = g;
     return PLBA_OK;
@@ -499,6 +561,11 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     h->grid_solve = h->n_sm * (h->solve_class == 0 ? 4 : 1);
     set_all_attrs();
     h->grid_chunks = h->n_sm * chunk_occupancy_for(prof);
+#ifndef PLBA_HOST_EMU
+    h->grid_warp = h->n_sm * warp_occupancy_for(prof);
+#else
+    h->grid_warp = 24;               // emulation: 24 one-warp "CTAs"
+#endif
 
     // ---- index work: signature order, chunks, segments --------------------------------------------------------
     std::vector<Chunk> &ch_pt = h->ch_pt, &ch_ls = h->ch_ls; std::vector<Seg> &sg_pt = h->sg_pt, &sg_ls = h->sg_ls; std::vector<int> &fp_pt = h->fp_pt, &fp_ls = h->fp_ls;
@@ -514,7 +581,73 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
         signature_order(p.n_pt, p.n_pobs, p.po_lm, p.po_kf, true, Lps[w]);
         signature_order(p.n_ls, p.n_lobs, p.lo_lm, p.lo_kf, prof != PLBA_PROFILE_H_END, Lls[w]);   // Q3 addresses endpoint lines by position
     }
-    for (int w = 0; w < n; w++) {
+    // route: the warp-autonomous kernels take windows whose longest track fits a warp; anything longer (or force_chunk) runs on the
+    // CTA-chunk kernels
+    int max_track = 0;
+    for (int w = 0; w < n; w++) for (int cls = 0; cls < 2; cls++) {
+        const ClassLayout &L = cls ? Lls[w] : Lps[w];
+        for (size_t l = 0; l + 1 < L.optr.size(); l++) max_track = std::max(max_track, L.optr[l + 1] - L.optr[l]);
+    }
+    // small uploads (less than about two passes per resident warp) are latency-bound: there the CTA-chunk kernels, whose warps share
+    // their instruction stream, measured faster (profiles/README.md r01f)
+    const int64_t n_obs_total = (int64_t)tot.n_pobs + tot.n_lobs;
+    const bool big = n_obs_total >= (int64_t)64 * h->grid_warp * WARPS_PER_CTA;
+    h->warp_path = h->force_chunk != 1 && max_track <= W_MAX_TRACK && (big || h->force_chunk == 2);
+    std::vector<WItem> &wi_pt = h->wi_pt, &wi_ls = h->wi_ls;
+    wi_pt.clear(); wi_ls.clear();
+    for (int w = 0; w < n && h->warp_path; w++) {
+        // runs of landmarks with identical keyframe sequence (kept as Seg records: n_lm unbounded, no chunk fields)
+        const plba_problem &p = probs[w]; const WinInfo &wi = h->wins[w];
+        for (int cls = 0; cls < 2; cls++) {
+            const ClassLayout &L = cls ? Lls[w] : Lps[w];
+            const int nl = cls ? p.n_ls : p.n_pt, lm0 = cls ? wi.ls0 : wi.pt0, ob0 = cls ? wi.lo0 : wi.po0;
+            const int32_t *kf = cls ? p.lo_kf : p.po_kf;
+            std::vector<int> &perm = cls ? h->ls_perm : h->pt_perm, &operm = cls ? h->lo_perm : h->po_perm, &ptr = cls ? ls_ptr : pt_ptr;
+            std::vector<Seg> &sgs = cls ? sg_ls : sg_pt; std::vector<int> &fps = cls ? fp_ls : fp_pt;
+            int ob = ob0, run_first_old = -1;
+            for (int nl_i = 0; nl_i < nl; nl_i++) {
+                const int old = L.perm[nl_i], a = L.optr[old], b = L.optr[old + 1], no = b - a;
+                const int g = lm0 + nl_i;
+                perm[g] = lm0 + old;
+                bool join = false;
+                if (run_first_old >= 0) {
+                    Seg &s = sgs.back();
+                    if (s.nobs == no) {
+                        const int fa = L.optr[run_first_old];
+                        if (!L.group.empty()) join = (L.group[run_first_old] == L.group[old]);
+                        else { join = true; for (int i = 0; i < no; i++) if (kf[fa + i] != kf[a + i]) { join = false; break; } }
+                    }
+                    if (join) s.n_lm++;
+                }
+                if (!join) {      // (a run of landmarks WITHOUT observations has nobs = 0: only the update kernel visits it)
+                    Seg s{}; s.lm0 = g; s.n_lm = 1; s.nobs = no; s.fp0 = (int)fps.size(); s.pad1 = w;
+                    for (int i = 0; i < no; i++) if (p.kf_slot[kf[a + i]] >= 0) { fps.push_back(i); s.nfree++; }
+                    sgs.push_back(s); run_first_old = old;
+                }
+                ptr[g] = ob;
+                for (int i = a; i < b; i++) operm[ob++] = ob0 + i;
+            }
+            ptr[lm0 + nl] = ob;
+        }
+    }
+    if (h->warp_path) {
+        // cut the runs into items of up to W_ITEM_PASSES_MAX passes (fewer when the upload is small)
+        int64_t total_passes = 0;
+        for (int cls = 0; cls < 2; cls++) for (const Seg &sg : (cls ? sg_ls : sg_pt)) { const int lpp = sg.nobs ? 32 / sg.nobs : 32; total_passes += (sg.n_lm + lpp - 1) / lpp; }
+        const int64_t warps = (int64_t)h->grid_warp * WARPS_PER_CTA;
+        const int item_passes = (int)std::max<int64_t>(1, std::min<int64_t>(W_ITEM_PASSES_MAX, total_passes / (8 * warps)));   // items are dealt dynamically: >= 8 per warp keeps the tail short
+        for (int cls = 0; cls < 2; cls++) {
+            std::vector<WItem> &items = cls ? wi_ls : wi_pt; const std::vector<int> &ptr = cls ? ls_ptr : pt_ptr;
+            for (const Seg &sg : (cls ? sg_ls : sg_pt)) {
+                const int lpp = sg.nobs ? 32 / sg.nobs : 32, step = lpp * item_passes;
+                for (int l = 0; l < sg.n_lm; l += step) {
+                    WItem it{}; it.lm0 = sg.lm0 + l; it.n_lm = std::min(step, sg.n_lm - l); it.ob0 = ptr[it.lm0]; it.k = sg.nobs; it.win = sg.pad1; it.nfree = sg.nfree; it.fp0 = sg.fp0;
+                    items.push_back(it);
+                }
+            }
+        }
+    }
+    for (int w = 0; w < n && !h->warp_path; w++) {
         const plba_problem &p = probs[w]; const WinInfo &wi = h->wins[w];
         const ClassLayout &Lp = Lps[w], &Ll = Lls[w];
         for (int cls = 0; cls < 2; cls++) {
@@ -600,6 +733,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     const size_t i_po_om = ci.take<double>(tot.n_pobs), i_lo_om = ci.take<double>(tot.n_lobs);
     const size_t i_ch_pt = ci.take<Chunk>(ch_pt.size()), i_ch_ls = ci.take<Chunk>(ch_ls.size()), i_sg_pt = ci.take<Seg>(sg_pt.size()), i_sg_ls = ci.take<Seg>(sg_ls.size());
     const size_t i_fp_pt = ci.take<int>(fp_pt.size()), i_fp_ls = ci.take<int>(fp_ls.size());
+    const size_t i_wi_pt = ci.take<WItem>(wi_pt.size()), i_wi_ls = ci.take<WItem>(wi_ls.size());
     const size_t i_ctrl0 = ci.take<WinCtrl>(n);
     h->in_bytes = ci.off; h->i_pts0 = i_pts0; h->i_lns0 = i_lns0; h->i_lmap = i_lmap;
     long long S_off = 0;
@@ -644,6 +778,8 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     if (!sg_ls.empty()) std::memcpy(hb + i_sg_ls, sg_ls.data(), sizeof(Seg) * sg_ls.size());
     if (!fp_pt.empty()) std::memcpy(hb + i_fp_pt, fp_pt.data(), sizeof(int) * fp_pt.size());
     if (!fp_ls.empty()) std::memcpy(hb + i_fp_ls, fp_ls.data(), sizeof(int) * fp_ls.size());
+    if (!wi_pt.empty()) std::memcpy(hb + i_wi_pt, wi_pt.data(), sizeof(WItem) * wi_pt.size());
+    if (!wi_ls.empty()) std::memcpy(hb + i_wi_ls, wi_ls.data(), sizeof(WItem) * wi_ls.size());
     const bool par_lm = (n <= 8);       // one (or few) big windows: parallel over landmarks; batches: parallel over windows
 #pragma omp parallel for schedule(dynamic, 4) if (!par_lm)
     for (int w = 0; w < n; w++) {
@@ -718,6 +854,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     P.po_uv = (double *)(db + i_po_uv); P.lo_ab = (double *)(db + i_lo_ab); P.po_om = (double *)(db + i_po_om); P.lo_om = (double *)(db + i_lo_om);
     P.chunks_pt = (Chunk *)(db + i_ch_pt); P.chunks_ls = (Chunk *)(db + i_ch_ls); P.segs_pt = (Seg *)(db + i_sg_pt); P.segs_ls = (Seg *)(db + i_sg_ls);
     P.freepos_pt = (int *)(db + i_fp_pt); P.freepos_ls = (int *)(db + i_fp_ls);
+    P.witems_pt = (WItem *)(db + i_wi_pt); P.witems_ls = (WItem *)(db + i_wi_ls); P.n_witems_pt = (int)wi_pt.size(); P.n_witems_ls = (int)wi_ls.size();
     P.ctrl0 = (WinCtrl *)(db + i_ctrl0);
     for (int b = 0; b < 2; b++) { P.poseT[b] = (double *)(db + s_poseT[b]); P.Xkf[b] = (double *)(db + s_X[b]); P.pts[b] = (double *)(db + s_pts[b]); P.lns[b] = (double *)(db + s_lns[b]); }
     P.po_lvl = (unsigned char *)(db + s_po_lvl); P.lo_lvl = (unsigned char *)(db + s_lo_lvl);
@@ -731,7 +868,8 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
 #ifndef PLBA_HOST_EMU
     if (h->small_path && !h->no_graph) {
         if ((rc = build_graph_for(h, prof))) return rc;
-        P.cond_while = (unsigned long long)h->cond_while[prof * 2 + h->solve_class]; P.cond_prep = (unsigned long long)h->cond_prep[prof * 2 + h->solve_class];
+        const int pi = (prof * 2 + h->solve_class) * 2 + (h->warp_path ? 1 : 0);
+        P.cond_while = (unsigned long long)h->cond_while[pi]; P.cond_prep = (unsigned long long)h->cond_prep[pi];
     }
 #endif
     *h->h_P = P;
@@ -783,7 +921,7 @@ static int run_async(plba_handle h) {
     h->timing.ms_assemble = h->timing.ms_solve = h->timing.ms_update = 0;
 #ifndef PLBA_HOST_EMU
     if (use_graph(h)) {
-        CK(cudaGraphLaunch(h->gexec[P.profile * 2 + h->solve_class], st));
+        CK(cudaGraphLaunch(h->gexec[(P.profile * 2 + h->solve_class) * 2 + (h->warp_path ? 1 : 0)], st));
         return PLBA_OK;
     }
 #endif
@@ -1012,6 +1150,7 @@ int plba_debug_prof(unsigned long long *out64, int reset) {
 }
 #endif
 int plba_set_force_dense(plba_handle h, int on) { if (!h) return PLBA_E_ARG; h->force_dense = on != 0; return PLBA_OK; }
+int plba_set_force_chunk(plba_handle h, int mode) { if (!h || mode < 0 || mode > 2) return PLBA_E_ARG; h->force_chunk = mode; return PLBA_OK; }
 int plba_layout_stats(plba_handle h, int64_t *out8) { if (!h || !h->uploaded || !out8) return PLBA_E_ARG; for (int i = 0; i < 8; i++) out8[i] = h->layout[i]; return PLBA_OK; }
 int plba_get_timing(plba_handle h, plba_timing *t) { if (!h || !t) return PLBA_E_ARG; *t = h->timing; return PLBA_OK; }
 int plba_set_detail_timing(plba_handle h, int on) { if (!h) return PLBA_E_ARG; h->detail_timing = on != 0; return PLBA_OK; }

@@ -42,6 +42,11 @@ struct Chunk { int lm0, lm1, ob0, ob1, win, seg0, seg1, pad; };
 // nfree of them in free keyframes at positions freepos[fp0 .. fp0+nfree); task0 = first (pose pair) task of the run in its chunk
 struct Seg { int lm0, n_lm, nobs, nfree, task0, fp0, dtask0, pad1; };   // task0 / dtask0: first off-diagonal / diagonal task
 
+// warp-path work item (plba_warp.h): a slice of a run of landmarks with identical keyframe sequence: n_lm consecutive landmarks
+// (internal order) from lm0, k observations each starting at ob0; nfree of the k track positions are free keyframes:
+// positions freepos[fp0 .. fp0 + nfree)
+struct WItem { int lm0, n_lm, ob0, k, win, nfree, fp0, pad; };
+
 struct WinCtrl {
     int cur, stage, iter, trial, need_init, do_gate, done, n_trace, solve_fail, apply, stop_code, pad;
     int n_lm_pt, n_lm_ls;            // landmark counts of the window (profile H normalisation)
@@ -52,7 +57,8 @@ struct WinCtrl {
 // per-window accumulators that ARE summed over ranks (landmark-sharded multi-GPU):
 // assemble-phase sums live in P.acc[4*w + ...], update-phase sums in P.accB[4*w + ...] (two all-reduce ranges)
 enum { ACC_CHI_LIN = 0, ACC_ERR_PT = 1, ACC_ERR_LS = 2, ACC_CHI_NEW = 0, ACC_SCALE = 1, ACC_DX2 = 2, ACC_N = 8 };
-enum { CNT_DONE = 0, CNT_NEED_INIT = 1, CNT_GATE = 2, CNT_TRIALS = 3, CNT_TICKET = 4, CNT_ROUNDS = 5, CNT_PREPS = 6, CNT_N = 8 };
+enum { CNT_DONE = 0, CNT_NEED_INIT = 1, CNT_GATE = 2, CNT_TRIALS = 3, CNT_TICKET = 4, CNT_ROUNDS = 5, CNT_PREPS = 6,
+       CNT_WORK_PT = 8, CNT_WORK_LS = 9, CNT_WTICKET = 10 /* warp path: next work item of each landmark class, CTA exit ticket */, CNT_N = 16 };
 
 struct DevP {
     Cam cam;
@@ -83,6 +89,7 @@ struct DevP {
     double *po_chi2, *lo_chi2;
     const Chunk *chunks_pt, *chunks_ls;
     const Seg *segs_pt, *segs_ls;
+    const WItem *witems_pt, *witems_ls; int n_witems_pt, n_witems_ls;
     const int *freepos_pt, *freepos_ls;
     // linear system
     double *S, *gs, *xp, *hpp_diag, *hpp_diag_init;
@@ -1030,6 +1037,7 @@ PLBA_KERNEL void k_reset(const DevP *Pp, int ls_dim, size_t sys_doubles, double 
             for (int w = 0; w < P.n_win; w++) ndone += P.ctrl0[w].done;
             P.counters[CNT_DONE] = ndone; P.counters[CNT_NEED_INIT] = P.n_win - ndone; P.counters[CNT_GATE] = 0;
             P.counters[CNT_TRIALS] = 0; P.counters[CNT_TICKET] = 0; P.counters[CNT_ROUNDS] = 0; P.counters[CNT_PREPS] = 0;
+            P.counters[CNT_WORK_PT] = 0; P.counters[CNT_WORK_LS] = 0; P.counters[CNT_WTICKET] = 0;
         }
     PHASE_END
 }

@@ -48,6 +48,23 @@ PLBA_D void plba_block_add(double *smem_dst, double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(smem_dst, v);     // <= 8 adds per call: the shared-memory CAS loop is fine here
 }
+// ---- warp-autonomous kernels (plba_warp.h): a warp owns its work item and its slice of shared memory; phases are separated
+// by __syncwarp only, so the warps of an SM drift apart and hide each other's latencies.  Lane-private values that live
+// across phases are plain registers here and per-lane arrays in the host emulation (LANE_VAR / LANE_ARR / LANE_BIND).
+#define WPHASE_BEGIN { const int lane = (int)(threadIdx.x & 31u); (void)lane;
+#define WPHASE_END } __syncwarp();
+#define PLBA_WARP_ID ((int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)))
+#define PLBA_NWARPS ((int)(gridDim.x * (blockDim.x >> 5)))
+#define PLBA_WARP_IN_CTA ((int)(threadIdx.x >> 5))
+#define LANE_VAR(T, name) T name
+#define LANE_ARR(T, name, N) T name[N]
+#define LANE_BIND(name)
+PLBA_D double plba_warp_sum(double v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
+PLBA_D double plba_warp_max(double v) { for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+// every lane of the warp calls these (inside a WPHASE): the warp's lanes are summed and leave the SM as one red / atomicMax
+#define PLBA_WARP_FLUSH_ADD(ptr, v) do { const double s_ = plba_warp_sum(v); if (lane == 0 && s_ != 0.0) plba_atomic_add((ptr), s_); } while (0)
+#define PLBA_WARP_FLUSH_MAX(ptr, v) do { const double s_ = plba_warp_max(v); if (lane == 0 && s_ > 0.0) plba_atomic_max_pos((ptr), s_); } while (0)
+PLBA_HD void plba_sincos(double x, double *s, double *c) { sincos(x, s, c); }
 // optional per-phase cycle accounting (development builds only: -DPLBA_PROF): thread 0 of every CTA adds the cycles between
 // two marks to a global table that tools read back through plba_debug_prof()
 #ifdef PLBA_PROF
@@ -110,6 +127,17 @@ inline void plba_atomic_add(double *p, double v) { *p += v; }
 inline void plba_atomic_add_i(int *p, int v) { *p += v; }
 inline void plba_atomic_max_pos(double *p, double v) { if (v > *p) *p = v; }
 inline void plba_block_add(double *d, double v) { *d += v; }
+#define WPHASE_BEGIN for (int lane = 0; lane < 32; ++lane) {
+#define WPHASE_END }
+#define PLBA_WARP_ID (plba_emu().bid)          // the emulation launches warp kernels with one warp per "CTA"
+#define PLBA_NWARPS (plba_emu().nb)
+#define PLBA_WARP_IN_CTA 0
+#define LANE_VAR(T, name) T name##_L[32]
+#define LANE_ARR(T, name, N) T name##_L[32][N]
+#define LANE_BIND(name) auto &name = name##_L[lane]
+#define PLBA_WARP_FLUSH_ADD(ptr, v) do { *(ptr) += (v); } while (0)
+#define PLBA_WARP_FLUSH_MAX(ptr, v) do { if ((v) > *(ptr)) *(ptr) = (v); } while (0)
+inline void plba_sincos(double x, double *s, double *c) { *s = std::sin(x); *c = std::cos(x); }
 #define PLBA_PARAMS(P, Pp) const DevP &P = *(Pp)
 #define PLBA_PARAMS_REF(P, Pin) const DevP &P = Pin
 #define PROF_DECL

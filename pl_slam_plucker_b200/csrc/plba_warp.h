@@ -1,0 +1,700 @@
+// Warp-autonomous assembly / update kernels (the default path; the CTA-chunk kernels of plba_kernels.h remain for windows
+// that contain a landmark with more than 32 observations).
+//
+// Work decomposition.  After the signature sort (plba_upload) landmarks seen by exactly the same keyframe sequence are
+// adjacent: a RUN.  A work ITEM is a slice of a run (<= a few passes); one warp owns an item from its first load to its
+// last red.global.add.  Inside an item every landmark has the same k observations in the same keyframes, so
+//   * lane t of a pass handles observation (landmark t / k, track position t % k): observation loads are contiguous
+//     (128-bit, coalesced), no per-observation index is read at all (the structure comes from the item descriptor),
+//   * the pose a lane works with never changes during the item,
+//   * the Schur tasks (pose pair (i <= j) of the track x two halves of three block rows) are the same for every landmark
+//     of the item: a lane keeps its 3x6 block IN REGISTERS across all passes and leaves the SM once per item.
+// Phases of a pass are separated by __syncwarp only (no block barrier anywhere in the loop): the 16 resident warps of an SM
+// drift apart and hide each other's latencies; the per-landmark work (H_ll, its inverse, v = H_ll^-1 b_l) is done
+// redundantly by all lanes of the landmark, which costs the same FP64-pipe slots as doing it on one lane and saves the
+// shared-memory round trip.
+#pragma once
+#include "plba_kernels.h"
+
+namespace plba {
+
+#ifndef PLBA_W_CTAS
+#define PLBA_W_CTAS 3      // resident 4-warp CTAs per SM the kernels are compiled for (register budget = 65536 / (128 * PLBA_W_CTAS))
+#endif
+#ifndef PLBA_W_PASSES
+#define PLBA_W_PASSES 8
+#endif
+enum { WARPS_PER_CTA = 4, WNT = 32 * WARPS_PER_CTA, W_CTAS_PER_SM = PLBA_W_CTAS, W_MAX_TRACK = 32, W_ITEM_PASSES_MAX = PLBA_W_PASSES };
+
+// per-warp shared memory: [component][lane] so that lane-indexed accesses are conflict free
+template <int PROF, int LT>
+struct WSmem {
+    typedef KT<PROF, LT> K;
+    enum { NA = K::RANK * 6, NB = K::RANK * K::D, NE = K::RANK, DOUBLES = (NA + 2 * NB + NE + K::D) * 32, INTS = 64 };
+    double *A, *B, *TA, *E, *V;
+    int *slot, *fpos;
+    static PLBA_HD size_t bytes() { return sizeof(double) * DOUBLES + sizeof(int) * INTS; }
+    PLBA_HD explicit WSmem(unsigned char *raw) {
+        double *p = (double *)raw;
+        A = p; p += NA * 32; B = p; p += NB * 32; TA = p; p += NB * 32; E = p; p += NE * 32; V = p; p += K::D * 32;
+        slot = (int *)p; fpos = slot + 32;
+    }
+};
+template <int PROF> struct WSmemMax {
+    static PLBA_HD size_t bytes() {
+        const size_t a = WSmem<PROF, LT_POINT>::bytes(), b = WSmem<PROF, LineOf<PROF>::LT>::bytes();
+        return a > b ? a : b;
+    }
+};
+
+// ---- landmark-only quantities, in registers (the warp path's form of lm_precompute) -------------------------------
+template <int LT> struct LmD;
+template <> struct LmD<LT_POINT> { double Pw[3]; };
+template <> struct LmD<LT_LINE_ORTH> { LinePre L; double o[4]; };
+template <> struct LmD<LT_LINE_END> { double Pw[3], Qw[3]; };
+
+// changeOrthToPluker with one sincos per angle (src/mapFeatures.cpp:203-224)
+PLBA_HD void orth_to_plk_sc(const double *o, double *pl) {
+    double s1, c1, s2, c2, s3, c3, w1, w2;
+    plba_sincos(o[0], &s1, &c1); plba_sincos(o[1], &s2, &c2); plba_sincos(o[2], &s3, &c3); plba_sincos(o[3], &w2, &w1);
+    pl[0] = w1 * (c2 * c3); pl[1] = w1 * (c2 * s3); pl[2] = w1 * (-s2);
+    pl[3] = w2 * (s1 * s2 * c3 - c1 * s3); pl[4] = w2 * (s1 * s2 * s3 + c1 * c3); pl[5] = w2 * (s1 * c2);
+}
+
+template <int PROF, int LT> struct LmLoad;
+template <int PROF> struct LmLoad<PROF, LT_POINT> {
+    static PLBA_HD void run(const DevP &, const WinCtrl &, int, int lm, const double *state, LmD<LT_POINT> &d) {
+        for (int i = 0; i < 3; i++) d.Pw[i] = state[(size_t)3 * lm + i];
+    }
+};
+template <int PROF> struct LmLoad<PROF, LT_LINE_ORTH> {
+    static PLBA_HD void run(const DevP &P, const WinCtrl &ctl, int, int lm, const double *state, LmD<LT_LINE_ORTH> &d) {
+        double pl[6];
+        for (int i = 0; i < 4; i++) d.o[i] = state[(size_t)4 * lm + i];
+        if (PROF == PLBA_PROFILE_H_PLK && ctl.iter == 0) { for (int i = 0; i < 6; i++) pl[i] = P.lns_map[(size_t)6 * lm + i]; }   // pass 0 reads map NDw (:1744)
+        else orth_to_plk_sc(d.o, pl);
+        line_pre_from_plk(pl, d.L);
+    }
+};
+template <int PROF> struct LmLoad<PROF, LT_LINE_END> {
+    static PLBA_HD void run(const DevP &P, const WinCtrl &ctl, int win, int lm, const double *state, LmD<LT_LINE_END> &d) {
+        // inside the loop the reference reads BOTH endpoints from offset 3*loc (Q3, :2697-2698)
+        const bool q3 = (!P.fixed_quirks && ctl.iter > 0);
+        const int l0 = P.win_ls0[win];
+        const size_t q3off = (size_t)6 * l0 + (size_t)3 * (lm - l0);      // endpoint lines are never re-ordered (see plba_upload)
+        for (int i = 0; i < 3; i++) {
+            d.Pw[i] = q3 ? state[q3off + i] : state[(size_t)6 * lm + i];
+            d.Qw[i] = q3 ? state[q3off + i] : state[(size_t)6 * lm + 3 + i];
+        }
+    }
+};
+
+template <int LT> struct ObsLoad;
+template <> struct ObsLoad<LT_POINT> {
+    double uv[2];
+    PLBA_HD void load(const DevP &P, int o) { const plba_d2 v = *(const plba_d2 *)(P.po_uv + (size_t)2 * o); uv[0] = v.x; uv[1] = v.y; }
+};
+template <> struct ObsLoad<LT_LINE_ORTH> {
+    double ab[4];
+    PLBA_HD void load(const DevP &P, int o) {
+        const plba_d2 a0 = *(const plba_d2 *)(P.lo_ab + (size_t)4 * o), a1 = *(const plba_d2 *)(P.lo_ab + (size_t)4 * o + 2);
+        ab[0] = a0.x; ab[1] = a0.y; ab[2] = a1.x; ab[3] = a1.y;
+    }
+};
+template <> struct ObsLoad<LT_LINE_END> : ObsLoad<LT_LINE_ORTH> {};
+
+// one observation -> scaled rows At = sqrt(w) J_pose, Bt = sqrt(w) J_lm, et = sqrt(w) e, in registers (same arithmetic as
+// obs_linearize; see there for the citations).  Returns false for an edge gated out of the active set (rows are zero).
+template <int PROF, int LT>
+PLBA_HD bool obs_lin_w(const DevP &P, const WinCtrl &ctl, int o, int kf, const LmD<LT> &lmd, const ObsLoad<LT> &ob, double *A, double *B, double *e, double &cost) {
+    typedef KT<PROF, LT> K;
+    typedef ObsAcc<LT> OA;
+    double wsq = 0.0;
+    bool active = true;
+    cost = 0.0;
+    if (PROF == PLBA_PROFILE_G) {
+        if (ctl.stage == 1 && OA::lvl(P)[o]) active = false;
+        if (active) {
+            const double *T = P.poseT[ctl.cur] + (size_t)12 * kf;
+            if constexpr (LT == LT_POINT) {
+                g_point_lin(P.cam, T, lmd.Pw, ob.uv, e, A, B);
+            } else if constexpr (LT == LT_LINE_ORTH) {
+                const LmD<LT_LINE_ORTH> &d = lmd; const ObsLoad<LT_LINE_ORTH> &q = ob;
+                double head[3], tail[3];
+                if (P.fixed_quirks) { for (int i = 0; i < 3; i++) { head[i] = d.L.n[i]; tail[i] = d.L.d[i]; } }
+                else { for (int i = 0; i < 3; i++) { head[i] = d.o[i]; tail[i] = d.o[1 + i]; } }   // Q12
+                g_line_lin(P.cam, T, d.L, head, tail, q.ab, e, A, B);
+            }
+            const double om = OA::om(P)[o];
+            const double chi2 = om * (e[0] * e[0] + e[1] * e[1]);
+            double rho0 = chi2, rho1 = 1.0;
+            if (ctl.stage == 0) huber(P.huber_delta, chi2, rho0, rho1);
+            cost = rho0;
+            wsq = sqrt(rho1 * om);
+        }
+    } else {
+        const bool pass0 = (ctl.iter == 0);
+        double r, w, Jp[6], Jl[6];
+        if constexpr (LT == LT_POINT) {
+            const double *T = P.poseT[ctl.cur] + (size_t)12 * kf;
+            h_point(P.cam, T, lmd.Pw, ob.uv, P.homog_th, Jp, Jl, r, w);
+        } else {
+            // Q4: inside the loop the line terms keep the MAP pose (:2700, :2010)
+            const double *T = (pass0 || P.fixed_quirks) ? P.poseT[ctl.cur] + (size_t)12 * kf : P.kf_Tmap + (size_t)12 * kf;
+            if constexpr (LT == LT_LINE_END) {
+                const double th = (pass0 || P.fixed_quirks) ? P.homog_th : 0.0000001;
+                h_endline(P.cam, T, lmd.Pw, lmd.Qw, ob.ab, th, P.fixed_quirks != 0, Jp, Jl, r, w);
+            } else {
+                h_plkline(P.cam, T, lmd.L, ob.ab, P.homog_th, P.fixed_quirks != 0, Jp, Jl, r, w);
+            }
+        }
+        wsq = sqrt(w);
+        for (int c = 0; c < 6; c++) A[c] = Jp[c];
+        for (int c = 0; c < K::D; c++) B[c] = Jl[c];
+        e[0] = -r;                 // g += J r w  ==  b = -J^T (w e) with e = -r
+        cost = w * r * r;
+    }
+    for (int i = 0; i < K::RANK * 6; i++) A[i] = active ? wsq * A[i] : 0.0;
+    for (int i = 0; i < K::RANK * K::D; i++) B[i] = active ? wsq * B[i] : 0.0;
+    for (int i = 0; i < K::RANK; i++) e[i] = active ? wsq * e[i] : 0.0;
+    return active;
+}
+
+// Schur task of a lane: pose pair (i <= j) of the free track positions, half = block rows hrow .. hrow + 2
+struct WTask { int on, pa, pb, sa, sb, hrow, diag, slice; };
+PLBA_HD void wtask_decode(int task, int nf, const int *fpos, const int *slot, int slot0, WTask &t) {
+    const int p = task >> 1;
+    t.hrow = 3 * (task & 1);
+    int q = p, i = 0;
+    while (q >= nf - i) { q -= nf - i; i++; }
+    const int j = i + q;
+    t.pa = fpos[i]; t.pb = fpos[j];
+    t.sa = slot[t.pa] - slot0; t.sb = slot[t.pb] - slot0;
+    t.diag = (i == j) ? 1 : 0;
+}
+
+// accumulate the landmarks m = first, first + step, ... < nlp of the pass into the lane's 3x6 block (and, on the diagonal, g / diag(H_pp))
+template <int PROF, int LT, int mode>
+PLBA_D void wtask_accumulate(const WSmem<PROF, LT> &sm, const WTask &t, int k, int first, int step, int nlp, double *blk, double *gv, double *hd) {
+    typedef KT<PROF, LT> K;
+    const int D = K::D, RANK = K::RANK;
+    for (int m = first; m < nlp; m += step) {
+        const int ta = m * k + t.pa, tb = m * k + t.pb;
+        if ((PROF != PLBA_PROFILE_G || mode == 0) && t.diag) {        // diag(H_pp): lambda init (all profiles) and the hand LM's multiplicative damping
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+#pragma unroll
+                for (int kk = 0; kk < RANK; kk++) { const double av = sm.A[(kk * 6 + t.hrow + r) * 32 + ta]; hd[r] += av * av; }
+            }
+        }
+        if (mode == 0) continue;
+        double M[RANK * RANK], MA[RANK * 6];
+        {
+            double Ta[RANK * D], Bb[RANK * D];
+#pragma unroll
+            for (int kk = 0; kk < RANK * D; kk++) { Ta[kk] = sm.TA[kk * 32 + ta]; Bb[kk] = sm.B[kk * 32 + tb]; }
+#pragma unroll
+            for (int kk = 0; kk < RANK; kk++) {
+#pragma unroll
+                for (int k2 = 0; k2 < RANK; k2++) {
+                    double sum = (t.diag && kk == k2) ? -1.0 : 0.0;          // diagonal: A^T (Ta B^T - I) A, subtracted below
+#pragma unroll
+                    for (int mm = 0; mm < D; mm++) sum += Ta[kk * D + mm] * Bb[k2 * D + mm];
+                    M[kk * RANK + k2] = sum;
+                }
+            }
+            if (t.diag) {
+                // g_a += -At^T (et + Bt v)
+                double ev[RANK];
+#pragma unroll
+                for (int kk = 0; kk < RANK; kk++) {
+                    double sum = sm.E[kk * 32 + ta];
+#pragma unroll
+                    for (int mm = 0; mm < D; mm++) sum += Bb[kk * D + mm] * sm.V[mm * 32 + ta];
+                    ev[kk] = sum;
+                }
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+#pragma unroll
+                    for (int kk = 0; kk < RANK; kk++) gv[r] -= sm.A[(kk * 6 + t.hrow + r) * 32 + ta] * ev[kk];
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            double ab[RANK];
+#pragma unroll
+            for (int k2 = 0; k2 < RANK; k2++) ab[k2] = sm.A[(k2 * 6 + c) * 32 + tb];
+#pragma unroll
+            for (int kk = 0; kk < RANK; kk++) {
+                double sum = 0;
+#pragma unroll
+                for (int k2 = 0; k2 < RANK; k2++) sum += M[kk * RANK + k2] * ab[k2];
+                MA[kk * 6 + c] = sum;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+#pragma unroll
+            for (int kk = 0; kk < RANK; kk++) {
+                const double av = sm.A[(kk * 6 + t.hrow + r) * 32 + ta];
+#pragma unroll
+                for (int c = 0; c < 6; c++) blk[r * 6 + c] -= av * MA[kk * 6 + c];
+            }
+        }
+    }
+}
+
+// the lane's block leaves the SM.  blk holds MINUS the Schur term, so S(a,b) += blk (upper storage; transposed if the pair is
+// stored the other way round), g, diag(H_pp).  Two observations of one landmark in the same keyframe (sa == sb off the track
+// diagonal: rare) put blk + blk^T onto the diagonal block.
+template <int PROF, int mode>
+PLBA_D void wtask_flush(const DevP &P, const WTask &t, double *Sw, int ld, int slot0, const double *blk, const double *gv, const double *hd) {
+    if (mode == 0) {
+        if (t.diag) {
+#pragma unroll
+            for (int r = 0; r < 3; r++) plba_atomic_add(&P.hpp_diag_init[(size_t)6 * (slot0 + t.sa) + t.hrow + r], hd[r]);
+        }
+        return;
+    }
+    const bool tr = (t.sa > t.sb);
+    const int ra = tr ? t.sb : t.sa, cb = tr ? t.sa : t.sb;
+    const long long sr = tr ? 1 : ld, sc = tr ? ld : 1;
+    double *p0 = Sw + (size_t)(6 * ra) * ld + 6 * cb + t.hrow * sr;
+    const bool upper_only = (t.sa == t.sb);                        // diagonal block of S: only its upper triangle is stored
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            if (!upper_only || t.hrow + r <= c) plba_atomic_add(p0 + r * sr + c * sc, blk[r * 6 + c]);
+        }
+    }
+    if (t.diag) {
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            plba_atomic_add(&P.gs[(size_t)6 * (slot0 + t.sa) + t.hrow + r], gv[r]);
+            if (PROF != PLBA_PROFILE_G) plba_atomic_add(&P.hpp_diag[(size_t)6 * (slot0 + t.sa) + t.hrow + r], hd[r]);
+        }
+    } else if (upper_only) {
+        // transposed copy of an off-track-diagonal block that landed on the diagonal of S
+        double *q0 = Sw + (size_t)(6 * t.sa) * ld + 6 * t.sa;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                if (c <= t.hrow + r) plba_atomic_add(q0 + (size_t)c * ld + t.hrow + r, blk[r * 6 + c]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// assembly: mode 0 = diagonal pass for the initial lambda (computeLambdaInit / Hmax, :2555-2561); mode 1 = full
+// ---------------------------------------------------------------------------------------------------------
+template <int PROF, int LT, int mode>
+PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, unsigned char *wraw) {
+    PLBA_PARAMS_REF(P, Pin);
+    typedef KT<PROF, LT> K;
+    typedef ObsAcc<LT> OA;
+    const int D = K::D, RANK = K::RANK;
+    WSmem<PROF, LT> sm(wraw);
+    LANE_VAR(double, cost_l); LANE_VAR(double, maxd_l);
+    LANE_ARR(double, blk, 18); LANE_ARR(double, gv, 3); LANE_ARR(double, hd, 3);
+    LANE_VAR(WTask, tk);
+    LANE_VAR(int, kf_l); LANE_VAR(int, m_l);
+    int cur_win = -1;
+    WPHASE_BEGIN
+        LANE_BIND(cost_l); LANE_BIND(maxd_l);
+        cost_l = 0.0; maxd_l = 0.0;
+    WPHASE_END
+    for (;;) {
+        // next work item: one atomic per warp (items differ in cost, a static deal leaves the slowest warp far behind)
+        WPHASE_BEGIN
+            if (lane == 0) sm.slot[48] = plba_atomic_fetch_add_i(&P.counters[LT == LT_POINT ? CNT_WORK_PT : CNT_WORK_LS], 1);
+        WPHASE_END
+        const int ii = sm.slot[48];
+        WPHASE_BEGIN
+        WPHASE_END
+        if (ii >= n_items) break;
+        const WItem it = items[ii];
+        const WinCtrl ctl = P.ctrl[it.win];             // the controller only runs between launches: a private copy is safe
+        if (ctl.done) continue;
+        if (mode == 0 && !ctl.need_init) continue;
+        if (it.k == 0) continue;                                  // landmarks without observations add nothing to the system
+        if (it.win != cur_win) {
+            if (cur_win >= 0) {
+                WPHASE_BEGIN
+                    LANE_BIND(cost_l); LANE_BIND(maxd_l);
+                    double *accw = P.acc + (size_t)4 * cur_win;
+                    if (mode == 1) PLBA_WARP_FLUSH_ADD((PROF == PLBA_PROFILE_G) ? &accw[ACC_CHI_LIN] : (LT == LT_POINT ? &accw[ACC_ERR_PT] : &accw[ACC_ERR_LS]), cost_l);
+                    else PLBA_WARP_FLUSH_MAX(&P.accmax[cur_win], maxd_l);
+                    cost_l = 0.0; maxd_l = 0.0;
+                WPHASE_END
+            }
+            cur_win = it.win;
+        }
+        const int k = it.k, nf = it.nfree;
+        const int lpp = 32 / k;                                  // landmarks per pass
+        const int npass = (it.n_lm + lpp - 1) / lpp;
+        const int ntask = nf * (nf + 1);                          // (pairs i <= j) x 2 halves
+        const int rounds = (ntask + 31) >> 5;
+        const bool keep = (rounds == 1);                          // the lane's block stays in registers for the whole item
+        const int nslice = (keep && ntask <= 16) ? 32 / ntask : 1;  // few tasks: the landmarks of a pass are dealt over several lanes per task
+        const int slot0 = P.win_slot0[it.win];
+        const int ld = 6 * P.win_nfree[it.win];
+        double *Sw = P.S + P.win_S_off[it.win];
+        const double *state = OA::state(P, ctl.cur);
+        WPHASE_BEGIN
+            LANE_BIND(kf_l); LANE_BIND(m_l);
+            m_l = lane / k;
+            kf_l = OA::kf(P)[it.ob0 + (lane - m_l * k)];
+            if (lane < k) sm.slot[lane] = P.kf_slot[kf_l];
+            if (lane < nf) sm.fpos[lane] = OA::freepos(P)[it.fp0 + lane];
+        WPHASE_END
+        if (keep) {
+            WPHASE_BEGIN
+                LANE_BIND(tk); LANE_BIND(blk); LANE_BIND(gv); LANE_BIND(hd);
+                const int slice = lane / ntask, task = lane - slice * ntask;
+                tk.on = (slice < nslice) ? 1 : 0; tk.slice = slice;
+                if (tk.on) wtask_decode(task, nf, sm.fpos, sm.slot, slot0, tk);
+#pragma unroll
+                for (int i = 0; i < 18; i++) blk[i] = 0.0;
+#pragma unroll
+                for (int i = 0; i < 3; i++) { gv[i] = 0.0; hd[i] = 0.0; }
+            WPHASE_END
+        }
+        for (int pass = 0; pass < npass; pass++) {
+            const int lmb = pass * lpp;
+            const int nlp = (it.n_lm - lmb < lpp) ? it.n_lm - lmb : lpp;
+            const int nvalid = nlp * k;
+            // ---- per observation: residual, Jacobians, robust weight (subsystem 1) ----
+            WPHASE_BEGIN
+                LANE_BIND(cost_l); LANE_BIND(kf_l); LANE_BIND(m_l);
+                if (lane < nvalid) {
+                    const int o = it.ob0 + lmb * k + lane;
+                    LmD<LT> lmd; ObsLoad<LT> ob;
+                    ob.load(P, o);
+                    LmLoad<PROF, LT>::run(P, ctl, it.win, it.lm0 + lmb + m_l, state, lmd);
+                    double A[RANK * 6], B[RANK * D], e[RANK], cost;
+                    obs_lin_w<PROF, LT>(P, ctl, o, kf_l, lmd, ob, A, B, e, cost);
+                    if (mode == 1) cost_l += cost;
+#pragma unroll
+                    for (int i = 0; i < RANK * 6; i++) sm.A[i * 32 + lane] = A[i];
+#pragma unroll
+                    for (int i = 0; i < RANK * D; i++) sm.B[i * 32 + lane] = B[i];
+#pragma unroll
+                    for (int i = 0; i < RANK; i++) sm.E[i * 32 + lane] = e[i];
+                }
+            WPHASE_END
+            // ---- per landmark (redundantly on each of its lanes): H_ll, b_l, damping, inverse; Ta = Bt H_ll^-1, v = H_ll^-1 b_l (subsystem 2) ----
+            WPHASE_BEGIN
+                LANE_BIND(maxd_l); LANE_BIND(m_l);
+                if (lane < nvalid) {
+                    const int t0 = m_l * k;
+                    double H[D * D], bl[D];
+#pragma unroll
+                    for (int i = 0; i < D * D; i++) H[i] = 0.0;
+#pragma unroll
+                    for (int i = 0; i < D; i++) bl[i] = 0.0;
+                    for (int t = t0; t < t0 + k; t++) {
+#pragma unroll
+                        for (int kk = 0; kk < RANK; kk++) {
+                            double b[D];
+#pragma unroll
+                            for (int c = 0; c < D; c++) b[c] = sm.B[(kk * D + c) * 32 + t];
+                            const double ek = sm.E[kk * 32 + t];
+#pragma unroll
+                            for (int r = 0; r < D; r++) {
+                                bl[r] -= b[r] * ek;
+#pragma unroll
+                                for (int c = r; c < D; c++) H[r * D + c] += b[r] * b[c];
+                            }
+                        }
+                    }
+                    double maxd = 0.0;
+#pragma unroll
+                    for (int r = 0; r < D; r++) {
+                        if (fabs(H[r * D + r]) > maxd) maxd = fabs(H[r * D + r]);
+#pragma unroll
+                        for (int c = 0; c < r; c++) H[r * D + c] = H[c * D + r];
+                    }
+                    if (mode == 0) { if (maxd > maxd_l) maxd_l = maxd; }
+                    else {
+                        damp_invert<PROF, D>(ctl, H);
+#pragma unroll
+                        for (int kk = 0; kk < RANK; kk++) {
+                            double b[D];
+#pragma unroll
+                            for (int c = 0; c < D; c++) b[c] = sm.B[(kk * D + c) * 32 + lane];
+#pragma unroll
+                            for (int c = 0; c < D; c++) {
+                                double sum = 0;
+#pragma unroll
+                                for (int mm = 0; mm < D; mm++) sum += b[mm] * H[mm * D + c];
+                                sm.TA[(kk * D + c) * 32 + lane] = sum;
+                            }
+                        }
+#pragma unroll
+                        for (int r = 0; r < D; r++) {
+                            double s = 0;
+#pragma unroll
+                            for (int c = 0; c < D; c++) s += H[r * D + c] * bl[c];
+                            sm.V[r * 32 + lane] = s;
+                        }
+                    }
+                }
+            WPHASE_END
+            // ---- Schur tasks (subsystem 3): one round when the lane keeps its block for the whole item, else a round per 32 tasks ----
+#pragma unroll 1
+            for (int r = 0; r < rounds; r++) {
+                WPHASE_BEGIN
+                    LANE_BIND(tk); LANE_BIND(blk); LANE_BIND(gv); LANE_BIND(hd);
+                    if (!keep) {
+                        const int task = r * 32 + lane;
+                        tk.on = (task < ntask) ? 1 : 0; tk.slice = 0;
+                        if (tk.on) wtask_decode(task, nf, sm.fpos, sm.slot, slot0, tk);
+#pragma unroll
+                        for (int i = 0; i < 18; i++) blk[i] = 0.0;
+#pragma unroll
+                        for (int i = 0; i < 3; i++) { gv[i] = 0.0; hd[i] = 0.0; }
+                    }
+                    if (tk.on) {
+                        wtask_accumulate<PROF, LT, mode>(sm, tk, k, tk.slice, nslice, nlp, blk, gv, hd);
+                        if (!keep || pass == npass - 1) wtask_flush<PROF, mode>(P, tk, Sw, ld, slot0, blk, gv, hd);
+                    }
+                WPHASE_END
+            }
+        }
+    }
+    if (cur_win >= 0) {
+        WPHASE_BEGIN
+            LANE_BIND(cost_l); LANE_BIND(maxd_l);
+            double *accw = P.acc + (size_t)4 * cur_win;
+            if (mode == 1) PLBA_WARP_FLUSH_ADD((PROF == PLBA_PROFILE_G) ? &accw[ACC_CHI_LIN] : (LT == LT_POINT ? &accw[ACC_ERR_PT] : &accw[ACC_ERR_LS]), cost_l);
+            else PLBA_WARP_FLUSH_MAX(&P.accmax[cur_win], maxd_l);
+        WPHASE_END
+    }
+}
+
+template <int PROF>
+PLBA_KERNEL void PLBA_BOUNDS(WNT, W_CTAS_PER_SM) k_assemble_w(const DevP *Pp, int mode) {
+    PLBA_SMEM(raw);
+    PLBA_PARAMS(P, Pp);
+    unsigned char *wraw = raw + (size_t)PLBA_WARP_IN_CTA * WSmemMax<PROF>::bytes();
+    if (mode == 0) {
+        assemble_items_w<PROF, LT_POINT, 0>(P, P.witems_pt, P.n_witems_pt, wraw);
+        assemble_items_w<PROF, LineOf<PROF>::LT, 0>(P, P.witems_ls, P.n_witems_ls, wraw);
+    } else {
+        assemble_items_w<PROF, LT_POINT, 1>(P, P.witems_pt, P.n_witems_pt, wraw);
+        assemble_items_w<PROF, LineOf<PROF>::LT, 1>(P, P.witems_ls, P.n_witems_ls, wraw);
+    }
+    // the last CTA out re-arms the work counters for the next launch
+    PHASE_BEGIN
+    PHASE_END
+    PHASE_BEGIN
+        if (tid == 0 && plba_atomic_fetch_add_i(&P.counters[CNT_WTICKET], 1) == PLBA_NB - 1) {
+            P.counters[CNT_WORK_PT] = 0; P.counters[CNT_WORK_LS] = 0; P.counters[CNT_WTICKET] = 0;
+        }
+    PHASE_END
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// update: re-linearise, back-substitute x_l = H_ll^-1 (b_l - W^T x_p), retract, evaluate the new cost (subsystem 4)
+// ---------------------------------------------------------------------------------------------------------
+template <int PROF, int LT>
+PLBA_D void update_items_w(const DevP &Pin, const WItem *items, int n_items, unsigned char *wraw) {
+    PLBA_PARAMS_REF(P, Pin);
+    typedef KT<PROF, LT> K;
+    typedef ObsAcc<LT> OA;
+    const int D = K::D, RANK = K::RANK;
+    WSmem<PROF, LT> sm(wraw);
+    double *U = sm.TA;                                           // [RANK][32]: J_pose x_p of each observation
+    LANE_VAR(double, chi_l); LANE_VAR(double, sc_l); LANE_VAR(double, d2_l);
+    LANE_ARR(double, xpl, 6);
+    LANE_VAR(int, kf_l); LANE_VAR(int, m_l); LANE_VAR(int, slot_l); LANE_VAR(int, act_l);
+    int cur_win = -1;
+    WPHASE_BEGIN
+        LANE_BIND(chi_l); LANE_BIND(sc_l); LANE_BIND(d2_l);
+        chi_l = 0.0; sc_l = 0.0; d2_l = 0.0;
+    WPHASE_END
+    for (;;) {
+        // next work item: one atomic per warp (items differ in cost, a static deal leaves the slowest warp far behind)
+        WPHASE_BEGIN
+            if (lane == 0) sm.slot[48] = plba_atomic_fetch_add_i(&P.counters[LT == LT_POINT ? CNT_WORK_PT : CNT_WORK_LS], 1);
+        WPHASE_END
+        const int ii = sm.slot[48];
+        WPHASE_BEGIN
+        WPHASE_END
+        if (ii >= n_items) break;
+        const WItem it = items[ii];
+        const WinCtrl ctl = P.ctrl[it.win];             // the controller only runs between launches: a private copy is safe
+        if (ctl.done) continue;
+        if (it.win != cur_win) {
+            if (cur_win >= 0) {
+                WPHASE_BEGIN
+                    LANE_BIND(chi_l); LANE_BIND(sc_l); LANE_BIND(d2_l);
+                    double *acc = P.accB + (size_t)4 * cur_win;
+                    if (PROF == PLBA_PROFILE_G) PLBA_WARP_FLUSH_ADD(&acc[ACC_CHI_NEW], chi_l);
+                    PLBA_WARP_FLUSH_ADD(&acc[ACC_SCALE], sc_l);
+                    PLBA_WARP_FLUSH_ADD(&acc[ACC_DX2], d2_l);
+                    chi_l = 0.0; sc_l = 0.0; d2_l = 0.0;
+                WPHASE_END
+            }
+            cur_win = it.win;
+        }
+        // k == 0: landmarks without observations still go through the damped solve of their (zero) block, lane = landmark
+        // (g2o: x_l = 0; the hand LM: 0/0, which the reference then adds to the state)
+        const int k = it.k;
+        const int lpp = k ? 32 / k : 32;
+        const int npass = (it.n_lm + lpp - 1) / lpp;
+        const double *state = OA::state(P, ctl.cur);
+        double *state_new = OA::state(P, ctl.cur ^ 1);
+        WPHASE_BEGIN
+            LANE_BIND(kf_l); LANE_BIND(m_l); LANE_BIND(slot_l); LANE_BIND(xpl); LANE_BIND(act_l);
+            m_l = k ? lane / k : lane;
+            kf_l = k ? OA::kf(P)[it.ob0 + (lane - m_l * k)] : 0;
+            slot_l = k ? P.kf_slot[kf_l] : -1;
+            act_l = 0;
+#pragma unroll
+            for (int c = 0; c < 6; c++) xpl[c] = (slot_l >= 0) ? P.xp[(size_t)6 * slot_l + c] : 0.0;
+        WPHASE_END
+        for (int pass = 0; pass < npass; pass++) {
+            const int lmb = pass * lpp;
+            const int nlp = (it.n_lm - lmb < lpp) ? it.n_lm - lmb : lpp;
+            const int nvalid = k ? nlp * k : nlp;
+            WPHASE_BEGIN
+                LANE_BIND(sc_l); LANE_BIND(kf_l); LANE_BIND(m_l); LANE_BIND(slot_l); LANE_BIND(xpl); LANE_BIND(act_l);
+                if (k && lane < nvalid) {
+                    const int o = it.ob0 + lmb * k + lane;
+                    LmD<LT> lmd; ObsLoad<LT> ob;
+                    ob.load(P, o);
+                    LmLoad<PROF, LT>::run(P, ctl, it.win, it.lm0 + lmb + m_l, state, lmd);
+                    double A[RANK * 6], B[RANK * D], e[RANK], cost;
+                    act_l = obs_lin_w<PROF, LT>(P, ctl, o, kf_l, lmd, ob, A, B, e, cost) ? 1 : 0;
+#pragma unroll
+                    for (int kk = 0; kk < RANK; kk++) {
+                        double u = 0.0;
+#pragma unroll
+                        for (int c = 0; c < 6; c++) u += A[kk * 6 + c] * xpl[c];
+                        if (slot_l < 0) u = 0.0;
+                        U[kk * 32 + lane] = u;
+                        sc_l -= u * e[kk];                     // x_p^T b_p restricted to this edge
+                    }
+#pragma unroll
+                    for (int i = 0; i < RANK * D; i++) sm.B[i * 32 + lane] = B[i];
+#pragma unroll
+                    for (int i = 0; i < RANK; i++) sm.E[i * 32 + lane] = e[i];
+                }
+            WPHASE_END
+            WPHASE_BEGIN
+                LANE_BIND(chi_l); LANE_BIND(sc_l); LANE_BIND(d2_l); LANE_BIND(kf_l); LANE_BIND(m_l); LANE_BIND(act_l);
+                if (lane < nvalid) {
+                    const int t0 = m_l * k;
+                    const int lm = it.lm0 + lmb + m_l;
+                    const bool leader = (k == 0) || (lane == t0);
+                    double H[D * D], bl[D], rhs[D];
+#pragma unroll
+                    for (int i = 0; i < D * D; i++) H[i] = 0.0;
+#pragma unroll
+                    for (int i = 0; i < D; i++) { bl[i] = 0.0; rhs[i] = 0.0; }
+                    for (int t = t0; t < t0 + k; t++) {
+#pragma unroll
+                        for (int kk = 0; kk < RANK; kk++) {
+                            double b[D];
+#pragma unroll
+                            for (int c = 0; c < D; c++) b[c] = sm.B[(kk * D + c) * 32 + t];
+                            const double ek = sm.E[kk * 32 + t], u = U[kk * 32 + t];
+#pragma unroll
+                            for (int r = 0; r < D; r++) {
+                                bl[r] -= b[r] * ek; rhs[r] -= b[r] * u;
+#pragma unroll
+                                for (int c = r; c < D; c++) H[r * D + c] += b[r] * b[c];
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < D; r++) {
+                        rhs[r] += bl[r];
+#pragma unroll
+                        for (int c = 0; c < r; c++) H[r * D + c] = H[c * D + r];
+                    }
+                    damp_invert<PROF, D>(ctl, H);
+                    double xl[D];
+#pragma unroll
+                    for (int r = 0; r < D; r++) {
+                        double s = 0;
+#pragma unroll
+                        for (int c = 0; c < D; c++) s += H[r * D + c] * rhs[c];
+                        xl[r] = s;
+                    }
+                    if (leader) {
+#pragma unroll
+                        for (int r = 0; r < D; r++) { sc_l += xl[r] * (ctl.lambda * xl[r] + bl[r]); d2_l += xl[r] * xl[r]; }
+                    }
+                    // retraction
+                    double cur[D], nw[D];
+#pragma unroll
+                    for (int i = 0; i < D; i++) cur[i] = state[(size_t)D * lm + i];
+                    if constexpr (LT == LT_LINE_ORTH) orth_update(cur, xl, nw);                 // updateOrthCoord (a11)
+                    else {
+#pragma unroll
+                        for (int i = 0; i < D; i++) nw[i] = cur[i] + xl[i];
+                    }
+                    if (leader && (PROF == PLBA_PROFILE_G || ctl.apply)) {
+#pragma unroll
+                        for (int i = 0; i < D; i++) state_new[(size_t)D * lm + i] = nw[i];
+                    }
+                    if constexpr (PROF == PLBA_PROFILE_G) if (act_l) {
+                        // new cost at the trial state (computeActiveErrors + activeRobustChi2 after update)
+                        const int o = it.ob0 + lmb * k + lane;
+                        const double *T = P.poseT[ctl.cur ^ 1] + (size_t)12 * kf_l;
+                        double e[2];
+                        ObsLoad<LT> ob; ob.load(P, o);
+                        if constexpr (LT == LT_POINT) { double zc; g_point_error(P.cam, T, nw, ob.uv, e, zc); }
+                        else { double pl[6]; orth_to_plk_sc(nw, pl); g_line_error(P.cam, T, pl, pl + 3, ob.ab, e); }
+                        const double chi2 = OA::om(P)[o] * (e[0] * e[0] + e[1] * e[1]);
+                        OA::chi2(P)[o] = chi2;                       // the cached _error of the edge (e->chi2())
+                        double rho0 = chi2, rho1;
+                        if (ctl.stage == 0) huber(P.huber_delta, chi2, rho0, rho1);
+                        chi_l += rho0;
+                    }
+                }
+            WPHASE_END
+        }
+    }
+    if (cur_win >= 0) {
+        WPHASE_BEGIN
+            LANE_BIND(chi_l); LANE_BIND(sc_l); LANE_BIND(d2_l);
+            double *acc = P.accB + (size_t)4 * cur_win;
+            if (PROF == PLBA_PROFILE_G) PLBA_WARP_FLUSH_ADD(&acc[ACC_CHI_NEW], chi_l);
+            PLBA_WARP_FLUSH_ADD(&acc[ACC_SCALE], sc_l);
+            PLBA_WARP_FLUSH_ADD(&acc[ACC_DX2], d2_l);
+        WPHASE_END
+    }
+}
+
+template <int PROF>
+PLBA_KERNEL void PLBA_BOUNDS(WNT, W_CTAS_PER_SM) k_update_w(const DevP *Pp, int flags) {
+    PLBA_SMEM(raw);
+    PLBA_PARAMS(P, Pp);
+    unsigned char *wraw = raw + (size_t)PLBA_WARP_IN_CTA * WSmemMax<PROF>::bytes();
+    update_items_w<PROF, LT_POINT>(P, P.witems_pt, P.n_witems_pt, wraw);
+    update_items_w<PROF, LineOf<PROF>::LT>(P, P.witems_ls, P.n_witems_ls, wraw);
+    // the last CTA to arrive re-arms the work counters and (fused mode) runs the controller for every window
+    int *last = (int *)raw;
+    PHASE_BEGIN
+    PHASE_END
+    PHASE_BEGIN
+        if (tid == 0) { plba_fence(); *last = (plba_atomic_fetch_add_i(&P.counters[CNT_TICKET], 1) == PLBA_NB - 1) ? 1 : 0; }
+    PHASE_END
+    if (!*last) return;
+    PHASE_BEGIN
+        if (tid == 0) { plba_fence(); P.counters[CNT_WORK_PT] = 0; P.counters[CNT_WORK_LS] = 0; }
+        if (flags & KF_FUSE_CONTROL) for (int w = tid; w < P.n_win; w += PLBA_NT) control_window(P, w);
+    PHASE_END
+    PHASE_BEGIN
+        if (tid == 0) { P.counters[CNT_TICKET] = 0; plba_fence(); if (flags & KF_FUSE_CONTROL) round_epilogue(P, flags); }
+    PHASE_END
+}
+
+}  // namespace plba

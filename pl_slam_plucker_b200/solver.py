@@ -111,6 +111,10 @@ class LBASolver:
         """Large windows: always use the dense DMMA Cholesky instead of the banded one."""
         self._check(self.L.plba_set_force_dense(self.h, 1 if on else 0))
 
+    def set_kernel_path(self, mode=0):
+        """Assembly / update kernels: 0 = route by size, 1 = CTA-chunk kernels, 2 = warp-autonomous kernels whenever tracks fit a warp."""
+        self._check(self.L.plba_set_force_chunk(self.h, int(mode)))
+
     def layout_stats(self):
         out = (C.c_int64 * 8)()
         self._check(self.L.plba_layout_stats(self.h, out))

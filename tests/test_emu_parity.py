@@ -7,9 +7,11 @@ import test_gpu_parity as g
 from pl_slam_plucker_b200 import solver
 
 
-@pytest.fixture(scope="module")
-def gpu_solver(emu):
+@pytest.fixture(scope="module", params=[1, 2], ids=["chunk-kernels", "warp-kernels"])
+def gpu_solver(emu, request):
+    """Both implementations of the assembly / update stage (CTA-chunk and warp-autonomous) run every case."""
     s = solver.LBASolver(0, lib=emu)
+    s.set_kernel_path(request.param)
     yield s
     s.close()
 
@@ -24,4 +26,5 @@ test_reduced_system_blocks_and_sparsity = g.test_reduced_system_blocks_and_spars
 test_edge_cases = g.test_edge_cases
 test_sigma_weights = g.test_sigma_weights
 test_global_ba_shell = g.test_global_ba_shell
+test_both_kernel_paths = g.test_both_kernel_paths
 test_map_handler_interface = g.test_map_handler_interface

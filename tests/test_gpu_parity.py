@@ -39,6 +39,23 @@ def test_small_window_all_profiles(gpu_solver, oracle, prof, q):
     _check(gpu_solver, oracle, P, prof, q)
 
 
+@pytest.mark.parametrize("path", [1, 2], ids=["chunk-kernels", "warp-kernels"])
+@pytest.mark.parametrize("prof,q", [(abi.PROFILE_G, 1), (abi.PROFILE_H_END, 0), (abi.PROFILE_H_PLK, 1)])
+def test_both_kernel_paths(gpu_solver, oracle, prof, q, path):
+    """The assembly / update stage has two implementations (routed by size, plba_set_force_chunk): each is forced in turn on the
+    same windows, including ragged tracks and a track longer than a warp (which the warp kernels must hand to the chunk kernels)."""
+    gpu_solver.set_kernel_path(path)
+    try:
+        P = _scene(1, prof, n_kf_free=8, n_kf_fixed=2, n_pt=500, n_ls=120, seed=23)
+        _check(gpu_solver, oracle, P, prof, q)
+        if prof == abi.PROFILE_G:
+            L = scene.make_scene(1, n_kf_free=22, n_kf_fixed=14, n_pt=300, n_ls=60, mean_track=34.0, seed=29)    # tracks of up to 36 observations
+            assert np.bincount(L.po_lm).max() > 32
+            _check(gpu_solver, oracle, L, prof, 1)
+    finally:
+        gpu_solver.set_kernel_path(0)
+
+
 @pytest.mark.parametrize("prof,q", ALL)
 def test_config1_euroc_window(gpu_solver, oracle, prof, q):
     """BASELINE config 1: 10-KF window, 2k points, 500 lines."""

@@ -13,7 +13,10 @@ for r in csv.reader(open(path, newline="")):
     if "Line No" in d and hdr[0] == "Line No":
         try: ln = int(d["Line No"])
         except ValueError: continue
-        s = int(d.get("# Samples", "0") or 0); ins = int(d.get("Instructions Executed", "0") or 0)
+        def _i(x):
+            try: return int(x)
+            except (ValueError, TypeError): return 0
+        s = _i(d.get("# Samples", "0")); ins = _i(d.get("Instructions Executed", "0"))
         a = agg[kern][(cur_file.split("/")[-1], ln)]
         a[0] += s; a[1] += ins; a[2] = r[1][:110]
 for k, lines in agg.items():
