@@ -60,7 +60,9 @@ struct plba_handle_s {
     int force_chunk = 0;             // 0 = route by size, 1 = always the CTA-chunk kernels, 2 = the warp kernels whenever every track fits a warp
     bool warp_path = true;           // this upload runs on the warp-autonomous kernels (plba_warp.h)
     std::vector<WItem> wi_pt, wi_ls;
-    int grid_warp = 592;
+    std::vector<BcrW> bcr;           // large banded windows: node storage of the block cyclic reduction (per window)
+    int large_solver = 0;            // 0 = block cyclic reduction (default), 1 = single-CTA banded Cholesky (A/B, tests)
+    int grid_warp = 592, grid_warp_upd = 592;
     bool uploaded = false, small_path = true;
     double *sysbuf = nullptr; size_t sys_doubles = 0, S_doubles = 0;
     int h_counters[CNT_N] = {0};
@@ -257,6 +259,8 @@ int plba_create(int32_t device, void *stream, plba_handle *out) {
     h->no_graph = ng && ng[0] == '1';
     const char *fd = std::getenv("PLBA_FORCE_DENSE");        // large windows: always take the dense DMMA Cholesky (tests, benchmarks)
     h->force_dense = fd && fd[0] == '1';
+    const char *ls = std::getenv("PLBA_LARGE_SOLVER");       // "band": the single-CTA banded Cholesky instead of the block cyclic reduction
+    h->large_solver = (ls && ls[0] == 'b' && ls[1] == 'a') ? 1 : 0;
     const char *fc = std::getenv("PLBA_FORCE_CHUNK");        // always take the CTA-chunk assembly / update kernels (tests, A/B runs)
     h->force_chunk = fc ? std::atoi(fc) : 0;
 #else
@@ -309,6 +313,8 @@ template <int PROF> static void set_smem_attr() {
         cudaFuncSetAttribute(k_update_w<PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WARPS_PER_CTA * WSmemMax<PROF>::bytes()));
         cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_small_smem(1));
         cudaFuncSetAttribute(k_solve_banded, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_banded_smem());
+        cudaFuncSetAttribute(k_bcr_elim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bcr_elim_smem());
+        cudaFuncSetAttribute(k_bcr_back, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bcr_back_smem());
         cudaFuncSetAttribute(k_potrf_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_block_smem());
         cudaFuncSetAttribute(k_trsm_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_block_smem());
         cudaFuncSetAttribute(k_syrk_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_dmma_smem());
@@ -335,20 +341,22 @@ static int chunk_occupancy_for(int prof) {
     return cache[prof] = prof == PLBA_PROFILE_G ? chunk_occupancy<PLBA_PROFILE_G>() : prof == PLBA_PROFILE_H_END ? chunk_occupancy<PLBA_PROFILE_H_END>() : chunk_occupancy<PLBA_PROFILE_H_PLK>();
 }
 // warp path: persistent grid of WARPS_PER_CTA-warp CTAs (emulation: one warp per "CTA")
-template <int PROF> static int warp_occupancy() {
+// (work items are dealt dynamically, so each kernel simply gets as many CTAs as can be resident)
+template <int PROF> static int warp_occupancy(int update) {
 #ifndef PLBA_HOST_EMU
-    int a = 1, b = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_assemble_w<PROF>, WNT, WARPS_PER_CTA * WSmemMax<PROF>::bytes());
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_update_w<PROF>, WNT, WARPS_PER_CTA * WSmemMax<PROF>::bytes());
-    return std::max(1, std::min(a, b));
+    int a = 1;
+    if (update) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_update_w<PROF>, WNT, WARPS_PER_CTA * WSmemMax<PROF>::bytes());
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_assemble_w<PROF>, WNT, WARPS_PER_CTA * WSmemMax<PROF>::bytes());
+    return std::max(1, a);
 #else
-    return 1;
+    (void)update; return 1;
 #endif
 }
-static int warp_occupancy_for(int prof) {
-    static int cache[3] = {0, 0, 0};
-    if (cache[prof]) return cache[prof];
-    return cache[prof] = prof == PLBA_PROFILE_G ? warp_occupancy<PLBA_PROFILE_G>() : prof == PLBA_PROFILE_H_END ? warp_occupancy<PLBA_PROFILE_H_END>() : warp_occupancy<PLBA_PROFILE_H_PLK>();
+static int warp_occupancy_for(int prof, int update) {
+    static int cache[6] = {0, 0, 0, 0, 0, 0};
+    int &c = cache[2 * prof + update];
+    if (c) return c;
+    return c = prof == PLBA_PROFILE_G ? warp_occupancy<PLBA_PROFILE_G>(update) : prof == PLBA_PROFILE_H_END ? warp_occupancy<PLBA_PROFILE_H_END>(update) : warp_occupancy<PLBA_PROFILE_H_PLK>(update);
 }
 static size_t warp_smem(int prof) {
     const size_t w = prof == PLBA_PROFILE_G ? WSmemMax<PLBA_PROFILE_G>::bytes() : prof == PLBA_PROFILE_H_END ? WSmemMax<PLBA_PROFILE_H_END>::bytes() : WSmemMax<PLBA_PROFILE_H_PLK>::bytes();
@@ -389,7 +397,7 @@ static void launch_assemble(plba_handle h, int mode) {
 static void launch_update(plba_handle h, int flags) {
     const DevP *Pp = h->d_P;
     if (h->warp_path) {
-        const dim3 g(h->grid_warp), b = warp_block(); const size_t sm = warp_smem(h->opt.profile);
+        const dim3 g(h->grid_warp_upd), b = warp_block(); const size_t sm = warp_smem(h->opt.profile);
         switch (h->opt.profile) {
         case PLBA_PROFILE_G: PLBA_LAUNCH((k_update_w<PLBA_PROFILE_G>), g, b, sm, h->stream, Pp, flags); break;
         case PLBA_PROFILE_H_END: PLBA_LAUNCH((k_update_w<PLBA_PROFILE_H_END>), g, b, sm, h->stream, Pp, flags); break;
@@ -415,8 +423,29 @@ static void launch_solve(plba_handle h) {
         return;
     }
     if (P.profile != PLBA_PROFILE_G) { PLBA_LAUNCH(k_control_h_pre, grid1(P.n_win, 128), dim3(128), 0, h->stream, Pp); h->timing.n_launches++; }
+    if (h->band_blocks <= BAND_MAX && !h->force_dense && h->large_solver == 0 && !h->bcr.empty()) {
+        // block-banded reduced camera system (no loop closure in the window): block cyclic reduction over nodes of >= band keyframes,
+        // ceil(log2 N) levels down and up, every level one launch with a CTA per eliminated node
+        for (int w = 0; w < P.n_win; w++) {
+            const BcrW &B = h->bcr[w];
+            if (B.N == 0 || h->wins[w].n_pobs + h->wins[w].n_lobs == 0) continue;
+            PLBA_LAUNCH(k_bcr_gather, dim3(B.N), dim3(256), 0, h->stream, Pp, w, B); h->timing.n_launches++;
+            int s_top = 0;
+            for (int s = 1; s < B.N; s *= 2) {
+                PLBA_LAUNCH(k_bcr_elim, dim3((B.N + s - 1) / (2 * s)), dim3(BCR_NT), bcr_elim_smem(), h->stream, Pp, w, B, s, 0); h->timing.n_launches++;
+                s_top = s;
+            }
+            PLBA_LAUNCH(k_bcr_elim, dim3(1), dim3(BCR_NT), bcr_elim_smem(), h->stream, Pp, w, B, 0, 1);
+            PLBA_LAUNCH(k_bcr_back, dim3(1), dim3(256), bcr_back_smem(), h->stream, Pp, w, B, 0, 1); h->timing.n_launches += 2;
+            for (int s = s_top; s >= 1; s /= 2) {
+                PLBA_LAUNCH(k_bcr_back, dim3((B.N + s - 1) / (2 * s)), dim3(256), bcr_back_smem(), h->stream, Pp, w, B, s, 0); h->timing.n_launches++;
+            }
+        }
+        PLBA_LAUNCH(k_pose_update, grid1(P.n_free, 128), dim3(128), 0, h->stream, Pp); h->timing.n_launches++;
+        return;
+    }
     if (h->band_blocks <= BAND_MAX && !h->force_dense) {
-        // block-banded reduced camera system (no loop closure in the window): banded left-looking Cholesky, one CTA per window
+        // the same, factored panel by panel by one CTA per window (kept for A/B runs: PLBA_LARGE_SOLVER=band)
         PLBA_LAUNCH(k_solve_banded, dim3(std::min(P.n_win, h->n_sm)), dim3(256), solve_banded_smem(), h->stream, Pp, h->band_blocks);
         PLBA_LAUNCH(k_pose_update, grid1(P.n_free, 128), dim3(128), 0, h->stream, Pp); h->timing.n_launches += 2;
         return;
@@ -490,7 +519,8 @@ template <int PROF> static int build_graph(plba_handle h) {
     CK(cudaGraphAddNode(&inode, body, nullptr, 0, &ip));
     cudaGraph_t prep = ip.conditional.phGraph_out[0];
     const DevP *Pp = h->d_P;
-    const dim3 gc(h->warp_path ? h->n_sm * warp_occupancy<PROF>() : h->n_sm * chunk_occupancy<PROF>()), bc(h->warp_path ? (int)WNT : (int)OC);
+    const dim3 gc(h->warp_path ? h->n_sm * warp_occupancy<PROF>(0) : h->n_sm * chunk_occupancy<PROF>()), bc(h->warp_path ? (int)WNT : (int)OC);
+    const dim3 gu(h->warp_path ? h->n_sm * warp_occupancy<PROF>(1) : h->n_sm * chunk_occupancy<PROF>());
     const size_t smc = h->warp_path ? WARPS_PER_CTA * WSmemMax<PROF>::bytes() : SmemMax<PROF>::bytes();
     void *f_asm = h->warp_path ? (void *)k_assemble_w<PROF> : (void *)k_assemble<PROF>, *f_upd = h->warp_path ? (void *)k_update_w<PROF> : (void *)k_update<PROF>;
     int mode0 = 0, mode1 = 1, fl = KF_FUSE_CONTROL | KF_IN_GRAPH;
@@ -501,7 +531,7 @@ template <int PROF> static int build_graph(plba_handle h) {
     CK(add_kernel(prep, &n3, n2, (void *)k_lambda_init, dim3(h->n_sm), dim3(128), 0, a_p));
     CK(add_kernel(body, &m1, inode, f_asm, gc, bc, smc, a_m1));
     CK(add_kernel(body, &m2, m1, (void *)k_solve_small, dim3(h->grid_solve), dim3(256), solve_small_smem(h->solve_class), a_p));
-    CK(add_kernel(body, &m3, m2, f_upd, gc, bc, smc, a_fl));
+    CK(add_kernel(body, &m3, m2, f_upd, gu, bc, smc, a_fl));
     CK(cudaGraphInstantiate(&h->gexec[pi], g, 0));
     h->graph[pi] = g;
     return PLBA_OK;
@@ -562,9 +592,9 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     set_all_attrs();
     h->grid_chunks = h->n_sm * chunk_occupancy_for(prof);
 #ifndef PLBA_HOST_EMU
-    h->grid_warp = h->n_sm * warp_occupancy_for(prof);
+    h->grid_warp = h->n_sm * warp_occupancy_for(prof, 0); h->grid_warp_upd = h->n_sm * warp_occupancy_for(prof, 1);
 #else
-    h->grid_warp = 24;               // emulation: 24 one-warp "CTAs"
+    h->grid_warp = h->grid_warp_upd = 24;               // emulation: 24 one-warp "CTAs"
 #endif
 
     // ---- index work: signature order, chunks, segments --------------------------------------------------------
@@ -746,6 +776,19 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     for (int b = 0; b < 2; b++) { s_poseT[b] = cs.take<double>((size_t)12 * tot.n_kf); s_X[b] = cs.take<double>((size_t)6 * tot.n_free); s_pts[b] = cs.take<double>((size_t)3 * tot.n_pt); s_lns[b] = cs.take<double>((size_t)ld * tot.n_ls); }
     const size_t s_po_lvl = cs.take<unsigned char>(tot.n_pobs), s_lo_lvl = cs.take<unsigned char>(tot.n_lobs);
     const size_t s_sys = cs.take<double>(h->sys_doubles), s_xp = cs.take<double>((size_t)6 * tot.n_free);
+    // node storage of the block cyclic reduction (large banded windows only)
+    h->bcr.clear();
+    std::vector<size_t> s_bcr;
+    if (!h->small_path && h->band_blocks <= BAND_MAX) {
+        const int bs = std::min((int)BCR_BS_MAX, std::max(h->band_blocks, 6)), m = 6 * bs;
+        for (int w = 0; w < n; w++) {
+            BcrW B{}; B.bs = bs; B.m = m; B.N = (h->wins[w].n_free + bs - 1) / bs;
+            h->bcr.push_back(B);
+            const size_t nn = (size_t)B.N * m * m;
+            for (int a = 0; a < 4; a++) s_bcr.push_back(cs.take<double>(nn));
+            for (int a = 0; a < 2; a++) s_bcr.push_back(cs.take<double>((size_t)B.N * m));
+        }
+    }
     const int trace_cap = (prof == PLBA_PROFILE_G) ? (opt->iters_stage1 + opt->iters_stage2) * opt->lm_max_trials + 2 : opt->max_iters_lba + 2;
     // output region (one D2H copy)
     h->out_off = cs.off;
@@ -863,6 +906,11 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     P.S = h->sysbuf; P.gs = P.S + h->S_doubles; P.hpp_diag = P.gs + (size_t)6 * tot.n_free; P.hpp_diag_init = P.hpp_diag + (size_t)6 * tot.n_free;
     P.acc = P.hpp_diag_init + (size_t)6 * tot.n_free; P.accB = P.acc + (size_t)4 * n; P.accmax = P.acc + (size_t)ACC_N * n;
     P.xp = (double *)(db + s_xp);
+    for (size_t w = 0; w < h->bcr.size(); w++) {
+        BcrW &B = h->bcr[w];
+        B.D = (double *)(db + s_bcr[6 * w]); B.U = (double *)(db + s_bcr[6 * w + 1]); B.Xl = (double *)(db + s_bcr[6 * w + 2]); B.Xr = (double *)(db + s_bcr[6 * w + 3]);
+        B.b = (double *)(db + s_bcr[6 * w + 4]); B.y = (double *)(db + s_bcr[6 * w + 5]);
+    }
     P.ctrl = (WinCtrl *)(db + h->o_ctrl); P.trace = (plba_trace_rec *)(db + h->o_trace); P.trace_cap = trace_cap; P.counters = (int *)(db + h->o_cnt);
     set_all_attrs();
 #ifndef PLBA_HOST_EMU
@@ -894,7 +942,9 @@ int plba_reset_state(plba_handle h) {
 // one LM round, host driven: (gate + lambda init) -> assemble -> [exchange] -> solve -> update -> [exchange] -> control
 static int run_round(plba_handle h, bool need_prep) {
     DevP &P = h->P; cudaStream_t st = h->stream; const DevP *Pp = h->d_P;
-    if (!h->small_path) CK(cudaMemsetAsync(h->sysbuf, 0, sizeof(double) * (h->S_doubles + (size_t)12 * P.n_free), st));
+    // (the block-cyclic-reduction solver clears what it consumes; the other large-window solvers leave S dirty)
+    const bool bcr_active = h->band_blocks <= BAND_MAX && !h->force_dense && h->large_solver == 0 && !h->bcr.empty();
+    if (!h->small_path && !bcr_active) CK(cudaMemsetAsync(h->sysbuf, 0, sizeof(double) * (h->S_doubles + (size_t)12 * P.n_free), st));
     if (need_prep) {
         PLBA_LAUNCH(k_gate, dim3(h->grid_chunks), dim3(256), 0, st, Pp); h->timing.n_launches++;
         launch_assemble(h, 0);

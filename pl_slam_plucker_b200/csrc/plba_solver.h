@@ -729,4 +729,187 @@ PLBA_KERNEL void k_solve_banded(const DevP *Pp, int bwb) {
     }
 }
 
+// ---- block cyclic reduction for block-banded reduced camera systems (6 Nkf > 144, sliding-window shape) -------------------------
+// With half bandwidth `band` pose blocks the reduced camera system is block tridiagonal in NODES of bs >= band keyframes
+// (m = 6 bs <= 90 unknowns).  Level l (stride s = 2^l) eliminates the nodes i = s, 3s, 5s, ... IN PARALLEL, one CTA each:
+//     D_i = L L^T ;  Xl = A[i-s,i] L^-T ;  Xr = A[i+s,i] L^-T ;  y = b_i L^-T          (one shared-memory Cholesky: the coupling
+//                                                                                      blocks and b ride along as extra rows)
+//     D_{i-s} -= Xl Xl^T ;  D_{i+s} -= Xr Xr^T ;  A[i-s,i+s] = -Xl Xr^T ;  b_{i-s} -= Xl y ;  b_{i+s} -= Xr y
+// which leaves a block tridiagonal system in the nodes that are multiples of 2s.  After ceil(log2 N) levels node 0 is solved and
+// the levels are walked back:  L^T x_i = y - Xl^T x_{i-s} - Xr^T x_{i+s}.
+// This is a Cholesky factorisation in a nested-dissection order of the keyframe chain: same system, same solution up to rounding,
+// but the 6 Nkf sequential pivots of the banded factorisation become 90 ceil(log2 N) and every level fills the GPU.
+struct BcrW { double *D, *U, *Xl, *Xr, *b, *y; int N, bs, m, pad; };      // node storage: D, U, Xl, Xr: [N][m*m] (row stride m); b, y: [N][m]
+enum { BCR_BS_MAX = 15, BCR_M_MAX = 6 * BCR_BS_MAX, BCR_NT = 512 };
+static inline size_t bcr_elim_smem() { return sizeof(double) * ((size_t)(3 * BCR_M_MAX + 1) * (BCR_M_MAX + 1) + BCR_M_MAX + 21 * BCR_BS_MAX + 6 * 264 + 8) + 64; }
+static inline size_t bcr_back_smem() { return sizeof(double) * ((size_t)BCR_M_MAX * (BCR_M_MAX + 1) + 3 * BCR_M_MAX + 8) + 64; }
+PLBA_HD int bcr_node_size(const BcrW &B, int nf, int i) { const int k0 = i * B.bs, k1 = (k0 + B.bs < nf) ? k0 + B.bs : nf; return 6 * (k1 - k0); }
+
+// dense S (upper storage) -> node form, damping added to the diagonal.  Everything the assembly wrote is read here exactly once
+// (blocks of one node, blocks between neighbouring nodes, g, diag(H_pp)) and cleared behind the read: the next assembly
+// accumulates into a clean system without a memset of the dense S (1.15 GB at config 5).
+PLBA_KERNEL void k_bcr_gather(const DevP *Pp, int w, BcrW B) {
+    PLBA_PARAMS(P, Pp);
+    const WinCtrl &ctl = P.ctrl[w];
+    if (ctl.done) return;
+    const int nf = P.win_nfree[w], n = 6 * nf, slot0 = P.win_slot0[w], m = B.m;
+    double *Sw = P.S + P.win_S_off[w];
+    const double lambda = ctl.lambda;
+    const int i = PLBA_BID, oi = 6 * i * B.bs, mi = bcr_node_size(B, nf, i);
+    double *D = B.D + (size_t)i * m * m, *U = B.U + (size_t)i * m * m;
+    PHASE_BEGIN
+        for (int idx = tid; idx < mi * mi; idx += PLBA_NT) {
+            const int c = idx / mi, r = idx - c * mi;                // consecutive threads walk a row of S (upper storage: row = c)
+            if (c > r) continue;
+            double v = Sw[(size_t)(oi + c) * n + oi + r];
+            Sw[(size_t)(oi + c) * n + oi + r] = 0.0;
+            if (r == c) {
+                if (P.profile == PLBA_PROFILE_G) v += lambda;
+                else { v += lambda * P.hpp_diag[(size_t)6 * slot0 + oi + r]; P.hpp_diag[(size_t)6 * slot0 + oi + r] = 0.0; }
+            }
+            D[(size_t)r * m + c] = v;
+        }
+        if (i > 0) {
+            const int ol = oi - m;                                   // the left neighbour is never the last node: full size
+            for (int idx = tid; idx < m * mi; idx += PLBA_NT) {
+                const int r = idx / mi, c = idx - r * mi;
+                U[(size_t)r * m + c] = Sw[(size_t)(ol + r) * n + oi + c];
+                Sw[(size_t)(ol + r) * n + oi + c] = 0.0;
+            }
+        }
+        for (int c = tid; c < mi; c += PLBA_NT) { B.b[(size_t)i * m + c] = P.gs[(size_t)6 * slot0 + oi + c]; P.gs[(size_t)6 * slot0 + oi + c] = 0.0; }
+    PHASE_END
+}
+
+// eliminate the nodes (2 j + 1) s of one level (final != 0: node 0, nothing left to couple to)
+PLBA_KERNEL void k_bcr_elim(const DevP *Pp, int w, BcrW B, int s, int final) {
+    PLBA_SMEM(raw);
+    PLBA_PARAMS(P, Pp);
+    WinCtrl &ctl = P.ctrl[w];
+    if (ctl.done) return;
+    const int nf = P.win_nfree[w], m = B.m, ldm = m + 1;
+    const int i = final ? 0 : (2 * PLBA_BID + 1) * s;
+    const int left = final ? -1 : i - s, right = (final || i + s >= B.N) ? -1 : i + s;
+    const int mi = bcr_node_size(B, nf, i), ml = left >= 0 ? m : 0, mr = right >= 0 ? bcr_node_size(B, nf, right) : 0;
+    const int nr = mi + ml + mr;                                    // row nr = right-hand side
+    double *M = (double *)raw, *dinv = M + (size_t)(3 * BCR_M_MAX + 1) * (BCR_M_MAX + 1), *Lblk = dinv + BCR_M_MAX, *part = Lblk + 21 * BCR_BS_MAX;
+    int *fail = (int *)(part + 6 * 264);
+    double *Di = B.D + (size_t)i * m * m, *Ui = B.U + (size_t)i * m * m;
+    double *Ur = right >= 0 ? B.U + (size_t)right * m * m : nullptr;
+    PHASE_BEGIN
+        if (tid == 0) *fail = 0;
+        for (int idx = tid; idx < mi * mi; idx += PLBA_NT) { const int r = idx / mi, c = idx - r * mi; if (c <= r) M[(size_t)r * ldm + c] = Di[(size_t)r * m + c]; }
+        for (int idx = tid; idx < ml * mi; idx += PLBA_NT) { const int r = idx / mi, c = idx - r * mi; M[(size_t)(mi + r) * ldm + c] = Ui[(size_t)r * m + c]; }
+        // A[i+s, i] = A[i, i+s]^T: rows = unknowns of the right neighbour (reads walk the rows of its U block: coalesced over r)
+        for (int idx = tid; idx < mr * mi; idx += PLBA_NT) { const int c = idx / mr, r = idx - c * mr; M[(size_t)(mi + ml + r) * ldm + c] = Ur[(size_t)c * m + r]; }
+        for (int c = tid; c < mi; c += PLBA_NT) M[(size_t)nr * ldm + c] = B.b[(size_t)i * m + c];
+    PHASE_END
+    chol_lower_panels(M, ldm, mi, nr, dinv, Lblk, part, fail);
+    double *Xl = B.Xl + (size_t)i * m * m, *Xr = B.Xr + (size_t)i * m * m;
+    PHASE_BEGIN
+        // factor and solved rows kept for the way back (the factored 6x6 diagonal blocks live in Lblk)
+        for (int idx = tid; idx < mi * mi; idx += PLBA_NT) {
+            const int r = idx / mi, c = idx - r * mi;
+            if (c > r) continue;
+            double v;
+            if (c / 6 == r / 6) { const int kb = r / 6, a = r - 6 * kb, b2 = c - 6 * kb; v = Lblk[kb * 21 + a * (a + 1) / 2 + b2]; }
+            else v = M[(size_t)r * ldm + c];
+            Di[(size_t)r * m + c] = v;
+        }
+        for (int idx = tid; idx < ml * mi; idx += PLBA_NT) { const int r = idx / mi, c = idx - r * mi; Xl[(size_t)r * m + c] = M[(size_t)(mi + r) * ldm + c]; }
+        for (int idx = tid; idx < mr * mi; idx += PLBA_NT) { const int r = idx / mi, c = idx - r * mi; Xr[(size_t)r * m + c] = M[(size_t)(mi + ml + r) * ldm + c]; }
+        for (int c = tid; c < mi; c += PLBA_NT) B.y[(size_t)i * m + c] = M[(size_t)nr * ldm + c];
+        if (tid == 0 && *fail) ctl.solve_fail = 1;
+    PHASE_END
+    if (final) return;
+    // Schur complement onto the neighbours: 3 x 3 register tiles over (rows of Xa) x (rows of Xb), operands in shared memory.
+    // Two CTAs of a level update the same D (its left and its right neighbour are both being eliminated): red.global.add.
+    PHASE_BEGIN
+        for (int job = 0; job < 3; job++) {
+            // job 0: D_left -= Xl Xl^T (lower); job 1: D_right -= Xr Xr^T (lower); job 2: A[left,right] = -Xl Xr^T
+            const int ma = (job == 1) ? mr : ml, mb = (job == 0) ? ml : mr;
+            if (ma == 0 || mb == 0) continue;
+            const double *Xa = M + (size_t)(mi + (job == 1 ? ml : 0)) * ldm, *Xb = M + (size_t)(mi + (job == 0 ? 0 : ml)) * ldm;
+            double *dst = (job == 0) ? B.D + (size_t)left * m * m : (job == 1) ? B.D + (size_t)right * m * m : Ur;
+            const int nta = (ma + 2) / 3, ntb = (mb + 2) / 3;
+            for (int t = tid; t < nta * ntb; t += PLBA_NT) {
+                const int ra0 = 3 * (t / ntb), rb0 = 3 * (t - (t / ntb) * ntb);
+                if (job < 2 && rb0 > ra0 + 2) continue;                 // symmetric update: lower triangle only
+                double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                const double *a0 = Xa + (size_t)ra0 * ldm, *b0 = Xb + (size_t)rb0 * ldm;
+                const bool a1 = ra0 + 1 < ma, a2 = ra0 + 2 < ma, b1 = rb0 + 1 < mb, b2 = rb0 + 2 < mb;
+#pragma unroll 2
+                for (int q = 0; q < mi; q++) {
+                    const double x0 = a0[q], x1 = a1 ? a0[ldm + q] : 0.0, x2 = a2 ? a0[2 * ldm + q] : 0.0;
+                    const double y0 = b0[q], y1 = b1 ? b0[ldm + q] : 0.0, y2 = b2 ? b0[2 * ldm + q] : 0.0;
+                    acc[0] += x0 * y0; acc[1] += x0 * y1; acc[2] += x0 * y2;
+                    acc[3] += x1 * y0; acc[4] += x1 * y1; acc[5] += x1 * y2;
+                    acc[6] += x2 * y0; acc[7] += x2 * y1; acc[8] += x2 * y2;
+                }
+#pragma unroll
+                for (int u = 0; u < 3; u++) {
+#pragma unroll
+                    for (int v = 0; v < 3; v++) {
+                        const int r = ra0 + u, c = rb0 + v;
+                        if (r >= ma || c >= mb) continue;
+                        if (job < 2) { if (c <= r) plba_atomic_add(dst + (size_t)r * m + c, -acc[u * 3 + v]); }
+                        else dst[(size_t)r * m + c] = -acc[u * 3 + v];
+                    }
+                }
+            }
+        }
+        // right-hand sides of the neighbours
+        for (int t = tid; t < ml + mr; t += PLBA_NT) {
+            const double *Xa = M + (size_t)(mi + t) * ldm, *yy = M + (size_t)nr * ldm;
+            double sum = 0.0;
+            for (int q = 0; q < mi; q++) sum += Xa[q] * yy[q];
+            plba_atomic_add(&B.b[(size_t)(t < ml ? left : right) * m + (t < ml ? t : t - ml)], -sum);
+        }
+    PHASE_END
+}
+
+// the way back: L^T x_i = y - Xl^T x_left - Xr^T x_right for the nodes (2 j + 1) s (final != 0: node 0)
+PLBA_KERNEL void k_bcr_back(const DevP *Pp, int w, BcrW B, int s, int final) {
+    PLBA_SMEM(raw);
+    PLBA_PARAMS(P, Pp);
+    const WinCtrl &ctl = P.ctrl[w];
+    if (ctl.done) return;
+    const int nf = P.win_nfree[w], m = B.m, ldm = m + 1, slot0 = P.win_slot0[w];
+    const int i = final ? 0 : (2 * PLBA_BID + 1) * s;
+    const int left = final ? -1 : i - s, right = (final || i + s >= B.N) ? -1 : i + s;
+    const int mi = bcr_node_size(B, nf, i), ml = left >= 0 ? m : 0, mr = right >= 0 ? bcr_node_size(B, nf, right) : 0;
+    double *L = (double *)raw, *rhs = L + (size_t)BCR_M_MAX * (BCR_M_MAX + 1), *xs = rhs + BCR_M_MAX, *dinv = xs + BCR_M_MAX;
+    const double *Di = B.D + (size_t)i * m * m, *Xl = B.Xl + (size_t)i * m * m, *Xr = B.Xr + (size_t)i * m * m;
+    double *x = P.xp + (size_t)6 * slot0;
+    PHASE_BEGIN
+        for (int idx = tid; idx < mi * mi; idx += PLBA_NT) { const int r = idx / mi, c = idx - r * mi; if (c <= r) { const double v = Di[(size_t)r * m + c]; L[(size_t)r * ldm + c] = v; if (c == r) dinv[r] = 1.0 / v; } }
+        for (int c = tid; c < mi; c += PLBA_NT) {
+            double v = B.y[(size_t)i * m + c];
+            const double *xl = x + (size_t)6 * left * B.bs, *xr = x + (size_t)6 * right * B.bs;
+            for (int r = 0; r < ml; r++) v -= Xl[(size_t)r * m + c] * xl[r];
+            for (int r = 0; r < mr; r++) v -= Xr[(size_t)r * m + c] * xr[r];
+            rhs[c] = v;
+        }
+    PHASE_END
+    // column-oriented backward substitution by ONE warp (the chain of mi steps is latency: warp barriers, not block barriers):
+    // x_j = rhs_j / L_jj, then rhs_r -= L[j][r] x_j for r < j (row j of L: contiguous)
+#ifndef PLBA_HOST_EMU
+    if (threadIdx.x < 32)
+#endif
+    for (int j = mi - 1; j >= 0; j--) {
+        WPHASE_BEGIN
+            if (lane == 0) xs[j] = rhs[j] * dinv[j];
+        WPHASE_END
+        WPHASE_BEGIN
+            const double xj = xs[j];
+            for (int r = lane; r < j; r += 32) rhs[r] -= L[(size_t)j * ldm + r] * xj;
+        WPHASE_END
+    }
+    PHASE_BEGIN
+    PHASE_END
+    PHASE_BEGIN
+        for (int c = tid; c < mi; c += PLBA_NT) x[(size_t)6 * i * B.bs + c] = xs[c];
+    PHASE_END
+}
+
 }  // namespace plba
