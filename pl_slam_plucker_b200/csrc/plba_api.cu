@@ -669,7 +669,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
         for (int cls = 0; cls < 2; cls++) {
             std::vector<WItem> &items = cls ? wi_ls : wi_pt; const std::vector<int> &ptr = cls ? ls_ptr : pt_ptr;
             for (const Seg &sg : (cls ? sg_ls : sg_pt)) {
-                const int lpp = sg.nobs ? 32 / sg.nobs : 32, step = lpp * item_passes;
+                const int lpp = sg.nobs ? 32 / sg.nobs : 32, step = cls ? std::min(lpp * item_passes, 32) : lpp * item_passes;   // lines: the update kernel retracts an item's landmarks one per lane
                 for (int l = 0; l < sg.n_lm; l += step) {
                     WItem it{}; it.lm0 = sg.lm0 + l; it.n_lm = std::min(step, sg.n_lm - l); it.ob0 = ptr[it.lm0]; it.k = sg.nobs; it.win = sg.pad1; it.nfree = sg.nfree; it.fp0 = sg.fp0;
                     items.push_back(it);
@@ -772,7 +772,8 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     h->S_doubles = (size_t)S_off;
     h->sys_doubles = h->S_doubles + (size_t)18 * tot.n_free + (size_t)ACC_N * n + (size_t)n;
     Carver cs = ci;   // device-only state follows the inputs
-    size_t s_poseT[2], s_X[2], s_pts[2], s_lns[2];
+    size_t s_poseT[2], s_X[2], s_pts[2], s_lns[2], s_lpre[2];
+    for (int b = 0; b < 2; b++) s_lpre[b] = cs.take<double>((size_t)LPRE_N * tot.n_ls);
     for (int b = 0; b < 2; b++) { s_poseT[b] = cs.take<double>((size_t)12 * tot.n_kf); s_X[b] = cs.take<double>((size_t)6 * tot.n_free); s_pts[b] = cs.take<double>((size_t)3 * tot.n_pt); s_lns[b] = cs.take<double>((size_t)ld * tot.n_ls); }
     const size_t s_po_lvl = cs.take<unsigned char>(tot.n_pobs), s_lo_lvl = cs.take<unsigned char>(tot.n_lobs);
     const size_t s_sys = cs.take<double>(h->sys_doubles), s_xp = cs.take<double>((size_t)6 * tot.n_free);
@@ -899,7 +900,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     P.freepos_pt = (int *)(db + i_fp_pt); P.freepos_ls = (int *)(db + i_fp_ls);
     P.witems_pt = (WItem *)(db + i_wi_pt); P.witems_ls = (WItem *)(db + i_wi_ls); P.n_witems_pt = (int)wi_pt.size(); P.n_witems_ls = (int)wi_ls.size();
     P.ctrl0 = (WinCtrl *)(db + i_ctrl0);
-    for (int b = 0; b < 2; b++) { P.poseT[b] = (double *)(db + s_poseT[b]); P.Xkf[b] = (double *)(db + s_X[b]); P.pts[b] = (double *)(db + s_pts[b]); P.lns[b] = (double *)(db + s_lns[b]); }
+    for (int b = 0; b < 2; b++) { P.poseT[b] = (double *)(db + s_poseT[b]); P.Xkf[b] = (double *)(db + s_X[b]); P.pts[b] = (double *)(db + s_pts[b]); P.lns[b] = (double *)(db + s_lns[b]); P.lpre[b] = (double *)(db + s_lpre[b]); }
     P.po_lvl = (unsigned char *)(db + s_po_lvl); P.lo_lvl = (unsigned char *)(db + s_lo_lvl);
     P.po_chi2 = (double *)(db + h->o_pchi); P.lo_chi2 = (double *)(db + h->o_lchi);
     h->sysbuf = (double *)(db + s_sys);

@@ -25,6 +25,7 @@
 namespace plba {
 
 enum { LT_POINT = 0, LT_LINE_ORTH = 1, LT_LINE_END = 2 };
+enum { LPRE_N = 17 };   // n(3) d(3) u1(3) u2(3) u3(3) w1 w2
 #ifndef PLBA_OC
 #define PLBA_OC 256
 #endif
@@ -78,6 +79,7 @@ struct DevP {
     const long long *win_S_off;       // per window: offset (doubles) of its dense (6 nf)^2 S
     // landmarks (double buffered) in internal (signature-sorted) order
     double *pts[2], *lns[2];
+    double *lpre[2];                  // [n_ls][LPRE_N] orthonormal lines: Plücker vector, U, W at the state of each buffer (warp kernels)
     const double *pts0, *lns0;        // initial values (reset, Q9)
     const double *lns_map;            // [n_ls][6] map Plücker (H_PLK pass 0)
     const int *pt_ptr, *ls_ptr;       // CSR landmark -> observations
@@ -1025,6 +1027,13 @@ PLBA_KERNEL void k_reset(const DevP *Pp, int ls_dim, size_t sys_doubles, double 
             for (size_t l = g0; l < (size_t)P.n_ls; l += gs) {
                 double o[4]; plk_to_orth(P.lns_map + 6 * l, o);
                 for (int i = 0; i < 4; i++) { lns0[4 * l + i] = o[i]; P.lns[0][4 * l + i] = o[i]; P.lns[1][4 * l + i] = o[i]; }
+                double pl[6]; orth_to_plk_sc(o, pl);
+                LinePre Ln; line_pre_from_plk(pl, Ln);
+                for (int b = 0; b < 2; b++) {
+                    double *c = P.lpre[b] + (size_t)LPRE_N * l;
+                    for (int i = 0; i < 3; i++) { c[i] = Ln.n[i]; c[3 + i] = Ln.d[i]; c[6 + i] = Ln.u1[i]; c[9 + i] = Ln.u2[i]; c[12 + i] = Ln.u3[i]; }
+                    c[15] = Ln.w1; c[16] = Ln.w2;
+                }
             }
         } else
         for (size_t i = g0; i < (size_t)ls_dim * P.n_ls; i += gs) { const double v = P.lns0[i]; P.lns[0][i] = v; P.lns[1][i] = v; }

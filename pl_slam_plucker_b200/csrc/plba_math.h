@@ -122,6 +122,13 @@ PLBA_HD void orth_to_plk(const double *o, double *pl) {
     pl[0] = w1 * R[0]; pl[1] = w1 * R[3]; pl[2] = w1 * R[6];
     pl[3] = w2 * R[1]; pl[4] = w2 * R[4]; pl[5] = w2 * R[7];
 }
+// changeOrthToPluker with one sincos per angle (src/mapFeatures.cpp:203-224)
+PLBA_HD void orth_to_plk_sc(const double *o, double *pl) {
+    double s1, c1, s2, c2, s3, c3, w1, w2;
+    plba_sincos(o[0], &s1, &c1); plba_sincos(o[1], &s2, &c2); plba_sincos(o[2], &s3, &c3); plba_sincos(o[3], &w2, &w1);
+    pl[0] = w1 * (c2 * c3); pl[1] = w1 * (c2 * s3); pl[2] = w1 * (-s2);
+    pl[3] = w2 * (s1 * s2 * c3 - c1 * s3); pl[4] = w2 * (s1 * s2 * s3 + c1 * c3); pl[5] = w2 * (s1 * c2);
+}
 // Per-LANDMARK quantities of a Plücker line: the 6-vector, U = [n/|n|, d/|d|, nxd/|nxd|] and W = (|n|,|d|)/sqrt(|n|^2+|d|^2)
 // (getOrhtRFromPluker / getOrthWFromPluker, g2o_types.h:472-495).  The reference recomputes these per edge.
 struct LinePre { double n[3], d[3], u1[3], u2[3], u3[3], w1, w2; };

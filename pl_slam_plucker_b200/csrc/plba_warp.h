@@ -56,14 +56,6 @@ template <> struct LmD<LT_POINT> { double Pw[3]; };
 template <> struct LmD<LT_LINE_ORTH> { LinePre L; double o[4]; };
 template <> struct LmD<LT_LINE_END> { double Pw[3], Qw[3]; };
 
-// changeOrthToPluker with one sincos per angle (src/mapFeatures.cpp:203-224)
-PLBA_HD void orth_to_plk_sc(const double *o, double *pl) {
-    double s1, c1, s2, c2, s3, c3, w1, w2;
-    plba_sincos(o[0], &s1, &c1); plba_sincos(o[1], &s2, &c2); plba_sincos(o[2], &s3, &c3); plba_sincos(o[3], &w2, &w1);
-    pl[0] = w1 * (c2 * c3); pl[1] = w1 * (c2 * s3); pl[2] = w1 * (-s2);
-    pl[3] = w2 * (s1 * s2 * c3 - c1 * s3); pl[4] = w2 * (s1 * s2 * s3 + c1 * c3); pl[5] = w2 * (s1 * c2);
-}
-
 template <int PROF, int LT> struct LmLoad;
 template <int PROF> struct LmLoad<PROF, LT_POINT> {
     static PLBA_HD void run(const DevP &, const WinCtrl &, int, int lm, const double *state, LmD<LT_POINT> &d) {
@@ -72,11 +64,18 @@ template <int PROF> struct LmLoad<PROF, LT_POINT> {
 };
 template <int PROF> struct LmLoad<PROF, LT_LINE_ORTH> {
     static PLBA_HD void run(const DevP &P, const WinCtrl &ctl, int, int lm, const double *state, LmD<LT_LINE_ORTH> &d) {
-        double pl[6];
         for (int i = 0; i < 4; i++) d.o[i] = state[(size_t)4 * lm + i];
-        if (PROF == PLBA_PROFILE_H_PLK && ctl.iter == 0) { for (int i = 0; i < 6; i++) pl[i] = P.lns_map[(size_t)6 * lm + i]; }   // pass 0 reads map NDw (:1744)
-        else orth_to_plk_sc(d.o, pl);
-        line_pre_from_plk(pl, d.L);
+        if (PROF == PLBA_PROFILE_H_PLK && ctl.iter == 0) {      // pass 0 reads map NDw (:1744)
+            double pl[6];
+            for (int i = 0; i < 6; i++) pl[i] = P.lns_map[(size_t)6 * lm + i];
+            line_pre_from_plk(pl, d.L);
+        } else {
+            // Plücker vector, U and W of the line at the CURRENT state: written once per landmark and state by k_reset / the update
+            // kernel (lane = landmark, all 32 lanes busy with the trigonometry) instead of once per observation and kernel
+            const double *c = P.lpre[ctl.cur] + (size_t)LPRE_N * lm;
+            for (int i = 0; i < 3; i++) { d.L.n[i] = c[i]; d.L.d[i] = c[3 + i]; d.L.u1[i] = c[6 + i]; d.L.u2[i] = c[9 + i]; d.L.u3[i] = c[12 + i]; }
+            d.L.w1 = c[15]; d.L.w2 = c[16];
+        }
     }
 };
 template <int PROF> struct LmLoad<PROF, LT_LINE_END> {
@@ -512,6 +511,8 @@ PLBA_D void update_items_w(const DevP &Pin, const WItem *items, int n_items, uns
     const int D = K::D, RANK = K::RANK;
     WSmem<PROF, LT> sm(wraw);
     double *U = sm.TA;                                           // [RANK][32]: J_pose x_p of each observation
+    double *XL = sm.A, *PL = sm.A + 4 * 32;                       // orthonormal lines: [4][32] step and [6][32] new Plücker vector per landmark of the item
+    (void)XL; (void)PL;                                          //   (the A rows stay in registers in this kernel: their shared-memory tile is free)
     LANE_VAR(double, chi_l); LANE_VAR(double, sc_l); LANE_VAR(double, d2_l);
     LANE_ARR(double, xpl, 6);
     LANE_VAR(int, kf_l); LANE_VAR(int, m_l); LANE_VAR(int, slot_l); LANE_VAR(int, act_l);
@@ -634,15 +635,20 @@ PLBA_D void update_items_w(const DevP &Pin, const WItem *items, int n_items, uns
 #pragma unroll
                         for (int r = 0; r < D; r++) { sc_l += xl[r] * (ctl.lambda * xl[r] + bl[r]); d2_l += xl[r] * xl[r]; }
                     }
+                    if constexpr (LT == LT_LINE_ORTH) {
+                        // orthonormal lines: the retraction and the new Plücker vector are trigonometry per LANDMARK; the step is
+                        // parked in shared memory and retracted below with one lane per landmark (items hold <= 32 line landmarks)
+                        if (leader) {
+#pragma unroll
+                            for (int i = 0; i < D; i++) XL[i * 32 + lmb + m_l] = xl[i];
+                        }
+                    } else {
                     // retraction
                     double cur[D], nw[D];
 #pragma unroll
                     for (int i = 0; i < D; i++) cur[i] = state[(size_t)D * lm + i];
-                    if constexpr (LT == LT_LINE_ORTH) orth_update(cur, xl, nw);                 // updateOrthCoord (a11)
-                    else {
 #pragma unroll
-                        for (int i = 0; i < D; i++) nw[i] = cur[i] + xl[i];
-                    }
+                    for (int i = 0; i < D; i++) nw[i] = cur[i] + xl[i];
                     if (leader && (PROF == PLBA_PROFILE_G || ctl.apply)) {
 #pragma unroll
                         for (int i = 0; i < D; i++) state_new[(size_t)D * lm + i] = nw[i];
@@ -653,16 +659,66 @@ PLBA_D void update_items_w(const DevP &Pin, const WItem *items, int n_items, uns
                         const double *T = P.poseT[ctl.cur ^ 1] + (size_t)12 * kf_l;
                         double e[2];
                         ObsLoad<LT> ob; ob.load(P, o);
-                        if constexpr (LT == LT_POINT) { double zc; g_point_error(P.cam, T, nw, ob.uv, e, zc); }
-                        else { double pl[6]; orth_to_plk_sc(nw, pl); g_line_error(P.cam, T, pl, pl + 3, ob.ab, e); }
+                        double zc; g_point_error(P.cam, T, nw, ob.uv, e, zc);
                         const double chi2 = OA::om(P)[o] * (e[0] * e[0] + e[1] * e[1]);
                         OA::chi2(P)[o] = chi2;                       // the cached _error of the edge (e->chi2())
                         double rho0 = chi2, rho1;
                         if (ctl.stage == 0) huber(P.huber_delta, chi2, rho0, rho1);
                         chi_l += rho0;
                     }
+                    }
                 }
             WPHASE_END
+        }
+        if constexpr (LT == LT_LINE_ORTH) {
+            // ---- lane = landmark: updateOrthCoord (a11), the new state, its Plücker vector / U / W for the next linearisation ----
+            WPHASE_BEGIN
+                if (lane < it.n_lm) {
+                    const int lm = it.lm0 + lane;
+                    double cur[4], xl[4], nw[4], pl[6];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { cur[i] = state[(size_t)4 * lm + i]; xl[i] = XL[i * 32 + lane]; }
+                    orth_update(cur, xl, nw);
+                    orth_to_plk_sc(nw, pl);
+#pragma unroll
+                    for (int i = 0; i < 6; i++) PL[i * 32 + lane] = pl[i];
+                    if (PROF == PLBA_PROFILE_G || ctl.apply) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) state_new[(size_t)4 * lm + i] = nw[i];
+                        LinePre Ln; line_pre_from_plk(pl, Ln);
+                        double *c = P.lpre[ctl.cur ^ 1] + (size_t)LPRE_N * lm;
+#pragma unroll
+                        for (int i = 0; i < 3; i++) { c[i] = Ln.n[i]; c[3 + i] = Ln.d[i]; c[6 + i] = Ln.u1[i]; c[9 + i] = Ln.u2[i]; c[12 + i] = Ln.u3[i]; }
+                        c[15] = Ln.w1; c[16] = Ln.w2;
+                    }
+                }
+            WPHASE_END
+            if constexpr (PROF == PLBA_PROFILE_G) {
+                // ---- new cost at the trial state (computeActiveErrors + activeRobustChi2 after update), lane = observation again ----
+                for (int pass = 0; pass < npass && k; pass++) {
+                    const int lmb = pass * lpp;
+                    const int nlp = (it.n_lm - lmb < lpp) ? it.n_lm - lmb : lpp;
+                    WPHASE_BEGIN
+                        LANE_BIND(chi_l); LANE_BIND(kf_l); LANE_BIND(m_l);
+                        if (lane < nlp * k) {
+                            const int o = it.ob0 + lmb * k + lane;
+                            if (!(ctl.stage == 1 && OA::lvl(P)[o])) {          // the active set of obs_lin_w
+                                const double *T = P.poseT[ctl.cur ^ 1] + (size_t)12 * kf_l;
+                                const int l = lmb + m_l;
+                                const double n3[3] = {PL[l], PL[32 + l], PL[64 + l]}, d3[3] = {PL[96 + l], PL[128 + l], PL[160 + l]};
+                                double e[2];
+                                ObsLoad<LT> ob; ob.load(P, o);
+                                g_line_error(P.cam, T, n3, d3, ob.ab, e);
+                                const double chi2 = OA::om(P)[o] * (e[0] * e[0] + e[1] * e[1]);
+                                OA::chi2(P)[o] = chi2;
+                                double rho0 = chi2, rho1;
+                                if (ctl.stage == 0) huber(P.huber_delta, chi2, rho0, rho1);
+                                chi_l += rho0;
+                            }
+                        }
+                    WPHASE_END
+                }
+            }
         }
     }
     if (cur_win >= 0) {
