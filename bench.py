@@ -124,7 +124,8 @@ def _peak():
 def _traffic(workload):
     """Measured DRAM bytes per k_assemble launch from the committed ncu capture (profiles/traffic.json), or None."""
     try:
-        return int(json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[workload]["k_assemble"])
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[workload]
+        return int(t.get("k_assemble_w", t["k_assemble"]) if workload == "C5" else t["k_assemble"])
     except Exception:
         return None
 
@@ -133,14 +134,15 @@ def largest_config_roofline(s, abi, scene, args):
     """Assembly kernel on BASELINE config 5 (2 000 KFs, 2M points, 500k lines; inputs 0.45 GB >> L2, so every launch is cold)."""
     P5 = scene.make_scene(5)
     s.upload(P5, abi.Options(PROFILES[args.profile] if args.profile != "H_END" else 0, args.quirks))
-    st = s.layout_stats()
+    st = s.layout_stats(); kp = s.kernel_path()
     A = algorithmic_bytes(P5, st["nnzb_S"]); F = algorithmic_flops(P5)
-    ms_a = s.time_kernel(0, 5); ms_u = s.time_kernel(2, 5)
+    ms_a = s.time_kernel(0, 5); ms_u = s.time_kernel(2, 5); ms_s = s.time_kernel(1, 3)
     peak, src = _peak()
     return {"workload": "C5: %d free KFs, %d points, %d lines, %d+%d observations" % (P5.n_free, P5.n_pt, P5.n_ls, P5.n_pobs, P5.n_lobs),
-            "kernel": "k_assemble", "bound": "hbm", "algorithmic_bytes": A, "ms_per_launch": ms_a, "achieved": A / (ms_a * 1e-3) / 1e9, "peak": peak,
+            "kernel": "k_assemble_w" if kp["assembly"] == "warp" else "k_assemble", "kernel_path": kp, "bound": "hbm", "algorithmic_bytes": A, "ms_per_launch": ms_a, "achieved": A / (ms_a * 1e-3) / 1e9, "peak": peak,
             "peak_source": src, "unit": "GB/s", "frac": A / (ms_a * 1e-3) / 1e9 / peak, "traffic": _traffic("C5"), "algorithmic_flops": F, "achieved_fp64_tflops": F / (ms_a * 1e-3) / 1e12,
-            "update_kernel_ms_per_launch": ms_u, "nnzb_S": st["nnzb_S"], "launches_timed": 5,
+            "update_kernel_ms_per_launch": ms_u, "solve_ms_per_trial": ms_s, "lm_trial_ms": ms_a + ms_u + ms_s,
+            "observations_per_s_per_trial": P5.n_obs / ((ms_a + ms_u + ms_s) * 1e-3), "nnzb_S": st["nnzb_S"], "launches_timed": 5,
             "note": "FP64 work (about %.1f GFLOP) bounds this kernel before HBM does: at the 37 TFLOP/s vector peak it needs %.0f us, the HBM roofline %.0f us" % (F / 1e9, F / 37e12 * 1e6, A / (peak * 1e9) * 1e6)}
 
 
@@ -220,7 +222,7 @@ def main():
 
     # ---- resident-problem throughput -------------------------------------------------------------------------
     s.upload(P, opt)
-    nnzb = s.layout_stats()["nnzb_S"]
+    nnzb = s.layout_stats()["nnzb_S"]; kpath = s.kernel_path()
     for _ in range(args.warmup):
         s.reset(); s.run()
     torch.cuda.synchronize()
@@ -288,7 +290,7 @@ def main():
                         "breakdown_ms": {"host_flatten": hp / e2e_steps, "device_lm_loop": gpu_ms / e2e_steps, "host_unpack": hu / e2e_steps}},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
-                "roofline": {"bound": "hbm", "kernel": "k_assemble (one launch per LM trial: points + lines)", "achieved": A / (asm_ms * 1e-3) / 1e9 if asm_ms > 0 else None,
+                "roofline": {"bound": "hbm", "kernel": ("k_assemble_w" if kpath["assembly"] == "warp" else "k_assemble") + " (one launch per LM trial: points + lines)", "kernel_path": kpath, "achieved": A / (asm_ms * 1e-3) / 1e9 if asm_ms > 0 else None,
                              "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": (A / (asm_ms * 1e-3) / 1e9 / peak) if asm_ms > 0 else None,
                              "traffic": _traffic(args.workload) if args.profile == "G" else None, "algorithmic_bytes": A, "ms_per_launch": asm_ms, "launches_timed": int(n_asm),
                              "stage_ms_per_step": {"assemble": t_asm / det_steps, "solve": t_sol / det_steps, "update": t_upd / det_steps},

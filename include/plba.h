@@ -209,6 +209,11 @@ int  plba_set_force_chunk(plba_handle h, int mode);
 /* Layout of the resident problem, for roofline accounting: out8 = { point chunks, line chunks, point segments, line segments,
  * off-diagonal Schur tasks, diagonal Schur tasks, structurally non-zero upper 6x6 blocks of S (nnzb), device arena bytes }. */
 int  plba_layout_stats(plba_handle h, int64_t *out8);
+/* Which kernels the resident upload runs on: out4 = { assembly / update: 0 = CTA-chunk kernels, 1 = warp-autonomous kernels;
+ * reduced-system solver: 0 = one CTA per window in shared memory (6 n_free <= 144), 1 = block cyclic reduction (block-banded
+ * large windows), 2 = single-CTA banded Cholesky, 3 = dense tiled FP64-tensor-core Cholesky; half bandwidth of S in pose
+ * blocks; number of work units (chunks or warp items) }. */
+int  plba_kernel_path(plba_handle h, int32_t *out4);
 /* Optional all-reduce hook called on the handle's stream wherever the path has its exchange step
  * (SURVEY.md §8e).  fn(dev_ptr, n_doubles, stream, user) must sum the buffer in place over all ranks. */
 typedef void (*plba_allreduce_fn)(void *dev_ptr, int64_t n_doubles, void *stream, void *user);

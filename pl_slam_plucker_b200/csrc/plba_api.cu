@@ -1202,6 +1202,14 @@ int plba_debug_prof(unsigned long long *out64, int reset) {
 #endif
 int plba_set_force_dense(plba_handle h, int on) { if (!h) return PLBA_E_ARG; h->force_dense = on != 0; return PLBA_OK; }
 int plba_set_force_chunk(plba_handle h, int mode) { if (!h || mode < 0 || mode > 2) return PLBA_E_ARG; h->force_chunk = mode; return PLBA_OK; }
+int plba_kernel_path(plba_handle h, int32_t *out4) {
+    if (!h || !h->uploaded || !out4) return PLBA_E_ARG;
+    out4[0] = h->warp_path ? 1 : 0;
+    out4[1] = h->small_path ? 0 : (h->band_blocks <= BAND_MAX && !h->force_dense) ? (h->large_solver == 0 && !h->bcr.empty() ? 1 : 2) : 3;
+    out4[2] = h->band_blocks;
+    out4[3] = h->warp_path ? (int)(h->wi_pt.size() + h->wi_ls.size()) : (int)(h->ch_pt.size() + h->ch_ls.size());
+    return PLBA_OK;
+}
 int plba_layout_stats(plba_handle h, int64_t *out8) { if (!h || !h->uploaded || !out8) return PLBA_E_ARG; for (int i = 0; i < 8; i++) out8[i] = h->layout[i]; return PLBA_OK; }
 int plba_get_timing(plba_handle h, plba_timing *t) { if (!h || !t) return PLBA_E_ARG; *t = h->timing; return PLBA_OK; }
 int plba_set_detail_timing(plba_handle h, int on) { if (!h) return PLBA_E_ARG; h->detail_timing = on != 0; return PLBA_OK; }

@@ -121,6 +121,13 @@ class LBASolver:
         keys = ("chunks_pt", "chunks_ls", "segments_pt", "segments_ls", "tasks_offdiag", "tasks_diag", "nnzb_S", "arena_bytes")
         return dict(zip(keys, [int(v) for v in out]))
 
+    def kernel_path(self):
+        """Kernels the resident upload runs on (plba_kernel_path)."""
+        out = (C.c_int32 * 4)()
+        self._check(self.L.plba_kernel_path(self.h, out))
+        return {"assembly": ("cta-chunk", "warp")[out[0]], "solver": ("shared-memory", "block-cyclic-reduction", "banded", "dense-dmma")[out[1]],
+                "band_blocks": int(out[2]), "work_units": int(out[3])}
+
     def set_allreduce(self, fn):
         """fn(ptr:int, n_doubles:int (negative => max-reduce of |n|), stream:int) sums the device buffer over ranks in place."""
         def _cb(ptr, n, stream, user):
