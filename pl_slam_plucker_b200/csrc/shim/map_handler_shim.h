@@ -12,6 +12,7 @@
 //   void localBundleAdjustmentForPlukerWithG2O()               src/mapHandler.cpp:5851-6323   -> PLBA_PROFILE_G
 //   void globalBundleAdjustment()                              src/mapHandler.cpp:3022-3126
 //   void levMarquardtOptimizationGBA(X_aux, kf_list, ...)      src/mapHandler.cpp:3128-3728   -> PLBA_PROFILE_H_END + PLBA_SHELL_GBA
+//   void removeBadMapLandmarksForPluker()                      src/mapHandler.cpp:3816-3897   (host bookkeeping right after the LBA)
 //
 // Only index bookkeeping (flattening, write-back, observation erasure) happens here; every FP64 operation of the path
 // runs in the CUDA library.  If the library reports an error the shim throws: there is no CPU fallback.
@@ -39,6 +40,7 @@ struct KeyFrame {      // include/keyFrame.h:47-79
     int kf_idx = 0;
     Matrix4d T_kf_w{};                          // camera -> world
     Vector6d x_kf_w{};                          // logmap_se3(T_kf_w), translation first (never refreshed by LBA: Q11)
+    std::vector<int> stereo_pt_idx, stereo_ls_idx;   // stereo_frame->stereo_pt[i]->idx / stereo_ls[i]->idx: map landmark of each stereo feature, -1 = none
 };
 struct MapPoint {      // include/mapFeatures.h:41-70
     int idx = 0; bool inlier = true, local = true;
@@ -58,6 +60,7 @@ struct PinholeStereoCamera { double fx, fy, cx, cy; double getFx() const { retur
 struct SlamConfig {    // src/slamConfig.cpp:65-67, src2/config.cpp:80-85
     double lambda_lba_lm = 1e-5, lambda_lba_k = 10.0; int max_iters_lba = 15;
     double homog_th = 1e-7, min_error = 1e-7, min_error_change = 1e-7;
+    int min_lm_obs = 5;                         // src/slamConfig.cpp:48
 };
 enum { VO_PROCESSING = 0, VO_INSERTING_KF = 1 };
 
@@ -68,6 +71,8 @@ public:
     std::vector<MapLine *> map_lines;
     PinholeStereoCamera *cam = nullptr;
     SlamConfig config;
+    unsigned int max_kf_idx = 0;                // include/mapHandler.h:156
+    std::map<int, std::vector<int>> map_points_kf_idx, map_lines_kf_idx;   // base KF -> landmarks first seen there (include/mapHandler.h:148-149)
     int vo_status = VO_PROCESSING;              // never assigned in the reference (Q17)
     int quirks = PLBA_QUIRKS_FAITHFUL;
     int n_bad_point_obs = 0, n_bad_line_obs = 0;
@@ -96,6 +101,15 @@ public:
                                      std::vector<Vector6i> pt_obs_list, std::vector<Vector6i> ls_obs_list) {
         if (pt_obs_list.size() + ls_obs_list.size() == 0) return;      // the reference would factor an empty system; nothing to write back
         hand_lm(PLBA_PROFILE_H_END, X_aux, kf_list, pt_list, ls_list, pt_obs_list, ls_obs_list, PLBA_SHELL_GBA);
+    }
+
+    // ---- culling right after the LBA (localMappingThread, src/mapHandler.cpp:1278-1279).  Landmarks are owned by the caller here, so a
+    //      culled landmark's slot is set to nullptr and the pointer is handed back instead of being deleted (:3851, :3892) ----
+    std::vector<void *> removeBadMapLandmarksForPluker() {
+        std::vector<void *> culled;
+        cull(map_points, map_points_kf_idx, true, culled);
+        cull(map_lines, map_lines_kf_idx, false, culled);
+        return culled;
     }
 
     // ---- the Plücker-mode LBA that actually runs in the reference (src/mapHandler.cpp:5851-6323) ----
@@ -255,6 +269,22 @@ private:
             for (int k = 0; k < 6; k++) (profile == PLBA_PROFILE_H_END ? l->line3D : l->NDw)[k] = (profile == PLBA_PROFILE_H_END ? o.ls_end : o.ls_plk)[6 * i + k];
         }
         return 0;
+    }
+
+    static size_t n_obs_for_culling(const MapPoint *p) { return p->obs_list.size(); }           // :3826
+    static size_t n_obs_for_culling(const MapLine *l) { return l->NDw_obs_list.size(); }        // :3865
+    template <typename LM>
+    void cull(std::vector<LM *> &lms, std::map<int, std::vector<int>> &by_kf, bool point, std::vector<void *> &culled) {
+        for (LM *&lm : lms) {
+            if (!lm || lm->local || !((long long)max_kf_idx - lm->kf_obs_list.at(0) > 10)) continue;                       // :3824 / :3863
+            if (lm->inlier && n_obs_for_culling(lm) >= (size_t)config.min_lm_obs) continue;                                  // :3826 / :3865
+            const int kf_obs = lm->kf_obs_list[0], lm_idx = lm->idx;
+            std::vector<int> &ids = point ? map_keyframes.at(kf_obs)->stereo_pt_idx : map_keyframes.at(kf_obs)->stereo_ls_idx;
+            for (int &v : ids) if (v == lm_idx) { v = -1; break; }                                                           // :3831-3838
+            auto it = by_kf.find(kf_obs);
+            if (it != by_kf.end()) for (size_t j = 0; j < it->second.size(); j++) if (it->second[j] == lm_idx) { it->second.erase(it->second.begin() + j); break; }   // :3841-3848
+            culled.push_back(lm); lm = nullptr;
+        }
     }
 
     template <typename LM>

@@ -21,6 +21,7 @@ VO_PROCESSING, VO_INSERTING_KF = 0, 1
 
 class SlamConfig:
     """The LBA-relevant keys of SlamConfig / Config (src/slamConfig.cpp:61-67, src2/config.cpp:80-85)."""
+    min_lm_obs = 5            # src/slamConfig.cpp:48
     lambda_lba_lm = 1e-5
     lambda_lba_k = 10.0
     max_iters_lba = 15
@@ -45,6 +46,8 @@ class KeyFrame:   # include/keyFrame.h:47-79
         self.T_kf_w = np.array(T_kf_w, dtype=np.float64).reshape(4, 4)
         self.x_kf_w = None if x_kf_w is None else np.array(x_kf_w, dtype=np.float64)
         self.local = bool(local)
+        # stereo_frame->stereo_pt[i]->idx / stereo_ls[i]->idx (include/stereoFeatures.h): map landmark id of each stereo feature, -1 = none
+        self.stereo_pt_idx, self.stereo_ls_idx = [], []
 
 
 class MapPoint:   # include/mapFeatures.h:41-70
@@ -80,6 +83,8 @@ class MapHandler:
         self.cam, self.solver, self.cfg, self.quirks = cam, solver, config or SlamConfig(), quirks
         self.map_keyframes, self.map_points, self.map_lines = [], [], []
         self.full_graph = None
+        self.max_kf_idx = 0                   # include/mapHandler.h:156
+        self.map_points_kf_idx, self.map_lines_kf_idx = {}, {}      # base KF -> landmark ids first seen there (include/mapHandler.h:148-149)
         self.vo_status = VO_PROCESSING        # never assigned in the reference (Q17): treated as VO_PROCESSING
         self.last_result = None
 
@@ -248,6 +253,36 @@ class MapHandler:
             p.point3D = res.pt_xyz[loc].copy()                                                    # :6306-6311
         for loc, l in enumerate(local_ls):
             l.NDw = res.ls_plk[loc].copy()                                                        # :6314-6319
+
+    def localMappingStep(self):
+        """The LBA part of one pass of localMappingThread in Plücker mode (src/mapHandler.cpp:1277-1279): LBA, then culling."""
+        self.localBundleAdjustmentForPlukerWithG2O()
+        self.removeBadMapLandmarksForPluker()
+
+    def removeBadMapLandmarksForPluker(self):
+        """src/mapHandler.cpp:3816-3897: the step right after the LBA.  A landmark that is no longer local, was first
+        seen more than 10 keyframes ago and is an outlier (the `inlier` flag the LBA write-back cleared) or has fewer than minLMObs
+        observations is deleted: its id is cleared in the stereo features of its base keyframe and in map_*_kf_idx."""
+        removed = [0, 0]
+        for cls, (lms, by_kf, feat) in enumerate(((self.map_points, self.map_points_kf_idx, "stereo_pt_idx"), (self.map_lines, self.map_lines_kf_idx, "stereo_ls_idx"))):
+            for i, lm in enumerate(lms):
+                if lm is None or lm.local or not (self.max_kf_idx - lm.kf_obs_list[0] > 10):
+                    continue
+                n_obs = len(lm.obs_list) if cls == 0 else len(lm.NDw_obs_list)          # :3826 / :3865
+                if lm.inlier and n_obs >= self.cfg.min_lm_obs:
+                    continue
+                kf_obs = lm.kf_obs_list[0]
+                ids = getattr(self.map_keyframes[kf_obs], feat)
+                for j, v in enumerate(ids):                                              # first match only (:3831-3838)
+                    if v == lm.idx:
+                        ids[j] = -1
+                        break
+                lst = by_kf.get(kf_obs, [])
+                if lm.idx in lst:
+                    lst.remove(lm.idx)                                                   # first occurrence (:3841-3848)
+                lms[i] = None
+                removed[cls] += 1
+        return tuple(removed)
 
     def _erase_bad(self, lms, ob_lm, flags, all_ids, ob_kf, point):
         n_bad = 0

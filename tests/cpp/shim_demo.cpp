@@ -36,6 +36,19 @@ int main(int argc, char **argv) {
         std::printf("hand_lm rc=%d iters=%zu\n", rc, mh.last_trace.size());
         mh.vo_status = VO_INSERTING_KF;
         std::printf("discarded rc=%d\n", mh.localBundleAdjustmentForPluker());
+        {   // culling right after the LBA (src/mapHandler.cpp:1278-1279): every landmark is old and non-local now; the ones the g2o path
+            // left with fewer than minLMObs observations (or flagged as outliers) go
+            mh.max_kf_idx = 100;
+            size_t expect = 0;
+            for (MapPoint *p : mh.map_points) { p->local = false; mh.map_points_kf_idx[p->kf_obs_list[0]].push_back(p->idx); if (!p->inlier || p->obs_list.size() < 5) expect++; }
+            for (MapLine *l : mh.map_lines) { l->local = false; if (!l->inlier || l->NDw_obs_list.size() < 5) expect++; }
+            const size_t culled = mh.removeBadMapLandmarksForPluker().size();
+            size_t left = 0; for (MapPoint *p : mh.map_points) if (p) left++;
+            std::printf("culled=%zu expected=%zu points_left=%zu\n", culled, expect, left);
+            // (the unique_ptr vectors above still own the culled objects; restore the slots so that the GBA below sees the whole map)
+            for (size_t i = 0; i < pts.size(); i++) { mh.map_points[i] = pts[i].get(); pts[i]->local = true; }
+            for (size_t i = 0; i < lns.size(); i++) { mh.map_lines[i] = lns[i].get(); lns[i]->local = true; }
+        }
         mh.globalBundleAdjustment();                                  // shutdown-time global BA: ignores vo_status and the `local` flags, returns nothing
         std::printf("gba iters=%zu\n", mh.last_trace.size());
     } catch (const std::exception &e) { std::fprintf(stderr, "error: %s\n", e.what()); plba_scene_destroy(sc); return 1; }

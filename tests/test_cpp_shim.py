@@ -29,6 +29,8 @@ def _check(out, oracle):
     assert int(m.group(4)) == int(((o.po_flags & abi.OBS_BAD) != 0).sum()) and int(m.group(5)) == int(((o.lo_flags & abi.OBS_BAD) != 0).sum())
     np.testing.assert_allclose([float(m.group(i)) for i in (6, 7, 8)], o.kf_T_wc[2][[3, 7, 11]], atol=1e-8)
     assert re.search(r"hand_lm rc=0 iters=\d+", out) and "discarded rc=-1" in out
+    m2 = re.search(r"culled=(\d+) expected=(\d+) points_left=(\d+)", out)      # removeBadMapLandmarksForPluker after the LBA
+    assert m2 and m2.group(1) == m2.group(2) and int(m2.group(1)) > 0 and int(m2.group(3)) < 120
     assert "gba iters=15" in out             # faithful GBA: err /= 0 in every pass, so all maxItersLba passes run (src/mapHandler.cpp:3662-3665)
 
 

@@ -177,3 +177,32 @@ def test_golden_fixtures(oracle, name):
     assert (r.trace["accepted"][:n] == z["trace_accepted"][:n]).all()
     np.testing.assert_allclose(r.kf_T_wc, z["out_kf_T_wc"], atol=1e-8)
     np.testing.assert_allclose(r.pt_xyz, z["out_pt_xyz"], atol=1e-8)
+
+
+def test_culling_after_lba_host_bookkeeping():
+    """removeBadMapLandmarksForPluker (src/mapHandler.cpp:3816-3897) in the Python mirror: pure index work, no solver."""
+    from pl_slam_plucker_b200 import map_handler as mhm
+    mh = mhm.MapHandler(mhm.PinholeStereoCamera(400, 400, 320, 240), solver=None)
+    for k in range(14):
+        mh.map_keyframes.append(mhm.KeyFrame(k, np.eye(4)))
+    mh.max_kf_idx = 13
+    def point(idx, base, n_obs, inlier=True, local=False):
+        p = mhm.MapPoint(idx, [0, 0, 5], local=local); p.inlier = inlier
+        for j in range(n_obs):
+            p.addMapPointObservation(base + j, [10.0, 20.0])
+        mh.map_points.append(p); mh.map_points_kf_idx.setdefault(base, []).append(idx); mh.map_keyframes[base].stereo_pt_idx.append(idx)
+        return p
+    point(0, 0, 6)                         # old, enough observations, inlier: kept
+    point(1, 0, 3)                         # old, too few observations (< minLMObs = 5): culled
+    point(2, 1, 6, inlier=False)           # old outlier (the LBA write-back cleared `inlier`): culled
+    point(3, 5, 2)                         # first seen 8 keyframes ago: too recent to be judged
+    point(4, 0, 2, local=True)             # still local: kept
+    ln = mhm.MapLine(0, NDw=[0, 0, 1, 1, 0, 0], local=False)
+    for j in range(2):
+        ln.addMapLineObservation(j, [1.0, 2.0, 3.0, 4.0])
+    mh.map_lines.append(ln); mh.map_lines_kf_idx[0] = [0]; mh.map_keyframes[0].stereo_ls_idx.append(0)
+    assert mh.removeBadMapLandmarksForPluker() == (2, 1)
+    assert [p is None for p in mh.map_points] == [False, True, True, False, False] and mh.map_lines[0] is None
+    assert mh.map_points_kf_idx[0] == [0, 4] and mh.map_points_kf_idx[1] == [] and mh.map_lines_kf_idx[0] == []
+    assert mh.map_keyframes[0].stereo_pt_idx == [0, -1, 4] and mh.map_keyframes[1].stereo_pt_idx == [-1] and mh.map_keyframes[0].stereo_ls_idx == [-1]
+    assert mh.removeBadMapLandmarksForPluker() == (0, 0)          # idempotent
