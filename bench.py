@@ -151,7 +151,7 @@ def sharded_run(s, abi, scene, args, rank, world, dev, stream, barrier):
     import torch
     import torch.distributed as dist
     from pl_slam_plucker_b200 import sharded, solver
-    P4 = scene.make_scene(4)
+    P4 = scene.make_scene(WORKLOADS[args.sharded_workload])
     s2 = solver.LBASolver(dev.index, stream=stream.cuda_stream)
     sh = sharded.ShardedLBA(s2, rank, world, device=dev)
     opt = abi.Options(abi.PROFILE_G, 1)
@@ -166,11 +166,12 @@ def sharded_run(s, abi, scene, args, rank, world, dev, stream, barrier):
             t_ms += e0.elapsed_time(e1); trials += s2.timing()["n_trials_run"]
     t = torch.tensor([t_ms], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    n_dbl = s2.reduced_system_ptr()[1]
+    n_dbl = s2.reduced_system_ptr()[1]; kpath = s2.kernel_path()
     s2.close()
-    return {"workload": "C4: %d free KFs, %d points, %d lines sharded by base keyframe over %d GPUs" % (P4.n_free, P4.n_pt, P4.n_ls, world),
+    return {"workload": "%s: %d free KFs, %d points, %d lines sharded by base keyframe over %d GPUs" % (args.sharded_workload, P4.n_free, P4.n_pt, P4.n_ls, world),
             "lm_trials": trials // reps, "ms_per_lba": float(t.item()) / reps, "observations_per_s": P4.n_obs * trials / (float(t.item()) * 1e-3),
-            "allreduce_bytes_per_trial": int(8 * n_dbl), "collective": "NCCL all-reduce of [S | g] per LM trial (torch.distributed)"}
+            "allreduce_bytes_per_trial": int(8 * n_dbl), "kernel_path": kpath,
+            "collective": "NCCL all-reduce per LM trial (torch.distributed) of the band of the reduced camera system in node form [D | U | b] when the block-cyclic-reduction solver runs, of the dense [S | g] otherwise"}
 
 
 def workload_name(args, P):
@@ -189,7 +190,8 @@ def main():
     ap.add_argument("--quirks", type=int, default=0, help="0 = faithful (bug-for-bug), 1 = fixed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-largest", action="store_true", help="skip the C5 assembly roofline measurement")
-    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the landmark-sharded C4 run")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the landmark-sharded run")
+    ap.add_argument("--sharded-workload", default="C4", choices=["C4", "C5"], help="N > 1: the window that is sharded by base keyframe over the ranks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":

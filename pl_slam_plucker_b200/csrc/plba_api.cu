@@ -43,6 +43,7 @@ struct plba_handle_s {
     char *h_in = nullptr; size_t h_in_cap = 0;       // pinned: staged inputs
     char *h_out = nullptr; size_t h_out_cap = 0;     // pinned: staged outputs
     DevP *d_P = nullptr;                             // fixed address: kernel parameters
+    double *d_scratch = nullptr;                     // a few doubles of device memory for upload-time exchanges
     DevP *h_P = nullptr;                             // pinned copy
     int *h_cnt = nullptr;                            // pinned counters
     DevP P{};
@@ -270,6 +271,8 @@ int plba_create(int32_t device, void *stream, plba_handle *out) {
     void *q = nullptr;
     if (cudaMalloc(&q, sizeof(DevP)) != cudaSuccess) { delete h; *out = nullptr; return PLBA_E_CUDA; }
     h->d_P = (DevP *)q;
+    if (cudaMalloc(&q, 64) != cudaSuccess) { cudaFree(h->d_P); delete h; *out = nullptr; return PLBA_E_CUDA; }
+    h->d_scratch = (double *)q;
     if (cudaMallocHost(&q, sizeof(DevP)) != cudaSuccess) { cudaFree(h->d_P); delete h; *out = nullptr; return PLBA_E_CUDA; }
     h->h_P = (DevP *)q;
     if (cudaMallocHost(&q, sizeof(int) * CNT_N) != cudaSuccess) { cudaFree(h->d_P); cudaFreeHost(h->h_P); delete h; *out = nullptr; return PLBA_E_CUDA; }
@@ -288,6 +291,7 @@ void plba_destroy(plba_handle h) {
 #endif
     h->release();
     if (h->d_P) cudaFree(h->d_P);
+    if (h->d_scratch) cudaFree(h->d_scratch);
     if (h->h_P) cudaFreeHost(h->h_P);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
     for (int i = 0; i < 8; i++) cudaEventDestroy(h->ev[i]);
@@ -414,6 +418,13 @@ static void launch_update(plba_handle h, int flags) {
     }
     h->timing.n_launches++;
 }
+static void allreduce(plba_handle h, double *p, size_t n, int op_max) {
+    if (!h->allreduce || !n) return;
+    // op is encoded in the sign of the count for the max reduction (the lambda-init scalar and the band width use it)
+    h->allreduce(p, op_max ? -(int64_t)n : (int64_t)n, (void *)h->stream, h->allreduce_user);
+}
+static inline size_t bcr_exchange_doubles(const BcrW &B) { return (size_t)2 * B.N * B.m * B.m + (size_t)2 * B.N * B.m; }
+static bool bcr_is_active(plba_handle h) { return !h->small_path && h->band_blocks <= BAND_MAX && !h->force_dense && h->large_solver == 0 && !h->bcr.empty(); }
 static void launch_solve(plba_handle h) {
     const DevP &P = h->P; const DevP *Pp = h->d_P;
     if (P.n_free == 0) return;
@@ -430,6 +441,9 @@ static void launch_solve(plba_handle h) {
             const BcrW &B = h->bcr[w];
             if (B.N == 0 || h->wins[w].n_pobs + h->wins[w].n_lobs == 0) continue;
             PLBA_LAUNCH(k_bcr_gather, dim3(B.N), dim3(256), 0, h->stream, Pp, w, B); h->timing.n_launches++;
+            // the exchange step of the landmark-sharded path: only the band [D | U | b | hd] of the window travels (config 5: 17 MB, not
+            // the 1.15 GB of the dense S)
+            allreduce(h, B.D, bcr_exchange_doubles(B), 0);
             int s_top = 0;
             for (int s = 1; s < B.N; s *= 2) {
                 PLBA_LAUNCH(k_bcr_elim, dim3((B.N + s - 1) / (2 * s)), dim3(BCR_NT), bcr_elim_smem(), h->stream, Pp, w, B, s, 0); h->timing.n_launches++;
@@ -475,11 +489,7 @@ static void launch_solve(plba_handle h) {
     }
     PLBA_LAUNCH(k_pose_update, grid1(P.n_free, 128), dim3(128), 0, h->stream, Pp); h->timing.n_launches++;
 }
-static void allreduce(plba_handle h, double *p, size_t n, int op_max) {
-    if (!h->allreduce || !n) return;
-    // op is encoded in the sign of the count for the max reduction (only the lambda-init scalar uses it)
-    h->allreduce(p, op_max ? -(int64_t)n : (int64_t)n, (void *)h->stream, h->allreduce_user);
-}
+
 static int poll_counters(plba_handle h) {
     CK(cudaMemcpyAsync(h->h_cnt, h->P.counters, sizeof(int) * CNT_N, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -749,6 +759,16 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
         }
         h->layout[0] = (int64_t)ch_pt.size(); h->layout[1] = (int64_t)ch_ls.size(); h->layout[2] = (int64_t)sg_pt.size(); h->layout[3] = (int64_t)sg_ls.size();
         h->layout[4] = n_off; h->layout[5] = n_diag; h->layout[6] = nnzb; h->band_blocks = band;
+        if (h->allreduce) {
+            // landmark-sharded path: every rank must pick the same solver and the same node layout, i.e. agree on the half bandwidth
+            // of the SUMMED reduced camera system = the largest over the shards (max all-reduce through the caller's hook)
+            double v = (double)band;
+            CK(cudaMemcpyAsync(h->d_scratch, &v, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            allreduce(h, h->d_scratch, 1, 1);
+            CK(cudaMemcpyAsync(&v, h->d_scratch, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            h->band_blocks = (int)v;
+        }
     }
 
     // ---- memory plan ----------------------------------------------------------------------------------------
@@ -786,8 +806,8 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
             BcrW B{}; B.bs = bs; B.m = m; B.N = (h->wins[w].n_free + bs - 1) / bs;
             h->bcr.push_back(B);
             const size_t nn = (size_t)B.N * m * m;
-            for (int a = 0; a < 4; a++) s_bcr.push_back(cs.take<double>(nn));
-            for (int a = 0; a < 2; a++) s_bcr.push_back(cs.take<double>((size_t)B.N * m));
+            s_bcr.push_back(cs.take<double>(2 * nn + (size_t)2 * B.N * m));       // [D | U | b | hd]: contiguous (exchange step)
+            s_bcr.push_back(cs.take<double>(nn)); s_bcr.push_back(cs.take<double>(nn)); s_bcr.push_back(cs.take<double>((size_t)B.N * m));   // Xl, Xr, y
         }
     }
     const int trace_cap = (prof == PLBA_PROFILE_G) ? (opt->iters_stage1 + opt->iters_stage2) * opt->lm_max_trials + 2 : opt->max_iters_lba + 2;
@@ -909,8 +929,9 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     P.xp = (double *)(db + s_xp);
     for (size_t w = 0; w < h->bcr.size(); w++) {
         BcrW &B = h->bcr[w];
-        B.D = (double *)(db + s_bcr[6 * w]); B.U = (double *)(db + s_bcr[6 * w + 1]); B.Xl = (double *)(db + s_bcr[6 * w + 2]); B.Xr = (double *)(db + s_bcr[6 * w + 3]);
-        B.b = (double *)(db + s_bcr[6 * w + 4]); B.y = (double *)(db + s_bcr[6 * w + 5]);
+        const size_t nn = (size_t)B.N * B.m * B.m;
+        B.D = (double *)(db + s_bcr[4 * w]); B.U = B.D + nn; B.b = B.U + nn; B.hd = B.b + (size_t)B.N * B.m;
+        B.Xl = (double *)(db + s_bcr[4 * w + 1]); B.Xr = (double *)(db + s_bcr[4 * w + 2]); B.y = (double *)(db + s_bcr[4 * w + 3]);
     }
     P.ctrl = (WinCtrl *)(db + h->o_ctrl); P.trace = (plba_trace_rec *)(db + h->o_trace); P.trace_cap = trace_cap; P.counters = (int *)(db + h->o_cnt);
     set_all_attrs();
@@ -926,6 +947,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     CK(cudaMemcpyAsync(h->d_P, h->h_P, sizeof(DevP), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_arena, h->h_in, h->in_bytes, cudaMemcpyHostToDevice, h->stream));
     h->timing.h2d_bytes += (int64_t)(h->in_bytes + sizeof(DevP));
+    for (const BcrW &B : h->bcr) CK(cudaMemsetAsync(B.D, 0, sizeof(double) * bcr_exchange_doubles(B), h->stream));   // entries no kernel writes (upper triangles, the unused U of node 0) stay 0 in the exchange
     h->uploaded = true;
     return launch_reset(h);
 }
@@ -944,7 +966,7 @@ int plba_reset_state(plba_handle h) {
 static int run_round(plba_handle h, bool need_prep) {
     DevP &P = h->P; cudaStream_t st = h->stream; const DevP *Pp = h->d_P;
     // (the block-cyclic-reduction solver clears what it consumes; the other large-window solvers leave S dirty)
-    const bool bcr_active = h->band_blocks <= BAND_MAX && !h->force_dense && h->large_solver == 0 && !h->bcr.empty();
+    const bool bcr_active = bcr_is_active(h);
     if (!h->small_path && !bcr_active) CK(cudaMemsetAsync(h->sysbuf, 0, sizeof(double) * (h->S_doubles + (size_t)12 * P.n_free), st));
     if (need_prep) {
         PLBA_LAUNCH(k_gate, dim3(h->grid_chunks), dim3(256), 0, st, Pp); h->timing.n_launches++;
@@ -956,7 +978,7 @@ static int run_round(plba_handle h, bool need_prep) {
     if (h->detail_timing) cudaEventRecord(h->ev[0], st);
     launch_assemble(h, 1);
     if (h->detail_timing) cudaEventRecord(h->ev[1], st);
-    allreduce(h, h->sysbuf, h->S_doubles + (size_t)12 * P.n_free, 0);            // the exchange step: S, g, hpp_diag
+    if (!bcr_is_active(h)) allreduce(h, h->sysbuf, h->S_doubles + (size_t)12 * P.n_free, 0);   // the exchange step: S, g, hpp_diag (block cyclic reduction: the band only, after its gather)
     allreduce(h, P.acc, (size_t)4 * P.n_win, 0);                                 // assemble-phase cost sums
     launch_solve(h);
     if (h->detail_timing) cudaEventRecord(h->ev[2], st);
@@ -1161,7 +1183,10 @@ int plba_trial_finish(plba_handle h, double lambda, double *chi_new, double *sca
 int plba_reduced_system(plba_handle h, void **dev_ptr, int64_t *n_doubles) {
     if (!h || !h->uploaded) return PLBA_E_ARG;
     if (dev_ptr) *dev_ptr = h->sysbuf;
-    if (n_doubles) *n_doubles = (int64_t)(h->S_doubles + (size_t)6 * h->P.n_free);
+    if (n_doubles) {
+        *n_doubles = (int64_t)(h->S_doubles + (size_t)6 * h->P.n_free);
+        if (bcr_is_active(h)) { int64_t t = 0; for (const BcrW &B : h->bcr) t += (int64_t)bcr_exchange_doubles(B); *n_doubles = t; }   // what the exchange step moves
+    }
     return PLBA_OK;
 }
 int plba_copy_reduced_system(plba_handle h, int32_t window, double *S_out, double *g_out) {

@@ -739,22 +739,23 @@ PLBA_KERNEL void k_solve_banded(const DevP *Pp, int bwb) {
 // the levels are walked back:  L^T x_i = y - Xl^T x_{i-s} - Xr^T x_{i+s}.
 // This is a Cholesky factorisation in a nested-dissection order of the keyframe chain: same system, same solution up to rounding,
 // but the 6 Nkf sequential pivots of the banded factorisation become 90 ceil(log2 N) and every level fills the GPU.
-struct BcrW { double *D, *U, *Xl, *Xr, *b, *y; int N, bs, m, pad; };      // node storage: D, U, Xl, Xr: [N][m*m] (row stride m); b, y: [N][m]
+struct BcrW { double *D, *U, *b, *hd, *Xl, *Xr, *y; int N, bs, m, pad; };   // node storage: D, U, Xl, Xr: [N][m*m] (row stride m); b, hd, y: [N][m];
+                                                                           // [D | U | b | hd] is one contiguous range: the exchange step of the sharded path
 enum { BCR_BS_MAX = 15, BCR_M_MAX = 6 * BCR_BS_MAX, BCR_NT = 512 };
 static inline size_t bcr_elim_smem() { return sizeof(double) * ((size_t)(3 * BCR_M_MAX + 1) * (BCR_M_MAX + 1) + BCR_M_MAX + 21 * BCR_BS_MAX + 6 * 264 + 8) + 64; }
 static inline size_t bcr_back_smem() { return sizeof(double) * ((size_t)BCR_M_MAX * (BCR_M_MAX + 1) + 3 * BCR_M_MAX + 8) + 64; }
 PLBA_HD int bcr_node_size(const BcrW &B, int nf, int i) { const int k0 = i * B.bs, k1 = (k0 + B.bs < nf) ? k0 + B.bs : nf; return 6 * (k1 - k0); }
 
-// dense S (upper storage) -> node form, damping added to the diagonal.  Everything the assembly wrote is read here exactly once
-// (blocks of one node, blocks between neighbouring nodes, g, diag(H_pp)) and cleared behind the read: the next assembly
-// accumulates into a clean system without a memset of the dense S (1.15 GB at config 5).
+// dense S (upper storage) -> node form (undamped: the damping goes on when a node is loaded for elimination, i.e. after the
+// exchange step of the sharded path).  Everything the assembly wrote is read here exactly once (blocks of one node, blocks
+// between neighbouring nodes, g, diag(H_pp)) and cleared behind the read: the next assembly accumulates into a clean system
+// without a memset of the dense S (1.15 GB at config 5).
 PLBA_KERNEL void k_bcr_gather(const DevP *Pp, int w, BcrW B) {
     PLBA_PARAMS(P, Pp);
     const WinCtrl &ctl = P.ctrl[w];
     if (ctl.done) return;
     const int nf = P.win_nfree[w], n = 6 * nf, slot0 = P.win_slot0[w], m = B.m;
     double *Sw = P.S + P.win_S_off[w];
-    const double lambda = ctl.lambda;
     const int i = PLBA_BID, oi = 6 * i * B.bs, mi = bcr_node_size(B, nf, i);
     double *D = B.D + (size_t)i * m * m, *U = B.U + (size_t)i * m * m;
     PHASE_BEGIN
@@ -763,10 +764,6 @@ PLBA_KERNEL void k_bcr_gather(const DevP *Pp, int w, BcrW B) {
             if (c > r) continue;
             double v = Sw[(size_t)(oi + c) * n + oi + r];
             Sw[(size_t)(oi + c) * n + oi + r] = 0.0;
-            if (r == c) {
-                if (P.profile == PLBA_PROFILE_G) v += lambda;
-                else { v += lambda * P.hpp_diag[(size_t)6 * slot0 + oi + r]; P.hpp_diag[(size_t)6 * slot0 + oi + r] = 0.0; }
-            }
             D[(size_t)r * m + c] = v;
         }
         if (i > 0) {
@@ -777,7 +774,10 @@ PLBA_KERNEL void k_bcr_gather(const DevP *Pp, int w, BcrW B) {
                 Sw[(size_t)(ol + r) * n + oi + c] = 0.0;
             }
         }
-        for (int c = tid; c < mi; c += PLBA_NT) { B.b[(size_t)i * m + c] = P.gs[(size_t)6 * slot0 + oi + c]; P.gs[(size_t)6 * slot0 + oi + c] = 0.0; }
+        for (int c = tid; c < mi; c += PLBA_NT) {
+            B.b[(size_t)i * m + c] = P.gs[(size_t)6 * slot0 + oi + c]; P.gs[(size_t)6 * slot0 + oi + c] = 0.0;
+            if (P.profile != PLBA_PROFILE_G) { B.hd[(size_t)i * m + c] = P.hpp_diag[(size_t)6 * slot0 + oi + c]; P.hpp_diag[(size_t)6 * slot0 + oi + c] = 0.0; }
+        }
     PHASE_END
 }
 
@@ -798,7 +798,13 @@ PLBA_KERNEL void k_bcr_elim(const DevP *Pp, int w, BcrW B, int s, int final) {
     double *Ur = right >= 0 ? B.U + (size_t)right * m * m : nullptr;
     PHASE_BEGIN
         if (tid == 0) *fail = 0;
-        for (int idx = tid; idx < mi * mi; idx += PLBA_NT) { const int r = idx / mi, c = idx - r * mi; if (c <= r) M[(size_t)r * ldm + c] = Di[(size_t)r * m + c]; }
+        for (int idx = tid; idx < mi * mi; idx += PLBA_NT) {
+            const int r = idx / mi, c = idx - r * mi;
+            if (c > r) continue;
+            double v = Di[(size_t)r * m + c];
+            if (c == r) v += (P.profile == PLBA_PROFILE_G) ? ctl.lambda : ctl.lambda * B.hd[(size_t)i * m + r];      // g2o: additive; hand LM: H_ii (1 + lambda)
+            M[(size_t)r * ldm + c] = v;
+        }
         for (int idx = tid; idx < ml * mi; idx += PLBA_NT) { const int r = idx / mi, c = idx - r * mi; M[(size_t)(mi + r) * ldm + c] = Ui[(size_t)r * m + c]; }
         // A[i+s, i] = A[i, i+s]^T: rows = unknowns of the right neighbour (reads walk the rows of its U block: coalesced over r)
         for (int idx = tid; idx < mr * mi; idx += PLBA_NT) { const int c = idx / mr, r = idx - c * mr; M[(size_t)(mi + ml + r) * ldm + c] = Ur[(size_t)c * m + r]; }

@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, quirks, out_dir):
+def _worker(rank, world, port, quirks, out_dir, shape):
     for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "emu")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -29,7 +29,7 @@ def _worker(rank, world, port, quirks, out_dir):
     from pl_slam_plucker_b200 import abi, scene, sharded, solver
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
     try:
-        P = scene.make_scene(1, n_kf_free=8, n_kf_fixed=2, n_pt=300, n_ls=80, seed=31)
+        P = scene.make_scene(1, seed=31, **shape)
         s = solver.LBASolver(0, lib=emu_lib.load())
         sh = sharded.ShardedLBA(s, rank, world)
         opt = abi.Options(abi.PROFILE_G, quirks)
@@ -43,13 +43,18 @@ def _worker(rank, world, port, quirks, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("quirks", [0, 1])
-def test_two_rank_sharded_lba_equals_single_process_oracle(tmp_path, oracle, quirks):
+SMALL = dict(n_kf_free=8, n_kf_fixed=2, n_pt=300, n_ls=80)          # reduced camera system solved in one CTA: the whole [S | g] is exchanged
+LARGE = dict(n_kf_free=40, n_kf_fixed=2, n_pt=800, n_ls=200)        # block cyclic reduction: only the band [D | U | b] of the nodes is exchanged,
+                                                                    # and the ranks first agree on the band width of the summed system
+
+
+@pytest.mark.parametrize("quirks,shape", [(0, SMALL), (1, SMALL), (1, LARGE)], ids=["faithful-small", "fixed-small", "fixed-large-banded"])
+def test_two_rank_sharded_lba_equals_single_process_oracle(tmp_path, oracle, quirks, shape):
     from helpers import COST_RTOL, RHO_MARGIN, STATE_ATOL
     from pl_slam_plucker_b200 import abi, scene
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), quirks, str(tmp_path)), nprocs=world, join=True)
-    P = scene.make_scene(1, n_kf_free=8, n_kf_fixed=2, n_pt=300, n_ls=80, seed=31)
+    mp.spawn(_worker, args=(world, _free_port(), quirks, str(tmp_path), shape), nprocs=world, join=True)
+    P = scene.make_scene(1, seed=31, **shape)
     o = oracle.solve(P, abi.Options(abi.PROFILE_G, quirks))
     z = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(world)]
     # every rank took the same LM decisions and ended with the same poses
