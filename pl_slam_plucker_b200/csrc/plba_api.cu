@@ -573,6 +573,8 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     if (opt->shell != PLBA_SHELL_LBA && !(opt->shell == PLBA_SHELL_GBA && opt->profile == PLBA_PROFILE_H_END)) { h->err = "the GBA shell exists for profile H_END only"; return PLBA_E_ARG; }
     CK(cudaSetDevice(h->device));
     const auto t_host0 = std::chrono::steady_clock::now();
+    auto t_hp = t_host0; const bool hostprof = std::getenv("PLBA_HOST_PROF") != nullptr;
+#define HOSTPROF(name) do { if (hostprof) { const auto t_ = std::chrono::steady_clock::now(); std::fprintf(stderr, "[upload] %-10s %.3f ms\n", name, std::chrono::duration<double, std::milli>(t_ - t_hp).count()); t_hp = t_; } } while (0)
     h->uploaded = false;
     h->opt = *opt;
     h->timing = plba_timing{};
@@ -594,6 +596,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
         max_nf = std::max(max_nf, p.n_free);
         for (int i = 0; i < 4; i++) if (p.cam[i] != probs[0].cam[i]) { h->err = "all windows of a batch must share the camera"; return PLBA_E_UNSUPPORTED; }
     }
+    HOSTPROF("validate");
     h->max_nf = max_nf;
     h->small_path = (6 * max_nf <= SMALL_NMAX);
     h->solve_class = solve_small_class(6 * max_nf);
@@ -621,6 +624,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
         signature_order(p.n_pt, p.n_pobs, p.po_lm, p.po_kf, true, Lps[w]);
         signature_order(p.n_ls, p.n_lobs, p.lo_lm, p.lo_kf, prof != PLBA_PROFILE_H_END, Lls[w]);   // Q3 addresses endpoint lines by position
     }
+    HOSTPROF("sigorder");
     // route: the warp-autonomous kernels take windows whose longest track fits a warp; anything longer (or force_chunk) runs on the
     // CTA-chunk kernels
     int max_track = 0;
@@ -734,6 +738,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     }
     if (too_long) { h->err = "a landmark has more than 256 observations"; return PLBA_E_UNSUPPORTED; }
 
+    HOSTPROF("chunks");
     {   // layout statistics (plba_layout_stats): structural non-zero 6x6 blocks of S = union over segments of their pose pairs
         std::vector<size_t> wbase(n + 1, 0);
         for (int w = 0; w < n; w++) wbase[w + 1] = wbase[w] + (size_t)h->wins[w].n_free * h->wins[w].n_free;
@@ -771,6 +776,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
         }
     }
 
+    HOSTPROF("stats");
     // ---- memory plan ----------------------------------------------------------------------------------------
     Carver ci;   // staged inputs (same offsets in pinned host memory and at the start of the device arena)
     const size_t i_kf_slot = ci.take<int>(tot.n_kf), i_kf_win = ci.take<int>(tot.n_kf), i_slot_kf = ci.take<int>(tot.n_free);
@@ -824,6 +830,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     if (rc) return rc;
     h->layout[7] = (int64_t)co.off;
 
+    HOSTPROF("memplan");
     // ---- flatten into the pinned staging buffer ------------------------------------------------------------------
     char *hb = h->h_in;
     int *kf_slot = (int *)(hb + i_kf_slot), *kf_win = (int *)(hb + i_kf_win), *slot_kf = (int *)(hb + i_slot_kf);
@@ -895,6 +902,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
         ctrl0[w] = c;
     }
 
+    HOSTPROF("flatten");
     // ---- kernel parameters ------------------------------------------------------------------------------------
     DevP &P = h->P;
     P = DevP{};
@@ -942,6 +950,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
         P.cond_while = (unsigned long long)h->cond_while[pi]; P.cond_prep = (unsigned long long)h->cond_prep[pi];
     }
 #endif
+    HOSTPROF("params");
     *h->h_P = P;
     h->timing.ms_host_prep = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
     CK(cudaMemcpyAsync(h->d_P, h->h_P, sizeof(DevP), cudaMemcpyHostToDevice, h->stream));
@@ -1071,6 +1080,8 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     const auto t_host0 = std::chrono::steady_clock::now();
+    auto t_hp = t_host0; const bool hostprof = std::getenv("PLBA_HOST_PROF") != nullptr;
+#define HOSTPROF(name) do { if (hostprof) { const auto t_ = std::chrono::steady_clock::now(); std::fprintf(stderr, "[upload] %-10s %.3f ms\n", name, std::chrono::duration<double, std::milli>(t_ - t_hp).count()); t_hp = t_; } } while (0)
     const char *ob = h->h_out - h->out_off;      // so that ob + o_xxx addresses the host copy
     const double *T = (const double *)(ob + h->o_T), *X = (const double *)(ob + h->o_x), *pt = (const double *)(ob + h->o_pt), *ls = (const double *)(ob + h->o_ls);
     const double *plk = (const double *)(ob + h->o_plk), *pchi = (const double *)(ob + h->o_pchi), *lchi = (const double *)(ob + h->o_lchi);
