@@ -65,6 +65,8 @@ PLBA_D double plba_warp_max(double v) { for (int o = 16; o > 0; o >>= 1) v = fma
 #define PLBA_WARP_FLUSH_ADD(ptr, v) do { const double s_ = plba_warp_sum(v); if (lane == 0 && s_ != 0.0) plba_atomic_add((ptr), s_); } while (0)
 #define PLBA_WARP_FLUSH_MAX(ptr, v) do { const double s_ = plba_warp_max(v); if (lane == 0 && s_ > 0.0) plba_atomic_max_pos((ptr), s_); } while (0)
 PLBA_HD void plba_sincos(double x, double *s, double *c) { sincos(x, s, c); }
+// pull a line into L1 ahead of its use (no register is tied up: the next pass of a warp kernel reads it after ~1 000 instructions)
+PLBA_D void plba_prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // optional per-phase cycle accounting (development builds only: -DPLBA_PROF): thread 0 of every CTA adds the cycles between
 // two marks to a global table that tools read back through plba_debug_prof()
 #ifdef PLBA_PROF
@@ -138,6 +140,7 @@ inline void plba_block_add(double *d, double v) { *d += v; }
 #define PLBA_WARP_FLUSH_ADD(ptr, v) do { *(ptr) += (v); } while (0)
 #define PLBA_WARP_FLUSH_MAX(ptr, v) do { if ((v) > *(ptr)) *(ptr) = (v); } while (0)
 inline void plba_sincos(double x, double *s, double *c) { *s = std::sin(x); *c = std::cos(x); }
+inline void plba_prefetch_l1(const void *) {}
 #define PLBA_PARAMS(P, Pp) const DevP &P = *(Pp)
 #define PLBA_PARAMS_REF(P, Pin) const DevP &P = Pin
 #define PROF_DECL

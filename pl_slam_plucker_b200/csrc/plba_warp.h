@@ -162,6 +162,19 @@ PLBA_HD bool obs_lin_w(const DevP &P, const WinCtrl &ctl, int o, int kf, const L
     return active;
 }
 
+// inputs of one observation of a pass (measurement, information, level flag, landmark state / line cache) pulled towards L1
+template <int PROF, int LT>
+PLBA_D void prefetch_obs_w(const DevP &P, const WinCtrl &ctl, int o, int lm, const double *state) {
+    typedef ObsAcc<LT> OA;
+    if (LT == LT_POINT) { plba_prefetch_l1(P.po_uv + (size_t)2 * o); plba_prefetch_l1(state + (size_t)3 * lm); }
+    else {
+        plba_prefetch_l1(P.lo_ab + (size_t)4 * o); plba_prefetch_l1(state + (size_t)KT<PROF, LT>::D * lm);
+        if (LT == LT_LINE_ORTH) { const double *c = P.lpre[ctl.cur] + (size_t)LPRE_N * lm; plba_prefetch_l1(c); plba_prefetch_l1(c + 16); }
+    }
+    plba_prefetch_l1(OA::om(P) + o);
+    if (PROF == PLBA_PROFILE_G && ctl.stage == 1) plba_prefetch_l1(OA::lvl(P) + o);
+}
+
 // Schur task of a lane: pose pair (i <= j) of the free track positions, half = block rows hrow .. hrow + 2
 struct WTask { int on, pa, pb, sa, sb, hrow, diag, slice; };
 PLBA_HD void wtask_decode(int task, int nf, const int *fpos, const int *slot, int slot0, WTask &t) {
@@ -450,7 +463,11 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
 #pragma unroll 1
             for (int r = 0; r < rounds; r++) {
                 WPHASE_BEGIN
-                    LANE_BIND(tk); LANE_BIND(blk); LANE_BIND(gv); LANE_BIND(hd);
+                    LANE_BIND(tk); LANE_BIND(blk); LANE_BIND(gv); LANE_BIND(hd); LANE_BIND(m_l);
+                    if (r == 0 && pass + 1 < npass && lane < lpp * k) {        // the next pass's inputs travel while this pass's Schur tasks run
+                        const int lmn = lmb + lpp + m_l;
+                        if (lmn < it.n_lm) prefetch_obs_w<PROF, LT>(P, ctl, it.ob0 + (lmb + lpp) * k + lane, it.lm0 + lmn, state);
+                    }
                     if (!keep) {
                         const int task = r * 32 + lane;
                         tk.on = (task < ntask) ? 1 : 0; tk.slice = 0;
@@ -592,6 +609,10 @@ PLBA_D void update_items_w(const DevP &Pin, const WItem *items, int n_items, uns
             WPHASE_END
             WPHASE_BEGIN
                 LANE_BIND(chi_l); LANE_BIND(sc_l); LANE_BIND(d2_l); LANE_BIND(kf_l); LANE_BIND(m_l); LANE_BIND(act_l);
+                if (k && pass + 1 < npass && lane < lpp * k) {                 // the next pass's inputs travel while this pass's landmarks are solved
+                    const int lmn = lmb + lpp + m_l;
+                    if (lmn < it.n_lm) prefetch_obs_w<PROF, LT>(P, ctl, it.ob0 + (lmb + lpp) * k + lane, it.lm0 + lmn, state);
+                }
                 if (lane < nvalid) {
                     const int t0 = m_l * k;
                     const int lm = it.lm0 + lmb + m_l;
