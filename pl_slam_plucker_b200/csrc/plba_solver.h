@@ -743,7 +743,7 @@ struct BcrW { double *D, *U, *b, *hd, *Xl, *Xr, *y; int N, bs, m, pad; };   // n
                                                                            // [D | U | b | hd] is one contiguous range: the exchange step of the sharded path
 enum { BCR_BS_MAX = 15, BCR_M_MAX = 6 * BCR_BS_MAX, BCR_NT = 512 };
 static inline size_t bcr_elim_smem() { return sizeof(double) * ((size_t)(3 * BCR_M_MAX + 1) * (BCR_M_MAX + 1) + BCR_M_MAX + 21 * BCR_BS_MAX + 6 * 264 + 8) + 64; }
-static inline size_t bcr_back_smem() { return sizeof(double) * ((size_t)BCR_M_MAX * (BCR_M_MAX + 1) + 3 * BCR_M_MAX + 8) + 64; }
+static inline size_t bcr_back_smem() { return sizeof(double) * ((size_t)BCR_M_MAX * (BCR_M_MAX + 1) + 7 * BCR_M_MAX + 8) + 64; }
 PLBA_HD int bcr_node_size(const BcrW &B, int nf, int i) { const int k0 = i * B.bs, k1 = (k0 + B.bs < nf) ? k0 + B.bs : nf; return 6 * (k1 - k0); }
 
 // dense S (upper storage) -> node form (undamped: the damping goes on when a node is loaded for elimination, i.e. after the
@@ -884,24 +884,47 @@ PLBA_KERNEL void k_bcr_back(const DevP *Pp, int w, BcrW B, int s, int final) {
     const int i = final ? 0 : (2 * PLBA_BID + 1) * s;
     const int left = final ? -1 : i - s, right = (final || i + s >= B.N) ? -1 : i + s;
     const int mi = bcr_node_size(B, nf, i), ml = left >= 0 ? m : 0, mr = right >= 0 ? bcr_node_size(B, nf, right) : 0;
-    double *L = (double *)raw, *rhs = L + (size_t)BCR_M_MAX * (BCR_M_MAX + 1), *xs = rhs + BCR_M_MAX, *dinv = xs + BCR_M_MAX;
+    double *L = (double *)raw, *rhs = L + (size_t)BCR_M_MAX * (BCR_M_MAX + 1), *xs = rhs + BCR_M_MAX, *dinv = xs + BCR_M_MAX, *xn = dinv + BCR_M_MAX, *part = xn + 2 * BCR_M_MAX;
     const double *Di = B.D + (size_t)i * m * m, *Xl = B.Xl + (size_t)i * m * m, *Xr = B.Xr + (size_t)i * m * m;
     double *x = P.xp + (size_t)6 * slot0;
     PHASE_BEGIN
         for (int idx = tid; idx < mi * mi; idx += PLBA_NT) { const int r = idx / mi, c = idx - r * mi; if (c <= r) { const double v = Di[(size_t)r * m + c]; L[(size_t)r * ldm + c] = v; if (c == r) dinv[r] = 1.0 / v; } }
-        for (int c = tid; c < mi; c += PLBA_NT) {
-            double v = B.y[(size_t)i * m + c];
-            const double *xl = x + (size_t)6 * left * B.bs, *xr = x + (size_t)6 * right * B.bs;
-            for (int r = 0; r < ml; r++) v -= Xl[(size_t)r * m + c] * xl[r];
-            for (int r = 0; r < mr; r++) v -= Xr[(size_t)r * m + c] * xr[r];
-            rhs[c] = v;
+        // the neighbours' solutions, staged once
+        for (int r = tid; r < ml; r += PLBA_NT) xn[r] = x[(size_t)6 * left * B.bs + r];
+        for (int r = tid; r < mr; r += PLBA_NT) xn[BCR_M_MAX + r] = x[(size_t)6 * right * B.bs + r];
+    PHASE_END
+    PHASE_BEGIN
+        // rhs = y - Xl^T x_left - Xr^T x_right: thread = (column c, quarter of the rows); the rows of Xl / Xr are read coalesced over c
+        const int c = tid % 128, qt = tid / 128;                       // 256 threads: two row halves per neighbour block, interleaved
+        if (c < mi) {
+            double acc = 0.0;
+            for (int r = qt; r < ml; r += 2) acc += Xl[(size_t)r * m + c] * xn[r];
+            for (int r = qt; r < mr; r += 2) acc += Xr[(size_t)r * m + c] * xn[BCR_M_MAX + r];
+            part[qt * BCR_M_MAX + c] = acc;
         }
     PHASE_END
-    // column-oriented backward substitution by ONE warp (the chain of mi steps is latency: warp barriers, not block barriers):
+    PHASE_BEGIN
+        for (int c = tid; c < mi; c += PLBA_NT) rhs[c] = B.y[(size_t)i * m + c] - part[c] - part[BCR_M_MAX + c];
+    PHASE_END
+    // column-oriented backward substitution by ONE warp (the chain of mi steps is latency: no block barrier inside):
     // x_j = rhs_j / L_jj, then rhs_r -= L[j][r] x_j for r < j (row j of L: contiguous)
 #ifndef PLBA_HOST_EMU
-    if (threadIdx.x < 32)
-#endif
+    if (threadIdx.x < 32) {
+        // rhs lives in registers (lane l owns entries l, l + 32, l + 64), x_j travels by shuffle: ~60 cycles per step
+        const int lane = (int)threadIdx.x;
+        double r0 = lane < mi ? rhs[lane] : 0.0, r1 = lane + 32 < mi ? rhs[lane + 32] : 0.0, r2 = lane + 64 < mi ? rhs[lane + 64] : 0.0;
+        const double d0 = lane < mi ? dinv[lane] : 0.0, d1 = lane + 32 < mi ? dinv[lane + 32] : 0.0, d2 = lane + 64 < mi ? dinv[lane + 64] : 0.0;
+        for (int j = mi - 1; j >= 0; j--) {
+            const double *Lj = L + (size_t)j * ldm;
+            const double l0 = lane < j ? Lj[lane] : 0.0, l1 = lane + 32 < j ? Lj[lane + 32] : 0.0, l2 = lane + 64 < j ? Lj[lane + 64] : 0.0;   // independent of the chain
+            const int q = j >> 5;
+            const double mine = (q == 0 ? r0 * d0 : q == 1 ? r1 * d1 : r2 * d2);
+            const double xj = __shfl_sync(0xffffffffu, mine, j & 31);
+            if (lane == (j & 31)) xs[j] = xj;
+            r0 -= l0 * xj; r1 -= l1 * xj; r2 -= l2 * xj;
+        }
+    }
+#else
     for (int j = mi - 1; j >= 0; j--) {
         WPHASE_BEGIN
             if (lane == 0) xs[j] = rhs[j] * dinv[j];
@@ -911,6 +934,7 @@ PLBA_KERNEL void k_bcr_back(const DevP *Pp, int w, BcrW B, int s, int final) {
             for (int r = lane; r < j; r += 32) rhs[r] -= L[(size_t)j * ldm + r] * xj;
         WPHASE_END
     }
+#endif
     PHASE_BEGIN
     PHASE_END
     PHASE_BEGIN
