@@ -748,18 +748,23 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
             const std::vector<Seg> &sgs = cls ? sg_ls : sg_pt; const std::vector<int> &fps = cls ? fp_ls : fp_pt;
             const std::vector<int> &ptr = cls ? ls_ptr : pt_ptr; const std::vector<int> &operm = cls ? h->lo_perm : h->po_perm;
             int w = 0;
+            std::vector<int> sl, sl_prev;
             for (const Seg &sg : sgs) {
                 n_off += (int64_t)sg.nfree * (sg.nfree - 1) / 2; n_diag += sg.nfree;
-                while (w + 1 < n && (cls ? h->wins[w + 1].ls0 : h->wins[w + 1].pt0) <= sg.lm0) w++;     // segments are emitted window by window
+                while (w + 1 < n && (cls ? h->wins[w + 1].ls0 : h->wins[w + 1].pt0) <= sg.lm0) { w++; sl_prev.clear(); }     // segments are emitted window by window
                 const plba_problem &p = probs[w]; const WinInfo &wi = h->wins[w];
                 const int32_t *kf = cls ? p.lo_kf : p.po_kf; const int ob0 = cls ? wi.lo0 : wi.po0, o0 = ptr[sg.lm0];
+                sl.resize(sg.nfree);
+                for (int i = 0; i < sg.nfree; i++) sl[i] = p.kf_slot[kf[operm[o0 + fps[sg.fp0 + i]] - ob0]];
+                if (sl == sl_prev) continue;                       // same free-keyframe set as the previous segment (a run cut into segments): nothing new to mark
                 for (int i = 0; i < sg.nfree; i++) for (int j = i; j < sg.nfree; j++) {
-                    int a = p.kf_slot[kf[operm[o0 + fps[sg.fp0 + i]] - ob0]], b = p.kf_slot[kf[operm[o0 + fps[sg.fp0 + j]] - ob0]];
+                    int a = sl[i], b = sl[j];
                     if (a > b) std::swap(a, b);
                     if (b - a > band) band = b - a;
                     unsigned char &m = mark[wbase[w] + (size_t)a * wi.n_free + b];
                     if (!m) { m = 1; nnzb++; }
                 }
+                sl_prev = sl;
             }
         }
         h->layout[0] = (int64_t)ch_pt.size(); h->layout[1] = (int64_t)ch_ls.size(); h->layout[2] = (int64_t)sg_pt.size(); h->layout[3] = (int64_t)sg_ls.size();
@@ -883,18 +888,25 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
             }
         }
 #pragma omp parallel for schedule(static) if (par_lm && p.n_pt > 200000)
-        for (int g = wi.pt0; g < wi.pt0 + p.n_pt; g++) for (int o = pt_ptr[g]; o < pt_ptr[g + 1]; o++) {
-            const int i = h->po_perm[o] - wi.po0;
-            po_kf[o] = wi.kf0 + p.po_kf[i]; po_lm[o] = g;
-            po_uv[(size_t)2 * o] = p.po_uv[(size_t)2 * i]; po_uv[(size_t)2 * o + 1] = p.po_uv[(size_t)2 * i + 1];
-            po_om[o] = p.po_sig2 ? (double)(float)(1.0 / p.po_sig2[i]) : 1.0;                        // const float& invSigma2 (:6009, Q13)
+        for (int g = wi.pt0; g < wi.pt0 + p.n_pt; g++) {
+            // the observations of a landmark are one contiguous run in the caller's arrays too: copy runs, not elements
+            const int o0 = pt_ptr[g], no = pt_ptr[g + 1] - o0;
+            if (no == 0) continue;
+            const int i0 = h->po_perm[o0] - wi.po0;
+            std::memcpy(po_uv + (size_t)2 * o0, p.po_uv + (size_t)2 * i0, sizeof(double) * 2 * no);
+            for (int j = 0; j < no; j++) { po_kf[o0 + j] = wi.kf0 + p.po_kf[i0 + j]; po_lm[o0 + j] = g; }
+            if (p.po_sig2) for (int j = 0; j < no; j++) po_om[o0 + j] = (double)(float)(1.0 / p.po_sig2[i0 + j]);           // const float& invSigma2 (:6009, Q13)
+            else for (int j = 0; j < no; j++) po_om[o0 + j] = 1.0;
         }
 #pragma omp parallel for schedule(static) if (par_lm && p.n_ls > 200000)
-        for (int g = wi.ls0; g < wi.ls0 + p.n_ls; g++) for (int o = ls_ptr[g]; o < ls_ptr[g + 1]; o++) {
-            const int i = h->lo_perm[o] - wi.lo0;
-            lo_kf[o] = wi.kf0 + p.lo_kf[i]; lo_lm[o] = g;
-            for (int k = 0; k < 4; k++) lo_ab[(size_t)4 * o + k] = p.lo_ab[(size_t)4 * i + k];
-            lo_om[o] = p.lo_sig2 ? (double)(float)(1.0 / p.lo_sig2[i]) : 1.0;
+        for (int g = wi.ls0; g < wi.ls0 + p.n_ls; g++) {
+            const int o0 = ls_ptr[g], no = ls_ptr[g + 1] - o0;
+            if (no == 0) continue;
+            const int i0 = h->lo_perm[o0] - wi.lo0;
+            std::memcpy(lo_ab + (size_t)4 * o0, p.lo_ab + (size_t)4 * i0, sizeof(double) * 4 * no);
+            for (int j = 0; j < no; j++) { lo_kf[o0 + j] = wi.kf0 + p.lo_kf[i0 + j]; lo_lm[o0 + j] = g; }
+            if (p.lo_sig2) for (int j = 0; j < no; j++) lo_om[o0 + j] = (double)(float)(1.0 / p.lo_sig2[i0 + j]);
+            else for (int j = 0; j < no; j++) lo_om[o0 + j] = 1.0;
         }
         WinCtrl c{};
         c.need_init = 1; c.apply = 1; c.ni = 2.0; c.err_prev = 999999999.9; c.n_lm_pt = p.n_pt; c.n_lm_ls = p.n_ls; c.n_obs = p.n_pobs + p.n_lobs;
