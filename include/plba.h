@@ -258,6 +258,45 @@ int  plba_scene_problem(plba_scene s, plba_problem *out);
 int  plba_scene_truth(plba_scene s, const double **kf_T_wc, const double **pt_xyz, const double **ls_plk);
 void plba_scene_destroy(plba_scene s);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Frame-to-frame pose tracking in Plücker mode (the step BEFORE the LBA path, it produces the keyframe
+ * poses): StereoFrameHandler::gaussNewtonOptimizationforPluker + optimizeFunctionsUsingPluker
+ * (src2/stereoFrameHandler.cpp:563-853).  Pose-only Gauss-Newton on point re-projection errors and endpoint-to-projected-
+ * Plücker-line distances, Cauchy weights scaled by the MAD of the residuals (src2/auxiliar.cpp:444-460), line weights
+ * multiplied by the segment overlap (src2/stereoFrame.cpp:547-660).  Frames are independent: a batch runs one CTA per frame.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct plba_track_frame {
+    int32_t n_pt, n_ls;
+    double  DT[12];                 /* initial guess, rows of [R|t] of the 4x4 DT (previous frame -> current frame)                 */
+    const double  *pt_P;            /* [n_pt][3] PointFeature::P       3-D point in the previous frame                               */
+    const double  *pt_obs;          /* [n_pt][2] PointFeature::pl_obs  pixel in the current frame                                    */
+    const uint8_t *pt_inlier;       /* [n_pt]    PointFeature::inlier  (NULL = all inliers)                                          */
+    const double  *ls_sP, *ls_eP;   /* [n_ls][3] LineFeature::sP / eP  3-D endpoints in the previous frame (overlap weight only)     */
+    const double  *ls_NDc;          /* [n_ls][6] LineFeature::NDc      Plücker line [n; d] in the previous frame                     */
+    const double  *ls_obs;          /* [n_ls][4] spl_obs.xy, epl_obs.xy  endpoint pixels in the current frame                        */
+    const double  *ls_seg;          /* [n_ls][4] spl.xy, epl.xy          endpoint pixels in the previous frame (overlap weight)      */
+    const double  *ls_sigma2;       /* [n_ls]    LineFeature::sigma2   (NULL = 1)                                                    */
+    const uint8_t *ls_inlier;       /* [n_ls]    LineFeature::inlier   (NULL = all inliers)                                          */
+} plba_track_frame;
+typedef struct plba_track_options {
+    double  cam[4];                 /* fx, fy, cx, cy                                                                                */
+    double  homog_th;               /* 1e-7  Config::homogTh                                                                         */
+    double  min_error;              /* 1e-7  Config::minError                                                                        */
+    double  min_error_change;       /* 1e-7  Config::minErrorChange                                                                  */
+    int32_t max_iters;              /* 5     Config::maxIters (10 = maxItersRef for the refinement call)                             */
+    int32_t reserved;
+} plba_track_options;
+typedef struct plba_track_result {
+    double  DT[12];                 /* optimised DT; the initial guess if the solve failed (:846-851)                                */
+    double  DT_cov[36];             /* H^-1 of the last linearisation; identity if the solve failed                                  */
+    double  err;                    /* normalised robust cost of the last linearisation; -1 if the solve failed                      */
+    int32_t iters;                  /* linearisations performed                                                                      */
+    int32_t good;                   /* solution_is_good (:809)                                                                       */
+} plba_track_result;
+void plba_track_default_options(plba_track_options *opt);
+/* n_frames independent frames, host buffers in and out.  At most 1024 point and 1024 line matches per frame. */
+int  plba_track_solve(plba_handle h, int32_t n_frames, const plba_track_frame *frames, const plba_track_options *opt, plba_track_result *results);
+
 #ifdef __cplusplus
 }
 #endif

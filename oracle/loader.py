@@ -15,7 +15,7 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "libplba_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("plba_oracle.cpp", "refmath.h", "smallmat.h")] + [os.path.join(_HERE, "..", "include", "plba.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("plba_oracle.cpp", "track_oracle.cpp", "refmath.h", "smallmat.h")] + [os.path.join(_HERE, "..", "include", "plba.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.exists(s)):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
@@ -132,3 +132,14 @@ def h_term(kind, cam, Tiw, lm, obs, th=1e-7, fixed=False):
     Jp = np.zeros(6); Jl = np.zeros(6); rw = np.zeros(2)
     lib().plba_oracle_h_term(C.c_int(kind), _p(cam), _p(T), _p(lm6), _p(ob4), C.c_double(th), C.c_int(1 if fixed else 0), _p(Jp), _p(Jl), _p(rw))
     return Jp, Jl, rw[0], rw[1]
+
+
+def track_solve(frame, opt):
+    """CPU oracle of the Plücker-mode pose tracking (oracle/track_oracle.cpp) on one frame: result dict as tracking.solve."""
+    from pl_slam_plucker_b200 import tracking as trk
+    L = lib()
+    L.plba_track_oracle.argtypes = [C.POINTER(trk.plba_track_frame), C.POINTER(trk.plba_track_options), C.POINTER(trk.plba_track_result)]
+    L.plba_track_oracle.restype = C.c_int
+    fc = frame.as_c(); res = trk.plba_track_result()
+    L.plba_track_oracle(C.byref(fc), C.byref(opt.c), C.byref(res))
+    return trk._unpack([res])[0]

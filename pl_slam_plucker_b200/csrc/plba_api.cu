@@ -20,6 +20,7 @@
 #include <chrono>
 #include "plba_solver.h"
 #include "plba_warp.h"
+#include "plba_track.h"
 
 using namespace plba;
 
@@ -44,6 +45,7 @@ struct plba_handle_s {
     char *h_out = nullptr; size_t h_out_cap = 0;     // pinned: staged outputs
     DevP *d_P = nullptr;                             // fixed address: kernel parameters
     double *d_scratch = nullptr;                     // a few doubles of device memory for upload-time exchanges
+    char *trk_dev = nullptr, *trk_host = nullptr; size_t trk_dev_cap = 0, trk_host_cap = 0;      // pose tracking (plba_track_solve): its own small arena
     DevP *h_P = nullptr;                             // pinned copy
     int *h_cnt = nullptr;                            // pinned counters
     DevP P{};
@@ -82,6 +84,9 @@ struct plba_handle_s {
         if (d_arena) cudaFree(d_arena);
         if (h_in) cudaFreeHost(h_in);
         if (h_out) cudaFreeHost(h_out);
+        if (trk_dev) cudaFree(trk_dev);
+        if (trk_host) cudaFreeHost(trk_host);
+        trk_dev = trk_host = nullptr; trk_dev_cap = trk_host_cap = 0;
         d_arena = nullptr; h_in = nullptr; h_out = nullptr; d_cap = h_in_cap = h_out_cap = 0; uploaded = false;
     }
 };
@@ -1250,6 +1255,82 @@ int plba_debug_prof(unsigned long long *out64, int reset) {
 #endif
 int plba_set_force_dense(plba_handle h, int on) { if (!h) return PLBA_E_ARG; h->force_dense = on != 0; return PLBA_OK; }
 int plba_set_force_chunk(plba_handle h, int mode) { if (!h || mode < 0 || mode > 2) return PLBA_E_ARG; h->force_chunk = mode; return PLBA_OK; }
+// ---- frame-to-frame pose tracking ---------------------------------------------------------------
+void plba_track_default_options(plba_track_options *o) {
+    std::memset(o, 0, sizeof(*o));
+    o->homog_th = 1e-7; o->min_error = 1e-7; o->min_error_change = 1e-7;          // src2/config.cpp:80-85
+    o->max_iters = 5;                                                             // Config::maxIters (src2/config.cpp:82)
+}
+int plba_track_solve(plba_handle h, int32_t n_frames, const plba_track_frame *frames, const plba_track_options *opt, plba_track_result *results) {
+    if (!h || n_frames <= 0 || !frames || !opt || !results) return PLBA_E_ARG;
+    CK(cudaSetDevice(h->device));
+    size_t npt = 0, nls = 0;
+    for (int f = 0; f < n_frames; f++) {
+        const plba_track_frame &F = frames[f];
+        if (F.n_pt < 0 || F.n_ls < 0 || F.n_pt > TRK_MAX || F.n_ls > TRK_MAX) { h->err = "a frame holds more than 1024 point or line matches"; return PLBA_E_UNSUPPORTED; }
+        if ((F.n_pt && (!F.pt_P || !F.pt_obs)) || (F.n_ls && (!F.ls_sP || !F.ls_eP || !F.ls_NDc || !F.ls_obs || !F.ls_seg))) { h->err = "frame arrays missing"; return PLBA_E_ARG; }
+        npt += F.n_pt; nls += F.n_ls;
+    }
+    Carver c;
+    const size_t o_fr = c.take<TrackFrameDev>(n_frames), o_pP = c.take<double>(3 * npt), o_pO = c.take<double>(2 * npt), o_pI = c.take<unsigned char>(npt);
+    const size_t o_lS = c.take<double>(3 * nls), o_lE = c.take<double>(3 * nls), o_lN = c.take<double>(6 * nls), o_lO = c.take<double>(4 * nls), o_lG = c.take<double>(4 * nls);
+    const size_t o_l2 = c.take<double>(nls), o_lI = c.take<unsigned char>(nls);
+    const size_t in_bytes = c.off, o_res = c.take<plba_track_result>(n_frames), total = c.off;
+    if (total > h->trk_dev_cap) {
+        cudaStreamSynchronize(h->stream);
+        if (h->trk_dev) cudaFree(h->trk_dev);
+        if (h->trk_host) cudaFreeHost(h->trk_host);
+        h->trk_dev = h->trk_host = nullptr; h->trk_dev_cap = h->trk_host_cap = 0;
+        const size_t want = total + total / 4 + (1 << 16);
+        void *q = nullptr;
+        if (cudaMalloc(&q, want) != cudaSuccess) { h->err = "cudaMalloc (tracking arena) failed"; return PLBA_E_CUDA; }
+        h->trk_dev = (char *)q;
+        if (cudaMallocHost(&q, want) != cudaSuccess) { h->err = "cudaMallocHost (tracking staging) failed"; return PLBA_E_CUDA; }
+        h->trk_host = (char *)q; h->trk_dev_cap = h->trk_host_cap = want;
+    }
+    char *hb = h->trk_host, *db = h->trk_dev;
+    TrackFrameDev *fr = (TrackFrameDev *)(hb + o_fr);
+    size_t p0 = 0, l0 = 0;
+    for (int f = 0; f < n_frames; f++) {
+        const plba_track_frame &F = frames[f];
+        fr[f].n_pt = F.n_pt; fr[f].n_ls = F.n_ls; fr[f].pt0 = (int)p0; fr[f].ls0 = (int)l0;
+        for (int i = 0; i < 12; i++) fr[f].DT[i] = F.DT[i];
+        if (F.n_pt) {
+            std::memcpy(hb + o_pP + sizeof(double) * 3 * p0, F.pt_P, sizeof(double) * 3 * F.n_pt);
+            std::memcpy(hb + o_pO + sizeof(double) * 2 * p0, F.pt_obs, sizeof(double) * 2 * F.n_pt);
+            for (int i = 0; i < F.n_pt; i++) ((unsigned char *)(hb + o_pI))[p0 + i] = F.pt_inlier ? (F.pt_inlier[i] ? 1 : 0) : 1;
+        }
+        if (F.n_ls) {
+            std::memcpy(hb + o_lS + sizeof(double) * 3 * l0, F.ls_sP, sizeof(double) * 3 * F.n_ls);
+            std::memcpy(hb + o_lE + sizeof(double) * 3 * l0, F.ls_eP, sizeof(double) * 3 * F.n_ls);
+            std::memcpy(hb + o_lN + sizeof(double) * 6 * l0, F.ls_NDc, sizeof(double) * 6 * F.n_ls);
+            std::memcpy(hb + o_lO + sizeof(double) * 4 * l0, F.ls_obs, sizeof(double) * 4 * F.n_ls);
+            std::memcpy(hb + o_lG + sizeof(double) * 4 * l0, F.ls_seg, sizeof(double) * 4 * F.n_ls);
+            for (int i = 0; i < F.n_ls; i++) {
+                ((double *)(hb + o_l2))[l0 + i] = F.ls_sigma2 ? F.ls_sigma2[i] : 1.0;
+                ((unsigned char *)(hb + o_lI))[l0 + i] = F.ls_inlier ? (F.ls_inlier[i] ? 1 : 0) : 1;
+            }
+        }
+        p0 += F.n_pt; l0 += F.n_ls;
+    }
+    CK(cudaMemcpyAsync(db, hb, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    TrackP T{};
+    T.frames = (const TrackFrameDev *)(db + o_fr);
+    T.pt_P = (const double *)(db + o_pP); T.pt_obs = (const double *)(db + o_pO); T.pt_in = (const unsigned char *)(db + o_pI);
+    T.ls_sP = (const double *)(db + o_lS); T.ls_eP = (const double *)(db + o_lE); T.ls_NDc = (const double *)(db + o_lN);
+    T.ls_obs = (const double *)(db + o_lO); T.ls_seg = (const double *)(db + o_lG); T.ls_s2 = (const double *)(db + o_l2); T.ls_in = (const unsigned char *)(db + o_lI);
+    T.res = (plba_track_result *)(db + o_res);
+    for (int i = 0; i < 4; i++) T.cam[i] = opt->cam[i];
+    T.homog_th = opt->homog_th; T.min_error = opt->min_error; T.min_error_change = opt->min_error_change; T.max_iters = opt->max_iters; T.n_frames = n_frames;
+    PLBA_LAUNCH(k_track_gn, dim3(std::min(n_frames, 8 * h->n_sm)), dim3(TRK_NT), track_smem(), h->stream, T);
+    h->timing.n_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hb + o_res, db + o_res, sizeof(plba_track_result) * n_frames, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::memcpy(results, hb + o_res, sizeof(plba_track_result) * n_frames);
+    return PLBA_OK;
+}
+
 int plba_kernel_path(plba_handle h, int32_t *out4) {
     if (!h || !h->uploaded || !out4) return PLBA_E_ARG;
     out4[0] = h->warp_path ? 1 : 0;
