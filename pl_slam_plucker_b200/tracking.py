@@ -68,14 +68,22 @@ def _unpack(res):
     return [{"DT": np.array(r.DT[:]).reshape(3, 4), "DT_cov": np.array(r.DT_cov[:]).reshape(6, 6), "err": float(r.err), "iters": int(r.iters), "good": int(r.good)} for r in res]
 
 
-def solve(solver, frames, opt):
-    """Tracks a batch of independent frames on the GPU of `solver` (an LBASolver): list of result dicts."""
+class Batch:
+    """The C array of plba_track_frame for a list of frames, marshalled once (a caller that tracks many frames per call keeps it)."""
+
+    def __init__(self, frames):
+        self.frames = list(frames)
+        self.n = len(self.frames)
+        self.arr = (plba_track_frame * self.n)(*[f.as_c() for f in self.frames])
+        self.res = (plba_track_result * self.n)()
+
+
+def solve(solver, frames, opt, unpack=True):
+    """Tracks a batch of independent frames (a list of Frame or a Batch) on the GPU of `solver` (an LBASolver): list of result dicts."""
     declare(solver.L)
-    n = len(frames)
-    arr = (plba_track_frame * n)(*[f.as_c() for f in frames])
-    res = (plba_track_result * n)()
-    solver._check(solver.L.plba_track_solve(solver.h, n, arr, C.byref(opt.c), res))
-    return _unpack(res)
+    b = frames if isinstance(frames, Batch) else Batch(frames)
+    solver._check(solver.L.plba_track_solve(solver.h, b.n, b.arr, C.byref(opt.c), b.res))
+    return _unpack(b.res) if unpack else b.res
 
 
 # ---- synthetic frames (tests / benchmarks) ---------------------------------------------------------------------------
