@@ -297,6 +297,25 @@ void plba_track_default_options(plba_track_options *opt);
 /* n_frames independent frames, host buffers in and out.  At most 1024 point and 1024 line matches per frame. */
 int  plba_track_solve(plba_handle h, int32_t n_frames, const plba_track_frame *frames, const plba_track_options *opt, plba_track_result *results);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Creation of Plücker line landmarks (it defines the on-wire meaning of NDw and the sqrt(5.991) gate):
+ * stereo triangulation of a segment as the intersection of the two viewing planes (StereoFrame::pi_from_ppp / pipi_plk,
+ * src2/stereoFrame.cpp:381-397, 870-883), transformation into the world with the |n| / |d| renormalisation and the
+ * re-projection gate against the matched segment of the current keyframe (src/mapHandler.cpp:449-492).  One thread per candidate.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct plba_newline_batch {
+    int32_t n, n_kf;
+    double  cam[5];                 /* fx, fy, cx, cy, stereo baseline                                                              */
+    const double  *seg_l;           /* [n][4] sp_l.xy, ep_l.xy: the segment in the left image of the keyframe that creates the line  */
+    const double  *seg_r;           /* [n][4] sp_r.xy, ep_r.xy: its match in the right image, after the row interpolation (:367-368) */
+    const double  *seg_curr;        /* [n][4] spl.xy, epl.xy of the matched segment in the current keyframe (the gate)               */
+    const int32_t *kf_prev, *kf_curr; /* [n] rows of kf_T_wc: creating keyframe, current keyframe                                    */
+    const double  *kf_T_wc;         /* [n_kf][12] KeyFrame::T_kf_w                                                                   */
+} plba_newline_batch;
+/* NDc [n][6] (camera frame of the creating keyframe), NDw [n][6] (world, MapLine::NDw), err_first / err_curr [n] = norm of the two
+ * endpoint-to-line distances in the creating / the current keyframe, accept [n] = !(err_curr > sqrt(5.991)) (:487).  Any output may be NULL. */
+int  plba_create_lines(plba_handle h, const plba_newline_batch *batch, double *NDc, double *NDw, double *err_first, double *err_curr, uint8_t *accept);
+
 #ifdef __cplusplus
 }
 #endif

@@ -143,3 +143,14 @@ def track_solve(frame, opt):
     fc = frame.as_c(); res = trk.plba_track_result()
     L.plba_track_oracle(C.byref(fc), C.byref(opt.c), C.byref(res))
     return trk._unpack([res])[0]
+
+
+def create_lines(cam5, seg_l, seg_r, seg_curr, kf_prev, kf_curr, kf_T_wc):
+    """CPU oracle of the Plücker line-landmark creation (oracle/track_oracle.cpp): dict as tracking.create_lines."""
+    from pl_slam_plucker_b200 import tracking as trk
+    L = lib()
+    pd, pb = C.POINTER(C.c_double), C.POINTER(C.c_uint8)
+    L.plba_create_lines_oracle.argtypes = [C.POINTER(trk.plba_newline_batch), pd, pd, pd, pd, pb]
+    L.plba_create_lines_oracle.restype = C.c_int
+    rc, out = trk._newline_call(L.plba_create_lines_oracle, (), cam5, seg_l, seg_r, seg_curr, kf_prev, kf_curr, kf_T_wc)
+    return out

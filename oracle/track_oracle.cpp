@@ -248,3 +248,56 @@ int plba_track_oracle(const plba_track_frame *frame, const plba_track_options *o
 }
 
 }  // extern "C"
+
+// ---- creation of Plücker line landmarks ------------------------------------------------------------
+namespace {
+// src2/stereoFrame.cpp:870-875
+V4 pi_from_ppp(V3 x1, V3 x2, V3 x3) {
+    V4 pi; V3 n = cross(x1 - x3, x2 - x3);
+    pi[0] = n[0]; pi[1] = n[1]; pi[2] = n[2]; pi[3] = -dot(x3, cross(x1, x2));
+    return pi;
+}
+// src2/stereoFrame.cpp:877-883
+V6 pipi_plk(V4 pi1, V4 pi2) {
+    V6 plk;
+    M4 dp = pi1 * pi2.T() - pi2 * pi1.T();
+    plk[0] = dp(0, 3); plk[1] = dp(1, 3); plk[2] = dp(2, 3); plk[3] = -dp(1, 2); plk[4] = dp(0, 2); plk[5] = -dp(0, 1);
+    return plk;
+}
+}  // namespace
+
+extern "C" int plba_create_lines_oracle(const plba_newline_batch *B, double *NDc, double *NDw, double *err_first, double *err_curr, uint8_t *accept) {
+    const double *cam = B->cam; const double b = B->cam[4];
+    const M3 KL = plukerK(cam);
+    for (int i = 0; i < B->n; i++) {
+        const double *sl = B->seg_l + 4 * i, *sr = B->seg_r + 4 * i;
+        // backProjection_unit (src2/pinholeStereoCamera.cpp:215-223); src2/stereoFrame.cpp:383-397
+        auto unit = [&](double u, double v) { V3 P; P[0] = (u - cam[2]) / cam[0]; P[1] = (v - cam[3]) / cam[1]; P[2] = 1.0; return P; };
+        V3 obs1s = unit(sl[0], sl[1]), obs1e = unit(sl[2], sl[3]), obs2s = unit(sr[0], sr[1]), obs2e = unit(sr[2], sr[3]);
+        obs2s[0] += b; obs2e[0] += b;
+        V3 o1, o2; o2[0] = b;
+        V6 line_pluker = pipi_plk(pi_from_ppp(obs1s, obs1e, o1), pi_from_ppp(obs2s, obs2e, o2));
+        // src/mapHandler.cpp:449-459
+        auto Tof = [&](int row) { M4 T = M4::Identity(); for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) T(r, c) = B->kf_T_wc[12 * row + 4 * r + c]; return T; };
+        M4 Tfw = Tof(B->kf_prev[i]);
+        V6 plukerLW = getTransformMatrixForPluker(Tfw) * line_pluker;
+        V3 nh = plukerLW.block<3, 1>(0, 0), dh = plukerLW.block<3, 1>(3, 0);
+        double d = nh.norm() / dh.norm();
+        dh = dh / dh.norm(); nh = nh / nh.norm();
+        V6 new_pluker_lw; for (int k = 0; k < 3; k++) { new_pluker_lw[k] = nh[k] * d; new_pluker_lw[3 + k] = dh[k]; }
+        auto reproj = [&](const M4 &Tkw, const double *pts) {      // :463-471 / :477-486
+            V6 plukerLc = getTransformMatrixForPluker(inverse(Tkw)) * new_pluker_lw;
+            V3 px = KL * plukerLc.block<3, 1>(0, 0);
+            double fenmu = std::sqrt(px[0] * px[0] + px[1] * px[1]);
+            V2 error; error[0] = (pts[0] * px[0] + pts[1] * px[1] + px[2]) / fenmu; error[1] = (pts[2] * px[0] + pts[3] * px[1] + px[2]) / fenmu;
+            return error.norm();
+        };
+        double e1 = reproj(Tfw, sl), e2 = reproj(Tof(B->kf_curr[i]), B->seg_curr + 4 * i);
+        if (NDc) for (int k = 0; k < 6; k++) NDc[6 * i + k] = line_pluker[k];
+        if (NDw) for (int k = 0; k < 6; k++) NDw[6 * i + k] = new_pluker_lw[k];
+        if (err_first) err_first[i] = e1;
+        if (err_curr) err_curr[i] = e2;
+        if (accept) accept[i] = (e2 > std::sqrt(5.991)) ? 0 : 1;   // :487
+    }
+    return 0;
+}

@@ -12,7 +12,7 @@ ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
 
 EXPORTS = ["plba_version", "plba_default_options", "plba_create", "plba_destroy", "plba_last_error", "plba_solve", "plba_solve_batch",
            "plba_upload", "plba_reset_state", "plba_run", "plba_download", "plba_trial_assemble", "plba_trial_finish",
-           "plba_reduced_system", "plba_copy_reduced_system", "plba_time_kernel", "plba_layout_stats", "plba_kernel_path", "plba_track_default_options", "plba_track_solve", "plba_set_force_dense", "plba_set_force_chunk", "plba_set_allreduce", "plba_get_timing", "plba_set_detail_timing", "plba_scene_preset", "plba_scene_create",
+           "plba_reduced_system", "plba_copy_reduced_system", "plba_time_kernel", "plba_layout_stats", "plba_kernel_path", "plba_track_default_options", "plba_track_solve", "plba_create_lines", "plba_set_force_dense", "plba_set_force_chunk", "plba_set_allreduce", "plba_get_timing", "plba_set_detail_timing", "plba_scene_preset", "plba_scene_create",
            "plba_scene_problem", "plba_scene_truth", "plba_scene_destroy"]
 
 

@@ -1331,6 +1331,51 @@ int plba_track_solve(plba_handle h, int32_t n_frames, const plba_track_frame *fr
     return PLBA_OK;
 }
 
+int plba_create_lines(plba_handle h, const plba_newline_batch *B, double *NDc, double *NDw, double *err_first, double *err_curr, uint8_t *accept) {
+    if (!h || !B || B->n < 0 || B->n_kf <= 0) return PLBA_E_ARG;
+    if (B->n == 0) return PLBA_OK;
+    if (!B->seg_l || !B->seg_r || !B->seg_curr || !B->kf_prev || !B->kf_curr || !B->kf_T_wc) { h->err = "batch arrays missing"; return PLBA_E_ARG; }
+    for (int i = 0; i < B->n; i++) if (B->kf_prev[i] < 0 || B->kf_prev[i] >= B->n_kf || B->kf_curr[i] < 0 || B->kf_curr[i] >= B->n_kf) { h->err = "keyframe row out of range"; return PLBA_E_ARG; }
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)B->n;
+    Carver c;
+    const size_t o_sl = c.take<double>(4 * n), o_sr = c.take<double>(4 * n), o_sc = c.take<double>(4 * n), o_kp = c.take<int>(n), o_kc = c.take<int>(n), o_T = c.take<double>((size_t)12 * B->n_kf);
+    const size_t in_bytes = c.off;
+    const size_t o_c = c.take<double>(6 * n), o_w = c.take<double>(6 * n), o_e1 = c.take<double>(n), o_e2 = c.take<double>(n), o_ac = c.take<unsigned char>(n), total = c.off;
+    if (total > h->trk_dev_cap) {
+        cudaStreamSynchronize(h->stream);
+        if (h->trk_dev) cudaFree(h->trk_dev);
+        if (h->trk_host) cudaFreeHost(h->trk_host);
+        h->trk_dev = h->trk_host = nullptr; h->trk_dev_cap = h->trk_host_cap = 0;
+        const size_t want = total + total / 4 + (1 << 16);
+        void *q = nullptr;
+        if (cudaMalloc(&q, want) != cudaSuccess) { h->err = "cudaMalloc (tracking arena) failed"; return PLBA_E_CUDA; }
+        h->trk_dev = (char *)q;
+        if (cudaMallocHost(&q, want) != cudaSuccess) { h->err = "cudaMallocHost (tracking staging) failed"; return PLBA_E_CUDA; }
+        h->trk_host = (char *)q; h->trk_dev_cap = h->trk_host_cap = want;
+    }
+    char *hb = h->trk_host, *db = h->trk_dev;
+    std::memcpy(hb + o_sl, B->seg_l, sizeof(double) * 4 * n); std::memcpy(hb + o_sr, B->seg_r, sizeof(double) * 4 * n); std::memcpy(hb + o_sc, B->seg_curr, sizeof(double) * 4 * n);
+    std::memcpy(hb + o_kp, B->kf_prev, sizeof(int) * n); std::memcpy(hb + o_kc, B->kf_curr, sizeof(int) * n); std::memcpy(hb + o_T, B->kf_T_wc, sizeof(double) * 12 * B->n_kf);
+    CK(cudaMemcpyAsync(db, hb, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    NewLineP Q{};
+    Q.n = B->n; for (int i = 0; i < 5; i++) Q.cam[i] = B->cam[i];
+    Q.seg_l = (const double *)(db + o_sl); Q.seg_r = (const double *)(db + o_sr); Q.seg_curr = (const double *)(db + o_sc);
+    Q.kf_prev = (const int *)(db + o_kp); Q.kf_curr = (const int *)(db + o_kc); Q.kf_T = (const double *)(db + o_T);
+    Q.NDc = (double *)(db + o_c); Q.NDw = (double *)(db + o_w); Q.err_first = (double *)(db + o_e1); Q.err_curr = (double *)(db + o_e2); Q.accept = (unsigned char *)(db + o_ac);
+    PLBA_LAUNCH(k_create_lines, grid1(B->n, 256), dim3(256), 0, h->stream, Q);
+    h->timing.n_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hb + o_c, db + o_c, total - o_c, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (NDc) std::memcpy(NDc, hb + o_c, sizeof(double) * 6 * n);
+    if (NDw) std::memcpy(NDw, hb + o_w, sizeof(double) * 6 * n);
+    if (err_first) std::memcpy(err_first, hb + o_e1, sizeof(double) * n);
+    if (err_curr) std::memcpy(err_curr, hb + o_e2, sizeof(double) * n);
+    if (accept) std::memcpy(accept, hb + o_ac, n);
+    return PLBA_OK;
+}
+
 int plba_kernel_path(plba_handle h, int32_t *out4) {
     if (!h || !h->uploaded || !out4) return PLBA_E_ARG;
     out4[0] = h->warp_path ? 1 : 0;

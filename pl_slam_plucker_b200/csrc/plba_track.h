@@ -248,6 +248,63 @@ PLBA_KERNEL void k_track_gn(TrackP T) {
         PHASE_END
     }
 }
+// ---- creation of Plücker line landmarks -----------------------------------------------------------
+struct NewLineP {
+    int n; double cam[5];
+    const double *seg_l, *seg_r, *seg_curr, *kf_T; const int *kf_prev, *kf_curr;
+    double *NDc, *NDw, *err_first, *err_curr; unsigned char *accept;
+};
+// StereoFrame::pi_from_ppp (src2/stereoFrame.cpp:870-875): plane through three points
+PLBA_HD void nl_pi_from_ppp(const double *x1, const double *x2, const double *x3, double *pi) {
+    const double a[3] = {x1[0] - x3[0], x1[1] - x3[1], x1[2] - x3[2]}, b[3] = {x2[0] - x3[0], x2[1] - x3[1], x2[2] - x3[2]};
+    double c12[3]; cross3(a, b, pi); cross3(x1, x2, c12);
+    pi[3] = -dot3(x3, c12);
+}
+// distance of two pixels to the image line of a world Plücker line seen from the keyframe with pose T_kf_w (:463-471, :477-486)
+PLBA_HD double nl_reproj(const double *cam, const double *Twc, const double *NDw, const double *seg) {
+    double Tcw[12], l[3], Rn[3], Rd[3];
+    inv_se3(Twc, Tcw);
+    g_line_project(*(const Cam *)cam, Tcw, NDw, NDw + 3, l, Rn, Rd);
+    const double f = sqrt(l[0] * l[0] + l[1] * l[1]);
+    const double e0 = (seg[0] * l[0] + seg[1] * l[1] + l[2]) / f, e1 = (seg[2] * l[0] + seg[3] * l[1] + l[2]) / f;
+    return sqrt(e0 * e0 + e1 * e1);
+}
+PLBA_HD void nl_create(const NewLineP &Q, int i) {
+    const double fx = Q.cam[0], fy = Q.cam[1], cx = Q.cam[2], cy = Q.cam[3], b = Q.cam[4];
+    const double *sl = Q.seg_l + 4 * i, *sr = Q.seg_r + 4 * i;
+    // back-projection to the normalised plane (backProjection_unit, src2/pinholeStereoCamera.cpp:215-223); right camera at (b, 0, 0)
+    const double o1s[3] = {(sl[0] - cx) / fx, (sl[1] - cy) / fy, 1.0}, o1e[3] = {(sl[2] - cx) / fx, (sl[3] - cy) / fy, 1.0};
+    const double o2s[3] = {(sr[0] - cx) / fx + b, (sr[1] - cy) / fy, 1.0}, o2e[3] = {(sr[2] - cx) / fx + b, (sr[3] - cy) / fy, 1.0};
+    const double c1[3] = {0, 0, 0}, c2[3] = {b, 0, 0};
+    double p1[4], p2[4];
+    nl_pi_from_ppp(o1s, o1e, c1, p1); nl_pi_from_ppp(o2s, o2e, c2, p2);
+    // pipi_plk (:877-883): dp = pi1 pi2^T - pi2 pi1^T ; plk = (dp03, dp13, dp23, -dp12, dp02, -dp01)
+#define NL_DP(r, c) (p1[r] * p2[c] - p2[r] * p1[c])
+    const double nd[6] = {NL_DP(0, 3), NL_DP(1, 3), NL_DP(2, 3), -NL_DP(1, 2), NL_DP(0, 2), -NL_DP(0, 1)};
+#undef NL_DP
+    if (Q.NDc) for (int k = 0; k < 6; k++) Q.NDc[6 * i + k] = nd[k];
+    // into the world: TransformForPluker(T_kf_w, NDc), then |d| = 1 and |n| = |n| / |d| (src/mapHandler.cpp:449-459)
+    const double *Twp = Q.kf_T + 12 * Q.kf_prev[i];
+    double Rn[3], Rd[3], tx[3];
+    rot(Twp, nd, Rn); rot(Twp, nd + 3, Rd);
+    const double t[3] = {Twp[3], Twp[7], Twp[11]};
+    cross3(t, Rd, tx);
+    double nw[3] = {Rn[0] + tx[0], Rn[1] + tx[1], Rn[2] + tx[2]};
+    const double nn = sqrt(dot3(nw, nw)), dn = sqrt(dot3(Rd, Rd)), d = nn / dn;
+    double W[6];
+    for (int k = 0; k < 3; k++) { W[k] = nw[k] / nn * d; W[3 + k] = Rd[k] / dn; }
+    if (Q.NDw) for (int k = 0; k < 6; k++) Q.NDw[6 * i + k] = W[k];
+    const double e1 = nl_reproj(Q.cam, Twp, W, sl);
+    const double e2 = nl_reproj(Q.cam, Q.kf_T + 12 * Q.kf_curr[i], W, Q.seg_curr + 4 * i);
+    if (Q.err_first) Q.err_first[i] = e1;
+    if (Q.err_curr) Q.err_curr[i] = e2;
+    if (Q.accept) Q.accept[i] = (e2 > sqrt(5.991)) ? 0 : 1;                       // :487
+}
+PLBA_KERNEL void k_create_lines(NewLineP Q) {
+    PHASE_BEGIN
+        for (int i = PLBA_BID * PLBA_NT + tid; i < Q.n; i += PLBA_NB * PLBA_NT) nl_create(Q, i);
+    PHASE_END
+}
 static inline size_t track_smem() { return sizeof(double) * (2 * TRK_MAX + 64 + 64 + 24) + 64; }
 
 }  // namespace plba

@@ -135,3 +135,73 @@ def make_frame(seed, n_pt=200, n_ls=80, cam=(435.2, 435.2, 367.2, 252.2), size=(
     so[badl] += rng.uniform(-30, 30, (int(badl.sum()), 2))
     DT0 = np.eye(4) if guess_noise == 0.0 else _exp_se3(rng.normal(size=6) * guess_noise)
     return Frame(DT0[:3, :], P, obs, sP, eP, NDc, np.concatenate([so, eo], 1), np.concatenate([spl, epl], 1)), DT
+
+
+# ---- creation of Plücker line landmarks (plba_create_lines) ---------------------------------------
+_pi = C.POINTER(C.c_int32)
+
+
+class plba_newline_batch(C.Structure):
+    _fields_ = [("n", C.c_int32), ("n_kf", C.c_int32), ("cam", C.c_double * 5), ("seg_l", _pd), ("seg_r", _pd), ("seg_curr", _pd),
+                ("kf_prev", _pi), ("kf_curr", _pi), ("kf_T_wc", _pd)]
+
+
+def _newline_batch(cam5, seg_l, seg_r, seg_curr, kf_prev, kf_curr, kf_T_wc):
+    keep = [np.ascontiguousarray(seg_l, np.float64).reshape(-1, 4), np.ascontiguousarray(seg_r, np.float64).reshape(-1, 4),
+            np.ascontiguousarray(seg_curr, np.float64).reshape(-1, 4), np.ascontiguousarray(kf_prev, np.int32), np.ascontiguousarray(kf_curr, np.int32),
+            np.ascontiguousarray(kf_T_wc, np.float64).reshape(-1, 12)]
+    B = plba_newline_batch()
+    B.n, B.n_kf = keep[0].shape[0], keep[5].shape[0]
+    for i in range(5):
+        B.cam[i] = float(cam5[i])
+    B.seg_l, B.seg_r, B.seg_curr = (a.ctypes.data_as(_pd) for a in keep[:3])
+    B.kf_prev, B.kf_curr, B.kf_T_wc = keep[3].ctypes.data_as(_pi), keep[4].ctypes.data_as(_pi), keep[5].ctypes.data_as(_pd)
+    return B, keep
+
+
+def _newline_call(fn, first_args, cam5, seg_l, seg_r, seg_curr, kf_prev, kf_curr, kf_T_wc):
+    B, keep = _newline_batch(cam5, seg_l, seg_r, seg_curr, kf_prev, kf_curr, kf_T_wc)
+    n = B.n
+    out = {"NDc": np.zeros((n, 6)), "NDw": np.zeros((n, 6)), "err_first": np.zeros(n), "err_curr": np.zeros(n), "accept": np.zeros(n, np.uint8)}
+    rc = fn(*first_args, C.byref(B), out["NDc"].ctypes.data_as(_pd), out["NDw"].ctypes.data_as(_pd), out["err_first"].ctypes.data_as(_pd),
+            out["err_curr"].ctypes.data_as(_pd), out["accept"].ctypes.data_as(_pb))
+    return rc, out
+
+
+def create_lines(solver, cam5, seg_l, seg_r, seg_curr, kf_prev, kf_curr, kf_T_wc):
+    """Stereo-triangulated Plücker lines in the creating keyframe (NDc) and in the world (NDw), re-projection errors and the sqrt(5.991) gate."""
+    L = solver.L
+    L.plba_create_lines.argtypes = [C.c_void_p, C.POINTER(plba_newline_batch), _pd, _pd, _pd, _pd, _pb]
+    L.plba_create_lines.restype = C.c_int
+    rc, out = _newline_call(L.plba_create_lines, (solver.h,), cam5, seg_l, seg_r, seg_curr, kf_prev, kf_curr, kf_T_wc)
+    solver._check(rc)
+    return out
+
+
+def make_line_candidates(seed, n=500, n_kf=6, cam5=(435.2, 435.2, 367.2, 252.2, 0.110078), noise=0.3, outliers=0.1):
+    """3-D segments seen by a rectified stereo pair at keyframe `kf_prev` and by the left camera of `kf_curr`.
+    Returns the arguments of create_lines plus the true world Plücker lines (unit direction)."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy, b = cam5
+    T = np.zeros((n_kf, 3, 4))
+    for k in range(n_kf):
+        T[k] = _exp_se3(np.r_[0.3 * k + rng.normal() * 0.02, rng.normal(size=2) * 0.02, rng.normal(size=3) * 0.02])[:3]      # camera -> world
+    kp = rng.integers(0, n_kf - 1, n).astype(np.int32); kc = (kp + 1).astype(np.int32)
+    u, v, z = rng.uniform(60, 700, n), rng.uniform(40, 440, n), rng.uniform(2.0, 10.0, n)
+    sP = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)                    # in the creating camera frame
+    d = rng.normal(size=(n, 3)); d[:, 2] *= 0.3; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    eP = sP + d * rng.uniform(0.4, 1.5, (n, 1)); eP[:, 2] = np.maximum(eP[:, 2], 1.0)
+    proj = lambda P, off=0.0: np.stack([cx + fx * (P[:, 0] - off) / P[:, 2], cy + fy * P[:, 1] / P[:, 2]], 1)
+    seg_l = np.concatenate([proj(sP), proj(eP)], 1) + rng.normal(size=(n, 4)) * noise
+    seg_r = np.concatenate([proj(sP, b), proj(eP, b)], 1) + rng.normal(size=(n, 4)) * noise
+    seg_r[:, 1], seg_r[:, 3] = seg_l[:, 1], seg_l[:, 3]                              # same rows after the interpolation of :367-368
+    Rp, tp = T[kp][:, :, :3], T[kp][:, :, 3]
+    sW = np.einsum("nij,nj->ni", Rp, sP) + tp; eW = np.einsum("nij,nj->ni", Rp, eP) + tp
+    Rc, tc = T[kc][:, :, :3], T[kc][:, :, 3]
+    toc = lambda Pw: np.einsum("nji,nj->ni", Rc, Pw - tc)
+    seg_curr = np.concatenate([proj(toc(sW)), proj(toc(eW))], 1) + rng.normal(size=(n, 4)) * noise
+    bad = rng.random(n) < outliers
+    seg_curr[bad] += rng.uniform(-25, 25, (int(bad.sum()), 4))
+    dW = (eW - sW) / np.linalg.norm(eW - sW, axis=1, keepdims=True)
+    truth = np.concatenate([np.cross(sW, dW), dW], 1)
+    return (cam5, seg_l, seg_r, seg_curr, kp, kc, T.reshape(n_kf, 12)), truth

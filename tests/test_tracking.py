@@ -85,3 +85,40 @@ def test_gpu_tracking_parity(gpu_solver, oracle):
     for i in (0, 151, 299):
         _close(oracle.track_solve(frames[i], trk.Options(CAM)), res[i])
     assert all(r["good"] for r in res)
+
+
+# ---- creation of Plücker line landmarks --------------------------------------------------------
+def test_line_creation_oracle_recovers_the_3d_line(oracle):
+    """Noise-free stereo segments: the triangulated NDw is the world Plücker line (unit direction) up to the sign of (n, d),
+    both re-projection errors vanish and every candidate passes the sqrt(5.991) gate."""
+    args, truth = trk.make_line_candidates(3, n=300, noise=0.0, outliers=0.0)
+    o = oracle.create_lines(*args)
+    sign = np.sign(np.sum(o["NDw"][:, 3:] * truth[:, 3:], axis=1))[:, None]
+    np.testing.assert_allclose(o["NDw"] * sign, truth, atol=1e-7)
+    np.testing.assert_allclose(np.linalg.norm(o["NDw"][:, 3:], axis=1), 1.0, atol=1e-12)
+    assert o["err_first"].max() < 1e-7 and o["err_curr"].max() < 1e-6 and o["accept"].all()
+    # NDc is a valid Plücker line: n . d = 0
+    assert np.abs(np.sum(o["NDc"][:, :3] * o["NDc"][:, 3:], axis=1)).max() < 1e-9 * np.abs(o["NDc"]).max() ** 2
+
+
+def _line_creation_parity(s, oracle):
+    args, _ = trk.make_line_candidates(4, n=700)
+    o, r = oracle.create_lines(*args), trk.create_lines(s, *args)
+    for k in ("NDc", "NDw", "err_first", "err_curr"):
+        np.testing.assert_allclose(r[k], o[k], rtol=1e-9, atol=1e-9)
+    near = np.abs(o["err_curr"] - np.sqrt(5.991)) < 1e-9
+    assert ((r["accept"] == o["accept"]) | near).all() and 0 < o["accept"].sum() < 700        # the gate is index work: bit-exact
+    assert ((o["err_curr"] > np.sqrt(5.991)) == (o["accept"] == 0)).all()
+
+
+def test_line_creation_in_emulation(emu, oracle):
+    s = solver.LBASolver(0, lib=emu)
+    try:
+        _line_creation_parity(s, oracle)
+    finally:
+        s.close()
+
+
+@pytest.mark.gpu
+def test_gpu_line_creation_parity(gpu_solver, oracle):
+    _line_creation_parity(gpu_solver, oracle)
