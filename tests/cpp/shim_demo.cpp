@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <memory>
 #include "../../pl_slam_plucker_b200/csrc/shim/map_handler_shim.h"
+#include "../../pl_slam_plucker_b200/csrc/shim/stereo_frame_handler_shim.h"
 using namespace plba_shim;
 
 int main(int argc, char **argv) {
@@ -51,6 +52,30 @@ int main(int argc, char **argv) {
         }
         mh.globalBundleAdjustment();                                  // shutdown-time global BA: ignores vo_status and the `local` flags, returns nothing
         std::printf("gba iters=%zu\n", mh.last_trace.size());
+        {   // the steps either side of the path under the reference's names: pose tracking on 60 synthetic point matches, one new map line
+            StereoFrameHandlerShim sfh(0);
+            sfh.fx = cam.fx; sfh.fy = cam.fy; sfh.cx = cam.cx; sfh.cy = cam.cy; sfh.b = 0.110078;
+            std::vector<std::unique_ptr<PointFeature>> feats;
+            const double tz = 0.05, tx = 0.02;                                  // true motion: pure translation previous -> current frame
+            for (int i = 0; i < 60; i++) {
+                feats.emplace_back(new PointFeature());
+                PointFeature *f = feats.back().get();
+                f->P = {-2.0 + 0.07 * i, -1.0 + 0.035 * ((i * 7) % 60), 4.0 + 0.1 * ((i * 13) % 40)};
+                f->pl_obs = {cam.cx + cam.fx * (f->P[0] + tx) / (f->P[2] + tz), cam.cy + cam.fy * f->P[1] / (f->P[2] + tz)};
+                sfh.matched_pt.push_back(f);
+            }
+            Matrix4d_rm DT{}; DT[0] = DT[5] = DT[10] = DT[15] = 1.0;
+            Matrix6d_rm cov{}; double err = 0;
+            sfh.gaussNewtonOptimizationforPluker(DT, cov, err, sfh.config.max_iters_ref);
+            std::printf("track good=%d iters=%d t=%.6f,%.6f,%.6f err=%.3e\n", sfh.last_good ? 1 : 0, sfh.last_iters, DT[3], DT[7], DT[11], err);
+            // a horizontal-ish 3-D segment seen by a rectified pair at the identity pose and by a second keyframe 0.3 m to the right
+            const double P1[3] = {-0.5, 0.2, 5.0}, P2[3] = {0.6, -0.3, 6.0};
+            auto px = [&](const double *P, double off) { return std::array<double, 2>{cam.cx + cam.fx * (P[0] - off) / P[2], cam.cy + cam.fy * P[1] / P[2]}; };
+            const auto a = px(P1, 0), c2 = px(P2, 0), ar = px(P1, sfh.b), cr = px(P2, sfh.b), ac = px(P1, 0.3), cc = px(P2, 0.3);
+            Matrix4d_rm T0{}; T0[0] = T0[5] = T0[10] = T0[15] = 1.0; Matrix4d_rm T1 = T0; T1[3] = 0.3;
+            const auto nl = sfh.createMapLine({a[0], a[1], c2[0], c2[1]}, {ar[0], ar[1], cr[0], cr[1]}, {ac[0], ac[1], cc[0], cc[1]}, T0, T1);
+            std::printf("newline accepted=%d error=%.3e error2=%.3e d=%.6f,%.6f,%.6f\n", nl.accepted ? 1 : 0, nl.error, nl.error2, nl.NDw[3], nl.NDw[4], nl.NDw[5]);
+        }
     } catch (const std::exception &e) { std::fprintf(stderr, "error: %s\n", e.what()); plba_scene_destroy(sc); return 1; }
     plba_scene_destroy(sc);
     return 0;

@@ -31,7 +31,15 @@ def _check(out, oracle):
     assert re.search(r"hand_lm rc=0 iters=\d+", out) and "discarded rc=-1" in out
     m2 = re.search(r"culled=(\d+) expected=(\d+) points_left=(\d+)", out)      # removeBadMapLandmarksForPluker after the LBA
     assert m2 and m2.group(1) == m2.group(2) and int(m2.group(1)) > 0 and int(m2.group(3)) < 120
-    assert "gba iters=15" in out             # faithful GBA: err /= 0 in every pass, so all maxItersLba passes run (src/mapHandler.cpp:3662-3665)
+    assert "gba iters=15" in out
+    # StereoFrameHandlerShim: the pose tracker recovers the pure translation (0.02, 0, 0.05); the triangulated line has the segment's direction
+    mt = re.search(r"track good=1 iters=\d+ t=(\S+),(\S+),(\S+) err=(\S+)", out)
+    assert mt, out
+    np.testing.assert_allclose([float(mt.group(i)) for i in (1, 2, 3)], [0.02, 0.0, 0.05], atol=1e-5)
+    ml = re.search(r"newline accepted=1 error=(\S+) error2=(\S+) d=(\S+),(\S+),(\S+)", out)
+    assert ml and float(ml.group(1)) < 1e-6 and float(ml.group(2)) < 1e-6, out
+    dtrue = np.array([1.1, -0.5, 1.0]) / np.linalg.norm([1.1, -0.5, 1.0]); dgot = np.array([float(ml.group(i)) for i in (3, 4, 5)])
+    assert min(np.abs(dgot - dtrue).max(), np.abs(dgot + dtrue).max()) < 1e-6             # faithful GBA: err /= 0 in every pass, so all maxItersLba passes run (src/mapHandler.cpp:3662-3665)
 
 
 def test_shim_compiles_and_runs_on_the_emulation_build(tmp_path, oracle, emu):
