@@ -9,7 +9,8 @@ over one synthetic window of the named workload.  Default workload = BASELINE co
   value : observations/s = (point + line observations) x LM trials / device time, problem resident in HBM
           (plba_reset_state + plba_run), CUDA events on the library's stream, L2 flushed between steps.
   e2e   : the same metric through plba_solve() with HOST buffers in and out (H2D + D2H inside the timed region).
-  N > 1 : one rank per GPU, one independent window per rank (different seed), no data-path collective: weak scaling.
+  N > 1 : one rank per GPU, one independent window per rank (the same synthetic window: identical per-GPU work), no data-path
+          collective: weak scaling.
 --impl reference : the CPU restatement of the reference (oracle/, all host threads) on the same workload; rank 0 only.
 """
 import argparse
@@ -211,7 +212,9 @@ def main():
     prof = PROFILES[args.profile]
     cfg = WORKLOADS[args.workload]
     sp = scene.preset(cfg)
-    P = scene.make_scene(cfg, line_mode=1 if prof == abi.PROFILE_H_END else 0, seed=int(sp.seed) + 1000 * rank)
+    # weak scaling: every rank solves its own copy of the SAME synthetic window, so that the per-GPU work is identical (windows drawn with
+    # different seeds take 19-25 LM trials and the step time, a maximum over ranks, would measure that imbalance instead)
+    P = scene.make_scene(cfg, line_mode=1 if prof == abi.PROFILE_H_END else 0, seed=int(sp.seed))
     opt = abi.Options(prof, args.quirks)
     stream = torch.cuda.Stream(device=dev)
     s = solver.LBASolver(local, stream=stream.cuda_stream)
@@ -286,7 +289,7 @@ def main():
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "lm_iters_per_s": trials_all / (ms_max * 1e-3), "lm_trials_per_step": trials / args.steps,
                 "config": {"workload": workload_name(args, P), "profile": args.profile, "quirks": args.quirks, "windows_per_gpu": 1,
-                           "l2": "flushed between steps (256 MiB write)", "parallelism": "one independent window per GPU, no collective"},
+                           "l2": "flushed between steps (256 MiB write)", "parallelism": "one independent window per GPU (the same synthetic window on every rank), no collective"},
                 "e2e": {"value": e2e_obs_trials / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
                         "ms_per_step": e2e_ms_max / e2e_steps, "steps": e2e_steps,
                         "breakdown_ms": {"host_flatten": hp / e2e_steps, "device_lm_loop": gpu_ms / e2e_steps, "host_unpack": hu / e2e_steps}},
