@@ -27,4 +27,5 @@ test_edge_cases = g.test_edge_cases
 test_sigma_weights = g.test_sigma_weights
 test_global_ba_shell = g.test_global_ba_shell
 test_both_kernel_paths = g.test_both_kernel_paths
+test_randomised_window_shapes = g.test_randomised_window_shapes
 test_map_handler_interface = g.test_map_handler_interface

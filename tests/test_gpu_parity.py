@@ -371,3 +371,31 @@ def test_config4_full_size_properties(gpu_solver):
     # H_pp of an observation travels with its landmark, so the sum is exact up to rounding
     np.testing.assert_allclose(Ssum, S, rtol=1e-9, atol=1e-6 * np.abs(S).max())
     np.testing.assert_allclose(gsum, g, rtol=1e-9, atol=1e-9 * np.abs(g).max())
+
+
+def _random_case(i):
+    """Deterministic pseudo-random window shape number i: keyframe counts, landmark counts, track lengths, loop closures, class mix."""
+    rng = np.random.default_rng(1000 + i)
+    nf = int(rng.integers(2, 15))
+    # well-posed shapes only (>= 12 point landmarks per free keyframe, mean track >= 3.5): an under-constrained window amplifies rounding
+    # beyond any fixed tolerance in every implementation (exploding rejected trials with rho ~ -1e3)
+    kw = dict(n_kf_free=nf, n_kf_fixed=int(rng.integers(1, 4)), n_pt=int(rng.integers(12 * nf, 12 * nf + 250)), n_ls=int(rng.integers(0, 80)),
+              mean_track=float(rng.uniform(3.5, 9.0)), seed=int(rng.integers(1, 10 ** 6)))
+    if rng.random() < 0.3:
+        kw["loop_every"] = int(rng.integers(3, 8))
+    prof, q = ALL[int(rng.integers(0, len(ALL)))]
+    return kw, prof, q, int(rng.integers(1, 3))
+
+
+@pytest.mark.parametrize("i", range(60))
+def test_randomised_window_shapes(gpu_solver, oracle, i):
+    """More parity cases: random shapes x profiles x quirk modes x both kernel implementations, every one against the oracle."""
+    kw, prof, q, path = _random_case(i)
+    P = _scene(1, prof, **kw)
+    if P.n_obs == 0:
+        pytest.skip("empty draw")
+    gpu_solver.set_kernel_path(path)
+    try:
+        _check(gpu_solver, oracle, P, prof, q)
+    finally:
+        gpu_solver.set_kernel_path(0)
