@@ -110,7 +110,7 @@ PLBA_HD void pose_oplus_g(const double *T, const double *dl, double *o) {
 // R(theta) = Rz(t3) Ry(t2) Rx(t1), written out as src/mapFeatures.cpp:211-215
 PLBA_HD void orth_R(const double *o, double *R) {
     double s1, c1, s2, c2, s3, c3;
-    s1 = sin(o[0]); c1 = cos(o[0]); s2 = sin(o[1]); c2 = cos(o[1]); s3 = sin(o[2]); c3 = cos(o[2]);
+    plba_sincos(o[0], &s1, &c1); plba_sincos(o[1], &s2, &c2); plba_sincos(o[2], &s3, &c3);      // one range reduction per angle
     R[0] = c2 * c3; R[1] = s1 * s2 * c3 - c1 * s3; R[2] = c1 * s2 * c3 + s1 * s3;
     R[3] = c2 * s3; R[4] = s1 * s2 * s3 + c1 * c3; R[5] = c1 * s2 * s3 - s1 * c3;
     R[6] = -s2;     R[7] = s1 * c2;                R[8] = c1 * c2;
@@ -118,7 +118,7 @@ PLBA_HD void orth_R(const double *o, double *R) {
 // changeOrthToPluker, src/mapFeatures.cpp:203-224 / g2o_types.h:367-387 :  n = cos(phi) R(:,0), d = sin(phi) R(:,1)
 PLBA_HD void orth_to_plk(const double *o, double *pl) {
     double R[9]; orth_R(o, R);
-    const double w1 = cos(o[3]), w2 = sin(o[3]);
+    double w1, w2; plba_sincos(o[3], &w2, &w1);
     pl[0] = w1 * R[0]; pl[1] = w1 * R[3]; pl[2] = w1 * R[6];
     pl[3] = w2 * R[1]; pl[4] = w2 * R[4]; pl[5] = w2 * R[7];
 }
@@ -134,13 +134,15 @@ PLBA_HD void orth_to_plk_sc(const double *o, double *pl) {
 struct LinePre { double n[3], d[3], u1[3], u2[3], u3[3], w1, w2; };
 PLBA_HD void line_pre_from_plk(const double *pl, LinePre &L) {
     for (int i = 0; i < 3; i++) { L.n[i] = pl[i]; L.d[i] = pl[3 + i]; }
-    const double nn = sqrt(dot3(L.n, L.n)), dn = sqrt(dot3(L.d, L.d));
-    for (int i = 0; i < 3; i++) { L.u1[i] = L.n[i] / nn; L.u2[i] = L.d[i] / dn; }
+    // four reciprocal square roots instead of four square roots and eleven divisions (this sits on the latency path of every line chunk)
+    const double n2 = dot3(L.n, L.n), d2 = dot3(L.d, L.d);
+    const double ni = plba_rsqrt_hd(n2), di = plba_rsqrt_hd(d2);
+    for (int i = 0; i < 3; i++) { L.u1[i] = L.n[i] * ni; L.u2[i] = L.d[i] * di; }
     double c[3]; cross3(L.n, L.d, c);
-    const double cn = sqrt(dot3(c, c));
-    for (int i = 0; i < 3; i++) L.u3[i] = c[i] / cn;
-    const double f = sqrt(nn * nn + dn * dn);
-    L.w1 = nn / f; L.w2 = dn / f;
+    const double ci = plba_rsqrt_hd(dot3(c, c));
+    for (int i = 0; i < 3; i++) L.u3[i] = c[i] * ci;
+    const double fi = plba_rsqrt_hd(n2 + d2);
+    L.w1 = n2 * ni * fi; L.w2 = d2 * di * fi;
 }
 // changePlukerToOrth, src/mapFeatures.cpp:186-201
 PLBA_HD void plk_to_orth(const double *pl, double *o) {
@@ -153,8 +155,8 @@ PLBA_HD void plk_to_orth(const double *pl, double *o) {
 // updateOrthCoord, include/mapHandler.h:252-335 / g2o_types.h:72-130:  U <- U Rx(d1) Ry(d2) Rz(d3), W <- W W(d4)
 PLBA_HD void orth_update(const double *D, const double *dl, double *o) {
     double R[9]; orth_R(D, R);
-    const double w1 = cos(D[3]), w2 = sin(D[3]);
-    const double sx = sin(dl[0]), cx = cos(dl[0]), sy = sin(dl[1]), cy = cos(dl[1]), sz = sin(dl[2]), cz = cos(dl[2]);
+    double w1, w2, sx, cx, sy, cy, sz, cz, s4, c4;
+    plba_sincos(D[3], &w2, &w1); plba_sincos(dl[0], &sx, &cx); plba_sincos(dl[1], &sy, &cy); plba_sincos(dl[2], &sz, &cz); plba_sincos(dl[3], &s4, &c4);
     // M = Rx*Ry*Rz
     const double M[9] = {cy * cz, -cy * sz, sy,
                          sx * sy * cz + cx * sz, -sx * sy * sz + cx * cz, -sx * cy,
@@ -166,7 +168,7 @@ PLBA_HD void orth_update(const double *D, const double *dl, double *o) {
     for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) RX[r * 3 + c] = R[r * 3] * Rx[c] + R[r * 3 + 1] * Rx[3 + c] + R[r * 3 + 2] * Rx[6 + c];
     for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) RXY[r * 3 + c] = RX[r * 3] * Ry[c] + RX[r * 3 + 1] * Ry[3 + c] + RX[r * 3 + 2] * Ry[6 + c];
     for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) Rn[r * 3 + c] = RXY[r * 3] * Rz[c] + RXY[r * 3 + 1] * Rz[3 + c] + RXY[r * 3 + 2] * Rz[6 + c];
-    const double W10 = w2 * cos(dl[3]) + w1 * sin(dl[3]);
+    const double W10 = w2 * c4 + w1 * s4;
     o[0] = atan2(Rn[7], Rn[8]);
     o[1] = asin(-Rn[6]);
     o[2] = atan2(Rn[3], Rn[0]);
