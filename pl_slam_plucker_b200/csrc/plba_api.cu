@@ -637,10 +637,11 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
         const ClassLayout &L = cls ? Lls[w] : Lps[w];
         for (size_t l = 0; l + 1 < L.optr.size(); l++) max_track = std::max(max_track, L.optr[l + 1] - L.optr[l]);
     }
-    // small uploads (less than about two passes per resident warp) are latency-bound: there the CTA-chunk kernels, whose warps share
-    // their instruction stream, measured faster (profiles/README.md r01f)
+    // routing by size, measured (profiles/README.md r01f-h, tools/route_sweep.py): up to ~0.7 M observations the two implementations are
+    // within 4 % of each other with the CTA-chunk kernels ahead (a small upload is latency-bound and their warps share one instruction
+    // stream); from ~1 M observations on the warp kernels win (config 3: 85 against 119 ms, config 5: assembly 1.9 against 2.8 ms)
     const int64_t n_obs_total = (int64_t)tot.n_pobs + tot.n_lobs;
-    const bool big = n_obs_total >= (int64_t)64 * h->grid_warp * WARPS_PER_CTA;
+    const bool big = n_obs_total >= (int64_t)6500 * h->n_sm;
     h->warp_path = h->force_chunk != 1 && max_track <= W_MAX_TRACK && (big || h->force_chunk == 2);
     std::vector<WItem> &wi_pt = h->wi_pt, &wi_ls = h->wi_ls;
     wi_pt.clear(); wi_ls.clear();
