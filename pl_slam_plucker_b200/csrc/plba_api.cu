@@ -78,7 +78,7 @@ struct plba_handle_s {
 #ifndef PLBA_HOST_EMU
     cudaGraph_t graph[12]{};       // [(profile * 2 + size class of the reduced system) * 2 + warp path]
     cudaGraphExec_t gexec[12]{};
-    cudaGraphConditionalHandle cond_while[12]{}, cond_prep[12]{};
+    cudaGraphConditionalHandle cond_while[12]{}, cond_prep[12]{}, cond_prep2[12]{};
 #endif
     void release() {
         if (d_arena) cudaFree(d_arena);
@@ -547,6 +547,26 @@ template <int PROF> static int build_graph(plba_handle h) {
     CK(add_kernel(body, &m1, inode, f_asm, gc, bc, smc, a_m1));
     CK(add_kernel(body, &m2, m1, (void *)k_solve_small, dim3(h->grid_solve), dim3(256), solve_small_smem(h->solve_class), a_p));
     CK(add_kernel(body, &m3, m2, f_upd, gu, bc, smc, a_fl));
+#ifdef PLBA_GRAPH_TWO_TRIALS
+    // a second LM trial inside the same WHILE iteration: the loop's per-iteration cost (evaluating the condition, re-launching the
+    // body) is paid once per two trials.  Its IF(prep) node has a handle of its own, set by the controller of the first trial; when
+    // the first trial finished the last window the second one runs as three empty launches, once per LBA.
+    {
+        CK(cudaGraphConditionalHandleCreate(&h->cond_prep2[pi], g, 1, cudaGraphCondAssignDefault));
+        cudaGraphNodeParams ip2{}; ip2.type = cudaGraphNodeTypeConditional;
+        ip2.conditional.handle = h->cond_prep2[pi]; ip2.conditional.type = cudaGraphCondTypeIf; ip2.conditional.size = 1;
+        cudaGraphNode_t inode2;
+        CK(cudaGraphAddNode(&inode2, body, &m3, 1, &ip2));
+        cudaGraph_t prep2 = ip2.conditional.phGraph_out[0];
+        cudaGraphNode_t q1, q2, q3, r1, r2, r3;
+        CK(add_kernel(prep2, &q1, nullptr, (void *)k_gate, dim3(h->grid_chunks), dim3(256), 0, a_p));
+        CK(add_kernel(prep2, &q2, q1, f_asm, gc, bc, smc, a_m0));
+        CK(add_kernel(prep2, &q3, q2, (void *)k_lambda_init, dim3(h->n_sm), dim3(128), 0, a_p));
+        CK(add_kernel(body, &r1, inode2, f_asm, gc, bc, smc, a_m1));
+        CK(add_kernel(body, &r2, r1, (void *)k_solve_small, dim3(h->grid_solve), dim3(256), solve_small_smem(h->solve_class), a_p));
+        CK(add_kernel(body, &r3, r2, f_upd, gu, bc, smc, a_fl));
+    }
+#endif
     CK(cudaGraphInstantiate(&h->gexec[pi], g, 0));
     h->graph[pi] = g;
     return PLBA_OK;
@@ -965,7 +985,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     if (h->small_path && !h->no_graph) {
         if ((rc = build_graph_for(h, prof))) return rc;
         const int pi = (prof * 2 + h->solve_class) * 2 + (h->warp_path ? 1 : 0);
-        P.cond_while = (unsigned long long)h->cond_while[pi]; P.cond_prep = (unsigned long long)h->cond_prep[pi];
+        P.cond_while = (unsigned long long)h->cond_while[pi]; P.cond_prep = (unsigned long long)h->cond_prep[pi]; P.cond_prep2 = (unsigned long long)h->cond_prep2[pi];
     }
 #endif
     HOSTPROF("params");

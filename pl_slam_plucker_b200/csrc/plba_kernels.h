@@ -101,7 +101,7 @@ struct DevP {
     const WinCtrl *ctrl0;             // initial controller state (reset)
     plba_trace_rec *trace; int trace_cap, pad1;
     int *counters;                    // [CNT_N]
-    unsigned long long cond_while, cond_prep;   // cudaGraphConditionalHandle of the LM-loop graph
+    unsigned long long cond_while, cond_prep, cond_prep2;   // cudaGraphConditionalHandle of the LM-loop graph (prep2: the IF node of the second trial of an iteration)
 };
 
 #ifndef PLBA_HOST_EMU
@@ -865,6 +865,7 @@ PLBA_D void round_epilogue(const DevP &P, int flags) {
         const int prep = plba_ld_l2(&P.counters[CNT_NEED_INIT]) + plba_ld_l2(&P.counters[CNT_GATE]);
         plba_graph_set(P.cond_while, (done < P.n_win && rounds < P.max_rounds) ? 1u : 0u);
         plba_graph_set(P.cond_prep, prep > 0 ? 1u : 0u);
+        if (P.cond_prep2) plba_graph_set(P.cond_prep2, prep > 0 ? 1u : 0u);
     }
 }
 
