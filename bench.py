@@ -299,7 +299,11 @@ def main():
                              "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": (A / (asm_ms * 1e-3) / 1e9 / peak) if asm_ms > 0 else None,
                              "traffic": _traffic(args.workload) if args.profile == "G" else None, "algorithmic_bytes": A, "ms_per_launch": asm_ms, "launches_timed": int(n_asm),
                              "stage_ms_per_step": {"assemble": t_asm / det_steps, "solve": t_sol / det_steps, "update": t_upd / det_steps},
-                             "how": "CUDA events around each stage in a host-driven replay of the same steps (the headline steps run as one CUDA graph)"}}
+                             "how": "CUDA events around each stage in a host-driven replay of the same steps (the headline steps run as one CUDA graph)",
+                             "note": "BASELINE's metric quotes the roofline on the assembly stage, so this object is the assembly kernel; on this small window "
+                                     "the largest share of the step is the reduced-system Cholesky (k_solve_small, %.0f %% of the stage time: n = %d sequential pivots, "
+                                     "latency-bound, ~0.6 MFLOP), and every kernel is launch/latency-bound: see roofline_largest for the configuration whose "
+                                     "assembly is throughput-bound" % (100.0 * t_sol / max(t_asm + t_sol + t_upd, 1e-9), 6 * P.n_free)}}
         line.update(extras)
         if not args.no_cpu_baseline:
             from oracle import loader as orc
