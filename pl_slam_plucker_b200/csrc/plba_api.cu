@@ -717,6 +717,11 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
             }
         }
     }
+    // segment length of the CTA-chunk kernels: 8 landmarks per (segment, pose pair) task is the throughput optimum (profiles/README.md
+    // r01b); an upload that fits one wave of CTAs is latency-bound by that 8-iteration loop, and 6 keeps a 256-observation chunk of
+    // 5-keyframe tracks within one round of 256 tasks (measured on C2: assembly 31.4 -> 27.3 us; 4 needs two rounds: 43.9 us)
+    const int64_t est_chunks = ((int64_t)tot.n_pobs + OC - 1) / OC + ((int64_t)tot.n_lobs + OC - 1) / OC + 2 * n;
+    const int seg_max = (est_chunks <= h->grid_chunks) ? 6 : (int)SEG_MAX;
     for (int w = 0; w < n && !h->warp_path; w++) {
         const plba_problem &p = probs[w]; const WinInfo &wi = h->wins[w];
         const ClassLayout &Lp = Lps[w], &Ll = Lls[w];
@@ -741,7 +746,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
                 if (seg_first_old >= 0) {
                     Seg &s = sgs.back();
                     const int fa = L.optr[seg_first_old];
-                    if (s.n_lm < SEG_MAX && s.nobs == no) {
+                    if (s.n_lm < seg_max && s.nobs == no) {
                         if (!L.group.empty()) join = (L.group[seg_first_old] == L.group[old]);
                         else { join = true; for (int i = 0; i < no; i++) if (kf[fa + i] != kf[a + i]) { join = false; break; } }
                     }
