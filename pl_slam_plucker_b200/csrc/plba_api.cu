@@ -717,11 +717,24 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
             }
         }
     }
-    // segment length of the CTA-chunk kernels: 8 landmarks per (segment, pose pair) task is the throughput optimum (profiles/README.md
-    // r01b); an upload that fits one wave of CTAs is latency-bound by that 8-iteration loop, and 6 keeps a 256-observation chunk of
-    // 5-keyframe tracks within one round of 256 tasks (measured on C2: assembly 31.4 -> 27.3 us; 4 needs two rounds: 43.9 us)
+    // Chunk and segment size of the CTA-chunk kernels.  256 observations per chunk and 8 landmarks per (segment, pose pair) task are the
+    // throughput optimum (profiles/README.md r01b).  An upload that fits ONE wave of CTAs is latency-bound instead: its observations are
+    // spread over the SMs (smaller chunks when there are fewer than 256 observations per SM) and the segments are as short as keeps a chunk within one round of 256 Schur tasks
+    // (the task loop runs seg_max iterations).  Measured on C2: assembly 31.4 us at (256, 8), 27.3 us at (256, 6), 43.9 us at (256, 4: two rounds).
+    const int64_t n_obs_all = (int64_t)tot.n_pobs + tot.n_lobs;
     const int64_t est_chunks = ((int64_t)tot.n_pobs + OC - 1) / OC + ((int64_t)tot.n_lobs + OC - 1) / OC + 2 * n;
-    const int seg_max = (est_chunks <= h->grid_chunks) ? 6 : (int)SEG_MAX;
+    int oc_cap = OC, seg_max = SEG_MAX;
+    if (est_chunks <= h->grid_chunks && n_obs_all > 0) {
+        // about one chunk per SM (two co-resident CTAs slow each other down: C2 at 298 chunks of 153 observations measured 35 us against
+        // 28.6 us at 180 chunks of 256; C1 at 148 chunks of 64 observations 17.0 us against 20.5 us at 37 chunks of 256)
+        oc_cap = (int)std::min<int64_t>(OC, std::max<int64_t>(64, (n_obs_all + h->n_sm - 1) / h->n_sm));
+        // mean track length -> landmarks per chunk and Schur tasks per segment (pairs x 2 halves + diagonal)
+        const double k_mean = (double)n_obs_all / std::max<int64_t>(1, (int64_t)tot.n_pt + tot.n_ls);
+        const double lm_per_chunk = oc_cap / std::max(1.0, k_mean), tasks_per_seg = k_mean * (k_mean - 1.0) + k_mean;
+        seg_max = 8;
+        for (int cand = 3; cand <= 8; cand++) if (std::ceil(lm_per_chunk / cand) * tasks_per_seg <= 0.85 * OC) { seg_max = cand; break; }
+    }
+    const int lc_cap = std::max(1, oc_cap / 2);
     for (int w = 0; w < n && !h->warp_path; w++) {
         const plba_problem &p = probs[w]; const WinInfo &wi = h->wins[w];
         const ClassLayout &Lp = Lps[w], &Ll = Lls[w];
@@ -740,7 +753,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
                 if (no > OC) { too_long = true; break; }
                 const int g = lm0 + nl_i;
                 perm[g] = lm0 + old;
-                if (open && ((g - c.lm0) >= LC || (ob - c.ob0) + no > OC)) close_chunk(g, ob);
+                if (open && ((g - c.lm0) >= lc_cap || (ob - c.ob0) + no > std::max(oc_cap, no))) close_chunk(g, ob);
                 if (!open) { c = Chunk{}; c.lm0 = g; c.ob0 = ob; c.win = w; c.seg0 = (int)sgs.size(); open = true; seg_first_old = -1; chunk_tasks = 0; chunk_dtasks = 0; }
                 bool join = false;
                 if (seg_first_old >= 0) {
