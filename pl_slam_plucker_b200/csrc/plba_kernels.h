@@ -185,11 +185,19 @@ PLBA_HD void lm_precompute(const DevP &P, const WinCtrl &ctl, int win, int lm, i
     if (LT == LT_POINT) {
         for (int i = 0; i < 3; i++) sm.Pre[i * LC + l] = state[(size_t)3 * lm + i];
     } else if (LT == LT_LINE_ORTH) {
-        double o[4], pl[6];
+        double o[4];
         for (int i = 0; i < 4; i++) o[i] = state[(size_t)4 * lm + i];
-        if (PROF == PLBA_PROFILE_H_PLK && ctl.iter == 0) { for (int i = 0; i < 6; i++) pl[i] = P.lns_map[(size_t)6 * lm + i]; }   // pass 0 reads map NDw (:1744)
-        else orth_to_plk(o, pl);
-        LinePre L; line_pre_from_plk(pl, L);
+        LinePre L;
+        if (PROF == PLBA_PROFILE_H_PLK && ctl.iter == 0) {      // pass 0 reads map NDw (:1744)
+            double pl[6];
+            for (int i = 0; i < 6; i++) pl[i] = P.lns_map[(size_t)6 * lm + i];
+            line_pre_from_plk(pl, L);
+        } else {
+            // Plücker vector, U and W at the current state: written once per landmark and state (k_reset, the update kernels), not per kernel
+            const double *c = P.lpre[ctl.cur] + (size_t)LPRE_N * lm;
+            for (int i = 0; i < 3; i++) { L.n[i] = c[i]; L.d[i] = c[3 + i]; L.u1[i] = c[6 + i]; L.u2[i] = c[9 + i]; L.u3[i] = c[12 + i]; }
+            L.w1 = c[15]; L.w2 = c[16];
+        }
         double *pre = sm.Pre + l;
         for (int i = 0; i < 3; i++) { pre[i * LC] = L.n[i]; pre[(3 + i) * LC] = L.d[i]; pre[(6 + i) * LC] = L.u1[i]; pre[(9 + i) * LC] = L.u2[i]; pre[(12 + i) * LC] = L.u3[i]; }
         pre[15 * LC] = L.w1; pre[16 * LC] = L.w2;
@@ -659,7 +667,19 @@ PLBA_D void update_chunk(const DevP &Pin, const Chunk &ch) {
             for (int i = 0; i < D; i++) cur[i] = state[(size_t)D * lm + i];
             if (LT == LT_LINE_ORTH) orth_update(cur, xl, nw);                 // updateOrthCoord (a11)
             else for (int i = 0; i < D; i++) nw[i] = cur[i] + xl[i];
-            if (PROF == PLBA_PROFILE_G || ctl.apply) for (int i = 0; i < D; i++) state_new[(size_t)D * lm + i] = nw[i];
+            if (PROF == PLBA_PROFILE_G || ctl.apply) {
+                for (int i = 0; i < D; i++) state_new[(size_t)D * lm + i] = nw[i];
+                if (LT == LT_LINE_ORTH) {
+                    // the new state's Plücker vector / U / W for the next linearisation (both kernels read it instead of redoing the trigonometry),
+                    // and, profile G, the Plücker vector for the cost evaluation below
+                    double pl[6]; orth_to_plk(nw, pl);
+                    LinePre Ln; line_pre_from_plk(pl, Ln);
+                    double *c = P.lpre[ctl.cur ^ 1] + (size_t)LPRE_N * lm;
+                    for (int i = 0; i < 3; i++) { c[i] = Ln.n[i]; c[3 + i] = Ln.d[i]; c[6 + i] = Ln.u1[i]; c[9 + i] = Ln.u2[i]; c[12 + i] = Ln.u3[i]; }
+                    c[15] = Ln.w1; c[16] = Ln.w2;
+                    if (PROF == PLBA_PROFILE_G) for (int i = 0; i < 6; i++) sm.Pre[i * LC + tid] = pl[i];
+                }
+            }
             for (int i = 0; i < D; i++) sm.Xl[i * LC + tid] = nw[i];
         }
         plba_block_add(&sm.red[1], sc);
@@ -668,14 +688,6 @@ PLBA_D void update_chunk(const DevP &Pin, const Chunk &ch) {
     PROF_MARK(23);
     if (PROF == PLBA_PROFILE_G) {
         // new cost at the trial state (computeActiveErrors + activeRobustChi2 after update)
-        PHASE_BEGIN
-            if (tid < nlm && LT == LT_LINE_ORTH) {
-                double o4[4], pl[6];
-                for (int i = 0; i < 4; i++) o4[i] = sm.Xl[i * LC + tid];
-                orth_to_plk(o4, pl);
-                for (int i = 0; i < 6; i++) sm.Pre[i * LC + tid] = pl[i];
-            }
-        PHASE_END
     PROF_MARK(24);
         PHASE_BEGIN
             double rho0 = 0.0;
