@@ -734,7 +734,13 @@ PLBA_D void lambda_init_window(const DevP &P, int w) {
     if (!c.done && c.need_init) {
         double m = plba_ld_l2(&P.accmax[w]);
         const int s0 = P.win_slot0[w], nf = P.win_nfree[w];
-        for (int i = 0; i < 6 * nf; i++) { const double h = fabs(plba_ld_l2(&P.hpp_diag_init[(size_t)6 * s0 + i])); if (h > m) m = h; P.hpp_diag_init[(size_t)6 * s0 + i] = 0.0; }
+        for (int i0 = 0; i0 < 6 * nf; i0 += 12) {      // twelve loads in flight (one thread per window: the loads, not the maximum, are the latency)
+            double hv[12];
+#pragma unroll
+            for (int u = 0; u < 12; u++) hv[u] = (i0 + u < 6 * nf) ? fabs(plba_ld_l2(&P.hpp_diag_init[(size_t)6 * s0 + i0 + u])) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 12; u++) { if (hv[u] > m) m = hv[u]; if (i0 + u < 6 * nf) P.hpp_diag_init[(size_t)6 * s0 + i0 + u] = 0.0; }
+        }
         P.accmax[w] = 0.0;
         if (P.profile == PLBA_PROFILE_G) { c.lambda = P.lm_tau * m; c.ni = 2.0; }
         else {
