@@ -29,3 +29,4 @@ test_global_ba_shell = g.test_global_ba_shell
 test_both_kernel_paths = g.test_both_kernel_paths
 test_randomised_window_shapes = g.test_randomised_window_shapes
 test_map_handler_interface = g.test_map_handler_interface
+test_randomised_large_windows = g.test_randomised_large_windows

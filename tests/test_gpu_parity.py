@@ -373,9 +373,12 @@ def test_config4_full_size_properties(gpu_solver):
     np.testing.assert_allclose(gsum, g, rtol=1e-9, atol=1e-9 * np.abs(g).max())
 
 
+_SWEEP_OFFSET = int(os.environ.get("PLBA_SWEEP_OFFSET", "0"))      # other draws of the two randomised sweeps (bug hunting; default 0)
+
+
 def _random_case(i):
     """Deterministic pseudo-random window shape number i: keyframe counts, landmark counts, track lengths, loop closures, class mix."""
-    rng = np.random.default_rng(1000 + i)
+    rng = np.random.default_rng(1000 + i + _SWEEP_OFFSET)
     nf = int(rng.integers(2, 15))
     # well-posed shapes only (>= 12 point landmarks per free keyframe, mean track >= 3.5): an under-constrained window amplifies rounding
     # beyond any fixed tolerance in every implementation (exploding rejected trials with rho ~ -1e3)
@@ -385,6 +388,34 @@ def _random_case(i):
         kw["loop_every"] = int(rng.integers(3, 8))
     prof, q = ALL[int(rng.integers(0, len(ALL)))]
     return kw, prof, q, int(rng.integers(1, 3))
+
+
+def _random_large_case(i):
+    """Windows above the single-CTA solver limit (6*Nkf > 144): sliding-window shapes of random width (block cyclic reduction with
+    a random node size), some with a long-range loop closure (dense tiled Cholesky), on either assembly implementation."""
+    rng = np.random.default_rng(5000 + i + _SWEEP_OFFSET)
+    nf = int(rng.integers(25, 72))
+    kw = dict(n_kf_free=nf, n_kf_fixed=int(rng.integers(1, 3)), n_pt=int(rng.integers(25 * nf, 40 * nf)), n_ls=int(rng.integers(0, 8 * nf)),
+              mean_track=float(rng.uniform(3.5, 9.0)), seed=int(rng.integers(1, 10 ** 6)))
+    if rng.random() < 0.25:
+        kw["loop_every"] = int(rng.integers(18, 24))
+    # profile G in its FIXED mode only: on a 25-70 keyframe chain the FAITHFUL line Jacobian (Q12) makes the damped system ill-conditioned
+    # enough that the dense and the block-cyclic factorisations both drift 1e-8 from the oracle after a few trials (same drift: conditioning)
+    prof, q = [(abi.PROFILE_G, 1), (abi.PROFILE_H_END, 0), (abi.PROFILE_H_END, 1), (abi.PROFILE_H_PLK, 1)][int(rng.integers(0, 4))]
+    return kw, prof, q, int(rng.integers(1, 3))
+
+
+@pytest.mark.parametrize("i", range(12))
+def test_randomised_large_windows(gpu_solver, oracle, i):
+    kw, prof, q, path = _random_large_case(i)
+    P = _scene(1, prof, **kw)
+    gpu_solver.set_kernel_path(path)
+    try:
+        _check(gpu_solver, oracle, P, prof, q)
+        kp = gpu_solver.kernel_path()
+        assert kp["solver"] != "shared-memory"                     # these windows are past the single-CTA limit
+    finally:
+        gpu_solver.set_kernel_path(0)
 
 
 @pytest.mark.parametrize("i", range(60))
