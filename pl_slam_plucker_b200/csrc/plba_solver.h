@@ -33,13 +33,16 @@ static inline size_t solve_small_smem(int cls) { const size_t nmax = cls == 0 ? 
 //     thread (no extra barrier), then the row is solved against it.
 //  F: the partial sums are folded into the panel, one thread per entry.
 // Must be called by all 256 threads of the CTA.
+#ifndef PLBA_SOLVE_INPLACE_K0
+#define PLBA_SOLVE_INPLACE_K0 36          // look-back (columns) up to which one thread per row updates the panel in place (measured: see profiles/README.md)
+#endif
 PLBA_D void chol_lower_panels(double *M, int ldm, int nd, int nr, double *dinv, double *Lblk, double *part, int *fail) {
     const int nf = nd / 6, n = nr;
 for (int kb = 0; kb < nf; kb++) {
     const int k0 = 6 * kb, m = n - k0 + 1;
     // the q range of a row is split over as many threads as the 256-thread CTA allows: late panels have few rows but long rows
     // short look-back (first panels): one thread per row updates the panel in place and the fold phase is skipped
-    const int mpad = (m + 31) & ~31, nsplit = (k0 <= 36) ? 1 : (mpad <= 32) ? 8 : (mpad <= 64) ? 4 : (mpad <= 128) ? 2 : 1;
+    const int mpad = (m + 31) & ~31, nsplit = (k0 <= PLBA_SOLVE_INPLACE_K0) ? 1 : (mpad <= 32) ? 8 : (mpad <= 64) ? 4 : (mpad <= 128) ? 2 : 1;
     PHASE_BEGIN
         const int sp = tid / mpad, rr = tid - sp * mpad;
         if (k0 > 0 && sp < nsplit && rr < m) {
