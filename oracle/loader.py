@@ -105,6 +105,15 @@ def orth_to_pluker(o):
     o = _v(o); pl = np.zeros(6); lib().plba_oracle_orth_to_pluker(_p(o), _p(pl)); return pl
 
 
+def orth_UW_jac(pl, q7=False):
+    pl = _v(pl); U = np.zeros(9); W = np.zeros(4); J = np.zeros(24)
+    lib().plba_oracle_orth_UW_jac(_p(pl), C.c_int(1 if q7 else 0), _p(U), _p(W), _p(J)); return U.reshape(3, 3), W.reshape(2, 2), J.reshape(6, 4)
+
+
+def transform_pluker(T, pl):
+    T = _v(T).reshape(16); pl = _v(pl); o = np.zeros(6); lib().plba_oracle_transform_pluker(_p(T), _p(pl), _p(o)); return o
+
+
 def update_orth(D, d):
     D = _v(D); d = _v(d); o = np.zeros(4); lib().plba_oracle_update_orth(_p(D), _p(d), _p(o)); return o
 

@@ -3,9 +3,15 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
 // The product (pl_slam_plucker_b200/csrc) never links, imports or calls anything in this directory.
 //
-// PARITY UNPINNED: kongan/PL-SLAM-plucker ships no test, golden vector, fixture or recorded log for its LBA
-//  and cannot be built here (Eigen, g2o, OpenCV, Boost, yaml-cpp, MRPT absent), so this
-// restatement is pinned only by self-made checks (finite differences, round trips, Schur == dense solve).
+// PARITY PARTLY PINNED.  kongan/PL-SLAM-plucker ships no test, golden vector, fixture or recorded log for its LBA
+//  and the application cannot be built here (Eigen, g2o, OpenCV, Boost, yaml-cpp, MRPT absent).
+//   PINNED on the reference's own code: the vertex / edge arithmetic of profile G and the MapLine orthonormal helpers
+//   (rows a6-a11, a17-a19 of SURVEY.md §8a) — g2o_types/g2o_types.h and src/mapFeatures.cpp compile UNMODIFIED against the
+//   stand-in headers of oracle/ref_shim/ into oracle/_ref/libref_g2o_types.so; refmath.h agrees with it bit for bit on
+//   seeded inputs (tests/test_ref_pin.py, committed vectors tests/golden/ref_g2o_types.npz).
+//   UNPINNED (no reference artefact exists): the g2o Levenberg / Schur shell (g2o is not under /root/reference and no version
+//   is pinned) and the hand-LM functions of src/mapHandler.cpp (OpenCV-entangled): those are pinned only by self-made checks
+//   (finite differences, round trips, Schur == dense solve).
 //
 // What is restated, with the reference lines followed:
 //   profile G     MapHandler::localBundleAdjustmentForPlukerWithG2O   src/mapHandler.cpp:5851-6323
@@ -896,6 +902,18 @@ void plba_oracle_logmap_se3(const double *T16, double *x6) { M4 T; for (int i = 
 void plba_oracle_inverse_se3(const double *T16, double *o16) { M4 T; for (int i = 0; i < 16; i++) T[i] = T16[i]; M4 o = inverse_se3(T); for (int i = 0; i < 16; i++) o16[i] = o[i]; }
 void plba_oracle_pluker_to_orth(const double *pl6, double *o4) { V6 p; for (int i = 0; i < 6; i++) p[i] = pl6[i]; V4 o = changePlukerToOrth(p); for (int i = 0; i < 4; i++) o4[i] = o[i]; }
 void plba_oracle_orth_to_pluker(const double *o4, double *pl6) { V4 o; for (int i = 0; i < 4; i++) o[i] = o4[i]; V6 p = changeOrthToPluker(o); for (int i = 0; i < 6; i++) pl6[i] = p[i]; }
+// U, W and d(Plücker)/d(orth) of a line; q7 != 0 selects the MapLine:: copy with the flipped sign (src/mapFeatures.cpp:260, quirk Q7)
+void plba_oracle_orth_UW_jac(const double *pl6, int q7, double *U9, double *W4, double *J24) {
+    V6 p; for (int i = 0; i < 6; i++) p[i] = pl6[i];
+    M3 U = getOrhtRFromPluker(p); M2 W = getOrthWFromPluker(p); Mat<6, 4> J = jacobianFromPlukerToOrth(U, W, q7 ? -1.0 : 1.0);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) U9[3 * i + j] = U(i, j);
+    for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) W4[2 * i + j] = W(i, j);
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 4; j++) J24[4 * i + j] = J(i, j);
+}
+void plba_oracle_transform_pluker(const double *T16, const double *pl6, double *out6) {
+    M4 T; for (int i = 0; i < 16; i++) T[i] = T16[i]; V6 p; for (int i = 0; i < 6; i++) p[i] = pl6[i];
+    V6 q = getTransformMatrixForPluker(T) * p; for (int i = 0; i < 6; i++) out6[i] = q[i];
+}
 void plba_oracle_update_orth(const double *D4, const double *d4, double *out4) { V4 D, d; for (int i = 0; i < 4; i++) { D[i] = D4[i]; d[i] = d4[i]; } V4 p = updateOrthCoord(D, d); for (int i = 0; i < 4; i++) out4[i] = p[i]; }
 void plba_oracle_pose_oplus(const double *T16, const double *d6, double *o16) { M4 T; for (int i = 0; i < 16; i++) T[i] = T16[i]; V6 d; for (int i = 0; i < 6; i++) d[i] = d6[i]; M4 o = poseOplusG2O(T, d); for (int i = 0; i < 16; i++) o16[i] = o[i]; }
 // EdgePosePoint: e[2], Jxi[2x3], Jxj[2x6]
