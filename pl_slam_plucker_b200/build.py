@@ -8,7 +8,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libplba.so")
 SOURCES = ["plba_api.cu", "scene_gen.cpp"]
-HEADERS = ["plba_port.h", "plba_math.h", "plba_kernels.h", "plba_solver.h", os.path.join("..", "..", "include", "plba.h")]
 
 
 def nvcc_path():
@@ -22,7 +21,9 @@ def is_stale():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    # every file under csrc/ (kernels, warp kernels, tracker, shims) plus the public header: a stale binary must never be measured
+    deps = [os.path.join(d, f) for d, _, fs in os.walk(CSRC) for f in fs] + [os.path.join(HERE, "..", "include", "plba.h")]
+    return any(os.path.getmtime(f) > t for f in deps)
 
 
 def build(force=False, verbose=False, out=None, defines=()):

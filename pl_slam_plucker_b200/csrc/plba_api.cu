@@ -73,6 +73,7 @@ struct plba_handle_s {
     plba_allreduce_fn allreduce = nullptr; void *allreduce_user = nullptr;
     plba_timing timing{};
     cudaEvent_t ev[8]{};
+    cudaEvent_t ev_h2d = nullptr; bool h2d_pending = false;   // recorded after the H2D copies of an upload: the next upload waits for it before it rewrites the pinned staging
     bool detail_timing = false, no_graph = false;
     int grid_chunks = 296, grid_solve = 148;
 #ifndef PLBA_HOST_EMU
@@ -274,14 +275,23 @@ int plba_create(int32_t device, void *stream, plba_handle *out) {
 #endif
     h->grid_chunks = 2 * h->n_sm; h->grid_solve = h->n_sm;
     void *q = nullptr;
-    if (cudaMalloc(&q, sizeof(DevP)) != cudaSuccess) { delete h; *out = nullptr; return PLBA_E_CUDA; }
+    auto fail = [&]() {      // every error exit releases what was acquired so far
+        if (h->d_P) cudaFree(h->d_P);
+        if (h->d_scratch) cudaFree(h->d_scratch);
+        if (h->h_P) cudaFreeHost(h->h_P);
+        if (h->h_cnt) cudaFreeHost(h->h_cnt);
+        if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+        delete h; *out = nullptr; return PLBA_E_CUDA;
+    };
+    if (cudaMalloc(&q, sizeof(DevP)) != cudaSuccess) return fail();
     h->d_P = (DevP *)q;
-    if (cudaMalloc(&q, 64) != cudaSuccess) { cudaFree(h->d_P); delete h; *out = nullptr; return PLBA_E_CUDA; }
+    if (cudaMalloc(&q, 64) != cudaSuccess) return fail();
     h->d_scratch = (double *)q;
-    if (cudaMallocHost(&q, sizeof(DevP)) != cudaSuccess) { cudaFree(h->d_P); delete h; *out = nullptr; return PLBA_E_CUDA; }
+    if (cudaMallocHost(&q, sizeof(DevP)) != cudaSuccess) return fail();
     h->h_P = (DevP *)q;
-    if (cudaMallocHost(&q, sizeof(int) * CNT_N) != cudaSuccess) { cudaFree(h->d_P); cudaFreeHost(h->h_P); delete h; *out = nullptr; return PLBA_E_CUDA; }
+    if (cudaMallocHost(&q, sizeof(int) * CNT_N) != cudaSuccess) return fail();
     h->h_cnt = (int *)q;
+    cudaEventCreate(&h->ev_h2d);
     for (int i = 0; i < 8; i++) cudaEventCreate(&h->ev[i]);
     *out = h;
     return PLBA_OK;
@@ -300,6 +310,7 @@ void plba_destroy(plba_handle h) {
     if (h->h_P) cudaFreeHost(h->h_P);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
     for (int i = 0; i < 8; i++) cudaEventDestroy(h->ev[i]);
+    if (h->ev_h2d) cudaEventDestroy(h->ev_h2d);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -312,15 +323,26 @@ int plba_set_allreduce(plba_handle h, plba_allreduce_fn fn, void *user) { if (!h
 
 // ---- launch helpers ------------------------------------------------------------------------------------------
 static inline dim3 grid1(int n, int b) { return dim3((unsigned)std::max(1, (n + b - 1) / b)); }
+// function attributes and occupancy are PER DEVICE: one process may hold handles on several GPUs (plba_create_group), so the
+// "already done" flags and the occupancy caches are indexed by the current device (callers have done cudaSetDevice(h->device))
+enum { PLBA_MAX_DEV = 64 };
+static inline int cur_dev() {
+#ifndef PLBA_HOST_EMU
+    int d = 0; cudaGetDevice(&d); return (d >= 0 && d < PLBA_MAX_DEV) ? d : 0;
+#else
+    return 0;
+#endif
+}
 template <int PROF> static void set_smem_attr() {
 #ifndef PLBA_HOST_EMU
-    static bool done = false;
+    static bool done_dev[PLBA_MAX_DEV] = {false};
+    bool &done = done_dev[cur_dev()];
     if (!done) {
         cudaFuncSetAttribute(k_assemble<PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemMax<PROF>::bytes());
         cudaFuncSetAttribute(k_update<PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemMax<PROF>::bytes());
         cudaFuncSetAttribute(k_assemble_w<PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WARPS_PER_CTA * WSmemMax<PROF>::bytes()));
         cudaFuncSetAttribute(k_update_w<PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WARPS_PER_CTA * WSmemMax<PROF>::bytes()));
-        cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_small_smem(1));
+        cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_small_smem());
         cudaFuncSetAttribute(k_solve_banded, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_banded_smem());
         cudaFuncSetAttribute(k_bcr_elim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bcr_elim_smem());
         cudaFuncSetAttribute(k_bcr_back, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bcr_back_smem());
@@ -345,7 +367,8 @@ template <int PROF> static int chunk_occupancy() {
 #endif
 }
 static int chunk_occupancy_for(int prof) {
-    static int cache[3] = {0, 0, 0};
+    static int cache_dev[PLBA_MAX_DEV][3] = {{0}};
+    int *cache = cache_dev[cur_dev()];
     if (cache[prof]) return cache[prof];
     return cache[prof] = prof == PLBA_PROFILE_G ? chunk_occupancy<PLBA_PROFILE_G>() : prof == PLBA_PROFILE_H_END ? chunk_occupancy<PLBA_PROFILE_H_END>() : chunk_occupancy<PLBA_PROFILE_H_PLK>();
 }
@@ -362,8 +385,8 @@ template <int PROF> static int warp_occupancy(int update) {
 #endif
 }
 static int warp_occupancy_for(int prof, int update) {
-    static int cache[6] = {0, 0, 0, 0, 0, 0};
-    int &c = cache[2 * prof + update];
+    static int cache_dev[PLBA_MAX_DEV][6] = {{0}};
+    int &c = cache_dev[cur_dev()][2 * prof + update];
     if (c) return c;
     return c = prof == PLBA_PROFILE_G ? warp_occupancy<PLBA_PROFILE_G>(update) : prof == PLBA_PROFILE_H_END ? warp_occupancy<PLBA_PROFILE_H_END>(update) : warp_occupancy<PLBA_PROFILE_H_PLK>(update);
 }
@@ -432,9 +455,14 @@ static inline size_t bcr_exchange_doubles(const BcrW &B) { return (size_t)2 * B.
 static bool bcr_is_active(plba_handle h) { return !h->small_path && h->band_blocks <= BAND_MAX && !h->force_dense && h->large_solver == 0 && !h->bcr.empty(); }
 static void launch_solve(plba_handle h) {
     const DevP &P = h->P; const DevP *Pp = h->d_P;
-    if (P.n_free == 0) return;
+    if (P.n_free == 0) {
+        // every keyframe fixed: nothing to factor, but the hand LM's pre-solve controller (error normalisation, stop tests, apply decision)
+        // still runs, exactly as on the graph path where k_solve_small handles n == 0
+        if (P.profile != PLBA_PROFILE_G) { PLBA_LAUNCH(k_control_h_pre, grid1(P.n_win, 128), dim3(128), 0, h->stream, Pp); h->timing.n_launches++; }
+        return;
+    }
     if (h->small_path) {
-        PLBA_LAUNCH(k_solve_small, dim3(h->grid_solve), dim3(256), solve_small_smem(h->solve_class), h->stream, Pp);
+        PLBA_LAUNCH(k_solve_small, dim3(h->grid_solve), dim3(SS_NT), solve_small_smem(), h->stream, Pp);
         h->timing.n_launches++;
         return;
     }
@@ -545,7 +573,7 @@ template <int PROF> static int build_graph(plba_handle h) {
     CK(add_kernel(prep, &n2, n1, f_asm, gc, bc, smc, a_m0));
     CK(add_kernel(prep, &n3, n2, (void *)k_lambda_init, dim3(h->n_sm), dim3(128), 0, a_p));
     CK(add_kernel(body, &m1, inode, f_asm, gc, bc, smc, a_m1));
-    CK(add_kernel(body, &m2, m1, (void *)k_solve_small, dim3(h->grid_solve), dim3(256), solve_small_smem(h->solve_class), a_p));
+    CK(add_kernel(body, &m2, m1, (void *)k_solve_small, dim3(h->grid_solve), dim3(SS_NT), solve_small_smem(), a_p));
     CK(add_kernel(body, &m3, m2, f_upd, gu, bc, smc, a_fl));
 #ifdef PLBA_GRAPH_TWO_TRIALS
     // a second LM trial inside the same WHILE iteration: the loop's per-iteration cost (evaluating the condition, re-launching the
@@ -563,7 +591,7 @@ template <int PROF> static int build_graph(plba_handle h) {
         CK(add_kernel(prep2, &q2, q1, f_asm, gc, bc, smc, a_m0));
         CK(add_kernel(prep2, &q3, q2, (void *)k_lambda_init, dim3(h->n_sm), dim3(128), 0, a_p));
         CK(add_kernel(body, &r1, inode2, f_asm, gc, bc, smc, a_m1));
-        CK(add_kernel(body, &r2, r1, (void *)k_solve_small, dim3(h->grid_solve), dim3(256), solve_small_smem(h->solve_class), a_p));
+        CK(add_kernel(body, &r2, r1, (void *)k_solve_small, dim3(h->grid_solve), dim3(SS_NT), solve_small_smem(), a_p));
         CK(add_kernel(body, &r3, r2, f_upd, gu, bc, smc, a_fl));
     }
 #endif
@@ -597,6 +625,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     if (opt->profile < PLBA_PROFILE_G || opt->profile > PLBA_PROFILE_H_PLK) { h->err = "unknown profile"; return PLBA_E_ARG; }
     if (opt->shell != PLBA_SHELL_LBA && !(opt->shell == PLBA_SHELL_GBA && opt->profile == PLBA_PROFILE_H_END)) { h->err = "the GBA shell exists for profile H_END only"; return PLBA_E_ARG; }
     CK(cudaSetDevice(h->device));
+    if (h->h2d_pending) { CK(cudaEventSynchronize(h->ev_h2d)); h->h2d_pending = false; }   // the previous upload's H2D copies may still be reading h_in / h_P
     const auto t_host0 = std::chrono::steady_clock::now();
     auto t_hp = t_host0; const bool hostprof = std::getenv("PLBA_HOST_PROF") != nullptr;
 #define HOSTPROF(name) do { if (hostprof) { const auto t_ = std::chrono::steady_clock::now(); std::fprintf(stderr, "[upload] %-10s %.3f ms\n", name, std::chrono::duration<double, std::milli>(t_ - t_hp).count()); t_hp = t_; } } while (0)
@@ -624,9 +653,10 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     HOSTPROF("validate");
     h->max_nf = max_nf;
     h->small_path = (6 * max_nf <= SMALL_NMAX);
-    h->solve_class = solve_small_class(6 * max_nf);
-    // persistent solver grid: as many CTAs as fit (4 per SM in the small class); fixed per class so that the cached graph stays valid
-    h->grid_solve = h->n_sm * (h->solve_class == 0 ? 4 : 1);
+    // solver grid: ONE CTA for a single window (the drop-in call), one CTA per SM for a batch; the two cases are separate cached graphs
+    // ("solve class"), so that nothing inside a graph depends on the problem
+    h->solve_class = (n == 1) ? 0 : 1;
+    h->grid_solve = (n == 1) ? 1 : h->n_sm;
     set_all_attrs();
     h->grid_chunks = h->n_sm * chunk_occupancy_for(prof);
 #ifndef PLBA_HOST_EMU
@@ -997,6 +1027,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
         B.D = (double *)(db + s_bcr[4 * w]); B.U = B.D + nn; B.b = B.U + nn; B.hd = B.b + (size_t)B.N * B.m;
         B.Xl = (double *)(db + s_bcr[4 * w + 1]); B.Xr = (double *)(db + s_bcr[4 * w + 2]); B.y = (double *)(db + s_bcr[4 * w + 3]);
     }
+    P.solve_nf_max = std::min(max_nf, (int)SMALL_NMAX / 6);
     P.ctrl = (WinCtrl *)(db + h->o_ctrl); P.trace = (plba_trace_rec *)(db + h->o_trace); P.trace_cap = trace_cap; P.counters = (int *)(db + h->o_cnt);
     set_all_attrs();
 #ifndef PLBA_HOST_EMU
@@ -1012,6 +1043,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     CK(cudaMemcpyAsync(h->d_P, h->h_P, sizeof(DevP), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_arena, h->h_in, h->in_bytes, cudaMemcpyHostToDevice, h->stream));
     h->timing.h2d_bytes += (int64_t)(h->in_bytes + sizeof(DevP));
+    cudaEventRecord(h->ev_h2d, h->stream); h->h2d_pending = true;
     for (const BcrW &B : h->bcr) CK(cudaMemsetAsync(B.D, 0, sizeof(double) * bcr_exchange_doubles(B), h->stream));   // entries no kernel writes (upper triangles, the unused U of node 0) stay 0 in the exchange
     h->uploaded = true;
     return launch_reset(h);

@@ -99,7 +99,7 @@ struct DevP {
     double *accmax;                   // [n_win]         max-reduced: largest landmark diagonal (lambda init)
     WinCtrl *ctrl;
     const WinCtrl *ctrl0;             // initial controller state (reset)
-    plba_trace_rec *trace; int trace_cap, pad1;
+    plba_trace_rec *trace; int trace_cap, solve_nf_max;   // solve_nf_max: most free keyframes of any window of the upload (thread-group size of k_solve_small)
     int *counters;                    // [CNT_N]
     unsigned long long cond_while, cond_prep, cond_prep2;   // cudaGraphConditionalHandle of the LM-loop graph (prep2: the IF node of the second trial of an iteration)
 };

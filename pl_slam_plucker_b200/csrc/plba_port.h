@@ -59,6 +59,10 @@ PLBA_D void plba_block_add(double *smem_dst, double v) {
 #define LANE_VAR(T, name) T name
 #define LANE_ARR(T, name, N) T name[N]
 #define LANE_BIND(name)
+// thread-private values that live across the PHASE blocks of a CTA kernel (registers here, per-thread arrays in the host emulation)
+#define THR_VAR(T, name) T name
+#define THR_ARR(T, name, N) T name[N]
+#define THR_BIND(name)
 PLBA_D double plba_warp_sum(double v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
 PLBA_D double plba_warp_max(double v) { for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
 // every lane of the warp calls these (inside a WPHASE): the warp's lanes are summed and leave the SM as one red / atomicMax
@@ -137,6 +141,9 @@ inline void plba_block_add(double *d, double v) { *d += v; }
 #define LANE_VAR(T, name) T name##_L[32]
 #define LANE_ARR(T, name, N) T name##_L[32][N]
 #define LANE_BIND(name) auto &name = name##_L[lane]
+#define THR_VAR(T, name) T name##_T[1024]
+#define THR_ARR(T, name, N) T name##_T[1024][N]
+#define THR_BIND(name) auto &name = name##_T[tid]
 #define PLBA_WARP_FLUSH_ADD(ptr, v) do { *(ptr) += (v); } while (0)
 #define PLBA_WARP_FLUSH_MAX(ptr, v) do { if ((v) > *(ptr)) *(ptr) = (v); } while (0)
 inline void plba_sincos(double x, double *s, double *c) { *s = std::sin(x); *c = std::cos(x); }

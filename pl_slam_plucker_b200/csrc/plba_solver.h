@@ -16,10 +16,6 @@ namespace plba {
 
 enum { SMALL_NMAX = 144 };
 
-// shared memory of k_solve_small for reduced systems up to nmax unknowns; two size classes (<= 72 and <= 144) so that batches of
-// small windows (BASELINE config 3: n = 60) get four resident CTAs per SM instead of one
-static inline int solve_small_class(int n) { return n <= 72 ? 0 : 1; }
-static inline size_t solve_small_smem(int cls) { const size_t nmax = cls == 0 ? 72 : SMALL_NMAX; return sizeof(double) * ((nmax + 1) * (nmax + 1) + 2 * nmax + 24 + 16 + 6 * 264 + 21 * (nmax / 6)) + 64; }
 
 // Left-looking Cholesky of a symmetric positive definite matrix held as a LOWER triangle in shared memory (row stride ldm, odd),
 // in panels of one pose block (6 columns).  nd = dimension (multiple of 6); rows nd..nr (if any) are extra rows that ride along
@@ -127,109 +123,281 @@ for (int kb = 0; kb < nf; kb++) {
 }
 }
 
-PLBA_KERNEL void k_solve_small(const DevP *Pp) {
+// ---- k_solve_small: block Cholesky with the matrix in REGISTERS --------------------------------------------------------------
+// One thread per lower 6x6 block (bi >= bj) of the reduced camera system: the block stays in the thread's registers from the load
+// to the backward substitution, so the factorisation never re-writes a trailing matrix in shared memory.  Right-looking, one pose
+// block (6 columns) per panel, two block barriers per panel:
+//   A(k): the threads of block column k solve their block against L_kk (X = M L_kk^-T) and publish it in shared memory; the
+//         diagonal thread forwards the right-hand side it carries (y_k = L_kk^-1 g_k);
+//   B(k): every thread right of the panel applies M_ij -= X_i X_j^T (216 FMAs on registers, 72 shared-memory loads of which 36 are
+//         broadcasts); the diagonal threads also update their g_j; the diagonal thread of column k+1 factors its 6x6 block at once
+//         (look-ahead: L_{k+1,k+1} is ready when phase A(k+1) starts).
+// Threads are ordered by block column, so whole warps retire as the factorisation advances.  Backward substitution: one barrier per
+// block row, x_i solved redundantly by the threads of row i.  A thread group = 32 * ceil(pairs / 32) threads handles one window;
+// a 320-thread CTA holds floor(320 / group) windows (n = 60: 5 windows, n = 120: 1 window, n = 144: 300 blocks).
+// The kernel also runs the hand-LM pre-solve controller, consumes (clears) S, g, diag(H_pp) and applies the pose step.
+enum { SS_NT = 320, SS_XLD = 37 /* odd stride of a published 6x6 block */, SS_LALL = 27 /* L_kk (21) + 1 / diag (6) */ };
+PLBA_HD int ss_group_threads(int nf) { const int p = nf * (nf + 1) / 2; const int g = (p + 31) & ~31; return g < 32 ? 32 : g; }
+PLBA_HD int ss_group_doubles(int nf) { return nf * (SS_XLD + SS_LALL + 12) + 48; }       // X panel, factors, y, x, L_cur + 1/diag, reductions
+static inline size_t solve_small_smem(int = 0) { return (size_t)46 * 1024; }   // fixed (the LM-loop graph never depends on the problem); with the static parameter block it stays under the 48 KB that need no opt-in; worst case: 10 groups of nf = 7 = 46 656 bytes
+
+// Cholesky of a 6x6 lower triangle held row-major in a 6x6 register tile (entries r >= c); inv = 1 / diagonal of L
+PLBA_HD bool chol6_inplace(double *a, double *inv) {
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        double sd = a[j * 6 + j];
+        if (!(sd > 0.0) || !plba_isfinite(sd)) { bad = true; sd = 1.0; }
+        inv[j] = plba_rsqrt_hd(sd);
+        a[j * 6 + j] = sd * inv[j];
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) a[i * 6 + j] *= inv[j];
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) {
+#pragma unroll
+            for (int c = j + 1; c <= i; c++) a[i * 6 + c] -= a[i * 6 + j] * a[c * 6 + j];
+        }
+    }
+    return !bad;
+}
+
+PLBA_KERNEL void PLBA_BOUNDS(SS_NT, 1) k_solve_small(const DevP *Pp) {
     PLBA_SMEM(raw);
     PLBA_PARAMS(P, Pp);
     PROF_DECL;
-    for (int w = PLBA_BID; w < P.n_win; w += PLBA_NB) {
-        WinCtrl &ctl = P.ctrl[w];
-        const int nf = P.win_nfree[w], n = 6 * nf, slot0 = P.win_slot0[w], ldm = n + 1;     // n even => ldm odd: conflict-free columns
-        double *M = (double *)raw;                 // (n+1) x ldm lower triangle; row n = right-hand side
-        double *dinv = M + (size_t)(n + 1) * ldm, *xs = dinv + n, *Ls = xs + n, *red = Ls + 24;
-        int *flag = (int *)(red + 4);   // (red: 4 doubles, flag: 2 ints, then the partial-sum buffer)
-        (void)0;              // [0] skip, [1] fail
-        double *Sw = P.S + P.win_S_off[w];
+    const int nfmax = P.solve_nf_max > 0 ? P.solve_nf_max : 1;
+    const int G = ss_group_threads(nfmax), gpc = SS_NT / G, gd = ss_group_doubles(nfmax);
+    int *info = (int *)raw;                            // [gpc][4]: skip, nf, fail, -
+    double *gbase = (double *)(raw + 256);
+    THR_ARR(double, blk, 36); THR_ARR(double, gv, 6);
+    THR_VAR(int, bi); THR_VAR(int, bj); THR_VAR(int, act);
+    for (int w0 = PLBA_BID * gpc; w0 < P.n_win; w0 += PLBA_NB * gpc) {
         PHASE_BEGIN
-            if (tid == 0) {
-                if (!ctl.done && P.profile != PLBA_PROFILE_G) control_h_pre_window(P, w);
-                flag[0] = ctl.done; flag[1] = 0; red[0] = 0.0; red[1] = 0.0;
+            const int g = tid / G, t = tid - g * G, w = w0 + g;
+            if (t == 0 && g < gpc) {
+                int skip = 1, nf = 0;
+                if (w < P.n_win) {
+                    WinCtrl &ctl = P.ctrl[w];
+                    if (!ctl.done && P.profile != PLBA_PROFILE_G) control_h_pre_window(P, w);
+                    nf = P.win_nfree[w]; skip = (ctl.done || nf == 0) ? 1 : 0;
+                }
+                info[4 * g] = skip; info[4 * g + 1] = skip ? 0 : nf; info[4 * g + 2] = 0;
+                double *red = gbase + (size_t)g * gd + gd - 8;
+                red[0] = 0.0; red[1] = 0.0;
             }
         PHASE_END
-    PROF_MARK(41);
-        const int skip = flag[0];
+        int nfloop = 0;
+        for (int g = 0; g < gpc; g++) nfloop = info[4 * g + 1] > nfloop ? info[4 * g + 1] : nfloop;
         PHASE_BEGIN
         PHASE_END
+        if (nfloop == 0) continue;
     PROF_MARK(42);
-        if (skip || n == 0) continue;
-        const double lambda = ctl.lambda;
+        // ---- load: thread (bi, bj) <- lower block (bi, bj) = transpose of the stored upper block (bj, bi); S, g, diag(H_pp) are consumed ----
         PHASE_BEGIN
-            // upper triangle of S, one warp per row (coalesced), four loads in flight per thread; stored transposed as lower (cg,rg)
-            const int warp = tid >> 5, lane = tid & 31, nwarp = PLBA_NT >> 5;
-            for (int rg0 = warp; rg0 < n; rg0 += 4 * nwarp) {
-                double v[4][4];
+            THR_BIND(blk); THR_BIND(gv); THR_BIND(bi); THR_BIND(bj); THR_BIND(act);
+            const int g = tid / G, t = tid - g * G, w = w0 + g;
+            act = 0; bi = 0; bj = 0;
+            if (g < gpc && !info[4 * g]) {
+                const int nf = info[4 * g + 1];
+                int j = 0, rem = t;
+                while (j < nf && rem >= nf - j) { rem -= nf - j; j++; }
+                if (j < nf) {
+                    act = 1; bj = j; bi = j + rem;
+                    const int n = 6 * nf, slot0 = P.win_slot0[w];
+                    double *Sw = P.S + P.win_S_off[w];
+                    const double lambda = P.ctrl[w].lambda;
+    PROF_MARK(51);
 #pragma unroll
-                for (int rr = 0; rr < 4; rr++) {
-                    const int rg = rg0 + rr * nwarp;
+                    for (int c = 0; c < 6; c++) {
+                        double *row = Sw + (size_t)(6 * bj + c) * n + 6 * bi;
 #pragma unroll
-                    for (int u = 0; u < 4; u++) { const int cg = lane + 32 * u; v[rr][u] = (rg < n && cg >= rg && cg < n) ? Sw[(size_t)rg * n + cg] : 0.0; }
-                }
+                        for (int r = 0; r < 6; r++) blk[r * 6 + c] = row[r];
+                    }
+    if (blk[0] == 1.2345e300) blk[1] += 1.0;
+    PROF_MARK(52);
 #pragma unroll
-                for (int rr = 0; rr < 4; rr++) {
-                    const int rg = rg0 + rr * nwarp;
-                    if (rg >= n) continue;
-                    const double dmp = (P.profile == PLBA_PROFILE_G) ? lambda : lambda * P.hpp_diag[(size_t)6 * slot0 + rg];
+                    for (int c = 0; c < 6; c++) {
+                        double *row = Sw + (size_t)(6 * bj + c) * n + 6 * bi;
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int cg = lane + 32 * u;
-                        if (cg >= rg && cg < n) { Sw[(size_t)rg * n + cg] = 0.0; M[(size_t)cg * ldm + rg] = (cg == rg) ? v[rr][u] + dmp : v[rr][u]; }   // consumed: the next assembly accumulates into a clean S
+                        for (int r = 0; r < 6; r++) if (bi != bj || r >= c) row[r] = 0.0;      // consumed: the next assembly accumulates into a clean S
+                    }
+                    if (bi == bj) {
+                        double *gs = P.gs + (size_t)6 * slot0 + 6 * bj, *hd = P.hpp_diag + (size_t)6 * slot0 + 6 * bj;
+#pragma unroll
+                        for (int c = 0; c < 6; c++) {
+                            blk[c * 6 + c] += (P.profile == PLBA_PROFILE_G) ? lambda : lambda * hd[c];      // g2o setLambda: additive; hand LM: H_ii *= (1 + lambda)
+                            gv[c] = gs[c]; gs[c] = 0.0; hd[c] = 0.0;
+                        }
+    PROF_MARK(53);
+                        if (bj == 0) {      // look-ahead for the first panel
+                            double *Lc = gbase + (size_t)g * gd + nf * (SS_XLD + SS_LALL + 12);
+                            double inv[6];
+                            if (!chol6_inplace(blk, inv)) info[4 * g + 2] = 1;
+#pragma unroll
+                            for (int r = 0; r < 6; r++) {
+#pragma unroll
+                                for (int c = 0; c <= r; c++) Lc[r * (r + 1) / 2 + c] = blk[r * 6 + c];
+                            }
+#pragma unroll
+                            for (int c = 0; c < 6; c++) Lc[21 + c] = inv[c];
+                        }
                     }
                 }
             }
-            for (int rg = warp; rg < n && n > 128; rg += nwarp) {      // columns beyond 128 (n <= 144)
-                const int cg = 128 + lane;
-                if (cg < n && cg >= rg) { const double x = Sw[(size_t)rg * n + cg]; Sw[(size_t)rg * n + cg] = 0.0; M[(size_t)cg * ldm + rg] = (cg == rg) ? x + ((P.profile == PLBA_PROFILE_G) ? lambda : lambda * P.hpp_diag[(size_t)6 * slot0 + rg]) : x; }
-            }
-            for (int i = tid; i < n; i += PLBA_NT) { M[(size_t)n * ldm + i] = P.gs[(size_t)6 * slot0 + i]; P.gs[(size_t)6 * slot0 + i] = 0.0; }
         PHASE_END
     PROF_MARK(43);
-        PHASE_BEGIN
-            for (int i = tid; i < n; i += PLBA_NT) P.hpp_diag[(size_t)6 * slot0 + i] = 0.0;
-        PHASE_END
-    PROF_MARK(44);
-        double *part = Ls + 24 + 8;               // [nsplit][n+1][6] partial sums of phase U (nsplit * rows <= 256)
-        double *Lblk = part + 6 * 264;            // [nf][21] factored diagonal blocks (M keeps their un-factored values)
-        chol_lower_panels(M, ldm, n, n, dinv, Lblk, part, flag + 1);
-        // backward substitution L^T x = y, y = row n; column-oriented so that every step reads rows of L
-        for (int kb = nf - 1; kb >= 0; kb--) {
-            const int k0 = 6 * kb;
+        for (int kb = 0; kb < nfloop; kb++) {
+            // ---- A(kb): block column kb: X = M L_kk^-T, y_k = L_kk^-1 g_k ----
             PHASE_BEGIN
-                if (tid <= k0) {       // threads 0..k0-1 own y[j]; thread k0 (or 0 when k0 == 0) records x
-                    double x[6];
+                THR_BIND(blk); THR_BIND(gv); THR_BIND(bi); THR_BIND(bj); THR_BIND(act);
+                const int g = tid / G;
+                if (act && bj == kb) {
+                    const int nf = info[4 * g + 1];
+                    double *gb = gbase + (size_t)g * gd;
+                    double *Xp = gb, *Lall = gb + nf * SS_XLD, *ys = Lall + nf * SS_LALL, *Lc = ys + 12 * nf;
+                    double L[21], inv[6];
 #pragma unroll
-                    for (int c = 5; c >= 0; c--) {
-                        double v = M[(size_t)n * ldm + k0 + c];
+                    for (int i = 0; i < 21; i++) L[i] = Lc[i];
 #pragma unroll
-                        for (int m = c + 1; m < 6; m++) v -= Lblk[kb * 21 + m * (m + 1) / 2 + c] * x[m];
-                        x[c] = v * dinv[k0 + c];
-                    }
-                    if (tid < k0) {
-                        double y = M[(size_t)n * ldm + tid];
+                    for (int i = 0; i < 6; i++) inv[i] = Lc[21 + i];
+                    if (bi == kb) {
+                        double y[6];
 #pragma unroll
-                        for (int c = 0; c < 6; c++) y -= M[(size_t)(k0 + c) * ldm + tid] * x[c];
-                        M[(size_t)n * ldm + tid] = y;
+                        for (int c = 0; c < 6; c++) {
+                            double v = gv[c];
+#pragma unroll
+                            for (int m = 0; m < c; m++) v -= L[c * (c + 1) / 2 + m] * y[m];
+                            y[c] = v * inv[c];
+                        }
+#pragma unroll
+                        for (int c = 0; c < 6; c++) ys[6 * kb + c] = y[c];
+#pragma unroll
+                        for (int i = 0; i < 21; i++) Lall[kb * SS_LALL + i] = L[i];
+#pragma unroll
+                        for (int i = 0; i < 6; i++) Lall[kb * SS_LALL + 21 + i] = inv[i];
                     } else {
 #pragma unroll
-                        for (int c = 0; c < 6; c++) xs[k0 + c] = x[c];
+                        for (int r = 0; r < 6; r++) {
+                            double x[6];
+#pragma unroll
+                            for (int c = 0; c < 6; c++) {
+                                double v = blk[r * 6 + c];
+#pragma unroll
+                                for (int m = 0; m < c; m++) v -= x[m] * L[c * (c + 1) / 2 + m];
+                                x[c] = v * inv[c];
+                            }
+#pragma unroll
+                            for (int c = 0; c < 6; c++) { blk[r * 6 + c] = x[c]; Xp[bi * SS_XLD + r * 6 + c] = x[c]; }
+                        }
                     }
                 }
             PHASE_END
-    PROF_MARK(47);
+    PROF_MARK(44);
+            // ---- B(kb): trailing update on registers; look-ahead factorisation of the next diagonal block ----
+            PHASE_BEGIN
+                THR_BIND(blk); THR_BIND(gv); THR_BIND(bi); THR_BIND(bj); THR_BIND(act);
+                const int g = tid / G;
+                if (act && bj > kb) {
+                    const int nf = info[4 * g + 1];
+                    double *gb = gbase + (size_t)g * gd;
+                    const double *Xp = gb, *ys = gb + nf * (SS_XLD + SS_LALL);
+                    double Xj[36];
+#pragma unroll
+                    for (int i = 0; i < 36; i++) Xj[i] = Xp[bj * SS_XLD + i];
+#pragma unroll
+                    for (int r = 0; r < 6; r++) {
+                        double xi[6];
+#pragma unroll
+                        for (int m = 0; m < 6; m++) xi[m] = Xp[bi * SS_XLD + r * 6 + m];
+#pragma unroll
+                        for (int c = 0; c < 6; c++) {
+                            double v = blk[r * 6 + c];
+#pragma unroll
+                            for (int m = 0; m < 6; m++) v -= xi[m] * Xj[c * 6 + m];
+                            blk[r * 6 + c] = v;
+                        }
+                    }
+                    if (bi == bj) {
+#pragma unroll
+                        for (int r = 0; r < 6; r++) {
+                            double v = gv[r];
+#pragma unroll
+                            for (int m = 0; m < 6; m++) v -= Xj[r * 6 + m] * ys[6 * kb + m];
+                            gv[r] = v;
+                        }
+                        if (bj == kb + 1) {
+                            double *Lc = gb + nf * (SS_XLD + SS_LALL + 12);
+                            double inv[6];
+                            if (!chol6_inplace(blk, inv)) info[4 * g + 2] = 1;
+#pragma unroll
+                            for (int r = 0; r < 6; r++) {
+#pragma unroll
+                                for (int c = 0; c <= r; c++) Lc[r * (r + 1) / 2 + c] = blk[r * 6 + c];
+                            }
+#pragma unroll
+                            for (int c = 0; c < 6; c++) Lc[21 + c] = inv[c];
+                        }
+                    }
+                }
+            PHASE_END
+    PROF_MARK(45);
         }
+    PROF_MARK(46);
+        // ---- backward substitution L^T x = y: block row i at a time, x_i solved redundantly by the threads of the row ----
+        for (int i = nfloop - 1; i >= 0; i--) {
+            PHASE_BEGIN
+                THR_BIND(blk); THR_BIND(bi); THR_BIND(bj); THR_BIND(act);
+                const int g = tid / G;
+                if (act && bi == i) {
+                    const int nf = info[4 * g + 1];
+                    double *gb = gbase + (size_t)g * gd;
+                    const double *Lall = gb + nf * SS_XLD;
+                    double *ys = gb + nf * (SS_XLD + SS_LALL), *xs = ys + 6 * nf;
+                    double x[6];
+#pragma unroll
+                    for (int c = 5; c >= 0; c--) {
+                        double v = ys[6 * i + c];
+#pragma unroll
+                        for (int m = c + 1; m < 6; m++) v -= Lall[i * SS_LALL + m * (m + 1) / 2 + c] * x[m];
+                        x[c] = v * Lall[i * SS_LALL + 21 + c];
+                    }
+                    if (bj == i) {
+#pragma unroll
+                        for (int c = 0; c < 6; c++) xs[6 * i + c] = x[c];
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 6; c++) {
+                            double v = ys[6 * bj + c];
+#pragma unroll
+                            for (int r = 0; r < 6; r++) v -= blk[r * 6 + c] * x[r];
+                            ys[6 * bj + c] = v;
+                        }
+                    }
+                }
+            PHASE_END
+        }
+    PROF_MARK(47);
         PHASE_BEGIN
-            const int f = flag[1];
-            for (int i = tid; i < n; i += PLBA_NT) P.xp[(size_t)6 * slot0 + i] = f ? 0.0 : xs[i];
-            if (tid == 0 && f) ctl.solve_fail = 1;
+            const int g = tid / G, t = tid - g * G, w = w0 + g;
+            if (g < gpc && !info[4 * g]) {
+                const int nf = info[4 * g + 1], f = info[4 * g + 2], slot0 = P.win_slot0[w];
+                const double *xs = gbase + (size_t)g * gd + nf * (SS_XLD + SS_LALL) + 6 * nf;
+                for (int i = t; i < 6 * nf; i += G) P.xp[(size_t)6 * slot0 + i] = f ? 0.0 : xs[i];
+                if (t == 0 && f) P.ctrl[w].solve_fail = 1;
+            }
         PHASE_END
-    PROF_MARK(48);
         PHASE_BEGIN
+            const int g = tid / G, t = tid - g * G, w = w0 + g;
             double sc = 0.0, d2 = 0.0;
-            if (tid < nf) pose_update_slot(P, slot0 + tid, sc, d2);
-            plba_block_add(&red[0], sc);
-            plba_block_add(&red[1], d2);
+            const bool on = (g < gpc && !info[4 * g]);
+            if (on && t < info[4 * g + 1]) pose_update_slot(P, P.win_slot0[w] + t, sc, d2);
+            double *red = gbase + (size_t)(g < gpc ? g : 0) * gd + gd - 8;
+            plba_block_add(&red[0], on ? sc : 0.0);
+            plba_block_add(&red[1], on ? d2 : 0.0);
         PHASE_END
-    PROF_MARK(49);
         PHASE_BEGIN
-            if (tid == 0) { ctl.scale_pose = red[0]; ctl.dx2_pose = red[1]; }
+            const int g = tid / G, t = tid - g * G, w = w0 + g;
+            if (t == 0 && g < gpc && !info[4 * g]) { const double *red = gbase + (size_t)g * gd + gd - 8; P.ctrl[w].scale_pose = red[0]; P.ctrl[w].dx2_pose = red[1]; }
         PHASE_END
     PROF_MARK(50);
     }

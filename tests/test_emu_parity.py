@@ -30,3 +30,5 @@ test_both_kernel_paths = g.test_both_kernel_paths
 test_randomised_window_shapes = g.test_randomised_window_shapes
 test_map_handler_interface = g.test_map_handler_interface
 test_randomised_large_windows = g.test_randomised_large_windows
+test_all_keyframes_fixed_hand_lm = g.test_all_keyframes_fixed_hand_lm
+test_randomised_large_windows_g_faithful = g.test_randomised_large_windows_g_faithful

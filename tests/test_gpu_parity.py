@@ -282,17 +282,20 @@ def test_map_handler_interface(gpu_solver, oracle):
 
 
 def test_config3_full_batch(gpu_solver, oracle):
-    """BASELINE config 3 at full size: 1024 independent 10-KF windows in ONE call; sampled windows against the oracle,
-    all windows against batch-wide invariants."""
+    """BASELINE config 3 at full size: 1024 independent 10-KF windows in ONE call; EVERY window against the oracle, and all
+    windows against batch-wide invariants."""
     probs = scene.make_batch(1024, 3)
     opt = abi.Options(abi.PROFILE_G, 0)
     rc, rs = gpu_solver.solve_batch(probs, opt)
     assert rc == abi.OK
     assert gpu_solver.timing()["n_trials_run"] == sum(r.n_trials for r in rs)
-    for w in (0, 1, 511, 1023):
-        o = oracle.solve(probs[w], opt)
-        assert_trace_close(o.trace, rs[w].trace, abi.PROFILE_G)
-        assert_state_close(o, rs[w], probs[w], abi.PROFILE_G)
+    # every one of the 1 024 windows against the oracle (the oracle's batch call is OpenMP-parallel over windows)
+    oracle.set_threads(os.cpu_count() or 1)
+    orc_rc, os_ = oracle.solve_batch(probs, opt)
+    assert orc_rc == abi.OK and len(os_) == len(rs)
+    for P, r, o in zip(probs, rs, os_):
+        assert_trace_close(o.trace, r.trace, abi.PROFILE_G)
+        assert_state_close(o, r, P, abi.PROFILE_G)
     for P, r in zip(probs, rs):
         assert r.rc == abi.OK and 15 <= r.n_trials <= 150
         tr = r.trace
@@ -302,6 +305,104 @@ def test_config3_full_batch(gpu_solver, oracle):
         fixed = P.kf_slot < 0
         np.testing.assert_array_equal(r.kf_T_wc[fixed], P.kf_T_wc[fixed])
         assert np.isfinite(r.pt_xyz).all() and np.isfinite(r.ls_orth).all()
+
+
+@pytest.mark.parametrize("q", [0, 1], ids=["faithful", "fixed"])
+def test_config4_full_size_against_oracle(gpu_solver, oracle, q):
+    """BASELINE config 4 at full size (200 free KFs, 200k points, 50k lines, 1.15 M observations), the FULL profile-G schedule
+    (5 + 10 outer iterations with the chi2 gate between them, src/mapHandler.cpp:5851-6323), both quirk modes: per-trial cost 1e-9,
+    final state 1e-8, gating flags as in every other parity test.  Runs on the warp kernels + block cyclic reduction."""
+    P = scene.make_scene(4)
+    oracle.set_threads(os.cpu_count() or 1)
+    r, o, n = _check(gpu_solver, oracle, P, abi.PROFILE_G, q)
+    assert n >= 15 and len(r.trace) == len(o.trace)
+    kp = gpu_solver.kernel_path()
+    assert kp["assembly"] == "warp" and kp["solver"] == "block-cyclic-reduction"
+
+
+@pytest.mark.parametrize("q", [0, 1], ids=["faithful", "fixed"])
+def test_config5_full_size_against_oracle(gpu_solver, oracle, q):
+    """BASELINE config 5 at full size (2 000 free KFs, 2 M points, 500 k lines, 12.5 M observations): 3 + 2 outer iterations
+    (>= 5, with the chi2 gate between the stages) against the oracle's skyline LDL^T on the 12 000-unknown band, both quirk modes."""
+    P = scene.make_scene(5)
+    oracle.set_threads(os.cpu_count() or 1)
+    opt = abi.Options(abi.PROFILE_G, q, iters_stage1=3, iters_stage2=2)
+    r, o = gpu_solver.solve(P, opt), oracle.solve(P, opt)
+    assert r.rc == o.rc == abi.OK and gpu_solver.timing()["n_launches"] > 0
+    n = assert_trace_close(o.trace, r.trace, abi.PROFILE_G)
+    assert n >= 5 and len(r.trace) == len(o.trace)
+    assert_state_close(o, r, P, abi.PROFILE_G)
+    assert gpu_solver.kernel_path()["assembly"] == "warp"
+
+
+def test_graph_equals_host_driven_loop(oracle):
+    """Small windows run the whole LM schedule as ONE CUDA graph (device-side controller steering WHILE / IF nodes); large windows,
+    the sharded exchange and per-stage timing run a host-driven loop over the SAME kernels.  Both must give identical results:
+    same trace records and bit-identical decisions; values to rounding (the atomics order differs from run to run)."""
+    from pl_slam_plucker_b200 import solver
+    s = solver.LBASolver(0)
+    try:
+        for prof, q, kw in ((abi.PROFILE_G, 0, dict(n_kf_free=8, n_kf_fixed=2, n_pt=500, n_ls=120, seed=41)), (abi.PROFILE_G, 1, dict()),
+                            (abi.PROFILE_H_END, 0, dict(n_kf_free=6, n_kf_fixed=2, n_pt=300, n_ls=80, seed=42)),
+                            (abi.PROFILE_H_PLK, 1, dict(n_kf_free=6, n_kf_fixed=2, n_pt=300, n_ls=80, seed=43))):
+            P = _scene(1, prof, **kw)
+            opt = abi.Options(prof, q)
+            s.set_detail_timing(False)
+            a = s.solve(P, opt); ta = s.timing()
+            s.set_detail_timing(True)                       # forces the host-driven loop (plba_api.cu use_graph())
+            b = s.solve(P, opt); tb = s.timing()
+            s.set_detail_timing(False)
+            assert ta["n_trials_run"] == tb["n_trials_run"] and tb["ms_assemble"] > 0 and ta["ms_assemble"] == 0
+            assert len(a.trace) == len(b.trace)
+            for k in ("stage", "iter", "trial", "accepted", "stop"):
+                assert (a.trace[k] == b.trace[k]).all(), k
+            for k in ("chi", "chi_new", "lambda", "dx_norm"):
+                fin = np.isfinite(a.trace[k])
+                np.testing.assert_allclose(b.trace[k][fin], a.trace[k][fin], rtol=1e-10, atol=1e-300)
+            assert_state_close(a, b, P, prof, atol=1e-9)
+            o = oracle.solve(P, opt)
+            assert_state_close(o, b, P, prof)
+    finally:
+        s.close()
+
+
+def test_all_keyframes_fixed_hand_lm(gpu_solver, oracle):
+    """A hand-LM window whose observers are all fixed (n_free == 0): the pre-solve controller must still run on the host-driven loop
+    exactly as inside the graph (same number of iterations as the oracle)."""
+    base = scene.make_scene(1, n_kf_free=3, n_kf_fixed=1, n_pt=40, n_ls=10, seed=21)
+    P = abi.Problem(base.cam, base.kf_T_wc, np.full(base.n_kf, -1, np.int32), base.pt_xyz, base.po_lm, base.po_kf, base.po_uv, ls_plk=base.ls_plk,
+                    lo_lm=base.lo_lm, lo_kf=base.lo_kf, lo_ab=base.lo_ab, x_pose=np.zeros((0, 6)))
+    opt = abi.Options(abi.PROFILE_H_PLK, 1)
+    o = oracle.solve(P, opt)
+    try:
+        for host_loop in (False, True):
+            gpu_solver.set_detail_timing(host_loop)      # True forces the host-driven loop (plba_api.cu use_graph())
+            r = gpu_solver.solve(P, opt)
+            assert len(r.trace) == len(o.trace)
+            assert_trace_close(o.trace, r.trace, abi.PROFILE_H_PLK)
+            assert_state_close(o, r, P, abi.PROFILE_H_PLK)
+    finally:
+        gpu_solver.set_detail_timing(False)
+
+
+def test_two_handles_on_different_devices_in_one_process(oracle):
+    """Function attributes (> 48 KB dynamic shared memory) and occupancy are per device: a handle created on a second GPU after one
+    on the first must work too (needs 2 GPUs)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from pl_slam_plucker_b200 import solver
+    P = scene.make_scene(1, n_kf_free=30, n_kf_fixed=2, n_pt=600, n_ls=150, seed=7)      # > 144 unknowns: block cyclic reduction (opt-in shared memory)
+    opt = abi.Options(abi.PROFILE_G, 1)
+    o = oracle.solve(P, opt)
+    s0, s1 = solver.LBASolver(0), solver.LBASolver(1)
+    try:
+        for s in (s0, s1, s0):
+            r = s.solve(P, opt)
+            assert_trace_close(o.trace, r.trace, abi.PROFILE_G)
+            assert_state_close(o, r, P, abi.PROFILE_G)
+    finally:
+        s0.close(); s1.close()
 
 
 def test_config5_full_size_properties(gpu_solver):
@@ -399,10 +500,33 @@ def _random_large_case(i):
               mean_track=float(rng.uniform(3.5, 9.0)), seed=int(rng.integers(1, 10 ** 6)))
     if rng.random() < 0.25:
         kw["loop_every"] = int(rng.integers(18, 24))
-    # profile G in its FIXED mode only: on a 25-70 keyframe chain the FAITHFUL line Jacobian (Q12) makes the damped system ill-conditioned
-    # enough that the dense and the block-cyclic factorisations both drift 1e-8 from the oracle after a few trials (same drift: conditioning)
     prof, q = [(abi.PROFILE_G, 1), (abi.PROFILE_H_END, 0), (abi.PROFILE_H_END, 1), (abi.PROFILE_H_PLK, 1)][int(rng.integers(0, 4))]
     return kw, prof, q, int(rng.integers(1, 3))
+
+
+# Profile G FAITHFUL (the mode the reference and the bench actually run) on 25-70 keyframe chains.  The wrong-but-deterministic line
+# Jacobian (Q12) makes some damped systems transiently ill-conditioned: on draw 6 the ORACLE'S OWN two solve paths (landmark Schur +
+# skyline LDL^T against the literal dense full-system LDL^T) differ by 6e-9 in the per-trial cost from trial 4 on and by 8e-10 in the
+# final state (tools/parity_report.py) — that is the reference arithmetic's own conditioning, no implementation can agree
+# with it more closely.  Measured on the GPU over the 12 draws: per-trial cost within 1.5e-8 (10 of 12 draws within 1e-9), final
+# state within 2.7e-9, flags identical.  Asserted: state at the BASELINE tolerance 1e-8, per-trial cost at 1e-7, decisions bit-exact.
+G_FAITHFUL_LARGE_COST_RTOL = 1e-7
+
+
+@pytest.mark.parametrize("i", range(12))
+def test_randomised_large_windows_g_faithful(gpu_solver, oracle, i):
+    kw, _, _, path = _random_large_case(i)
+    P = _scene(1, abi.PROFILE_G, **kw)
+    gpu_solver.set_kernel_path(path)
+    try:
+        opt = abi.Options(abi.PROFILE_G, 0)
+        r, o = gpu_solver.solve(P, opt), oracle.solve(P, opt)
+        assert r.rc == o.rc
+        assert_trace_close(o.trace, r.trace, abi.PROFILE_G, cost_rtol=G_FAITHFUL_LARGE_COST_RTOL)
+        assert_state_close(o, r, P, abi.PROFILE_G, chi2_rtol=1e-4)      # per-observation chi2: a state deviation of 3e-9 is 5e-6 relative on a small residual
+        assert gpu_solver.kernel_path()["solver"] != "shared-memory"
+    finally:
+        gpu_solver.set_kernel_path(0)
 
 
 @pytest.mark.parametrize("i", range(12))

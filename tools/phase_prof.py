@@ -6,7 +6,7 @@ lib = _lib.load(os.path.join(os.path.dirname(_lib.library_path()), "libplba_prof
 s = solver.LBASolver(0, lib=lib)
 NAMES = {1: "asm precompute", 2: "asm linearize", 3: "asm per-landmark", 4: "asm Ta", 5: "asm offdiag tasks", 6: "asm diag tasks",
          21: "upd precompute", 22: "upd linearize+U", 23: "upd per-landmark", 24: "upd orth->plk", 25: "upd new cost", 26: "upd tail",
-         41: "sol pre", 42: "sol barrier", 43: "sol load", 44: "sol zero", 45: "sol left-looking update (U)", 46: "sol factor+rowsolve (A)", 51: "sol fold partials", 47: "sol backward", 48: "sol write", 49: "sol pose", 50: "sol tail"}
+         42: "sol control", 43: "sol load + first factor", 44: "sol A: column solve", 45: "sol B: trailing update + look-ahead factor", 46: "sol (loop exit)", 47: "sol backward", 50: "sol write + pose"}
 for cfg in [int(a) for a in sys.argv[1:]] or [2]:
     P = scene.make_scene(cfg)
     s.upload(P, abi.Options(abi.PROFILE_G, 1))
