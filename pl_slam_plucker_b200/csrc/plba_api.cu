@@ -1028,6 +1028,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
         B.Xl = (double *)(db + s_bcr[4 * w + 1]); B.Xr = (double *)(db + s_bcr[4 * w + 2]); B.y = (double *)(db + s_bcr[4 * w + 3]);
     }
     P.solve_nf_max = std::min(max_nf, (int)SMALL_NMAX / 6);
+    P.S_clear_doubles = h->small_path ? (long long)((h->S_doubles + 1) & ~(size_t)1) : 0;      // (the buffer continues with g: an odd tail would only clear g[0], which the solver has consumed too; S_doubles is even anyway)
     P.ctrl = (WinCtrl *)(db + h->o_ctrl); P.trace = (plba_trace_rec *)(db + h->o_trace); P.trace_cap = trace_cap; P.counters = (int *)(db + h->o_cnt);
     set_all_attrs();
 #ifndef PLBA_HOST_EMU

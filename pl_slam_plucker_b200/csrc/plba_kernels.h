@@ -101,6 +101,7 @@ struct DevP {
     const WinCtrl *ctrl0;             // initial controller state (reset)
     plba_trace_rec *trace; int trace_cap, solve_nf_max;   // solve_nf_max: most free keyframes of any window of the upload (thread-group size of k_solve_small)
     int *counters;                    // [CNT_N]
+    long long S_clear_doubles;        // small-window path: doubles of S the update kernel clears (the solver consumed them); 0 = the solver path clears S itself
     unsigned long long cond_while, cond_prep, cond_prep2;   // cudaGraphConditionalHandle of the LM-loop graph (prep2: the IF node of the second trial of an iteration)
 };
 
@@ -887,10 +888,23 @@ PLBA_D void round_epilogue(const DevP &P, int flags) {
     }
 }
 
+// The reduced camera system of small windows is consumed by k_solve_small (one CTA per window) but cleared HERE, by every CTA of the
+// update kernel that runs next: clearing 115 KB (config 2) with the store path of the solver's single SM costs ~4 000 cycles of the
+// latency-critical kernel (measured), spread over the grid it is free.  Coalesced 128-bit stores.
+PLBA_D void clear_consumed_S(const DevP &P) {
+    PHASE_BEGIN
+        const long long n2 = P.S_clear_doubles / 2;
+        plba_d2 *Sz = (plba_d2 *)P.S;
+        const plba_d2 z = {0.0, 0.0};
+        for (long long i = (long long)PLBA_BID * PLBA_NT + tid; i < n2; i += (long long)PLBA_NB * PLBA_NT) Sz[i] = z;
+    PHASE_END
+}
+
 template <int PROF>
 PLBA_KERNEL void PLBA_BOUNDS(OC, PLBA_CTAS_PER_SM) k_update(const DevP *Pp, int flags) {
     PLBA_SMEM(raw);
     PLBA_PARAMS(P, Pp);
+    if (P.S_clear_doubles) clear_consumed_S(P);
     const int ntot = P.n_chunks_pt + P.n_chunks_ls;
     for (int c = PLBA_BID; c < ntot; c += PLBA_NB) {
         if (c < P.n_chunks_pt) { const Chunk ch = P.chunks_pt[c]; update_chunk<PROF, LT_POINT>(P, ch); }

@@ -96,6 +96,29 @@ PLBA_D int plba_ld_l2(const int *p) { return __ldcg(p); }
 PLBA_D void plba_fence() { __threadfence(); }
 PLBA_D int plba_atomic_fetch_add_i(int *p, int v) { return atomicAdd(p, v); }
 PLBA_D double plba_rsqrt(double x) { return rsqrt(x); }   // (an FP32-seeded Newton variant measured slower: profiles/README.md)
+// Reciprocal / reciprocal square root for LATENCY-bound dependency chains (the 6x6 pivots of k_solve_small): hardware seed (2^-23) plus
+// two Newton steps, no special-case branches: 5 / 7 dependent operations instead of the ~10 of the IEEE-rounded library routines.
+// Faithful to about one ulp for normal, positive arguments (callers have already rejected non-positive or non-finite pivots).
+PLBA_HD double plba_rcp_fast(double d) {
+#if defined(__CUDA_ARCH__)
+    double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0); r = fma(r, e, r);
+    e = fma(-d, r, 1.0); r = fma(r, e, r);
+    return r;
+#else
+    return 1.0 / d;
+#endif
+}
+PLBA_HD double plba_rsqrt_fast(double x) {
+#if defined(__CUDA_ARCH__)
+    double y; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double t = y * y, e = fma(-x, t, 1.0); y = fma(0.5 * y, e, y);
+    t = y * y; e = fma(-x, t, 1.0); y = fma(0.5 * y, e, y);
+    return y;
+#else
+    return 1.0 / std::sqrt(x);
+#endif
+}
 // WHILE / IF nodes of the LM-loop graph are steered from the controller (cudaGraphSetConditional is a device runtime builtin)
 PLBA_D void plba_graph_set(unsigned long long handle, unsigned int v) { cudaGraphSetConditional((cudaGraphConditionalHandle)handle, v); }
 #else
@@ -157,6 +180,8 @@ inline int plba_ld_l2(const int *p) { return *p; }
 inline void plba_fence() {}
 inline int plba_atomic_fetch_add_i(int *p, int v) { int o = *p; *p += v; return o; }
 inline double plba_rsqrt(double x) { return 1.0 / std::sqrt(x); }
+inline double plba_rcp_fast(double d) { return 1.0 / d; }
+inline double plba_rsqrt_fast(double x) { return 1.0 / std::sqrt(x); }
 inline void plba_graph_set(unsigned long long, unsigned int) {}
 // minimal CUDA runtime stand-ins
 typedef int cudaError_t; typedef void *cudaStream_t; typedef void *cudaEvent_t;

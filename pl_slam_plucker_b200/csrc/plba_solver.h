@@ -135,28 +135,39 @@ for (int kb = 0; kb < nf; kb++) {
 // Threads are ordered by block column, so whole warps retire as the factorisation advances.  Backward substitution: one barrier per
 // block row, x_i solved redundantly by the threads of row i.  A thread group = 32 * ceil(pairs / 32) threads handles one window;
 // a 320-thread CTA holds floor(320 / group) windows (n = 60: 5 windows, n = 120: 1 window, n = 144: 300 blocks).
-// The kernel also runs the hand-LM pre-solve controller, consumes (clears) S, g, diag(H_pp) and applies the pose step.
+// The kernel also runs the hand-LM pre-solve controller, consumes S (cleared by the next update kernel), clears g and diag(H_pp) and
+// applies the pose step.
 enum { SS_NT = 320, SS_XLD = 37 /* odd stride of a published 6x6 block */, SS_LALL = 27 /* L_kk (21) + 1 / diag (6) */ };
-PLBA_HD int ss_group_threads(int nf) { const int p = nf * (nf + 1) / 2; const int g = (p + 31) & ~31; return g < 32 ? 32 : g; }
+PLBA_HD int ss_group_threads(int nf) { const int off = nf * (nf - 1) / 2; return 32 + ((off > 0 ? off + 31 : 32) & ~31); }   // warp 0: diagonal blocks; then the strictly lower blocks by column
 PLBA_HD int ss_group_doubles(int nf) { return nf * (SS_XLD + SS_LALL + 12) + 48; }       // X panel, factors, y, x, L_cur + 1/diag, reductions
 static inline size_t solve_small_smem(int = 0) { return (size_t)46 * 1024; }   // fixed (the LM-loop graph never depends on the problem); with the static parameter block it stays under the 48 KB that need no opt-in; worst case: 10 groups of nf = 7 = 46 656 bytes
 
-// Cholesky of a 6x6 lower triangle held row-major in a 6x6 register tile (entries r >= c); inv = 1 / diagonal of L
+// Cholesky of a 6x6 lower triangle held row-major in a 6x6 register tile (entries r >= c); inv = 1 / diagonal of L.
+// The factorisation is a chain of six dependent pivots and FP64 operations have ~20 cycles of dependent-issue latency on sm_100a, so
+// the chain is what a panel of k_solve_small waits for.  It is therefore run in the LDL^T form: per pivot one fast reciprocal (5
+// operations), one multiply and one FMA are on the chain; the square roots that turn L D L^T into L L^T are taken off the chain.
 PLBA_HD bool chol6_inplace(double *a, double *inv) {
     bool bad = false;
+    double d[6];
 #pragma unroll
     for (int j = 0; j < 6; j++) {
         double sd = a[j * 6 + j];
         if (!(sd > 0.0) || !plba_isfinite(sd)) { bad = true; sd = 1.0; }
-        inv[j] = plba_rsqrt_hd(sd);
-        a[j * 6 + j] = sd * inv[j];
-#pragma unroll
-        for (int i = j + 1; i < 6; i++) a[i * 6 + j] *= inv[j];
+        d[j] = sd;
+        const double r = plba_rcp_fast(sd);
 #pragma unroll
         for (int i = j + 1; i < 6; i++) {
+            const double q = a[i * 6 + j] * r;
 #pragma unroll
-            for (int c = j + 1; c <= i; c++) a[i * 6 + c] -= a[i * 6 + j] * a[c * 6 + j];
+            for (int c = j + 1; c <= i; c++) a[i * 6 + c] -= q * a[c * 6 + j];
         }
+    }
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        inv[j] = plba_rsqrt_fast(d[j]);
+        a[j * 6 + j] = d[j] * inv[j];
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) a[i * 6 + j] *= inv[j];
     }
     return !bad;
 }
@@ -199,27 +210,20 @@ PLBA_KERNEL void PLBA_BOUNDS(SS_NT, 1) k_solve_small(const DevP *Pp) {
             act = 0; bi = 0; bj = 0;
             if (g < gpc && !info[4 * g]) {
                 const int nf = info[4 * g + 1];
-                int j = 0, rem = t;
-                while (j < nf && rem >= nf - j) { rem -= nf - j; j++; }
+                int j = nf, rem = 0;
+                if (t < 32) { if (t < nf) { j = t; rem = 0; } }                 // warp 0 of the group: the diagonal blocks
+                else { j = 0; rem = t - 32; while (j < nf - 1 && rem >= nf - 1 - j) { rem -= nf - 1 - j; j++; } if (j >= nf - 1) j = nf; else rem += 1; }
                 if (j < nf) {
                     act = 1; bj = j; bi = j + rem;
                     const int n = 6 * nf, slot0 = P.win_slot0[w];
                     double *Sw = P.S + P.win_S_off[w];
                     const double lambda = P.ctrl[w].lambda;
-    PROF_MARK(51);
+                    // 128-bit loads (rows of S are 16-byte aligned: n and 6 bi are even); S is cleared by the update kernel that runs next (clear_consumed_S)
 #pragma unroll
                     for (int c = 0; c < 6; c++) {
-                        double *row = Sw + (size_t)(6 * bj + c) * n + 6 * bi;
+                        const plba_d2 *row = (const plba_d2 *)(Sw + (size_t)(6 * bj + c) * n + 6 * bi);
 #pragma unroll
-                        for (int r = 0; r < 6; r++) blk[r * 6 + c] = row[r];
-                    }
-    if (blk[0] == 1.2345e300) blk[1] += 1.0;
-    PROF_MARK(52);
-#pragma unroll
-                    for (int c = 0; c < 6; c++) {
-                        double *row = Sw + (size_t)(6 * bj + c) * n + 6 * bi;
-#pragma unroll
-                        for (int r = 0; r < 6; r++) if (bi != bj || r >= c) row[r] = 0.0;      // consumed: the next assembly accumulates into a clean S
+                        for (int r2 = 0; r2 < 3; r2++) { const plba_d2 v = row[r2]; blk[(2 * r2) * 6 + c] = v.x; blk[(2 * r2 + 1) * 6 + c] = v.y; }
                     }
                     if (bi == bj) {
                         double *gs = P.gs + (size_t)6 * slot0 + 6 * bj, *hd = P.hpp_diag + (size_t)6 * slot0 + 6 * bj;
@@ -228,7 +232,6 @@ PLBA_KERNEL void PLBA_BOUNDS(SS_NT, 1) k_solve_small(const DevP *Pp) {
                             blk[c * 6 + c] += (P.profile == PLBA_PROFILE_G) ? lambda : lambda * hd[c];      // g2o setLambda: additive; hand LM: H_ii *= (1 + lambda)
                             gv[c] = gs[c]; gs[c] = 0.0; hd[c] = 0.0;
                         }
-    PROF_MARK(53);
                         if (bj == 0) {      // look-ahead for the first panel
                             double *Lc = gbase + (size_t)g * gd + nf * (SS_XLD + SS_LALL + 12);
                             double inv[6];
@@ -263,11 +266,12 @@ PLBA_KERNEL void PLBA_BOUNDS(SS_NT, 1) k_solve_small(const DevP *Pp) {
                     if (bi == kb) {
                         double y[6];
 #pragma unroll
-                        for (int c = 0; c < 6; c++) {
-                            double v = gv[c];
+                        for (int c = 0; c < 6; c++) y[c] = gv[c];
 #pragma unroll
-                            for (int m = 0; m < c; m++) v -= L[c * (c + 1) / 2 + m] * y[m];
-                            y[c] = v * inv[c];
+                        for (int c = 0; c < 6; c++) {         // column sweeps: two dependent operations per pivot
+                            y[c] *= inv[c];
+#pragma unroll
+                            for (int m = c + 1; m < 6; m++) y[m] -= L[m * (m + 1) / 2 + c] * y[c];
                         }
 #pragma unroll
                         for (int c = 0; c < 6; c++) ys[6 * kb + c] = y[c];
@@ -277,18 +281,17 @@ PLBA_KERNEL void PLBA_BOUNDS(SS_NT, 1) k_solve_small(const DevP *Pp) {
                         for (int i = 0; i < 6; i++) Lall[kb * SS_LALL + 21 + i] = inv[i];
                     } else {
 #pragma unroll
-                        for (int r = 0; r < 6; r++) {
-                            double x[6];
+                        for (int c = 0; c < 6; c++) {         // column sweeps over all six rows at once: two dependent operations per pivot
 #pragma unroll
-                            for (int c = 0; c < 6; c++) {
-                                double v = blk[r * 6 + c];
+                            for (int r = 0; r < 6; r++) blk[r * 6 + c] *= inv[c];
 #pragma unroll
-                                for (int m = 0; m < c; m++) v -= x[m] * L[c * (c + 1) / 2 + m];
-                                x[c] = v * inv[c];
+                            for (int m = c + 1; m < 6; m++) {
+#pragma unroll
+                                for (int r = 0; r < 6; r++) blk[r * 6 + m] -= blk[r * 6 + c] * L[m * (m + 1) / 2 + c];
                             }
-#pragma unroll
-                            for (int c = 0; c < 6; c++) { blk[r * 6 + c] = x[c]; Xp[bi * SS_XLD + r * 6 + c] = x[c]; }
                         }
+#pragma unroll
+                        for (int i = 0; i < 36; i++) Xp[bi * SS_XLD + i] = blk[i];
                     }
                 }
             PHASE_END
@@ -304,20 +307,31 @@ PLBA_KERNEL void PLBA_BOUNDS(SS_NT, 1) k_solve_small(const DevP *Pp) {
                     double Xj[36];
 #pragma unroll
                     for (int i = 0; i < 36; i++) Xj[i] = Xp[bj * SS_XLD + i];
+                    if (bi != bj) {
 #pragma unroll
-                    for (int r = 0; r < 6; r++) {
-                        double xi[6];
+                        for (int r = 0; r < 6; r++) {
+                            double xi[6];
 #pragma unroll
-                        for (int m = 0; m < 6; m++) xi[m] = Xp[bi * SS_XLD + r * 6 + m];
+                            for (int m = 0; m < 6; m++) xi[m] = Xp[bi * SS_XLD + r * 6 + m];
 #pragma unroll
-                        for (int c = 0; c < 6; c++) {
-                            double v = blk[r * 6 + c];
+                            for (int c = 0; c < 6; c++) {
+                                double v = blk[r * 6 + c];
 #pragma unroll
-                            for (int m = 0; m < 6; m++) v -= xi[m] * Xj[c * 6 + m];
-                            blk[r * 6 + c] = v;
+                                for (int m = 0; m < 6; m++) v -= xi[m] * Xj[c * 6 + m];
+                                blk[r * 6 + c] = v;
+                            }
                         }
-                    }
-                    if (bi == bj) {
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 6; r++) {       // diagonal block: its lower triangle only
+#pragma unroll
+                            for (int c = 0; c <= r; c++) {
+                                double v = blk[r * 6 + c];
+#pragma unroll
+                                for (int m = 0; m < 6; m++) v -= Xj[r * 6 + m] * Xj[c * 6 + m];
+                                blk[r * 6 + c] = v;
+                            }
+                        }
 #pragma unroll
                         for (int r = 0; r < 6; r++) {
                             double v = gv[r];
@@ -355,11 +369,12 @@ PLBA_KERNEL void PLBA_BOUNDS(SS_NT, 1) k_solve_small(const DevP *Pp) {
                     double *ys = gb + nf * (SS_XLD + SS_LALL), *xs = ys + 6 * nf;
                     double x[6];
 #pragma unroll
-                    for (int c = 5; c >= 0; c--) {
-                        double v = ys[6 * i + c];
+                    for (int c = 0; c < 6; c++) x[c] = ys[6 * i + c];
 #pragma unroll
-                        for (int m = c + 1; m < 6; m++) v -= Lall[i * SS_LALL + m * (m + 1) / 2 + c] * x[m];
-                        x[c] = v * Lall[i * SS_LALL + 21 + c];
+                    for (int c = 5; c >= 0; c--) {          // column sweeps: two dependent operations per pivot
+                        x[c] *= Lall[i * SS_LALL + 21 + c];
+#pragma unroll
+                        for (int m = 0; m < c; m++) x[m] -= Lall[i * SS_LALL + c * (c + 1) / 2 + m] * x[c];
                     }
                     if (bj == i) {
 #pragma unroll
