@@ -43,11 +43,9 @@ struct WSmem {
         slot = (int *)p; fpos = slot + 32;
     }
 };
-template <int PROF> struct WSmemMax {
-    static PLBA_HD size_t bytes() {
-        const size_t a = WSmem<PROF, LT_POINT>::bytes(), b = WSmem<PROF, LineOf<PROF>::LT>::bytes();
-        return a > b ? a : b;
-    }
+template <int PROF, int LT> struct WRec;
+template <int PROF> struct WSmemMax {      // per warp: the larger of the update kernel's [component][lane] tile and the assembly kernel's record array
+    static PLBA_HD size_t bytes();
 };
 
 // ---- landmark-only quantities, in registers (the warp path's form of lm_precompute) -------------------------------
@@ -175,11 +173,38 @@ PLBA_D void prefetch_obs_w(const DevP &P, const WinCtrl &ctl, int o, int lm, con
     if (PROF == PLBA_PROFILE_G && ctl.stage == 1) plba_prefetch_l1(OA::lvl(P) + o);
 }
 
-// Schur task of a lane: pose pair (i <= j) of the free track positions, half = block rows hrow .. hrow + 2
-struct WTask { int on, pa, pb, sa, sb, hrow, diag, slice; };
+// ---- assembly: shared-memory record of one observation (one per lane and pass) ---------------------------------------
+// Array-of-structures, every sub-array 16-byte aligned, so that the Schur phase (which re-reads the records of the two poses of its
+// pair for every landmark) moves them with 128-bit shared-memory loads: half the instructions and half the wavefronts of the
+// [component][lane] layout, and the kernel's first limiter was the shared-memory pipe (ncu: LSU wavefronts 66 % of peak at config 5,
+// FP64 pipe 36 %).  The record stride is even with an odd half, so that the 128-bit accesses of eight consecutive lanes fall into
+// eight different 16-byte bank groups (conflict-free stores of the linearisation phase).
+template <int PROF, int LT>
+struct WRec {
+    typedef KT<PROF, LT> K;
+    // A (the pose rows) is stored as [column half][row of the residual][3 + one pad]: a Schur task that owns three columns of a 6x6
+    // block reads "its" half of A_b as one aligned run
+    enum { RANK = K::RANK, D = K::D, NAH = RANK * 4, NA = 2 * NAH, NB = RANK * D, NBp = (NB + 1) & ~1, NEp = (RANK + 1) & ~1, NVp = (D + 1) & ~1,
+           OA = 0, OB = NA, OT = OB + NBp, OE = OT + NBp, OV = OE + NEp, SIZE = OV + NVp, STRIDE = ((SIZE / 2) % 2 == 1) ? SIZE : SIZE + 2 };
+    static PLBA_HD size_t bytes() { return sizeof(double) * STRIDE * 32 + sizeof(int) * 64; }
+};
+template <int N> PLBA_HD void wrec_ld(const double *p, double *r) {      // N even, p 16-byte aligned
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) { const plba_d2 v = ((const plba_d2 *)p)[i]; r[2 * i] = v.x; r[2 * i + 1] = v.y; }
+}
+template <int N> PLBA_HD void wrec_st(double *p, const double *r) {
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) { plba_d2 v; v.x = r[2 * i]; v.y = r[2 * i + 1]; ((plba_d2 *)p)[i] = v; }
+}
+
+// Schur task of a lane: pose pair (i <= j) of the free track positions x one COLUMN half of the 6x6 block (columns hcol .. hcol + 2).
+// Both halves need M = Ta B^T (4 D FMAs), but each computes only its three columns of M A_b and of the block: 60 FMAs per landmark
+// and half against the 72 of the round-1 split by rows (where both halves computed all of M A_b), with 18 accumulators per lane
+// (whole blocks, 36 accumulators, spill around the linearisation at 168 registers: measured 2.10 against 1.92 ms at config 5).
+struct WTask { int on, pa, pb, sa, sb, half, diag, slice; };
 PLBA_HD void wtask_decode(int task, int nf, const int *fpos, const int *slot, int slot0, WTask &t) {
     const int p = task >> 1;
-    t.hrow = 3 * (task & 1);
+    t.half = task & 1;
     int q = p, i = 0;
     while (q >= nf - i) { q -= nf - i; i++; }
     const int j = i + q;
@@ -188,26 +213,28 @@ PLBA_HD void wtask_decode(int task, int nf, const int *fpos, const int *slot, in
     t.diag = (i == j) ? 1 : 0;
 }
 
-// accumulate the landmarks m = first, first + step, ... < nlp of the pass into the lane's 3x6 block (and, on the diagonal, g / diag(H_pp))
+// accumulate the landmarks m = first, first + step, ... < nlp of the pass into the lane's 6x3 half block blk[r * 3 + cc] (and, on the
+// diagonal, its three entries of g / diag(H_pp))
 template <int PROF, int LT, int mode>
-PLBA_D void wtask_accumulate(const WSmem<PROF, LT> &sm, const WTask &t, int k, int first, int step, int nlp, double *blk, double *gv, double *hd) {
-    typedef KT<PROF, LT> K;
-    const int D = K::D, RANK = K::RANK;
+PLBA_D void wtask_accumulate(const double *rec, const WTask &t, int k, int first, int step, int nlp, double *blk, double *gv, double *hd) {
+    typedef WRec<PROF, LT> R;
+    const int D = R::D, RANK = R::RANK;
     for (int m = first; m < nlp; m += step) {
-        const int ta = m * k + t.pa, tb = m * k + t.pb;
+        const double *ra = rec + (size_t)(m * k + t.pa) * R::STRIDE, *rb = rec + (size_t)(m * k + t.pb) * R::STRIDE;
         if ((PROF != PLBA_PROFILE_G || mode == 0) && t.diag) {        // diag(H_pp): lambda init (all profiles) and the hand LM's multiplicative damping
+            double Ah[R::NAH];
+            wrec_ld<R::NAH>(ra + R::OA + t.half * R::NAH, Ah);
 #pragma unroll
-            for (int r = 0; r < 3; r++) {
+            for (int cc = 0; cc < 3; cc++) {
 #pragma unroll
-                for (int kk = 0; kk < RANK; kk++) { const double av = sm.A[(kk * 6 + t.hrow + r) * 32 + ta]; hd[r] += av * av; }
+                for (int kk = 0; kk < RANK; kk++) hd[cc] += Ah[kk * 4 + cc] * Ah[kk * 4 + cc];
             }
         }
         if (mode == 0) continue;
-        double M[RANK * RANK], MA[RANK * 6];
+        double MA[RANK * 3];
         {
-            double Ta[RANK * D], Bb[RANK * D];
-#pragma unroll
-            for (int kk = 0; kk < RANK * D; kk++) { Ta[kk] = sm.TA[kk * 32 + ta]; Bb[kk] = sm.B[kk * 32 + tb]; }
+            double M[RANK * RANK], Ta[R::NBp], Bb[R::NBp], Abh[R::NAH];
+            wrec_ld<R::NBp>(ra + R::OT, Ta); wrec_ld<R::NBp>(rb + R::OB, Bb); wrec_ld<R::NAH>(rb + R::OA + t.half * R::NAH, Abh);
 #pragma unroll
             for (int kk = 0; kk < RANK; kk++) {
 #pragma unroll
@@ -219,85 +246,87 @@ PLBA_D void wtask_accumulate(const WSmem<PROF, LT> &sm, const WTask &t, int k, i
                 }
             }
             if (t.diag) {
-                // g_a += -At^T (et + Bt v)
-                double ev[RANK];
+                // g_a += -At^T (et + Bt v): this lane's three entries
+                double ev[R::NEp], V[R::NVp];
+                wrec_ld<R::NEp>(ra + R::OE, ev); wrec_ld<R::NVp>(ra + R::OV, V);
 #pragma unroll
                 for (int kk = 0; kk < RANK; kk++) {
-                    double sum = sm.E[kk * 32 + ta];
 #pragma unroll
-                    for (int mm = 0; mm < D; mm++) sum += Bb[kk * D + mm] * sm.V[mm * 32 + ta];
-                    ev[kk] = sum;
+                    for (int mm = 0; mm < D; mm++) ev[kk] += Bb[kk * D + mm] * V[mm];
                 }
 #pragma unroll
-                for (int r = 0; r < 3; r++) {
+                for (int cc = 0; cc < 3; cc++) {
 #pragma unroll
-                    for (int kk = 0; kk < RANK; kk++) gv[r] -= sm.A[(kk * 6 + t.hrow + r) * 32 + ta] * ev[kk];
+                    for (int kk = 0; kk < RANK; kk++) gv[cc] -= Abh[kk * 4 + cc] * ev[kk];      // (diagonal task: record b == record a)
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < RANK; kk++) {
+#pragma unroll
+                for (int cc = 0; cc < 3; cc++) {
+                    double sum = 0;
+#pragma unroll
+                    for (int k2 = 0; k2 < RANK; k2++) sum += M[kk * RANK + k2] * Abh[k2 * 4 + cc];
+                    MA[kk * 3 + cc] = sum;
                 }
             }
         }
 #pragma unroll
-        for (int c = 0; c < 6; c++) {
-            double ab[RANK];
+        for (int h = 0; h < 2; h++) {
+            double Aa[R::NAH];
+            wrec_ld<R::NAH>(ra + R::OA + h * R::NAH, Aa);
 #pragma unroll
-            for (int k2 = 0; k2 < RANK; k2++) ab[k2] = sm.A[(k2 * 6 + c) * 32 + tb];
+            for (int rr = 0; rr < 3; rr++) {
 #pragma unroll
-            for (int kk = 0; kk < RANK; kk++) {
-                double sum = 0;
+                for (int kk = 0; kk < RANK; kk++) {
+                    const double av = Aa[kk * 4 + rr];
 #pragma unroll
-                for (int k2 = 0; k2 < RANK; k2++) sum += M[kk * RANK + k2] * ab[k2];
-                MA[kk * 6 + c] = sum;
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-#pragma unroll
-            for (int kk = 0; kk < RANK; kk++) {
-                const double av = sm.A[(kk * 6 + t.hrow + r) * 32 + ta];
-#pragma unroll
-                for (int c = 0; c < 6; c++) blk[r * 6 + c] -= av * MA[kk * 6 + c];
+                    for (int cc = 0; cc < 3; cc++) blk[(3 * h + rr) * 3 + cc] -= av * MA[kk * 3 + cc];
+                }
             }
         }
     }
 }
 
-// the lane's block leaves the SM.  blk holds MINUS the Schur term, so S(a,b) += blk (upper storage; transposed if the pair is
+// the lane's half block leaves the SM.  blk holds MINUS the Schur term, so S(a,b) += blk (upper storage; transposed if the pair is
 // stored the other way round), g, diag(H_pp).  Two observations of one landmark in the same keyframe (sa == sb off the track
 // diagonal: rare) put blk + blk^T onto the diagonal block.
 template <int PROF, int mode>
 PLBA_D void wtask_flush(const DevP &P, const WTask &t, double *Sw, int ld, int slot0, const double *blk, const double *gv, const double *hd) {
+    const int hcol = 3 * t.half;
     if (mode == 0) {
         if (t.diag) {
 #pragma unroll
-            for (int r = 0; r < 3; r++) plba_atomic_add(&P.hpp_diag_init[(size_t)6 * (slot0 + t.sa) + t.hrow + r], hd[r]);
+            for (int cc = 0; cc < 3; cc++) plba_atomic_add(&P.hpp_diag_init[(size_t)6 * (slot0 + t.sa) + hcol + cc], hd[cc]);
         }
         return;
     }
     const bool tr = (t.sa > t.sb);
     const int ra = tr ? t.sb : t.sa, cb = tr ? t.sa : t.sb;
     const long long sr = tr ? 1 : ld, sc = tr ? ld : 1;
-    double *p0 = Sw + (size_t)(6 * ra) * ld + 6 * cb + t.hrow * sr;
+    double *p0 = Sw + (size_t)(6 * ra) * ld + 6 * cb + hcol * sc;
     const bool upper_only = (t.sa == t.sb);                        // diagonal block of S: only its upper triangle is stored
 #pragma unroll
-    for (int r = 0; r < 3; r++) {
+    for (int r = 0; r < 6; r++) {
 #pragma unroll
-        for (int c = 0; c < 6; c++) {
-            if (!upper_only || t.hrow + r <= c) plba_atomic_add(p0 + r * sr + c * sc, blk[r * 6 + c]);
+        for (int cc = 0; cc < 3; cc++) {
+            if (!upper_only || r <= hcol + cc) plba_atomic_add(p0 + r * sr + cc * sc, blk[r * 3 + cc]);
         }
     }
     if (t.diag) {
 #pragma unroll
-        for (int r = 0; r < 3; r++) {
-            plba_atomic_add(&P.gs[(size_t)6 * (slot0 + t.sa) + t.hrow + r], gv[r]);
-            if (PROF != PLBA_PROFILE_G) plba_atomic_add(&P.hpp_diag[(size_t)6 * (slot0 + t.sa) + t.hrow + r], hd[r]);
+        for (int cc = 0; cc < 3; cc++) {
+            plba_atomic_add(&P.gs[(size_t)6 * (slot0 + t.sa) + hcol + cc], gv[cc]);
+            if (PROF != PLBA_PROFILE_G) plba_atomic_add(&P.hpp_diag[(size_t)6 * (slot0 + t.sa) + hcol + cc], hd[cc]);
         }
     } else if (upper_only) {
         // transposed copy of an off-track-diagonal block that landed on the diagonal of S
         double *q0 = Sw + (size_t)(6 * t.sa) * ld + 6 * t.sa;
 #pragma unroll
-        for (int r = 0; r < 3; r++) {
+        for (int r = 0; r < 6; r++) {
 #pragma unroll
-            for (int c = 0; c < 6; c++) {
-                if (c <= t.hrow + r) plba_atomic_add(q0 + (size_t)c * ld + t.hrow + r, blk[r * 6 + c]);
+            for (int cc = 0; cc < 3; cc++) {
+                if (hcol + cc <= r) plba_atomic_add(q0 + (size_t)(hcol + cc) * ld + r, blk[r * 3 + cc]);
             }
         }
     }
@@ -311,8 +340,10 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
     PLBA_PARAMS_REF(P, Pin);
     typedef KT<PROF, LT> K;
     typedef ObsAcc<LT> OA;
+    typedef WRec<PROF, LT> R;
     const int D = K::D, RANK = K::RANK;
-    WSmem<PROF, LT> sm(wraw);
+    double *rec = (double *)wraw;                                 // [32] records of the pass
+    int *slot_s = (int *)(rec + (size_t)R::STRIDE * 32), *fpos_s = slot_s + 32;
     LANE_VAR(double, cost_l); LANE_VAR(double, maxd_l);
     LANE_ARR(double, blk, 18); LANE_ARR(double, gv, 3); LANE_ARR(double, hd, 3);
     LANE_VAR(WTask, tk);
@@ -325,9 +356,9 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
     for (;;) {
         // next work item: one atomic per warp (items differ in cost, a static deal leaves the slowest warp far behind)
         WPHASE_BEGIN
-            if (lane == 0) sm.slot[48] = plba_atomic_fetch_add_i(&P.counters[LT == LT_POINT ? CNT_WORK_PT : CNT_WORK_LS], 1);
+            if (lane == 0) slot_s[48] = plba_atomic_fetch_add_i(&P.counters[LT == LT_POINT ? CNT_WORK_PT : CNT_WORK_LS], 1);
         WPHASE_END
-        const int ii = sm.slot[48];
+        const int ii = slot_s[48];
         WPHASE_BEGIN
         WPHASE_END
         if (ii >= n_items) break;
@@ -351,10 +382,10 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
         const int k = it.k, nf = it.nfree;
         const int lpp = 32 / k;                                  // landmarks per pass
         const int npass = (it.n_lm + lpp - 1) / lpp;
-        const int ntask = nf * (nf + 1);                          // (pairs i <= j) x 2 halves
+        const int ntask = nf * (nf + 1);                          // (pairs i <= j) x 2 column halves
         const int rounds = (ntask + 31) >> 5;
         const bool keep = (rounds == 1);                          // the lane's block stays in registers for the whole item
-        const int nslice = (keep && ntask <= 16) ? 32 / ntask : 1;  // few tasks: the landmarks of a pass are dealt over several lanes per task
+        const int nslice = keep ? 32 / ntask : 1;                 // few tasks: the landmarks of a pass are dealt over several lanes per task
         const int slot0 = P.win_slot0[it.win];
         const int ld = 6 * P.win_nfree[it.win];
         double *Sw = P.S + P.win_S_off[it.win];
@@ -363,15 +394,15 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
             LANE_BIND(kf_l); LANE_BIND(m_l);
             m_l = lane / k;
             kf_l = OA::kf(P)[it.ob0 + (lane - m_l * k)];
-            if (lane < k) sm.slot[lane] = P.kf_slot[kf_l];
-            if (lane < nf) sm.fpos[lane] = OA::freepos(P)[it.fp0 + lane];
+            if (lane < k) slot_s[lane] = P.kf_slot[kf_l];
+            if (lane < nf) fpos_s[lane] = OA::freepos(P)[it.fp0 + lane];
         WPHASE_END
         if (keep) {
             WPHASE_BEGIN
                 LANE_BIND(tk); LANE_BIND(blk); LANE_BIND(gv); LANE_BIND(hd);
                 const int slice = lane / ntask, task = lane - slice * ntask;
                 tk.on = (slice < nslice) ? 1 : 0; tk.slice = slice;
-                if (tk.on) wtask_decode(task, nf, sm.fpos, sm.slot, slot0, tk);
+                if (tk.on) wtask_decode(task, nf, fpos_s, slot_s, slot0, tk);
 #pragma unroll
                 for (int i = 0; i < 18; i++) blk[i] = 0.0;
 #pragma unroll
@@ -390,15 +421,23 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
                     LmD<LT> lmd; ObsLoad<LT> ob;
                     ob.load(P, o);
                     LmLoad<PROF, LT>::run(P, ctl, it.win, it.lm0 + lmb + m_l, state, lmd);
-                    double A[RANK * 6], B[RANK * D], e[RANK], cost;
+                    double A[RANK * 6], B[R::NBp], e[R::NEp], cost;
+                    if (R::NBp > RANK * D) B[R::NBp - 1] = 0.0;
+                    if (R::NEp > RANK) e[R::NEp - 1] = 0.0;
                     obs_lin_w<PROF, LT>(P, ctl, o, kf_l, lmd, ob, A, B, e, cost);
                     if (mode == 1) cost_l += cost;
+                    double *r = rec + (size_t)lane * R::STRIDE;
+                    double Ah[R::NA];
 #pragma unroll
-                    for (int i = 0; i < RANK * 6; i++) sm.A[i * 32 + lane] = A[i];
+                    for (int h = 0; h < 2; h++) {
 #pragma unroll
-                    for (int i = 0; i < RANK * D; i++) sm.B[i * 32 + lane] = B[i];
+                        for (int kk = 0; kk < RANK; kk++) {
 #pragma unroll
-                    for (int i = 0; i < RANK; i++) sm.E[i * 32 + lane] = e[i];
+                            for (int cc = 0; cc < 3; cc++) Ah[h * R::NAH + kk * 4 + cc] = A[kk * 6 + 3 * h + cc];
+                            Ah[h * R::NAH + kk * 4 + 3] = 0.0;
+                        }
+                    }
+                    wrec_st<R::NA>(r + R::OA, Ah); wrec_st<R::NBp>(r + R::OB, B); wrec_st<R::NEp>(r + R::OE, e);
                 }
             WPHASE_END
             // ---- per landmark (redundantly on each of its lanes): H_ll, b_l, damping, inverse; Ta = Bt H_ll^-1, v = H_ll^-1 b_l (subsystem 2) ----
@@ -412,17 +451,15 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
 #pragma unroll
                     for (int i = 0; i < D; i++) bl[i] = 0.0;
                     for (int t = t0; t < t0 + k; t++) {
+                        double b[R::NBp], ee[R::NEp];
+                        wrec_ld<R::NBp>(rec + (size_t)t * R::STRIDE + R::OB, b); wrec_ld<R::NEp>(rec + (size_t)t * R::STRIDE + R::OE, ee);
 #pragma unroll
                         for (int kk = 0; kk < RANK; kk++) {
-                            double b[D];
-#pragma unroll
-                            for (int c = 0; c < D; c++) b[c] = sm.B[(kk * D + c) * 32 + t];
-                            const double ek = sm.E[kk * 32 + t];
 #pragma unroll
                             for (int r = 0; r < D; r++) {
-                                bl[r] -= b[r] * ek;
+                                bl[r] -= b[kk * D + r] * ee[kk];
 #pragma unroll
-                                for (int c = r; c < D; c++) H[r * D + c] += b[r] * b[c];
+                                for (int c = r; c < D; c++) H[r * D + c] += b[kk * D + r] * b[kk * D + c];
                             }
                         }
                     }
@@ -436,26 +473,29 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
                     if (mode == 0) { if (maxd > maxd_l) maxd_l = maxd; }
                     else {
                         damp_invert<PROF, D>(ctl, H);
+                        double *r = rec + (size_t)lane * R::STRIDE;
+                        double b[R::NBp], ta[R::NBp], v[R::NVp];
+                        wrec_ld<R::NBp>(r + R::OB, b);
+                        if (R::NBp > RANK * D) ta[R::NBp - 1] = 0.0;
+                        if (R::NVp > D) v[R::NVp - 1] = 0.0;
 #pragma unroll
                         for (int kk = 0; kk < RANK; kk++) {
-                            double b[D];
-#pragma unroll
-                            for (int c = 0; c < D; c++) b[c] = sm.B[(kk * D + c) * 32 + lane];
 #pragma unroll
                             for (int c = 0; c < D; c++) {
                                 double sum = 0;
 #pragma unroll
-                                for (int mm = 0; mm < D; mm++) sum += b[mm] * H[mm * D + c];
-                                sm.TA[(kk * D + c) * 32 + lane] = sum;
+                                for (int mm = 0; mm < D; mm++) sum += b[kk * D + mm] * H[mm * D + c];
+                                ta[kk * D + c] = sum;
                             }
                         }
 #pragma unroll
-                        for (int r = 0; r < D; r++) {
-                            double s = 0;
+                        for (int rr = 0; rr < D; rr++) {
+                            double sum = 0;
 #pragma unroll
-                            for (int c = 0; c < D; c++) s += H[r * D + c] * bl[c];
-                            sm.V[r * 32 + lane] = s;
+                            for (int c = 0; c < D; c++) sum += H[rr * D + c] * bl[c];
+                            v[rr] = sum;
                         }
+                        wrec_st<R::NBp>(r + R::OT, ta); wrec_st<R::NVp>(r + R::OV, v);
                     }
                 }
             WPHASE_END
@@ -471,14 +511,14 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
                     if (!keep) {
                         const int task = r * 32 + lane;
                         tk.on = (task < ntask) ? 1 : 0; tk.slice = 0;
-                        if (tk.on) wtask_decode(task, nf, sm.fpos, sm.slot, slot0, tk);
+                        if (tk.on) wtask_decode(task, nf, fpos_s, slot_s, slot0, tk);
 #pragma unroll
                         for (int i = 0; i < 18; i++) blk[i] = 0.0;
 #pragma unroll
                         for (int i = 0; i < 3; i++) { gv[i] = 0.0; hd[i] = 0.0; }
                     }
                     if (tk.on) {
-                        wtask_accumulate<PROF, LT, mode>(sm, tk, k, tk.slice, nslice, nlp, blk, gv, hd);
+                        wtask_accumulate<PROF, LT, mode>(rec, tk, k, tk.slice, nslice, nlp, blk, gv, hd);
                         if (!keep || pass == npass - 1) wtask_flush<PROF, mode>(P, tk, Sw, ld, slot0, blk, gv, hd);
                     }
                 WPHASE_END
@@ -493,6 +533,15 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
             else PLBA_WARP_FLUSH_MAX(&P.accmax[cur_win], maxd_l);
         WPHASE_END
     }
+}
+
+template <int PROF> PLBA_HD size_t WSmemMax<PROF>::bytes() {
+    size_t m = WSmem<PROF, LT_POINT>::bytes();
+    const size_t b = WSmem<PROF, LineOf<PROF>::LT>::bytes(), c = WRec<PROF, LT_POINT>::bytes(), d = WRec<PROF, LineOf<PROF>::LT>::bytes();
+    if (b > m) m = b;
+    if (c > m) m = c;
+    if (d > m) m = d;
+    return (m + 15) & ~(size_t)15;
 }
 
 template <int PROF>
