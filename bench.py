@@ -154,7 +154,7 @@ def sharded_run(s, abi, scene, args, rank, world, dev, stream, barrier):
     from pl_slam_plucker_b200 import sharded, solver
     P4 = scene.make_scene(WORKLOADS[args.sharded_workload])
     s2 = solver.LBASolver(dev.index, stream=stream.cuda_stream)
-    sh = sharded.ShardedLBA(s2, rank, world, device=dev)
+    sh = sharded.ShardedLBA(s2, rank, world, device=dev, nccl=True)       # the collective is the library's own ncclAllReduce (plba_comm_init_rank)
     opt = abi.Options(abi.PROFILE_G, 1)
     with torch.cuda.stream(stream):
         sh.upload(P4, opt)
@@ -172,7 +172,7 @@ def sharded_run(s, abi, scene, args, rank, world, dev, stream, barrier):
     return {"workload": "%s: %d free KFs, %d points, %d lines sharded by base keyframe over %d GPUs" % (args.sharded_workload, P4.n_free, P4.n_pt, P4.n_ls, world),
             "lm_trials": trials // reps, "ms_per_lba": float(t.item()) / reps, "observations_per_s": P4.n_obs * trials / (float(t.item()) * 1e-3),
             "allreduce_bytes_per_trial": int(8 * n_dbl), "kernel_path": kpath,
-            "collective": "NCCL all-reduce per LM trial (torch.distributed) of the band of the reduced camera system in node form [D | U | b] when the block-cyclic-reduction solver runs, of the dense [S | g] otherwise"}
+            "collective": "ncclAllReduce issued by the library on its own stream (plba_comm_init_rank), one per LM trial (+ 4 doubles after the update kernel), no host synchronisation inside the LM loop: the band of the reduced camera system in node form [D | U | b] when the block-cyclic-reduction solver runs, of the dense [S | g] otherwise"}
 
 
 def workload_name(args, P):

@@ -218,6 +218,27 @@ int  plba_kernel_path(plba_handle h, int32_t *out4);
  * (SURVEY.md §8e).  fn(dev_ptr, n_doubles, stream, user) must sum the buffer in place over all ranks. */
 typedef void (*plba_allreduce_fn)(void *dev_ptr, int64_t n_doubles, void *stream, void *user);
 int  plba_set_allreduce(plba_handle h, plba_allreduce_fn fn, void *user);
+/* with a caller-supplied all-reduce the library also needs the rank layout (the lambda-init maximum travels as one slot per rank
+ * inside a SUM exchange): nranks <= 16 */
+int  plba_set_allreduce_ranks(plba_handle h, int32_t nranks, int32_t rank);
+
+/* ---- landmark-sharded LBA over several GPUs (the partition notion is the reference's base keyframe of a landmark,
+ * include/mapHandler.h:148-149).  Every rank uploads ITS landmarks (with all their observations) and ALL keyframes; the library then
+ * sums the reduced camera system over the ranks once per LM trial with ncclAllReduce on the handle's stream (plus one scalar
+ * exchange after the update kernel), and every rank takes the same LM decisions.  NCCL is resolved at run time (libnccl.so.2 already
+ * mapped into the process, or PLBA_NCCL_LIB, or the loader path): the library has no link-time dependency on it.
+ *   one process per GPU : rank 0 calls plba_comm_unique_id(), ships the 128 bytes to the other ranks (MPI, sockets, torch.distributed,
+ *                         a file ...), every rank calls plba_comm_init_rank() on its handle;
+ *   one process, N GPUs : plba_create_group() = plba_create per device + ncclCommInitAll; drive each handle from its own host thread.
+ * plba_set_allreduce() (a caller-supplied all-reduce) remains for hosts without NCCL and for the CPU tests. */
+#define PLBA_COMM_ID_BYTES 128
+int  plba_comm_unique_id(void *id_out);
+int  plba_comm_init_rank(plba_handle h, int32_t nranks, int32_t rank, const void *id);
+int  plba_comm_destroy(plba_handle h);
+int  plba_create_group(int32_t ndev, const int32_t *devs, plba_handle *out_handles);
+void plba_destroy_group(int32_t ndev, plba_handle *handles);
+/* out2 = { ranks of the handle's communicator (1 = not sharded), this rank } */
+int  plba_comm_info(plba_handle h, int32_t *out2);
 
 /* Timing of the last plba_run(): CUDA-event milliseconds per kernel family and launch counts. */
 typedef struct plba_timing {

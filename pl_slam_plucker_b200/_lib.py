@@ -12,7 +12,7 @@ ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
 
 EXPORTS = ["plba_version", "plba_default_options", "plba_create", "plba_destroy", "plba_last_error", "plba_solve", "plba_solve_batch",
            "plba_upload", "plba_reset_state", "plba_run", "plba_download", "plba_trial_assemble", "plba_trial_finish",
-           "plba_reduced_system", "plba_copy_reduced_system", "plba_time_kernel", "plba_layout_stats", "plba_kernel_path", "plba_track_default_options", "plba_track_solve", "plba_create_lines", "plba_set_force_dense", "plba_set_force_chunk", "plba_set_allreduce", "plba_get_timing", "plba_set_detail_timing", "plba_scene_preset", "plba_scene_create",
+           "plba_reduced_system", "plba_copy_reduced_system", "plba_time_kernel", "plba_layout_stats", "plba_kernel_path", "plba_track_default_options", "plba_track_solve", "plba_create_lines", "plba_set_force_dense", "plba_set_force_chunk", "plba_set_allreduce", "plba_set_allreduce_ranks", "plba_comm_unique_id", "plba_comm_init_rank", "plba_comm_destroy", "plba_create_group", "plba_destroy_group", "plba_comm_info", "plba_get_timing", "plba_set_detail_timing", "plba_scene_preset", "plba_scene_create",
            "plba_scene_problem", "plba_scene_truth", "plba_scene_destroy"]
 
 
@@ -59,6 +59,20 @@ def declare(L):
     L.plba_layout_stats.restype = C.c_int
     L.plba_set_allreduce.argtypes = [C.c_void_p, ALLREDUCE_FN, C.c_void_p]
     L.plba_set_allreduce.restype = C.c_int
+    L.plba_set_allreduce_ranks.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    L.plba_set_allreduce_ranks.restype = C.c_int
+    L.plba_comm_unique_id.argtypes = [C.c_void_p]
+    L.plba_comm_unique_id.restype = C.c_int
+    L.plba_comm_init_rank.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    L.plba_comm_init_rank.restype = C.c_int
+    L.plba_comm_destroy.argtypes = [C.c_void_p]
+    L.plba_comm_destroy.restype = C.c_int
+    L.plba_create_group.argtypes = [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]
+    L.plba_create_group.restype = C.c_int
+    L.plba_destroy_group.argtypes = [C.c_int32, C.POINTER(C.c_void_p)]
+    L.plba_destroy_group.restype = None
+    L.plba_comm_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+    L.plba_comm_info.restype = C.c_int
     L.plba_get_timing.argtypes = [C.c_void_p, C.POINTER(abi.plba_timing)]
     L.plba_get_timing.restype = C.c_int
     L.plba_set_detail_timing.argtypes = [C.c_void_p, C.c_int]

@@ -21,8 +21,52 @@
 #include "plba_solver.h"
 #include "plba_warp.h"
 #include "plba_track.h"
+#ifndef PLBA_HOST_EMU
+#include <dlfcn.h>
+#include <mutex>
+#endif
 
 using namespace plba;
+
+// ---- NCCL, resolved at run time (no link-time dependency; the prototypes below are NCCL's public C API, nccl.h) ---------------
+#ifndef PLBA_HOST_EMU
+namespace {
+typedef struct ncclComm *plba_ncclComm_t;
+typedef struct { char internal[PLBA_COMM_ID_BYTES]; } plba_ncclUniqueId;
+enum { PLBA_NCCL_SUM = 0, PLBA_NCCL_MAX = 2, PLBA_NCCL_F64 = 8 };
+struct NcclApi {
+    int (*GetUniqueId)(plba_ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(plba_ncclComm_t *, int, plba_ncclUniqueId, int) = nullptr;
+    int (*CommInitAll)(plba_ncclComm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(plba_ncclComm_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, plba_ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false; std::string why;
+};
+NcclApi &nccl_api() {
+    static NcclApi api; static std::once_flag once;
+    std::call_once(once, [] {
+        void *hd = nullptr;
+        const char *env = std::getenv("PLBA_NCCL_LIB");
+        if (env && env[0]) hd = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+        if (!hd && dlsym(RTLD_DEFAULT, "ncclAllReduce")) hd = RTLD_DEFAULT;       // already mapped (e.g. by torch): use that copy
+        if (!hd) hd = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!hd) hd = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!hd) { api.why = "libnccl.so.2 not found (set PLBA_NCCL_LIB)"; return; }
+        auto sym = [&](const char *n) { void *q = dlsym(hd, n); if (!q) api.why = std::string("missing NCCL symbol ") + n; return q; };
+        api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+        api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
+        api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+        api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+        api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommInitAll && api.CommDestroy && api.AllReduce && api.GetErrorString;
+    });
+    return api;
+}
+}  // namespace
+#endif
+enum { PLBA_MAX_RANKS = 16 };
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return PLBA_E_CUDA; } } while (0)
 
@@ -71,6 +115,10 @@ struct plba_handle_s {
     int h_counters[CNT_N] = {0};
     int64_t layout[8] = {0};
     plba_allreduce_fn allreduce = nullptr; void *allreduce_user = nullptr;
+    void *nccl_comm = nullptr;       // ncclComm_t owned by the handle (plba_comm_init_rank / plba_create_group)
+    int n_ranks = 1, rank = 0;
+    int nccl_failed = 0;
+    int *h_poll = nullptr; cudaEvent_t ev_poll[4]{};    // pinned copies of the device counters, one per in-flight round of the pipelined loop
     plba_timing timing{};
     cudaEvent_t ev[8]{};
     cudaEvent_t ev_h2d = nullptr; bool h2d_pending = false;   // recorded after the H2D copies of an upload: the next upload waits for it before it rewrites the pinned staging
@@ -91,6 +139,8 @@ struct plba_handle_s {
         d_arena = nullptr; h_in = nullptr; h_out = nullptr; d_cap = h_in_cap = h_out_cap = 0; uploaded = false;
     }
 };
+
+static inline bool has_exchange(plba_handle h) { return h->nccl_comm != nullptr || h->allreduce != nullptr; }
 
 static int ensure(plba_handle h, size_t dev_bytes, size_t in_bytes, size_t out_bytes) {
     if (dev_bytes > h->d_cap) {
@@ -280,6 +330,7 @@ int plba_create(int32_t device, void *stream, plba_handle *out) {
         if (h->d_scratch) cudaFree(h->d_scratch);
         if (h->h_P) cudaFreeHost(h->h_P);
         if (h->h_cnt) cudaFreeHost(h->h_cnt);
+        if (h->h_poll) cudaFreeHost(h->h_poll);
         if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
         delete h; *out = nullptr; return PLBA_E_CUDA;
     };
@@ -292,6 +343,9 @@ int plba_create(int32_t device, void *stream, plba_handle *out) {
     if (cudaMallocHost(&q, sizeof(int) * CNT_N) != cudaSuccess) return fail();
     h->h_cnt = (int *)q;
     cudaEventCreate(&h->ev_h2d);
+    if (cudaMallocHost(&q, sizeof(int) * CNT_N * 4) != cudaSuccess) return fail();
+    h->h_poll = (int *)q;
+    for (int i = 0; i < 4; i++) cudaEventCreate(&h->ev_poll[i]);
     for (int i = 0; i < 8; i++) cudaEventCreate(&h->ev[i]);
     *out = h;
     return PLBA_OK;
@@ -311,13 +365,75 @@ void plba_destroy(plba_handle h) {
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
     for (int i = 0; i < 8; i++) cudaEventDestroy(h->ev[i]);
     if (h->ev_h2d) cudaEventDestroy(h->ev_h2d);
+    for (int i = 0; i < 4; i++) if (h->ev_poll[i]) cudaEventDestroy(h->ev_poll[i]);
+    if (h->h_poll) cudaFreeHost(h->h_poll);
+#ifndef PLBA_HOST_EMU
+    if (h->nccl_comm) { nccl_api().CommDestroy((plba_ncclComm_t)h->nccl_comm); h->nccl_comm = nullptr; }
+#endif
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
 const char *plba_last_error(plba_handle h) { return h ? h->err.c_str() : "null handle"; }
 
-int plba_set_allreduce(plba_handle h, plba_allreduce_fn fn, void *user) { if (!h) return PLBA_E_ARG; h->allreduce = fn; h->allreduce_user = user; return PLBA_OK; }
+int plba_set_allreduce(plba_handle h, plba_allreduce_fn fn, void *user) { if (!h) return PLBA_E_ARG; h->allreduce = fn; h->allreduce_user = user; if (!fn && !h->nccl_comm) { h->n_ranks = 1; h->rank = 0; } return PLBA_OK; }
+int plba_set_allreduce_ranks(plba_handle h, int32_t nranks, int32_t rank) {
+    if (!h || nranks < 1 || nranks > PLBA_MAX_RANKS || rank < 0 || rank >= nranks) return PLBA_E_ARG;
+    h->n_ranks = nranks; h->rank = rank; return PLBA_OK;
+}
+int plba_comm_info(plba_handle h, int32_t *out2) { if (!h || !out2) return PLBA_E_ARG; out2[0] = has_exchange(h) ? h->n_ranks : 1; out2[1] = h->rank; return PLBA_OK; }
+#ifndef PLBA_HOST_EMU
+int plba_comm_unique_id(void *id_out) {
+    if (!id_out) return PLBA_E_ARG;
+    NcclApi &N = nccl_api();
+    if (!N.ok) return PLBA_E_UNSUPPORTED;
+    plba_ncclUniqueId id;
+    if (N.GetUniqueId(&id) != 0) return PLBA_E_CUDA;
+    std::memcpy(id_out, id.internal, PLBA_COMM_ID_BYTES);
+    return PLBA_OK;
+}
+int plba_comm_init_rank(plba_handle h, int32_t nranks, int32_t rank, const void *id_in) {
+    if (!h || !id_in || nranks < 1 || nranks > PLBA_MAX_RANKS || rank < 0 || rank >= nranks) return PLBA_E_ARG;
+    NcclApi &N = nccl_api();
+    if (!N.ok) { h->err = "NCCL unavailable: " + N.why; return PLBA_E_UNSUPPORTED; }
+    CK(cudaSetDevice(h->device));
+    if (h->nccl_comm) { N.CommDestroy((plba_ncclComm_t)h->nccl_comm); h->nccl_comm = nullptr; }
+    plba_ncclUniqueId id; std::memcpy(id.internal, id_in, PLBA_COMM_ID_BYTES);
+    plba_ncclComm_t c = nullptr;
+    const int rc = N.CommInitRank(&c, nranks, id, rank);
+    if (rc != 0) { h->err = std::string("ncclCommInitRank: ") + N.GetErrorString(rc); return PLBA_E_CUDA; }
+    h->nccl_comm = c; h->n_ranks = nranks; h->rank = rank; h->nccl_failed = 0;
+    return PLBA_OK;
+}
+int plba_comm_destroy(plba_handle h) {
+    if (!h) return PLBA_E_ARG;
+    if (h->nccl_comm) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); nccl_api().CommDestroy((plba_ncclComm_t)h->nccl_comm); h->nccl_comm = nullptr; }
+    if (!h->allreduce) { h->n_ranks = 1; h->rank = 0; }
+    return PLBA_OK;
+}
+int plba_create_group(int32_t ndev, const int32_t *devs, plba_handle *out) {
+    if (ndev < 1 || ndev > PLBA_MAX_RANKS || !devs || !out) return PLBA_E_ARG;
+    NcclApi &N = nccl_api();
+    if (!N.ok) return PLBA_E_UNSUPPORTED;
+    for (int i = 0; i < ndev; i++) out[i] = nullptr;
+    for (int i = 0; i < ndev; i++) {
+        const int rc = plba_create(devs[i], nullptr, &out[i]);
+        if (rc) { for (int j = 0; j < i; j++) { plba_destroy(out[j]); out[j] = nullptr; } return rc; }
+    }
+    std::vector<plba_ncclComm_t> comms(ndev, nullptr);
+    std::vector<int> dl(devs, devs + ndev);
+    if (N.CommInitAll(comms.data(), ndev, dl.data()) != 0) { for (int i = 0; i < ndev; i++) { plba_destroy(out[i]); out[i] = nullptr; } return PLBA_E_CUDA; }
+    for (int i = 0; i < ndev; i++) { out[i]->nccl_comm = comms[i]; out[i]->n_ranks = ndev; out[i]->rank = i; }
+    return PLBA_OK;
+}
+void plba_destroy_group(int32_t ndev, plba_handle *hs) { if (!hs) return; for (int i = 0; i < ndev; i++) { plba_destroy(hs[i]); hs[i] = nullptr; } }
+#else
+int plba_comm_unique_id(void *) { return PLBA_E_UNSUPPORTED; }
+int plba_comm_init_rank(plba_handle, int32_t, int32_t, const void *) { return PLBA_E_UNSUPPORTED; }
+int plba_comm_destroy(plba_handle) { return PLBA_OK; }
+int plba_create_group(int32_t, const int32_t *, plba_handle *) { return PLBA_E_UNSUPPORTED; }
+void plba_destroy_group(int32_t, plba_handle *) {}
+#endif
 
 }  // extern "C"
 
@@ -447,11 +563,19 @@ static void launch_update(plba_handle h, int flags) {
     h->timing.n_launches++;
 }
 static void allreduce(plba_handle h, double *p, size_t n, int op_max) {
-    if (!h->allreduce || !n) return;
-    // op is encoded in the sign of the count for the max reduction (the lambda-init scalar and the band width use it)
+    if (!n) return;
+#ifndef PLBA_HOST_EMU
+    if (h->nccl_comm) {      // in place, on the handle's stream: ordered with the kernels around it, no host synchronisation
+        const int rc = nccl_api().AllReduce(p, p, n, PLBA_NCCL_F64, op_max ? PLBA_NCCL_MAX : PLBA_NCCL_SUM, (plba_ncclComm_t)h->nccl_comm, h->stream);
+        if (rc != 0 && !h->nccl_failed) { h->nccl_failed = 1; h->err = std::string("ncclAllReduce: ") + nccl_api().GetErrorString(rc); }
+        return;
+    }
+#endif
+    if (!h->allreduce) return;
+    // op is encoded in the sign of the count for the max reduction (only the band width at upload uses it)
     h->allreduce(p, op_max ? -(int64_t)n : (int64_t)n, (void *)h->stream, h->allreduce_user);
 }
-static inline size_t bcr_exchange_doubles(const BcrW &B) { return (size_t)2 * B.N * B.m * B.m + (size_t)2 * B.N * B.m; }
+static inline size_t bcr_exchange_doubles(const BcrW &B) { return (size_t)2 * B.N * B.m * B.m + (size_t)2 * B.N * B.m + 8; }      // [D | U | b | hd | tail]
 static bool bcr_is_active(plba_handle h) { return !h->small_path && h->band_blocks <= BAND_MAX && !h->force_dense && h->large_solver == 0 && !h->bcr.empty(); }
 static void launch_solve(plba_handle h) {
     const DevP &P = h->P; const DevP *Pp = h->d_P;
@@ -608,7 +732,7 @@ static bool use_graph(plba_handle h) {
 #ifdef PLBA_HOST_EMU
     (void)h; return false;
 #else
-    return h->small_path && !h->no_graph && !h->allreduce && !h->detail_timing;
+    return h->small_path && !h->no_graph && !has_exchange(h) && !h->detail_timing;
 #endif
 }
 
@@ -843,7 +967,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
         }
         h->layout[0] = (int64_t)ch_pt.size(); h->layout[1] = (int64_t)ch_ls.size(); h->layout[2] = (int64_t)sg_pt.size(); h->layout[3] = (int64_t)sg_ls.size();
         h->layout[4] = n_off; h->layout[5] = n_diag; h->layout[6] = nnzb; h->band_blocks = band;
-        if (h->allreduce) {
+        if (has_exchange(h)) {
             // landmark-sharded path: every rank must pick the same solver and the same node layout, i.e. agree on the half bandwidth
             // of the SUMMED reduced camera system = the largest over the shards (max all-reduce through the caller's hook)
             double v = (double)band;
@@ -875,7 +999,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     std::vector<long long> win_S_off(n);
     for (int w = 0; w < n; w++) { win_S_off[w] = S_off; S_off += (long long)36 * h->wins[w].n_free * h->wins[w].n_free; }
     h->S_doubles = (size_t)S_off;
-    h->sys_doubles = h->S_doubles + (size_t)18 * tot.n_free + (size_t)ACC_N * n + (size_t)n;
+    h->sys_doubles = h->S_doubles + (size_t)18 * tot.n_free + (size_t)ACC_N * n + (size_t)n + (size_t)PLBA_MAX_RANKS * n;
     Carver cs = ci;   // device-only state follows the inputs
     size_t s_poseT[2], s_X[2], s_pts[2], s_lns[2], s_lpre[2];
     for (int b = 0; b < 2; b++) s_lpre[b] = cs.take<double>((size_t)LPRE_N * tot.n_ls);
@@ -891,7 +1015,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
             BcrW B{}; B.bs = bs; B.m = m; B.N = (h->wins[w].n_free + bs - 1) / bs;
             h->bcr.push_back(B);
             const size_t nn = (size_t)B.N * m * m;
-            s_bcr.push_back(cs.take<double>(2 * nn + (size_t)2 * B.N * m));       // [D | U | b | hd]: contiguous (exchange step)
+            s_bcr.push_back(cs.take<double>(2 * nn + (size_t)2 * B.N * m + 8));   // [D | U | b | hd | tail]: contiguous (exchange step)
             s_bcr.push_back(cs.take<double>(nn)); s_bcr.push_back(cs.take<double>(nn)); s_bcr.push_back(cs.take<double>((size_t)B.N * m));   // Xl, Xr, y
         }
     }
@@ -1019,12 +1143,14 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     P.po_chi2 = (double *)(db + h->o_pchi); P.lo_chi2 = (double *)(db + h->o_lchi);
     h->sysbuf = (double *)(db + s_sys);
     P.S = h->sysbuf; P.gs = P.S + h->S_doubles; P.hpp_diag = P.gs + (size_t)6 * tot.n_free; P.hpp_diag_init = P.hpp_diag + (size_t)6 * tot.n_free;
-    P.acc = P.hpp_diag_init + (size_t)6 * tot.n_free; P.accB = P.acc + (size_t)4 * n; P.accmax = P.acc + (size_t)ACC_N * n;
+    P.acc = P.hpp_diag_init + (size_t)6 * tot.n_free; P.accB = P.acc + (size_t)4 * n; P.accmax = P.acc + (size_t)ACC_N * n; P.maxslots = P.accmax + n;
+    P.n_ranks = has_exchange(h) ? h->n_ranks : 1; P.rank = h->rank;
     P.xp = (double *)(db + s_xp);
     for (size_t w = 0; w < h->bcr.size(); w++) {
         BcrW &B = h->bcr[w];
         const size_t nn = (size_t)B.N * B.m * B.m;
-        B.D = (double *)(db + s_bcr[4 * w]); B.U = B.D + nn; B.b = B.U + nn; B.hd = B.b + (size_t)B.N * B.m;
+        B.D = (double *)(db + s_bcr[4 * w]); B.U = B.D + nn; B.b = B.U + nn; B.hd = B.b + (size_t)B.N * B.m; B.tail = B.hd + (size_t)B.N * B.m;
+        B.pad = (has_exchange(h) && prof == PLBA_PROFILE_G) ? 1 : 0;       // the assemble-phase cost sums ride in the tail of the exchange
         B.Xl = (double *)(db + s_bcr[4 * w + 1]); B.Xr = (double *)(db + s_bcr[4 * w + 2]); B.y = (double *)(db + s_bcr[4 * w + 3]);
     }
     P.solve_nf_max = std::min(max_nf, (int)SMALL_NMAX / 6);
@@ -1060,33 +1186,48 @@ int plba_reset_state(plba_handle h) {
 
 }  // extern "C"
 
-// one LM round, host driven: (gate + lambda init) -> assemble -> [exchange] -> solve -> update -> [exchange] -> control
+// one LM round, host driven: (gate + lambda init) -> assemble -> [exchange] -> solve -> update -> [exchange] -> control.
+// need_prep: the host KNOWS that a window waits for its chi2 gate / initial lambda (synchronous loop) or cannot know (pipelined
+// loop: the prep kernels are launched every round and leave at once when nothing waits for them).
+// Exchange steps of the landmark-sharded path (has_exchange): per LM trial ONE all-reduce of the reduced camera system with the cost
+// sums riding along, plus 4 doubles per window after the update kernel; per prep block one all-reduce of [diag(H_pp) | slots of the
+// landmark-diagonal maxima].  All of them on the handle's stream: no host synchronisation.
 static int run_round(plba_handle h, bool need_prep) {
     DevP &P = h->P; cudaStream_t st = h->stream; const DevP *Pp = h->d_P;
     // (the block-cyclic-reduction solver clears what it consumes; the other large-window solvers leave S dirty)
     const bool bcr_active = bcr_is_active(h);
+    const bool xch = has_exchange(h);
     if (!h->small_path && !bcr_active) CK(cudaMemsetAsync(h->sysbuf, 0, sizeof(double) * (h->S_doubles + (size_t)12 * P.n_free), st));
     if (need_prep) {
         PLBA_LAUNCH(k_gate, dim3(h->grid_chunks), dim3(256), 0, st, Pp); h->timing.n_launches++;
         launch_assemble(h, 0);
-        allreduce(h, P.hpp_diag_init, (size_t)6 * P.n_free, 0);
-        allreduce(h, P.accmax, (size_t)P.n_win, 1);
+        if (xch) {
+            // [diag(H_pp) of the prep pass | acc | accB (both zero here) | accmax | one slot per rank]: the maximum travels as a sum of slots
+            PLBA_LAUNCH(k_pack_max, grid1(P.n_ranks * P.n_win, 128), dim3(128), 0, st, Pp); h->timing.n_launches++;
+            allreduce(h, P.hpp_diag_init, (size_t)6 * P.n_free + (size_t)ACC_N * P.n_win + (size_t)P.n_win + (size_t)P.n_ranks * P.n_win, 0);
+        }
         PLBA_LAUNCH(k_lambda_init, dim3(h->n_sm), dim3(128), 0, st, Pp); h->timing.n_launches++;
     }
     if (h->detail_timing) cudaEventRecord(h->ev[0], st);
     launch_assemble(h, 1);
     if (h->detail_timing) cudaEventRecord(h->ev[1], st);
-    if (!bcr_is_active(h)) allreduce(h, h->sysbuf, h->S_doubles + (size_t)12 * P.n_free, 0);   // the exchange step: S, g, hpp_diag (block cyclic reduction: the band only, after its gather)
-    allreduce(h, P.acc, (size_t)4 * P.n_win, 0);                                 // assemble-phase cost sums
+    if (xch) {
+        // the exchange step.  Dense / small windows: [S | g | diag(H_pp) | (zero) prep diagonal | cost sums] is one contiguous range.
+        // Block cyclic reduction: the band only, in node form, after its gather (launch_solve); the cost sums ride in its tail for
+        // profile G, the hand LM needs them before its pre-solve controller
+        if (!bcr_active) allreduce(h, h->sysbuf, h->S_doubles + (size_t)18 * P.n_free + (size_t)4 * P.n_win, 0);
+        else if (P.profile != PLBA_PROFILE_G) allreduce(h, P.acc, (size_t)4 * P.n_win, 0);
+    }
     launch_solve(h);
     if (h->detail_timing) cudaEventRecord(h->ev[2], st);
     launch_update(h, 0);
     if (h->detail_timing) cudaEventRecord(h->ev[3], st);
-    allreduce(h, P.accB, (size_t)4 * P.n_win, 0);                                // update-phase sums (new cost, scale, |dx|^2)
+    if (xch) allreduce(h, P.accB, (size_t)4 * P.n_win, 0);                     // update-phase sums (new cost, scale, |dx|^2)
     PLBA_LAUNCH(k_control, dim3(1), dim3(256), 0, st, Pp, 0); h->timing.n_launches++;
     return PLBA_OK;
 }
 
+enum { PLBA_ROUNDS_IN_FLIGHT = 2 };
 static int run_async(plba_handle h) {
     DevP &P = h->P; cudaStream_t st = h->stream;
     h->timing.ms_assemble = h->timing.ms_solve = h->timing.ms_update = 0;
@@ -1097,6 +1238,29 @@ static int run_async(plba_handle h) {
     }
 #endif
     int rc;
+#ifndef PLBA_HOST_EMU
+    if (!h->detail_timing) {
+        // Pipelined host-driven loop (large windows, sharded path): the host never waits for the round it has just launched.  The
+        // controller runs on the device; the host only needs to learn WHEN every window is done, and reads the counters of the round
+        // it launched PLBA_ROUNDS_IN_FLIGHT rounds ago (pinned copy + event), so the stream never drains.  At most that many rounds
+        // are launched in vain; their kernels return at once for finished windows.  No per-round cudaStreamSynchronize.
+        bool done = false;
+        for (int round = 0; round < P.max_rounds && !done; round++) {
+            if ((rc = run_round(h, true))) return rc;
+            const int slot = round % 4;
+            CK(cudaMemcpyAsync(h->h_poll + slot * CNT_N, P.counters, sizeof(int) * CNT_N, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(h->ev_poll[slot], st));
+            if (round >= PLBA_ROUNDS_IN_FLIGHT) {
+                const int old = (round - PLBA_ROUNDS_IN_FLIGHT) % 4;
+                CK(cudaEventSynchronize(h->ev_poll[old]));
+                done = h->h_poll[old * CNT_N + CNT_DONE] >= P.n_win;
+            }
+        }
+        if (h->nccl_failed) return PLBA_E_CUDA;
+        return PLBA_OK;
+    }
+#endif
+    // synchronous loop (per-stage event timing, host emulation): one round, one poll
     if ((rc = poll_counters(h))) return rc;
     for (int round = 0; round < P.max_rounds; round++) {
         if (h->h_counters[CNT_DONE] >= P.n_win) break;

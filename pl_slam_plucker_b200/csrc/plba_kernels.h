@@ -96,7 +96,9 @@ struct DevP {
     // linear system
     double *S, *gs, *xp, *hpp_diag, *hpp_diag_init;
     double *acc, *accB;               // [n_win][4] each: sum-reduced accumulators (tail of the reduced-system buffer)
-    double *accmax;                   // [n_win]         max-reduced: largest landmark diagonal (lambda init)
+    double *accmax;                   // [n_win]         largest landmark diagonal of this rank (lambda init)
+    double *maxslots;                 // [16][n_win]     sharded path: accmax of every rank, one slot each, so that the maximum travels inside a SUM exchange
+    int n_ranks, rank;
     WinCtrl *ctrl;
     const WinCtrl *ctrl0;             // initial controller state (reset)
     plba_trace_rec *trace; int trace_cap, solve_nf_max;   // solve_nf_max: most free keyframes of any window of the upload (thread-group size of k_solve_small)
@@ -594,6 +596,7 @@ PLBA_D void assemble_chunk(const DevP &Pin, const Chunk &ch, int mode) {
 // persistent grid: CTA b walks chunks b, b + gridDim, ... (points first, then lines)
 template <int PROF>
 PLBA_KERNEL void PLBA_BOUNDS(OC, PLBA_CTAS_PER_SM) k_assemble(const DevP *Pp, int mode) {
+    if (mode == 0 && Pp->counters[CNT_NEED_INIT] == 0) return;        // no window waits for its initial lambda (the counter only changes between launches)
     PLBA_PARAMS(P, Pp);
     const int ntot = P.n_chunks_pt + P.n_chunks_ls;
     for (int c = PLBA_BID; c < ntot; c += PLBA_NB) {
@@ -734,6 +737,7 @@ PLBA_D void lambda_init_window(const DevP &P, int w) {
     WinCtrl &c = P.ctrl[w];
     if (!c.done && c.need_init) {
         double m = plba_ld_l2(&P.accmax[w]);
+        if (P.n_ranks > 1) { m = 0.0; for (int r = 0; r < P.n_ranks; r++) { const double v = plba_ld_l2(&P.maxslots[(size_t)r * P.n_win + w]); if (v > m) m = v; } }
         const int s0 = P.win_slot0[w], nf = P.win_nfree[w];
         for (int i0 = 0; i0 < 6 * nf; i0 += 12) {      // twelve loads in flight (one thread per window: the loads, not the maximum, are the latency)
             double hv[12];
@@ -927,11 +931,23 @@ PLBA_KERNEL void PLBA_BOUNDS(OC, PLBA_CTAS_PER_SM) k_update(const DevP *Pp, int 
 }
 
 // ---- stand-alone per-window / per-keyframe kernels (host-driven loop: sharded multi-GPU and the tiled solver path) ----
+// (the prep kernels are launched unconditionally by the pipelined host loop: they leave at once when no window asks for them)
 PLBA_KERNEL void k_lambda_init(const DevP *Pp) {
     PLBA_PARAMS(P, Pp);
+    if (P.counters[CNT_NEED_INIT] == 0 && P.counters[CNT_GATE] == 0) return;
     PHASE_BEGIN
         for (int w = PLBA_BID * PLBA_NT + tid; w < P.n_win; w += PLBA_NB * PLBA_NT) lambda_init_window(P, w);
         if (PLBA_BID == 0 && tid == 0) P.counters[CNT_PREPS]++;
+    PHASE_END
+}
+// sharded path, before the prep exchange: this rank's landmark-diagonal maximum goes into its slot, the other slots are cleared
+PLBA_KERNEL void k_pack_max(const DevP *Pp) {
+    PLBA_PARAMS(P, Pp);
+    PHASE_BEGIN
+        for (int i = PLBA_BID * PLBA_NT + tid; i < P.n_ranks * P.n_win; i += PLBA_NB * PLBA_NT) {
+            const int r = i / P.n_win, w = i - r * P.n_win;
+            P.maxslots[i] = (r == P.rank) ? P.accmax[w] : 0.0;
+        }
     PHASE_END
 }
 PLBA_KERNEL void k_control_h_pre(const DevP *Pp) {
@@ -979,6 +995,7 @@ PLBA_D void gate_obs(const DevP &P, int o) {
 }
 PLBA_KERNEL void k_gate(const DevP *Pp) {
     PLBA_PARAMS(P, Pp);
+    if (P.counters[CNT_GATE] == 0) return;
     PHASE_BEGIN
         for (int o = PLBA_BID * PLBA_NT + tid; o < P.n_pobs; o += PLBA_NB * PLBA_NT) gate_obs<LT_POINT>(P, o);
         for (int o = PLBA_BID * PLBA_NT + tid; o < P.n_lobs; o += PLBA_NB * PLBA_NT) gate_obs<LT_LINE_ORTH>(P, o);

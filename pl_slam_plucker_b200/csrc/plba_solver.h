@@ -925,8 +925,8 @@ PLBA_KERNEL void k_solve_banded(const DevP *Pp, int bwb) {
 // the levels are walked back:  L^T x_i = y - Xl^T x_{i-s} - Xr^T x_{i+s}.
 // This is a Cholesky factorisation in a nested-dissection order of the keyframe chain: same system, same solution up to rounding,
 // but the 6 Nkf sequential pivots of the banded factorisation become 90 ceil(log2 N) and every level fills the GPU.
-struct BcrW { double *D, *U, *b, *hd, *Xl, *Xr, *y; int N, bs, m, pad; };   // node storage: D, U, Xl, Xr: [N][m*m] (row stride m); b, hd, y: [N][m];
-                                                                           // [D | U | b | hd] is one contiguous range: the exchange step of the sharded path
+struct BcrW { double *D, *U, *b, *hd, *tail, *Xl, *Xr, *y; int N, bs, m, pad; };   // node storage: D, U, Xl, Xr: [N][m*m] (row stride m); b, hd, y: [N][m];
+                                                                           // [D | U | b | hd | tail] is one contiguous range: the exchange step of the sharded path (tail: the window's 4 assemble-phase cost sums ride along, 8 doubles)
 enum { BCR_BS_MAX = 15, BCR_M_MAX = 6 * BCR_BS_MAX, BCR_NT = 512 };
 static inline size_t bcr_elim_smem() { return sizeof(double) * ((size_t)(3 * BCR_M_MAX + 1) * (BCR_M_MAX + 1) + BCR_M_MAX + 21 * BCR_BS_MAX + 6 * 264 + 8) + 64; }
 static inline size_t bcr_back_smem() { return sizeof(double) * ((size_t)BCR_M_MAX * (BCR_M_MAX + 1) + 7 * BCR_M_MAX + 8) + 64; }
@@ -939,6 +939,11 @@ PLBA_HD int bcr_node_size(const BcrW &B, int nf, int i) { const int k0 = i * B.b
 PLBA_KERNEL void k_bcr_gather(const DevP *Pp, int w, BcrW B) {
     PLBA_PARAMS(P, Pp);
     const WinCtrl &ctl = P.ctrl[w];
+    // the assemble-phase cost sums of the window travel in the tail of the node storage: ONE exchange per LM trial (profile G reads
+    // them only in the controller, after the solve).  Written even for a finished window, so that the tail never accumulates.
+    PHASE_BEGIN
+        if (PLBA_BID == 0 && tid < 8) B.tail[tid] = (tid < 4 && !ctl.done) ? P.acc[(size_t)4 * w + tid] : 0.0;
+    PHASE_END
     if (ctl.done) return;
     const int nf = P.win_nfree[w], n = 6 * nf, slot0 = P.win_slot0[w], m = B.m;
     double *Sw = P.S + P.win_S_off[w];
@@ -1066,6 +1071,11 @@ PLBA_KERNEL void k_bcr_back(const DevP *Pp, int w, BcrW B, int s, int final) {
     PLBA_PARAMS(P, Pp);
     const WinCtrl &ctl = P.ctrl[w];
     if (ctl.done) return;
+    if (final && B.pad) {      // B.pad != 0: the cost sums were exchanged in the tail (sharded profile G): hand them to the controller
+        PHASE_BEGIN
+            if (tid < 4) P.acc[(size_t)4 * w + tid] = B.tail[tid];
+        PHASE_END
+    }
     const int nf = P.win_nfree[w], m = B.m, ldm = m + 1, slot0 = P.win_slot0[w];
     const int i = final ? 0 : (2 * PLBA_BID + 1) * s;
     const int left = final ? -1 : i - s, right = (final || i + s >= B.N) ? -1 : i + s;

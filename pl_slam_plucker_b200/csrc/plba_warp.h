@@ -27,7 +27,13 @@ namespace plba {
 #ifndef PLBA_W_PASSES
 #define PLBA_W_PASSES 8
 #endif
-enum { WARPS_PER_CTA = 4, WNT = 32 * WARPS_PER_CTA, W_CTAS_PER_SM = PLBA_W_CTAS, W_MAX_TRACK = 32, W_ITEM_PASSES_MAX = PLBA_W_PASSES };
+#ifndef PLBA_W_FULL
+#define PLBA_W_FULL 0      // 1: a Schur task = a whole 6x6 block (36 accumulators per lane), 0: a column half (18 accumulators)
+#endif
+#ifndef PLBA_W_WARPS
+#define PLBA_W_WARPS 4
+#endif
+enum { WARPS_PER_CTA = PLBA_W_WARPS, WNT = 32 * WARPS_PER_CTA, W_CTAS_PER_SM = PLBA_W_CTAS, W_MAX_TRACK = 32, W_ITEM_PASSES_MAX = PLBA_W_PASSES };
 
 // per-warp shared memory: [component][lane] so that lane-indexed accesses are conflict free
 template <int PROF, int LT>
@@ -182,10 +188,16 @@ PLBA_D void prefetch_obs_w(const DevP &P, const WinCtrl &ctl, int o, int lm, con
 template <int PROF, int LT>
 struct WRec {
     typedef KT<PROF, LT> K;
-    // A (the pose rows) is stored as [column half][row of the residual][3 + one pad]: a Schur task that owns three columns of a 6x6
-    // block reads "its" half of A_b as one aligned run
-    enum { RANK = K::RANK, D = K::D, NAH = RANK * 4, NA = 2 * NAH, NB = RANK * D, NBp = (NB + 1) & ~1, NEp = (RANK + 1) & ~1, NVp = (D + 1) & ~1,
-           OA = 0, OB = NA, OT = OB + NBp, OE = OT + NBp, OV = OE + NEp, SIZE = OV + NVp, STRIDE = ((SIZE / 2) % 2 == 1) ? SIZE : SIZE + 2 };
+    // A (the pose rows) is stored as [column half][row of the residual][3]: a Schur task that owns three columns of a 6x6 block reads
+    // "its" half of A_b as one aligned run (two residual rows: 6 doubles, no padding; one row: 3 + one pad)
+#if PLBA_W_FULL
+    enum { RANK = K::RANK, D = K::D, NAH = RANK * 3, AHS = 3, NA = RANK * 6, NB = RANK * D,      // whole-block tasks: A as [row of the residual][6]
+#else
+    enum { RANK = K::RANK, D = K::D, NAH = (RANK * 3 + 1) & ~1, AHS = NAH / RANK, NA = 2 * NAH, NB = RANK * D,      // AHS: row stride inside a half (3, or 4 with a pad when RANK * 3 is odd)
+#endif
+           NBp = (NB + 1) & ~1, NEp = (RANK + 1) & ~1, NVp = (D + 1) & ~1,
+           NVp_ = NVp, OA = 0, OB = NA, OT = OB + NBp, OE = OT + NBp, OV = OE + NEp, SIZE = OV + NVp, STRIDE = ((SIZE / 2) % 2 == 1) ? SIZE : SIZE + 2,
+           NACC = PLBA_W_FULL ? 36 : 18, NG = PLBA_W_FULL ? 6 : 3 };
     static PLBA_HD size_t bytes() { return sizeof(double) * STRIDE * 32 + sizeof(int) * 64; }
 };
 template <int N> PLBA_HD void wrec_ld(const double *p, double *r) {      // N even, p 16-byte aligned
@@ -201,6 +213,126 @@ template <int N> PLBA_HD void wrec_st(double *p, const double *r) {
 // Both halves need M = Ta B^T (4 D FMAs), but each computes only its three columns of M A_b and of the block: 60 FMAs per landmark
 // and half against the 72 of the round-1 split by rows (where both halves computed all of M A_b), with 18 accumulators per lane
 // (whole blocks, 36 accumulators, spill around the linearisation at 168 registers: measured 2.10 against 1.92 ms at config 5).
+#if PLBA_W_FULL
+struct WTask { int on, pa, pb, sa, sb, half, diag, slice; };
+// whole-block variant: per landmark and pair 4 D + 12 RANK + 36 RANK FMAs on 36 doubles read from shared memory (3 FMAs per double;
+// the column-half variant: 1.7).  The shared-memory pipe delivers 4 bytes per lane and clock whatever the access width or the
+// multicast, so the Schur phase is bound by the doubles it reads.
+PLBA_HD void wtask_decode(int task, int nf, const int *fpos, const int *slot, int slot0, WTask &t) {
+    t.half = 0;
+    int q = task, i = 0;
+    while (q >= nf - i) { q -= nf - i; i++; }
+    const int j = i + q;
+    t.pa = fpos[i]; t.pb = fpos[j];
+    t.sa = slot[t.pa] - slot0; t.sb = slot[t.pb] - slot0;
+    t.diag = (i == j) ? 1 : 0;
+}
+template <int PROF, int LT, int mode>
+PLBA_D void wtask_accumulate(const double *rec, const WTask &t, int k, int first, int step, int nlp, double *blk, double *gv, double *hd) {
+    typedef WRec<PROF, LT> R;
+    const int D = R::D, RANK = R::RANK;
+    for (int m = first; m < nlp; m += step) {
+        const double *ra = rec + (size_t)(m * k + t.pa) * R::STRIDE, *rb = rec + (size_t)(m * k + t.pb) * R::STRIDE;
+        double Aa[R::NA];
+        wrec_ld<R::NA>(ra + R::OA, Aa);
+        if ((PROF != PLBA_PROFILE_G || mode == 0) && t.diag) {        // diag(H_pp): lambda init (all profiles) and the hand LM's multiplicative damping
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+#pragma unroll
+                for (int kk = 0; kk < RANK; kk++) hd[r] += Aa[kk * 6 + r] * Aa[kk * 6 + r];
+            }
+        }
+        if (mode == 0) continue;
+        double MA[RANK * 6];
+        {
+            double M[RANK * RANK], Ta[R::NBp], Bb[R::NBp], Ab[R::NA];
+            wrec_ld<R::NBp>(ra + R::OT, Ta); wrec_ld<R::NBp>(rb + R::OB, Bb); wrec_ld<R::NA>(rb + R::OA, Ab);
+#pragma unroll
+            for (int kk = 0; kk < RANK; kk++) {
+#pragma unroll
+                for (int k2 = 0; k2 < RANK; k2++) {
+                    double sum = (t.diag && kk == k2) ? -1.0 : 0.0;          // diagonal: A^T (Ta B^T - I) A, subtracted below
+#pragma unroll
+                    for (int mm = 0; mm < D; mm++) sum += Ta[kk * D + mm] * Bb[k2 * D + mm];
+                    M[kk * RANK + k2] = sum;
+                }
+            }
+            if (t.diag) {
+                double ev[R::NEp], V[R::NVp_];
+                wrec_ld<R::NEp>(ra + R::OE, ev); wrec_ld<R::NVp_>(ra + R::OV, V);
+#pragma unroll
+                for (int kk = 0; kk < RANK; kk++) {
+#pragma unroll
+                    for (int mm = 0; mm < D; mm++) ev[kk] += Bb[kk * D + mm] * V[mm];
+                }
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+#pragma unroll
+                    for (int kk = 0; kk < RANK; kk++) gv[r] -= Aa[kk * 6 + r] * ev[kk];
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < RANK; kk++) {
+#pragma unroll
+                for (int c = 0; c < 6; c++) {
+                    double sum = 0;
+#pragma unroll
+                    for (int k2 = 0; k2 < RANK; k2++) sum += M[kk * RANK + k2] * Ab[k2 * 6 + c];
+                    MA[kk * 6 + c] = sum;
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+#pragma unroll
+            for (int kk = 0; kk < RANK; kk++) {
+                const double av = Aa[kk * 6 + r];
+#pragma unroll
+                for (int c = 0; c < 6; c++) blk[r * 6 + c] -= av * MA[kk * 6 + c];
+            }
+        }
+    }
+}
+template <int PROF, int mode>
+PLBA_D void wtask_flush(const DevP &P, const WTask &t, double *Sw, int ld, int slot0, const double *blk, const double *gv, const double *hd) {
+    if (mode == 0) {
+        if (t.diag) {
+#pragma unroll
+            for (int r = 0; r < 6; r++) plba_atomic_add(&P.hpp_diag_init[(size_t)6 * (slot0 + t.sa) + r], hd[r]);
+        }
+        return;
+    }
+    const bool tr = (t.sa > t.sb);
+    const int ra = tr ? t.sb : t.sa, cb = tr ? t.sa : t.sb;
+    const long long sr = tr ? 1 : ld, sc = tr ? ld : 1;
+    double *p0 = Sw + (size_t)(6 * ra) * ld + 6 * cb;
+    const bool upper_only = (t.sa == t.sb);                        // diagonal block of S: only its upper triangle is stored
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            if (!upper_only || r <= c) plba_atomic_add(p0 + r * sr + c * sc, blk[r * 6 + c]);
+        }
+    }
+    if (t.diag) {
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            plba_atomic_add(&P.gs[(size_t)6 * (slot0 + t.sa) + r], gv[r]);
+            if (PROF != PLBA_PROFILE_G) plba_atomic_add(&P.hpp_diag[(size_t)6 * (slot0 + t.sa) + r], hd[r]);
+        }
+    } else if (upper_only) {
+        // transposed copy of an off-track-diagonal block that landed on the diagonal of S
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                if (c <= r) plba_atomic_add(p0 + (size_t)c * ld + r, blk[r * 6 + c]);
+            }
+        }
+    }
+}
+
+#else
 struct WTask { int on, pa, pb, sa, sb, half, diag, slice; };
 PLBA_HD void wtask_decode(int task, int nf, const int *fpos, const int *slot, int slot0, WTask &t) {
     const int p = task >> 1;
@@ -227,7 +359,7 @@ PLBA_D void wtask_accumulate(const double *rec, const WTask &t, int k, int first
 #pragma unroll
             for (int cc = 0; cc < 3; cc++) {
 #pragma unroll
-                for (int kk = 0; kk < RANK; kk++) hd[cc] += Ah[kk * 4 + cc] * Ah[kk * 4 + cc];
+                for (int kk = 0; kk < RANK; kk++) hd[cc] += Ah[kk * R::AHS + cc] * Ah[kk * R::AHS + cc];
             }
         }
         if (mode == 0) continue;
@@ -257,7 +389,7 @@ PLBA_D void wtask_accumulate(const double *rec, const WTask &t, int k, int first
 #pragma unroll
                 for (int cc = 0; cc < 3; cc++) {
 #pragma unroll
-                    for (int kk = 0; kk < RANK; kk++) gv[cc] -= Abh[kk * 4 + cc] * ev[kk];      // (diagonal task: record b == record a)
+                    for (int kk = 0; kk < RANK; kk++) gv[cc] -= Abh[kk * R::AHS + cc] * ev[kk];      // (diagonal task: record b == record a)
                 }
             }
 #pragma unroll
@@ -266,7 +398,7 @@ PLBA_D void wtask_accumulate(const double *rec, const WTask &t, int k, int first
                 for (int cc = 0; cc < 3; cc++) {
                     double sum = 0;
 #pragma unroll
-                    for (int k2 = 0; k2 < RANK; k2++) sum += M[kk * RANK + k2] * Abh[k2 * 4 + cc];
+                    for (int k2 = 0; k2 < RANK; k2++) sum += M[kk * RANK + k2] * Abh[k2 * R::AHS + cc];
                     MA[kk * 3 + cc] = sum;
                 }
             }
@@ -279,7 +411,7 @@ PLBA_D void wtask_accumulate(const double *rec, const WTask &t, int k, int first
             for (int rr = 0; rr < 3; rr++) {
 #pragma unroll
                 for (int kk = 0; kk < RANK; kk++) {
-                    const double av = Aa[kk * 4 + rr];
+                    const double av = Aa[kk * R::AHS + rr];
 #pragma unroll
                     for (int cc = 0; cc < 3; cc++) blk[(3 * h + rr) * 3 + cc] -= av * MA[kk * 3 + cc];
                 }
@@ -332,6 +464,8 @@ PLBA_D void wtask_flush(const DevP &P, const WTask &t, double *Sw, int ld, int s
     }
 }
 
+#endif
+
 // ---------------------------------------------------------------------------------------------------------
 // assembly: mode 0 = diagonal pass for the initial lambda (computeLambdaInit / Hmax, :2555-2561); mode 1 = full
 // ---------------------------------------------------------------------------------------------------------
@@ -345,7 +479,7 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
     double *rec = (double *)wraw;                                 // [32] records of the pass
     int *slot_s = (int *)(rec + (size_t)R::STRIDE * 32), *fpos_s = slot_s + 32;
     LANE_VAR(double, cost_l); LANE_VAR(double, maxd_l);
-    LANE_ARR(double, blk, 18); LANE_ARR(double, gv, 3); LANE_ARR(double, hd, 3);
+    LANE_ARR(double, blk, R::NACC); LANE_ARR(double, gv, R::NG); LANE_ARR(double, hd, R::NG);
     LANE_VAR(WTask, tk);
     LANE_VAR(int, kf_l); LANE_VAR(int, m_l);
     int cur_win = -1;
@@ -382,7 +516,7 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
         const int k = it.k, nf = it.nfree;
         const int lpp = 32 / k;                                  // landmarks per pass
         const int npass = (it.n_lm + lpp - 1) / lpp;
-        const int ntask = nf * (nf + 1);                          // (pairs i <= j) x 2 column halves
+        const int ntask = PLBA_W_FULL ? nf * (nf + 1) / 2 : nf * (nf + 1);      // pairs i <= j (x 2 column halves)
         const int rounds = (ntask + 31) >> 5;
         const bool keep = (rounds == 1);                          // the lane's block stays in registers for the whole item
         const int nslice = keep ? 32 / ntask : 1;                 // few tasks: the landmarks of a pass are dealt over several lanes per task
@@ -404,9 +538,9 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
                 tk.on = (slice < nslice) ? 1 : 0; tk.slice = slice;
                 if (tk.on) wtask_decode(task, nf, fpos_s, slot_s, slot0, tk);
 #pragma unroll
-                for (int i = 0; i < 18; i++) blk[i] = 0.0;
+                for (int i = 0; i < R::NACC; i++) blk[i] = 0.0;
 #pragma unroll
-                for (int i = 0; i < 3; i++) { gv[i] = 0.0; hd[i] = 0.0; }
+                for (int i = 0; i < R::NG; i++) { gv[i] = 0.0; hd[i] = 0.0; }
             WPHASE_END
         }
         for (int pass = 0; pass < npass; pass++) {
@@ -427,17 +561,21 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
                     obs_lin_w<PROF, LT>(P, ctl, o, kf_l, lmd, ob, A, B, e, cost);
                     if (mode == 1) cost_l += cost;
                     double *r = rec + (size_t)lane * R::STRIDE;
+#if PLBA_W_FULL
+                    wrec_st<R::NA>(r + R::OA, A); wrec_st<R::NBp>(r + R::OB, B); wrec_st<R::NEp>(r + R::OE, e);
+#else
                     double Ah[R::NA];
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
 #pragma unroll
                         for (int kk = 0; kk < RANK; kk++) {
 #pragma unroll
-                            for (int cc = 0; cc < 3; cc++) Ah[h * R::NAH + kk * 4 + cc] = A[kk * 6 + 3 * h + cc];
-                            Ah[h * R::NAH + kk * 4 + 3] = 0.0;
+                            for (int cc = 0; cc < 3; cc++) Ah[h * R::NAH + kk * R::AHS + cc] = A[kk * 6 + 3 * h + cc];
                         }
+                        if (R::NAH > RANK * 3) Ah[h * R::NAH + R::NAH - 1] = 0.0;
                     }
                     wrec_st<R::NA>(r + R::OA, Ah); wrec_st<R::NBp>(r + R::OB, B); wrec_st<R::NEp>(r + R::OE, e);
+#endif
                 }
             WPHASE_END
             // ---- per landmark (redundantly on each of its lanes): H_ll, b_l, damping, inverse; Ta = Bt H_ll^-1, v = H_ll^-1 b_l (subsystem 2) ----
@@ -513,9 +651,9 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
                         tk.on = (task < ntask) ? 1 : 0; tk.slice = 0;
                         if (tk.on) wtask_decode(task, nf, fpos_s, slot_s, slot0, tk);
 #pragma unroll
-                        for (int i = 0; i < 18; i++) blk[i] = 0.0;
+                        for (int i = 0; i < R::NACC; i++) blk[i] = 0.0;
 #pragma unroll
-                        for (int i = 0; i < 3; i++) { gv[i] = 0.0; hd[i] = 0.0; }
+                        for (int i = 0; i < R::NG; i++) { gv[i] = 0.0; hd[i] = 0.0; }
                     }
                     if (tk.on) {
                         wtask_accumulate<PROF, LT, mode>(rec, tk, k, tk.slice, nslice, nlp, blk, gv, hd);
@@ -546,6 +684,7 @@ template <int PROF> PLBA_HD size_t WSmemMax<PROF>::bytes() {
 
 template <int PROF>
 PLBA_KERNEL void PLBA_BOUNDS(WNT, W_CTAS_PER_SM) k_assemble_w(const DevP *Pp, int mode) {
+    if (mode == 0 && Pp->counters[CNT_NEED_INIT] == 0) return;        // no window waits for its initial lambda (the counter only changes between launches)
     PLBA_SMEM(raw);
     PLBA_PARAMS(P, Pp);
     unsigned char *wraw = raw + (size_t)PLBA_WARP_IN_CTA * WSmemMax<PROF>::bytes();
@@ -553,8 +692,12 @@ PLBA_KERNEL void PLBA_BOUNDS(WNT, W_CTAS_PER_SM) k_assemble_w(const DevP *Pp, in
         assemble_items_w<PROF, LT_POINT, 0>(P, P.witems_pt, P.n_witems_pt, wraw);
         assemble_items_w<PROF, LineOf<PROF>::LT, 0>(P, P.witems_ls, P.n_witems_ls, wraw);
     } else {
+#ifndef PLBA_W_EXP_NO_PT
         assemble_items_w<PROF, LT_POINT, 1>(P, P.witems_pt, P.n_witems_pt, wraw);
+#endif
+#ifndef PLBA_W_EXP_NO_LS
         assemble_items_w<PROF, LineOf<PROF>::LT, 1>(P, P.witems_ls, P.n_witems_ls, wraw);
+#endif
     }
     // the last CTA out re-arms the work counters for the next launch
     PHASE_BEGIN

@@ -7,8 +7,11 @@ step: the reduced camera system [S | g | diag(H_pp)] and the cost scalars are su
 NVLink on the GPUs; gloo in the CPU tests), after which every rank solves the same small system, back-substitutes its own
 landmarks and takes the same LM decision.  There is no other data-path collective.
 
-The all-reduce itself is `torch.distributed` plumbing handed to the library as a callback (plba_set_allreduce); the
-library calls it on its own stream between the assembly and the solve kernels.
+On GPUs the collective lives INSIDE the library: `ShardedLBA(..., nccl=True)` has rank 0 create an NCCL unique id
+(plba_comm_unique_id), ships it to the other ranks over torch.distributed (plumbing: a 128-byte broadcast, any backend) and
+every rank calls plba_comm_init_rank(); from then on the library itself issues ncclAllReduce on its stream, with no host
+synchronisation inside the LM loop — exactly what a C++ host gets.  `nccl=False` hands the library a
+caller-supplied all-reduce instead (plba_set_allreduce): that is how the CPU tests run the same protocol over gloo.
 """
 import numpy as np
 
@@ -87,18 +90,34 @@ class ShardedLBA:
     """One rank of a landmark-sharded LBA.  `solver` is this rank's LBASolver; `P` the FULL problem (every rank holds it,
     or at least its own shard plus the keyframe table)."""
 
-    def __init__(self, solver, rank, world, group=None, device=None):
+    def __init__(self, solver, rank, world, group=None, device=None, nccl=False):
         self.solver, self.rank, self.world = solver, int(rank), int(world)
-        self._fn = make_allreduce(group, device)
-        self.solver.set_allreduce(self._fn)
         self.shard = self.pt_index = self.ls_index = None
+        if nccl:
+            import torch
+            import torch.distributed as dist
+            dev = torch.device(device) if device is not None else torch.device("cpu")
+            uid = torch.zeros(128, dtype=torch.uint8, device=dev if dist.get_backend(group) == "nccl" else "cpu")
+            if self.rank == 0:
+                uid.copy_(torch.tensor(list(self.solver.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, src=0, group=group)
+            self.solver.comm_init_rank(self.world, self.rank, bytes(uid.cpu().tolist()))
+            self._fn = None
+        else:
+            self._fn = make_allreduce(group, device)
+            self.solver.set_allreduce(self._fn)
+            self.solver.set_allreduce_ranks(self.world, self.rank)
 
     def upload(self, P, opt):
         if opt.profile != abi.PROFILE_G:
             raise ValueError("sharding is defined for profile G (the Plücker-mode LBA of BASELINE configs 4-5)")
+        # emptiness is decided from the FULL problem, identically on every rank, before anything collective happens: a rank that
+        # raised alone would leave the others blocked in the first exchange
+        for r in range(self.world):
+            mp_, ml_ = shard_masks(P, r, self.world)
+            if int(mp_[P.po_lm].sum()) + int(ml_[P.lo_lm].sum()) == 0:
+                raise ValueError("rank %d would receive an empty shard: use fewer ranks for this window" % r)
         self.shard, self.pt_index, self.ls_index = shard_problem(P, self.rank, self.world)
-        if self.shard.n_obs == 0:
-            raise ValueError("rank %d received an empty shard: use fewer ranks for this window" % self.rank)
         self.full = P
         self.solver.upload(self.shard, opt)
 

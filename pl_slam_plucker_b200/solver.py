@@ -12,19 +12,23 @@ class LBAError(RuntimeError):
 class LBASolver:
     """B200 LBA solver handle.  `solve()` is the drop-in for the reference's three LBA functions (see include/plba.h)."""
 
-    def __init__(self, device=0, stream=None, lib=None):
+    def __init__(self, device=0, stream=None, lib=None, _handle=None):
         self.L = lib or _lib.load()
         self.h = C.c_void_p()
-        rc = self.L.plba_create(int(device), C.c_void_p(stream) if stream else None, C.byref(self.h))
-        if rc != 0 or not self.h:
-            raise LBAError("plba_create(device=%d) failed (%d): a CUDA device is required; there is no CPU fallback" % (device, rc))
+        self._owned = _handle is None
+        if _handle is not None:
+            self.h = C.c_void_p(_handle)                 # a member of a plba_create_group() group (LBAGroup owns it)
+        else:
+            rc = self.L.plba_create(int(device), C.c_void_p(stream) if stream else None, C.byref(self.h))
+            if rc != 0 or not self.h:
+                raise LBAError("plba_create(device=%d) failed (%d): a CUDA device is required; there is no CPU fallback" % (device, rc))
         self._cb = None
         self._probs = None
 
     def close(self):
-        if self.h:
+        if self.h and self._owned:
             self.L.plba_destroy(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -135,6 +139,28 @@ class LBASolver:
         self._cb = _lib.ALLREDUCE_FN(_cb)
         self._check(self.L.plba_set_allreduce(self.h, self._cb, None))
 
+    # ---- landmark-sharded multi-GPU: the collective lives in the library (NCCL on the handle's stream) ----
+    def comm_unique_id(self):
+        """128 bytes that rank 0 hands to the other ranks (any transport) before comm_init_rank()."""
+        buf = (C.c_ubyte * 128)()
+        self._check(self.L.plba_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init_rank(self, nranks, rank, unique_id):
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self.L.plba_comm_init_rank(self.h, int(nranks), int(rank), buf))
+
+    def comm_destroy(self):
+        self._check(self.L.plba_comm_destroy(self.h))
+
+    def comm_info(self):
+        out = (C.c_int32 * 2)()
+        self._check(self.L.plba_comm_info(self.h, out))
+        return int(out[0]), int(out[1])
+
+    def set_allreduce_ranks(self, nranks, rank):
+        self._check(self.L.plba_set_allreduce_ranks(self.h, int(nranks), int(rank)))
+
     def set_detail_timing(self, on=True):
         self.L.plba_set_detail_timing(self.h, 1 if on else 0)
 
@@ -142,3 +168,25 @@ class LBASolver:
         t = abi.plba_timing()
         self.L.plba_get_timing(self.h, C.byref(t))
         return {k: getattr(t, k) for k, _ in abi.plba_timing._fields_}
+
+
+class LBAGroup:
+    """One process, several GPUs: plba_create_group() = one handle per device + one NCCL communicator over them (ncclCommInitAll).
+    Drive each member from its own host thread (every member takes part in every collective)."""
+
+    def __init__(self, devices, lib=None):
+        self.L = lib or _lib.load()
+        n = len(devices)
+        devs = (C.c_int32 * n)(*[int(d) for d in devices])
+        self._hs = (C.c_void_p * n)()
+        rc = self.L.plba_create_group(n, devs, self._hs)
+        if rc != 0:
+            raise LBAError("plba_create_group(%s) failed (%d)" % (list(devices), rc))
+        self.members = [LBASolver(lib=self.L, _handle=self._hs[i]) for i in range(n)]
+
+    def close(self):
+        if self._hs is not None:
+            self.L.plba_destroy_group(len(self.members), self._hs)
+            for m in self.members:
+                m.h = C.c_void_p()
+            self._hs = None

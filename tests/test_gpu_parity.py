@@ -413,6 +413,62 @@ def test_two_handles_on_different_devices_in_one_process(oracle):
         s0.close(); s1.close()
 
 
+@pytest.mark.parametrize("shape", ["small", "banded", "C4"])
+def test_sharded_two_gpus_equal_single_gpu_and_oracle(oracle, shape):
+    """The landmark-sharded path on 2 GPUs of one box, driven as a C++ host would drive it: plba_create_group() (one handle per device,
+    NCCL communicator inside the library), one host thread per handle, every rank uploads its shard.  The collective is the library's
+    own ncclAllReduce on the handle's stream.  Result == the oracle on the whole window (cost 1e-9, state 1e-8) on every rank."""
+    import threading
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from pl_slam_plucker_b200 import sharded, solver
+    if shape == "small":
+        P = scene.make_scene(1, seed=31, n_kf_free=8, n_kf_fixed=2, n_pt=300, n_ls=80); q = 0        # one-CTA solver: [S | g | ...] is exchanged
+    elif shape == "banded":
+        P = scene.make_scene(1, seed=31, n_kf_free=40, n_kf_fixed=2, n_pt=800, n_ls=200); q = 1      # block cyclic reduction: the band in node form
+    else:
+        P = scene.make_scene(4); q = 0                                                                # BASELINE config 4 at full size, profile G faithful
+    opt = abi.Options(abi.PROFILE_G, q)
+    oracle.set_threads(os.cpu_count() or 1)
+    o = oracle.solve(P, opt)
+    world = 2
+    grp = solver.LBAGroup(list(range(world)))
+    res, errs = [None] * world, []
+
+    def work(r):
+        try:
+            s = grp.members[r]
+            assert s.comm_info() == (world, r)
+            shard, pti, lsi = sharded.shard_problem(P, r, world)
+            s.upload(shard, opt)
+            s.run()
+            res[r] = (s.download()[0], pti, lsi, s.timing(), s.kernel_path())
+        except Exception as e:      # noqa: BLE001
+            errs.append((r, repr(e)))
+    try:
+        th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+        [t.start() for t in th]; [t.join(600) for t in th]
+        assert not errs, errs
+        assert all(x is not None for x in res)
+        for r in range(world):
+            rr, pti, lsi, tm, kp = res[r]
+            assert tm["n_launches_run"] > 0
+            n = assert_trace_close(o.trace, rr.trace, abi.PROFILE_G)
+            assert n >= 10
+            np.testing.assert_allclose(rr.kf_T_wc, o.kf_T_wc, rtol=0, atol=STATE_ATOL)
+            np.testing.assert_allclose(rr.pt_xyz, o.pt_xyz[pti], rtol=0, atol=STATE_ATOL)
+            np.testing.assert_allclose(rr.ls_orth, o.ls_orth[lsi], rtol=0, atol=STATE_ATOL)
+            np.testing.assert_allclose(rr.ls_plk, o.ls_plk[lsi], rtol=0, atol=STATE_ATOL)
+            mp_, ml_ = sharded.shard_masks(P, r, world)
+            near = np.abs(o.po_chi2[mp_[P.po_lm]] - 5.991) < 1e-6
+            assert ((rr.po_flags == o.po_flags[mp_[P.po_lm]]) | near).all()
+        if shape != "small":
+            assert res[0][4]["solver"] == "block-cyclic-reduction"
+    finally:
+        grp.close()
+
+
 def test_config5_full_size_properties(gpu_solver):
     """BASELINE config 5 at full size (2 000 KFs, 2 M points, 500 k lines, dense 12 000^2 reduced system on the tiled
     DMMA Cholesky): the invariants that need no oracle run."""
