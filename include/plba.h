@@ -197,6 +197,9 @@ int  plba_copy_reduced_system(plba_handle h, int32_t window, double *S_out, doub
  * two CUDA events on the handle's stream.  which: 0 = assembly (linearise + blocks + Schur), 1 = reduced-system solve,
  * 2 = update (back-substitution + retraction + new cost).  The LM state is not advanced. */
 int  plba_time_kernel(plba_handle h, int32_t which, int32_t reps, double lambda, double *ms_avg);
+/* Measured FP64 roof of the device (the denominators of an FP64-bound roofline are measured, not nominal): which 0 = DFMA on the vector
+ * pipe, 1 = mma.sync.m8n8k4.f64 on the tensor pipe; best of `reps` launches, CUDA events; TFLOP/s. */
+int  plba_measure_fp64_peak(plba_handle h, int32_t which, int32_t reps, double *tflops);
 /* Large windows (6 n_free > 144): the reduced camera system is solved by a banded Cholesky when no landmark track spans more
  * than 15 free keyframes (sliding-window shape), by the dense tensor-core (FP64 DMMA) Cholesky otherwise.  on != 0 forces the
  * dense path (benchmarks, tests). */

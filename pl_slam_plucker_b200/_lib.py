@@ -12,7 +12,7 @@ ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
 
 EXPORTS = ["plba_version", "plba_default_options", "plba_create", "plba_destroy", "plba_last_error", "plba_solve", "plba_solve_batch",
            "plba_upload", "plba_reset_state", "plba_run", "plba_download", "plba_trial_assemble", "plba_trial_finish",
-           "plba_reduced_system", "plba_copy_reduced_system", "plba_time_kernel", "plba_layout_stats", "plba_kernel_path", "plba_track_default_options", "plba_track_solve", "plba_create_lines", "plba_set_force_dense", "plba_set_force_chunk", "plba_set_allreduce", "plba_set_allreduce_ranks", "plba_comm_unique_id", "plba_comm_init_rank", "plba_comm_destroy", "plba_create_group", "plba_destroy_group", "plba_comm_info", "plba_get_timing", "plba_set_detail_timing", "plba_scene_preset", "plba_scene_create",
+           "plba_reduced_system", "plba_copy_reduced_system", "plba_time_kernel", "plba_layout_stats", "plba_kernel_path", "plba_track_default_options", "plba_track_solve", "plba_create_lines", "plba_set_force_dense", "plba_set_force_chunk", "plba_set_allreduce", "plba_set_allreduce_ranks", "plba_comm_unique_id", "plba_comm_init_rank", "plba_comm_destroy", "plba_create_group", "plba_destroy_group", "plba_comm_info", "plba_measure_fp64_peak", "plba_get_timing", "plba_set_detail_timing", "plba_scene_preset", "plba_scene_create",
            "plba_scene_problem", "plba_scene_truth", "plba_scene_destroy"]
 
 
@@ -73,11 +73,31 @@ def declare(L):
     L.plba_destroy_group.restype = None
     L.plba_comm_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
     L.plba_comm_info.restype = C.c_int
+    L.plba_measure_fp64_peak.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _pd]
+    L.plba_measure_fp64_peak.restype = C.c_int
     L.plba_get_timing.argtypes = [C.c_void_p, C.POINTER(abi.plba_timing)]
     L.plba_get_timing.restype = C.c_int
     L.plba_set_detail_timing.argtypes = [C.c_void_p, C.c_int]
     L.plba_set_detail_timing.restype = C.c_int
     return L
+
+
+_SCENE = None
+
+
+def load_scene():
+    """The synthetic-scene generator (libplba_scene.so: host code only, no CUDA).  Scenes never come from libplba.so, so that the CPU
+    reference arm of bench.py and the oracle tests do not map the product library."""
+    global _SCENE
+    if _SCENE is None:
+        so = os.path.join(_HERE, "libplba_scene.so")
+        if not os.path.exists(so):
+            from . import build as _b
+            _b.build_scene()
+        L = C.CDLL(so)
+        abi.declare_common(L)
+        _SCENE = L
+    return _SCENE
 
 
 def library_path():

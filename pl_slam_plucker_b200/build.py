@@ -7,6 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libplba.so")
+SCENE_SO = os.path.join(HERE, "libplba_scene.so")      # the synthetic-scene generator alone (host code): what the CPU reference arm loads
 SOURCES = ["plba_api.cu", "scene_gen.cpp"]
 
 
@@ -26,8 +27,19 @@ def is_stale():
     return any(os.path.getmtime(f) > t for f in deps)
 
 
+def build_scene(force=False):
+    """g++ build of the scene generator alone: bench.py --impl reference must not map the product library."""
+    src = os.path.join(CSRC, "scene_gen.cpp")
+    hdr = os.path.join(HERE, "..", "include", "plba.h")
+    if force or not os.path.exists(SCENE_SO) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(SCENE_SO):
+        subprocess.check_call(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SCENE_SO, src])
+    return SCENE_SO
+
+
 def build(force=False, verbose=False, out=None, defines=()):
     global SO
+    if out is None:
+        build_scene(force)
     if out is None and not force and not is_stale():
         return SO
     target = out or SO

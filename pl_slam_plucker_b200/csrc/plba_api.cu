@@ -113,6 +113,7 @@ struct plba_handle_s {
     bool uploaded = false, small_path = true;
     double *sysbuf = nullptr; size_t sys_doubles = 0, S_doubles = 0;
     int h_counters[CNT_N] = {0};
+    int klaunch_seen = 0;            // device launch counter (CNT_KLAUNCH) at the last poll; 0 after a reset
     int64_t layout[8] = {0};
     plba_allreduce_fn allreduce = nullptr; void *allreduce_user = nullptr;
     void *nccl_comm = nullptr;       // ncclComm_t owned by the handle (plba_comm_init_rank / plba_create_group)
@@ -737,6 +738,7 @@ static bool use_graph(plba_handle h) {
 }
 
 static int launch_reset(plba_handle h) {
+    h->klaunch_seen = 0;
     PLBA_LAUNCH(k_reset, dim3(h->grid_chunks), dim3(256), 0, h->stream, (const DevP *)h->d_P, h->ls_dim, h->sys_doubles, h->sysbuf);
     h->timing.n_launches++;
     return PLBA_OK;
@@ -1284,11 +1286,11 @@ static int finish_pending_gate(plba_handle h) {
     return PLBA_OK;
 }
 
-static void account_graph_launches(plba_handle h) {
-    // kernels executed inside the graph, reconstructed from the device-side round / prep counters
-    const int rounds = h->h_counters[CNT_ROUNDS], preps = h->h_counters[CNT_PREPS];
-    h->timing.n_launches += (int64_t)3 * rounds + (int64_t)3 * preps;
-    h->timing.n_assemble += rounds;
+static void account_graph_launches(plba_handle h, int64_t launches0) {
+    // kernels that ran inside the graph: COUNTED on the device (every kernel of the library bumps CNT_KLAUNCH when it starts; the
+    // counter restarts at every reset).  The count includes the host-launched kernels of the same span, so it replaces the host's tally.
+    h->timing.n_launches = launches0 + (int64_t)(h->h_counters[CNT_KLAUNCH] - h->klaunch_seen);
+    h->timing.n_assemble += h->h_counters[CNT_ROUNDS];
 }
 
 extern "C" {
@@ -1305,7 +1307,8 @@ int plba_run(plba_handle h) {
     if ((rc = finish_pending_gate(h))) return rc;
     cudaEventRecord(h->ev[7], st);
     if ((rc = poll_counters(h))) return rc;
-    if (graph) account_graph_launches(h);
+    if (graph) account_graph_launches(h, launches0);
+    h->klaunch_seen = h->h_counters[CNT_KLAUNCH];
     float ms = 0; cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]);
     h->timing.ms_total = ms;
     h->timing.ms_other = ms - h->timing.ms_assemble - h->timing.ms_solve - h->timing.ms_update;
@@ -1402,7 +1405,8 @@ int plba_solve_batch(plba_handle h, int32_t n, const plba_problem *probs, const 
     if ((rc = finish_pending_gate(h))) return rc;
     cudaEventRecord(h->ev[7], h->stream);
     rc = plba_download(h, n, res);              // one synchronisation for the whole call
-    if (graph) account_graph_launches(h);
+    if (graph) account_graph_launches(h, launches0);
+    h->klaunch_seen = h->h_counters[CNT_KLAUNCH];
     float ms = 0; cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]);
     h->timing.ms_total = ms; h->timing.ms_other = ms - h->timing.ms_assemble - h->timing.ms_solve - h->timing.ms_update;
     h->timing.n_launches_run = h->timing.n_launches - launches0;
@@ -1488,6 +1492,68 @@ int plba_debug_prof(unsigned long long *out64, int reset) {
     if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(plba_prof_table, z, sizeof(z)); }
     return 0;
 }
+#endif
+#ifndef PLBA_HOST_EMU
+}  // extern "C"
+// ---- measured FP64 roof (bench.py: the roofline denominators of an FP64-bound path are measured, not nominal) ----
+// DFMA: 8 independent chains per thread, 8 warps per CTA, 8 CTAs per SM.  DMMA: mma.sync.m8n8k4.f64, 4 independent accumulator pairs.
+__global__ void __launch_bounds__(256) k_peak_dfma(double *out, int iters, double a, double b) {
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = a + i * 1e-3 + threadIdx.x * 1e-6;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i] = fma(x[i], b, a);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += x[i];
+    if (s == 1.2345e300) out[0] = s;
+}
+__global__ void __launch_bounds__(256) k_peak_dmma(double *out, int iters, double a, double b) {
+    double c[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { c[i][0] = a * i; c[i][1] = b * i; }
+    const double fa = a + threadIdx.x * 1e-6, fb = b;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) plba_dmma(c[i][0], c[i][1], fa, fb);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) s += c[i][0] + c[i][1];
+    if (s == 1.2345e300) out[0] = s;
+}
+extern "C" {
+// which: 0 = DFMA (vector pipe), 1 = DMMA (mma.sync.m8n8k4.f64).  Best of `reps` timed launches, CUDA events on the handle's stream.
+int plba_measure_fp64_peak(plba_handle h, int32_t which, int32_t reps, double *tflops) {
+    if (!h || !tflops || reps <= 0) return PLBA_E_ARG;
+    CK(cudaSetDevice(h->device));
+    const int iters = 20000, grid = 8 * h->n_sm;
+    double best = 0.0;
+    for (int r = 0; r < reps + 1; r++) {
+        cudaEventRecord(h->ev[4], h->stream);
+        if (which == 0) k_peak_dfma<<<grid, 256, 0, h->stream>>>(h->d_scratch, iters, 1.0000001, 0.9999999);
+        else k_peak_dmma<<<grid, 256, 0, h->stream>>>(h->d_scratch, iters, 1.0000001, 0.9999999);
+        cudaEventRecord(h->ev[5], h->stream);
+        CK(cudaStreamSynchronize(h->stream));
+        float ms = 0; cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]);
+        // DFMA: 32 FMAs per thread and iteration; DMMA: 16 MMAs per warp and iteration, 8 x 8 x 4 FMAs each
+        const double flops = which == 0 ? 2.0 * 32.0 * iters * 256.0 * grid : 2.0 * 16.0 * 256.0 * iters * 8.0 * grid;
+        if (r > 0 && ms > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    *tflops = best;
+    CK(cudaGetLastError());
+    return PLBA_OK;
+}
+#else
+int plba_measure_fp64_peak(plba_handle, int32_t, int32_t, double *) { return PLBA_E_UNSUPPORTED; }
 #endif
 int plba_set_force_dense(plba_handle h, int on) { if (!h) return PLBA_E_ARG; h->force_dense = on != 0; return PLBA_OK; }
 int plba_set_force_chunk(plba_handle h, int mode) { if (!h || mode < 0 || mode > 2) return PLBA_E_ARG; h->force_chunk = mode; return PLBA_OK; }

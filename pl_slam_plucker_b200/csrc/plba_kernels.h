@@ -59,7 +59,8 @@ struct WinCtrl {
 // assemble-phase sums live in P.acc[4*w + ...], update-phase sums in P.accB[4*w + ...] (two all-reduce ranges)
 enum { ACC_CHI_LIN = 0, ACC_ERR_PT = 1, ACC_ERR_LS = 2, ACC_CHI_NEW = 0, ACC_SCALE = 1, ACC_DX2 = 2, ACC_N = 8 };
 enum { CNT_DONE = 0, CNT_NEED_INIT = 1, CNT_GATE = 2, CNT_TRIALS = 3, CNT_TICKET = 4, CNT_ROUNDS = 5, CNT_PREPS = 6,
-       CNT_WORK_PT = 8, CNT_WORK_LS = 9, CNT_WTICKET = 10 /* warp path: next work item of each landmark class, CTA exit ticket */, CNT_N = 16 };
+       CNT_WORK_PT = 8, CNT_WORK_LS = 9, CNT_WTICKET = 10 /* warp path: next work item of each landmark class, CTA exit ticket */,
+       CNT_KLAUNCH = 11 /* kernels of the library that have started since the last reset: counted ON THE DEVICE (PLBA_PARAMS), so that launches inside the LM-loop graph are counted, not inferred */, CNT_N = 16 };
 
 struct DevP {
     Cam cam;
@@ -596,7 +597,7 @@ PLBA_D void assemble_chunk(const DevP &Pin, const Chunk &ch, int mode) {
 // persistent grid: CTA b walks chunks b, b + gridDim, ... (points first, then lines)
 template <int PROF>
 PLBA_KERNEL void PLBA_BOUNDS(OC, PLBA_CTAS_PER_SM) k_assemble(const DevP *Pp, int mode) {
-    if (mode == 0 && Pp->counters[CNT_NEED_INIT] == 0) return;        // no window waits for its initial lambda (the counter only changes between launches)
+    if (mode == 0 && Pp->counters[CNT_NEED_INIT] == 0) { PLBA_COUNT_LAUNCH(Pp); return; }        // no window waits for its initial lambda (the counter only changes between launches)
     PLBA_PARAMS(P, Pp);
     const int ntot = P.n_chunks_pt + P.n_chunks_ls;
     for (int c = PLBA_BID; c < ntot; c += PLBA_NB) {
@@ -1096,7 +1097,7 @@ PLBA_KERNEL void k_reset(const DevP *Pp, int ls_dim, size_t sys_doubles, double 
             for (int w = 0; w < P.n_win; w++) ndone += P.ctrl0[w].done;
             P.counters[CNT_DONE] = ndone; P.counters[CNT_NEED_INIT] = P.n_win - ndone; P.counters[CNT_GATE] = 0;
             P.counters[CNT_TRIALS] = 0; P.counters[CNT_TICKET] = 0; P.counters[CNT_ROUNDS] = 0; P.counters[CNT_PREPS] = 0;
-            P.counters[CNT_WORK_PT] = 0; P.counters[CNT_WORK_LS] = 0; P.counters[CNT_WTICKET] = 0;
+            P.counters[CNT_WORK_PT] = 0; P.counters[CNT_WORK_LS] = 0; P.counters[CNT_WTICKET] = 0; P.counters[CNT_KLAUNCH] = 0;
         }
     PHASE_END
 }

@@ -83,7 +83,9 @@ __device__ unsigned long long plba_prof_table[64];
 #endif
 // kernel parameters live in device memory (one fixed address per handle, so that the CUDA graph of the LM loop never
 // has to be rebuilt); every CTA stages them into shared memory once.
+#define PLBA_COUNT_LAUNCH(Pp) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) atomicAdd(&(Pp)->counters[11 /* CNT_KLAUNCH */], 1); } while (0)
 #define PLBA_PARAMS(P, Pp)                                                                                   \
+    PLBA_COUNT_LAUNCH(Pp);                                                                                   \
     for (int i_ = (int)threadIdx.x; i_ < (int)(sizeof(DevP) / 4); i_ += (int)blockDim.x)                       \
         ((int *)&plba_params_smem)[i_] = ((const int *)(Pp))[i_];                                            \
     __syncthreads();                                                                                         \
@@ -171,7 +173,8 @@ inline void plba_block_add(double *d, double v) { *d += v; }
 #define PLBA_WARP_FLUSH_MAX(ptr, v) do { if ((v) > *(ptr)) *(ptr) = (v); } while (0)
 inline void plba_sincos(double x, double *s, double *c) { *s = std::sin(x); *c = std::cos(x); }
 inline void plba_prefetch_l1(const void *) {}
-#define PLBA_PARAMS(P, Pp) const DevP &P = *(Pp)
+#define PLBA_COUNT_LAUNCH(Pp) do { if (plba_emu().bid == 0 && plba_emu().bidy == 0) (Pp)->counters[11]++; } while (0)
+#define PLBA_PARAMS(P, Pp) PLBA_COUNT_LAUNCH(Pp); const DevP &P = *(Pp)
 #define PLBA_PARAMS_REF(P, Pin) const DevP &P = Pin
 #define PROF_DECL
 #define PROF_MARK(id)

@@ -684,7 +684,7 @@ template <int PROF> PLBA_HD size_t WSmemMax<PROF>::bytes() {
 
 template <int PROF>
 PLBA_KERNEL void PLBA_BOUNDS(WNT, W_CTAS_PER_SM) k_assemble_w(const DevP *Pp, int mode) {
-    if (mode == 0 && Pp->counters[CNT_NEED_INIT] == 0) return;        // no window waits for its initial lambda (the counter only changes between launches)
+    if (mode == 0 && Pp->counters[CNT_NEED_INIT] == 0) { PLBA_COUNT_LAUNCH(Pp); return; }        // no window waits for its initial lambda (the counter only changes between launches)
     PLBA_SMEM(raw);
     PLBA_PARAMS(P, Pp);
     unsigned char *wraw = raw + (size_t)PLBA_WARP_IN_CTA * WSmemMax<PROF>::bytes();

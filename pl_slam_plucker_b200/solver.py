@@ -49,11 +49,17 @@ class LBASolver:
         res.rc = self._check(self.L.plba_solve(self.h, C.byref(pc), C.byref(opt.c), C.byref(res.c)))
         return res
 
-    def solve_batch(self, probs, opt, trace_cap=64):
+    def batch_buffers(self, probs, trace_cap=64):
+        """Caller-owned argument / result arrays of a batch call, built once and re-used (a steady-state caller does not re-allocate)."""
         n = len(probs)
         arr = (abi.plba_problem * n)(*[p.as_c() for p in probs])
         results = [abi.Result(p, trace_cap) for p in probs]
         rarr = (abi.plba_result * n)(*[r.c for r in results])
+        return arr, results, rarr
+
+    def solve_batch(self, probs, opt, trace_cap=64, out=None):
+        n = len(probs)
+        arr, results, rarr = out if out is not None else self.batch_buffers(probs, trace_cap)
         rc = self._check(self.L.plba_solve_batch(self.h, n, arr, C.byref(opt.c), rarr))
         for i, r in enumerate(results):
             r.c = rarr[i]
@@ -110,6 +116,12 @@ class LBASolver:
         ms = C.c_double(0)
         self._check(self.L.plba_time_kernel(self.h, int(which), int(reps), float(lam), C.byref(ms)))
         return ms.value
+
+    def measure_fp64_peak(self, which=0, reps=3):
+        """Measured FP64 roof in TFLOP/s: which 0 = DFMA (vector pipe), 1 = DMMA (mma.sync.m8n8k4.f64)."""
+        v = C.c_double(0)
+        self._check(self.L.plba_measure_fp64_peak(self.h, int(which), int(reps), C.byref(v)))
+        return v.value
 
     def set_force_dense(self, on=True):
         """Large windows: always use the dense DMMA Cholesky instead of the banded one."""
