@@ -50,7 +50,9 @@ enum {
     PLBA_DISCARDED   = -1,  /* nothing to do (no observations) / results discarded    */
     PLBA_E_ARG       = -2,  /* malformed problem (index out of range, NULL pointer …) */
     PLBA_E_CUDA      = -3,  /* CUDA runtime failure, see plba_last_error()            */
-    PLBA_E_NUMERIC   = -4,  /* reduced camera system not positive definite            */
+    PLBA_E_NUMERIC   = -4,  /* the reduced camera system was not positive definite in EVERY trial of an LM iteration: outputs are
+                               written (the rejected trials left the state untouched) but no longer follow the reference, whose
+                               SimplicialLDLT has no positivity requirement */
     PLBA_E_UNSUPPORTED = -5
 };
 

@@ -1351,7 +1351,7 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
     for (int w = 0; w < n; w++) {
         const WinInfo &wi = h->wins[w]; plba_result &r = res[w];
         r.n_trace = ctrl[w].n_trace; r.n_trials = ctrl[w].n_trials;
-        r.status = (wi.n_pobs + wi.n_lobs == 0) ? PLBA_DISCARDED : PLBA_OK;
+        r.status = (wi.n_pobs + wi.n_lobs == 0) ? PLBA_DISCARDED : (ctrl[w].numeric & (1 << 30)) ? PLBA_E_NUMERIC : PLBA_OK;
         if (r.trace) for (int i = 0; i < std::min(r.n_trace, std::min(r.trace_cap, P.trace_cap)); i++) r.trace[i] = trace[(size_t)w * P.trace_cap + i];
         if (r.kf_T_wc) for (int i = 0; i < 12 * wi.n_kf; i++) r.kf_T_wc[i] = T[(size_t)12 * wi.kf0 + i];
         if (r.x_pose) for (int i = 0; i < 6 * wi.n_free; i++) r.x_pose[i] = X[(size_t)6 * wi.slot0 + i];
@@ -1389,7 +1389,7 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
             }
         }
     }
-    for (int w = 0; w < n; w++) if (res[w].status < PLBA_DISCARDED) rc_all = res[w].status;
+    for (int w = 0; w < n; w++) if (res[w].status < PLBA_DISCARDED) { rc_all = res[w].status; if (rc_all == PLBA_E_NUMERIC) h->err = "the reduced camera system was not positive definite in every trial of an LM iteration"; }
     h->timing.ms_host_unpack = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
     return rc_all;
 }

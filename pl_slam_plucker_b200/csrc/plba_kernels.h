@@ -49,7 +49,7 @@ struct Seg { int lm0, n_lm, nobs, nfree, task0, fp0, dtask0, pad1; };   // task0
 struct WItem { int lm0, n_lm, ob0, k, win, nfree, fp0, pad; };
 
 struct WinCtrl {
-    int cur, stage, iter, trial, need_init, do_gate, done, n_trace, solve_fail, apply, stop_code, pad;
+    int cur, stage, iter, trial, need_init, do_gate, done, n_trace, solve_fail, apply, stop_code, numeric;   // numeric: low 16 bits = consecutive failed solves, bit 30 = PLBA_E_NUMERIC
     int n_lm_pt, n_lm_ls;            // landmark counts of the window (profile H normalisation)
     double lambda, ni, chi_cur, err_prev;
     double scale_pose, dx2_pose;     // pose part of computeScale() / ||DX||^2 (replicated on every rank, never all-reduced)
@@ -832,6 +832,13 @@ PLBA_D void control_window(const DevP &P, int w) {
     if (c.done) return;
     c.n_trials++;
     plba_atomic_add_i(&P.counters[CNT_TRIALS], 1);
+    // PLBA_E_NUMERIC: the reduced camera system was not positive definite in EVERY trial of an outer iteration (profile G) / in an
+    // iteration of the hand LM.  The reference's SimplicialLDLT has no positivity requirement and would carry on with an indefinite
+    // system; this library rejects such trials, so the caller is told that the result no longer follows the reference.
+    int fail_streak = (c.trial == 0) ? 0 : (c.numeric & 0xffff);
+    if (c.solve_fail) fail_streak++;
+    c.numeric = (c.numeric & ~0xffff) | (fail_streak & 0xffff);
+    if (c.solve_fail && P.profile != PLBA_PROFILE_G) c.numeric |= (1 << 30);
     if (P.profile == PLBA_PROFILE_G) {
         if (c.trial == 0) c.chi_cur = a_chi;                // currentChi = activeRobustChi2()
         const double tempChi = c.solve_fail ? 1.7976931348623157e308 : b_chi;
@@ -853,6 +860,7 @@ PLBA_D void control_window(const DevP &P, int w) {
         write_trace(P, w, c, accepted, terminate ? 1 : 0, chi_before, tempChi, rho, lam_used, scale, 0.0, a_ept, a_els);
         if (again) c.trial = qmax;
         else {
+            if (fail_streak == qmax) c.numeric |= (1 << 30);       // every trial of this outer iteration failed in the factorisation
             c.trial = 0; c.iter++;
             const int n_outer = c.stage == 0 ? P.iters_stage1 : P.iters_stage2;
             if (terminate || c.iter >= n_outer) {

@@ -692,12 +692,8 @@ PLBA_KERNEL void PLBA_BOUNDS(WNT, W_CTAS_PER_SM) k_assemble_w(const DevP *Pp, in
         assemble_items_w<PROF, LT_POINT, 0>(P, P.witems_pt, P.n_witems_pt, wraw);
         assemble_items_w<PROF, LineOf<PROF>::LT, 0>(P, P.witems_ls, P.n_witems_ls, wraw);
     } else {
-#ifndef PLBA_W_EXP_NO_PT
         assemble_items_w<PROF, LT_POINT, 1>(P, P.witems_pt, P.n_witems_pt, wraw);
-#endif
-#ifndef PLBA_W_EXP_NO_LS
         assemble_items_w<PROF, LineOf<PROF>::LT, 1>(P, P.witems_ls, P.n_witems_ls, wraw);
-#endif
     }
     // the last CTA out re-arms the work counters for the next launch
     PHASE_BEGIN

@@ -32,3 +32,4 @@ test_map_handler_interface = g.test_map_handler_interface
 test_randomised_large_windows = g.test_randomised_large_windows
 test_all_keyframes_fixed_hand_lm = g.test_all_keyframes_fixed_hand_lm
 test_randomised_large_windows_g_faithful = g.test_randomised_large_windows_g_faithful
+test_numeric_failure_is_reported = g.test_numeric_failure_is_reported

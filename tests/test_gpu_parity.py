@@ -374,6 +374,20 @@ def test_graph_equals_host_driven_loop(oracle):
         s.close()
 
 
+def test_numeric_failure_is_reported(gpu_solver):
+    """PLBA_E_NUMERIC: a window whose reduced camera system is not positive definite in every trial (here: a NaN measurement poisons the
+    system) must be reported, not silently returned as OK."""
+    from pl_slam_plucker_b200.solver import LBAError
+    base = scene.make_scene(1, n_kf_free=4, n_kf_fixed=1, n_pt=60, n_ls=10, seed=77)
+    uv = base.po_uv.copy(); uv[5, 0] = np.nan
+    bad = abi.Problem(base.cam, base.kf_T_wc, base.kf_slot, base.pt_xyz, base.po_lm, base.po_kf, uv, ls_plk=base.ls_plk, lo_lm=base.lo_lm,
+                      lo_kf=base.lo_kf, lo_ab=base.lo_ab, x_pose=base.x_pose)
+    with pytest.raises(LBAError, match="-4"):
+        gpu_solver.solve(bad, abi.Options(abi.PROFILE_G, 1))
+    r = gpu_solver.solve(base, abi.Options(abi.PROFILE_G, 1))          # the handle stays usable
+    assert r.rc == abi.OK
+
+
 def test_all_keyframes_fixed_hand_lm(gpu_solver, oracle):
     """A hand-LM window whose observers are all fixed (n_free == 0): the pre-solve controller must still run on the host-driven loop
     exactly as inside the graph (same number of iterations as the oracle)."""
