@@ -111,6 +111,7 @@ struct plba_handle_s {
     int large_solver = 0;            // 0 = block cyclic reduction (default), 1 = single-CTA banded Cholesky (A/B, tests)
     int grid_warp = 592, grid_warp_upd = 592;
     bool uploaded = false, small_path = true;
+    bool bcr_layout = false;         // this upload stores the reduced camera system of its (large, block-banded) windows in the node form of the block cyclic reduction
     double *sysbuf = nullptr; size_t sys_doubles = 0, S_doubles = 0;
     int h_counters[CNT_N] = {0};
     int klaunch_seen = 0;            // device launch counter (CNT_KLAUNCH) at the last poll; 0 after a reset
@@ -576,8 +577,7 @@ static void allreduce(plba_handle h, double *p, size_t n, int op_max) {
     // op is encoded in the sign of the count for the max reduction (only the band width at upload uses it)
     h->allreduce(p, op_max ? -(int64_t)n : (int64_t)n, (void *)h->stream, h->allreduce_user);
 }
-static inline size_t bcr_exchange_doubles(const BcrW &B) { return (size_t)2 * B.N * B.m * B.m + (size_t)2 * B.N * B.m + 8; }      // [D | U | b | hd | tail]
-static bool bcr_is_active(plba_handle h) { return !h->small_path && h->band_blocks <= BAND_MAX && !h->force_dense && h->large_solver == 0 && !h->bcr.empty(); }
+static bool bcr_is_active(plba_handle h) { return h->bcr_layout; }      // decided at upload: the window's S is stored (and assembled) in node form
 static void launch_solve(plba_handle h) {
     const DevP &P = h->P; const DevP *Pp = h->d_P;
     if (P.n_free == 0) {
@@ -592,16 +592,14 @@ static void launch_solve(plba_handle h) {
         return;
     }
     if (P.profile != PLBA_PROFILE_G) { PLBA_LAUNCH(k_control_h_pre, grid1(P.n_win, 128), dim3(128), 0, h->stream, Pp); h->timing.n_launches++; }
-    if (h->band_blocks <= BAND_MAX && !h->force_dense && h->large_solver == 0 && !h->bcr.empty()) {
+    if (h->bcr_layout) {
         // block-banded reduced camera system (no loop closure in the window): block cyclic reduction over nodes of >= band keyframes,
         // ceil(log2 N) levels down and up, every level one launch with a CTA per eliminated node
         for (int w = 0; w < P.n_win; w++) {
             const BcrW &B = h->bcr[w];
             if (B.N == 0 || h->wins[w].n_pobs + h->wins[w].n_lobs == 0) continue;
-            PLBA_LAUNCH(k_bcr_gather, dim3(B.N), dim3(256), 0, h->stream, Pp, w, B); h->timing.n_launches++;
-            // the exchange step of the landmark-sharded path: only the band [D | U | b | hd] of the window travels (config 5: 17 MB, not
-            // the 1.15 GB of the dense S)
-            allreduce(h, B.D, bcr_exchange_doubles(B), 0);
+            // (the assembly kernels have accumulated straight into the node form, and the exchange step of the sharded path has summed
+            //  it over the ranks: config 5 moves 17 MB, there is no dense S)
             int s_top = 0;
             for (int s = 1; s < B.N; s *= 2) {
                 PLBA_LAUNCH(k_bcr_elim, dim3((B.N + s - 1) / (2 * s)), dim3(BCR_NT), bcr_elim_smem(), h->stream, Pp, w, B, s, 0); h->timing.n_launches++;
@@ -986,6 +984,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     Carver ci;   // staged inputs (same offsets in pinned host memory and at the start of the device arena)
     const size_t i_kf_slot = ci.take<int>(tot.n_kf), i_kf_win = ci.take<int>(tot.n_kf), i_slot_kf = ci.take<int>(tot.n_free);
     const size_t i_win_slot0 = ci.take<int>(n), i_win_nfree = ci.take<int>(n), i_win_ls0 = ci.take<int>(n), i_win_S = ci.take<long long>(n);
+    const size_t i_win_bs = ci.take<int>(n), i_win_N = ci.take<int>(n);
     const size_t i_Tmap = ci.take<double>((size_t)12 * tot.n_kf), i_X0 = ci.take<double>((size_t)6 * tot.n_free);
     const size_t i_pts0 = ci.take<double>((size_t)3 * tot.n_pt), i_lns0 = ci.take<double>((size_t)ld * tot.n_ls), i_lmap = ci.take<double>((size_t)6 * tot.n_ls);
     const size_t i_pt_ptr = ci.take<int>(tot.n_pt + 1), i_ls_ptr = ci.take<int>(tot.n_ls + 1), i_pt_win = ci.take<int>(tot.n_pt), i_ls_win = ci.take<int>(tot.n_ls);
@@ -997,9 +996,17 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     const size_t i_wi_pt = ci.take<WItem>(wi_pt.size()), i_wi_ls = ci.take<WItem>(wi_ls.size());
     const size_t i_ctrl0 = ci.take<WinCtrl>(n);
     h->in_bytes = ci.off; h->i_pts0 = i_pts0; h->i_lns0 = i_lns0; h->i_lmap = i_lmap;
+    // reduced camera system: dense (6 nf)^2 per window, or — large block-banded windows on the block-cyclic-reduction solver — the
+    // solver's node form [D | U], N nodes of m = 6 bs unknowns: 2 N m^2 doubles (config 5: 35 MB instead of 1.15 GB)
+    h->bcr_layout = !h->small_path && h->band_blocks <= BAND_MAX && !h->force_dense && h->large_solver == 0;
+    const int bcr_bs = std::min((int)BCR_BS_MAX, std::max(h->band_blocks, 6)), bcr_m = 6 * bcr_bs;
     long long S_off = 0;
     std::vector<long long> win_S_off(n);
-    for (int w = 0; w < n; w++) { win_S_off[w] = S_off; S_off += (long long)36 * h->wins[w].n_free * h->wins[w].n_free; }
+    for (int w = 0; w < n; w++) {
+        win_S_off[w] = S_off;
+        const long long nf_w = h->wins[w].n_free, N_w = (nf_w + bcr_bs - 1) / bcr_bs;
+        S_off += h->bcr_layout ? 2 * N_w * bcr_m * bcr_m : 36 * nf_w * nf_w;
+    }
     h->S_doubles = (size_t)S_off;
     h->sys_doubles = h->S_doubles + (size_t)18 * tot.n_free + (size_t)ACC_N * n + (size_t)n + (size_t)PLBA_MAX_RANKS * n;
     Carver cs = ci;   // device-only state follows the inputs
@@ -1011,14 +1018,13 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     // node storage of the block cyclic reduction (large banded windows only)
     h->bcr.clear();
     std::vector<size_t> s_bcr;
-    if (!h->small_path && h->band_blocks <= BAND_MAX) {
-        const int bs = std::min((int)BCR_BS_MAX, std::max(h->band_blocks, 6)), m = 6 * bs;
+    if (h->bcr_layout) {
+        const int bs = bcr_bs, m = bcr_m;
         for (int w = 0; w < n; w++) {
             BcrW B{}; B.bs = bs; B.m = m; B.N = (h->wins[w].n_free + bs - 1) / bs;
             h->bcr.push_back(B);
             const size_t nn = (size_t)B.N * m * m;
-            s_bcr.push_back(cs.take<double>(2 * nn + (size_t)2 * B.N * m + 8));   // [D | U | b | hd | tail]: contiguous (exchange step)
-            s_bcr.push_back(cs.take<double>(nn)); s_bcr.push_back(cs.take<double>(nn)); s_bcr.push_back(cs.take<double>((size_t)B.N * m));   // Xl, Xr, y
+            s_bcr.push_back(cs.take<double>(nn)); s_bcr.push_back(cs.take<double>(nn)); s_bcr.push_back(cs.take<double>((size_t)B.N * m));   // Xl, Xr, y (D, U, b, hd live in the system buffer)
         }
     }
     const int trace_cap = (prof == PLBA_PROFILE_G) ? (opt->iters_stage1 + opt->iters_stage2) * opt->lm_max_trials + 2 : opt->max_iters_lba + 2;
@@ -1041,6 +1047,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     int *kf_slot = (int *)(hb + i_kf_slot), *kf_win = (int *)(hb + i_kf_win), *slot_kf = (int *)(hb + i_slot_kf);
     int *win_slot0 = (int *)(hb + i_win_slot0), *win_nfree = (int *)(hb + i_win_nfree), *win_ls0 = (int *)(hb + i_win_ls0);
     long long *winS = (long long *)(hb + i_win_S);
+    int *win_bs = (int *)(hb + i_win_bs), *win_N = (int *)(hb + i_win_N);
     double *Tmap = (double *)(hb + i_Tmap), *X0 = (double *)(hb + i_X0), *pts0 = (double *)(hb + i_pts0), *lns0 = (double *)(hb + i_lns0), *lmap = (double *)(hb + i_lmap);
     int *d_pt_ptr = (int *)(hb + i_pt_ptr), *d_ls_ptr = (int *)(hb + i_ls_ptr), *pt_win = (int *)(hb + i_pt_win), *ls_win = (int *)(hb + i_ls_win);
     int *po_kf = (int *)(hb + i_po_kf), *po_lm = (int *)(hb + i_po_lm), *lo_kf = (int *)(hb + i_lo_kf), *lo_lm = (int *)(hb + i_lo_lm);
@@ -1061,6 +1068,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     for (int w = 0; w < n; w++) {
         const plba_problem &p = probs[w]; const WinInfo &wi = h->wins[w];
         win_slot0[w] = wi.slot0; win_nfree[w] = wi.n_free; win_ls0[w] = wi.ls0; winS[w] = win_S_off[w];
+        win_bs[w] = h->bcr_layout ? bcr_bs : 0; win_N[w] = h->bcr_layout ? (wi.n_free + bcr_bs - 1) / bcr_bs : 0;
         for (int k = 0; k < p.n_kf; k++) {
             const int s = p.kf_slot[k];
             kf_slot[wi.kf0 + k] = s < 0 ? -1 : wi.slot0 + s; kf_win[wi.kf0 + k] = w;
@@ -1132,6 +1140,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     P.lambda_lba_lm = opt->lambda_lba_lm; P.lambda_lba_k = opt->lambda_lba_k;
     P.kf_slot = (int *)(db + i_kf_slot); P.kf_win = (int *)(db + i_kf_win); P.slot_kf = (int *)(db + i_slot_kf);
     P.win_slot0 = (int *)(db + i_win_slot0); P.win_nfree = (int *)(db + i_win_nfree); P.win_ls0 = (int *)(db + i_win_ls0); P.win_S_off = (long long *)(db + i_win_S);
+    P.win_bcr_bs = (int *)(db + i_win_bs); P.win_bcr_N = (int *)(db + i_win_N);
     P.kf_Tmap = (double *)(db + i_Tmap); P.X0 = (double *)(db + i_X0); P.pts0 = (double *)(db + i_pts0); P.lns0 = (double *)(db + i_lns0); P.lns_map = (double *)(db + i_lmap);
     P.pt_ptr = (int *)(db + i_pt_ptr); P.ls_ptr = (int *)(db + i_ls_ptr); P.pt_win = (int *)(db + i_pt_win); P.ls_win = (int *)(db + i_ls_win);
     P.po_kf = (int *)(db + i_po_kf); P.po_lm = (int *)(db + i_po_lm); P.lo_kf = (int *)(db + i_lo_kf); P.lo_lm = (int *)(db + i_lo_lm);
@@ -1151,9 +1160,9 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     for (size_t w = 0; w < h->bcr.size(); w++) {
         BcrW &B = h->bcr[w];
         const size_t nn = (size_t)B.N * B.m * B.m;
-        B.D = (double *)(db + s_bcr[4 * w]); B.U = B.D + nn; B.b = B.U + nn; B.hd = B.b + (size_t)B.N * B.m; B.tail = B.hd + (size_t)B.N * B.m;
-        B.pad = (has_exchange(h) && prof == PLBA_PROFILE_G) ? 1 : 0;       // the assemble-phase cost sums ride in the tail of the exchange
-        B.Xl = (double *)(db + s_bcr[4 * w + 1]); B.Xr = (double *)(db + s_bcr[4 * w + 2]); B.y = (double *)(db + s_bcr[4 * w + 3]);
+        B.D = P.S + win_S_off[w]; B.U = B.D + nn;
+        B.b = P.gs + (size_t)6 * h->wins[w].slot0; B.hd = P.hpp_diag + (size_t)6 * h->wins[w].slot0;      // node i, unknown c <-> slot i bs + c / 6: the same index as in g
+        B.Xl = (double *)(db + s_bcr[3 * w]); B.Xr = (double *)(db + s_bcr[3 * w + 1]); B.y = (double *)(db + s_bcr[3 * w + 2]);
     }
     P.solve_nf_max = std::min(max_nf, (int)SMALL_NMAX / 6);
     P.S_clear_doubles = h->small_path ? (long long)((h->S_doubles + 1) & ~(size_t)1) : 0;      // (the buffer continues with g: an odd tail would only clear g[0], which the solver has consumed too; S_doubles is even anyway)
@@ -1173,7 +1182,6 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     CK(cudaMemcpyAsync(h->d_arena, h->h_in, h->in_bytes, cudaMemcpyHostToDevice, h->stream));
     h->timing.h2d_bytes += (int64_t)(h->in_bytes + sizeof(DevP));
     cudaEventRecord(h->ev_h2d, h->stream); h->h2d_pending = true;
-    for (const BcrW &B : h->bcr) CK(cudaMemsetAsync(B.D, 0, sizeof(double) * bcr_exchange_doubles(B), h->stream));   // entries no kernel writes (upper triangles, the unused U of node 0) stay 0 in the exchange
     h->uploaded = true;
     return launch_reset(h);
 }
@@ -1196,10 +1204,9 @@ int plba_reset_state(plba_handle h) {
 // landmark-diagonal maxima].  All of them on the handle's stream: no host synchronisation.
 static int run_round(plba_handle h, bool need_prep) {
     DevP &P = h->P; cudaStream_t st = h->stream; const DevP *Pp = h->d_P;
-    // (the block-cyclic-reduction solver clears what it consumes; the other large-window solvers leave S dirty)
-    const bool bcr_active = bcr_is_active(h);
+    // (the large-window solvers factor in place: S, g and diag(H_pp) are cleared before every assembly; in node form that is 17 MB at config 5)
     const bool xch = has_exchange(h);
-    if (!h->small_path && !bcr_active) CK(cudaMemsetAsync(h->sysbuf, 0, sizeof(double) * (h->S_doubles + (size_t)12 * P.n_free), st));
+    if (!h->small_path) CK(cudaMemsetAsync(h->sysbuf, 0, sizeof(double) * (h->S_doubles + (size_t)12 * P.n_free), st));
     if (need_prep) {
         PLBA_LAUNCH(k_gate, dim3(h->grid_chunks), dim3(256), 0, st, Pp); h->timing.n_launches++;
         launch_assemble(h, 0);
@@ -1214,11 +1221,9 @@ static int run_round(plba_handle h, bool need_prep) {
     launch_assemble(h, 1);
     if (h->detail_timing) cudaEventRecord(h->ev[1], st);
     if (xch) {
-        // the exchange step.  Dense / small windows: [S | g | diag(H_pp) | (zero) prep diagonal | cost sums] is one contiguous range.
-        // Block cyclic reduction: the band only, in node form, after its gather (launch_solve); the cost sums ride in its tail for
-        // profile G, the hand LM needs them before its pre-solve controller
-        if (!bcr_active) allreduce(h, h->sysbuf, h->S_doubles + (size_t)18 * P.n_free + (size_t)4 * P.n_win, 0);
-        else if (P.profile != PLBA_PROFILE_G) allreduce(h, P.acc, (size_t)4 * P.n_win, 0);
+        // the exchange step: [S | g | diag(H_pp) | (zero) prep diagonal | cost sums] is ONE contiguous range, whatever the storage of S
+        // (dense, or the band in node form for the block cyclic reduction: 17 MB at config 5)
+        allreduce(h, h->sysbuf, h->S_doubles + (size_t)18 * P.n_free + (size_t)4 * P.n_win, 0);
     }
     launch_solve(h);
     if (h->detail_timing) cudaEventRecord(h->ev[2], st);
@@ -1453,7 +1458,6 @@ int plba_reduced_system(plba_handle h, void **dev_ptr, int64_t *n_doubles) {
     if (dev_ptr) *dev_ptr = h->sysbuf;
     if (n_doubles) {
         *n_doubles = (int64_t)(h->S_doubles + (size_t)6 * h->P.n_free);
-        if (bcr_is_active(h)) { int64_t t = 0; for (const BcrW &B : h->bcr) t += (int64_t)bcr_exchange_doubles(B); *n_doubles = t; }   // what the exchange step moves
     }
     return PLBA_OK;
 }
@@ -1461,11 +1465,29 @@ int plba_copy_reduced_system(plba_handle h, int32_t window, double *S_out, doubl
     if (!h || !h->uploaded || window < 0 || window >= h->P.n_win) return PLBA_E_ARG;
     const WinInfo &wi = h->wins[window];
     const size_t n = (size_t)6 * wi.n_free;
-    size_t off = 0;
-    for (int w = 0; w < window; w++) off += (size_t)36 * h->wins[w].n_free * h->wins[w].n_free;
-    if (S_out && n) CK(cudaMemcpyAsync(S_out, h->P.S + off, sizeof(double) * n * n, cudaMemcpyDeviceToHost, h->stream));
     if (g_out && n) CK(cudaMemcpyAsync(g_out, h->P.gs + (size_t)6 * wi.slot0, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (S_out && n && !h->bcr_layout) {
+        size_t off = 0;
+        for (int w = 0; w < window; w++) off += (size_t)36 * h->wins[w].n_free * h->wins[w].n_free;
+        CK(cudaMemcpyAsync(S_out, h->P.S + off, sizeof(double) * n * n, cudaMemcpyDeviceToHost, h->stream));
+    }
     CK(cudaStreamSynchronize(h->stream));
+    if (S_out && n && h->bcr_layout) {
+        // the window is stored in the node form of the block cyclic reduction (s_block()): unfold it into the dense upper storage
+        const BcrW &B = h->bcr[window];
+        const size_t nn = (size_t)B.N * B.m * B.m;
+        std::vector<double> nodes(2 * nn);
+        CK(cudaMemcpyAsync(nodes.data(), B.D, sizeof(double) * 2 * nn, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        std::memset(S_out, 0, sizeof(double) * n * n);
+        const int m = B.m;
+        for (int i = 0; i < B.N; i++) {
+            const int oi = i * m, mi = bcr_node_size(B, wi.n_free, i);
+            const double *D = nodes.data() + (size_t)i * m * m, *U = nodes.data() + nn + (size_t)i * m * m;
+            for (int r = 0; r < mi; r++) for (int c = 0; c <= r; c++) S_out[(size_t)(oi + c) * n + oi + r] = D[(size_t)r * m + c];      // lower of the node = upper of S
+            if (i > 0) for (int r = 0; r < m; r++) for (int c = 0; c < mi; c++) S_out[(size_t)(oi - m + r) * n + oi + c] = U[(size_t)r * m + c];
+        }
+    }
     return PLBA_OK;
 }
 // Average device time of one launch of a stage kernel on the resident problem: `reps` back-to-back launches bracketed by
@@ -1681,7 +1703,7 @@ int plba_create_lines(plba_handle h, const plba_newline_batch *B, double *NDc, d
 int plba_kernel_path(plba_handle h, int32_t *out4) {
     if (!h || !h->uploaded || !out4) return PLBA_E_ARG;
     out4[0] = h->warp_path ? 1 : 0;
-    out4[1] = h->small_path ? 0 : (h->band_blocks <= BAND_MAX && !h->force_dense) ? (h->large_solver == 0 && !h->bcr.empty() ? 1 : 2) : 3;
+    out4[1] = h->small_path ? 0 : h->bcr_layout ? 1 : (h->band_blocks <= BAND_MAX && !h->force_dense) ? 2 : 3;
     out4[2] = h->band_blocks;
     out4[3] = h->warp_path ? (int)(h->wi_pt.size() + h->wi_ls.size()) : (int)(h->ch_pt.size() + h->ch_ls.size());
     return PLBA_OK;

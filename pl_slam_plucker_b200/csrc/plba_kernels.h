@@ -77,7 +77,8 @@ struct DevP {
     const double *X0;                 // [n_free][6] initial X (reset)
     const int *win_slot0, *win_nfree; // per window: first global slot, number of free KFs
     const int *win_ls0;               // per window: first global line index (Q3 indexing is window-relative)
-    const long long *win_S_off;       // per window: offset (doubles) of its dense (6 nf)^2 S
+    const long long *win_S_off;       // per window: offset (doubles) of its reduced camera system inside S: dense (6 nf)^2, or node form [D | U] (see s_block)
+    const int *win_bcr_bs, *win_bcr_N; // per window: keyframes per node / nodes of the block cyclic reduction (0 = dense storage)
     // landmarks (double buffered) in internal (signature-sorted) order
     double *pts[2], *lns[2];
     double *lpre[2];                  // [n_ls][LPRE_N] orthonormal lines: Plücker vector, U, W at the state of each buffer (warp kernels)
@@ -155,6 +156,25 @@ template <int PROF> struct SmemMax {
         return a > b ? a : b;
     }
 };
+
+// Where the 6x6 block (ra, cb), ra <= cb (free-keyframe positions inside one window), of the reduced camera system lives: address of
+// its entry (0, 0) and the strides of its rows and columns.
+//   dense windows (one-CTA solver, dense DMMA Cholesky): row-major (6 nf)^2, upper block triangle;
+//   block-banded large windows (block cyclic reduction): the assembly kernels accumulate straight into the solver's NODE form —
+//     nodes of bs keyframes (m = 6 bs unknowns), D_i = lower triangle of the node's diagonal block (row stride m), U_j = the block between
+//     node j - 1 (rows) and node j (columns).  No dense S exists for such a window (config 5: 35 MB instead of 1.15 GB) and no gather
+//     kernel runs before the solve (round 1: 0.35 ms of a 1.77 ms solve).  The half bandwidth is <= bs, so cb / bs - ra / bs <= 1.
+struct SBlk { double *p; long long sr, sc; };
+PLBA_HD SBlk s_block(const DevP &P, int win, int ra, int cb) {
+    double *Sw = P.S + P.win_S_off[win];
+    const int bs = P.win_bcr_bs[win];
+    SBlk b;
+    if (bs == 0) { const long long ld = 6 * (long long)P.win_nfree[win]; b.p = Sw + (size_t)(6 * ra) * ld + 6 * cb; b.sr = ld; b.sc = 1; return b; }
+    const int m = 6 * bs, i = ra / bs, j = cb / bs, a = ra - i * bs, c = cb - j * bs;
+    if (i == j) { b.p = Sw + (size_t)i * m * m + (size_t)(6 * c) * m + 6 * a; b.sr = 1; b.sc = m; }       // D_i[(6c + col) m + 6a + row]: lower triangle
+    else { b.p = Sw + (size_t)P.win_bcr_N[win] * m * m + (size_t)j * m * m + (size_t)(6 * a) * m + 6 * c; b.sr = m; b.sc = 1; }   // U_j[(6a + row) m + 6c + col]
+    return b;
+}
 
 PLBA_HD int symidx(int r, int c, int D) { return r <= c ? r * D - r * (r - 1) / 2 + (c - r) : c * D - c * (c - 1) / 2 + (r - c); }
 
@@ -488,8 +508,9 @@ PLBA_D void assemble_chunk(const DevP &Pin, const Chunk &ch, int mode) {
             for (int pass = 0; pass < npass; pass++) {
                 const bool tr = same ? (pass == 1) : (sa > sb);
                 const int ra = tr ? sb : sa, cb = tr ? sa : sb;
-                double *base = Sw + (size_t)(6 * ra) * ld + 6 * cb;
-                const int sr = tr ? 1 : ld, sc = tr ? ld : 1;
+                const SBlk sb_ = s_block(P, ch.win, ra, cb);
+                double *base = sb_.p;
+                const long long sr = tr ? sb_.sc : sb_.sr, sc = tr ? sb_.sr : sb_.sc;
 #pragma unroll
                 for (int r = 0; r < 3; r++) {
 #pragma unroll
@@ -579,11 +600,11 @@ PLBA_D void assemble_chunk(const DevP &Pin, const Chunk &ch, int mode) {
                 for (int c = 0; c < 6; c++) plba_atomic_add(&P.hpp_diag_init[(size_t)6 * (slot0 + sa) + c], hd[c]);
             } else {
                 int idx = 0;
-                double *base = Sw + (size_t)(6 * sa) * ld + 6 * sa;
+                const SBlk sd_ = s_block(P, ch.win, sa, sa);
 #pragma unroll
                 for (int r = 0; r < 6; r++) {
 #pragma unroll
-                    for (int c = r; c < 6; c++) plba_atomic_add(base + r * ld + c, Sd[idx++]);
+                    for (int c = r; c < 6; c++) plba_atomic_add(sd_.p + r * sd_.sr + c * sd_.sc, Sd[idx++]);
                     plba_atomic_add(&P.gs[(size_t)6 * (slot0 + sa) + r], gv[r]);
                     if (PROF != PLBA_PROFILE_G) plba_atomic_add(&P.hpp_diag[(size_t)6 * (slot0 + sa) + r], hd[r]);
                 }

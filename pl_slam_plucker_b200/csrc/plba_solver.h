@@ -925,52 +925,12 @@ PLBA_KERNEL void k_solve_banded(const DevP *Pp, int bwb) {
 // the levels are walked back:  L^T x_i = y - Xl^T x_{i-s} - Xr^T x_{i+s}.
 // This is a Cholesky factorisation in a nested-dissection order of the keyframe chain: same system, same solution up to rounding,
 // but the 6 Nkf sequential pivots of the banded factorisation become 90 ceil(log2 N) and every level fills the GPU.
-struct BcrW { double *D, *U, *b, *hd, *tail, *Xl, *Xr, *y; int N, bs, m, pad; };   // node storage: D, U, Xl, Xr: [N][m*m] (row stride m); b, hd, y: [N][m];
-                                                                           // [D | U | b | hd | tail] is one contiguous range: the exchange step of the sharded path (tail: the window's 4 assemble-phase cost sums ride along, 8 doubles)
+struct BcrW { double *D, *U, *b, *hd, *Xl, *Xr, *y; int N, bs, m, pad; };   // node storage: D, U, Xl, Xr: [N][m*m] (row stride m); b, hd, y: [N][m];
+                                                                           // D, U: the window's slice of P.S (the assembly kernels accumulate into the node form directly, s_block()); b = the window's slice of g, hd of diag(H_pp)
 enum { BCR_BS_MAX = 15, BCR_M_MAX = 6 * BCR_BS_MAX, BCR_NT = 512 };
 static inline size_t bcr_elim_smem() { return sizeof(double) * ((size_t)(3 * BCR_M_MAX + 1) * (BCR_M_MAX + 1) + BCR_M_MAX + 21 * BCR_BS_MAX + 6 * 264 + 8) + 64; }
 static inline size_t bcr_back_smem() { return sizeof(double) * ((size_t)BCR_M_MAX * (BCR_M_MAX + 1) + 7 * BCR_M_MAX + 8) + 64; }
 PLBA_HD int bcr_node_size(const BcrW &B, int nf, int i) { const int k0 = i * B.bs, k1 = (k0 + B.bs < nf) ? k0 + B.bs : nf; return 6 * (k1 - k0); }
-
-// dense S (upper storage) -> node form (undamped: the damping goes on when a node is loaded for elimination, i.e. after the
-// exchange step of the sharded path).  Everything the assembly wrote is read here exactly once (blocks of one node, blocks
-// between neighbouring nodes, g, diag(H_pp)) and cleared behind the read: the next assembly accumulates into a clean system
-// without a memset of the dense S (1.15 GB at config 5).
-PLBA_KERNEL void k_bcr_gather(const DevP *Pp, int w, BcrW B) {
-    PLBA_PARAMS(P, Pp);
-    const WinCtrl &ctl = P.ctrl[w];
-    // the assemble-phase cost sums of the window travel in the tail of the node storage: ONE exchange per LM trial (profile G reads
-    // them only in the controller, after the solve).  Written even for a finished window, so that the tail never accumulates.
-    PHASE_BEGIN
-        if (PLBA_BID == 0 && tid < 8) B.tail[tid] = (tid < 4 && !ctl.done) ? P.acc[(size_t)4 * w + tid] : 0.0;
-    PHASE_END
-    if (ctl.done) return;
-    const int nf = P.win_nfree[w], n = 6 * nf, slot0 = P.win_slot0[w], m = B.m;
-    double *Sw = P.S + P.win_S_off[w];
-    const int i = PLBA_BID, oi = 6 * i * B.bs, mi = bcr_node_size(B, nf, i);
-    double *D = B.D + (size_t)i * m * m, *U = B.U + (size_t)i * m * m;
-    PHASE_BEGIN
-        for (int idx = tid; idx < mi * mi; idx += PLBA_NT) {
-            const int c = idx / mi, r = idx - c * mi;                // consecutive threads walk a row of S (upper storage: row = c)
-            if (c > r) continue;
-            double v = Sw[(size_t)(oi + c) * n + oi + r];
-            Sw[(size_t)(oi + c) * n + oi + r] = 0.0;
-            D[(size_t)r * m + c] = v;
-        }
-        if (i > 0) {
-            const int ol = oi - m;                                   // the left neighbour is never the last node: full size
-            for (int idx = tid; idx < m * mi; idx += PLBA_NT) {
-                const int r = idx / mi, c = idx - r * mi;
-                U[(size_t)r * m + c] = Sw[(size_t)(ol + r) * n + oi + c];
-                Sw[(size_t)(ol + r) * n + oi + c] = 0.0;
-            }
-        }
-        for (int c = tid; c < mi; c += PLBA_NT) {
-            B.b[(size_t)i * m + c] = P.gs[(size_t)6 * slot0 + oi + c]; P.gs[(size_t)6 * slot0 + oi + c] = 0.0;
-            if (P.profile != PLBA_PROFILE_G) { B.hd[(size_t)i * m + c] = P.hpp_diag[(size_t)6 * slot0 + oi + c]; P.hpp_diag[(size_t)6 * slot0 + oi + c] = 0.0; }
-        }
-    PHASE_END
-}
 
 // eliminate the nodes (2 j + 1) s of one level (final != 0: node 0, nothing left to couple to)
 PLBA_KERNEL void k_bcr_elim(const DevP *Pp, int w, BcrW B, int s, int final) {
@@ -1071,11 +1031,6 @@ PLBA_KERNEL void k_bcr_back(const DevP *Pp, int w, BcrW B, int s, int final) {
     PLBA_PARAMS(P, Pp);
     const WinCtrl &ctl = P.ctrl[w];
     if (ctl.done) return;
-    if (final && B.pad) {      // B.pad != 0: the cost sums were exchanged in the tail (sharded profile G): hand them to the controller
-        PHASE_BEGIN
-            if (tid < 4) P.acc[(size_t)4 * w + tid] = B.tail[tid];
-        PHASE_END
-    }
     const int nf = P.win_nfree[w], m = B.m, ldm = m + 1, slot0 = P.win_slot0[w];
     const int i = final ? 0 : (2 * PLBA_BID + 1) * s;
     const int left = final ? -1 : i - s, right = (final || i + s >= B.N) ? -1 : i + s;

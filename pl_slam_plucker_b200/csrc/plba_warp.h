@@ -27,9 +27,6 @@ namespace plba {
 #ifndef PLBA_W_PASSES
 #define PLBA_W_PASSES 8
 #endif
-#ifndef PLBA_W_FULL
-#define PLBA_W_FULL 0      // 1: a Schur task = a whole 6x6 block (36 accumulators per lane), 0: a column half (18 accumulators)
-#endif
 #ifndef PLBA_W_WARPS
 #define PLBA_W_WARPS 4
 #endif
@@ -190,14 +187,10 @@ struct WRec {
     typedef KT<PROF, LT> K;
     // A (the pose rows) is stored as [column half][row of the residual][3]: a Schur task that owns three columns of a 6x6 block reads
     // "its" half of A_b as one aligned run (two residual rows: 6 doubles, no padding; one row: 3 + one pad)
-#if PLBA_W_FULL
-    enum { RANK = K::RANK, D = K::D, NAH = RANK * 3, AHS = 3, NA = RANK * 6, NB = RANK * D,      // whole-block tasks: A as [row of the residual][6]
-#else
     enum { RANK = K::RANK, D = K::D, NAH = (RANK * 3 + 1) & ~1, AHS = NAH / RANK, NA = 2 * NAH, NB = RANK * D,      // AHS: row stride inside a half (3, or 4 with a pad when RANK * 3 is odd)
-#endif
            NBp = (NB + 1) & ~1, NEp = (RANK + 1) & ~1, NVp = (D + 1) & ~1,
            NVp_ = NVp, OA = 0, OB = NA, OT = OB + NBp, OE = OT + NBp, OV = OE + NEp, SIZE = OV + NVp, STRIDE = ((SIZE / 2) % 2 == 1) ? SIZE : SIZE + 2,
-           NACC = PLBA_W_FULL ? 36 : 18, NG = PLBA_W_FULL ? 6 : 3 };
+           NACC = 18, NG = 3 };
     static PLBA_HD size_t bytes() { return sizeof(double) * STRIDE * 32 + sizeof(int) * 64; }
 };
 template <int N> PLBA_HD void wrec_ld(const double *p, double *r) {      // N even, p 16-byte aligned
@@ -213,126 +206,6 @@ template <int N> PLBA_HD void wrec_st(double *p, const double *r) {
 // Both halves need M = Ta B^T (4 D FMAs), but each computes only its three columns of M A_b and of the block: 60 FMAs per landmark
 // and half against the 72 of the round-1 split by rows (where both halves computed all of M A_b), with 18 accumulators per lane
 // (whole blocks, 36 accumulators, spill around the linearisation at 168 registers: measured 2.10 against 1.92 ms at config 5).
-#if PLBA_W_FULL
-struct WTask { int on, pa, pb, sa, sb, half, diag, slice; };
-// whole-block variant: per landmark and pair 4 D + 12 RANK + 36 RANK FMAs on 36 doubles read from shared memory (3 FMAs per double;
-// the column-half variant: 1.7).  The shared-memory pipe delivers 4 bytes per lane and clock whatever the access width or the
-// multicast, so the Schur phase is bound by the doubles it reads.
-PLBA_HD void wtask_decode(int task, int nf, const int *fpos, const int *slot, int slot0, WTask &t) {
-    t.half = 0;
-    int q = task, i = 0;
-    while (q >= nf - i) { q -= nf - i; i++; }
-    const int j = i + q;
-    t.pa = fpos[i]; t.pb = fpos[j];
-    t.sa = slot[t.pa] - slot0; t.sb = slot[t.pb] - slot0;
-    t.diag = (i == j) ? 1 : 0;
-}
-template <int PROF, int LT, int mode>
-PLBA_D void wtask_accumulate(const double *rec, const WTask &t, int k, int first, int step, int nlp, double *blk, double *gv, double *hd) {
-    typedef WRec<PROF, LT> R;
-    const int D = R::D, RANK = R::RANK;
-    for (int m = first; m < nlp; m += step) {
-        const double *ra = rec + (size_t)(m * k + t.pa) * R::STRIDE, *rb = rec + (size_t)(m * k + t.pb) * R::STRIDE;
-        double Aa[R::NA];
-        wrec_ld<R::NA>(ra + R::OA, Aa);
-        if ((PROF != PLBA_PROFILE_G || mode == 0) && t.diag) {        // diag(H_pp): lambda init (all profiles) and the hand LM's multiplicative damping
-#pragma unroll
-            for (int r = 0; r < 6; r++) {
-#pragma unroll
-                for (int kk = 0; kk < RANK; kk++) hd[r] += Aa[kk * 6 + r] * Aa[kk * 6 + r];
-            }
-        }
-        if (mode == 0) continue;
-        double MA[RANK * 6];
-        {
-            double M[RANK * RANK], Ta[R::NBp], Bb[R::NBp], Ab[R::NA];
-            wrec_ld<R::NBp>(ra + R::OT, Ta); wrec_ld<R::NBp>(rb + R::OB, Bb); wrec_ld<R::NA>(rb + R::OA, Ab);
-#pragma unroll
-            for (int kk = 0; kk < RANK; kk++) {
-#pragma unroll
-                for (int k2 = 0; k2 < RANK; k2++) {
-                    double sum = (t.diag && kk == k2) ? -1.0 : 0.0;          // diagonal: A^T (Ta B^T - I) A, subtracted below
-#pragma unroll
-                    for (int mm = 0; mm < D; mm++) sum += Ta[kk * D + mm] * Bb[k2 * D + mm];
-                    M[kk * RANK + k2] = sum;
-                }
-            }
-            if (t.diag) {
-                double ev[R::NEp], V[R::NVp_];
-                wrec_ld<R::NEp>(ra + R::OE, ev); wrec_ld<R::NVp_>(ra + R::OV, V);
-#pragma unroll
-                for (int kk = 0; kk < RANK; kk++) {
-#pragma unroll
-                    for (int mm = 0; mm < D; mm++) ev[kk] += Bb[kk * D + mm] * V[mm];
-                }
-#pragma unroll
-                for (int r = 0; r < 6; r++) {
-#pragma unroll
-                    for (int kk = 0; kk < RANK; kk++) gv[r] -= Aa[kk * 6 + r] * ev[kk];
-                }
-            }
-#pragma unroll
-            for (int kk = 0; kk < RANK; kk++) {
-#pragma unroll
-                for (int c = 0; c < 6; c++) {
-                    double sum = 0;
-#pragma unroll
-                    for (int k2 = 0; k2 < RANK; k2++) sum += M[kk * RANK + k2] * Ab[k2 * 6 + c];
-                    MA[kk * 6 + c] = sum;
-                }
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < 6; r++) {
-#pragma unroll
-            for (int kk = 0; kk < RANK; kk++) {
-                const double av = Aa[kk * 6 + r];
-#pragma unroll
-                for (int c = 0; c < 6; c++) blk[r * 6 + c] -= av * MA[kk * 6 + c];
-            }
-        }
-    }
-}
-template <int PROF, int mode>
-PLBA_D void wtask_flush(const DevP &P, const WTask &t, double *Sw, int ld, int slot0, const double *blk, const double *gv, const double *hd) {
-    if (mode == 0) {
-        if (t.diag) {
-#pragma unroll
-            for (int r = 0; r < 6; r++) plba_atomic_add(&P.hpp_diag_init[(size_t)6 * (slot0 + t.sa) + r], hd[r]);
-        }
-        return;
-    }
-    const bool tr = (t.sa > t.sb);
-    const int ra = tr ? t.sb : t.sa, cb = tr ? t.sa : t.sb;
-    const long long sr = tr ? 1 : ld, sc = tr ? ld : 1;
-    double *p0 = Sw + (size_t)(6 * ra) * ld + 6 * cb;
-    const bool upper_only = (t.sa == t.sb);                        // diagonal block of S: only its upper triangle is stored
-#pragma unroll
-    for (int r = 0; r < 6; r++) {
-#pragma unroll
-        for (int c = 0; c < 6; c++) {
-            if (!upper_only || r <= c) plba_atomic_add(p0 + r * sr + c * sc, blk[r * 6 + c]);
-        }
-    }
-    if (t.diag) {
-#pragma unroll
-        for (int r = 0; r < 6; r++) {
-            plba_atomic_add(&P.gs[(size_t)6 * (slot0 + t.sa) + r], gv[r]);
-            if (PROF != PLBA_PROFILE_G) plba_atomic_add(&P.hpp_diag[(size_t)6 * (slot0 + t.sa) + r], hd[r]);
-        }
-    } else if (upper_only) {
-        // transposed copy of an off-track-diagonal block that landed on the diagonal of S
-#pragma unroll
-        for (int r = 0; r < 6; r++) {
-#pragma unroll
-            for (int c = 0; c < 6; c++) {
-                if (c <= r) plba_atomic_add(p0 + (size_t)c * ld + r, blk[r * 6 + c]);
-            }
-        }
-    }
-}
-
-#else
 struct WTask { int on, pa, pb, sa, sb, half, diag, slice; };
 PLBA_HD void wtask_decode(int task, int nf, const int *fpos, const int *slot, int slot0, WTask &t) {
     const int p = task >> 1;
@@ -424,7 +297,7 @@ PLBA_D void wtask_accumulate(const double *rec, const WTask &t, int k, int first
 // stored the other way round), g, diag(H_pp).  Two observations of one landmark in the same keyframe (sa == sb off the track
 // diagonal: rare) put blk + blk^T onto the diagonal block.
 template <int PROF, int mode>
-PLBA_D void wtask_flush(const DevP &P, const WTask &t, double *Sw, int ld, int slot0, const double *blk, const double *gv, const double *hd) {
+PLBA_D void wtask_flush(const DevP &P, const WTask &t, int win, int slot0, const double *blk, const double *gv, const double *hd) {
     const int hcol = 3 * t.half;
     if (mode == 0) {
         if (t.diag) {
@@ -435,8 +308,9 @@ PLBA_D void wtask_flush(const DevP &P, const WTask &t, double *Sw, int ld, int s
     }
     const bool tr = (t.sa > t.sb);
     const int ra = tr ? t.sb : t.sa, cb = tr ? t.sa : t.sb;
-    const long long sr = tr ? 1 : ld, sc = tr ? ld : 1;
-    double *p0 = Sw + (size_t)(6 * ra) * ld + 6 * cb + hcol * sc;
+    const SBlk sb_ = s_block(P, win, ra, cb);                      // dense upper storage, or the solver's node form (large banded windows)
+    const long long sr = tr ? sb_.sc : sb_.sr, sc = tr ? sb_.sr : sb_.sc;
+    double *p0 = sb_.p + hcol * sc;
     const bool upper_only = (t.sa == t.sb);                        // diagonal block of S: only its upper triangle is stored
 #pragma unroll
     for (int r = 0; r < 6; r++) {
@@ -453,18 +327,15 @@ PLBA_D void wtask_flush(const DevP &P, const WTask &t, double *Sw, int ld, int s
         }
     } else if (upper_only) {
         // transposed copy of an off-track-diagonal block that landed on the diagonal of S
-        double *q0 = Sw + (size_t)(6 * t.sa) * ld + 6 * t.sa;
 #pragma unroll
         for (int r = 0; r < 6; r++) {
 #pragma unroll
             for (int cc = 0; cc < 3; cc++) {
-                if (hcol + cc <= r) plba_atomic_add(q0 + (size_t)(hcol + cc) * ld + r, blk[r * 3 + cc]);
+                if (hcol + cc <= r) plba_atomic_add(sb_.p + (size_t)(hcol + cc) * sb_.sr + r * sb_.sc, blk[r * 3 + cc]);
             }
         }
     }
 }
-
-#endif
 
 // ---------------------------------------------------------------------------------------------------------
 // assembly: mode 0 = diagonal pass for the initial lambda (computeLambdaInit / Hmax, :2555-2561); mode 1 = full
@@ -516,13 +387,11 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
         const int k = it.k, nf = it.nfree;
         const int lpp = 32 / k;                                  // landmarks per pass
         const int npass = (it.n_lm + lpp - 1) / lpp;
-        const int ntask = PLBA_W_FULL ? nf * (nf + 1) / 2 : nf * (nf + 1);      // pairs i <= j (x 2 column halves)
+        const int ntask = nf * (nf + 1);                          // (pairs i <= j) x 2 column halves
         const int rounds = (ntask + 31) >> 5;
         const bool keep = (rounds == 1);                          // the lane's block stays in registers for the whole item
         const int nslice = keep ? 32 / ntask : 1;                 // few tasks: the landmarks of a pass are dealt over several lanes per task
         const int slot0 = P.win_slot0[it.win];
-        const int ld = 6 * P.win_nfree[it.win];
-        double *Sw = P.S + P.win_S_off[it.win];
         const double *state = OA::state(P, ctl.cur);
         WPHASE_BEGIN
             LANE_BIND(kf_l); LANE_BIND(m_l);
@@ -561,9 +430,6 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
                     obs_lin_w<PROF, LT>(P, ctl, o, kf_l, lmd, ob, A, B, e, cost);
                     if (mode == 1) cost_l += cost;
                     double *r = rec + (size_t)lane * R::STRIDE;
-#if PLBA_W_FULL
-                    wrec_st<R::NA>(r + R::OA, A); wrec_st<R::NBp>(r + R::OB, B); wrec_st<R::NEp>(r + R::OE, e);
-#else
                     double Ah[R::NA];
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
@@ -575,7 +441,6 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
                         if (R::NAH > RANK * 3) Ah[h * R::NAH + R::NAH - 1] = 0.0;
                     }
                     wrec_st<R::NA>(r + R::OA, Ah); wrec_st<R::NBp>(r + R::OB, B); wrec_st<R::NEp>(r + R::OE, e);
-#endif
                 }
             WPHASE_END
             // ---- per landmark (redundantly on each of its lanes): H_ll, b_l, damping, inverse; Ta = Bt H_ll^-1, v = H_ll^-1 b_l (subsystem 2) ----
@@ -657,7 +522,7 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
                     }
                     if (tk.on) {
                         wtask_accumulate<PROF, LT, mode>(rec, tk, k, tk.slice, nslice, nlp, blk, gv, hd);
-                        if (!keep || pass == npass - 1) wtask_flush<PROF, mode>(P, tk, Sw, ld, slot0, blk, gv, hd);
+                        if (!keep || pass == npass - 1) wtask_flush<PROF, mode>(P, tk, it.win, slot0, blk, gv, hd);
                     }
                 WPHASE_END
             }
