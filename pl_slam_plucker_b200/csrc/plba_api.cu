@@ -111,6 +111,7 @@ struct plba_handle_s {
     int large_solver = 0;            // 0 = block cyclic reduction (default), 1 = single-CTA banded Cholesky (A/B, tests)
     int grid_warp = 592, grid_warp_upd = 592;
     bool uploaded = false, small_path = true;
+    bool bcr_v1 = false;             // PLBA_BCR_V1=1: the one-CTA-per-node elimination kernel of round 1 (A/B runs)
     bool bcr_layout = false;         // this upload stores the reduced camera system of its (large, block-banded) windows in the node form of the block cyclic reduction
     double *sysbuf = nullptr; size_t sys_doubles = 0, S_doubles = 0;
     int h_counters[CNT_N] = {0};
@@ -320,6 +321,8 @@ int plba_create(int32_t device, void *stream, plba_handle *out) {
     h->force_dense = fd && fd[0] == '1';
     const char *ls = std::getenv("PLBA_LARGE_SOLVER");       // "band": the single-CTA banded Cholesky instead of the block cyclic reduction
     h->large_solver = (ls && ls[0] == 'b' && ls[1] == 'a') ? 1 : 0;
+    const char *b1 = std::getenv("PLBA_BCR_V1");
+    h->bcr_v1 = b1 && b1[0] == '1';
     const char *fc = std::getenv("PLBA_FORCE_CHUNK");        // always take the CTA-chunk assembly / update kernels (tests, A/B runs)
     h->force_chunk = fc ? std::atoi(fc) : 0;
 #else
@@ -464,6 +467,8 @@ template <int PROF> static void set_smem_attr() {
         cudaFuncSetAttribute(k_solve_banded, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_banded_smem());
         cudaFuncSetAttribute(k_bcr_elim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bcr_elim_smem());
         cudaFuncSetAttribute(k_bcr_back, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bcr_back_smem());
+        cudaFuncSetAttribute(k_bcr_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bcr_factor_smem());
+        cudaFuncSetAttribute(k_bcr_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bcr_schur_smem());
         cudaFuncSetAttribute(k_potrf_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_block_smem());
         cudaFuncSetAttribute(k_trsm_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_block_smem());
         cudaFuncSetAttribute(k_syrk_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_dmma_smem());
@@ -602,10 +607,17 @@ static void launch_solve(plba_handle h) {
             //  it over the ranks: config 5 moves 17 MB, there is no dense S)
             int s_top = 0;
             for (int s = 1; s < B.N; s *= 2) {
-                PLBA_LAUNCH(k_bcr_elim, dim3((B.N + s - 1) / (2 * s)), dim3(BCR_NT), bcr_elim_smem(), h->stream, Pp, w, B, s, 0); h->timing.n_launches++;
+                const int ne = (B.N + s - 1) / (2 * s);
+                if (h->bcr_v1) { PLBA_LAUNCH(k_bcr_elim, dim3(ne), dim3(BCR_NT), bcr_elim_smem(), h->stream, Pp, w, B, s, 0); h->timing.n_launches++; }
+                else {
+                    // a node's elimination over seven CTAs: two factor its diagonal block with one coupling block each, five form the Schur products
+                    PLBA_LAUNCH(k_bcr_factor, dim3(2 * ne), dim3(BF_NT), bcr_factor_smem(), h->stream, Pp, w, B, s, 0);
+                    PLBA_LAUNCH(k_bcr_schur, dim3(BS_PARTS * ne), dim3(BS_NT), bcr_schur_smem(), h->stream, Pp, w, B, s); h->timing.n_launches += 2;
+                }
                 s_top = s;
             }
-            PLBA_LAUNCH(k_bcr_elim, dim3(1), dim3(BCR_NT), bcr_elim_smem(), h->stream, Pp, w, B, 0, 1);
+            if (h->bcr_v1) PLBA_LAUNCH(k_bcr_elim, dim3(1), dim3(BCR_NT), bcr_elim_smem(), h->stream, Pp, w, B, 0, 1);
+            else PLBA_LAUNCH(k_bcr_factor, dim3(1), dim3(BF_NT), bcr_factor_smem(), h->stream, Pp, w, B, 0, 1);
             PLBA_LAUNCH(k_bcr_back, dim3(1), dim3(256), bcr_back_smem(), h->stream, Pp, w, B, 0, 1); h->timing.n_launches += 2;
             for (int s = s_top; s >= 1; s /= 2) {
                 PLBA_LAUNCH(k_bcr_back, dim3((B.N + s - 1) / (2 * s)), dim3(256), bcr_back_smem(), h->stream, Pp, w, B, s, 0); h->timing.n_launches++;
@@ -1025,6 +1037,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
             h->bcr.push_back(B);
             const size_t nn = (size_t)B.N * m * m;
             s_bcr.push_back(cs.take<double>(nn)); s_bcr.push_back(cs.take<double>(nn)); s_bcr.push_back(cs.take<double>((size_t)B.N * m));   // Xl, Xr, y (D, U, b, hd live in the system buffer)
+            s_bcr.push_back(cs.take<double>(nn));                                                                                                // Lf
         }
     }
     const int trace_cap = (prof == PLBA_PROFILE_G) ? (opt->iters_stage1 + opt->iters_stage2) * opt->lm_max_trials + 2 : opt->max_iters_lba + 2;
@@ -1162,7 +1175,8 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
         const size_t nn = (size_t)B.N * B.m * B.m;
         B.D = P.S + win_S_off[w]; B.U = B.D + nn;
         B.b = P.gs + (size_t)6 * h->wins[w].slot0; B.hd = P.hpp_diag + (size_t)6 * h->wins[w].slot0;      // node i, unknown c <-> slot i bs + c / 6: the same index as in g
-        B.Xl = (double *)(db + s_bcr[3 * w]); B.Xr = (double *)(db + s_bcr[3 * w + 1]); B.y = (double *)(db + s_bcr[3 * w + 2]);
+        B.Xl = (double *)(db + s_bcr[4 * w]); B.Xr = (double *)(db + s_bcr[4 * w + 1]); B.y = (double *)(db + s_bcr[4 * w + 2]);
+        B.Lf = h->bcr_v1 ? nullptr : (double *)(db + s_bcr[4 * w + 3]);
     }
     P.solve_nf_max = std::min(max_nf, (int)SMALL_NMAX / 6);
     P.S_clear_doubles = h->small_path ? (long long)((h->S_doubles + 1) & ~(size_t)1) : 0;      // (the buffer continues with g: an odd tail would only clear g[0], which the solver has consumed too; S_doubles is even anyway)

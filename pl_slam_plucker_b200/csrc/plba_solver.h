@@ -925,11 +925,11 @@ PLBA_KERNEL void k_solve_banded(const DevP *Pp, int bwb) {
 // the levels are walked back:  L^T x_i = y - Xl^T x_{i-s} - Xr^T x_{i+s}.
 // This is a Cholesky factorisation in a nested-dissection order of the keyframe chain: same system, same solution up to rounding,
 // but the 6 Nkf sequential pivots of the banded factorisation become 90 ceil(log2 N) and every level fills the GPU.
-struct BcrW { double *D, *U, *b, *hd, *Xl, *Xr, *y; int N, bs, m, pad; };   // node storage: D, U, Xl, Xr: [N][m*m] (row stride m); b, hd, y: [N][m];
+struct BcrW { double *D, *U, *b, *hd, *Xl, *Xr, *y, *Lf; int N, bs, m, pad; };   // Lf: factors of the split elimination (k_bcr_factor: the two CTAs of a node both read D_i, so L cannot overwrite it)   // node storage: D, U, Xl, Xr: [N][m*m] (row stride m); b, hd, y: [N][m];
                                                                            // D, U: the window's slice of P.S (the assembly kernels accumulate into the node form directly, s_block()); b = the window's slice of g, hd of diag(H_pp)
 enum { BCR_BS_MAX = 15, BCR_M_MAX = 6 * BCR_BS_MAX, BCR_NT = 512 };
 static inline size_t bcr_elim_smem() { return sizeof(double) * ((size_t)(3 * BCR_M_MAX + 1) * (BCR_M_MAX + 1) + BCR_M_MAX + 21 * BCR_BS_MAX + 6 * 264 + 8) + 64; }
-static inline size_t bcr_back_smem() { return sizeof(double) * ((size_t)BCR_M_MAX * (BCR_M_MAX + 1) + 7 * BCR_M_MAX + 8) + 64; }
+static inline size_t bcr_back_smem() { return sizeof(double) * ((size_t)BCR_M_MAX * (BCR_M_MAX + 1) + 11 * BCR_M_MAX + 8) + 64; }
 PLBA_HD int bcr_node_size(const BcrW &B, int nf, int i) { const int k0 = i * B.bs, k1 = (k0 + B.bs < nf) ? k0 + B.bs : nf; return 6 * (k1 - k0); }
 
 // eliminate the nodes (2 j + 1) s of one level (final != 0: node 0, nothing left to couple to)
@@ -1036,26 +1036,52 @@ PLBA_KERNEL void k_bcr_back(const DevP *Pp, int w, BcrW B, int s, int final) {
     const int left = final ? -1 : i - s, right = (final || i + s >= B.N) ? -1 : i + s;
     const int mi = bcr_node_size(B, nf, i), ml = left >= 0 ? m : 0, mr = right >= 0 ? bcr_node_size(B, nf, right) : 0;
     double *L = (double *)raw, *rhs = L + (size_t)BCR_M_MAX * (BCR_M_MAX + 1), *xs = rhs + BCR_M_MAX, *dinv = xs + BCR_M_MAX, *xn = dinv + BCR_M_MAX, *part = xn + 2 * BCR_M_MAX;
-    const double *Di = B.D + (size_t)i * m * m, *Xl = B.Xl + (size_t)i * m * m, *Xr = B.Xr + (size_t)i * m * m;
+    const double *Di = (B.Lf ? B.Lf : B.D) + (size_t)i * m * m, *Xl = B.Xl + (size_t)i * m * m, *Xr = B.Xr + (size_t)i * m * m;      // the factor: over D_i (one-CTA elimination) or in Lf (split elimination)
     double *x = P.xp + (size_t)6 * slot0;
     PHASE_BEGIN
-        for (int idx = tid; idx < mi * mi; idx += PLBA_NT) { const int r = idx / mi, c = idx - r * mi; if (c <= r) { const double v = Di[(size_t)r * m + c]; L[(size_t)r * ldm + c] = v; if (c == r) dinv[r] = 1.0 / v; } }
+        // the factor, 128-bit loads, four independent loads in flight per thread (this kernel is pure latency: 50 us per level before)
+        const int npair = mi * mi / 2;                                   // mi is a multiple of 6: rows hold whole pairs
+        for (int i0 = tid; i0 < npair; i0 += 4 * PLBA_NT) {
+            plba_d2 v[4]; int rr[4], cc[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int idx = i0 + u * PLBA_NT;
+                rr[u] = (2 * idx) / mi; cc[u] = 2 * idx - rr[u] * mi;
+                const bool on = idx < npair && cc[u] <= rr[u];
+                v[u] = on ? *(const plba_d2 *)(Di + (size_t)rr[u] * m + cc[u]) : plba_d2{0.0, 0.0};
+                if (!on) rr[u] = -1;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (rr[u] >= 0) {
+                L[(size_t)rr[u] * ldm + cc[u]] = v[u].x;
+                if (cc[u] == rr[u]) dinv[rr[u]] = 1.0 / v[u].x;
+                if (cc[u] + 1 <= rr[u]) { L[(size_t)rr[u] * ldm + cc[u] + 1] = v[u].y; if (cc[u] + 1 == rr[u]) dinv[rr[u]] = 1.0 / v[u].y; }
+            }
+        }
         // the neighbours' solutions, staged once
         for (int r = tid; r < ml; r += PLBA_NT) xn[r] = x[(size_t)6 * left * B.bs + r];
         for (int r = tid; r < mr; r += PLBA_NT) xn[BCR_M_MAX + r] = x[(size_t)6 * right * B.bs + r];
     PHASE_END
     PHASE_BEGIN
-        // rhs = y - Xl^T x_left - Xr^T x_right: thread = (column c, quarter of the rows); the rows of Xl / Xr are read coalesced over c
-        const int c = tid % 128, qt = tid / 128;                       // 256 threads: two row halves per neighbour block, interleaved
-        if (c < mi) {
-            double acc = 0.0;
-            for (int r = qt; r < ml; r += 2) acc += Xl[(size_t)r * m + c] * xn[r];
-            for (int r = qt; r < mr; r += 2) acc += Xr[(size_t)r * m + c] * xn[BCR_M_MAX + r];
-            part[qt * BCR_M_MAX + c] = acc;
+        // rhs = y - Xl^T x_left - Xr^T x_right: thread = (pair of columns, fifth of the rows), 128-bit loads, six rows in flight
+        const int ncp = mi / 2, cp = tid % 48, qt = tid / 48;           // 256 threads: 5 row groups x 48 column pairs (45 used at m = 90)
+        if (cp < ncp && qt < 5) {
+            double a0 = 0.0, a1 = 0.0;
+            for (int pass = 0; pass < 2; pass++) {
+                const double *X = pass ? Xr : Xl; const double *xv = pass ? xn + BCR_M_MAX : xn; const int rows = pass ? mr : ml;
+                for (int r0 = qt; r0 < rows; r0 += 30) {
+                    plba_d2 v[6];
+#pragma unroll
+                    for (int u = 0; u < 6; u++) { const int r = r0 + 5 * u; v[u] = r < rows ? *(const plba_d2 *)(X + (size_t)r * m + 2 * cp) : plba_d2{0.0, 0.0}; }
+#pragma unroll
+                    for (int u = 0; u < 6; u++) { const int r = r0 + 5 * u; if (r < rows) { a0 += v[u].x * xv[r]; a1 += v[u].y * xv[r]; } }
+                }
+            }
+            part[qt * BCR_M_MAX + 2 * cp] = a0; part[qt * BCR_M_MAX + 2 * cp + 1] = a1;
         }
     PHASE_END
     PHASE_BEGIN
-        for (int c = tid; c < mi; c += PLBA_NT) rhs[c] = B.y[(size_t)i * m + c] - part[c] - part[BCR_M_MAX + c];
+        for (int c = tid; c < mi; c += PLBA_NT) { double v = B.y[(size_t)i * m + c]; for (int q = 0; q < 5; q++) v -= part[q * BCR_M_MAX + c]; rhs[c] = v; }
     PHASE_END
     // column-oriented backward substitution by ONE warp (the chain of mi steps is latency: no block barrier inside):
     // x_j = rhs_j / L_jj, then rhs_r -= L[j][r] x_j for r < j (row j of L: contiguous)
@@ -1090,6 +1116,321 @@ PLBA_KERNEL void k_bcr_back(const DevP *Pp, int w, BcrW B, int s, int final) {
     PHASE_END
     PHASE_BEGIN
         for (int c = tid; c < mi; c += PLBA_NT) x[(size_t)6 * i * B.bs + c] = xs[c];
+    PHASE_END
+}
+
+
+// ---- block cyclic reduction, second generation: the elimination of a node split over SEVEN CTAs in two launches ------------------
+// k_bcr_elim above factors a node, solves both coupling blocks against the factor and forms the three Schur products in ONE CTA:
+// ~4 M FMAs on one SM (>= 32 us at the FP64 peak of an SM, ~130 us measured) while most of the GPU idles at the deep levels.
+//   k_bcr_factor : two CTAs per eliminated node (side 0: left coupling block + right-hand side, side 1: right coupling block).  Each
+//                  factors the node's diagonal block itself (same instructions, same bits: no communication) with the register-
+//                  resident block Cholesky of k_solve_small — one thread per 6x6 block, the coupling block rides along as extra
+//                  block rows — and writes L, X = A L^-T and y = L^-1 b.
+//   k_bcr_schur  : five CTAs per eliminated node: D_left -= Xl Xl^T (+ b_left -= Xl y), D_right -= Xr Xr^T (+ b_right), and three row
+//                  groups of A[left, right] = -Xl Xr^T; operands staged in shared memory, one thread per 6x6 output block.
+enum { BF_NT = 384, BF_LOW0 = 32, BF_X0 = 32 + BCR_BS_MAX * (BCR_BS_MAX - 1) / 2 /* 137 */, BF_XLD = 37, BS_NT = 256, BS_PARTS = 5 };   // 384 threads = 3 warps per scheduler: 168 registers
+static inline size_t bcr_factor_smem() { return sizeof(double) * ((size_t)(2 * BCR_BS_MAX) * BF_XLD + 32 + BCR_M_MAX + 8) + 64; }
+static inline size_t bcr_schur_smem() { return sizeof(double) * ((size_t)(BCR_M_MAX + 30) * (BCR_M_MAX + 1) + BCR_M_MAX + 8); }   // 88 KB (parts 0-1: one 90-row operand; parts 2-4: 30 + 90 rows); compiled for one CTA per SM: 164 registers, no spills (two CTAs at 128 registers measured 3 % slower)
+
+PLBA_KERNEL void PLBA_BOUNDS(BF_NT, 1) k_bcr_factor(const DevP *Pp, int w, BcrW B, int s, int final) {
+    PLBA_SMEM(raw);
+    PLBA_PARAMS(P, Pp);
+    WinCtrl &ctl = P.ctrl[w];
+    if (ctl.done) return;
+    const int nf = P.win_nfree[w], m = B.m;
+    const int side = final ? 0 : (PLBA_BID & 1);
+    const int i = final ? 0 : (2 * (PLBA_BID >> 1) + 1) * s;
+    const int right = (final || i + s >= B.N) ? -1 : i + s;
+    if (side == 1 && right < 0) return;
+    const int mi = bcr_node_size(B, nf, i), nb = mi / 6;
+    const int nx = final ? 0 : (side == 0 ? m / 6 : bcr_node_size(B, nf, right) / 6);      // block rows of the coupling block that rides along
+    double *Xp = (double *)raw, *Lc = Xp + (size_t)(2 * BCR_BS_MAX) * BF_XLD, *ys = Lc + 32;
+    int *fail = (int *)(ys + BCR_M_MAX);
+    double *Di = B.D + (size_t)i * m * m;
+    const double *Ui = B.U + (size_t)i * m * m, *Ur = right >= 0 ? B.U + (size_t)right * m * m : nullptr;
+    const double lambda = ctl.lambda;
+    THR_ARR(double, blk, 36); THR_ARR(double, gv, 6);
+    THR_VAR(int, bi); THR_VAR(int, bj); THR_VAR(int, act);
+    PHASE_BEGIN
+        THR_BIND(blk); THR_BIND(gv); THR_BIND(bi); THR_BIND(bj); THR_BIND(act);
+        if (tid == 0) *fail = 0;
+        act = 0; bi = 0; bj = 0;
+        // thread -> block: warp 0 the diagonal blocks, threads 32..136 the strictly lower blocks of the node by column, threads 137.. the
+        // coupling block by column (block row nb + xi): 137 + 225 <= 384
+        if (tid < BF_LOW0) { if (tid < nb) { act = 1; bi = bj = tid; } }
+        else if (tid < BF_X0) {
+            int j = 0, rem = tid - BF_LOW0;
+            while (j < nb - 1 && rem >= nb - 1 - j) { rem -= nb - 1 - j; j++; }
+            if (j < nb - 1) { act = 1; bj = j; bi = j + 1 + rem; }
+        } else if (nx > 0) {
+            const int u = tid - BF_X0;
+            if (u < nx * nb) { act = 2; bj = u / nx; bi = nb + (u - bj * nx); }
+        }
+        if (act == 1) {
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                const plba_d2 *row = (const plba_d2 *)(Di + (size_t)(6 * bi + r) * m + 6 * bj);
+#pragma unroll
+                for (int c2 = 0; c2 < 3; c2++) { const plba_d2 v = row[c2]; blk[r * 6 + 2 * c2] = v.x; blk[r * 6 + 2 * c2 + 1] = v.y; }
+            }
+            if (bi == bj) {
+#pragma unroll
+                for (int c = 0; c < 6; c++) {
+                    blk[c * 6 + c] += (P.profile == PLBA_PROFILE_G) ? lambda : lambda * B.hd[(size_t)i * m + 6 * bj + c];      // g2o: additive; hand LM: H_ii (1 + lambda)
+                    gv[c] = B.b[(size_t)i * m + 6 * bj + c];
+                }
+                if (bj == 0) {      // look-ahead for the first panel
+                    double inv[6];
+                    if (!chol6_inplace(blk, inv)) *fail = 1;
+#pragma unroll
+                    for (int r = 0; r < 6; r++) {
+#pragma unroll
+                        for (int c = 0; c <= r; c++) Lc[r * (r + 1) / 2 + c] = blk[r * 6 + c];
+                    }
+#pragma unroll
+                    for (int c = 0; c < 6; c++) Lc[21 + c] = inv[c];
+                }
+            }
+        } else if (act == 2) {
+            const int xi = bi - nb;
+            if (side == 0) {      // A[i - s, i] = U_i: rows = unknowns of the left neighbour
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+                    const plba_d2 *row = (const plba_d2 *)(Ui + (size_t)(6 * xi + r) * m + 6 * bj);
+#pragma unroll
+                    for (int c2 = 0; c2 < 3; c2++) { const plba_d2 v = row[c2]; blk[r * 6 + 2 * c2] = v.x; blk[r * 6 + 2 * c2 + 1] = v.y; }
+                }
+            } else {              // A[i + s, i] = U_right^T: rows = unknowns of the right neighbour
+#pragma unroll
+                for (int c = 0; c < 6; c++) {
+                    const plba_d2 *col = (const plba_d2 *)(Ur + (size_t)(6 * bj + c) * m + 6 * xi);
+#pragma unroll
+                    for (int r2 = 0; r2 < 3; r2++) { const plba_d2 v = col[r2]; blk[(2 * r2) * 6 + c] = v.x; blk[(2 * r2 + 1) * 6 + c] = v.y; }
+                }
+            }
+        }
+    PHASE_END
+    for (int kb = 0; kb < nb; kb++) {
+        // ---- A(kb): block column kb: X = M L_kk^-T, y_k = L_kk^-1 b_k ----
+        PHASE_BEGIN
+            THR_BIND(blk); THR_BIND(gv); THR_BIND(bi); THR_BIND(bj); THR_BIND(act);
+            if (act && bj == kb) {
+                double L[21], inv[6];
+#pragma unroll
+                for (int q = 0; q < 21; q++) L[q] = Lc[q];
+#pragma unroll
+                for (int q = 0; q < 6; q++) inv[q] = Lc[21 + q];
+                if (bi == kb) {
+                    double y[6];
+#pragma unroll
+                    for (int c = 0; c < 6; c++) y[c] = gv[c];
+#pragma unroll
+                    for (int c = 0; c < 6; c++) {
+                        y[c] *= inv[c];
+#pragma unroll
+                        for (int mm = c + 1; mm < 6; mm++) y[mm] -= L[mm * (mm + 1) / 2 + c] * y[c];
+                    }
+#pragma unroll
+                    for (int c = 0; c < 6; c++) ys[6 * kb + c] = y[c];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 6; c++) {
+#pragma unroll
+                        for (int r = 0; r < 6; r++) blk[r * 6 + c] *= inv[c];
+#pragma unroll
+                        for (int mm = c + 1; mm < 6; mm++) {
+#pragma unroll
+                            for (int r = 0; r < 6; r++) blk[r * 6 + mm] -= blk[r * 6 + c] * L[mm * (mm + 1) / 2 + c];
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 36; q++) Xp[bi * BF_XLD + q] = blk[q];
+                }
+            }
+        PHASE_END
+        // ---- B(kb): trailing update on registers; look-ahead factorisation of the next diagonal block ----
+        PHASE_BEGIN
+            THR_BIND(blk); THR_BIND(gv); THR_BIND(bi); THR_BIND(bj); THR_BIND(act);
+            if (act && bj > kb) {
+                double Xj[36];
+#pragma unroll
+                for (int q = 0; q < 36; q++) Xj[q] = Xp[bj * BF_XLD + q];
+                if (bi != bj) {
+#pragma unroll
+                    for (int r = 0; r < 6; r++) {
+                        double xi[6];
+#pragma unroll
+                        for (int mm = 0; mm < 6; mm++) xi[mm] = Xp[bi * BF_XLD + r * 6 + mm];
+#pragma unroll
+                        for (int c = 0; c < 6; c++) {
+                            double v = blk[r * 6 + c];
+#pragma unroll
+                            for (int mm = 0; mm < 6; mm++) v -= xi[mm] * Xj[c * 6 + mm];
+                            blk[r * 6 + c] = v;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 6; r++) {
+#pragma unroll
+                        for (int c = 0; c <= r; c++) {
+                            double v = blk[r * 6 + c];
+#pragma unroll
+                            for (int mm = 0; mm < 6; mm++) v -= Xj[r * 6 + mm] * Xj[c * 6 + mm];
+                            blk[r * 6 + c] = v;
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 6; r++) {
+                        double v = gv[r];
+#pragma unroll
+                        for (int mm = 0; mm < 6; mm++) v -= Xj[r * 6 + mm] * ys[6 * kb + mm];
+                        gv[r] = v;
+                    }
+                    if (bj == kb + 1) {
+                        double inv[6];
+                        if (!chol6_inplace(blk, inv)) *fail = 1;
+#pragma unroll
+                        for (int r = 0; r < 6; r++) {
+#pragma unroll
+                            for (int c = 0; c <= r; c++) Lc[r * (r + 1) / 2 + c] = blk[r * 6 + c];
+                        }
+#pragma unroll
+                        for (int c = 0; c < 6; c++) Lc[21 + c] = inv[c];
+                    }
+                }
+            }
+        PHASE_END
+    }
+    // ---- results: L over D_i (side 0), X = A L^-T into Xl / Xr, y ----
+    PHASE_BEGIN
+        THR_BIND(blk); THR_BIND(bi); THR_BIND(bj); THR_BIND(act);
+        if (act == 1 && side == 0) {
+            double *Li = B.Lf + (size_t)i * m * m;      // (not over D_i: the other CTA of this node may still be loading it)
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+#pragma unroll
+                for (int c = 0; c < 6; c++) if (bi != bj || c <= r) Li[(size_t)(6 * bi + r) * m + 6 * bj + c] = blk[r * 6 + c];
+            }
+        } else if (act == 2) {
+            double *X = (side == 0 ? B.Xl : B.Xr) + (size_t)i * m * m;
+            const int xi = bi - nb;
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                plba_d2 *row = (plba_d2 *)(X + (size_t)(6 * xi + r) * m + 6 * bj);
+#pragma unroll
+                for (int c2 = 0; c2 < 3; c2++) { plba_d2 v; v.x = blk[r * 6 + 2 * c2]; v.y = blk[r * 6 + 2 * c2 + 1]; row[c2] = v; }
+            }
+        }
+        if (side == 0) for (int c = tid; c < mi; c += PLBA_NT) B.y[(size_t)i * m + c] = ys[c];
+        if (tid == 0 && *fail) ctl.solve_fail = 1;
+    PHASE_END
+}
+
+PLBA_KERNEL void PLBA_BOUNDS(BS_NT, 1) k_bcr_schur(const DevP *Pp, int w, BcrW B, int s) {
+    PLBA_SMEM(raw);
+    PLBA_PARAMS(P, Pp);
+    const WinCtrl &ctl = P.ctrl[w];
+    if (ctl.done) return;
+    const int nf = P.win_nfree[w], m = B.m, ld = m + 1;
+    const int part = PLBA_BID % BS_PARTS, i = (2 * (PLBA_BID / BS_PARTS) + 1) * s;
+    const int left = i - s, right = (i + s >= B.N) ? -1 : i + s;
+    if (part >= 1 && right < 0) return;
+    const int mi = bcr_node_size(B, nf, i), nb = mi / 6, ml = m, mr = right >= 0 ? bcr_node_size(B, nf, right) : 0;
+    double *Xa = (double *)raw, *Xb = Xa + (size_t)30 * (BCR_M_MAX + 1), *ysm = Xa + (size_t)(BCR_M_MAX + 30) * (BCR_M_MAX + 1);      // parts 0-1 use Xa alone (up to 90 rows: it runs into Xb's space)
+    const double *Xl = B.Xl + (size_t)i * m * m, *Xr = B.Xr + (size_t)i * m * m;
+    // operands: part 0: Xa = Xl; part 1: Xa = Xr; parts 2-4: Xa = five block rows of Xl, Xb = Xr
+    const int rg = part - 2;                                         // row group of the left neighbour (parts 2-4)
+    const int ra0 = part >= 2 ? 30 * rg : 0;
+    const int rows_a = part == 0 ? ml : part == 1 ? mr : ((ml - ra0) < 30 ? ((ml - ra0) > 0 ? ml - ra0 : 0) : 30);
+    const double *srcA = part == 1 ? Xr : Xl + (size_t)ra0 * m;
+    PHASE_BEGIN
+        const int warp = tid >> 5, lane = tid & 31, nw = PLBA_NT >> 5;
+        for (int r = warp; r < rows_a; r += nw) for (int c = lane; c < mi; c += 32) Xa[(size_t)r * ld + c] = srcA[(size_t)r * m + c];
+        if (part >= 2) for (int r = warp; r < mr; r += nw) for (int c = lane; c < mi; c += 32) Xb[(size_t)r * ld + c] = Xr[(size_t)r * m + c];
+        if (part < 2) for (int c = tid; c < mi; c += PLBA_NT) ysm[c] = B.y[(size_t)i * m + c];
+    PHASE_END
+    PHASE_BEGIN
+        if (part < 2) {
+            // D_n -= X X^T on the lower blocks (p >= q); two eliminations of one level meet in the same D: red.global.add
+            const int nbo = rows_a / 6, nblk = nbo * (nbo + 1) / 2;
+            double *Dn = B.D + (size_t)(part == 0 ? left : right) * m * m;
+            if (tid < nblk) {
+                int q = 0, rem = tid;
+                while (rem >= nbo - q) { rem -= nbo - q; q++; }
+                const int p = q + rem;
+                double acc[36];
+#pragma unroll
+                for (int e = 0; e < 36; e++) acc[e] = 0.0;
+                for (int c = 0; c < nb; c++) {
+                    double Xq[36];
+#pragma unroll
+                    for (int r = 0; r < 6; r++) {
+#pragma unroll
+                        for (int k = 0; k < 6; k++) Xq[r * 6 + k] = Xa[(size_t)(6 * q + r) * ld + 6 * c + k];
+                    }
+#pragma unroll
+                    for (int r = 0; r < 6; r++) {
+                        double xp[6];
+#pragma unroll
+                        for (int k = 0; k < 6; k++) xp[k] = Xa[(size_t)(6 * p + r) * ld + 6 * c + k];
+#pragma unroll
+                        for (int cc = 0; cc < 6; cc++) {
+#pragma unroll
+                            for (int k = 0; k < 6; k++) acc[r * 6 + cc] += xp[k] * Xq[cc * 6 + k];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+#pragma unroll
+                    for (int cc = 0; cc < 6; cc++) if (p != q || cc <= r) plba_atomic_add(Dn + (size_t)(6 * p + r) * m + 6 * q + cc, -acc[r * 6 + cc]);
+                }
+            } else if (tid >= 128 && tid - 128 < rows_a) {
+                // right-hand side of the neighbour: b_n -= X y
+                const int r = tid - 128;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+                int q = 0;
+                for (; q + 2 < mi; q += 3) { s0 += Xa[(size_t)r * ld + q] * ysm[q]; s1 += Xa[(size_t)r * ld + q + 1] * ysm[q + 1]; s2 += Xa[(size_t)r * ld + q + 2] * ysm[q + 2]; }
+                for (; q < mi; q++) s0 += Xa[(size_t)r * ld + q] * ysm[q];
+                plba_atomic_add(&B.b[(size_t)(part == 0 ? left : right) * m + r], -(s0 + s1 + s2));
+            }
+        } else {
+            // A[left, right] = -Xl Xr^T (rows 30 rg .. of the left neighbour): plain stores, this CTA is the only writer
+            double *Un = B.U + (size_t)right * m * m;
+            const int nbp = rows_a / 6, nbq = mr / 6;
+            if (tid < nbp * nbq) {
+                const int p = tid / nbq, q = tid - p * nbq;
+                double acc[36];
+#pragma unroll
+                for (int e = 0; e < 36; e++) acc[e] = 0.0;
+                for (int c = 0; c < nb; c++) {
+                    double Xq[36];
+#pragma unroll
+                    for (int r = 0; r < 6; r++) {
+#pragma unroll
+                        for (int k = 0; k < 6; k++) Xq[r * 6 + k] = Xb[(size_t)(6 * q + r) * ld + 6 * c + k];
+                    }
+#pragma unroll
+                    for (int r = 0; r < 6; r++) {
+                        double xp[6];
+#pragma unroll
+                        for (int k = 0; k < 6; k++) xp[k] = Xa[(size_t)(6 * p + r) * ld + 6 * c + k];
+#pragma unroll
+                        for (int cc = 0; cc < 6; cc++) {
+#pragma unroll
+                            for (int k = 0; k < 6; k++) acc[r * 6 + cc] += xp[k] * Xq[cc * 6 + k];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+#pragma unroll
+                    for (int cc = 0; cc < 6; cc++) Un[(size_t)(ra0 + 6 * p + r) * m + 6 * q + cc] = -acc[r * 6 + cc];
+                }
+            }
+        }
     PHASE_END
 }
 
