@@ -165,14 +165,16 @@ template <int PROF> struct SmemMax {
 //     node j - 1 (rows) and node j (columns).  No dense S exists for such a window (config 5: 35 MB instead of 1.15 GB) and no gather
 //     kernel runs before the solve (round 1: 0.35 ms of a 1.77 ms solve).  The half bandwidth is <= bs, so cb / bs - ra / bs <= 1.
 struct SBlk { double *p; long long sr, sc; };
-PLBA_HD SBlk s_block(const DevP &P, int win, int ra, int cb) {
-    double *Sw = P.S + P.win_S_off[win];
-    const int bs = P.win_bcr_bs[win];
+struct SWin { double *Sw; long long ld; int bs, N; };      // one window's storage, read ONCE per chunk / work item (three dependent global loads)
+PLBA_HD SWin s_window(const DevP &P, int win) {
+    SWin w; w.Sw = P.S + P.win_S_off[win]; w.bs = P.win_bcr_bs[win]; w.N = P.win_bcr_N[win]; w.ld = 6 * (long long)P.win_nfree[win]; return w;
+}
+PLBA_HD SBlk s_block(const SWin &w, int ra, int cb) {
     SBlk b;
-    if (bs == 0) { const long long ld = 6 * (long long)P.win_nfree[win]; b.p = Sw + (size_t)(6 * ra) * ld + 6 * cb; b.sr = ld; b.sc = 1; return b; }
-    const int m = 6 * bs, i = ra / bs, j = cb / bs, a = ra - i * bs, c = cb - j * bs;
-    if (i == j) { b.p = Sw + (size_t)i * m * m + (size_t)(6 * c) * m + 6 * a; b.sr = 1; b.sc = m; }       // D_i[(6c + col) m + 6a + row]: lower triangle
-    else { b.p = Sw + (size_t)P.win_bcr_N[win] * m * m + (size_t)j * m * m + (size_t)(6 * a) * m + 6 * c; b.sr = m; b.sc = 1; }   // U_j[(6a + row) m + 6c + col]
+    if (w.bs == 0) { b.p = w.Sw + (size_t)(6 * ra) * w.ld + 6 * cb; b.sr = w.ld; b.sc = 1; return b; }
+    const int bs = w.bs, m = 6 * bs, i = ra / bs, j = cb / bs, a = ra - i * bs, c = cb - j * bs;
+    if (i == j) { b.p = w.Sw + (size_t)i * m * m + (size_t)(6 * c) * m + 6 * a; b.sr = 1; b.sc = m; }       // D_i[(6c + col) m + 6a + row]: lower triangle
+    else { b.p = w.Sw + (size_t)w.N * m * m + (size_t)j * m * m + (size_t)(6 * a) * m + 6 * c; b.sr = m; b.sc = 1; }   // U_j[(6a + row) m + 6c + col]
     return b;
 }
 
@@ -280,7 +282,7 @@ PLBA_HD double obs_linearize(const DevP &P, const WinCtrl &ctl, int o, int t, in
             double rho0 = chi2, rho1 = 1.0;
             if (ctl.stage == 0) huber(P.huber_delta, chi2, rho0, rho1);
             cost = rho0;
-            wsq = sqrt(rho1 * om);
+            { const double ww = rho1 * om; wsq = (ww > 1e-290 && ww < 1e290) ? ww * plba_rsqrt_fast(ww) : sqrt(ww); }      // sqrt(rho1 Omega)
         }
     } else {
         const bool pass0 = (ctl.iter == 0);
@@ -439,7 +441,7 @@ PLBA_D void assemble_chunk(const DevP &Pin, const Chunk &ch, int mode) {
     }
     const int slot0 = P.win_slot0[ch.win];
     const int ld = 6 * P.win_nfree[ch.win];
-    double *Sw = P.S + P.win_S_off[ch.win];
+    const SWin swin = s_window(P, ch.win);
     // ---- off-diagonal pose pairs (a,b), a before b in the landmark's track: S_ab -= At_a^T (Ta_a Bt_b^T) At_b ----
     PHASE_BEGIN
         const int ntasks = (nseg && mode == 1) ? sm.seg_task0[nseg] : 0;
@@ -508,16 +510,17 @@ PLBA_D void assemble_chunk(const DevP &Pin, const Chunk &ch, int mode) {
             for (int pass = 0; pass < npass; pass++) {
                 const bool tr = same ? (pass == 1) : (sa > sb);
                 const int ra = tr ? sb : sa, cb = tr ? sa : sb;
-                const SBlk sb_ = s_block(P, ch.win, ra, cb);
+                const SBlk sb_ = s_block(swin, ra, cb);
                 double *base = sb_.p;
-                const long long sr = tr ? sb_.sc : sb_.sr, sc = tr ? sb_.sr : sb_.sc;
+                // 32-bit strides (a row of the largest storage is 12 000 doubles): this address arithmetic sits on the latency path of a small window
+                const int sr = (int)(tr ? sb_.sc : sb_.sr), sc = (int)(tr ? sb_.sr : sb_.sc);
 #pragma unroll
                 for (int r = 0; r < 3; r++) {
 #pragma unroll
                     for (int c = 0; c < 6; c++) {
                         const int rr = hrow + r;
                         const bool on = !same || (pass == 0 ? (rr <= c) : (c <= rr));
-                        if (on) plba_atomic_add(base + rr * sr + c * sc, -blk[r * 6 + c]);
+                        if (on) plba_atomic_add(base + (rr * sr + c * sc), -blk[r * 6 + c]);
                     }
                 }
             }
@@ -600,11 +603,11 @@ PLBA_D void assemble_chunk(const DevP &Pin, const Chunk &ch, int mode) {
                 for (int c = 0; c < 6; c++) plba_atomic_add(&P.hpp_diag_init[(size_t)6 * (slot0 + sa) + c], hd[c]);
             } else {
                 int idx = 0;
-                const SBlk sd_ = s_block(P, ch.win, sa, sa);
+                const SBlk sd_ = s_block(swin, sa, sa);
 #pragma unroll
                 for (int r = 0; r < 6; r++) {
 #pragma unroll
-                    for (int c = r; c < 6; c++) plba_atomic_add(sd_.p + r * sd_.sr + c * sd_.sc, Sd[idx++]);
+                    for (int c = r; c < 6; c++) plba_atomic_add(sd_.p + (r * (int)sd_.sr + c * (int)sd_.sc), Sd[idx++]);
                     plba_atomic_add(&P.gs[(size_t)6 * (slot0 + sa) + r], gv[r]);
                     if (PROF != PLBA_PROFILE_G) plba_atomic_add(&P.hpp_diag[(size_t)6 * (slot0 + sa) + r], hd[r]);
                 }

@@ -179,7 +179,7 @@ PLBA_HD void orth_update(const double *D, const double *dl, double *o) {
 PLBA_HD void huber(double delta, double e, double &rho0, double &rho1) {
     const double dsqr = delta * delta;
     if (e <= dsqr) { rho0 = e; rho1 = 1.0; }
-    else { const double sq = sqrt(e); rho0 = 2 * sq * delta - dsqr; rho1 = delta / sq; }
+    else { const double isq = plba_rsqrt_safe(e), sq = e * isq; rho0 = 2 * sq * delta - dsqr; rho1 = delta * isq; }      // one reciprocal square root (7 dependent operations) instead of sqrt + division
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -189,18 +189,21 @@ PLBA_HD void huber(double delta, double e, double &rho0, double &rho1) {
 PLBA_HD void g_point_error(const Cam &cam, const double *T, const double *Pw, const double *uv, double *e, double &zc) {
     double q[3]; rot(T, Pw, q);
     const double x = q[0] + T[3], y = q[1] + T[7], z = q[2] + T[11];
-    e[0] = uv[0] - (x / z * cam.fx + cam.cx);
-    e[1] = uv[1] - (y / z * cam.fy + cam.cy);
+    const double invz = plba_rcp_safe(z);
+    e[0] = uv[0] - (x * invz * cam.fx + cam.cx);
+    e[1] = uv[1] - (y * invz * cam.fy + cam.cy);
     zc = z;
 }
 // EdgePosePoint::linearizeOplus, g2o_types.h:271-296
 PLBA_HD void g_point_lin(const Cam &cam, const double *T, const double *Pw, const double *uv, double *e, double *A, double *B) {
     double q[3]; rot(T, Pw, q);                       // q = R Pw
     const double x = q[0] + T[3], y = q[1] + T[7], z = q[2] + T[11];
-    e[0] = uv[0] - (x / z * cam.fx + cam.cx);
-    e[1] = uv[1] - (y / z * cam.fy + cam.cy);
-    const double invz = 1.0 / z, invz2 = invz * invz;
-    const double a = cam.fx / z, b = -cam.fx * x * invz2, c = cam.fy / z, d = -cam.fy * y * invz2;
+    // ONE reciprocal (hardware seed + two Newton steps) replaces the five IEEE divisions of the reference's expressions: each of those is
+    // a ~15-instruction subroutine on the GPU, i.e. a quarter of this function; the results differ from the oracle's in the last bit
+    const double invz = plba_rcp_safe(z), invz2 = invz * invz;
+    e[0] = uv[0] - (x * invz * cam.fx + cam.cx);
+    e[1] = uv[1] - (y * invz * cam.fy + cam.cy);
+    const double a = cam.fx * invz, b = -cam.fx * x * invz2, c = cam.fy * invz, d = -cam.fy * y * invz2;
     // Jxi = -jpc R
     B[0] = -(a * T[0] + b * T[8]); B[1] = -(a * T[1] + b * T[9]); B[2] = -(a * T[2] + b * T[10]);
     B[3] = -(c * T[4] + d * T[8]); B[4] = -(c * T[5] + d * T[9]); B[5] = -(c * T[6] + d * T[10]);
@@ -218,23 +221,23 @@ PLBA_HD void g_line_project(const Cam &cam, const double *T, const double *n, co
 }
 PLBA_HD void g_line_error(const Cam &cam, const double *T, const double *n, const double *d, const double *ab, double *e) {
     double l[3], Rn[3], Rd[3]; g_line_project(cam, T, n, d, l, Rn, Rd);
-    const double fen = sqrt(l[0] * l[0] + l[1] * l[1]);
-    e[0] = (l[0] * ab[0] + l[1] * ab[1] + l[2]) / fen;
-    e[1] = (l[0] * ab[2] + l[1] * ab[3] + l[2]) / fen;
+    const double ifen = plba_rsqrt_safe(l[0] * l[0] + l[1] * l[1]);
+    e[0] = (l[0] * ab[0] + l[1] * ab[1] + l[2]) * ifen;
+    e[1] = (l[0] * ab[2] + l[1] * ab[3] + l[2]) * ifen;
 }
 // EdgePoseLine::linearizeOplus, g2o_types.h:389-453.  head/tail: the 3-vectors the pose Jacobian is built from
 // (Q12: the reference feeds orth.head(3)/orth.tail(3); intended maths feeds n / d).
 PLBA_HD void g_line_lin(const Cam &cam, const double *T, const LinePre &L, const double *head, const double *tail, const double *ab,
                         double *e, double *A, double *B) {
     double l[3], Rn[3], Rd[3]; g_line_project(cam, T, L.n, L.d, l, Rn, Rd);
-    const double fen = sqrt(l[0] * l[0] + l[1] * l[1]), fen2 = fen * fen;
-    e[0] = (l[0] * ab[0] + l[1] * ab[1] + l[2]) / fen;
-    e[1] = (l[0] * ab[2] + l[1] * ab[3] + l[2]) / fen;
+    const double ifen = plba_rsqrt_safe(l[0] * l[0] + l[1] * l[1]), ifen2 = ifen * ifen;      // 1 / fenmu and 1 / fenmu^2: one reciprocal square root for the sqrt and the seven divisions of :406-421
+    e[0] = (l[0] * ab[0] + l[1] * ab[1] + l[2]) * ifen;
+    e[1] = (l[0] * ab[2] + l[1] * ab[3] + l[2]) * ifen;
     const double t[3] = {T[3], T[7], T[11]};
     double Rh[3], Rt[3];
     rot(T, head, Rh); rot(T, tail, Rt);
     for (int k = 0; k < 2; k++) {
-        const double j0 = -l[0] * e[k] / fen2 + ab[2 * k] / fen, j1 = -l[1] * e[k] / fen2 + ab[2 * k + 1] / fen, j2 = 1.0 / fen;
+        const double j0 = -l[0] * e[k] * ifen2 + ab[2 * k] * ifen, j1 = -l[1] * e[k] * ifen2 + ab[2 * k + 1] * ifen, j2 = ifen;
         // g = j * K_L  (1x3, derivative w.r.t. n_c)
         const double g[3] = {j0 * cam.fy - j2 * cam.fy * cam.cx, j1 * cam.fx - j2 * cam.fx * cam.cy, j2 * cam.fx * cam.fy};
         // pose:  g^T(-hat(Rt)) = Rt x g ;  g^T(-hat(Rh) - hat(t) hat(Rt)) = Rh x g - (g x t) x Rt
@@ -349,7 +352,7 @@ PLBA_HD bool spd_inverse(double *M) {
         double s = M[j * D + j];
         for (int k = 0; k < j; k++) s -= Lm[j * D + k] * Lm[j * D + k];
         if (!(s > 0.0)) return false;
-        ri[j] = plba_rsqrt_hd(s);
+        ri[j] = plba_rsqrt_safe(s);
         Lm[j * D + j] = s * ri[j];
         for (int i = j + 1; i < D; i++) {
             double v = M[i * D + j];

@@ -111,6 +111,11 @@ PLBA_HD double plba_rcp_fast(double d) {
     return 1.0 / d;
 #endif
 }
+// the same for arguments that are not known to be normal and non-zero (depths, line norms): the IEEE routine takes over outside
+// [1e-290, 1e290] (never in practice; keeps zero / infinite / NaN inputs on the library's behaviour)
+PLBA_HD double plba_rcp_safe(double d) { const double a = fabs(d); return (a > 1e-290 && a < 1e290) ? plba_rcp_fast(d) : 1.0 / d; }
+PLBA_HD double plba_rsqrt_fast(double x);
+PLBA_HD double plba_rsqrt_safe(double x) { return (x > 1e-290 && x < 1e290) ? plba_rsqrt_fast(x) : 1.0 / sqrt(x); }
 PLBA_HD double plba_rsqrt_fast(double x) {
 #if defined(__CUDA_ARCH__)
     double y; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
@@ -185,6 +190,8 @@ inline int plba_atomic_fetch_add_i(int *p, int v) { int o = *p; *p += v; return 
 inline double plba_rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline double plba_rcp_fast(double d) { return 1.0 / d; }
 inline double plba_rsqrt_fast(double x) { return 1.0 / std::sqrt(x); }
+inline double plba_rcp_safe(double d) { return 1.0 / d; }
+inline double plba_rsqrt_safe(double x) { return 1.0 / std::sqrt(x); }
 inline void plba_graph_set(unsigned long long, unsigned int) {}
 // minimal CUDA runtime stand-ins
 typedef int cudaError_t; typedef void *cudaStream_t; typedef void *cudaEvent_t;

@@ -133,7 +133,7 @@ PLBA_HD bool obs_lin_w(const DevP &P, const WinCtrl &ctl, int o, int kf, const L
             double rho0 = chi2, rho1 = 1.0;
             if (ctl.stage == 0) huber(P.huber_delta, chi2, rho0, rho1);
             cost = rho0;
-            wsq = sqrt(rho1 * om);
+            { const double ww = rho1 * om; wsq = (ww > 1e-290 && ww < 1e290) ? ww * plba_rsqrt_fast(ww) : sqrt(ww); }      // sqrt(rho1 Omega)
         }
     } else {
         const bool pass0 = (ctl.iter == 0);
@@ -297,7 +297,7 @@ PLBA_D void wtask_accumulate(const double *rec, const WTask &t, int k, int first
 // stored the other way round), g, diag(H_pp).  Two observations of one landmark in the same keyframe (sa == sb off the track
 // diagonal: rare) put blk + blk^T onto the diagonal block.
 template <int PROF, int mode>
-PLBA_D void wtask_flush(const DevP &P, const WTask &t, int win, int slot0, const double *blk, const double *gv, const double *hd) {
+PLBA_D void wtask_flush(const DevP &P, const WTask &t, const SWin &swin, int slot0, const double *blk, const double *gv, const double *hd) {
     const int hcol = 3 * t.half;
     if (mode == 0) {
         if (t.diag) {
@@ -308,7 +308,7 @@ PLBA_D void wtask_flush(const DevP &P, const WTask &t, int win, int slot0, const
     }
     const bool tr = (t.sa > t.sb);
     const int ra = tr ? t.sb : t.sa, cb = tr ? t.sa : t.sb;
-    const SBlk sb_ = s_block(P, win, ra, cb);                      // dense upper storage, or the solver's node form (large banded windows)
+    const SBlk sb_ = s_block(swin, ra, cb);                        // dense upper storage, or the solver's node form (large banded windows)
     const long long sr = tr ? sb_.sc : sb_.sr, sc = tr ? sb_.sr : sb_.sc;
     double *p0 = sb_.p + hcol * sc;
     const bool upper_only = (t.sa == t.sb);                        // diagonal block of S: only its upper triangle is stored
@@ -393,6 +393,7 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
         const int nslice = keep ? 32 / ntask : 1;                 // few tasks: the landmarks of a pass are dealt over several lanes per task
         const int slot0 = P.win_slot0[it.win];
         const double *state = OA::state(P, ctl.cur);
+        const SWin swin = s_window(P, it.win);
         WPHASE_BEGIN
             LANE_BIND(kf_l); LANE_BIND(m_l);
             m_l = lane / k;
@@ -522,7 +523,7 @@ PLBA_D void assemble_items_w(const DevP &Pin, const WItem *items, int n_items, u
                     }
                     if (tk.on) {
                         wtask_accumulate<PROF, LT, mode>(rec, tk, k, tk.slice, nslice, nlp, blk, gv, hd);
-                        if (!keep || pass == npass - 1) wtask_flush<PROF, mode>(P, tk, it.win, slot0, blk, gv, hd);
+                        if (!keep || pass == npass - 1) wtask_flush<PROF, mode>(P, tk, swin, slot0, blk, gv, hd);
                     }
                 WPHASE_END
             }
