@@ -191,14 +191,19 @@ static int validate_problem(const plba_problem &p, const plba_options &o, std::s
         if (s >= 0) { if (s != last + 1) { err = "kf_slot must ascend 0..n_free-1"; return PLBA_E_ARG; } last = s; nfree++; }
     }
     if (nfree != p.n_free) { err = "n_free does not match kf_slot"; return PLBA_E_ARG; }
+    int bad_p = 0, bad_l = 0;      // 1 = index out of range, 2 = not landmark-major
+#pragma omp parallel for schedule(static) reduction(max : bad_p) if (p.n_pobs > 1000000)
     for (int i = 0; i < p.n_pobs; i++) {
-        if (p.po_lm[i] < 0 || p.po_lm[i] >= p.n_pt || p.po_kf[i] < 0 || p.po_kf[i] >= p.n_kf) { err = "point observation index out of range"; return PLBA_E_ARG; }
-        if (i && p.po_lm[i] < p.po_lm[i - 1]) { err = "point observations not landmark-major"; return PLBA_E_ARG; }
+        if (p.po_lm[i] < 0 || p.po_lm[i] >= p.n_pt || p.po_kf[i] < 0 || p.po_kf[i] >= p.n_kf) bad_p = bad_p > 1 ? bad_p : 1;
+        else if (i && p.po_lm[i] < p.po_lm[i - 1]) bad_p = 2;
     }
+#pragma omp parallel for schedule(static) reduction(max : bad_l) if (p.n_lobs > 1000000)
     for (int i = 0; i < p.n_lobs; i++) {
-        if (p.lo_lm[i] < 0 || p.lo_lm[i] >= p.n_ls || p.lo_kf[i] < 0 || p.lo_kf[i] >= p.n_kf) { err = "line observation index out of range"; return PLBA_E_ARG; }
-        if (i && p.lo_lm[i] < p.lo_lm[i - 1]) { err = "line observations not landmark-major"; return PLBA_E_ARG; }
+        if (p.lo_lm[i] < 0 || p.lo_lm[i] >= p.n_ls || p.lo_kf[i] < 0 || p.lo_kf[i] >= p.n_kf) bad_l = bad_l > 1 ? bad_l : 1;
+        else if (i && p.lo_lm[i] < p.lo_lm[i - 1]) bad_l = 2;
     }
+    if (bad_p) { err = bad_p == 1 ? "point observation index out of range" : "point observations not landmark-major"; return PLBA_E_ARG; }
+    if (bad_l) { err = bad_l == 1 ? "line observation index out of range" : "line observations not landmark-major"; return PLBA_E_ARG; }
     return PLBA_OK;
 }
 
@@ -209,21 +214,30 @@ struct ClassLayout {
     std::vector<int> group;      // signature group of each OLD landmark (equal group <=> identical keyframe sequence); empty = not grouped
 };
 static void signature_order(int n_lm, int n_obs, const int32_t *lm, const int32_t *kf, bool permute, ClassLayout &L) {
-    L.optr.assign(n_lm + 1, 0);
-    for (int i = 0; i < n_obs; i++) L.optr[lm[i] + 1]++;
-    for (int l = 0; l < n_lm; l++) L.optr[l + 1] += L.optr[l];
+    const bool par = n_obs > 1000000;      // one large window: the loops below run in parallel (a region costs more than a small window's whole sort)
+    L.optr.assign(n_lm + 1, n_obs);
+    // lm[] is non-decreasing (validated): optr[l] = first observation whose landmark is >= l
+#pragma omp parallel for schedule(static) if (par)
+    for (int i = 0; i < n_obs; i++) {
+        const int lo = i ? lm[i - 1] + 1 : 0;
+        for (int l = lo; l <= lm[i]; l++) L.optr[l] = i;
+    }
     L.perm.resize(n_lm);
+#pragma omp parallel for schedule(static) if (par)
     for (int l = 0; l < n_lm; l++) L.perm[l] = l;
     if (!permute || n_lm < 2) return;
     {   // fast path: every track is a contiguous keyframe run (the usual sliding-window case) => the signature IS (first KF, length):
         // one pass over the observations and a counting sort, no hashing
-        int maxlen = 0, maxkf = 0; bool contiguous = true;
-        for (int l = 0; l < n_lm && contiguous; l++) {
+        int maxlen = 0, maxkf = 0, broken = 0;
+#pragma omp parallel for schedule(static) reduction(max : maxlen, maxkf, broken) if (par)
+        for (int l = 0; l < n_lm; l++) {
+            if (broken > 0) continue;      // (a max-reduction's private copy starts at INT_MIN, not at 0)
             const int a = L.optr[l], b = L.optr[l + 1];
             if (b - a > maxlen) maxlen = b - a;
             if (b > a && kf[a] > maxkf) maxkf = kf[a];
-            for (int i = a + 1; i < b; i++) if (kf[i] != kf[i - 1] + 1) { contiguous = false; break; }
+            for (int i = a + 1; i < b; i++) if (kf[i] != kf[i - 1] + 1) { broken = 1; break; }
         }
+        const bool contiguous = broken <= 0;
         if (contiguous && (int64_t)(maxkf + 2) * (maxlen + 1) <= 4 * (int64_t)n_lm + 4096) {
             const int W = maxlen + 1, nkeys = (maxkf + 2) * W;
             std::vector<int> cnt(nkeys + 1, 0);
@@ -809,11 +823,13 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     pt_ptr.assign(tot.n_pt + 1, 0); ls_ptr.assign(tot.n_ls + 1, 0);
     bool too_long = false;
     std::vector<ClassLayout> Lps(n), Lls(n);
-#pragma omp parallel for schedule(dynamic, 4) if (n > 8)
-    for (int w = 0; w < n; w++) {
+    // batches: parallel over windows; one LARGE window: parallel inside signature_order
+#pragma omp parallel for schedule(dynamic, 1) if (n > 8)
+    for (int wc = 0; wc < 2 * n; wc++) {
+        const int w = wc >> 1;
         const plba_problem &p = probs[w];
-        signature_order(p.n_pt, p.n_pobs, p.po_lm, p.po_kf, true, Lps[w]);
-        signature_order(p.n_ls, p.n_lobs, p.lo_lm, p.lo_kf, prof != PLBA_PROFILE_H_END, Lls[w]);   // Q3 addresses endpoint lines by position
+        if (wc & 1) signature_order(p.n_ls, p.n_lobs, p.lo_lm, p.lo_kf, prof != PLBA_PROFILE_H_END, Lls[w]);   // Q3 addresses endpoint lines by position
+        else signature_order(p.n_pt, p.n_pobs, p.po_lm, p.po_kf, true, Lps[w]);
     }
     HOSTPROF("sigorder");
     // route: the warp-autonomous kernels take windows whose longest track fits a warp; anything longer (or force_chunk) runs on the
@@ -840,11 +856,21 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
             const int32_t *kf = cls ? p.lo_kf : p.po_kf;
             std::vector<int> &perm = cls ? h->ls_perm : h->pt_perm, &operm = cls ? h->lo_perm : h->po_perm, &ptr = cls ? ls_ptr : pt_ptr;
             std::vector<Seg> &sgs = cls ? sg_ls : sg_pt; std::vector<int> &fps = cls ? fp_ls : fp_pt;
-            int ob = ob0, run_first_old = -1;
+            // (1) observation offsets of the re-ordered landmarks (serial prefix), (2) the observation permutation (parallel for large
+            // windows: 12.5 M entries at config 5), (3) the runs (serial, index compares only)
+            int ob = ob0;
+            for (int nl_i = 0; nl_i < nl; nl_i++) { const int old = L.perm[nl_i]; ptr[lm0 + nl_i] = ob; ob += L.optr[old + 1] - L.optr[old]; }
+#pragma omp parallel for schedule(static) if (nl > 200000)
+            for (int nl_i = 0; nl_i < nl; nl_i++) {
+                const int old = L.perm[nl_i], a = L.optr[old], b = L.optr[old + 1];
+                perm[lm0 + nl_i] = lm0 + old;
+                int o = ptr[lm0 + nl_i];
+                for (int i = a; i < b; i++) operm[o++] = ob0 + i;
+            }
+            int run_first_old = -1;
             for (int nl_i = 0; nl_i < nl; nl_i++) {
                 const int old = L.perm[nl_i], a = L.optr[old], b = L.optr[old + 1], no = b - a;
                 const int g = lm0 + nl_i;
-                perm[g] = lm0 + old;
                 bool join = false;
                 if (run_first_old >= 0) {
                     Seg &s = sgs.back();
@@ -860,8 +886,6 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
                     for (int i = 0; i < no; i++) if (p.kf_slot[kf[a + i]] >= 0) { fps.push_back(i); s.nfree++; }
                     sgs.push_back(s); run_first_old = old;
                 }
-                ptr[g] = ob;
-                for (int i = a; i < b; i++) operm[ob++] = ob0 + i;
             }
             ptr[lm0 + nl] = ob;
         }
