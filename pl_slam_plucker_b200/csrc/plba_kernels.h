@@ -313,9 +313,16 @@ PLBA_HD double obs_linearize(const DevP &P, const WinCtrl &ctl, int o, int t, in
         e[0] = -r;                 // g += J r w  ==  b = -J^T (w e) with e = -r
         cost = w * r * r;
     }
-    for (int i = 0; i < K::RANK * 6; i++) sm.A[i * OC + t] = active ? wsq * A[i] : 0.0;
-    for (int i = 0; i < K::RANK * K::D; i++) sm.B[i * OC + t] = active ? wsq * B[i] : 0.0;
-    for (int i = 0; i < K::RANK; i++) sm.E[i * OC + t] = active ? wsq * e[i] : 0.0;
+    // (an edge gated out of the active set leaves zero rows: one branch instead of a select per entry)
+    if (active) {
+        for (int i = 0; i < K::RANK * 6; i++) sm.A[i * OC + t] = wsq * A[i];
+        for (int i = 0; i < K::RANK * K::D; i++) sm.B[i * OC + t] = wsq * B[i];
+        for (int i = 0; i < K::RANK; i++) sm.E[i * OC + t] = wsq * e[i];
+    } else {
+        for (int i = 0; i < K::RANK * 6; i++) sm.A[i * OC + t] = 0.0;
+        for (int i = 0; i < K::RANK * K::D; i++) sm.B[i * OC + t] = 0.0;
+        for (int i = 0; i < K::RANK; i++) sm.E[i * OC + t] = 0.0;
+    }
     sm.slot[t] = slot;                   // structural: >= 0 free KF, -1 fixed observer
     sm.act[t] = active ? 1 : 0;
     return cost;

@@ -157,9 +157,16 @@ PLBA_HD bool obs_lin_w(const DevP &P, const WinCtrl &ctl, int o, int kf, const L
         e[0] = -r;                 // g += J r w  ==  b = -J^T (w e) with e = -r
         cost = w * r * r;
     }
-    for (int i = 0; i < K::RANK * 6; i++) A[i] = active ? wsq * A[i] : 0.0;
-    for (int i = 0; i < K::RANK * K::D; i++) B[i] = active ? wsq * B[i] : 0.0;
-    for (int i = 0; i < K::RANK; i++) e[i] = active ? wsq * e[i] : 0.0;
+    // (an edge gated out of the active set leaves zero rows: one branch instead of a select per entry — 40 selects per observation)
+    if (active) {
+        for (int i = 0; i < K::RANK * 6; i++) A[i] *= wsq;
+        for (int i = 0; i < K::RANK * K::D; i++) B[i] *= wsq;
+        for (int i = 0; i < K::RANK; i++) e[i] *= wsq;
+    } else {
+        for (int i = 0; i < K::RANK * 6; i++) A[i] = 0.0;
+        for (int i = 0; i < K::RANK * K::D; i++) B[i] = 0.0;
+        for (int i = 0; i < K::RANK; i++) e[i] = 0.0;
+    }
     return active;
 }
 
