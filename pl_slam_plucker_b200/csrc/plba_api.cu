@@ -1398,12 +1398,15 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
         if (r.trace) for (int i = 0; i < std::min(r.n_trace, std::min(r.trace_cap, P.trace_cap)); i++) r.trace[i] = trace[(size_t)w * P.trace_cap + i];
         if (r.kf_T_wc) for (int i = 0; i < 12 * wi.n_kf; i++) r.kf_T_wc[i] = T[(size_t)12 * wi.kf0 + i];
         if (r.x_pose) for (int i = 0; i < 6 * wi.n_free; i++) r.x_pose[i] = X[(size_t)6 * wi.slot0 + i];
+        const bool par_lm = (n <= 8);       // one (or few) big windows: parallel over landmarks / observations; batches: parallel over windows
+#pragma omp parallel for schedule(static) if (par_lm && wi.n_pt > 200000)
         for (int g = wi.pt0; g < wi.pt0 + wi.n_pt; g++) {
             const int old = h->pt_perm[g] - wi.pt0;
             if (r.pt_xyz) for (int i = 0; i < 3; i++) r.pt_xyz[(size_t)3 * old + i] = pt[(size_t)3 * g + i];
             // inlier rule of the hand-LM write-back (src/mapHandler.cpp:2858-2860, 2871-2873); profile G leaves it to the final chi2 test
             if (r.pt_inlier) { double d2 = 0; for (int i = 0; i < 3; i++) { const double d = pt[(size_t)3 * g + i] - pt0[(size_t)3 * g + i]; d2 += d * d; } r.pt_inlier[old] = (!G && !P.gba && std::sqrt(d2) > 0.01) ? 0 : 1; }
         }
+#pragma omp parallel for schedule(static) if (par_lm && wi.n_ls > 200000)
         for (int g = wi.ls0; g < wi.ls0 + wi.n_ls; g++) {
             const int old = h->ls_perm[g] - wi.ls0;
             if (ld == 4) {
@@ -1420,11 +1423,13 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
             }
         }
         if (G) {
+#pragma omp parallel for schedule(static) if (par_lm && wi.n_pobs > 1000000)
             for (int o = wi.po0; o < wi.po0 + wi.n_pobs; o++) {
                 const int i = h->po_perm[o] - wi.po0;
                 if (r.po_chi2) r.po_chi2[i] = pchi[o];
                 if (r.po_flags) r.po_flags[i] = pf[o];
             }
+#pragma omp parallel for schedule(static) if (par_lm && wi.n_lobs > 1000000)
             for (int o = wi.lo0; o < wi.lo0 + wi.n_lobs; o++) {
                 const int i = h->lo_perm[o] - wi.lo0;
                 if (r.lo_chi2) r.lo_chi2[i] = lchi[o];
@@ -1522,7 +1527,7 @@ int plba_copy_reduced_system(plba_handle h, int32_t window, double *S_out, doubl
         for (int i = 0; i < B.N; i++) {
             const int oi = i * m, mi = bcr_node_size(B, wi.n_free, i);
             const double *D = nodes.data() + (size_t)i * m * m, *U = nodes.data() + nn + (size_t)i * m * m;
-            for (int r = 0; r < mi; r++) for (int c = 0; c <= r; c++) S_out[(size_t)(oi + c) * n + oi + r] = D[(size_t)r * m + c];      // lower of the node = upper of S
+            for (int r = 0; r < mi; r++) for (int c = r; c < mi; c++) S_out[(size_t)(oi + r) * n + oi + c] = D[(size_t)r * m + c];      // the node's upper triangle
             if (i > 0) for (int r = 0; r < m; r++) for (int c = 0; c < mi; c++) S_out[(size_t)(oi - m + r) * n + oi + c] = U[(size_t)r * m + c];
         }
     }

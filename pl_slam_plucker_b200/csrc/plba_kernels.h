@@ -161,7 +161,7 @@ template <int PROF> struct SmemMax {
 // its entry (0, 0) and the strides of its rows and columns.
 //   dense windows (one-CTA solver, dense DMMA Cholesky): row-major (6 nf)^2, upper block triangle;
 //   block-banded large windows (block cyclic reduction): the assembly kernels accumulate straight into the solver's NODE form —
-//     nodes of bs keyframes (m = 6 bs unknowns), D_i = lower triangle of the node's diagonal block (row stride m), U_j = the block between
+//     nodes of bs keyframes (m = 6 bs unknowns), D_i = upper triangle of the node's diagonal block (row stride m), U_j = the block between
 //     node j - 1 (rows) and node j (columns).  No dense S exists for such a window (config 5: 35 MB instead of 1.15 GB) and no gather
 //     kernel runs before the solve (round 1: 0.35 ms of a 1.77 ms solve).  The half bandwidth is <= bs, so cb / bs - ra / bs <= 1.
 struct SBlk { double *p; long long sr, sc; };
@@ -173,7 +173,7 @@ PLBA_HD SBlk s_block(const SWin &w, int ra, int cb) {
     SBlk b;
     if (w.bs == 0) { b.p = w.Sw + (size_t)(6 * ra) * w.ld + 6 * cb; b.sr = w.ld; b.sc = 1; return b; }
     const int bs = w.bs, m = 6 * bs, i = ra / bs, j = cb / bs, a = ra - i * bs, c = cb - j * bs;
-    if (i == j) { b.p = w.Sw + (size_t)i * m * m + (size_t)(6 * c) * m + 6 * a; b.sr = 1; b.sc = m; }       // D_i[(6c + col) m + 6a + row]: lower triangle
+    if (i == j) { b.p = w.Sw + (size_t)i * m * m + (size_t)(6 * a) * m + 6 * c; b.sr = m; b.sc = 1; }       // D_i[(6a + row) m + 6c + col]: UPPER triangle, the same strides as the dense storage (the two column halves of a block share cache lines: half the RED wavefronts of a transposed layout)
     else { b.p = w.Sw + (size_t)w.N * m * m + (size_t)j * m * m + (size_t)(6 * a) * m + 6 * c; b.sr = m; b.sc = 1; }   // U_j[(6a + row) m + 6c + col]
     return b;
 }

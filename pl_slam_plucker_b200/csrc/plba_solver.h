@@ -926,7 +926,7 @@ PLBA_KERNEL void k_solve_banded(const DevP *Pp, int bwb) {
 // This is a Cholesky factorisation in a nested-dissection order of the keyframe chain: same system, same solution up to rounding,
 // but the 6 Nkf sequential pivots of the banded factorisation become 90 ceil(log2 N) and every level fills the GPU.
 struct BcrW { double *D, *U, *b, *hd, *Xl, *Xr, *y, *Lf; int N, bs, m, pad; };   // Lf: factors of the split elimination (k_bcr_factor: the two CTAs of a node both read D_i, so L cannot overwrite it)   // node storage: D, U, Xl, Xr: [N][m*m] (row stride m); b, hd, y: [N][m];
-                                                                           // D, U: the window's slice of P.S (the assembly kernels accumulate into the node form directly, s_block()); b = the window's slice of g, hd of diag(H_pp)
+                                                                           // D (upper triangles), U: the window's slice of P.S (the assembly kernels accumulate into the node form directly, s_block()); b = the window's slice of g, hd of diag(H_pp)
 enum { BCR_BS_MAX = 15, BCR_M_MAX = 6 * BCR_BS_MAX, BCR_NT = 512 };
 static inline size_t bcr_elim_smem() { return sizeof(double) * ((size_t)(3 * BCR_M_MAX + 1) * (BCR_M_MAX + 1) + BCR_M_MAX + 21 * BCR_BS_MAX + 6 * 264 + 8) + 64; }
 static inline size_t bcr_back_smem() { return sizeof(double) * ((size_t)BCR_M_MAX * (BCR_M_MAX + 1) + 11 * BCR_M_MAX + 8) + 64; }
@@ -952,7 +952,7 @@ PLBA_KERNEL void k_bcr_elim(const DevP *Pp, int w, BcrW B, int s, int final) {
         for (int idx = tid; idx < mi * mi; idx += PLBA_NT) {
             const int r = idx / mi, c = idx - r * mi;
             if (c > r) continue;
-            double v = Di[(size_t)r * m + c];
+            double v = Di[(size_t)c * m + r];                          // D is stored as an upper triangle (s_block): entry (r, c), c <= r, sits at (c, r)
             if (c == r) v += (P.profile == PLBA_PROFILE_G) ? ctl.lambda : ctl.lambda * B.hd[(size_t)i * m + r];      // g2o: additive; hand LM: H_ii (1 + lambda)
             M[(size_t)r * ldm + c] = v;
         }
@@ -1009,7 +1009,7 @@ PLBA_KERNEL void k_bcr_elim(const DevP *Pp, int w, BcrW B, int s, int final) {
                     for (int v = 0; v < 3; v++) {
                         const int r = ra0 + u, c = rb0 + v;
                         if (r >= ma || c >= mb) continue;
-                        if (job < 2) { if (c <= r) plba_atomic_add(dst + (size_t)r * m + c, -acc[u * 3 + v]); }
+                        if (job < 2) { if (c <= r) plba_atomic_add(dst + (size_t)c * m + r, -acc[u * 3 + v]); }
                         else dst[(size_t)r * m + c] = -acc[u * 3 + v];
                     }
                 }
@@ -1168,11 +1168,12 @@ PLBA_KERNEL void PLBA_BOUNDS(BF_NT, 1) k_bcr_factor(const DevP *Pp, int w, BcrW 
             if (u < nx * nb) { act = 2; bj = u / nx; bi = nb + (u - bj * nx); }
         }
         if (act == 1) {
+            // lower block (bi, bj) = transpose of the stored upper block (bj, bi)
 #pragma unroll
-            for (int r = 0; r < 6; r++) {
-                const plba_d2 *row = (const plba_d2 *)(Di + (size_t)(6 * bi + r) * m + 6 * bj);
+            for (int c = 0; c < 6; c++) {
+                const plba_d2 *col = (const plba_d2 *)(Di + (size_t)(6 * bj + c) * m + 6 * bi);
 #pragma unroll
-                for (int c2 = 0; c2 < 3; c2++) { const plba_d2 v = row[c2]; blk[r * 6 + 2 * c2] = v.x; blk[r * 6 + 2 * c2 + 1] = v.y; }
+                for (int r2 = 0; r2 < 3; r2++) { const plba_d2 v = col[r2]; blk[(2 * r2) * 6 + c] = v.x; blk[(2 * r2 + 1) * 6 + c] = v.y; }
             }
             if (bi == bj) {
 #pragma unroll
@@ -1385,7 +1386,7 @@ PLBA_KERNEL void PLBA_BOUNDS(BS_NT, 1) k_bcr_schur(const DevP *Pp, int w, BcrW B
 #pragma unroll
                 for (int r = 0; r < 6; r++) {
 #pragma unroll
-                    for (int cc = 0; cc < 6; cc++) if (p != q || cc <= r) plba_atomic_add(Dn + (size_t)(6 * p + r) * m + 6 * q + cc, -acc[r * 6 + cc]);
+                    for (int cc = 0; cc < 6; cc++) if (p != q || cc <= r) plba_atomic_add(Dn + (size_t)(6 * q + cc) * m + 6 * p + r, -acc[r * 6 + cc]);      // (upper storage: entry (row, col) of the lower triangle sits at (col, row))
                 }
             } else if (tid >= 128 && tid - 128 < rows_a) {
                 // right-hand side of the neighbour: b_n -= X y
