@@ -107,6 +107,7 @@ struct plba_handle_s {
     int force_chunk = 0;             // 0 = route by size, 1 = always the CTA-chunk kernels, 2 = the warp kernels whenever every track fits a warp
     bool warp_path = true;           // this upload runs on the warp-autonomous kernels (plba_warp.h)
     std::vector<WItem> wi_pt, wi_ls;
+    std::vector<long long> win_S_off; // offset of each window's reduced camera system inside P.S (host copy of DevP::win_S_off)
     std::vector<BcrW> bcr;           // large banded windows: node storage of the block cyclic reduction (per window)
     int large_solver = 0;            // 0 = block cyclic reduction (default), 1 = single-CTA banded Cholesky (A/B, tests)
     int grid_warp = 592, grid_warp_upd = 592;
@@ -124,6 +125,8 @@ struct plba_handle_s {
     int *h_poll = nullptr; cudaEvent_t ev_poll[4]{};    // pinned copies of the device counters, one per in-flight round of the pipelined loop
     plba_timing timing{};
     cudaEvent_t ev[8]{};
+    cudaStream_t stream_panel = nullptr; cudaEvent_t ev_la[2]{};   // dense tiled Cholesky: the look-ahead panel runs on a stream of its own
+    bool no_lookahead = false;                                     // PLBA_NO_LOOKAHEAD=1 (A/B runs)
     cudaEvent_t ev_h2d = nullptr; bool h2d_pending = false;   // recorded after the H2D copies of an upload: the next upload waits for it before it rewrites the pinned staging
     bool detail_timing = false, no_graph = false;
     int grid_chunks = 296, grid_solve = 148;
@@ -366,6 +369,15 @@ int plba_create(int32_t device, void *stream, plba_handle *out) {
     h->h_poll = (int *)q;
     for (int i = 0; i < 4; i++) cudaEventCreate(&h->ev_poll[i]);
     for (int i = 0; i < 8; i++) cudaEventCreate(&h->ev[i]);
+#ifndef PLBA_HOST_EMU
+    {   // the look-ahead panel stream of the dense tiled Cholesky: created lazily would do, but a stream and two events cost nothing
+        int lo_p = 0, hi_p = 0; cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+        if (cudaStreamCreateWithPriority(&h->stream_panel, cudaStreamNonBlocking, hi_p) != cudaSuccess) { h->stream_panel = nullptr; cudaGetLastError(); }
+        for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&h->ev_la[i], cudaEventDisableTiming);
+        const char *nl = std::getenv("PLBA_NO_LOOKAHEAD");
+        h->no_lookahead = nl && nl[0] == '1';
+    }
+#endif
     *out = h;
     return PLBA_OK;
 }
@@ -388,6 +400,10 @@ void plba_destroy(plba_handle h) {
     if (h->h_poll) cudaFreeHost(h->h_poll);
 #ifndef PLBA_HOST_EMU
     if (h->nccl_comm) { nccl_api().CommDestroy((plba_ncclComm_t)h->nccl_comm); h->nccl_comm = nullptr; }
+#endif
+#ifndef PLBA_HOST_EMU
+    if (h->stream_panel) { cudaStreamSynchronize(h->stream_panel); cudaStreamDestroy(h->stream_panel); }
+    for (int i = 0; i < 2; i++) if (h->ev_la[i]) cudaEventDestroy(h->ev_la[i]);
 #endif
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -646,27 +662,50 @@ static void launch_solve(plba_handle h) {
         PLBA_LAUNCH(k_pose_update, grid1(P.n_free, 128), dim3(128), 0, h->stream, Pp); h->timing.n_launches += 2;
         return;
     }
+    // Dense tiled Cholesky with ONE STEP OF LOOK-AHEAD: the trailing update of step k is launched as (a) the tile row that holds the rows of
+    // panel k + 1 and (b) the rest; panel k + 1 (diagonal block, block row, right-hand side) starts on a second, high-priority stream as soon
+    // as (a) is done and runs under (b) — the panel chain (one CTA, then one wave of small CTAs) no longer idles the machine 125 times.
+    // (b) writes rows >= lo + 128 only, the panel reads / writes rows lo .. lo + 95: disjoint; both read the finished rows of panel k.
     for (int w = 0; w < P.n_win; w++) {
         const int n = 6 * h->wins[w].n_free;
         if (n == 0 || h->wins[w].n_pobs + h->wins[w].n_lobs == 0) continue;
-        PLBA_LAUNCH(k_rhs_init, grid1(n, 256), dim3(256), 0, h->stream, Pp, w); h->timing.n_launches++;
+        cudaStream_t sm = h->stream, sp = h->stream;
+#ifndef PLBA_HOST_EMU
+        if (h->stream_panel && !h->no_lookahead) sp = h->stream_panel;
+#endif
+        const bool la = (sp != sm);
+        double *Sw = P.S + h->win_S_off[w], *xw = P.xp + (size_t)6 * h->wins[w].slot0;      // y (forward substitution) and then x live in xp
+        auto launch_panel = [&](cudaStream_t st, int k0) {
+            const int nb = std::min((int)NBK, n - k0), lo = k0 + nb;
+            PLBA_LAUNCH(k_potrf_block, dim3(1), dim3(256), potrf_block_smem(), st, Pp, w, k0, nb);
+            // columns right of the block + the right-hand side column
+            PLBA_LAUNCH(k_trsm_block, dim3((n - lo + 1 + TRSM_COLS - 1) / TRSM_COLS), dim3(TRSM_COLS), trsm_block_smem(), st, Pp, Sw, n, xw, k0, nb);
+            h->timing.n_launches += 2;
+            if (lo < n) { PLBA_LAUNCH(k_rhs_update, dim3((n - lo + 255) / 256, (nb + RHS_ROWS - 1) / RHS_ROWS), dim3(256), 0, st, Pp, w, k0, nb); h->timing.n_launches++; }
+        };
+        PLBA_LAUNCH(k_rhs_init, grid1(n, 256), dim3(256), 0, sm, Pp, w); h->timing.n_launches++;
+        launch_panel(sm, 0);
         for (int k0 = 0; k0 < n; k0 += NBK) {
             const int nb = std::min((int)NBK, n - k0), lo = k0 + nb;
-            PLBA_LAUNCH(k_potrf_block, dim3(1), dim3(256), potrf_block_smem(), h->stream, Pp, w, k0, nb);
-            // columns right of the block + the right-hand side column
-            PLBA_LAUNCH(k_trsm_block, dim3((n - lo + 1 + TRSM_COLS - 1) / TRSM_COLS), dim3(256), trsm_block_smem(), h->stream, Pp, w, k0, nb);
-            h->timing.n_launches += 2;
-            if (lo < n) {
-                PLBA_LAUNCH(k_rhs_update, grid1(n - lo, 256), dim3(256), 0, h->stream, Pp, w, k0, nb);
-                const int T = (n - lo + ST - 1) / ST;
-                PLBA_LAUNCH(k_syrk_dmma, dim3(T * (T + 1) / 2), dim3(256), syrk_dmma_smem(), h->stream, Pp, w, k0, nb, lo);
-                h->timing.n_launches += 2;
-            }
+            if (lo >= n) break;
+            const int TM = (n - lo + STM - 1) / STM;
+            const int ga = syrk_tiles(n - lo, 0, 1), gb = syrk_tiles(n - lo, 1, TM);
+            PLBA_LAUNCH(k_syrk_dmma, dim3(ga), dim3(256), syrk_dmma_smem(), sm, Pp, Sw, n, k0, nb, lo, 0); h->timing.n_launches++;
+#ifndef PLBA_HOST_EMU
+            if (la) { cudaEventRecord(h->ev_la[0], sm); cudaStreamWaitEvent(sp, h->ev_la[0], 0); }
+#endif
+            if (gb > 0) { PLBA_LAUNCH(k_syrk_dmma, dim3(gb), dim3(256), syrk_dmma_smem(), sm, Pp, Sw, n, k0, nb, lo, 1); h->timing.n_launches++; }
+            launch_panel(sp, lo);
+#ifndef PLBA_HOST_EMU
+            if (la) { cudaEventRecord(h->ev_la[1], sp); cudaStreamWaitEvent(sm, h->ev_la[1], 0); }
+#endif
         }
+        // backward substitution, column-oriented: solve block k (one CTA, the 96 x 96 triangle), then take it out of every row above
         for (int k0 = ((n - 1) / NBK) * NBK; k0 >= 0; k0 -= NBK) {
             const int nb = std::min((int)NBK, n - k0);
-            PLBA_LAUNCH(k_back_block, dim3(1), dim3(512), back_block_smem(), h->stream, Pp, w, k0, nb);
+            PLBA_LAUNCH(k_back_block, dim3(1), dim3(256), back_block_smem(), sm, Pp, (const double *)Sw, n, xw, (const WinCtrl *)(P.ctrl + w), k0, nb);
             h->timing.n_launches++;
+            if (k0 > 0) { PLBA_LAUNCH(k_back_update, dim3((k0 + BU_ROWS - 1) / BU_ROWS), dim3(2 * BU_ROWS), 0, sm, Pp, (const double *)Sw, n, xw, k0, nb); h->timing.n_launches++; }
         }
     }
     PLBA_LAUNCH(k_pose_update, grid1(P.n_free, 128), dim3(128), 0, h->stream, Pp); h->timing.n_launches++;
@@ -1037,7 +1076,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     h->bcr_layout = !h->small_path && h->band_blocks <= BAND_MAX && !h->force_dense && h->large_solver == 0;
     const int bcr_bs = std::min((int)BCR_BS_MAX, std::max(h->band_blocks, 6)), bcr_m = 6 * bcr_bs;
     long long S_off = 0;
-    std::vector<long long> win_S_off(n);
+    std::vector<long long> &win_S_off = h->win_S_off; win_S_off.assign(n, 0);
     for (int w = 0; w < n; w++) {
         win_S_off[w] = S_off;
         const long long nf_w = h->wins[w].n_free, N_w = (nf_w + bcr_bs - 1) / bcr_bs;

@@ -28,6 +28,7 @@ struct alignas(16) plba_d2 { double x, y; };
 #define PLBA_COLD __host__ __device__ __noinline__
 #define PLBA_BOUNDS(t, b) __launch_bounds__(t, b)
 #define PLBA_SMEM(ptr) extern __shared__ __align__(16) unsigned char plba_smem_raw[]; unsigned char *ptr = plba_smem_raw
+#define PLBA_SHARED __shared__
 #define PHASE_BEGIN { const int tid = (int)threadIdx.x; (void)tid;
 #define PHASE_END } __syncthreads();
 #define PLBA_NT ((int)blockDim.x)
@@ -142,6 +143,7 @@ typedef plba_dim3 dim3;
 struct PlbaEmuCtx { int nt = 1, bid = 0, bidy = 0, nb = 1; unsigned char *smem = nullptr; };
 inline PlbaEmuCtx &plba_emu() { static thread_local PlbaEmuCtx c; return c; }
 #define PLBA_SMEM(ptr) unsigned char *ptr = plba_emu().smem
+#define PLBA_SHARED static
 #define PHASE_BEGIN for (int tid = 0; tid < plba_emu().nt; ++tid) {
 #define PHASE_END }
 #define PLBA_NT (plba_emu().nt)

@@ -428,7 +428,23 @@ PLBA_KERNEL void PLBA_BOUNDS(SS_NT, 1) k_solve_small(const DevP *Pp) {
 //                   (mma.sync.m8n8k4.f64: the only dense contraction of the path — north star: "FP64 DMMA only for the dense
 //                   reduced-camera-system Cholesky"); K = 96 streamed through shared memory in cp.async double-buffered chunks of 32
 //   k_back_block  : backward substitution U x = y, one block row at a time
-enum { NBK = 96, ST = 128 /* SYRK tile */, SKC = 32 /* K chunk */, SLD = ST + 4 /* row stride: fragment loads conflict-free */ };
+enum { NBK = 96 };
+
+#ifndef PLBA_HOST_EMU
+// Ampere-style asynchronous copies global -> shared (fire and forget: a thread can have dozens in flight without holding registers)
+PLBA_D void plba_cp_async16(void *smem_dst, const void *gsrc, bool valid) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 16 : 0;                    // src-size 0: the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
+}
+PLBA_D void plba_cp_async8(void *smem_dst, const void *gsrc, bool valid) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
+}
+PLBA_D void plba_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> PLBA_D void plba_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
 
 static inline size_t potrf_block_smem() { return sizeof(double) * ((size_t)NBK * (NBK + 1) + NBK + 21 * (NBK / 6) + 6 * 264 + 16); }
 PLBA_KERNEL void k_potrf_block(const DevP *Pp, int w, int k0, int nb) {
@@ -441,13 +457,22 @@ PLBA_KERNEL void k_potrf_block(const DevP *Pp, int w, int k0, int nb) {
     int *fail = (int *)(part + 6 * 264);
     PHASE_BEGIN
         if (tid == 0) *fail = 0;
+        // the block travels as asynchronous 8-byte copies straight into its (transposed) place: all 36 of a thread are in flight at once
+#ifndef PLBA_HOST_EMU
         for (int idx = tid; idx < nb * nb; idx += PLBA_NT) {
             const int r = idx / nb, c = idx - r * nb;
-            if (c < r) continue;
-            double v = Sw[(size_t)(k0 + r) * n + k0 + c];
-            if (r == c) v += (P.profile == PLBA_PROFILE_G) ? ctl.lambda : ctl.lambda * P.hpp_diag[(size_t)6 * slot0 + k0 + r];
-            M[(size_t)c * ldm + r] = v;                 // lower (c,r)
+            if (c >= r) plba_cp_async8(&M[(size_t)c * ldm + r], &Sw[(size_t)(k0 + r) * n + k0 + c], true);      // lower (c,r)
         }
+        plba_cp_async_commit(); plba_cp_async_wait<0>();
+#else
+        for (int idx = tid; idx < nb * nb; idx += PLBA_NT) {
+            const int r = idx / nb, c = idx - r * nb;
+            if (c >= r) M[(size_t)c * ldm + r] = Sw[(size_t)(k0 + r) * n + k0 + c];
+        }
+#endif
+    PHASE_END
+    PHASE_BEGIN
+        if (tid < nb) M[(size_t)tid * ldm + tid] += (P.profile == PLBA_PROFILE_G) ? ctl.lambda : ctl.lambda * P.hpp_diag[(size_t)6 * slot0 + k0 + tid];
     PHASE_END
     chol_lower_panels(M, ldm, nb, nb - 1, dinv, Lblk, part, fail);
     PHASE_BEGIN
@@ -464,83 +489,106 @@ PLBA_KERNEL void k_potrf_block(const DevP *Pp, int w, int k0, int nb) {
 }
 
 // columns k0+nb .. n-1 of block row k, plus the right-hand side as one more column (handled by the last CTA)
-enum { TRSM_COLS = 128 };
-static inline size_t trsm_block_smem() { return sizeof(double) * ((size_t)NBK * (NBK + 1) + (size_t)NBK * (TRSM_COLS + 1) + NBK); }
-PLBA_KERNEL void k_trsm_block(const DevP *Pp, int w, int k0, int nb) {
+// Round 2, second half: ONE THREAD PER COLUMN WITH THE WHOLE COLUMN IN REGISTERS.  The first version kept the CTA's 96 x 128 columns in shared
+// memory and paid ~1.3 shared loads per FMA plus 32 block barriers (66 us per step on the factorisation's critical path).  Here a thread
+// loads its 96 entries once and runs the forward substitution right-looking, one pose block (6 pivots) per loop iteration: solve the 6 x 6
+// triangle, then a_r -= sum_i U[p0+i][r] x_i for every later row — independent FMAs, the U rows are BROADCAST 128-bit shared loads (one
+// load per two FMAs), no barrier at all.  Register indices must be compile-time, so the column SLIDES: after each block the live rows
+// move down by six registers and the loop body always works on registers 0..95 (a fully unrolled nest, 112 KB of straight-line code,
+// measured 100 us: every instruction line came from L2).
+enum { TRSM_COLS = 64, TRSM_LD = NBK };
+static inline size_t trsm_block_smem() { return sizeof(double) * ((size_t)NBK * TRSM_LD + NBK); }
+PLBA_KERNEL void PLBA_BOUNDS(TRSM_COLS, 1) k_trsm_block(const DevP *Pp, double *Sw, int n, double *g, int k0, int nb) {
     PLBA_SMEM(raw);
-    PLBA_PARAMS(P, Pp);
-    const int n = 6 * P.win_nfree[w], slot0 = P.win_slot0[w], ldl = nb + 1, ldx = TRSM_COLS + 1;
-    double *Sw = P.S + P.win_S_off[w];
-    double *Lk = (double *)raw, *X = Lk + (size_t)NBK * (NBK + 1), *Dk = X + (size_t)NBK * (TRSM_COLS + 1);      // Lk = U_kk^T (lower), X = the CTA's columns, Dk = 1 / diag
+    PLBA_COUNT_LAUNCH(Pp);
+    double *Uk = (double *)raw, *Dk = Uk + (size_t)NBK * TRSM_LD;      // Uk[q][r] = U_kk[q][r] (r > q); rows / columns >= nb: identity
     const int c0 = k0 + nb + PLBA_BID * TRSM_COLS;                     // first column of this CTA; column index n = right-hand side
-    double *g = P.xp + (size_t)6 * slot0;                              // y is built in xp (copied from gs by the first block)
+    THR_ARR(double, a, NBK);
     PHASE_BEGIN
-        for (int idx = tid; idx < nb * nb; idx += PLBA_NT) {
-            const int r = idx / nb, c = idx - r * nb;
-            if (c >= r) { const double v = Sw[(size_t)(k0 + r) * n + k0 + c]; Lk[(size_t)c * ldl + r] = v; if (c == r) Dk[r] = 1.0 / v; }
+        THR_BIND(a);
+        // U_kk as asynchronous 16-byte copies (72 per thread, all in flight; rows / columns past nb are zero-filled), the thread's own
+        // column as 96 plain loads issued behind them: one HBM round trip for everything
+#ifndef PLBA_HOST_EMU
+        for (int idx = tid; idx < NBK * NBK / 2; idx += PLBA_NT) {
+            const int q = idx / (NBK / 2), r = (idx - q * (NBK / 2)) * 2;
+            const bool ok = q < nb && r < nb;
+            plba_cp_async16(Uk + (size_t)q * TRSM_LD + r, Sw + (size_t)(k0 + (ok ? q : 0)) * n + k0 + (ok ? r : 0), ok);
         }
-        for (int idx = tid; idx < nb * TRSM_COLS; idx += PLBA_NT) {
-            const int r = idx / TRSM_COLS, cc = idx - r * TRSM_COLS, c = c0 + cc;
-            X[(size_t)r * ldx + cc] = (c < n) ? Sw[(size_t)(k0 + r) * n + c] : (c == n ? g[k0 + r] : 0.0);
+        plba_cp_async_commit();
+#else
+        for (int idx = tid; idx < NBK * NBK; idx += PLBA_NT) {
+            const int q = idx / NBK, r = idx - q * NBK;
+            Uk[(size_t)q * TRSM_LD + r] = (q < nb && r < nb) ? Sw[(size_t)(k0 + q) * n + k0 + r] : 0.0;
         }
+#endif
+        const int c = c0 + tid;
+        if (c <= n) {
+#pragma unroll
+            for (int r = 0; r < NBK; r++) a[r] = (r < nb) ? ((c < n) ? Sw[(size_t)(k0 + r) * n + c] : g[k0 + r]) : 0.0;
+        }
+#ifndef PLBA_HOST_EMU
+        plba_cp_async_wait<0>();
+#endif
     PHASE_END
-    // forward substitution L X = A in panels of 6 rows: (1) all 256 threads subtract the contribution of the rows already
-    // solved (thread = column x half of the panel's rows, three accumulators against broadcast rows of L), (2) one thread per
-    // column solves the 6 x 6 triangle
-    for (int p0 = 0; p0 < nb; p0 += 6) {
-        PHASE_BEGIN
-            const int cc = tid & (TRSM_COLS - 1), hf = tid >> 7;
-            if (p0 > 0 && c0 + cc <= n) {
-                double acc[3] = {0, 0, 0};
-                const double *L0 = Lk + (size_t)(p0 + 3 * hf) * ldl;
-#pragma unroll 4
-                for (int q = 0; q < p0; q++) {
-                    const double v = X[(size_t)q * ldx + cc];
-                    acc[0] += v * L0[q]; acc[1] += v * L0[ldl + q]; acc[2] += v * L0[2 * ldl + q];
-                }
-#pragma unroll
-                for (int c = 0; c < 3; c++) X[(size_t)(p0 + 3 * hf + c) * ldx + cc] -= acc[c];
-            }
-        PHASE_END
-        PHASE_BEGIN
-            if (tid < TRSM_COLS && c0 + tid <= n) {
-                const int cc = tid;
-                double x[6];
-#pragma unroll
-                for (int c = 0; c < 6; c++) {
-                    double v = X[(size_t)(p0 + c) * ldx + cc];
-#pragma unroll
-                    for (int k = 0; k < c; k++) v -= x[k] * Lk[(size_t)(p0 + c) * ldl + p0 + k];
-                    x[c] = v * Dk[p0 + c];
-                }
-#pragma unroll
-                for (int c = 0; c < 6; c++) X[(size_t)(p0 + c) * ldx + cc] = x[c];
-            }
-        PHASE_END
-    }
     PHASE_BEGIN
-        for (int idx = tid; idx < nb * TRSM_COLS; idx += PLBA_NT) {
-            const int r = idx / TRSM_COLS, cc = idx - r * TRSM_COLS, c = c0 + cc;
-            if (c < n) Sw[(size_t)(k0 + r) * n + c] = X[(size_t)r * ldx + cc];
-            else if (c == n) g[k0 + r] = X[(size_t)r * ldx + cc];
+        for (int q = tid; q < NBK; q += PLBA_NT) Dk[q] = (q < nb) ? 1.0 / Uk[(size_t)q * TRSM_LD + q] : 1.0;
+    PHASE_END
+    PHASE_BEGIN
+        THR_BIND(a);
+        const int c = c0 + tid;
+        if (c <= n) {
+#pragma unroll 1
+            for (int p0 = 0; p0 < NBK; p0 += 6) {
+                double xq[6];
+#pragma unroll
+                for (int i = 0; i < 6; i++) {
+                    xq[i] = a[i] * Dk[p0 + i];
+#pragma unroll
+                    for (int j = i + 1; j < 6; j++) a[j] -= Uk[(size_t)(p0 + i) * TRSM_LD + p0 + j] * xq[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 6; i++) {
+                    if (p0 + i < nb) { if (c < n) Sw[(size_t)(k0 + p0 + i) * n + c] = xq[i]; else g[k0 + p0 + i] = xq[i]; }
+                }
+                // live rows p0 + 6 .. 95 sit in registers 6 .. 95 - p0, in blocks of 18 (a block past the end is skipped as a whole)
+#pragma unroll
+                for (int b = 0; b < 5; b++) {
+                    if (p0 + 6 + 18 * b < NBK) {
+#pragma unroll
+                        for (int i = 0; i < 6; i++) {
+                            const double *ur = Uk + (size_t)(p0 + i) * TRSM_LD + p0 + 6 + 18 * b;      // even offset: 16-byte aligned
+#pragma unroll
+                            for (int j = 0; j < 18; j += 2) {
+                                const plba_d2 u2 = (p0 + 6 + 18 * b + j < NBK) ? *(const plba_d2 *)(ur + j) : plba_d2{0.0, 0.0};
+                                a[6 + 18 * b + j] -= u2.x * xq[i]; a[6 + 18 * b + j + 1] -= u2.y * xq[i];
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int m = 0; m < NBK - 6; m++) a[m] = a[m + 6];
+            }
         }
     PHASE_END
 }
 
-// g_j -= sum_r U[k0+r][j] y[k0+r]   for every column j right of the block
+// g_j -= sum_r U[k0+r][j] y[k0+r]   for every column j right of the block; the block's rows are dealt over gridDim.y groups of RHS_ROWS
+// (a thread's chain is 12 products instead of 96: the kernel sits on the factorisation's critical path)
+enum { RHS_ROWS = 12 };
 PLBA_KERNEL void k_rhs_update(const DevP *Pp, int w, int k0, int nb) {
     PLBA_PARAMS(P, Pp);
     const int n = 6 * P.win_nfree[w], slot0 = P.win_slot0[w];
     const double *Sw = P.S + P.win_S_off[w];
     double *g = P.xp + (size_t)6 * slot0;
     PHASE_BEGIN
-        for (int j = k0 + nb + PLBA_BID * PLBA_NT + tid; j < n; j += PLBA_NB * PLBA_NT) {
+        const int j = k0 + nb + PLBA_BID * PLBA_NT + tid, r0 = PLBA_BIDY * RHS_ROWS;
+        if (j < n && r0 < nb) {
             double s0 = 0.0, s1 = 0.0, s2 = 0.0;          // nb is a multiple of 6: three independent chains, loads issued ahead
-#pragma unroll 2
-            for (int r = 0; r < nb; r += 3) {
-                s0 += Sw[(size_t)(k0 + r) * n + j] * g[k0 + r]; s1 += Sw[(size_t)(k0 + r + 1) * n + j] * g[k0 + r + 1]; s2 += Sw[(size_t)(k0 + r + 2) * n + j] * g[k0 + r + 2];
+#pragma unroll
+            for (int r = r0; r < r0 + RHS_ROWS; r += 3) {
+                if (r < nb) { s0 += Sw[(size_t)(k0 + r) * n + j] * g[k0 + r]; s1 += Sw[(size_t)(k0 + r + 1) * n + j] * g[k0 + r + 1]; s2 += Sw[(size_t)(k0 + r + 2) * n + j] * g[k0 + r + 2]; }
             }
-            g[j] -= (s0 + s1) + s2;
+            plba_atomic_add(&g[j], -((s0 + s1) + s2));
         }
     PHASE_END
 }
@@ -556,32 +604,37 @@ PLBA_KERNEL void k_rhs_init(const DevP *Pp, int w) {
 PLBA_D void plba_dmma(double &d0, double &d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
-PLBA_D void plba_cp_async16(void *smem_dst, const void *gsrc, bool valid) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int sz = valid ? 16 : 0;                    // src-size 0: the 16 bytes are zero-filled
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
-}
-PLBA_D void plba_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> PLBA_D void plba_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
 
-static inline size_t syrk_dmma_smem() { return sizeof(double) * (size_t)(2 * 2 * SKC * SLD); }
-// A_ij -= U_ki^T U_kj for the trailing tiles (ti <= tj) of step k; lo = first trailing row / column
-PLBA_KERNEL void PLBA_BOUNDS(256, 1) k_syrk_dmma(const DevP *Pp, int w, int k0, int nb, int lo) {
+// Trailing update, second generation (round 2).  What the first one measured (profiles/README.md r02j): 12.7 TFLOP/s although ONE warp
+// alone reaches a quarter of the chip's FP64 tensor rate — with K = 96 per visit of a C tile, the 256 KB read-modify-write of the tile and
+// the pipeline fill cost more than the 24 k-steps between them, and one 8-warp CTA per SM (128 accumulator registers per thread) has
+// nothing to overlap them with.  Now: 128 x 64 tiles, 32 x 32 per warp (64 accumulator registers) -> TWO CTAs per SM, so that one CTA's
+// epilogue / prologue runs under the other's k-steps; K chunks of 16 rows in a four-stage ring (three chunks in flight, one block barrier
+// per chunk).  Tile rows [tr0, tr1) only: the factorisation's look-ahead launches the tile row that holds the next panel on its own.
+enum { STM = 128, STN = 64, SKC2 = 16, SST = 4, SLDA = STM + 4, SLDB = STN + 4, SYRK_STAGE = SKC2 * (SLDA + SLDB) };
+static inline size_t syrk_dmma_smem() { return sizeof(double) * (size_t)(SST * SYRK_STAGE); }
+// number of 128 x 64 tiles of tile rows [tr0, tr1) of the upper-triangular trailing matrix of order m: tile row ti needs the column tiles 2 ti .. TN - 1
+static inline int syrk_tiles(int m, int tr0, int tr1) {
+    const int TN = (m + STN - 1) / STN;
+    int c = 0;
+    for (int ti = tr0; ti < tr1; ti++) c += std::max(0, TN - 2 * ti);
+    return c;
+}
+// A_ij -= U_ki^T U_kj for the trailing tiles of step k; lo = first trailing row / column
+PLBA_KERNEL void PLBA_BOUNDS(256, 2) k_syrk_dmma(const DevP *Pp, double *Sw, int n, int k0, int nb, int lo, int tr0) {
     PLBA_SMEM(raw);
-    PLBA_PARAMS(P, Pp);
-    const int n = 6 * P.win_nfree[w];
-    double *Sw = P.S + P.win_S_off[w];
-    const int T = (n - lo + ST - 1) / ST;
-    int p = PLBA_BID, ti = 0;
-    while (p >= T - ti) { p -= T - ti; ti++; }
-    const int tj = ti + p;
-    const int i0 = lo + ti * ST, j0 = lo + tj * ST;
+    PLBA_COUNT_LAUNCH(Pp);            // (matrix pointer and order are kernel arguments: no parameter block, no dependent loads before the first copy)
+    const int TN = (n - lo + STN - 1) / STN;
+    int p = PLBA_BID, ti = tr0;
+    while (p >= TN - 2 * ti) { p -= TN - 2 * ti; ti++; }
+    const int tj = 2 * ti + p;
+    const int i0 = lo + ti * STM, j0 = lo + tj * STN;
 #ifdef PLBA_HOST_EMU
     (void)raw;
     PHASE_BEGIN     // plain loops on the host (the MMA fragments exist only on the GPU)
-        for (int idx = tid; idx < ST * ST; idx += PLBA_NT) {
-            const int r = i0 + idx / ST, c = j0 + idx % ST;
+        for (int idx = tid; idx < STM * STN; idx += PLBA_NT) {
+            const int r = i0 + idx / STN, c = j0 + idx % STN;
             if (r >= n || c >= n || c < r) continue;
             double sum = 0.0;
             for (int q = 0; q < nb; q++) sum += Sw[(size_t)(k0 + q) * n + r] * Sw[(size_t)(k0 + q) * n + c];
@@ -589,120 +642,177 @@ PLBA_KERNEL void PLBA_BOUNDS(256, 1) k_syrk_dmma(const DevP *Pp, int w, int k0, 
         }
     PHASE_END
 #else
-    double *As = (double *)raw, *Bs = As + 2 * SKC * SLD;     // [2 stages][SKC][SLD] each
+    double *ring = (double *)raw;                              // [SST stages][SKC2 rows][SLDA of A | SLDB of B]
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp & 1, wn = warp >> 1;                   // 2 x 4 warps: 64 x 32 per warp
-    const bool diag = (ti == tj);
-    double acc[8][4][2];
+    const int wm = warp & 3, wn = warp >> 2;                   // 4 x 2 warps: 32 x 32 per warp
+    double acc[4][4][2];
 #pragma unroll
-    for (int a = 0; a < 8; a++)
+    for (int a = 0; a < 4; a++)
 #pragma unroll
         for (int b = 0; b < 4; b++) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
-    const int nchunk = (nb + SKC - 1) / SKC;
-    auto load_chunk = [&](int ch, int stage) {
-        // SKC rows x 128 doubles per operand = 2048 x 16-byte copies; 256 threads -> 8 each per operand
-        for (int it = 0; it < 8; it++) {
-            const int e = tid + it * 256, r = e >> 6, c2 = (e & 63) * 2;
-            const int kr = ch * SKC + r;
-            const bool okr = kr < nb;
-            const size_t row = (size_t)(k0 + (okr ? kr : 0)) * n;
-            { const int c = i0 + c2; const bool ok = okr && c < n; plba_cp_async16(As + (size_t)(stage * SKC + r) * SLD + c2, Sw + row + (ok ? c : 0), ok); }
-            if (!diag) { const int c = j0 + c2; const bool ok = okr && c < n; plba_cp_async16(Bs + (size_t)(stage * SKC + r) * SLD + c2, Sw + row + (ok ? c : 0), ok); }
+    const int nchunk = (nb + SKC2 - 1) / SKC2;
+    auto load_chunk = [&](int ch) {
+        if (ch < nchunk) {
+            double *As = ring + (size_t)(ch % SST) * SYRK_STAGE, *Bs = As + SKC2 * SLDA;
+            // 16 rows x (128 + 64) doubles = 1 536 16-byte copies: 4 + 2 per thread
+#pragma unroll
+            for (int it = 0; it < 4; it++) {
+                const int e = tid + it * 256, r = e >> 6, c2 = (e & 63) * 2, kr = ch * SKC2 + r, c = i0 + c2;
+                const bool ok = kr < nb && c < n;
+                plba_cp_async16(As + (size_t)r * SLDA + c2, Sw + (size_t)(k0 + (ok ? kr : 0)) * n + (ok ? c : 0), ok);
+            }
+#pragma unroll
+            for (int it = 0; it < 2; it++) {
+                const int e = tid + it * 256, r = e >> 5, c2 = (e & 31) * 2, kr = ch * SKC2 + r, c = j0 + c2;
+                const bool ok = kr < nb && c < n;
+                plba_cp_async16(Bs + (size_t)r * SLDB + c2, Sw + (size_t)(k0 + (ok ? kr : 0)) * n + (ok ? c : 0), ok);
+            }
         }
-        plba_cp_async_commit();
+        plba_cp_async_commit();                                // (an empty group past the last chunk keeps the wait count uniform)
     };
-    load_chunk(0, 0);
+    load_chunk(0); load_chunk(1); load_chunk(2);
+    // the C tile is read only in the epilogue, ~10 us from now: pull its lines into L2 meanwhile (the trailing matrix does not fit L2)
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        const int r = i0 + wm * 32 + a * 8 + (lane >> 2), cb = j0 + wn * 32 + 8 * (lane & 3);      // the row's 32 columns as four 64-byte pieces
+        if (r < n && cb < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(Sw + (size_t)r * n + cb));
+    }
     for (int ch = 0; ch < nchunk; ch++) {
-        const int stage = ch & 1;
-        if (ch + 1 < nchunk) { load_chunk(ch + 1, stage ^ 1); plba_cp_async_wait<1>(); } else plba_cp_async_wait<0>();
-        __syncthreads();
-        const double *Ac = As + (size_t)stage * SKC * SLD, *Bc = diag ? Ac : Bs + (size_t)stage * SKC * SLD;
+        plba_cp_async_wait<2>();                               // chunk ch has landed (this thread's copies); the barrier makes it everyone's
+        __syncthreads();                                       // ... and says that every warp is done with chunk ch - 1, whose stage is refilled now
+        load_chunk(ch + 3);
+        const double *Ac = ring + (size_t)(ch % SST) * SYRK_STAGE, *Bc = Ac + SKC2 * SLDA;
 #pragma unroll
-        for (int kk = 0; kk < SKC; kk += 4) {
-            double af[8], bf[4];
-            const double *ar = Ac + (size_t)(kk + (lane & 3)) * SLD + wm * 64 + (lane >> 2);
-            const double *br = Bc + (size_t)(kk + (lane & 3)) * SLD + wn * 32 + (lane >> 2);
+        for (int kk = 0; kk < SKC2; kk += 4) {
+            double af[4], bf[4];
+            const double *ar = Ac + (size_t)(kk + (lane & 3)) * SLDA + wm * 32 + (lane >> 2);
+            const double *br = Bc + (size_t)(kk + (lane & 3)) * SLDB + wn * 32 + (lane >> 2);
 #pragma unroll
-            for (int a = 0; a < 8; a++) af[a] = ar[a * 8];
+            for (int a = 0; a < 4; a++) af[a] = ar[a * 8];
 #pragma unroll
             for (int b = 0; b < 4; b++) bf[b] = br[b * 8];
 #pragma unroll
-            for (int a = 0; a < 8; a++)
+            for (int a = 0; a < 4; a++)
 #pragma unroll
                 for (int b = 0; b < 4; b++) plba_dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
         }
-        __syncthreads();
     }
+    // epilogue: C -= acc (upper triangle only); two rows of four fragments (eight 16-byte loads) are in flight per thread
 #pragma unroll
-    for (int a = 0; a < 8; a++) {
-        const int r = i0 + wm * 64 + a * 8 + (lane >> 2);
+    for (int a2 = 0; a2 < 4; a2 += 2) {
+        plba_d2 v[2][4];
+        bool fast[2];
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const int c = j0 + wn * 32 + b * 8 + 2 * (lane & 3);
-            if (r < n && c + 1 < n && c >= r) {
-                plba_d2 *dst = (plba_d2 *)(Sw + (size_t)r * n + c);
-                plba_d2 v = *dst; v.x -= acc[a][b][0]; v.y -= acc[a][b][1]; *dst = v;
-            } else if (r < n) {
-                if (c < n && c >= r) Sw[(size_t)r * n + c] -= acc[a][b][0];
-                if (c + 1 < n && c + 1 >= r) Sw[(size_t)r * n + c + 1] -= acc[a][b][1];
+        for (int h = 0; h < 2; h++) {
+            const int r = i0 + wm * 32 + (a2 + h) * 8 + (lane >> 2), cb = j0 + wn * 32 + 2 * (lane & 3);
+            fast[h] = (r < n && cb >= r && cb + 24 + 1 < n);      // the common case: the lane's four 16-byte pieces lie inside the upper triangle
+            if (fast[h]) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) v[h][b] = *(const plba_d2 *)(Sw + (size_t)r * n + cb + b * 8);
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int a = a2 + h, r = i0 + wm * 32 + a * 8 + (lane >> 2), cb = j0 + wn * 32 + 2 * (lane & 3);
+            if (r >= n) continue;
+            double *row = Sw + (size_t)r * n;
+            if (fast[h]) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) { v[h][b].x -= acc[a][b][0]; v[h][b].y -= acc[a][b][1]; *(plba_d2 *)(row + cb + b * 8) = v[h][b]; }
+            } else {
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int c = cb + b * 8;
+                    if (c < n && c >= r) row[c] -= acc[a][b][0];
+                    if (c + 1 < n && c + 1 >= r) row[c + 1] -= acc[a][b][1];
+                }
             }
         }
     }
 #endif
 }
 
-// backward substitution U x = y for block row k (blocks are visited last to first; x overwrites y in xp)
-static inline size_t back_block_smem() { return sizeof(double) * ((size_t)NBK * (NBK + 1) + (size_t)NBK * 33 + 2 * NBK); }
-PLBA_KERNEL void k_back_block(const DevP *Pp, int w, int k0, int nb) {
+// backward substitution U_kk x_k = y_k for block k (blocks are visited last to first; x overwrites y in xp; k_back_update has already
+// taken the blocks right of k out of y_k).  The CTA loads the triangle (six loads in flight per thread), then ONE WARP solves it: lane l
+// keeps y of rows l, l + 32, l + 64 in registers; column by column the owner publishes x_c and every lane takes it out of its rows
+// (column reads of the odd-stride triangle are conflict-free): ~100 cycles per unknown, no block barrier inside the solve.
+enum { BB_LD = NBK + 1 };
+static inline size_t back_block_smem() { return sizeof(double) * ((size_t)NBK * BB_LD + 2 * NBK); }
+PLBA_KERNEL void PLBA_BOUNDS(256, 1) k_back_block(const DevP *Pp, const double *Sw, int n, double *x, const WinCtrl *ctl, int k0, int nb) {
     PLBA_SMEM(raw);
-    PLBA_PARAMS(P, Pp);
-    WinCtrl &ctl = P.ctrl[w];
-    const int n = 6 * P.win_nfree[w], slot0 = P.win_slot0[w], ldu = nb + 1;
-    const double *Sw = P.S + P.win_S_off[w];
-    double *x = P.xp + (size_t)6 * slot0;
-    double *Uk = (double *)raw, *part = Uk + (size_t)NBK * (NBK + 1), *yk = part + (size_t)NBK * 33;
+    PLBA_COUNT_LAUNCH(Pp);
+    double *Uk = (double *)raw, *Dk = Uk + (size_t)NBK * BB_LD, *xs = Dk + NBK;
     PHASE_BEGIN
-        for (int idx = tid; idx < nb * nb; idx += PLBA_NT) {
-            const int r = idx / nb, c = idx - r * nb;
-            if (c >= r) Uk[(size_t)r * ldu + c] = Sw[(size_t)(k0 + r) * n + k0 + c];
+#ifndef PLBA_HOST_EMU
+        for (int idx = tid; idx < NBK * NBK; idx += PLBA_NT) {
+            const int r = idx / NBK, c = idx - r * NBK;
+            const bool ok = c >= r && c < nb;
+            if (c >= r) plba_cp_async8(&Uk[(size_t)r * BB_LD + c], &Sw[(size_t)(k0 + (ok ? r : 0)) * n + k0 + (ok ? c : 0)], ok);
         }
-        // partial dot products of row r with the already solved x_j, j right of the block: 32 lanes per row, coalesced
-        const int lane = tid & 31, wrp = tid >> 5, nw = PLBA_NT >> 5;
-        for (int r = wrp; r < nb; r += nw) {
-            double sum = 0.0;
-            const double *row = Sw + (size_t)(k0 + r) * n;
-            for (int j = k0 + nb + lane; j < n; j += 32) sum += row[j] * x[j];
-            part[(size_t)r * 33 + lane] = sum;
+        plba_cp_async_commit(); plba_cp_async_wait<0>();
+#else
+        for (int idx = tid; idx < NBK * NBK; idx += PLBA_NT) {
+            const int r = idx / NBK, c = idx - r * NBK;
+            if (c >= r) Uk[(size_t)r * BB_LD + c] = (c < nb) ? Sw[(size_t)(k0 + r) * n + k0 + c] : 0.0;
         }
+#endif
     PHASE_END
     PHASE_BEGIN
-        if (tid < nb) { double sum = x[k0 + tid]; for (int l = 0; l < 32; l++) sum -= part[(size_t)tid * 33 + l]; yk[tid] = sum; }
+        for (int r = tid; r < NBK; r += PLBA_NT) Dk[r] = (r < nb) ? 1.0 / Uk[(size_t)r * BB_LD + r] : 1.0;
     PHASE_END
-    for (int p0 = nb - 6; p0 >= 0; p0 -= 6) {   // back substitution in panels of 6: every thread solves the 6 x 6 triangle redundantly,
-        PHASE_BEGIN                             // thread t < p0 then removes the panel from its own y[t] (reads a row segment of U)
-            if (tid <= p0) {
-                double xs[6];
+    if (PLBA_WARP_IN_CTA == 0) {
+        LANE_ARR(double, y, 3);
+        WPHASE_BEGIN
+            LANE_BIND(y);
 #pragma unroll
-                for (int c = 5; c >= 0; c--) {
-                    double v = yk[p0 + c];
+            for (int j = 0; j < 3; j++) y[j] = (lane + 32 * j < nb) ? x[k0 + lane + 32 * j] : 0.0;
+        WPHASE_END
 #pragma unroll
-                    for (int m = c + 1; m < 6; m++) v -= Uk[(size_t)(p0 + c) * ldu + p0 + m] * xs[m];
-                    xs[c] = v / Uk[(size_t)(p0 + c) * ldu + p0 + c];
-                }
-                if (tid < p0) {
-                    double y = yk[tid];
+        for (int c = NBK - 1; c >= 0; c--) {
+            WPHASE_BEGIN
+                LANE_BIND(y);
+                if (lane == (c & 31)) xs[c] = y[c >> 5] * Dk[c];
+            WPHASE_END
+            WPHASE_BEGIN
+                LANE_BIND(y);
+                const double xc = xs[c];
 #pragma unroll
-                    for (int c = 0; c < 6; c++) y -= Uk[(size_t)tid * ldu + p0 + c] * xs[c];
-                    yk[tid] = y;
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 6; c++) yk[NBK + p0 + c] = xs[c];
-                }
-            }
-        PHASE_END
+                for (int j = 0; j < 3; j++) { if (lane + 32 * j < c) y[j] -= Uk[(size_t)(lane + 32 * j) * BB_LD + c] * xc; }
+            WPHASE_END
+        }
     }
     PHASE_BEGIN
-        if (tid < nb) x[k0 + tid] = ctl.solve_fail ? 0.0 : yk[NBK + tid];
+    PHASE_END
+    PHASE_BEGIN
+        if (tid < nb) x[k0 + tid] = ctl->solve_fail ? 0.0 : xs[tid];
+    PHASE_END
+}
+
+// Column-oriented half of the backward substitution: once block k is solved, y_i -= U[i][block k] x_k for EVERY row i above it — rows
+// are independent (two threads per row, 48 contiguous columns each, 128-bit loads), so the whole machine reads the 96-column strip at
+// once instead of one CTA reading a 96 x (n - k0) block row (round 2, first half: up to 370 us per step, 25.8 ms per solve at n = 12 000).
+enum { BU_ROWS = 128 };
+PLBA_KERNEL void PLBA_BOUNDS(2 * BU_ROWS, 1) k_back_update(const DevP *Pp, const double *Sw, int n, double *x, int k0, int nb) {
+    PLBA_COUNT_LAUNCH(Pp);
+    PLBA_SHARED double xs[NBK], part[2 * BU_ROWS];
+    PHASE_BEGIN
+        if (tid < NBK) xs[tid] = (tid < nb) ? x[k0 + tid] : 0.0;
+    PHASE_END
+    PHASE_BEGIN
+        const int i = PLBA_BID * BU_ROWS + (tid >> 1), hf = tid & 1, c0 = hf * (NBK / 2);
+        double s0 = 0.0, s1 = 0.0;
+        if (i < k0) {
+            const double *row = Sw + (size_t)i * n + k0 + c0;            // (k0 and n are even: 16-byte aligned)
+#pragma unroll 8
+            for (int c = 0; c < NBK / 2; c += 2) {
+                if (c0 + c < nb) { const plba_d2 v = *(const plba_d2 *)(row + c); s0 += v.x * xs[c0 + c]; s1 += v.y * xs[c0 + c + 1]; }
+            }
+        }
+        part[tid] = s0 + s1;
+    PHASE_END
+    PHASE_BEGIN
+        const int i = PLBA_BID * BU_ROWS + tid;
+        if (tid < BU_ROWS && i < k0) x[i] -= part[2 * tid] + part[2 * tid + 1];
     PHASE_END
 }
 
