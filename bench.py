@@ -304,6 +304,26 @@ def largest_config_roofline(s, abi, args, P5, peaks):
                     "frac is against the HBM roof (BASELINE's metric), frac_fp64 against the measured FP64 roof" % (F / 1e9, F / ((fp or 37.0) * 1e12) * 1e6, A / (peak * 1e9) * 1e6)}
 
 
+def dense_cholesky_roofline(s, abi, args, P5, peaks):
+    """The reduced camera system of config 5 (12 000 unknowns) factored as a DENSE matrix — the route a loop-closure-shaped window of that
+    size takes (its reduced system is not block-banded, so the block cyclic reduction does not apply).  Tensor-bound: n^3 / 3 FP64 flops on
+    mma.sync.m8n8k4.f64 against the DMMA peak measured in the same run."""
+    try:
+        s.set_force_dense(True)
+        s.upload(P5, abi.Options(PROFILES[args.profile] if args.profile != "H_END" else 0, args.quirks))
+        n = 6 * P5.n_free
+        ms = s.time_kernel(1, 3)
+        fl = n ** 3 / 3.0
+        fp = peaks.get("dmma_tflops")
+        return {"workload": "dense reduced camera system of C5: n = %d (factorisation + both substitutions)" % n, "kernel": "k_syrk_dmma (+ k_potrf_block, k_trsm_block, k_rhs_update, k_back_block, k_back_update)",
+                "bound": "tensor", "ms_per_solve": ms, "flops": fl, "achieved": fl / (ms * 1e-3) / 1e12, "peak": fp, "unit": "TFLOP/s", "frac": (fl / (ms * 1e-3) / 1e12 / fp) if fp else None,
+                "peak_source": "measured in this run (k_peak_dmma)", "kernel_path": s.kernel_path(), "solves_timed": 3}
+    except Exception as e:      # noqa: BLE001
+        return {"error": str(e)}
+    finally:
+        s.set_force_dense(False)
+
+
 def other_configs(tm, s, abi, scene, orc, args, prof, p5_holder):
     """Whole-LBA numbers of the BASELINE configs other than the headline one: resident, end-to-end, 1-thread CPU sample."""
     out = {}
@@ -467,6 +487,7 @@ def main():
         peaks = fp64_peaks(s)
         extras["fp64_peaks"] = peaks
         extras["roofline_largest"] = largest_config_roofline(s, abi, args, p5[0] if p5 else make_workload("C5", 0, scene, abi), peaks)
+        extras["dense_cholesky"] = dense_cholesky_roofline(s, abi, args, p5[0] if p5 else make_workload("C5", 0, scene, abi), peaks)
     if world > 1 and not args.no_sharded:
         extras["c3_replicas"] = c3_replicas(tm, s, abi, scene, args, prof, rank, world, torch, dist, dev)
         extras["sharded"] = {name: sharded_run(abi, scene, args, rank, world, dev, stream, barrier, torch, dist, name) for name in ("C4", "C5")}

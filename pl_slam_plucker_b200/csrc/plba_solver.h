@@ -442,6 +442,19 @@ PLBA_D void plba_cp_async8(void *smem_dst, const void *gsrc, bool valid) {
     const int sz = valid ? 8 : 0;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
 }
+// TMA bulk copies (cp.async.bulk, SASS UBLKCP): one instruction moves a whole operand row global -> shared, completion is counted in
+// bytes on an mbarrier — no per-thread address arithmetic, no registers, no wait groups
+PLBA_D unsigned plba_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+PLBA_D void plba_mbar_init(void *bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(plba_smem_u32(bar)), "r"(count) : "memory"); }
+PLBA_D void plba_mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+PLBA_D void plba_mbar_expect_tx(void *bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(plba_smem_u32(bar)), "r"(bytes) : "memory"); }
+PLBA_D void plba_mbar_arrive(void *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(plba_smem_u32(bar)) : "memory"); }
+PLBA_D void plba_mbar_wait(void *bar, unsigned parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(plba_smem_u32(bar)), "r"(parity) : "memory");
+}
+PLBA_D void plba_bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, void *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(plba_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(plba_smem_u32(bar)) : "memory");
+}
 PLBA_D void plba_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> PLBA_D void plba_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
@@ -613,7 +626,10 @@ PLBA_D void plba_dmma(double &d0, double &d1, double a, double b) {
 // epilogue / prologue runs under the other's k-steps; K chunks of 16 rows in a four-stage ring (three chunks in flight, one block barrier
 // per chunk).  Tile rows [tr0, tr1) only: the factorisation's look-ahead launches the tile row that holds the next panel on its own.
 enum { STM = 128, STN = 64, SKC2 = 16, SST = 4, SLDA = STM + 4, SLDB = STN + 4, SYRK_STAGE = SKC2 * (SLDA + SLDB) };
-static inline size_t syrk_dmma_smem() { return sizeof(double) * (size_t)(SST * SYRK_STAGE); }
+#ifndef PLBA_SYRK_TMA
+#define PLBA_SYRK_TMA 1      // operand rows by TMA bulk copies + mbarriers (0: per-thread 16-byte cp.async, the first version of this kernel)
+#endif
+static inline size_t syrk_dmma_smem() { return sizeof(double) * (size_t)(SST * SYRK_STAGE) + 16 * SST; }
 // number of 128 x 64 tiles of tile rows [tr0, tr1) of the upper-triangular trailing matrix of order m: tile row ti needs the column tiles 2 ti .. TN - 1
 static inline int syrk_tiles(int m, int tr0, int tr1) {
     const int TN = (m + STN - 1) / STN;
@@ -651,6 +667,41 @@ PLBA_KERNEL void PLBA_BOUNDS(256, 2) k_syrk_dmma(const DevP *Pp, double *Sw, int
 #pragma unroll
         for (int b = 0; b < 4; b++) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
     const int nchunk = (nb + SKC2 - 1) / SKC2;
+#if PLBA_SYRK_TMA
+    // warp 0 is the producer: lane r < 16 moves row r of the A operand (128 doubles), lane 16 + r row r of the B operand (64 doubles) of a chunk
+    // as ONE bulk copy each; lane 0 announces the chunk's byte count on the stage's FULL mbarrier first.  Every warp waits on that mbarrier,
+    // and says on the stage's EMPTY mbarrier when it is done with the chunk: the producer refills a stage once all eight warps have released
+    // it — NO block barrier in the k-loop (the cp.async variant needs one per chunk to make the copies of other threads visible).
+    unsigned long long *full = (unsigned long long *)(ring + (size_t)SST * SYRK_STAGE), *empty = full + SST;
+    if (tid == 0) {
+#pragma unroll
+        for (int st = 0; st < SST; st++) { plba_mbar_init(&full[st], 1); plba_mbar_init(&empty[st], 8); }
+        plba_mbar_init_fence();
+    }
+    __syncthreads();
+    const unsigned a_bytes = 8u * (unsigned)((n - i0 < STM) ? n - i0 : STM), b_bytes = 8u * (unsigned)((n - j0 < STN) ? n - j0 : STN);      // (even counts: multiples of 16 bytes)
+    auto load_chunk = [&](int ch) {
+        if (warp == 0 && ch < nchunk) {
+            const int st = ch % SST, rows = (nb - ch * SKC2 < SKC2) ? nb - ch * SKC2 : SKC2;
+            double *As = ring + (size_t)st * SYRK_STAGE, *Bs = As + SKC2 * SLDA;
+            if (ch >= SST) plba_mbar_wait(&empty[st], (unsigned)((ch / SST - 1) & 1));      // every warp has finished chunk ch - SST
+            const int r = lane & 15;
+            if (r >= rows) {
+                // rows past the end of the panel (its last chunk only) are zeros: plain stores, released to the consumers by lane 0's arrive below
+                if (lane < 16) { for (int c = 0; c < STM; c++) As[(size_t)r * SLDA + c] = 0.0; }
+                else { for (int c = 0; c < STN; c++) Bs[(size_t)r * SLDB + c] = 0.0; }
+            }
+            __syncwarp();
+            if (lane == 0) plba_mbar_expect_tx(&full[st], (unsigned)rows * (a_bytes + b_bytes));
+            __syncwarp();
+            const double *src = Sw + (size_t)(k0 + ch * SKC2 + r) * n;
+            if (r < rows) {
+                if (lane < 16) plba_bulk_g2s(As + (size_t)r * SLDA, src + i0, a_bytes, &full[st]);
+                else plba_bulk_g2s(Bs + (size_t)r * SLDB, src + j0, b_bytes, &full[st]);
+            }
+        }
+    };
+#else
     auto load_chunk = [&](int ch) {
         if (ch < nchunk) {
             double *As = ring + (size_t)(ch % SST) * SYRK_STAGE, *Bs = As + SKC2 * SLDA;
@@ -670,6 +721,7 @@ PLBA_KERNEL void PLBA_BOUNDS(256, 2) k_syrk_dmma(const DevP *Pp, double *Sw, int
         }
         plba_cp_async_commit();                                // (an empty group past the last chunk keeps the wait count uniform)
     };
+#endif
     load_chunk(0); load_chunk(1); load_chunk(2);
     // the C tile is read only in the epilogue, ~10 us from now: pull its lines into L2 meanwhile (the trailing matrix does not fit L2)
 #pragma unroll
@@ -678,9 +730,13 @@ PLBA_KERNEL void PLBA_BOUNDS(256, 2) k_syrk_dmma(const DevP *Pp, double *Sw, int
         if (r < n && cb < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(Sw + (size_t)r * n + cb));
     }
     for (int ch = 0; ch < nchunk; ch++) {
+#if PLBA_SYRK_TMA
+        plba_mbar_wait(&full[ch % SST], (unsigned)((ch / SST) & 1));      // chunk ch has landed (all its bytes)
+#else
         plba_cp_async_wait<2>();                               // chunk ch has landed (this thread's copies); the barrier makes it everyone's
-        __syncthreads();                                       // ... and says that every warp is done with chunk ch - 1, whose stage is refilled now
+        __syncthreads();                                       // every warp is done with chunk ch - 1, whose stage is refilled now
         load_chunk(ch + 3);
+#endif
         const double *Ac = ring + (size_t)(ch % SST) * SYRK_STAGE, *Bc = Ac + SKC2 * SLDA;
 #pragma unroll
         for (int kk = 0; kk < SKC2; kk += 4) {
@@ -696,6 +752,11 @@ PLBA_KERNEL void PLBA_BOUNDS(256, 2) k_syrk_dmma(const DevP *Pp, double *Sw, int
 #pragma unroll
                 for (int b = 0; b < 4; b++) plba_dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
         }
+#if PLBA_SYRK_TMA
+        __syncwarp();
+        if (lane == 0) plba_mbar_arrive(&empty[ch % SST]);     // this warp is done with the stage
+        load_chunk(ch + 3);                                    // (producer warp: refill the stage of chunk ch - 1 once all warps have released it)
+#endif
     }
     // epilogue: C -= acc (upper triangle only); two rows of four fragments (eight 16-byte loads) are in flight per thread
 #pragma unroll
