@@ -127,6 +127,8 @@ struct plba_handle_s {
     cudaEvent_t ev[8]{};
     cudaStream_t stream_panel = nullptr; cudaEvent_t ev_la[2]{};   // dense tiled Cholesky: the look-ahead panel runs on a stream of its own
     bool no_lookahead = false;                                     // PLBA_NO_LOOKAHEAD=1 (A/B runs)
+    int dense_group = 0;                                           // panels per trailing update of the dense tiled Cholesky (PLBA_DENSE_GROUP; 0 = by size)
+    bool dense_k1 = false;                                         // PLBA_DENSE_K1=1: one trailing update per panel instead of per panel pair (A/B runs)
     cudaEvent_t ev_h2d = nullptr; bool h2d_pending = false;   // recorded after the H2D copies of an upload: the next upload waits for it before it rewrites the pinned staging
     bool detail_timing = false, no_graph = false;
     int grid_chunks = 296, grid_solve = 148;
@@ -376,6 +378,10 @@ int plba_create(int32_t device, void *stream, plba_handle *out) {
         for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&h->ev_la[i], cudaEventDisableTiming);
         const char *nl = std::getenv("PLBA_NO_LOOKAHEAD");
         h->no_lookahead = nl && nl[0] == '1';
+        const char *k1 = std::getenv("PLBA_DENSE_K1");
+        h->dense_k1 = k1 && k1[0] == '1';
+        const char *dg = std::getenv("PLBA_DENSE_GROUP");
+        if (dg && std::atoi(dg) >= 1 && std::atoi(dg) <= 8) h->dense_group = std::atoi(dg);
     }
 #endif
     *out = h;
@@ -683,21 +689,57 @@ static void launch_solve(plba_handle h) {
             h->timing.n_launches += 2;
             if (lo < n) { PLBA_LAUNCH(k_rhs_update, dim3((n - lo + 255) / 256, (nb + RHS_ROWS - 1) / RHS_ROWS), dim3(256), 0, st, Pp, w, k0, nb); h->timing.n_launches++; }
         };
+        auto launch_syrk = [&](cudaStream_t st, int k0, int nb, int lo, int tr0, int tr1, int rmax) {
+            const int g = syrk_tiles(n - lo, tr0, tr1);
+            if (g > 0) { PLBA_LAUNCH(k_syrk_dmma, dim3(g), dim3(256), syrk_dmma_smem(), st, Pp, Sw, n, k0, nb, lo, tr0, rmax); h->timing.n_launches++; }
+        };
         PLBA_LAUNCH(k_rhs_init, grid1(n, 256), dim3(256), 0, sm, Pp, w); h->timing.n_launches++;
         launch_panel(sm, 0);
-        for (int k0 = 0; k0 < n; k0 += NBK) {
-            const int nb = std::min((int)NBK, n - k0), lo = k0 + nb;
-            if (lo >= n) break;
-            const int TM = (n - lo + STM - 1) / STM;
-            const int ga = syrk_tiles(n - lo, 0, 1), gb = syrk_tiles(n - lo, 1, TM);
-            PLBA_LAUNCH(k_syrk_dmma, dim3(ga), dim3(256), syrk_dmma_smem(), sm, Pp, Sw, n, k0, nb, lo, 0); h->timing.n_launches++;
+        if (h->dense_k1) {
+            // first version of the look-ahead (A/B: PLBA_DENSE_K1=1): every panel updates the whole trailing matrix on its own (K = 96 per visit of a tile)
+            for (int k0 = 0; k0 < n; k0 += NBK) {
+                const int nb = std::min((int)NBK, n - k0), lo = k0 + nb;
+                if (lo >= n) break;
+                const int TM = (n - lo + STM - 1) / STM;
+                launch_syrk(sm, k0, nb, lo, 0, 1, n);
 #ifndef PLBA_HOST_EMU
-            if (la) { cudaEventRecord(h->ev_la[0], sm); cudaStreamWaitEvent(sp, h->ev_la[0], 0); }
+                if (la) { cudaEventRecord(h->ev_la[0], sm); cudaStreamWaitEvent(sp, h->ev_la[0], 0); }
 #endif
-            if (gb > 0) { PLBA_LAUNCH(k_syrk_dmma, dim3(gb), dim3(256), syrk_dmma_smem(), sm, Pp, Sw, n, k0, nb, lo, 1); h->timing.n_launches++; }
-            launch_panel(sp, lo);
+                launch_syrk(sm, k0, nb, lo, 1, TM, n);
+                launch_panel(sp, lo);
 #ifndef PLBA_HOST_EMU
-            if (la) { cudaEventRecord(h->ev_la[1], sp); cudaStreamWaitEvent(sm, h->ev_la[1], 0); }
+                if (la) { cudaEventRecord(h->ev_la[1], sp); cudaStreamWaitEvent(sm, h->ev_la[1], 0); }
+#endif
+            }
+        } else {
+            // PANEL GROUPS of G: inside a group a panel updates only the rows of the group's remaining panels (<= 96 (G - 1) rows, K = 96);
+            // the trailing matrix right of / below the group is visited ONCE per group with K = 96 G — 1 / G of the read-modify-write
+            // traffic and of the pipeline fills of the C tiles.  Look-ahead: the tile rows that hold the next group go first, then the next
+            // group (its panels and their in-group updates) runs on the panel stream under the rest of the update, which touches later rows only.
+            const int G = h->dense_group > 0 ? h->dense_group : (n >= 4800 ? 3 : 2);      // measured at n = 12 000: G = 1 30.9 ms, 2 28.8, 3 28.3, 4 28.5, 6 28.7; n = 1 200: 2 is best
+            cudaStream_t pw = sm;                                   // stream of the current group's panel work (the first group has nothing to hide under)
+            for (int kG = 0; kG < n; kG += G * NBK) {
+                const int gEnd = std::min(n, kG + G * NBK);
+                for (int k0 = kG; k0 < gEnd; k0 += NBK) {
+                    if (k0 > kG) launch_panel(pw, k0);              // (the group's first panel is already in flight: launched before the loop / at the end of the previous iteration)
+                    const int lo = k0 + NBK;
+                    if (lo < gEnd) launch_syrk(pw, k0, NBK, lo, 0, (gEnd - lo + STM - 1) / STM, gEnd);      // rows of the group's remaining panels only
+                }
+#ifndef PLBA_HOST_EMU
+                if (pw != sm) { cudaEventRecord(h->ev_la[1], pw); cudaStreamWaitEvent(sm, h->ev_la[1], 0); }
+#endif
+                if (gEnd >= n) break;
+                const int TM = (n - gEnd + STM - 1) / STM, TA = std::min(TM, (std::min(G * NBK, n - gEnd) + STM - 1) / STM);
+                launch_syrk(sm, kG, gEnd - kG, gEnd, 0, TA, n);     // the tile rows of the next group
+#ifndef PLBA_HOST_EMU
+                if (la) { cudaEventRecord(h->ev_la[0], sm); cudaStreamWaitEvent(sp, h->ev_la[0], 0); }
+#endif
+                launch_syrk(sm, kG, gEnd - kG, gEnd, TA, TM, n);
+                pw = sp;
+                launch_panel(pw, gEnd);                             // first panel of the next group
+            }
+#ifndef PLBA_HOST_EMU
+            if (pw != sm) { cudaEventRecord(h->ev_la[1], pw); cudaStreamWaitEvent(sm, h->ev_la[1], 0); }      // join (the last panel ran on the panel stream)
 #endif
         }
         // backward substitution, column-oriented: solve block k (one CTA, the 96 x 96 triangle), then take it out of every row above

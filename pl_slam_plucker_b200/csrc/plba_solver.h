@@ -638,7 +638,7 @@ static inline int syrk_tiles(int m, int tr0, int tr1) {
     return c;
 }
 // A_ij -= U_ki^T U_kj for the trailing tiles of step k; lo = first trailing row / column
-PLBA_KERNEL void PLBA_BOUNDS(256, 2) k_syrk_dmma(const DevP *Pp, double *Sw, int n, int k0, int nb, int lo, int tr0) {
+PLBA_KERNEL void PLBA_BOUNDS(256, 2) k_syrk_dmma(const DevP *Pp, double *Sw, int n, int k0, int nb, int lo, int tr0, int rmax) {      // rows >= rmax are left alone
     PLBA_SMEM(raw);
     PLBA_COUNT_LAUNCH(Pp);            // (matrix pointer and order are kernel arguments: no parameter block, no dependent loads before the first copy)
     const int TN = (n - lo + STN - 1) / STN;
@@ -651,7 +651,7 @@ PLBA_KERNEL void PLBA_BOUNDS(256, 2) k_syrk_dmma(const DevP *Pp, double *Sw, int
     PHASE_BEGIN     // plain loops on the host (the MMA fragments exist only on the GPU)
         for (int idx = tid; idx < STM * STN; idx += PLBA_NT) {
             const int r = i0 + idx / STN, c = j0 + idx % STN;
-            if (r >= n || c >= n || c < r) continue;
+            if (r >= rmax || c >= n || c < r) continue;
             double sum = 0.0;
             for (int q = 0; q < nb; q++) sum += Sw[(size_t)(k0 + q) * n + r] * Sw[(size_t)(k0 + q) * n + c];
             Sw[(size_t)r * n + c] -= sum;
@@ -727,7 +727,7 @@ PLBA_KERNEL void PLBA_BOUNDS(256, 2) k_syrk_dmma(const DevP *Pp, double *Sw, int
 #pragma unroll
     for (int a = 0; a < 4; a++) {
         const int r = i0 + wm * 32 + a * 8 + (lane >> 2), cb = j0 + wn * 32 + 8 * (lane & 3);      // the row's 32 columns as four 64-byte pieces
-        if (r < n && cb < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(Sw + (size_t)r * n + cb));
+        if (r < rmax && cb < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(Sw + (size_t)r * n + cb));
     }
     for (int ch = 0; ch < nchunk; ch++) {
 #if PLBA_SYRK_TMA
@@ -766,7 +766,7 @@ PLBA_KERNEL void PLBA_BOUNDS(256, 2) k_syrk_dmma(const DevP *Pp, double *Sw, int
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int r = i0 + wm * 32 + (a2 + h) * 8 + (lane >> 2), cb = j0 + wn * 32 + 2 * (lane & 3);
-            fast[h] = (r < n && cb >= r && cb + 24 + 1 < n);      // the common case: the lane's four 16-byte pieces lie inside the upper triangle
+            fast[h] = (r < rmax && cb >= r && cb + 24 + 1 < n);      // the common case: the lane's four 16-byte pieces lie inside the upper triangle
             if (fast[h]) {
 #pragma unroll
                 for (int b = 0; b < 4; b++) v[h][b] = *(const plba_d2 *)(Sw + (size_t)r * n + cb + b * 8);
@@ -775,7 +775,7 @@ PLBA_KERNEL void PLBA_BOUNDS(256, 2) k_syrk_dmma(const DevP *Pp, double *Sw, int
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int a = a2 + h, r = i0 + wm * 32 + a * 8 + (lane >> 2), cb = j0 + wn * 32 + 2 * (lane & 3);
-            if (r >= n) continue;
+            if (r >= rmax) continue;
             double *row = Sw + (size_t)r * n;
             if (fast[h]) {
 #pragma unroll
