@@ -70,6 +70,9 @@ enum { PLBA_MAX_RANKS = 16 };
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return PLBA_E_CUDA; } } while (0)
 
+// host loops of upload / download run in parallel above these sizes (a parallel region costs tens of microseconds: a config-2 window of
+// 45 000 observations stays serial, config 4 with 1.15 M observations does not)
+enum { PAR_LM = 40000, PAR_OBS = 200000 };
 struct WinInfo { int n_kf, n_free, n_pt, n_ls, n_pobs, n_lobs, kf0, slot0, pt0, ls0, po0, lo0; };
 
 // bump allocator over a byte range (device arena or pinned staging): 256-byte aligned carve-outs
@@ -197,12 +200,12 @@ static int validate_problem(const plba_problem &p, const plba_options &o, std::s
     }
     if (nfree != p.n_free) { err = "n_free does not match kf_slot"; return PLBA_E_ARG; }
     int bad_p = 0, bad_l = 0;      // 1 = index out of range, 2 = not landmark-major
-#pragma omp parallel for schedule(static) reduction(max : bad_p) if (p.n_pobs > 1000000)
+#pragma omp parallel for schedule(static) reduction(max : bad_p) if (p.n_pobs > PAR_OBS)
     for (int i = 0; i < p.n_pobs; i++) {
         if (p.po_lm[i] < 0 || p.po_lm[i] >= p.n_pt || p.po_kf[i] < 0 || p.po_kf[i] >= p.n_kf) bad_p = bad_p > 1 ? bad_p : 1;
         else if (i && p.po_lm[i] < p.po_lm[i - 1]) bad_p = 2;
     }
-#pragma omp parallel for schedule(static) reduction(max : bad_l) if (p.n_lobs > 1000000)
+#pragma omp parallel for schedule(static) reduction(max : bad_l) if (p.n_lobs > PAR_OBS)
     for (int i = 0; i < p.n_lobs; i++) {
         if (p.lo_lm[i] < 0 || p.lo_lm[i] >= p.n_ls || p.lo_kf[i] < 0 || p.lo_kf[i] >= p.n_kf) bad_l = bad_l > 1 ? bad_l : 1;
         else if (i && p.lo_lm[i] < p.lo_lm[i - 1]) bad_l = 2;
@@ -219,7 +222,7 @@ struct ClassLayout {
     std::vector<int> group;      // signature group of each OLD landmark (equal group <=> identical keyframe sequence); empty = not grouped
 };
 static void signature_order(int n_lm, int n_obs, const int32_t *lm, const int32_t *kf, bool permute, ClassLayout &L) {
-    const bool par = n_obs > 1000000;      // one large window: the loops below run in parallel (a region costs more than a small window's whole sort)
+    const bool par = n_obs > PAR_OBS;      // one large window: the loops below run in parallel (a region costs more than a small window's whole sort)
     L.optr.assign(n_lm + 1, n_obs);
     // lm[] is non-decreasing (validated): optr[l] = first observation whose landmark is >= l
 #pragma omp parallel for schedule(static) if (par)
@@ -941,7 +944,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
             // windows: 12.5 M entries at config 5), (3) the runs (serial, index compares only)
             int ob = ob0;
             for (int nl_i = 0; nl_i < nl; nl_i++) { const int old = L.perm[nl_i]; ptr[lm0 + nl_i] = ob; ob += L.optr[old + 1] - L.optr[old]; }
-#pragma omp parallel for schedule(static) if (nl > 200000)
+#pragma omp parallel for schedule(static) if (nl > PAR_LM)
             for (int nl_i = 0; nl_i < nl; nl_i++) {
                 const int old = L.perm[nl_i], a = L.optr[old], b = L.optr[old + 1];
                 perm[lm0 + nl_i] = lm0 + old;
@@ -1181,6 +1184,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     if (!fp_ls.empty()) std::memcpy(hb + i_fp_ls, fp_ls.data(), sizeof(int) * fp_ls.size());
     if (!wi_pt.empty()) std::memcpy(hb + i_wi_pt, wi_pt.data(), sizeof(WItem) * wi_pt.size());
     if (!wi_ls.empty()) std::memcpy(hb + i_wi_ls, wi_ls.data(), sizeof(WItem) * wi_ls.size());
+    HOSTPROF("fl.tables");
     const bool par_lm = (n <= 8);       // one (or few) big windows: parallel over landmarks; batches: parallel over windows
 #pragma omp parallel for schedule(dynamic, 4) if (!par_lm)
     for (int w = 0; w < n; w++) {
@@ -1197,13 +1201,14 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
                 else log_se3(p.kf_T_wc + 12 * (size_t)k, &X0[(size_t)(wi.slot0 + s) * 6]);
             }
         }
-#pragma omp parallel for schedule(static) if (par_lm && p.n_pt > 200000)
+        if (n == 1) HOSTPROF("fl.kf");
+#pragma omp parallel for schedule(static) if (par_lm && p.n_pt > PAR_LM)
         for (int g = wi.pt0; g < wi.pt0 + p.n_pt; g++) {
             const int old = h->pt_perm[g] - wi.pt0;
             pt_win[g] = w;
             for (int i = 0; i < 3; i++) pts0[(size_t)3 * g + i] = p.pt_xyz[(size_t)3 * old + i];
         }
-#pragma omp parallel for schedule(static) if (par_lm && p.n_ls > 200000)
+#pragma omp parallel for schedule(static) if (par_lm && p.n_ls > PAR_LM)
         for (int g = wi.ls0; g < wi.ls0 + p.n_ls; g++) {
             const int old = h->ls_perm[g] - wi.ls0;
             ls_win[g] = w;
@@ -1213,27 +1218,36 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
                 for (int i = 0; i < 6; i++) lmap[(size_t)6 * g + i] = p.ls_plk[(size_t)6 * old + i];
             }
         }
-#pragma omp parallel for schedule(static) if (par_lm && p.n_pt > 200000)
+        if (n == 1) HOSTPROF("fl.lm");
+#pragma omp parallel for schedule(static) if (par_lm && p.n_pt > PAR_LM)
         for (int g = wi.pt0; g < wi.pt0 + p.n_pt; g++) {
             // the observations of a landmark are one contiguous run in the caller's arrays too: copy runs, not elements
             const int o0 = pt_ptr[g], no = pt_ptr[g + 1] - o0;
             if (no == 0) continue;
             const int i0 = h->po_perm[o0] - wi.po0;
-            std::memcpy(po_uv + (size_t)2 * o0, p.po_uv + (size_t)2 * i0, sizeof(double) * 2 * no);
-            for (int j = 0; j < no; j++) { po_kf[o0 + j] = wi.kf0 + p.po_kf[i0 + j]; po_lm[o0 + j] = g; }
-            if (p.po_sig2) for (int j = 0; j < no; j++) po_om[o0 + j] = (double)(float)(1.0 / p.po_sig2[i0 + j]);           // const float& invSigma2 (:6009, Q13)
-            else for (int j = 0; j < no; j++) po_om[o0 + j] = 1.0;
+            if (g + 8 < wi.pt0 + p.n_pt) {      // the caller's arrays are read in signature order, i.e. at scattered places: pull the run of landmark g + 8 in now
+                const int on = pt_ptr[g + 8];
+                if (on < wi.po0 + p.n_pobs) { const int in = h->po_perm[on] - wi.po0; __builtin_prefetch(p.po_uv + (size_t)2 * in); __builtin_prefetch(p.po_uv + (size_t)2 * in + 8); __builtin_prefetch(p.po_kf + in); }
+            }
+            // one fused loop per run (tracks hold ~5 observations: a memcpy call per array costs more than the copy)
+            const double *suv = p.po_uv + (size_t)2 * i0; double *duv = po_uv + (size_t)2 * o0;
+            const int32_t *skf = p.po_kf + i0; int *dkf = po_kf + o0, *dlm = po_lm + o0; double *dom = po_om + o0;
+            if (p.po_sig2) for (int j = 0; j < no; j++) { duv[2 * j] = suv[2 * j]; duv[2 * j + 1] = suv[2 * j + 1]; dkf[j] = wi.kf0 + skf[j]; dlm[j] = g; dom[j] = (double)(float)(1.0 / p.po_sig2[i0 + j]); }   // const float& invSigma2 (:6009, Q13)
+            else for (int j = 0; j < no; j++) { duv[2 * j] = suv[2 * j]; duv[2 * j + 1] = suv[2 * j + 1]; dkf[j] = wi.kf0 + skf[j]; dlm[j] = g; dom[j] = 1.0; }
         }
-#pragma omp parallel for schedule(static) if (par_lm && p.n_ls > 200000)
+#pragma omp parallel for schedule(static) if (par_lm && p.n_ls > PAR_LM)
         for (int g = wi.ls0; g < wi.ls0 + p.n_ls; g++) {
             const int o0 = ls_ptr[g], no = ls_ptr[g + 1] - o0;
             if (no == 0) continue;
             const int i0 = h->lo_perm[o0] - wi.lo0;
-            std::memcpy(lo_ab + (size_t)4 * o0, p.lo_ab + (size_t)4 * i0, sizeof(double) * 4 * no);
-            for (int j = 0; j < no; j++) { lo_kf[o0 + j] = wi.kf0 + p.lo_kf[i0 + j]; lo_lm[o0 + j] = g; }
-            if (p.lo_sig2) for (int j = 0; j < no; j++) lo_om[o0 + j] = (double)(float)(1.0 / p.lo_sig2[i0 + j]);
-            else for (int j = 0; j < no; j++) lo_om[o0 + j] = 1.0;
+            const double *sab = p.lo_ab + (size_t)4 * i0; double *dab = lo_ab + (size_t)4 * o0;
+            const int32_t *skf = p.lo_kf + i0; int *dkf = lo_kf + o0, *dlm = lo_lm + o0; double *dom = lo_om + o0;
+            for (int j = 0; j < no; j++) {
+                dab[4 * j] = sab[4 * j]; dab[4 * j + 1] = sab[4 * j + 1]; dab[4 * j + 2] = sab[4 * j + 2]; dab[4 * j + 3] = sab[4 * j + 3];
+                dkf[j] = wi.kf0 + skf[j]; dlm[j] = g; dom[j] = p.lo_sig2 ? (double)(float)(1.0 / p.lo_sig2[i0 + j]) : 1.0;
+            }
         }
+        if (n == 1) HOSTPROF("fl.obs");
         WinCtrl c{};
         c.need_init = 1; c.apply = 1; c.ni = 2.0; c.err_prev = 999999999.9; c.n_lm_pt = p.n_pt; c.n_lm_ls = p.n_ls; c.n_obs = p.n_pobs + p.n_lobs;
         if (p.n_pobs + p.n_lobs == 0) c.done = 1;      // nothing to do (src/mapHandler.cpp:1496-1500)
@@ -1480,14 +1494,14 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
         if (r.kf_T_wc) for (int i = 0; i < 12 * wi.n_kf; i++) r.kf_T_wc[i] = T[(size_t)12 * wi.kf0 + i];
         if (r.x_pose) for (int i = 0; i < 6 * wi.n_free; i++) r.x_pose[i] = X[(size_t)6 * wi.slot0 + i];
         const bool par_lm = (n <= 8);       // one (or few) big windows: parallel over landmarks / observations; batches: parallel over windows
-#pragma omp parallel for schedule(static) if (par_lm && wi.n_pt > 200000)
+#pragma omp parallel for schedule(static) if (par_lm && wi.n_pt > PAR_LM)
         for (int g = wi.pt0; g < wi.pt0 + wi.n_pt; g++) {
             const int old = h->pt_perm[g] - wi.pt0;
             if (r.pt_xyz) for (int i = 0; i < 3; i++) r.pt_xyz[(size_t)3 * old + i] = pt[(size_t)3 * g + i];
             // inlier rule of the hand-LM write-back (src/mapHandler.cpp:2858-2860, 2871-2873); profile G leaves it to the final chi2 test
             if (r.pt_inlier) { double d2 = 0; for (int i = 0; i < 3; i++) { const double d = pt[(size_t)3 * g + i] - pt0[(size_t)3 * g + i]; d2 += d * d; } r.pt_inlier[old] = (!G && !P.gba && std::sqrt(d2) > 0.01) ? 0 : 1; }
         }
-#pragma omp parallel for schedule(static) if (par_lm && wi.n_ls > 200000)
+#pragma omp parallel for schedule(static) if (par_lm && wi.n_ls > PAR_LM)
         for (int g = wi.ls0; g < wi.ls0 + wi.n_ls; g++) {
             const int old = h->ls_perm[g] - wi.ls0;
             if (ld == 4) {
@@ -1504,13 +1518,13 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
             }
         }
         if (G) {
-#pragma omp parallel for schedule(static) if (par_lm && wi.n_pobs > 1000000)
+#pragma omp parallel for schedule(static) if (par_lm && wi.n_pobs > PAR_OBS)
             for (int o = wi.po0; o < wi.po0 + wi.n_pobs; o++) {
                 const int i = h->po_perm[o] - wi.po0;
                 if (r.po_chi2) r.po_chi2[i] = pchi[o];
                 if (r.po_flags) r.po_flags[i] = pf[o];
             }
-#pragma omp parallel for schedule(static) if (par_lm && wi.n_lobs > 1000000)
+#pragma omp parallel for schedule(static) if (par_lm && wi.n_lobs > PAR_OBS)
             for (int o = wi.lo0; o < wi.lo0 + wi.n_lobs; o++) {
                 const int i = h->lo_perm[o] - wi.lo0;
                 if (r.lo_chi2) r.lo_chi2[i] = lchi[o];
