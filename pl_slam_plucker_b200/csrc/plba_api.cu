@@ -686,7 +686,7 @@ static void launch_solve(plba_handle h) {
         double *Sw = P.S + h->win_S_off[w], *xw = P.xp + (size_t)6 * h->wins[w].slot0;      // y (forward substitution) and then x live in xp
         auto launch_panel = [&](cudaStream_t st, int k0) {
             const int nb = std::min((int)NBK, n - k0), lo = k0 + nb;
-            PLBA_LAUNCH(k_potrf_block, dim3(1), dim3(256), potrf_block_smem(), st, Pp, w, k0, nb);
+            PLBA_LAUNCH(k_potrf_block, dim3(1), dim3(PB_NT), potrf_block_smem(), st, Pp, Sw, n, P.ctrl + w, (const double *)(P.hpp_diag + (size_t)6 * h->wins[w].slot0), P.profile == PLBA_PROFILE_G ? 1 : 0, k0, nb);
             // columns right of the block + the right-hand side column
             PLBA_LAUNCH(k_trsm_block, dim3((n - lo + 1 + TRSM_COLS - 1) / TRSM_COLS), dim3(TRSM_COLS), trsm_block_smem(), st, Pp, Sw, n, xw, k0, nb);
             h->timing.n_launches += 2;

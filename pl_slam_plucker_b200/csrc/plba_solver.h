@@ -459,45 +459,140 @@ PLBA_D void plba_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "
 template <int N> PLBA_D void plba_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
 
-static inline size_t potrf_block_smem() { return sizeof(double) * ((size_t)NBK * (NBK + 1) + NBK + 21 * (NBK / 6) + 6 * 264 + 16); }
-PLBA_KERNEL void k_potrf_block(const DevP *Pp, int w, int k0, int nb) {
+// Diagonal block of a step (96 x 96 = 16 x 16 pose blocks): the register-resident block Cholesky of k_solve_small — one thread per lower
+// 6 x 6 block, which stays in that thread's registers from the load to the write-back; per block column two block barriers: A the threads
+// of column kb solve against L_kk and publish their block, B every thread right of it applies M_ij -= X_i X_j^T and the diagonal thread of
+// column kb + 1 factors its block at once.  (The first version ran the left-looking shared-memory panels of round 1: 44 us per step on
+// the factorisation's critical path.)
+enum { PB_NT = 160, PB_XLD = 37 };
+static inline size_t potrf_block_smem() { return sizeof(double) * ((size_t)(NBK / 6) * PB_XLD + 32) + 16; }
+PLBA_KERNEL void PLBA_BOUNDS(PB_NT, 1) k_potrf_block(const DevP *Pp, double *Sw, int n, WinCtrl *ctl, const double *hd, int additive, int k0, int nb) {
     PLBA_SMEM(raw);
-    PLBA_PARAMS(P, Pp);
-    WinCtrl &ctl = P.ctrl[w];
-    const int n = 6 * P.win_nfree[w], slot0 = P.win_slot0[w], ldm = nb + 1;
-    double *Sw = P.S + P.win_S_off[w];
-    double *M = (double *)raw, *dinv = M + (size_t)NBK * (NBK + 1), *Lblk = dinv + NBK, *part = Lblk + 21 * (NBK / 6);
-    int *fail = (int *)(part + 6 * 264);
+    PLBA_COUNT_LAUNCH(Pp);
+    double *Xp = (double *)raw, *Lc = Xp + (size_t)(NBK / 6) * PB_XLD;      // published X blocks of the current column; L_kk (21) + 1 / diag (6)
+    int *fail = (int *)(Lc + 32);
+    const int nbk = nb / 6;
+    THR_ARR(double, blk, 36);
+    THR_VAR(int, bi); THR_VAR(int, bj); THR_VAR(int, act);
     PHASE_BEGIN
+        THR_BIND(blk); THR_BIND(bi); THR_BIND(bj); THR_BIND(act);
         if (tid == 0) *fail = 0;
-        // the block travels as asynchronous 8-byte copies straight into its (transposed) place: all 36 of a thread are in flight at once
-#ifndef PLBA_HOST_EMU
-        for (int idx = tid; idx < nb * nb; idx += PLBA_NT) {
-            const int r = idx / nb, c = idx - r * nb;
-            if (c >= r) plba_cp_async8(&M[(size_t)c * ldm + r], &Sw[(size_t)(k0 + r) * n + k0 + c], true);      // lower (c,r)
+        act = 0; bi = 0; bj = 0;
+        int j = nbk, rem = 0;
+        if (tid < 32) { if (tid < nbk) { j = tid; rem = 0; } }                 // warp 0: the diagonal blocks
+        else { j = 0; rem = tid - 32; while (j < nbk - 1 && rem >= nbk - 1 - j) { rem -= nbk - 1 - j; j++; } if (j >= nbk - 1) j = nbk; else rem += 1; }
+        if (j < nbk) {
+            act = 1; bj = j; bi = j + rem;
+            // lower block (bi, bj) = transpose of the stored upper block (bj, bi); 128-bit loads (n, k0, 6 bi are even)
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                const plba_d2 *row = (const plba_d2 *)(Sw + (size_t)(k0 + 6 * bj + c) * n + k0 + 6 * bi);
+#pragma unroll
+                for (int r2 = 0; r2 < 3; r2++) { const plba_d2 v = row[r2]; blk[(2 * r2) * 6 + c] = v.x; blk[(2 * r2 + 1) * 6 + c] = v.y; }
+            }
+            if (bi == bj) {
+                const double lambda = ctl->lambda;
+#pragma unroll
+                for (int c = 0; c < 6; c++) blk[c * 6 + c] += additive ? lambda : lambda * hd[k0 + 6 * bj + c];      // g2o setLambda: additive; hand LM: H_ii *= (1 + lambda)
+                if (bj == 0) {
+                    double inv[6];
+                    if (!chol6_inplace(blk, inv)) *fail = 1;
+#pragma unroll
+                    for (int r = 0; r < 6; r++) {
+#pragma unroll
+                        for (int c = 0; c <= r; c++) Lc[r * (r + 1) / 2 + c] = blk[r * 6 + c];
+                    }
+#pragma unroll
+                    for (int c = 0; c < 6; c++) Lc[21 + c] = inv[c];
+                }
+            }
         }
-        plba_cp_async_commit(); plba_cp_async_wait<0>();
-#else
-        for (int idx = tid; idx < nb * nb; idx += PLBA_NT) {
-            const int r = idx / nb, c = idx - r * nb;
-            if (c >= r) M[(size_t)c * ldm + r] = Sw[(size_t)(k0 + r) * n + k0 + c];
-        }
-#endif
     PHASE_END
+    for (int kb = 0; kb < nbk; kb++) {
+        PHASE_BEGIN
+            THR_BIND(blk); THR_BIND(bi); THR_BIND(bj); THR_BIND(act);
+            if (act && bj == kb && bi > kb) {
+                double L[21], inv[6];
+#pragma unroll
+                for (int i = 0; i < 21; i++) L[i] = Lc[i];
+#pragma unroll
+                for (int i = 0; i < 6; i++) inv[i] = Lc[21 + i];
+#pragma unroll
+                for (int c = 0; c < 6; c++) {         // X = M L_kk^-T, column sweeps over all six rows at once
+#pragma unroll
+                    for (int r = 0; r < 6; r++) blk[r * 6 + c] *= inv[c];
+#pragma unroll
+                    for (int m = c + 1; m < 6; m++) {
+#pragma unroll
+                        for (int r = 0; r < 6; r++) blk[r * 6 + m] -= blk[r * 6 + c] * L[m * (m + 1) / 2 + c];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 36; i++) Xp[bi * PB_XLD + i] = blk[i];
+            }
+        PHASE_END
+        PHASE_BEGIN
+            THR_BIND(blk); THR_BIND(bi); THR_BIND(bj); THR_BIND(act);
+            if (act && bj > kb) {
+                double Xj[36];
+#pragma unroll
+                for (int i = 0; i < 36; i++) Xj[i] = Xp[bj * PB_XLD + i];
+                if (bi != bj) {
+#pragma unroll
+                    for (int r = 0; r < 6; r++) {
+                        double xi[6];
+#pragma unroll
+                        for (int m = 0; m < 6; m++) xi[m] = Xp[bi * PB_XLD + r * 6 + m];
+#pragma unroll
+                        for (int c = 0; c < 6; c++) {
+                            double v = blk[r * 6 + c];
+#pragma unroll
+                            for (int m = 0; m < 6; m++) v -= xi[m] * Xj[c * 6 + m];
+                            blk[r * 6 + c] = v;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 6; r++) {       // diagonal block: its lower triangle only
+#pragma unroll
+                        for (int c = 0; c <= r; c++) {
+                            double v = blk[r * 6 + c];
+#pragma unroll
+                            for (int m = 0; m < 6; m++) v -= Xj[r * 6 + m] * Xj[c * 6 + m];
+                            blk[r * 6 + c] = v;
+                        }
+                    }
+                    if (bj == kb + 1) {                 // look-ahead: the next column's L_kk is ready when phase A(kb + 1) starts
+                        double inv[6];
+                        if (!chol6_inplace(blk, inv)) *fail = 1;
+#pragma unroll
+                        for (int r = 0; r < 6; r++) {
+#pragma unroll
+                            for (int c = 0; c <= r; c++) Lc[r * (r + 1) / 2 + c] = blk[r * 6 + c];
+                        }
+#pragma unroll
+                        for (int c = 0; c < 6; c++) Lc[21 + c] = inv[c];
+                    }
+                }
+            }
+        PHASE_END
+    }
     PHASE_BEGIN
-        if (tid < nb) M[(size_t)tid * ldm + tid] += (P.profile == PLBA_PROFILE_G) ? ctl.lambda : ctl.lambda * P.hpp_diag[(size_t)6 * slot0 + k0 + tid];
-    PHASE_END
-    chol_lower_panels(M, ldm, nb, nb - 1, dinv, Lblk, part, fail);
-    PHASE_BEGIN
-        for (int idx = tid; idx < nb * nb; idx += PLBA_NT) {
-            const int r = idx / nb, c = idx - r * nb;     // U[r][c] = L[c][r], c >= r
-            if (c < r) continue;
-            double v;
-            if (c / 6 == r / 6) { const int kb = r / 6, i = c - 6 * kb, j = r - 6 * kb; v = Lblk[kb * 21 + i * (i + 1) / 2 + j]; }
-            else v = M[(size_t)c * ldm + r];
-            Sw[(size_t)(k0 + r) * n + k0 + c] = v;
+        THR_BIND(blk); THR_BIND(bi); THR_BIND(bj); THR_BIND(act);
+        if (act) {                                      // U[6 bj + c][6 bi + r] = L[6 bi + r][6 bj + c]
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                double *row = Sw + (size_t)(k0 + 6 * bj + c) * n + k0 + 6 * bi;
+                if (bi != bj) {
+#pragma unroll
+                    for (int r2 = 0; r2 < 3; r2++) { plba_d2 v; v.x = blk[(2 * r2) * 6 + c]; v.y = blk[(2 * r2 + 1) * 6 + c]; ((plba_d2 *)row)[r2] = v; }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 6; r++) if (r >= c) row[r] = blk[r * 6 + c];
+                }
+            }
         }
-        if (tid == 0 && *fail) ctl.solve_fail = 1;
+        if (tid == 0 && *fail) ctl->solve_fail = 1;
     PHASE_END
 }
 
