@@ -106,6 +106,15 @@ template <> struct ObsLoad<LT_LINE_ORTH> {
 };
 template <> struct ObsLoad<LT_LINE_END> : ObsLoad<LT_LINE_ORTH> {};
 
+template <int N> PLBA_HD void wrec_ld(const double *p, double *r) {      // N even, p 16-byte aligned
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) { const plba_d2 v = ((const plba_d2 *)p)[i]; r[2 * i] = v.x; r[2 * i + 1] = v.y; }
+}
+template <int N> PLBA_HD void wrec_st(double *p, const double *r) {
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) { plba_d2 v; v.x = r[2 * i]; v.y = r[2 * i + 1]; ((plba_d2 *)p)[i] = v; }
+}
+
 // one observation -> scaled rows At = sqrt(w) J_pose, Bt = sqrt(w) J_lm, et = sqrt(w) e, in registers (same arithmetic as
 // obs_linearize; see there for the citations).  Returns false for an edge gated out of the active set (rows are zero).
 template <int PROF, int LT>
@@ -118,7 +127,9 @@ PLBA_HD bool obs_lin_w(const DevP &P, const WinCtrl &ctl, int o, int kf, const L
     if (PROF == PLBA_PROFILE_G) {
         if (ctl.stage == 1 && OA::lvl(P)[o]) active = false;
         if (active) {
-            const double *T = P.poseT[ctl.cur] + (size_t)12 * kf;
+            // the pose as six 128-bit loads (L1 hits, lanes of one keyframe share them): half the load instructions of twelve scalar reads
+            double T[12];
+            wrec_ld<12>(P.poseT[ctl.cur] + (size_t)12 * kf, T);
             if constexpr (LT == LT_POINT) {
                 g_point_lin(P.cam, T, lmd.Pw, ob.uv, e, A, B);
             } else if constexpr (LT == LT_LINE_ORTH) {
@@ -200,14 +211,6 @@ struct WRec {
            NACC = 18, NG = 3 };
     static PLBA_HD size_t bytes() { return sizeof(double) * STRIDE * 32 + sizeof(int) * 64; }
 };
-template <int N> PLBA_HD void wrec_ld(const double *p, double *r) {      // N even, p 16-byte aligned
-#pragma unroll
-    for (int i = 0; i < N / 2; i++) { const plba_d2 v = ((const plba_d2 *)p)[i]; r[2 * i] = v.x; r[2 * i + 1] = v.y; }
-}
-template <int N> PLBA_HD void wrec_st(double *p, const double *r) {
-#pragma unroll
-    for (int i = 0; i < N / 2; i++) { plba_d2 v; v.x = r[2 * i]; v.y = r[2 * i + 1]; ((plba_d2 *)p)[i] = v; }
-}
 
 // Schur task of a lane: pose pair (i <= j) of the free track positions x one COLUMN half of the 6x6 block (columns hcol .. hcol + 2).
 // Both halves need M = Ta B^T (4 D FMAs), but each computes only its three columns of M A_b and of the block: 60 FMAs per landmark
