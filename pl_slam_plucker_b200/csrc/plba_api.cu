@@ -131,6 +131,7 @@ struct plba_handle_s {
     cudaStream_t stream_panel = nullptr; cudaEvent_t ev_la[2]{};   // dense tiled Cholesky: the look-ahead panel runs on a stream of its own
     bool no_lookahead = false;                                     // PLBA_NO_LOOKAHEAD=1 (A/B runs)
     int dense_group = 0;                                           // panels per trailing update of the dense tiled Cholesky (PLBA_DENSE_GROUP; 0 = by size)
+    bool no_overlap = false;                                       // PLBA_NO_OVERLAP=1: solver and update kernel of a small window strictly one after the other (A/B runs)
     bool dense_k1 = false;                                         // PLBA_DENSE_K1=1: one trailing update per panel instead of per panel pair (A/B runs)
     cudaEvent_t ev_h2d = nullptr; bool h2d_pending = false;   // recorded after the H2D copies of an upload: the next upload waits for it before it rewrites the pinned staging
     bool detail_timing = false, no_graph = false;
@@ -381,6 +382,8 @@ int plba_create(int32_t device, void *stream, plba_handle *out) {
         for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&h->ev_la[i], cudaEventDisableTiming);
         const char *nl = std::getenv("PLBA_NO_LOOKAHEAD");
         h->no_lookahead = nl && nl[0] == '1';
+        const char *no = std::getenv("PLBA_NO_OVERLAP");
+        h->no_overlap = no && no[0] == '1';
         const char *k1 = std::getenv("PLBA_DENSE_K1");
         h->dense_k1 = k1 && k1[0] == '1';
         const char *dg = std::getenv("PLBA_DENSE_GROUP");
@@ -807,6 +810,18 @@ template <int PROF> static int build_graph(plba_handle h) {
     CK(add_kernel(prep, &n3, n2, (void *)k_lambda_init, dim3(h->n_sm), dim3(128), 0, a_p));
     CK(add_kernel(body, &m1, inode, f_asm, gc, bc, smc, a_m1));
     CK(add_kernel(body, &m2, m1, (void *)k_solve_small, dim3(h->grid_solve), dim3(SS_NT), solve_small_smem(), a_p));
+    // single small window, profile G, CTA-chunk kernels: the update kernel runs BESIDE the solver (programmatic edge: launched as soon as the
+    // solver's one CTA is resident) and waits for the solver's flag where it first needs x_p — its re-linearisation at the old state and the
+    // kernel boundary disappear from the trial's critical path.  PLBA_NO_OVERLAP=1 keeps the plain chain (A/B runs).
+    const bool overlap = (PROF == PLBA_PROFILE_G) && h->solve_class == 0 && !h->warp_path && !h->no_overlap;
+    int fl_ov = fl | KF_WAIT_SOLVE;
+    void *a_flov[2] = {(void *)&Pp, (void *)&fl_ov};
+    if (overlap) {
+        CK(add_kernel(body, &m3, nullptr, f_upd, gu, bc, smc, a_flov));
+        cudaGraphEdgeData ed{};
+        ed.from_port = cudaGraphKernelNodePortProgrammatic; ed.to_port = 0; ed.type = cudaGraphDependencyTypeProgrammatic;
+        CK(cudaGraphAddDependencies_v2(body, &m2, &m3, &ed, 1));
+    } else
     CK(add_kernel(body, &m3, m2, f_upd, gu, bc, smc, a_fl));
 #ifdef PLBA_GRAPH_TWO_TRIALS
     // a second LM trial inside the same WHILE iteration: the loop's per-iteration cost (evaluating the condition, re-launching the

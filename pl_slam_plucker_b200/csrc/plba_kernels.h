@@ -33,7 +33,7 @@ enum { LPRE_N = 17 };   // n(3) d(3) u1(3) u2(3) u3(3) w1 w2
 #define PLBA_SEG_MAX 8
 #endif
 enum { OC = PLBA_OC /* observations (= threads) per chunk */, LC = PLBA_OC / 2 /* landmarks per chunk */, SEG_MAX = PLBA_SEG_MAX /* landmarks per segment */ };
-enum { KF_FUSE_CONTROL = 1, KF_IN_GRAPH = 2 };   // kernel flags
+enum { KF_FUSE_CONTROL = 1, KF_IN_GRAPH = 2, KF_WAIT_SOLVE = 4 };   // kernel flags (KF_WAIT_SOLVE: the update kernel runs concurrently with k_solve_small, see k_update)
 #ifndef PLBA_CTAS_PER_SM
 #define PLBA_CTAS_PER_SM 2   // measured: 2 resident CTAs (128 registers, small spills) beat 1 CTA with 254 registers on C2, C4 and C5
 #endif
@@ -60,6 +60,7 @@ struct WinCtrl {
 enum { ACC_CHI_LIN = 0, ACC_ERR_PT = 1, ACC_ERR_LS = 2, ACC_CHI_NEW = 0, ACC_SCALE = 1, ACC_DX2 = 2, ACC_N = 8 };
 enum { CNT_DONE = 0, CNT_NEED_INIT = 1, CNT_GATE = 2, CNT_TRIALS = 3, CNT_TICKET = 4, CNT_ROUNDS = 5, CNT_PREPS = 6,
        CNT_WORK_PT = 8, CNT_WORK_LS = 9, CNT_WTICKET = 10 /* warp path: next work item of each landmark class, CTA exit ticket */,
+       CNT_SOLVE_DONE = 12 /* k_solve_small (single window) has published x_p and the trial poses: the update kernel that runs BESIDE it waits for this */,
        CNT_KLAUNCH = 11 /* kernels of the library that have started since the last reset: counted ON THE DEVICE (PLBA_PARAMS), so that launches inside the LM-loop graph are counted, not inferred */, CNT_N = 16 };
 
 struct DevP {
@@ -630,6 +631,7 @@ template <int PROF>
 PLBA_KERNEL void PLBA_BOUNDS(OC, PLBA_CTAS_PER_SM) k_assemble(const DevP *Pp, int mode) {
     if (mode == 0 && Pp->counters[CNT_NEED_INIT] == 0) { PLBA_COUNT_LAUNCH(Pp); return; }        // no window waits for its initial lambda (the counter only changes between launches)
     PLBA_PARAMS(P, Pp);
+    if (PLBA_BID == 0 && (int)PLBA_TID0 == 0) P.counters[CNT_SOLVE_DONE] = 0;      // (this launch lies between the update kernel that read the flag and the solver that sets it next)
     const int ntot = P.n_chunks_pt + P.n_chunks_ls;
     for (int c = PLBA_BID; c < ntot; c += PLBA_NB) {
         if (c < P.n_chunks_pt) { const Chunk ch = P.chunks_pt[c]; assemble_chunk<PROF, LT_POINT>(P, ch, mode); }
@@ -641,7 +643,7 @@ PLBA_KERNEL void PLBA_BOUNDS(OC, PLBA_CTAS_PER_SM) k_assemble(const DevP *Pp, in
 // update_chunk: re-linearise, back-substitute x_l = H_ll^-1 (b_l - W^T x_p), retract, evaluate the new cost
 // ---------------------------------------------------------------------------------------------------------
 template <int PROF, int LT>
-PLBA_D void update_chunk(const DevP &Pin, const Chunk &ch) {
+PLBA_D void update_chunk(const DevP &Pin, const Chunk &ch, bool wait_solve) {
     PLBA_PARAMS_REF(P, Pin);
     PLBA_SMEM(raw);
     typedef KT<PROF, LT> K;
@@ -663,12 +665,29 @@ PLBA_D void update_chunk(const DevP &Pin, const Chunk &ch) {
     PHASE_END
     PROF_MARK(21);
     PHASE_BEGIN
-        double sc = 0.0;
         if (tid < nob) {
             const int o = ch.ob0 + tid;
             const int l = OA::lm(P)[o] - ch.lm0;
             sm.lmof[tid] = l;
             obs_linearize<PROF, LT>(P, ctl, o, tid, l, sm);
+        }
+    PHASE_END
+    // per landmark: H_ll, b_l, the damped inverse — still the old state only; kept in the landmark thread's registers across the wait
+    THR_ARR(double, Hs, D * D); THR_ARR(double, bls, D);
+    PHASE_BEGIN
+        THR_BIND(Hs); THR_BIND(bls);
+        if (tid < nlm) {
+            double maxd;
+            lm_blocks<PROF, LT>(sm.lm_t0[tid], sm.lm_t0[tid + 1], sm, Hs, bls, maxd);
+            damp_invert<PROF, D>(ctl, Hs);
+        }
+    PHASE_END
+    PROF_MARK(27);
+    // everything above reads the OLD state only; from here on the pose step x_p and the trial poses of the solver are needed
+    if (wait_solve) plba_wait_flag(&P.counters[CNT_SOLVE_DONE]);
+    PHASE_BEGIN
+        double sc = 0.0;
+        if (tid < nob) {
             const int slot = sm.slot[tid];
             for (int k = 0; k < RANK; k++) {
                 double u = 0.0;
@@ -682,13 +701,12 @@ PLBA_D void update_chunk(const DevP &Pin, const Chunk &ch) {
     PHASE_END
     PROF_MARK(22);
     PHASE_BEGIN
+        THR_BIND(Hs); THR_BIND(bls);
         double sc = 0.0, d2 = 0.0;
         if (tid < nlm) {
             const int lm = ch.lm0 + tid;
             const int t0 = sm.lm_t0[tid], t1 = sm.lm_t0[tid + 1];
-            double H[D * D], bl[D], maxd;
-            lm_blocks<PROF, LT>(t0, t1, sm, H, bl, maxd);
-            damp_invert<PROF, D>(ctl, H);
+            const double *H = Hs, *bl = bls;
             double rhs[D];
             for (int c = 0; c < D; c++) rhs[c] = bl[c];
             for (int t = t0; t < t1; t++) {
@@ -935,12 +953,12 @@ PLBA_D void round_epilogue(const DevP &P, int flags) {
 // The reduced camera system of small windows is consumed by k_solve_small (one CTA per window) but cleared HERE, by every CTA of the
 // update kernel that runs next: clearing 115 KB (config 2) with the store path of the solver's single SM costs ~4 000 cycles of the
 // latency-critical kernel (measured), spread over the grid it is free.  Coalesced 128-bit stores.
-PLBA_D void clear_consumed_S(const DevP &P) {
+PLBA_D void clear_consumed_S(const DevP &P, int part, int nparts) {
     PHASE_BEGIN
         const long long n2 = P.S_clear_doubles / 2;
         plba_d2 *Sz = (plba_d2 *)P.S;
         const plba_d2 z = {0.0, 0.0};
-        for (long long i = (long long)PLBA_BID * PLBA_NT + tid; i < n2; i += (long long)PLBA_NB * PLBA_NT) Sz[i] = z;
+        for (long long i = (long long)part * PLBA_NT + tid; i < n2; i += (long long)nparts * PLBA_NT) Sz[i] = z;
     PHASE_END
 }
 
@@ -948,11 +966,20 @@ template <int PROF>
 PLBA_KERNEL void PLBA_BOUNDS(OC, PLBA_CTAS_PER_SM) k_update(const DevP *Pp, int flags) {
     PLBA_SMEM(raw);
     PLBA_PARAMS(P, Pp);
-    if (P.S_clear_doubles) clear_consumed_S(P);
+    // KF_WAIT_SOLVE (single small window, profile G, inside the LM-loop graph): this kernel is launched BESIDE k_solve_small (programmatic
+    // edge: it starts once the solver's CTA is resident), re-linearises its chunks at the old state while the solver factors, and waits
+    // for the solver's flag only where x_p is first needed.  S is consumed by the solver, so it is cleared after the wait; CTAs without a
+    // chunk leave at once (they must not hold SM slots while they spin).
+    const bool wait_solve = (flags & KF_WAIT_SOLVE) != 0;
+    if (P.S_clear_doubles && !wait_solve) clear_consumed_S(P, PLBA_BID, PLBA_NB);
     const int ntot = P.n_chunks_pt + P.n_chunks_ls;
     for (int c = PLBA_BID; c < ntot; c += PLBA_NB) {
-        if (c < P.n_chunks_pt) { const Chunk ch = P.chunks_pt[c]; update_chunk<PROF, LT_POINT>(P, ch); }
-        else { const Chunk ch = P.chunks_ls[c - P.n_chunks_pt]; update_chunk<PROF, LineOf<PROF>::LT>(P, ch); }
+        if (c < P.n_chunks_pt) { const Chunk ch = P.chunks_pt[c]; update_chunk<PROF, LT_POINT>(P, ch, wait_solve); }
+        else { const Chunk ch = P.chunks_ls[c - P.n_chunks_pt]; update_chunk<PROF, LineOf<PROF>::LT>(P, ch, wait_solve); }
+    }
+    if (wait_solve && P.S_clear_doubles && PLBA_BID < ntot) {
+        plba_wait_flag(&P.counters[CNT_SOLVE_DONE]);      // (a chunk of a finished window returns without waiting)
+        clear_consumed_S(P, PLBA_BID, PLBA_NB < ntot ? PLBA_NB : ntot);
     }
     if (!(flags & KF_FUSE_CONTROL)) return;
     // the last CTA to arrive runs the controller for every window

@@ -174,6 +174,7 @@ PLBA_HD bool chol6_inplace(double *a, double *inv) {
 
 PLBA_KERNEL void PLBA_BOUNDS(SS_NT, 1) k_solve_small(const DevP *Pp) {
     PLBA_SMEM(raw);
+    plba_launch_dependents();         // (an update kernel attached by a programmatic edge starts beside this kernel: see k_update, KF_WAIT_SOLVE)
     PLBA_PARAMS(P, Pp);
     PROF_DECL;
     const int nfmax = P.solve_nf_max > 0 ? P.solve_nf_max : 1;
@@ -415,6 +416,13 @@ PLBA_KERNEL void PLBA_BOUNDS(SS_NT, 1) k_solve_small(const DevP *Pp) {
             if (t == 0 && g < gpc && !info[4 * g]) { const double *red = gbase + (size_t)g * gd + gd - 8; P.ctrl[w].scale_pose = red[0]; P.ctrl[w].dx2_pose = red[1]; }
         PHASE_END
     PROF_MARK(50);
+    }
+    if (PLBA_NB == 1) {               // single window: x_p, the trial poses and the controller inputs are published
+        PHASE_BEGIN
+        PHASE_END
+        PHASE_BEGIN
+            if (tid == 0) plba_set_flag(&P.counters[CNT_SOLVE_DONE]);
+        PHASE_END
     }
 }
 

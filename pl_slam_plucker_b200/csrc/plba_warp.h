@@ -822,7 +822,7 @@ PLBA_KERNEL void PLBA_BOUNDS(WNT, PLBA_WU_CTAS) k_update_w(const DevP *Pp, int f
     PLBA_SMEM(raw);
     PLBA_PARAMS(P, Pp);
     unsigned char *wraw = raw + (size_t)PLBA_WARP_IN_CTA * WSmemMax<PROF>::bytes();
-    if (P.S_clear_doubles) clear_consumed_S(P);
+    if (P.S_clear_doubles) clear_consumed_S(P, PLBA_BID, PLBA_NB);
     update_items_w<PROF, LT_POINT>(P, P.witems_pt, P.n_witems_pt, wraw);
     update_items_w<PROF, LineOf<PROF>::LT>(P, P.witems_ls, P.n_witems_ls, wraw);
     // the last CTA to arrive re-arms the work counters and (fused mode) runs the controller for every window

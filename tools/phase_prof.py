@@ -5,7 +5,7 @@ from pl_slam_plucker_b200 import abi, scene, solver, _lib
 lib = _lib.load(os.path.join(os.path.dirname(_lib.library_path()), "libplba_prof.so"))
 s = solver.LBASolver(0, lib=lib)
 NAMES = {1: "asm precompute", 2: "asm linearize", 3: "asm per-landmark", 4: "asm Ta", 5: "asm offdiag tasks", 6: "asm diag tasks",
-         21: "upd precompute", 22: "upd linearize+U", 23: "upd per-landmark", 24: "upd orth->plk", 25: "upd new cost", 26: "upd tail",
+         21: "upd precompute", 27: "upd linearize (old state: before the solver's flag)", 22: "upd J x_p", 23: "upd per-landmark", 24: "upd orth->plk", 25: "upd new cost", 26: "upd tail",
          42: "sol control", 43: "sol load + first factor", 44: "sol A: column solve", 45: "sol B: trailing update + look-ahead factor", 46: "sol (loop exit)", 47: "sol backward", 50: "sol write + pose"}
 for cfg in [int(a) for a in sys.argv[1:]] or [2]:
     P = scene.make_scene(cfg)
