@@ -14,6 +14,8 @@ over one synthetic window of the named workload (C3: over a batch of 1 024 windo
 The same JSON line also carries, measured in the same run (rank 0; --no-configs skips them):
   configs           : whole-LBA resident + end-to-end + 1-thread CPU numbers of the OTHER BASELINE configs (C1, C3, C4, C5),
   roofline_largest  : the assembly kernel at config 5 against the measured HBM peak AND the measured FP64 peak (DFMA / DMMA micro-benchmarks),
+  dense_cholesky    : the reduced camera system of config 5 factored as a DENSE 12 000 x 12 000 matrix (the route of loop-closure-shaped windows):
+                      n^3 / 3 FP64 flops on mma.sync.m8n8k4.f64 against the DMMA peak measured in the same run (bound: tensor),
   N > 1             : c3_replicas (config 3: 1 024 windows, 1 024 / N per rank, no collective) and sharded (configs 4 and 5, landmarks
                       sharded by base keyframe, the library's own ncclAllReduce per LM trial) next to their single-GPU times.
 --impl reference : the CPU restatement of the reference (oracle/, all host threads) on the same workload; rank 0 only; loads neither

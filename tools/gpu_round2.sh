@@ -20,6 +20,11 @@ if [ "$1" = "ncu" ]; then
   PLBA_FORCE_DENSE=1 timeout 300 python tools/solve_only.py 5 > gpurun_out/plain.log 2>&1 &&
   PLBA_FORCE_DENSE=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_syrk_dmma" -s 1 -c 1 -o gpurun_out/${T}_dense_syrk python tools/solve_only.py 5 > gpurun_out/ncu_syrk.log 2>&1
   tail -n 2 gpurun_out/ncu_syrk.log
+  timeout 300 python tools/prof_assemble.py 5 > gpurun_out/pa5.log 2>&1 &&
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_assemble_w|k_update_w" -s 2 -c 2 -o gpurun_out/${T}_c5 python tools/prof_assemble.py 5 > gpurun_out/pa5_ncu.log 2>&1
+  timeout 300 python tools/prof_run.py 2 > gpurun_out/pa2.log 2>&1 &&
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_assemble|k_solve_small|k_update" -s 3 -c 3 -o gpurun_out/${T}_c2 python tools/prof_run.py 2 > gpurun_out/pa2_ncu.log 2>&1
+  tail -n 1 gpurun_out/pa5_ncu.log; tail -n 1 gpurun_out/pa2_ncu.log
   timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-largest --no-configs > gpurun_out/plain2.log 2>&1 &&
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${T}_launches_C2_G.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-largest --no-configs > gpurun_out/ncu_l.log 2>&1
   tail -n 1 gpurun_out/ncu_l.log | cut -c1-300
