@@ -741,7 +741,8 @@ PLBA_D void update_chunk(const DevP &Pin, const Chunk &ch, bool wait_solve) {
     PHASE_END
     PROF_MARK(23);
     if (PROF == PLBA_PROFILE_G) {
-        // new cost at the trial state (computeActiveErrors + activeRobustChi2 after update)
+        // new cost at the trial state (computeActiveErrors + activeRobustChi2 after update): needs the trial poses (flag value 2)
+        if (wait_solve) plba_wait_flag(&P.counters[CNT_SOLVE_DONE], 2);
     PROF_MARK(24);
         PHASE_BEGIN
             double rho0 = 0.0;
@@ -978,7 +979,7 @@ PLBA_KERNEL void PLBA_BOUNDS(OC, PLBA_CTAS_PER_SM) k_update(const DevP *Pp, int 
         else { const Chunk ch = P.chunks_ls[c - P.n_chunks_pt]; update_chunk<PROF, LineOf<PROF>::LT>(P, ch, wait_solve); }
     }
     if (wait_solve && P.S_clear_doubles && PLBA_BID < ntot) {
-        plba_wait_flag(&P.counters[CNT_SOLVE_DONE]);      // (a chunk of a finished window returns without waiting)
+        plba_wait_flag(&P.counters[CNT_SOLVE_DONE], 2);   // (a chunk of a finished window returns without waiting)
         clear_consumed_S(P, PLBA_BID, PLBA_NB < ntot ? PLBA_NB : ntot);
     }
     if (!(flags & KF_FUSE_CONTROL)) return;

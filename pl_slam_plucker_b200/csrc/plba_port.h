@@ -100,14 +100,14 @@ PLBA_D void plba_fence() { __threadfence(); }
 #define PLBA_TID0 (threadIdx.x)
 // Block-wide wait for a flag that another kernel running at the same time sets to non-zero (release / acquire at GPU scope).  Thread 0
 // polls, the block barrier hands the acquire on to the other threads.
-PLBA_D void plba_wait_flag(const int *flag) {
+PLBA_D void plba_wait_flag(const int *flag, int at_least = 1) {
     if (threadIdx.x == 0) {
         int v;
-        do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory"); if (!v) __nanosleep(200); } while (!v);
+        do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory"); if (v < at_least) __nanosleep(100); } while (v < at_least);
     }
     __syncthreads();
 }
-PLBA_D void plba_set_flag(int *flag) { __threadfence(); asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory"); }
+PLBA_D void plba_set_flag(int *flag, int value = 1) { __threadfence(); asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(value) : "memory"); }
 // programmatic dependent launch: kernels connected to this one by a programmatic edge may start now
 PLBA_D void plba_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 PLBA_D int plba_atomic_fetch_add_i(int *p, int v) { return atomicAdd(p, v); }
@@ -202,8 +202,8 @@ inline double plba_ld_l2(const double *p) { return *p; }
 inline int plba_ld_l2(const int *p) { return *p; }
 inline void plba_fence() {}
 #define PLBA_TID0 0
-inline void plba_wait_flag(const int *flag) { if (!*flag) std::abort(); }      // the emulation runs kernels one after the other: the flag must be set already
-inline void plba_set_flag(int *flag) { *flag = 1; }
+inline void plba_wait_flag(const int *flag, int at_least = 1) { if (*flag < at_least) std::abort(); }      // the emulation runs kernels one after the other: the flag must be set already
+inline void plba_set_flag(int *flag, int value = 1) { *flag = value; }
 inline void plba_launch_dependents() {}
 inline int plba_atomic_fetch_add_i(int *p, int v) { int o = *p; *p += v; return o; }
 inline double plba_rsqrt(double x) { return 1.0 / std::sqrt(x); }

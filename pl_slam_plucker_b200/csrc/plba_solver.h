@@ -402,6 +402,11 @@ PLBA_KERNEL void PLBA_BOUNDS(SS_NT, 1) k_solve_small(const DevP *Pp) {
                 if (t == 0 && f) P.ctrl[w].solve_fail = 1;
             }
         PHASE_END
+        if (PLBA_NB == 1) {           // single window: x_p is out — the update kernel running beside this one can go on (the trial poses follow: flag value 2)
+            PHASE_BEGIN
+                if (tid == 0) plba_set_flag(&P.counters[CNT_SOLVE_DONE], 1);
+            PHASE_END
+        }
         PHASE_BEGIN
             const int g = tid / G, t = tid - g * G, w = w0 + g;
             double sc = 0.0, d2 = 0.0;
@@ -421,7 +426,7 @@ PLBA_KERNEL void PLBA_BOUNDS(SS_NT, 1) k_solve_small(const DevP *Pp) {
         PHASE_BEGIN
         PHASE_END
         PHASE_BEGIN
-            if (tid == 0) plba_set_flag(&P.counters[CNT_SOLVE_DONE]);
+            if (tid == 0) plba_set_flag(&P.counters[CNT_SOLVE_DONE], 2);
         PHASE_END
     }
 }
