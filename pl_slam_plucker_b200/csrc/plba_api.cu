@@ -1399,14 +1399,18 @@ static int run_async(plba_handle h) {
         // controller runs on the device; the host only needs to learn WHEN every window is done, and reads the counters of the round
         // it launched PLBA_ROUNDS_IN_FLIGHT rounds ago (pinned copy + event), so the stream never drains.  At most that many rounds
         // are launched in vain; their kernels return at once for finished windows.  No per-round cudaStreamSynchronize.
+        // (The kernels of the dense tiled Cholesky do not look at the windows' done flags — a check would sit on the critical path of 125
+        //  panel steps — and one of its solves costs tens of milliseconds: windows on that solver are polled every round.)
+        const bool dense_solver = !h->small_path && !h->bcr_layout && !(h->band_blocks <= BAND_MAX && !h->force_dense);
+        const int in_flight = dense_solver ? 0 : (int)PLBA_ROUNDS_IN_FLIGHT;
         bool done = false;
         for (int round = 0; round < P.max_rounds && !done; round++) {
             if ((rc = run_round(h, true))) return rc;
             const int slot = round % 4;
             CK(cudaMemcpyAsync(h->h_poll + slot * CNT_N, P.counters, sizeof(int) * CNT_N, cudaMemcpyDeviceToHost, st));
             CK(cudaEventRecord(h->ev_poll[slot], st));
-            if (round >= PLBA_ROUNDS_IN_FLIGHT) {
-                const int old = (round - PLBA_ROUNDS_IN_FLIGHT) % 4;
+            if (round >= in_flight) {
+                const int old = (round - in_flight) % 4;
                 CK(cudaEventSynchronize(h->ev_poll[old]));
                 done = h->h_poll[old * CNT_N + CNT_DONE] >= P.n_win;
             }
