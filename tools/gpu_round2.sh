@@ -13,12 +13,13 @@ import json
 d = json.loads(open("gpurun_out/${T}_bench.json").read().strip().splitlines()[-1])
 print("C2 ms/step", d["ms_per_step"], "e2e ms", d["e2e"]["ms_per_step"], "launches", d["gpu_launches"])
 print("roofline_largest", {k: d["roofline_largest"][k] for k in ("ms_per_launch", "frac", "frac_fp64", "update_kernel_ms_per_launch", "solve_ms_per_trial")})
-print("dense", d.get("dense_cholesky"))
+dc = d.get("dense_cholesky") or {}
+print("dense", {k: dc.get(k) for k in ("ms_per_solve", "achieved", "frac")}, "loop closure", {k: (dc.get("loop_closure_window") or {}).get(k) for k in ("ms_per_lba", "lm_trials", "stage_ms_per_lba")})
 print("configs", {k: v.get("ms_per_lba") for k, v in d.get("configs", {}).items()})
 PY
 if [ "$1" = "ncu" ]; then
   PLBA_FORCE_DENSE=1 timeout 300 python tools/solve_only.py 5 > gpurun_out/plain.log 2>&1 &&
-  PLBA_FORCE_DENSE=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_syrk_dmma" -s 1 -c 1 -o gpurun_out/${T}_dense_syrk python tools/solve_only.py 5 > gpurun_out/ncu_syrk.log 2>&1
+  PLBA_FORCE_DENSE=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_syrk_dmma" -s 3 -c 1 -o gpurun_out/${T}_dense_syrk python tools/solve_only.py 5 > gpurun_out/ncu_syrk.log 2>&1
   tail -n 2 gpurun_out/ncu_syrk.log
   timeout 300 python tools/prof_assemble.py 5 > gpurun_out/pa5.log 2>&1 &&
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_assemble_w|k_update_w" -s 2 -c 2 -o gpurun_out/${T}_c5 python tools/prof_assemble.py 5 > gpurun_out/pa5_ncu.log 2>&1
