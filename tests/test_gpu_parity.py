@@ -374,6 +374,58 @@ def test_graph_equals_host_driven_loop(oracle):
         s.close()
 
 
+def _solver_with_env(**env):
+    """A handle created under the given A/B switches (they are read once, in plba_create)."""
+    from pl_slam_plucker_b200 import solver
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return solver.LBASolver(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_solver_beside_update_equals_plain_chain(oracle):
+    """Single small windows in profile G run the update kernel BESIDE k_solve_small (programmatic graph edge + release / acquire flag); with
+    PLBA_NO_OVERLAP=1 the two kernels run one after the other.  Same decisions, same values to rounding, both equal to the oracle."""
+    a, b = _solver_with_env(PLBA_NO_OVERLAP=0), _solver_with_env(PLBA_NO_OVERLAP=1)
+    try:
+        for q, kw in ((0, dict(n_kf_free=8, n_kf_fixed=2, n_pt=500, n_ls=120, seed=51)), (1, dict()), (0, dict(n_kf_free=20, n_kf_fixed=2, n_pt=2000, n_ls=500, seed=52))):
+            P = _scene(1, abi.PROFILE_G, **kw)
+            opt = abi.Options(abi.PROFILE_G, q)
+            for _ in range(3):                              # the flag protocol must hold call after call on one handle
+                ra = a.solve(P, opt)
+            rb = b.solve(P, opt)
+            o = oracle.solve(P, opt)
+            # (decisions are compared up to the first trial whose gain ratio is rounding noise, as everywhere: helpers.assert_trace_close)
+            assert assert_trace_close(o.trace, ra.trace, abi.PROFILE_G) >= 5 and assert_trace_close(o.trace, rb.trace, abi.PROFILE_G) >= 5
+            assert_state_close(ra, rb, P, abi.PROFILE_G, atol=1e-9)
+            assert_state_close(o, ra, P, abi.PROFILE_G)
+    finally:
+        a.close(); b.close()
+
+
+def test_dense_cholesky_variants_agree(oracle):
+    """The dense tiled Cholesky (loop-closure-shaped windows) in its A/B forms: panel groups of 1-4, one trailing update per panel
+    (PLBA_DENSE_K1), no look-ahead stream — all against the oracle on a window whose order (408) is no multiple of the 96-column panel."""
+    P = scene.make_scene(1, n_kf_free=68, n_kf_fixed=2, n_pt=2400, n_ls=500, loop_every=30, seed=61)
+    opt = abi.Options(abi.PROFILE_G, 1)
+    o = oracle.solve(P, opt)
+    for env in (dict(PLBA_DENSE_GROUP=1), dict(PLBA_DENSE_GROUP=2), dict(PLBA_DENSE_GROUP=4), dict(PLBA_DENSE_K1=1), dict(PLBA_NO_LOOKAHEAD=1)):
+        s = _solver_with_env(**env)
+        try:
+            r = s.solve(P, opt)
+            assert s.kernel_path()["solver"] == "dense-dmma", env
+            assert_trace_close(o.trace, r.trace, abi.PROFILE_G)
+            assert_state_close(o, r, P, abi.PROFILE_G)
+        finally:
+            s.close()
+
+
 def test_numeric_failure_is_reported(gpu_solver):
     """PLBA_E_NUMERIC: a window whose reduced camera system is not positive definite in every trial (here: a NaN measurement poisons the
     system) must be reported, not silently returned as OK."""
