@@ -832,7 +832,8 @@ template <int PROF> static int build_graph(plba_handle h) {
         cudaGraphNodeParams ip2{}; ip2.type = cudaGraphNodeTypeConditional;
         ip2.conditional.handle = h->cond_prep2[pi]; ip2.conditional.type = cudaGraphCondTypeIf; ip2.conditional.size = 1;
         cudaGraphNode_t inode2;
-        CK(cudaGraphAddNode(&inode2, body, &m3, 1, &ip2));
+        cudaGraphNode_t deps2[2] = {m3, m2};
+        CK(cudaGraphAddNode(&inode2, body, deps2, 2, &ip2));
         cudaGraph_t prep2 = ip2.conditional.phGraph_out[0];
         cudaGraphNode_t q1, q2, q3, r1, r2, r3;
         CK(add_kernel(prep2, &q1, nullptr, (void *)k_gate, dim3(h->grid_chunks), dim3(256), 0, a_p));
@@ -840,6 +841,12 @@ template <int PROF> static int build_graph(plba_handle h) {
         CK(add_kernel(prep2, &q3, q2, (void *)k_lambda_init, dim3(h->n_sm), dim3(128), 0, a_p));
         CK(add_kernel(body, &r1, inode2, f_asm, gc, bc, smc, a_m1));
         CK(add_kernel(body, &r2, r1, (void *)k_solve_small, dim3(h->grid_solve), dim3(SS_NT), solve_small_smem(), a_p));
+        if (overlap) {
+            CK(add_kernel(body, &r3, nullptr, f_upd, gu, bc, smc, a_flov));
+            cudaGraphEdgeData ed{};
+            ed.from_port = cudaGraphKernelNodePortProgrammatic; ed.to_port = 0; ed.type = cudaGraphDependencyTypeProgrammatic;
+            CK(cudaGraphAddDependencies_v2(body, &r2, &r3, &ed, 1));
+        } else
         CK(add_kernel(body, &r3, r2, f_upd, gu, bc, smc, a_fl));
     }
 #endif
