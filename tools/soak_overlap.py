@@ -1,0 +1,22 @@
+"""Soak test of the solver / update overlap: many back-to-back plba_solve calls on small windows of changing shape through one handle
+(graph path); every result must match the first solve of its window to rounding.  python tools/soak_overlap.py [n]"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from pl_slam_plucker_b200 import abi, scene, solver
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+s = solver.LBASolver(0)
+shapes = [dict(n_kf_free=4, n_kf_fixed=2, n_pt=60, n_ls=20), dict(n_kf_free=10, n_kf_fixed=2, n_pt=2000, n_ls=500), dict(n_kf_free=20, n_kf_fixed=2, n_pt=8000, n_ls=2000),
+          dict(n_kf_free=7, n_kf_fixed=1, n_pt=300, n_ls=0), dict(n_kf_free=21, n_kf_fixed=3, n_pt=1500, n_ls=400)]
+Ps = [scene.make_scene(1, seed=900 + i, **kw) for i, kw in enumerate(shapes)]
+ref = {}
+t0 = time.time(); worst = 0.0
+for it in range(n):
+    i = (it * 7 + it // 3) % len(Ps); q = it % 2
+    r = s.solve(Ps[i], abi.Options(abi.PROFILE_G, q))
+    key = (i, q)
+    if key not in ref: ref[key] = r
+    else:
+        d = float(np.abs(r.kf_T_wc - ref[key].kf_T_wc).max()); worst = max(worst, d)
+        assert d < 1e-9 and abs(len(r.trace) - len(ref[key].trace)) <= 2, (it, key, d, len(r.trace), len(ref[key].trace))
+print("soak ok: %d solves in %.1f s, worst pose deviation between repeats %.2e" % (n, time.time() - t0, worst))
