@@ -384,12 +384,14 @@ int plba_create(int32_t device, void *stream, plba_handle *out) {
         h->no_lookahead = nl && nl[0] == '1';
         const char *no = std::getenv("PLBA_NO_OVERLAP");
         h->no_overlap = no && no[0] == '1';
+    }
+#endif
+    {   // launch geometry of the dense tiled Cholesky (also read by the host emulation, so that the CPU tests walk every variant)
         const char *k1 = std::getenv("PLBA_DENSE_K1");
         h->dense_k1 = k1 && k1[0] == '1';
         const char *dg = std::getenv("PLBA_DENSE_GROUP");
         if (dg && std::atoi(dg) >= 1 && std::atoi(dg) <= 8) h->dense_group = std::atoi(dg);
     }
-#endif
     *out = h;
     return PLBA_OK;
 }
