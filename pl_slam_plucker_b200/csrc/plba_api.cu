@@ -20,6 +20,9 @@
 #include <chrono>
 #include "plba_solver.h"
 #include "plba_warp.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include "plba_track.h"
 #ifndef PLBA_HOST_EMU
 #include <dlfcn.h>
@@ -73,6 +76,20 @@ enum { PLBA_MAX_RANKS = 16 };
 // host loops of upload / download run in parallel above these sizes (a parallel region costs tens of microseconds: a config-2 window of
 // 45 000 observations stays serial, config 4 with 1.15 M observations does not)
 enum { PAR_LM = 40000, PAR_OBS = 200000 };
+// ... and on about one thread per 150 000 observations, not on every core: config 4 (1.15 M observations) prepares in 8.8 ms on 8 threads
+// and in 17.6 ms on the box's 16 (a parallel region's fork / join over 16 virtual CPUs costs more than a mid-size loop gains; config 5's
+// 11 M observations take all of them).  PLBA_HOST_THREADS overrides.  Set at the top of plba_upload / plba_download.
+static thread_local int g_host_nt = 1;
+static int host_threads_for(int64_t n_obs) {
+#ifdef _OPENMP
+    static const int env = [] { const char *e = std::getenv("PLBA_HOST_THREADS"); return e ? std::atoi(e) : 0; }();
+    const int mx = omp_get_max_threads();
+    if (env > 0) return std::min(env, std::max(mx, 1));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(mx, n_obs / 150000));
+#else
+    (void)n_obs; return 1;
+#endif
+}
 struct WinInfo { int n_kf, n_free, n_pt, n_ls, n_pobs, n_lobs, kf0, slot0, pt0, ls0, po0, lo0; };
 
 // bump allocator over a byte range (device arena or pinned staging): 256-byte aligned carve-outs
@@ -201,12 +218,12 @@ static int validate_problem(const plba_problem &p, const plba_options &o, std::s
     }
     if (nfree != p.n_free) { err = "n_free does not match kf_slot"; return PLBA_E_ARG; }
     int bad_p = 0, bad_l = 0;      // 1 = index out of range, 2 = not landmark-major
-#pragma omp parallel for schedule(static) reduction(max : bad_p) if (p.n_pobs > PAR_OBS)
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) reduction(max : bad_p) if (p.n_pobs > PAR_OBS)
     for (int i = 0; i < p.n_pobs; i++) {
         if (p.po_lm[i] < 0 || p.po_lm[i] >= p.n_pt || p.po_kf[i] < 0 || p.po_kf[i] >= p.n_kf) bad_p = bad_p > 1 ? bad_p : 1;
         else if (i && p.po_lm[i] < p.po_lm[i - 1]) bad_p = 2;
     }
-#pragma omp parallel for schedule(static) reduction(max : bad_l) if (p.n_lobs > PAR_OBS)
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) reduction(max : bad_l) if (p.n_lobs > PAR_OBS)
     for (int i = 0; i < p.n_lobs; i++) {
         if (p.lo_lm[i] < 0 || p.lo_lm[i] >= p.n_ls || p.lo_kf[i] < 0 || p.lo_kf[i] >= p.n_kf) bad_l = bad_l > 1 ? bad_l : 1;
         else if (i && p.lo_lm[i] < p.lo_lm[i - 1]) bad_l = 2;
@@ -226,19 +243,19 @@ static void signature_order(int n_lm, int n_obs, const int32_t *lm, const int32_
     const bool par = n_obs > PAR_OBS;      // one large window: the loops below run in parallel (a region costs more than a small window's whole sort)
     L.optr.assign(n_lm + 1, n_obs);
     // lm[] is non-decreasing (validated): optr[l] = first observation whose landmark is >= l
-#pragma omp parallel for schedule(static) if (par)
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) if (par)
     for (int i = 0; i < n_obs; i++) {
         const int lo = i ? lm[i - 1] + 1 : 0;
         for (int l = lo; l <= lm[i]; l++) L.optr[l] = i;
     }
     L.perm.resize(n_lm);
-#pragma omp parallel for schedule(static) if (par)
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) if (par)
     for (int l = 0; l < n_lm; l++) L.perm[l] = l;
     if (!permute || n_lm < 2) return;
     {   // fast path: every track is a contiguous keyframe run (the usual sliding-window case) => the signature IS (first KF, length):
         // one pass over the observations and a counting sort, no hashing
         int maxlen = 0, maxkf = 0, broken = 0;
-#pragma omp parallel for schedule(static) reduction(max : maxlen, maxkf, broken) if (par)
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) reduction(max : maxlen, maxkf, broken) if (par)
         for (int l = 0; l < n_lm; l++) {
             if (broken > 0) continue;      // (a max-reduction's private copy starts at INT_MIN, not at 0)
             const int a = L.optr[l], b = L.optr[l + 1];
@@ -926,13 +943,14 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     // ---- index work: signature order, chunks, segments --------------------------------------------------------
     std::vector<Chunk> &ch_pt = h->ch_pt, &ch_ls = h->ch_ls; std::vector<Seg> &sg_pt = h->sg_pt, &sg_ls = h->sg_ls; std::vector<int> &fp_pt = h->fp_pt, &fp_ls = h->fp_ls;
     ch_pt.clear(); ch_ls.clear(); sg_pt.clear(); sg_ls.clear(); fp_pt.clear(); fp_ls.clear();
+    g_host_nt = host_threads_for((int64_t)tot.n_pobs + tot.n_lobs);
     h->pt_perm.resize(tot.n_pt); h->ls_perm.resize(tot.n_ls); h->po_perm.resize(tot.n_pobs); h->lo_perm.resize(tot.n_lobs);
     std::vector<int> &pt_ptr = h->pt_ptr, &ls_ptr = h->ls_ptr;
     pt_ptr.assign(tot.n_pt + 1, 0); ls_ptr.assign(tot.n_ls + 1, 0);
     bool too_long = false;
     std::vector<ClassLayout> Lps(n), Lls(n);
     // batches: parallel over windows; one LARGE window: parallel inside signature_order
-#pragma omp parallel for schedule(dynamic, 1) if (n > 8)
+#pragma omp parallel for num_threads(g_host_nt) schedule(dynamic, 1) if (n > 8)
     for (int wc = 0; wc < 2 * n; wc++) {
         const int w = wc >> 1;
         const plba_problem &p = probs[w];
@@ -968,7 +986,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
             // windows: 12.5 M entries at config 5), (3) the runs (serial, index compares only)
             int ob = ob0;
             for (int nl_i = 0; nl_i < nl; nl_i++) { const int old = L.perm[nl_i]; ptr[lm0 + nl_i] = ob; ob += L.optr[old + 1] - L.optr[old]; }
-#pragma omp parallel for schedule(static) if (nl > PAR_LM)
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) if (nl > PAR_LM)
             for (int nl_i = 0; nl_i < nl; nl_i++) {
                 const int old = L.perm[nl_i], a = L.optr[old], b = L.optr[old + 1];
                 perm[lm0 + nl_i] = lm0 + old;
@@ -1210,7 +1228,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     if (!wi_ls.empty()) std::memcpy(hb + i_wi_ls, wi_ls.data(), sizeof(WItem) * wi_ls.size());
     HOSTPROF("fl.tables");
     const bool par_lm = (n <= 8);       // one (or few) big windows: parallel over landmarks; batches: parallel over windows
-#pragma omp parallel for schedule(dynamic, 4) if (!par_lm)
+#pragma omp parallel for num_threads(g_host_nt) schedule(dynamic, 4) if (!par_lm)
     for (int w = 0; w < n; w++) {
         const plba_problem &p = probs[w]; const WinInfo &wi = h->wins[w];
         win_slot0[w] = wi.slot0; win_nfree[w] = wi.n_free; win_ls0[w] = wi.ls0; winS[w] = win_S_off[w];
@@ -1226,13 +1244,13 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
             }
         }
         if (n == 1) HOSTPROF("fl.kf");
-#pragma omp parallel for schedule(static) if (par_lm && p.n_pt > PAR_LM)
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) if (par_lm && p.n_pt > PAR_LM)
         for (int g = wi.pt0; g < wi.pt0 + p.n_pt; g++) {
             const int old = h->pt_perm[g] - wi.pt0;
             pt_win[g] = w;
             for (int i = 0; i < 3; i++) pts0[(size_t)3 * g + i] = p.pt_xyz[(size_t)3 * old + i];
         }
-#pragma omp parallel for schedule(static) if (par_lm && p.n_ls > PAR_LM)
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) if (par_lm && p.n_ls > PAR_LM)
         for (int g = wi.ls0; g < wi.ls0 + p.n_ls; g++) {
             const int old = h->ls_perm[g] - wi.ls0;
             ls_win[g] = w;
@@ -1243,7 +1261,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
             }
         }
         if (n == 1) HOSTPROF("fl.lm");
-#pragma omp parallel for schedule(static) if (par_lm && p.n_pt > PAR_LM)
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) if (par_lm && p.n_pt > PAR_LM)
         for (int g = wi.pt0; g < wi.pt0 + p.n_pt; g++) {
             // the observations of a landmark are one contiguous run in the caller's arrays too: copy runs, not elements
             const int o0 = pt_ptr[g], no = pt_ptr[g + 1] - o0;
@@ -1259,7 +1277,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
             if (p.po_sig2) for (int j = 0; j < no; j++) { duv[2 * j] = suv[2 * j]; duv[2 * j + 1] = suv[2 * j + 1]; dkf[j] = wi.kf0 + skf[j]; dlm[j] = g; dom[j] = (double)(float)(1.0 / p.po_sig2[i0 + j]); }   // const float& invSigma2 (:6009, Q13)
             else for (int j = 0; j < no; j++) { duv[2 * j] = suv[2 * j]; duv[2 * j + 1] = suv[2 * j + 1]; dkf[j] = wi.kf0 + skf[j]; dlm[j] = g; dom[j] = 1.0; }
         }
-#pragma omp parallel for schedule(static) if (par_lm && p.n_ls > PAR_LM)
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) if (par_lm && p.n_ls > PAR_LM)
         for (int g = wi.ls0; g < wi.ls0 + p.n_ls; g++) {
             const int o0 = ls_ptr[g], no = ls_ptr[g + 1] - o0;
             if (no == 0) continue;
@@ -1489,6 +1507,7 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
     if (!h || !h->uploaded || n != h->P.n_win || !res) return PLBA_E_ARG;
     CK(cudaSetDevice(h->device));
     DevP &P = h->P; cudaStream_t st = h->stream;
+    g_host_nt = host_threads_for((int64_t)P.n_pobs + P.n_lobs);
     const bool G = (P.profile == PLBA_PROFILE_G);
     const int ld = h->ls_dim;
     char *db = h->d_arena;
@@ -1513,7 +1532,7 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
     for (int i = 0; i < CNT_N; i++) h->h_counters[i] = cnt[i];
     const double *pt0 = (const double *)(h->h_in + h->i_pts0), *ls0 = (const double *)(h->h_in + h->i_lns0);
     int rc_all = PLBA_OK;
-#pragma omp parallel for schedule(dynamic, 4) if (n > 8)
+#pragma omp parallel for num_threads(g_host_nt) schedule(dynamic, 4) if (n > 8)
     for (int w = 0; w < n; w++) {
         const WinInfo &wi = h->wins[w]; plba_result &r = res[w];
         r.n_trace = ctrl[w].n_trace; r.n_trials = ctrl[w].n_trials;
@@ -1522,14 +1541,14 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
         if (r.kf_T_wc) for (int i = 0; i < 12 * wi.n_kf; i++) r.kf_T_wc[i] = T[(size_t)12 * wi.kf0 + i];
         if (r.x_pose) for (int i = 0; i < 6 * wi.n_free; i++) r.x_pose[i] = X[(size_t)6 * wi.slot0 + i];
         const bool par_lm = (n <= 8);       // one (or few) big windows: parallel over landmarks / observations; batches: parallel over windows
-#pragma omp parallel for schedule(static) if (par_lm && wi.n_pt > PAR_LM)
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) if (par_lm && wi.n_pt > PAR_LM)
         for (int g = wi.pt0; g < wi.pt0 + wi.n_pt; g++) {
             const int old = h->pt_perm[g] - wi.pt0;
             if (r.pt_xyz) for (int i = 0; i < 3; i++) r.pt_xyz[(size_t)3 * old + i] = pt[(size_t)3 * g + i];
             // inlier rule of the hand-LM write-back (src/mapHandler.cpp:2858-2860, 2871-2873); profile G leaves it to the final chi2 test
             if (r.pt_inlier) { double d2 = 0; for (int i = 0; i < 3; i++) { const double d = pt[(size_t)3 * g + i] - pt0[(size_t)3 * g + i]; d2 += d * d; } r.pt_inlier[old] = (!G && !P.gba && std::sqrt(d2) > 0.01) ? 0 : 1; }
         }
-#pragma omp parallel for schedule(static) if (par_lm && wi.n_ls > PAR_LM)
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) if (par_lm && wi.n_ls > PAR_LM)
         for (int g = wi.ls0; g < wi.ls0 + wi.n_ls; g++) {
             const int old = h->ls_perm[g] - wi.ls0;
             if (ld == 4) {
@@ -1546,13 +1565,13 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
             }
         }
         if (G) {
-#pragma omp parallel for schedule(static) if (par_lm && wi.n_pobs > PAR_OBS)
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) if (par_lm && wi.n_pobs > PAR_OBS)
             for (int o = wi.po0; o < wi.po0 + wi.n_pobs; o++) {
                 const int i = h->po_perm[o] - wi.po0;
                 if (r.po_chi2) r.po_chi2[i] = pchi[o];
                 if (r.po_flags) r.po_flags[i] = pf[o];
             }
-#pragma omp parallel for schedule(static) if (par_lm && wi.n_lobs > PAR_OBS)
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) if (par_lm && wi.n_lobs > PAR_OBS)
             for (int o = wi.lo0; o < wi.lo0 + wi.n_lobs; o++) {
                 const int i = h->lo_perm[o] - wi.lo0;
                 if (r.lo_chi2) r.lo_chi2[i] = lchi[o];
