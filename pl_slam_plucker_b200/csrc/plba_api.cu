@@ -886,9 +886,9 @@ static bool use_graph(plba_handle h) {
 #endif
 }
 
-static int launch_reset(plba_handle h) {
+static int launch_reset(plba_handle h, int gather = 0) {
     h->klaunch_seen = 0;
-    PLBA_LAUNCH(k_reset, dim3(h->grid_chunks), dim3(256), 0, h->stream, (const DevP *)h->d_P, h->ls_dim, h->sys_doubles, h->sysbuf);
+    PLBA_LAUNCH(k_reset, dim3(h->grid_chunks), dim3(256), 0, h->stream, (const DevP *)h->d_P, h->ls_dim, h->sys_doubles, h->sysbuf, gather);
     h->timing.n_launches++;
     return PLBA_OK;
 }
@@ -913,10 +913,24 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     h->wins.assign(n, WinInfo{});
     WinInfo tot{};
     int max_nf = 0;
+    {   // host threads of this upload (see host_threads_for); a batch validates its windows in parallel, the first bad window (in order) reports
+        int64_t nobs_hint = 0;
+        for (int w = 0; w < n; w++) nobs_hint += (int64_t)std::max(probs[w].n_pobs, 0) + std::max(probs[w].n_lobs, 0);
+        g_host_nt = host_threads_for(nobs_hint);
+        int first_bad = n, rc_bad = 0;
+#pragma omp parallel for num_threads(g_host_nt) schedule(dynamic, 8) if (n > 8)
+        for (int w = 0; w < n; w++) {
+            std::string e;
+            const int rc = validate_problem(probs[w], *opt, e);
+            if (rc) {
+#pragma omp critical(plba_validate)
+                if (w < first_bad) { first_bad = w; rc_bad = rc; h->err = e; }
+            }
+        }
+        if (first_bad < n) return rc_bad;
+    }
     for (int w = 0; w < n; w++) {
         const plba_problem &p = probs[w];
-        int rc = validate_problem(p, *opt, h->err);
-        if (rc) return rc;
         WinInfo &wi = h->wins[w];
         wi.n_kf = p.n_kf; wi.n_free = p.n_free; wi.n_pt = p.n_pt; wi.n_ls = p.n_ls; wi.n_pobs = p.n_pobs; wi.n_lobs = p.n_lobs;
         wi.kf0 = tot.n_kf; wi.slot0 = tot.n_free; wi.pt0 = tot.n_pt; wi.ls0 = tot.n_ls; wi.po0 = tot.n_pobs; wi.lo0 = tot.n_lobs;
@@ -973,15 +987,22 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     h->warp_path = h->force_chunk != 1 && max_track <= W_MAX_TRACK && (big || h->force_chunk == 2);
     std::vector<WItem> &wi_pt = h->wi_pt, &wi_ls = h->wi_ls;
     wi_pt.clear(); wi_ls.clear();
-    for (int w = 0; w < n && h->warp_path; w++) {
+    // first segment of every (class, window) in sg_pt / sg_ls (the layout statistics walk the windows in parallel)
+    std::vector<int> seg_begin[2]; seg_begin[0].assign(n + 1, 0); seg_begin[1].assign(n + 1, 0);
+    // a batch builds the runs of its windows in parallel into per-(window, class) lists, concatenated in window order below
+    std::vector<std::vector<Seg>> loc_sg(h->warp_path ? 2 * (size_t)n : 0); std::vector<std::vector<int>> loc_fp(h->warp_path ? 2 * (size_t)n : 0);
+#pragma omp parallel for num_threads(g_host_nt) schedule(dynamic, 1) if (n > 8)
+    for (int wc = 0; wc < (h->warp_path ? 2 * n : 0); wc++) {
         // runs of landmarks with identical keyframe sequence (kept as Seg records: n_lm unbounded, no chunk fields)
+        const int w = wc >> 1;
         const plba_problem &p = probs[w]; const WinInfo &wi = h->wins[w];
-        for (int cls = 0; cls < 2; cls++) {
+        {
+            const int cls = wc & 1;
             const ClassLayout &L = cls ? Lls[w] : Lps[w];
             const int nl = cls ? p.n_ls : p.n_pt, lm0 = cls ? wi.ls0 : wi.pt0, ob0 = cls ? wi.lo0 : wi.po0;
             const int32_t *kf = cls ? p.lo_kf : p.po_kf;
             std::vector<int> &perm = cls ? h->ls_perm : h->pt_perm, &operm = cls ? h->lo_perm : h->po_perm, &ptr = cls ? ls_ptr : pt_ptr;
-            std::vector<Seg> &sgs = cls ? sg_ls : sg_pt; std::vector<int> &fps = cls ? fp_ls : fp_pt;
+            std::vector<Seg> &sgs = loc_sg[wc]; std::vector<int> &fps = loc_fp[wc];      // fp0 is relative to this list until the concatenation
             // (1) observation offsets of the re-ordered landmarks (serial prefix), (2) the observation permutation (parallel for large
             // windows: 12.5 M entries at config 5), (3) the runs (serial, index compares only)
             int ob = ob0;
@@ -1013,10 +1034,19 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
                     sgs.push_back(s); run_first_old = old;
                 }
             }
-            ptr[lm0 + nl] = ob;
+            (void)ob;      // = ob0 + the window's observations: the entry after its last landmark is the next window's first (written there); the very last one below
         }
     }
     if (h->warp_path) {
+        pt_ptr[tot.n_pt] = tot.n_pobs; ls_ptr[tot.n_ls] = tot.n_lobs;
+        for (int w = 0; w < n; w++) for (int cls = 0; cls < 2; cls++) {
+            std::vector<Seg> &sgs = cls ? sg_ls : sg_pt; std::vector<int> &fps = cls ? fp_ls : fp_pt;
+            seg_begin[cls][w] = (int)sgs.size();
+            const int base = (int)fps.size();
+            for (Seg sg : loc_sg[2 * (size_t)w + cls]) { sg.fp0 += base; sgs.push_back(sg); }
+            fps.insert(fps.end(), loc_fp[2 * (size_t)w + cls].begin(), loc_fp[2 * (size_t)w + cls].end());
+        }
+        seg_begin[0][n] = (int)sg_pt.size(); seg_begin[1][n] = (int)sg_ls.size();
         // cut the runs into items of up to W_ITEM_PASSES_MAX passes (fewer when the upload is small)
         int64_t total_passes = 0;
         for (int cls = 0; cls < 2; cls++) for (const Seg &sg : (cls ? sg_ls : sg_pt)) { const int lpp = sg.nobs ? 32 / sg.nobs : 32; total_passes += (sg.n_lm + lpp - 1) / lpp; }
@@ -1060,6 +1090,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
             const int32_t *kf = cls ? p.lo_kf : p.po_kf;
             std::vector<int> &perm = cls ? h->ls_perm : h->pt_perm, &operm = cls ? h->lo_perm : h->po_perm, &ptr = cls ? ls_ptr : pt_ptr;
             std::vector<Chunk> &chs = cls ? ch_ls : ch_pt; std::vector<Seg> &sgs = cls ? sg_ls : sg_pt; std::vector<int> &fps = cls ? fp_ls : fp_pt;
+            seg_begin[cls][w] = (int)sgs.size();
             int chunk_tasks = 0, chunk_dtasks = 0;
             int ob = ob0;
             Chunk c{}; bool open = false; int seg_first_old = -1;
@@ -1097,6 +1128,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
         if (too_long) break;
     }
     if (too_long) { h->err = "a landmark has more than 256 observations"; return PLBA_E_UNSUPPORTED; }
+    seg_begin[0][n] = (int)sg_pt.size(); seg_begin[1][n] = (int)sg_ls.size();
 
     HOSTPROF("chunks");
     {   // layout statistics (plba_layout_stats): structural non-zero 6x6 blocks of S = union over segments of their pose pairs
@@ -1104,16 +1136,18 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
         for (int w = 0; w < n; w++) wbase[w + 1] = wbase[w] + (size_t)h->wins[w].n_free * h->wins[w].n_free;
         std::vector<unsigned char> &mark = h->mark; mark.assign(wbase[n], 0);
         int64_t n_off = 0, n_diag = 0, nnzb = 0; int band = 0;
-        for (int cls = 0; cls < 2; cls++) {
+        // windows in parallel for a batch: the marks of a window are its own stretch of `mark`
+#pragma omp parallel for num_threads(g_host_nt) schedule(dynamic, 4) reduction(+ : n_off, n_diag, nnzb) reduction(max : band) if (n > 8)
+        for (int w = 0; w < n; w++) for (int cls = 0; cls < 2; cls++) {
             const std::vector<Seg> &sgs = cls ? sg_ls : sg_pt; const std::vector<int> &fps = cls ? fp_ls : fp_pt;
             const std::vector<int> &ptr = cls ? ls_ptr : pt_ptr; const std::vector<int> &operm = cls ? h->lo_perm : h->po_perm;
-            int w = 0;
+            const plba_problem &p = probs[w]; const WinInfo &wi = h->wins[w];
+            const int32_t *kf = cls ? p.lo_kf : p.po_kf; const int ob0 = cls ? wi.lo0 : wi.po0;
             std::vector<int> sl, sl_prev;
-            for (const Seg &sg : sgs) {
+            for (int si = seg_begin[cls][w]; si < seg_begin[cls][w + 1]; si++) {
+                const Seg &sg = sgs[si];
                 n_off += (int64_t)sg.nfree * (sg.nfree - 1) / 2; n_diag += sg.nfree;
-                while (w + 1 < n && (cls ? h->wins[w + 1].ls0 : h->wins[w + 1].pt0) <= sg.lm0) { w++; sl_prev.clear(); }     // segments are emitted window by window
-                const plba_problem &p = probs[w]; const WinInfo &wi = h->wins[w];
-                const int32_t *kf = cls ? p.lo_kf : p.po_kf; const int ob0 = cls ? wi.lo0 : wi.po0, o0 = ptr[sg.lm0];
+                const int o0 = ptr[sg.lm0];
                 sl.resize(sg.nfree);
                 for (int i = 0; i < sg.nfree; i++) sl[i] = p.kf_slot[kf[operm[o0 + fps[sg.fp0 + i]] - ob0]];
                 if (sl == sl_prev) continue;                       // same free-keyframe set as the previous segment (a run cut into segments): nothing new to mark
@@ -1150,9 +1184,13 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     const size_t i_Tmap = ci.take<double>((size_t)12 * tot.n_kf), i_X0 = ci.take<double>((size_t)6 * tot.n_free);
     const size_t i_pts0 = ci.take<double>((size_t)3 * tot.n_pt), i_lns0 = ci.take<double>((size_t)ld * tot.n_ls), i_lmap = ci.take<double>((size_t)6 * tot.n_ls);
     const size_t i_pt_ptr = ci.take<int>(tot.n_pt + 1), i_ls_ptr = ci.take<int>(tot.n_ls + 1), i_pt_win = ci.take<int>(tot.n_pt), i_ls_win = ci.take<int>(tot.n_ls);
-    const size_t i_po_kf = ci.take<int>(tot.n_pobs), i_po_lm = ci.take<int>(tot.n_pobs), i_lo_kf = ci.take<int>(tot.n_lobs), i_lo_lm = ci.take<int>(tot.n_lobs);
-    const size_t i_po_uv = ci.take<double>((size_t)2 * tot.n_pobs), i_lo_ab = ci.take<double>((size_t)4 * tot.n_lobs);
-    const size_t i_po_om = ci.take<double>(tot.n_pobs), i_lo_om = ci.take<double>(tot.n_lobs);
+    // observations travel in the CALLER's order (straight copies on the host); the first kernel after the upload gathers them into the
+    // internal order (k_reset, gather = 1): per landmark the first staged index of its run, per observation (u, v) / (a, b), the global
+    // keyframe index and sigma^2 (1 where the caller gave none) — 28 / 44 bytes per observation + 4 per landmark
+    const size_t i_pt_src = ci.take<int>(tot.n_pt), i_ls_src = ci.take<int>(tot.n_ls);
+    const size_t i_r_po_kf = ci.take<int>(tot.n_pobs), i_r_lo_kf = ci.take<int>(tot.n_lobs);
+    const size_t i_r_po_uv = ci.take<double>((size_t)2 * tot.n_pobs), i_r_lo_ab = ci.take<double>((size_t)4 * tot.n_lobs);
+    const size_t i_r_po_s2 = ci.take<double>(tot.n_pobs), i_r_lo_s2 = ci.take<double>(tot.n_lobs);
     const size_t i_ch_pt = ci.take<Chunk>(ch_pt.size()), i_ch_ls = ci.take<Chunk>(ch_ls.size()), i_sg_pt = ci.take<Seg>(sg_pt.size()), i_sg_ls = ci.take<Seg>(sg_ls.size());
     const size_t i_fp_pt = ci.take<int>(fp_pt.size()), i_fp_ls = ci.take<int>(fp_ls.size());
     const size_t i_wi_pt = ci.take<WItem>(wi_pt.size()), i_wi_ls = ci.take<WItem>(wi_ls.size());
@@ -1172,10 +1210,14 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     h->S_doubles = (size_t)S_off;
     h->sys_doubles = h->S_doubles + (size_t)18 * tot.n_free + (size_t)ACC_N * n + (size_t)n + (size_t)PLBA_MAX_RANKS * n;
     Carver cs = ci;   // device-only state follows the inputs
+    const size_t i_po_kf = cs.take<int>(tot.n_pobs), i_po_lm = cs.take<int>(tot.n_pobs), i_lo_kf = cs.take<int>(tot.n_lobs), i_lo_lm = cs.take<int>(tot.n_lobs);
+    const size_t i_po_uv = cs.take<double>((size_t)2 * tot.n_pobs), i_lo_ab = cs.take<double>((size_t)4 * tot.n_lobs);
+    const size_t i_po_om = cs.take<double>(tot.n_pobs), i_lo_om = cs.take<double>(tot.n_lobs);
     size_t s_poseT[2], s_X[2], s_pts[2], s_lns[2], s_lpre[2];
     for (int b = 0; b < 2; b++) s_lpre[b] = cs.take<double>((size_t)LPRE_N * tot.n_ls);
     for (int b = 0; b < 2; b++) { s_poseT[b] = cs.take<double>((size_t)12 * tot.n_kf); s_X[b] = cs.take<double>((size_t)6 * tot.n_free); s_pts[b] = cs.take<double>((size_t)3 * tot.n_pt); s_lns[b] = cs.take<double>((size_t)ld * tot.n_ls); }
     const size_t s_po_lvl = cs.take<unsigned char>(tot.n_pobs), s_lo_lvl = cs.take<unsigned char>(tot.n_lobs);
+    const size_t s_po_chi2 = cs.take<double>(tot.n_pobs), s_lo_chi2 = cs.take<double>(tot.n_lobs);      // cached chi2 of every edge (internal order; the output region holds the caller-order copy of k_export)
     const size_t s_sys = cs.take<double>(h->sys_doubles), s_xp = cs.take<double>((size_t)6 * tot.n_free);
     // node storage of the block cyclic reduction (large banded windows only)
     h->bcr.clear();
@@ -1213,8 +1255,8 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     int *win_bs = (int *)(hb + i_win_bs), *win_N = (int *)(hb + i_win_N);
     double *Tmap = (double *)(hb + i_Tmap), *X0 = (double *)(hb + i_X0), *pts0 = (double *)(hb + i_pts0), *lns0 = (double *)(hb + i_lns0), *lmap = (double *)(hb + i_lmap);
     int *d_pt_ptr = (int *)(hb + i_pt_ptr), *d_ls_ptr = (int *)(hb + i_ls_ptr), *pt_win = (int *)(hb + i_pt_win), *ls_win = (int *)(hb + i_ls_win);
-    int *po_kf = (int *)(hb + i_po_kf), *po_lm = (int *)(hb + i_po_lm), *lo_kf = (int *)(hb + i_lo_kf), *lo_lm = (int *)(hb + i_lo_lm);
-    double *po_uv = (double *)(hb + i_po_uv), *lo_ab = (double *)(hb + i_lo_ab), *po_om = (double *)(hb + i_po_om), *lo_om = (double *)(hb + i_lo_om);
+    int *pt_src = (int *)(hb + i_pt_src), *ls_src = (int *)(hb + i_ls_src), *r_po_kf = (int *)(hb + i_r_po_kf), *r_lo_kf = (int *)(hb + i_r_lo_kf);
+    double *r_po_uv = (double *)(hb + i_r_po_uv), *r_lo_ab = (double *)(hb + i_r_lo_ab), *r_po_s2 = (double *)(hb + i_r_po_s2), *r_lo_s2 = (double *)(hb + i_r_lo_s2);
     WinCtrl *ctrl0 = (WinCtrl *)(hb + i_ctrl0);
     std::memcpy(d_pt_ptr, pt_ptr.data(), sizeof(int) * pt_ptr.size());
     std::memcpy(d_ls_ptr, ls_ptr.data(), sizeof(int) * ls_ptr.size());
@@ -1248,12 +1290,14 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
         for (int g = wi.pt0; g < wi.pt0 + p.n_pt; g++) {
             const int old = h->pt_perm[g] - wi.pt0;
             pt_win[g] = w;
+            pt_src[g] = pt_ptr[g + 1] > pt_ptr[g] ? h->po_perm[pt_ptr[g]] : 0;      // first observation of the landmark's run in the caller's (staged) order
             for (int i = 0; i < 3; i++) pts0[(size_t)3 * g + i] = p.pt_xyz[(size_t)3 * old + i];
         }
 #pragma omp parallel for num_threads(g_host_nt) schedule(static) if (par_lm && p.n_ls > PAR_LM)
         for (int g = wi.ls0; g < wi.ls0 + p.n_ls; g++) {
             const int old = h->ls_perm[g] - wi.ls0;
             ls_win[g] = w;
+            ls_src[g] = ls_ptr[g + 1] > ls_ptr[g] ? h->lo_perm[ls_ptr[g]] : 0;
             if (prof == PLBA_PROFILE_H_END) for (int i = 0; i < 6; i++) lns0[(size_t)6 * g + i] = p.ls_end[(size_t)6 * old + i];
             else {
                 // changePlukerToOrth (:6040, :1577) runs on the device (k_reset): four inverse trig calls per line are not host work
@@ -1261,32 +1305,26 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
             }
         }
         if (n == 1) HOSTPROF("fl.lm");
-#pragma omp parallel for num_threads(g_host_nt) schedule(static) if (par_lm && p.n_pt > PAR_LM)
-        for (int g = wi.pt0; g < wi.pt0 + p.n_pt; g++) {
-            // the observations of a landmark are one contiguous run in the caller's arrays too: copy runs, not elements
-            const int o0 = pt_ptr[g], no = pt_ptr[g + 1] - o0;
-            if (no == 0) continue;
-            const int i0 = h->po_perm[o0] - wi.po0;
-            if (g + 8 < wi.pt0 + p.n_pt) {      // the caller's arrays are read in signature order, i.e. at scattered places: pull the run of landmark g + 8 in now
-                const int on = pt_ptr[g + 8];
-                if (on < wi.po0 + p.n_pobs) { const int in = h->po_perm[on] - wi.po0; __builtin_prefetch(p.po_uv + (size_t)2 * in); __builtin_prefetch(p.po_uv + (size_t)2 * in + 8); __builtin_prefetch(p.po_kf + in); }
-            }
-            // one fused loop per run (tracks hold ~5 observations: a memcpy call per array costs more than the copy)
-            const double *suv = p.po_uv + (size_t)2 * i0; double *duv = po_uv + (size_t)2 * o0;
-            const int32_t *skf = p.po_kf + i0; int *dkf = po_kf + o0, *dlm = po_lm + o0; double *dom = po_om + o0;
-            if (p.po_sig2) for (int j = 0; j < no; j++) { duv[2 * j] = suv[2 * j]; duv[2 * j + 1] = suv[2 * j + 1]; dkf[j] = wi.kf0 + skf[j]; dlm[j] = g; dom[j] = (double)(float)(1.0 / p.po_sig2[i0 + j]); }   // const float& invSigma2 (:6009, Q13)
-            else for (int j = 0; j < no; j++) { duv[2 * j] = suv[2 * j]; duv[2 * j + 1] = suv[2 * j + 1]; dkf[j] = wi.kf0 + skf[j]; dlm[j] = g; dom[j] = 1.0; }
-        }
-#pragma omp parallel for num_threads(g_host_nt) schedule(static) if (par_lm && p.n_ls > PAR_LM)
-        for (int g = wi.ls0; g < wi.ls0 + p.n_ls; g++) {
-            const int o0 = ls_ptr[g], no = ls_ptr[g + 1] - o0;
-            if (no == 0) continue;
-            const int i0 = h->lo_perm[o0] - wi.lo0;
-            const double *sab = p.lo_ab + (size_t)4 * i0; double *dab = lo_ab + (size_t)4 * o0;
-            const int32_t *skf = p.lo_kf + i0; int *dkf = lo_kf + o0, *dlm = lo_lm + o0; double *dom = lo_om + o0;
-            for (int j = 0; j < no; j++) {
-                dab[4 * j] = sab[4 * j]; dab[4 * j + 1] = sab[4 * j + 1]; dab[4 * j + 2] = sab[4 * j + 2]; dab[4 * j + 3] = sab[4 * j + 3];
-                dkf[j] = wi.kf0 + skf[j]; dlm[j] = g; dom[j] = p.lo_sig2 ? (double)(float)(1.0 / p.lo_sig2[i0 + j]) : 1.0;
+        // observations: straight copies in the caller's order, in slices so that a large window's copy runs on every host thread
+        {
+            const int SL = 65536, nsp = (p.n_pobs + SL - 1) / SL, nsl = (p.n_lobs + SL - 1) / SL;
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) if (par_lm && p.n_pobs + p.n_lobs > PAR_OBS)
+            for (int sl = 0; sl < nsp + nsl; sl++) {
+                if (sl < nsp) {
+                    const size_t a = (size_t)sl * SL, c = std::min<size_t>(SL, (size_t)p.n_pobs - a), d = (size_t)wi.po0 + a;
+                    std::memcpy(r_po_uv + 2 * d, p.po_uv + 2 * a, sizeof(double) * 2 * c);
+                    if (wi.kf0 == 0) std::memcpy(r_po_kf + d, p.po_kf + a, sizeof(int) * c);
+                    else for (size_t j = 0; j < c; j++) r_po_kf[d + j] = wi.kf0 + p.po_kf[a + j];
+                    if (p.po_sig2) std::memcpy(r_po_s2 + d, p.po_sig2 + a, sizeof(double) * c);
+                    else for (size_t j = 0; j < c; j++) r_po_s2[d + j] = 1.0;
+                } else {
+                    const size_t a = (size_t)(sl - nsp) * SL, c = std::min<size_t>(SL, (size_t)p.n_lobs - a), d = (size_t)wi.lo0 + a;
+                    std::memcpy(r_lo_ab + 4 * d, p.lo_ab + 4 * a, sizeof(double) * 4 * c);
+                    if (wi.kf0 == 0) std::memcpy(r_lo_kf + d, p.lo_kf + a, sizeof(int) * c);
+                    else for (size_t j = 0; j < c; j++) r_lo_kf[d + j] = wi.kf0 + p.lo_kf[a + j];
+                    if (p.lo_sig2) std::memcpy(r_lo_s2 + d, p.lo_sig2 + a, sizeof(double) * c);
+                    else for (size_t j = 0; j < c; j++) r_lo_s2[d + j] = 1.0;
+                }
             }
         }
         if (n == 1) HOSTPROF("fl.obs");
@@ -1319,13 +1357,15 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     P.pt_ptr = (int *)(db + i_pt_ptr); P.ls_ptr = (int *)(db + i_ls_ptr); P.pt_win = (int *)(db + i_pt_win); P.ls_win = (int *)(db + i_ls_win);
     P.po_kf = (int *)(db + i_po_kf); P.po_lm = (int *)(db + i_po_lm); P.lo_kf = (int *)(db + i_lo_kf); P.lo_lm = (int *)(db + i_lo_lm);
     P.po_uv = (double *)(db + i_po_uv); P.lo_ab = (double *)(db + i_lo_ab); P.po_om = (double *)(db + i_po_om); P.lo_om = (double *)(db + i_lo_om);
+    P.pt_src = (int *)(db + i_pt_src); P.ls_src = (int *)(db + i_ls_src); P.r_po_kf = (int *)(db + i_r_po_kf); P.r_lo_kf = (int *)(db + i_r_lo_kf);
+    P.r_po_uv = (double *)(db + i_r_po_uv); P.r_lo_ab = (double *)(db + i_r_lo_ab); P.r_po_s2 = (double *)(db + i_r_po_s2); P.r_lo_s2 = (double *)(db + i_r_lo_s2);
     P.chunks_pt = (Chunk *)(db + i_ch_pt); P.chunks_ls = (Chunk *)(db + i_ch_ls); P.segs_pt = (Seg *)(db + i_sg_pt); P.segs_ls = (Seg *)(db + i_sg_ls);
     P.freepos_pt = (int *)(db + i_fp_pt); P.freepos_ls = (int *)(db + i_fp_ls);
     P.witems_pt = (WItem *)(db + i_wi_pt); P.witems_ls = (WItem *)(db + i_wi_ls); P.n_witems_pt = (int)wi_pt.size(); P.n_witems_ls = (int)wi_ls.size();
     P.ctrl0 = (WinCtrl *)(db + i_ctrl0);
     for (int b = 0; b < 2; b++) { P.poseT[b] = (double *)(db + s_poseT[b]); P.Xkf[b] = (double *)(db + s_X[b]); P.pts[b] = (double *)(db + s_pts[b]); P.lns[b] = (double *)(db + s_lns[b]); P.lpre[b] = (double *)(db + s_lpre[b]); }
     P.po_lvl = (unsigned char *)(db + s_po_lvl); P.lo_lvl = (unsigned char *)(db + s_lo_lvl);
-    P.po_chi2 = (double *)(db + h->o_pchi); P.lo_chi2 = (double *)(db + h->o_lchi);
+    P.po_chi2 = (double *)(db + s_po_chi2); P.lo_chi2 = (double *)(db + s_lo_chi2);
     h->sysbuf = (double *)(db + s_sys);
     P.S = h->sysbuf; P.gs = P.S + h->S_doubles; P.hpp_diag = P.gs + (size_t)6 * tot.n_free; P.hpp_diag_init = P.hpp_diag + (size_t)6 * tot.n_free;
     P.acc = P.hpp_diag_init + (size_t)6 * tot.n_free; P.accB = P.acc + (size_t)4 * n; P.accmax = P.acc + (size_t)ACC_N * n; P.maxslots = P.accmax + n;
@@ -1358,7 +1398,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     h->timing.h2d_bytes += (int64_t)(h->in_bytes + sizeof(DevP));
     cudaEventRecord(h->ev_h2d, h->stream); h->h2d_pending = true;
     h->uploaded = true;
-    return launch_reset(h);
+    return launch_reset(h, 1);
 }
 
 int plba_reset_state(plba_handle h) {
@@ -1513,7 +1553,7 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
     char *db = h->d_arena;
     ExportP E{};
     E.T_wc = (double *)(db + h->o_T); E.x = (double *)(db + h->o_x); E.pt = (double *)(db + h->o_pt); E.ls = (double *)(db + h->o_ls); E.plk = (double *)(db + h->o_plk);
-    E.pf = (unsigned char *)(db + h->o_pf); E.lf = (unsigned char *)(db + h->o_lf);
+    E.pf = (unsigned char *)(db + h->o_pf); E.lf = (unsigned char *)(db + h->o_lf); E.pchi = (double *)(db + h->o_pchi); E.lchi = (double *)(db + h->o_lchi);
     E.ls_dim = ld; E.q9 = (P.profile == PLBA_PROFILE_H_PLK && !P.fixed_quirks) ? 1 : 0; E.do_final = G ? 1 : 0;
     PLBA_LAUNCH(k_export, dim3(h->grid_chunks), dim3(256), 0, st, (const DevP *)h->d_P, E); h->timing.n_launches++;
     CK(cudaMemcpyAsync(h->h_out, db + h->out_off, h->out_bytes, cudaMemcpyDeviceToHost, st));
@@ -1565,17 +1605,19 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
             }
         }
         if (G) {
-#pragma omp parallel for num_threads(g_host_nt) schedule(static) if (par_lm && wi.n_pobs > PAR_OBS)
-            for (int o = wi.po0; o < wi.po0 + wi.n_pobs; o++) {
-                const int i = h->po_perm[o] - wi.po0;
-                if (r.po_chi2) r.po_chi2[i] = pchi[o];
-                if (r.po_flags) r.po_flags[i] = pf[o];
-            }
-#pragma omp parallel for num_threads(g_host_nt) schedule(static) if (par_lm && wi.n_lobs > PAR_OBS)
-            for (int o = wi.lo0; o < wi.lo0 + wi.n_lobs; o++) {
-                const int i = h->lo_perm[o] - wi.lo0;
-                if (r.lo_chi2) r.lo_chi2[i] = lchi[o];
-                if (r.lo_flags) r.lo_flags[i] = lf[o];
+            // k_export wrote chi2 and flags in the caller's order: straight copies (in slices for a large window)
+            const int SL = 262144, nsp = (wi.n_pobs + SL - 1) / SL, nsl = (wi.n_lobs + SL - 1) / SL;
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) if (par_lm && wi.n_pobs + wi.n_lobs > PAR_OBS)
+            for (int sl = 0; sl < nsp + nsl; sl++) {
+                if (sl < nsp) {
+                    const size_t a = (size_t)sl * SL, c = std::min<size_t>(SL, (size_t)wi.n_pobs - a), d = (size_t)wi.po0 + a;
+                    if (r.po_chi2) std::memcpy(r.po_chi2 + a, pchi + d, sizeof(double) * c);
+                    if (r.po_flags) std::memcpy(r.po_flags + a, pf + d, c);
+                } else {
+                    const size_t a = (size_t)(sl - nsp) * SL, c = std::min<size_t>(SL, (size_t)wi.n_lobs - a), d = (size_t)wi.lo0 + a;
+                    if (r.lo_chi2) std::memcpy(r.lo_chi2 + a, lchi + d, sizeof(double) * c);
+                    if (r.lo_flags) std::memcpy(r.lo_flags + a, lf + d, c);
+                }
             }
         }
     }

@@ -90,6 +90,10 @@ struct DevP {
     // observations (SoA)
     const int *po_kf, *lo_kf, *po_lm, *lo_lm;
     const double *po_uv, *lo_ab, *po_om, *lo_om;
+    // the caller's observation arrays as staged by plba_upload (caller's order, keyframe indices already global) and, per landmark, the first
+    // staged index of its run: k_reset(gather = 1) re-orders them into the arrays above once per upload
+    const int *r_po_kf, *r_lo_kf, *pt_src, *ls_src;
+    const double *r_po_uv, *r_lo_ab, *r_po_s2, *r_lo_s2;
     unsigned char *po_lvl, *lo_lvl;
     double *po_chi2, *lo_chi2;
     const Chunk *chunks_pt, *chunks_ls;
@@ -1070,9 +1074,11 @@ PLBA_KERNEL void k_gate(const DevP *Pp) {
     PHASE_END
 }
 
-// final per-observation test (src/mapHandler.cpp:6156-6161, 6224-6230): level-1 edges are re-evaluated at the final estimate
+// final per-observation test (src/mapHandler.cpp:6156-6161, 6224-6230): level-1 edges are re-evaluated at the final estimate.
+// chi2 and flags leave in the CALLER's observation order (run of the landmark in the staged arrays + position inside the run), so that
+// plba_download copies them straight through
 template <int LT>
-PLBA_D void final_obs(const DevP &P, int o, unsigned char *flags_out) {
+PLBA_D void final_obs(const DevP &P, int o, unsigned char *flags_out, double *chi2_out) {
     typedef ObsAcc<LT> OA;
     const int kf = OA::kf(P)[o];
     const WinCtrl &c = P.ctrl[P.kf_win[kf]];
@@ -1094,12 +1100,13 @@ PLBA_D void final_obs(const DevP &P, int o, unsigned char *flags_out) {
     }
     if (chi2 > P.chi2_gate) f |= PLBA_OBS_BAD;
     OA::chi2(P)[o] = chi2;
-    flags_out[o] = f;
+    const size_t i = (size_t)(LT == LT_POINT ? P.pt_src : P.ls_src)[lm] + (size_t)(o - (LT == LT_POINT ? P.pt_ptr : P.ls_ptr)[lm]);
+    flags_out[i] = f; chi2_out[i] = chi2;
 }
 
 // write-back: T_kf_w = estimate^-1 (:6302) / expmap_se3(X) (:2851-2852); NDw = changeOrthToPluker(orth) (:6318);
 // final chi2 test.  One launch, outputs land in the contiguous D2H staging region.
-struct ExportP { double *T_wc, *x, *pt, *ls, *plk; unsigned char *pf, *lf; int ls_dim, q9, do_final, pad; };
+struct ExportP { double *T_wc, *x, *pt, *ls, *plk, *pchi, *lchi; unsigned char *pf, *lf; int ls_dim, q9, do_final, pad; };
 PLBA_KERNEL void k_export(const DevP *Pp, ExportP E) {
     PLBA_PARAMS(P, Pp);
     PHASE_BEGIN
@@ -1126,17 +1133,40 @@ PLBA_KERNEL void k_export(const DevP *Pp, ExportP E) {
             }
         }
         if (E.do_final) {
-            for (int o = g0; o < P.n_pobs; o += gs) final_obs<LT_POINT>(P, o, E.pf);
-            for (int o = g0; o < P.n_lobs; o += gs) final_obs<LT_LINE_ORTH>(P, o, E.lf);
+            for (int o = g0; o < P.n_pobs; o += gs) final_obs<LT_POINT>(P, o, E.pf, E.pchi);
+            for (int o = g0; o < P.n_lobs; o += gs) final_obs<LT_LINE_ORTH>(P, o, E.lf, E.lchi);
         }
     PHASE_END
 }
 
-// state <- uploaded initial values (plba_reset_state): one launch
-PLBA_KERNEL void k_reset(const DevP *Pp, int ls_dim, size_t sys_doubles, double *sysbuf) {
+// state <- uploaded initial values (plba_reset_state): one launch.  gather = 1 (the launch that follows an upload): the observations are
+// first brought from the caller's order into the internal one — a landmark's observations are ONE run in the caller's arrays (validated:
+// landmark-major) and one run here, so a thread moves the run of one landmark; weights as the reference forms them:
+// const float& invSigma2 = 1 / sigma2 (src/mapHandler.cpp:6009, Q13; double division and the float conversion round as on the host)
+PLBA_KERNEL void k_reset(const DevP *Pp, int ls_dim, size_t sys_doubles, double *sysbuf, int gather) {
     PLBA_PARAMS(P, Pp);
     PHASE_BEGIN
         const size_t g0 = (size_t)PLBA_BID * PLBA_NT + tid, gs = (size_t)PLBA_NB * PLBA_NT;
+        if (gather) {
+            int *po_kf = const_cast<int *>(P.po_kf), *po_lm = const_cast<int *>(P.po_lm), *lo_kf = const_cast<int *>(P.lo_kf), *lo_lm = const_cast<int *>(P.lo_lm);
+            double *po_uv = const_cast<double *>(P.po_uv), *po_om = const_cast<double *>(P.po_om), *lo_ab = const_cast<double *>(P.lo_ab), *lo_om = const_cast<double *>(P.lo_om);
+            for (size_t g = g0; g < (size_t)P.n_pt; g += gs) {
+                const int o0 = P.pt_ptr[g], no = P.pt_ptr[g + 1] - o0; const size_t i0 = (size_t)P.pt_src[g];
+                for (int j = 0; j < no; j++) {
+                    const size_t o = (size_t)o0 + j, i = i0 + j;
+                    po_uv[2 * o] = P.r_po_uv[2 * i]; po_uv[2 * o + 1] = P.r_po_uv[2 * i + 1];
+                    po_kf[o] = P.r_po_kf[i]; po_lm[o] = (int)g; po_om[o] = (double)(float)(1.0 / P.r_po_s2[i]);
+                }
+            }
+            for (size_t g = g0; g < (size_t)P.n_ls; g += gs) {
+                const int o0 = P.ls_ptr[g], no = P.ls_ptr[g + 1] - o0; const size_t i0 = (size_t)P.ls_src[g];
+                for (int j = 0; j < no; j++) {
+                    const size_t o = (size_t)o0 + j, i = i0 + j;
+                    for (int k = 0; k < 4; k++) lo_ab[4 * o + k] = P.r_lo_ab[4 * i + k];
+                    lo_kf[o] = P.r_lo_kf[i]; lo_lm[o] = (int)g; lo_om[o] = (double)(float)(1.0 / P.r_lo_s2[i]);
+                }
+            }
+        }
         for (size_t i = g0; i < (size_t)12 * P.n_kf; i += gs) { const double v = P.kf_Tmap[i]; P.poseT[0][i] = v; P.poseT[1][i] = v; }
         for (size_t i = g0; i < (size_t)6 * P.n_free; i += gs) { const double v = P.X0[i]; P.Xkf[0][i] = v; P.Xkf[1][i] = v; P.xp[i] = 0.0; }
         for (size_t i = g0; i < (size_t)3 * P.n_pt; i += gs) { const double v = P.pts0[i]; P.pts[0][i] = v; P.pts[1][i] = v; }
