@@ -241,12 +241,22 @@ struct ClassLayout {
 };
 static void signature_order(int n_lm, int n_obs, const int32_t *lm, const int32_t *kf, bool permute, ClassLayout &L) {
     const bool par = n_obs > PAR_OBS;      // one large window: the loops below run in parallel (a region costs more than a small window's whole sort)
-    L.optr.assign(n_lm + 1, n_obs);
     // lm[] is non-decreasing (validated): optr[l] = first observation whose landmark is >= l
-#pragma omp parallel for num_threads(g_host_nt) schedule(static) if (par)
-    for (int i = 0; i < n_obs; i++) {
-        const int lo = i ? lm[i - 1] + 1 : 0;
-        for (int l = lo; l <= lm[i]; l++) L.optr[l] = i;
+    if (par) {
+        L.optr.assign(n_lm + 1, n_obs);
+#pragma omp parallel for num_threads(g_host_nt) schedule(static)
+        for (int i = 0; i < n_obs; i++) {
+            const int lo = i ? lm[i - 1] + 1 : 0;
+            for (int l = lo; l <= lm[i]; l++) L.optr[l] = i;
+        }
+    } else {
+        // serial form without data-dependent branches (tracks hold ~5 observations: a loop per track mispredicts its exit every time —
+        // measured 157 -> 42 us on 36 000 observations): backwards, unconditional stores, the last one of a landmark is its first observation;
+        // landmarks without observations take their successor's entry
+        L.optr.assign(n_lm + 1, -1);
+        L.optr[n_lm] = n_obs;
+        for (int i = n_obs - 1; i >= 0; i--) L.optr[lm[i]] = i;
+        for (int l = n_lm - 1; l >= 0; l--) L.optr[l] = L.optr[l] < 0 ? L.optr[l + 1] : L.optr[l];
     }
     L.perm.resize(n_lm);
 #pragma omp parallel for num_threads(g_host_nt) schedule(static) if (par)
@@ -255,13 +265,24 @@ static void signature_order(int n_lm, int n_obs, const int32_t *lm, const int32_
     {   // fast path: every track is a contiguous keyframe run (the usual sliding-window case) => the signature IS (first KF, length):
         // one pass over the observations and a counting sort, no hashing
         int maxlen = 0, maxkf = 0, broken = 0;
-#pragma omp parallel for num_threads(g_host_nt) schedule(static) reduction(max : maxlen, maxkf, broken) if (par)
-        for (int l = 0; l < n_lm; l++) {
-            if (broken > 0) continue;      // (a max-reduction's private copy starts at INT_MIN, not at 0)
-            const int a = L.optr[l], b = L.optr[l + 1];
-            if (b - a > maxlen) maxlen = b - a;
-            if (b > a && kf[a] > maxkf) maxkf = kf[a];
-            for (int i = a + 1; i < b; i++) if (kf[i] != kf[i - 1] + 1) { broken = 1; break; }
+        if (par) {
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) reduction(max : maxlen, maxkf, broken)
+            for (int l = 0; l < n_lm; l++) {
+                if (broken > 0) continue;      // (a max-reduction's private copy starts at INT_MIN, not at 0)
+                const int a = L.optr[l], b = L.optr[l + 1];
+                if (b - a > maxlen) maxlen = b - a;
+                if (b > a && kf[a] > maxkf) maxkf = kf[a];
+                for (int i = a + 1; i < b; i++) if (kf[i] != kf[i - 1] + 1) { broken = 1; break; }
+            }
+        } else {      // the same three results from branch-free passes (one over the observations, one over the landmarks)
+            for (int i = 1; i < n_obs; i++) broken |= (int)(lm[i] == lm[i - 1]) & (int)(kf[i] != kf[i - 1] + 1);
+            const int last = std::max(n_obs - 1, 0);
+            for (int l = 0; l < n_lm && n_obs > 0; l++) {
+                const int a = L.optr[l], b = L.optr[l + 1];
+                maxlen = std::max(maxlen, b - a);
+                const int v = kf[std::min(a, last)];
+                maxkf = std::max(maxkf, b > a ? v : 0);
+            }
         }
         const bool contiguous = broken <= 0;
         if (contiguous && (int64_t)(maxkf + 2) * (maxlen + 1) <= 4 * (int64_t)n_lm + 4096) {
