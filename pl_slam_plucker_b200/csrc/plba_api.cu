@@ -82,7 +82,7 @@ enum { PAR_LM = 40000, PAR_OBS = 200000 };
 static thread_local int g_host_nt = 1;
 static int host_threads_for(int64_t n_obs) {
 #ifdef _OPENMP
-    static const int env = [] { const char *e = std::getenv("PLBA_HOST_THREADS"); return e ? std::atoi(e) : 0; }();
+    const char *e = std::getenv("PLBA_HOST_THREADS"); const int env = e ? std::atoi(e) : 0;      // read per call: the tests switch it between uploads
     const int mx = omp_get_max_threads();
     if (env > 0) return std::min(env, std::max(mx, 1));
     return (int)std::max<int64_t>(1, std::min<int64_t>(mx, n_obs / 150000));
@@ -287,8 +287,31 @@ static void signature_order(int n_lm, int n_obs, const int32_t *lm, const int32_
         const bool contiguous = broken <= 0;
         if (contiguous && (int64_t)(maxkf + 2) * (maxlen + 1) <= 4 * (int64_t)n_lm + 4096) {
             const int W = maxlen + 1, nkeys = (maxkf + 2) * W;
-            std::vector<int> cnt(nkeys + 1, 0);
             L.group.resize(n_lm);
+            if (par && g_host_nt > 1) {
+                // one large window: the same stable counting sort over landmark slices — a histogram per slice, offsets in (key, slice) order,
+                // every slice scatters its own landmarks (config 4: the serial sort was half of the host preparation)
+                const int T = g_host_nt; const int per = (n_lm + T - 1) / T;
+                std::vector<int> cnt((size_t)T * nkeys, 0);
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+                for (int sidx = 0; sidx < T; sidx++) {
+                    int *c = cnt.data() + (size_t)sidx * nkeys;
+                    for (int l = sidx * per; l < std::min(n_lm, (sidx + 1) * per); l++) {
+                        const int a = L.optr[l], b = L.optr[l + 1];
+                        const int key = (b > a ? kf[a] : maxkf + 1) * W + (b - a);
+                        L.group[l] = key; c[key]++;
+                    }
+                }
+                int running = 0;
+                for (int k = 0; k < nkeys; k++) for (int sidx = 0; sidx < T; sidx++) { int &c = cnt[(size_t)sidx * nkeys + k]; const int v = c; c = running; running += v; }
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+                for (int sidx = 0; sidx < T; sidx++) {
+                    int *c = cnt.data() + (size_t)sidx * nkeys;
+                    for (int l = sidx * per; l < std::min(n_lm, (sidx + 1) * per); l++) L.perm[c[L.group[l]]++] = l;
+                }
+                return;
+            }
+            std::vector<int> cnt(nkeys + 1, 0);
             for (int l = 0; l < n_lm; l++) {
                 const int a = L.optr[l], b = L.optr[l + 1];
                 const int key = (b > a ? kf[a] : maxkf + 1) * W + (b - a);      // landmarks without observations go last

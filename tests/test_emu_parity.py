@@ -61,3 +61,53 @@ def test_dense_cholesky_launch_geometry(emu, oracle, env):
         g.assert_state_close(o, r, P, abi.PROFILE_G)
     finally:
         s.close()
+
+
+def _with_threads(n, fn):
+    import os
+    old = os.environ.get("PLBA_HOST_THREADS")
+    os.environ["PLBA_HOST_THREADS"] = str(n)
+    try:
+        return fn()
+    finally:
+        if old is None:
+            os.environ.pop("PLBA_HOST_THREADS", None)
+        else:
+            os.environ["PLBA_HOST_THREADS"] = old
+
+
+def _same_results(a, b):
+    import numpy as np
+    for f in ("kf_T_wc", "pt_xyz", "ls_plk", "ls_orth", "po_chi2", "lo_chi2", "po_flags", "lo_flags"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    assert a.n_trials == b.n_trials and np.array_equal(a.trace, b.trace)
+
+
+@pytest.mark.parametrize("path", [1, 2], ids=["chunk-kernels", "warp-kernels"])
+def test_host_preparation_parallel_equals_serial(emu, path):
+    """The host side of plba_upload / plba_download on several threads (a large window: slice-parallel signature order, counting sort, copies; a
+    batch: window-parallel validation, runs, layout statistics) lays the problem out exactly as one thread does: same layout statistics, and —
+    the emulation adds in a fixed order — bit-identical results, chi2 and flags in the caller's order included."""
+    from pl_slam_plucker_b200 import abi, scene
+    opt = abi.Options(abi.PROFILE_G, 1, iters_stage1=1, iters_stage2=0)
+    big = scene.make_scene(1, n_kf_free=30, n_kf_fixed=2, n_pt=60000, n_ls=4000, seed=77)      # > 200 000 point observations, > 40 000 landmarks: the parallel loops are taken
+    assert big.n_pobs > 200000 and big.n_pt > 40000
+    batch = scene.make_batch(12, 3, n_pt=300, n_ls=60)
+    out = {}
+    for nt in (1, 4):
+        s = solver.LBASolver(0, lib=emu)
+        s.set_kernel_path(path)
+        try:
+            def run():
+                r = s.solve(big, opt)
+                st = s.layout_stats()
+                rc, rs = s.solve_batch(batch, opt)
+                return r, st, rs, s.layout_stats()
+            out[nt] = _with_threads(nt, run)
+        finally:
+            s.close()
+    (r1, st1, b1, bst1), (r4, st4, b4, bst4) = out[1], out[4]
+    assert st1 == st4 and bst1 == bst4
+    _same_results(r1, r4)
+    for x, y in zip(b1, b4):
+        _same_results(x, y)
