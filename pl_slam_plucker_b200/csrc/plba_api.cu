@@ -1049,36 +1049,73 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
             std::vector<Seg> &sgs = loc_sg[wc]; std::vector<int> &fps = loc_fp[wc];      // fp0 is relative to this list until the concatenation
             // (1) observation offsets of the re-ordered landmarks (serial prefix), (2) the observation permutation (parallel for large
             // windows: 12.5 M entries at config 5), (3) the runs (serial, index compares only)
-            int ob = ob0;
-            for (int nl_i = 0; nl_i < nl; nl_i++) { const int old = L.perm[nl_i]; ptr[lm0 + nl_i] = ob; ob += L.optr[old + 1] - L.optr[old]; }
-#pragma omp parallel for num_threads(g_host_nt) schedule(static) if (nl > PAR_LM)
-            for (int nl_i = 0; nl_i < nl; nl_i++) {
-                const int old = L.perm[nl_i], a = L.optr[old], b = L.optr[old + 1];
-                perm[lm0 + nl_i] = lm0 + old;
-                int o = ptr[lm0 + nl_i];
-                for (int i = a; i < b; i++) operm[o++] = ob0 + i;
-            }
-            int run_first_old = -1;
-            for (int nl_i = 0; nl_i < nl; nl_i++) {
-                const int old = L.perm[nl_i], a = L.optr[old], b = L.optr[old + 1], no = b - a;
-                const int g = lm0 + nl_i;
-                bool join = false;
-                if (run_first_old >= 0) {
-                    Seg &s = sgs.back();
-                    if (s.nobs == no) {
-                        const int fa = L.optr[run_first_old];
-                        if (!L.group.empty()) join = (L.group[run_first_old] == L.group[old]);
-                        else { join = true; for (int i = 0; i < no; i++) if (kf[fa + i] != kf[a + i]) { join = false; break; } }
+            // One large window (first branch): L.optr is read in signature order, i.e. at scattered places, so everything that touches it
+            // runs in parallel — track lengths and "a new run starts here" flags (a landmark joins the run of its PREDECESSOR, which has the
+            // run's signature) — and the serial passes walk sequential arrays only.
+            if (nl > PAR_LM && g_host_nt > 1) {
+                std::vector<int> lens(nl); std::vector<unsigned char> brk(nl);
+#pragma omp parallel for num_threads(g_host_nt) schedule(static)
+                for (int nl_i = 0; nl_i < nl; nl_i++) {
+                    const int old = L.perm[nl_i], a = L.optr[old], no = L.optr[old + 1] - a;
+                    lens[nl_i] = no;
+                    bool join = false;
+                    if (nl_i > 0) {
+                        const int pold = L.perm[nl_i - 1], pa = L.optr[pold];
+                        if (L.optr[pold + 1] - pa == no) {
+                            if (!L.group.empty()) join = (L.group[pold] == L.group[old]);
+                            else { join = true; for (int i = 0; i < no; i++) if (kf[pa + i] != kf[a + i]) { join = false; break; } }
+                        }
                     }
-                    if (join) s.n_lm++;
+                    brk[nl_i] = join ? 0 : 1;
                 }
-                if (!join) {      // (a run of landmarks WITHOUT observations has nobs = 0: only the update kernel visits it)
-                    Seg s{}; s.lm0 = g; s.n_lm = 1; s.nobs = no; s.fp0 = (int)fps.size(); s.pad1 = w;
+                int ob = ob0;
+                for (int nl_i = 0; nl_i < nl; nl_i++) { ptr[lm0 + nl_i] = ob; ob += lens[nl_i]; }
+#pragma omp parallel for num_threads(g_host_nt) schedule(static)
+                for (int nl_i = 0; nl_i < nl; nl_i++) {
+                    const int old = L.perm[nl_i], a = L.optr[old];
+                    perm[lm0 + nl_i] = lm0 + old;
+                    int o = ptr[lm0 + nl_i];
+                    for (int i = 0; i < lens[nl_i]; i++) operm[o++] = ob0 + a + i;
+                }
+                for (int nl_i = 0; nl_i < nl; nl_i++) {
+                    if (!brk[nl_i]) { sgs.back().n_lm++; continue; }
+                    const int old = L.perm[nl_i], a = L.optr[old], no = lens[nl_i];
+                    Seg s{}; s.lm0 = lm0 + nl_i; s.n_lm = 1; s.nobs = no; s.fp0 = (int)fps.size(); s.pad1 = w;
                     for (int i = 0; i < no; i++) if (p.kf_slot[kf[a + i]] >= 0) { fps.push_back(i); s.nfree++; }
-                    sgs.push_back(s); run_first_old = old;
+                    sgs.push_back(s);
+                }
+            } else {
+                int ob = ob0;
+                for (int nl_i = 0; nl_i < nl; nl_i++) { const int old = L.perm[nl_i]; ptr[lm0 + nl_i] = ob; ob += L.optr[old + 1] - L.optr[old]; }
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) if (nl > PAR_LM)
+                for (int nl_i = 0; nl_i < nl; nl_i++) {
+                    const int old = L.perm[nl_i], a = L.optr[old], b = L.optr[old + 1];
+                    perm[lm0 + nl_i] = lm0 + old;
+                    int o = ptr[lm0 + nl_i];
+                    for (int i = a; i < b; i++) operm[o++] = ob0 + i;
+                }
+                int run_first_old = -1;
+                for (int nl_i = 0; nl_i < nl; nl_i++) {
+                    const int old = L.perm[nl_i], a = L.optr[old], b = L.optr[old + 1], no = b - a;
+                    const int g = lm0 + nl_i;
+                    bool join = false;
+                    if (run_first_old >= 0) {
+                        Seg &s = sgs.back();
+                        if (s.nobs == no) {
+                            const int fa = L.optr[run_first_old];
+                            if (!L.group.empty()) join = (L.group[run_first_old] == L.group[old]);
+                            else { join = true; for (int i = 0; i < no; i++) if (kf[fa + i] != kf[a + i]) { join = false; break; } }
+                        }
+                        if (join) s.n_lm++;
+                    }
+                    if (!join) {      // (a run of landmarks WITHOUT observations has nobs = 0: only the update kernel visits it)
+                        Seg s{}; s.lm0 = g; s.n_lm = 1; s.nobs = no; s.fp0 = (int)fps.size(); s.pad1 = w;
+                        for (int i = 0; i < no; i++) if (p.kf_slot[kf[a + i]] >= 0) { fps.push_back(i); s.nfree++; }
+                        sgs.push_back(s); run_first_old = old;
+                    }
                 }
             }
-            (void)ob;      // = ob0 + the window's observations: the entry after its last landmark is the next window's first (written there); the very last one below
+            // (the entry after a window's last landmark = ob0 + its observations is the next window's first, written there; the very last one below)
         }
     }
     if (h->warp_path) {
