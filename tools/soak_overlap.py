@@ -18,5 +18,6 @@ for it in range(n):
     if key not in ref: ref[key] = r
     else:
         d = float(np.abs(r.kf_T_wc - ref[key].kf_T_wc).max()); worst = max(worst, d)
-        assert d < 1e-9 and abs(len(r.trace) - len(ref[key].trace)) <= 4,      # (a stalled LM decides on rounding: the 21-keyframe window's trace runs 30-33 records from run to run, tools/trace_len_dist.py)  (it, key, d, len(r.trace), len(ref[key].trace))
+        # (a stalled LM decides on rounding: the 21-keyframe window's trace runs 30-33 records from run to run, tools/trace_len_dist.py)
+        assert d < 1e-9 and abs(len(r.trace) - len(ref[key].trace)) <= 4, (it, key, d, len(r.trace), len(ref[key].trace))
 print("soak ok: %d solves in %.1f s, worst pose deviation between repeats %.2e" % (n, time.time() - t0, worst))
