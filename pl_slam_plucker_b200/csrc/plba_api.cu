@@ -707,7 +707,7 @@ static void launch_solve(plba_handle h) {
         // ceil(log2 N) levels down and up, every level one launch with a CTA per eliminated node
         for (int w = 0; w < P.n_win; w++) {
             const BcrW &B = h->bcr[w];
-            if (B.N == 0 || h->wins[w].n_pobs + h->wins[w].n_lobs == 0) continue;
+            if (B.N == 0 || (h->wins[w].n_pobs + h->wins[w].n_lobs == 0 && !has_exchange(h))) continue;      // (a rank with an EMPTY SHARD still solves the summed system: every rank must take the same step)
             // (the assembly kernels have accumulated straight into the node form, and the exchange step of the sharded path has summed
             //  it over the ranks: config 5 moves 17 MB, there is no dense S)
             int s_top = 0;
@@ -743,7 +743,7 @@ static void launch_solve(plba_handle h) {
     // (b) writes rows >= lo + 128 only, the panel reads / writes rows lo .. lo + 95: disjoint; both read the finished rows of panel k.
     for (int w = 0; w < P.n_win; w++) {
         const int n = 6 * h->wins[w].n_free;
-        if (n == 0 || h->wins[w].n_pobs + h->wins[w].n_lobs == 0) continue;
+        if (n == 0 || (h->wins[w].n_pobs + h->wins[w].n_lobs == 0 && !has_exchange(h))) continue;
         cudaStream_t sm = h->stream, sp = h->stream;
 #ifndef PLBA_HOST_EMU
         if (h->stream_panel && !h->no_lookahead) sp = h->stream_panel;
@@ -1411,7 +1411,9 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
         if (n == 1) HOSTPROF("fl.obs");
         WinCtrl c{};
         c.need_init = 1; c.apply = 1; c.ni = 2.0; c.err_prev = 999999999.9; c.n_lm_pt = p.n_pt; c.n_lm_ls = p.n_ls; c.n_obs = p.n_pobs + p.n_lobs;
-        if (p.n_pobs + p.n_lobs == 0) c.done = 1;      // nothing to do (src/mapHandler.cpp:1496-1500)
+        // nothing to do (src/mapHandler.cpp:1496-1500) — except on the landmark-sharded path: a rank whose shard is empty contributes zeros to
+        // every exchange and takes the same LM decisions as the others (skipping it would leave them blocked in the first all-reduce)
+        if (p.n_pobs + p.n_lobs == 0 && !has_exchange(h)) c.done = 1;
         ctrl0[w] = c;
     }
 
@@ -1657,7 +1659,7 @@ int plba_download(plba_handle h, int32_t n, plba_result *res) {
     for (int w = 0; w < n; w++) {
         const WinInfo &wi = h->wins[w]; plba_result &r = res[w];
         r.n_trace = ctrl[w].n_trace; r.n_trials = ctrl[w].n_trials;
-        r.status = (wi.n_pobs + wi.n_lobs == 0) ? PLBA_DISCARDED : (ctrl[w].numeric & (1 << 30)) ? PLBA_E_NUMERIC : PLBA_OK;
+        r.status = (wi.n_pobs + wi.n_lobs == 0 && !has_exchange(h)) ? PLBA_DISCARDED : (ctrl[w].numeric & (1 << 30)) ? PLBA_E_NUMERIC : PLBA_OK;
         if (r.trace) for (int i = 0; i < std::min(r.n_trace, std::min(r.trace_cap, P.trace_cap)); i++) r.trace[i] = trace[(size_t)w * P.trace_cap + i];
         if (r.kf_T_wc) for (int i = 0; i < 12 * wi.n_kf; i++) r.kf_T_wc[i] = T[(size_t)12 * wi.kf0 + i];
         if (r.x_pose) for (int i = 0; i < 6 * wi.n_free; i++) r.x_pose[i] = X[(size_t)6 * wi.slot0 + i];
@@ -1732,7 +1734,7 @@ int plba_solve_batch(plba_handle h, int32_t n, const plba_problem *probs, const 
 
 int plba_solve(plba_handle h, const plba_problem *prob, const plba_options *opt, plba_result *res) {
     if (!prob || !res) return PLBA_E_ARG;
-    if (prob->n_pobs + prob->n_lobs == 0) { res->status = PLBA_DISCARDED; res->n_trace = 0; res->n_trials = 0; return PLBA_DISCARDED; }   // src/mapHandler.cpp:1496-1500
+    if (prob->n_pobs + prob->n_lobs == 0 && !(h && has_exchange(h))) { res->status = PLBA_DISCARDED; res->n_trace = 0; res->n_trials = 0; return PLBA_DISCARDED; }   // src/mapHandler.cpp:1496-1500
     int rc = plba_solve_batch(h, 1, prob, opt, res);
     return rc ? rc : res->status;
 }

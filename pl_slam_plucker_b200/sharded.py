@@ -108,9 +108,18 @@ class ShardedLBA:
             self.solver.set_allreduce(self._fn)
             self.solver.set_allreduce_ranks(self.world, self.rank)
 
-    def upload(self, P, opt):
+    def upload(self, P, opt, masks=None):
+        """`masks` = (point mask, line mask) of this rank's landmarks instead of the balanced base-keyframe split (the masks of all ranks
+        must partition the landmarks).  An EMPTY shard is legal inside the library — the rank contributes zeros to every exchange and takes the
+        same LM decisions —; the default split refuses it because it means the window was spread over too many ranks."""
         if opt.profile != abi.PROFILE_G:
             raise ValueError("sharding is defined for profile G (the Plücker-mode LBA of BASELINE configs 4-5)")
+        if masks is not None:
+            mp_, ml_ = masks
+            self.shard, self.pt_index, self.ls_index = P.subset_landmarks(mp_, ml_), np.flatnonzero(mp_), np.flatnonzero(ml_)
+            self.full = P
+            self.solver.upload(self.shard, opt)
+            return
         # emptiness is decided from the FULL problem, identically on every rank, before anything collective happens: a rank that
         # raised alone would leave the others blocked in the first exchange
         for r in range(self.world):
@@ -124,9 +133,9 @@ class ShardedLBA:
     def run(self):
         self.solver.run()
 
-    def solve(self, P, opt):
+    def solve(self, P, opt, masks=None):
         """Upload the rank's shard, run the whole LM schedule with the exchange step, return this rank's Result."""
-        self.upload(P, opt)
+        self.upload(P, opt, masks)
         self.solver.run()
         return self.solver.download()[0]
 

@@ -479,7 +479,7 @@ def test_two_handles_on_different_devices_in_one_process(oracle):
         s0.close(); s1.close()
 
 
-@pytest.mark.parametrize("shape", ["small", "banded", "C4"])
+@pytest.mark.parametrize("shape", ["small", "banded", "C4", "empty-shard"])
 def test_sharded_two_gpus_equal_single_gpu_and_oracle(oracle, shape):
     """The landmark-sharded path on 2 GPUs of one box, driven as a C++ host would drive it: plba_create_group() (one handle per device,
     NCCL communicator inside the library), one host thread per handle, every rank uploads its shard.  The collective is the library's
@@ -491,7 +491,7 @@ def test_sharded_two_gpus_equal_single_gpu_and_oracle(oracle, shape):
     from pl_slam_plucker_b200 import sharded, solver
     if shape == "small":
         P = scene.make_scene(1, seed=31, n_kf_free=8, n_kf_fixed=2, n_pt=300, n_ls=80); q = 0        # one-CTA solver: [S | g | ...] is exchanged
-    elif shape == "banded":
+    elif shape in ("banded", "empty-shard"):
         P = scene.make_scene(1, seed=31, n_kf_free=40, n_kf_fixed=2, n_pt=800, n_ls=200); q = 1      # block cyclic reduction: the band in node form
     else:
         P = scene.make_scene(4); q = 0                                                                # BASELINE config 4 at full size, profile G faithful
@@ -506,7 +506,12 @@ def test_sharded_two_gpus_equal_single_gpu_and_oracle(oracle, shape):
         try:
             s = grp.members[r]
             assert s.comm_info() == (world, r)
-            shard, pti, lsi = sharded.shard_problem(P, r, world)
+            if shape == "empty-shard":      # rank 0 holds every landmark, rank 1 none: it must still take part in every exchange and end with the same poses
+                own = np.ones if r == 0 else np.zeros
+                mp_, ml_ = own(P.n_pt, bool), own(P.n_ls, bool)
+                shard, pti, lsi = P.subset_landmarks(mp_, ml_), np.flatnonzero(mp_), np.flatnonzero(ml_)
+            else:
+                shard, pti, lsi = sharded.shard_problem(P, r, world)
             s.upload(shard, opt)
             s.run()
             res[r] = (s.download()[0], pti, lsi, s.timing(), s.kernel_path())
@@ -527,6 +532,9 @@ def test_sharded_two_gpus_equal_single_gpu_and_oracle(oracle, shape):
             np.testing.assert_allclose(rr.ls_orth, o.ls_orth[lsi], rtol=0, atol=STATE_ATOL)
             np.testing.assert_allclose(rr.ls_plk, o.ls_plk[lsi], rtol=0, atol=STATE_ATOL)
             mp_, ml_ = sharded.shard_masks(P, r, world)
+            if shape == "empty-shard":
+                mp_ = (np.ones if r == 0 else np.zeros)(P.n_pt, bool)
+                assert rr.status == 0
             near = np.abs(o.po_chi2[mp_[P.po_lm]] - 5.991) < 1e-6
             assert ((rr.po_flags == o.po_flags[mp_[P.po_lm]]) | near).all()
         if shape != "small":

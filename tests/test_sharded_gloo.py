@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, quirks, out_dir, shape):
+def _worker(rank, world, port, quirks, out_dir, shape, empty_rank=-1):
     for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "emu")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -33,11 +33,16 @@ def _worker(rank, world, port, quirks, out_dir, shape):
         s = solver.LBASolver(0, lib=emu_lib.load())
         sh = sharded.ShardedLBA(s, rank, world)
         opt = abi.Options(abi.PROFILE_G, quirks)
-        r = sh.solve(P, opt)
+        masks = None
+        if empty_rank >= 0:      # one rank holds every landmark, the other an EMPTY shard (it still takes part in every exchange)
+            own = np.ones if rank != empty_rank else np.zeros
+            masks = (own(P.n_pt, bool), own(P.n_ls, bool))
+        r = sh.solve(P, opt, masks)
         np.savez(os.path.join(out_dir, "rank%d.npz" % rank), kf_T_wc=r.kf_T_wc, pt_xyz=r.pt_xyz, ls_orth=r.ls_orth, ls_plk=r.ls_plk,
                  pt_index=sh.pt_index, ls_index=sh.ls_index, chi=r.trace["chi"], chi_new=r.trace["chi_new"], lam=r.trace["lambda"],
                  accepted=r.trace["accepted"], rho=r.trace["rho"], po_flags=r.po_flags, lo_flags=r.lo_flags,
-                 po_sel=sharded.shard_masks(P, rank, world)[0][P.po_lm], lo_sel=sharded.shard_masks(P, rank, world)[1][P.lo_lm])
+                 po_sel=(masks or sharded.shard_masks(P, rank, world))[0][P.po_lm], lo_sel=(masks or sharded.shard_masks(P, rank, world))[1][P.lo_lm],
+                 status=r.status, n_trials=r.n_trials)
         s.close()
     finally:
         dist.destroy_process_group()
@@ -85,6 +90,34 @@ def test_two_rank_sharded_lba_equals_single_process_oracle(tmp_path, oracle, qui
     assert ((pf == o.po_flags) | near).all()
     nearl = np.abs(o.lo_chi2 - 5.991) < 1e-6
     assert ((lf == o.lo_flags) | nearl).all()
+
+
+@pytest.mark.parametrize("shape", [SMALL, LARGE], ids=["small", "large-banded"])
+def test_rank_with_empty_shard_takes_part(tmp_path, oracle, shape):
+    """A rank whose shard holds no landmark at all (more ranks than a window can feed) must not drop out: it contributes zeros to every
+    exchange, solves the same summed system and ends with the same poses as the rank that holds everything — which equal the oracle's."""
+    from helpers import COST_RTOL, RHO_MARGIN, STATE_ATOL
+    from pl_slam_plucker_b200 import abi, scene
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), 1, str(tmp_path), shape, 1), nprocs=world, join=True)
+    P = scene.make_scene(1, seed=31, **shape)
+    o = oracle.solve(P, abi.Options(abi.PROFILE_G, 1))
+    z = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(world)]
+    assert int(z[0]["status"]) == 0 and int(z[1]["status"]) == 0 and int(z[0]["n_trials"]) == int(z[1]["n_trials"]) > 0
+    for k in ("chi", "chi_new", "lam", "accepted"):
+        np.testing.assert_array_equal(z[0][k], z[1][k])
+    np.testing.assert_array_equal(z[0]["kf_T_wc"], z[1]["kf_T_wc"])
+    assert z[1]["pt_index"].size == 0 and z[1]["po_flags"].size == 0
+    n = 0
+    for t in o.trace:
+        if abs(t["rho"]) < RHO_MARGIN and t["chi_new"] != 0.0:
+            break
+        n += 1
+    n = min(n, len(z[0]["chi"]))
+    assert n >= 5
+    np.testing.assert_allclose(z[0]["chi"][:n], o.trace["chi"][:n], rtol=COST_RTOL)
+    np.testing.assert_allclose(z[0]["kf_T_wc"], o.kf_T_wc, atol=STATE_ATOL)
+    np.testing.assert_allclose(z[0]["pt_xyz"], o.pt_xyz, atol=STATE_ATOL)
 
 
 def test_shard_partition_properties():
