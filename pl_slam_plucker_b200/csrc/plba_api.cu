@@ -1217,9 +1217,37 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
         for (int w = 0; w < n; w++) wbase[w + 1] = wbase[w] + (size_t)h->wins[w].n_free * h->wins[w].n_free;
         std::vector<unsigned char> &mark = h->mark; mark.assign(wbase[n], 0);
         int64_t n_off = 0, n_diag = 0, nnzb = 0; int band = 0;
+        // one (or few) large windows: the segments in parallel — marks are idempotent byte stores, the structural blocks are counted afterwards
+        const bool seg_par = n <= 8 && g_host_nt > 1 && sg_pt.size() + sg_ls.size() > 4096;
+        for (int w = 0; w < n && seg_par; w++) for (int cls = 0; cls < 2; cls++) {
+            const std::vector<Seg> &sgs = cls ? sg_ls : sg_pt; const std::vector<int> &fps = cls ? fp_ls : fp_pt;
+            const std::vector<int> &ptr = cls ? ls_ptr : pt_ptr; const std::vector<int> &operm = cls ? h->lo_perm : h->po_perm;
+            const plba_problem &p = probs[w]; const WinInfo &wi = h->wins[w];
+            const int32_t *kf = cls ? p.lo_kf : p.po_kf; const int ob0 = cls ? wi.lo0 : wi.po0;
+            unsigned char *mk = mark.data() + wbase[w];
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) reduction(+ : n_off, n_diag) reduction(max : band)
+            for (int si = seg_begin[cls][w]; si < seg_begin[cls][w + 1]; si++) {
+                const Seg &sg = sgs[si];
+                n_off += (int64_t)sg.nfree * (sg.nfree - 1) / 2; n_diag += sg.nfree;
+                const int o0 = ptr[sg.lm0];
+                int sl[OC];      // (a track holds at most OC observations: checked when the runs were built)
+                for (int i = 0; i < sg.nfree; i++) sl[i] = p.kf_slot[kf[operm[o0 + fps[sg.fp0 + i]] - ob0]];
+                for (int i = 0; i < sg.nfree; i++) for (int j = i; j < sg.nfree; j++) {
+                    int a = sl[i], b = sl[j];
+                    if (a > b) std::swap(a, b);
+                    if (b - a > band) band = b - a;
+                    __atomic_store_n(&mk[(size_t)a * wi.n_free + b], (unsigned char)1, __ATOMIC_RELAXED);
+                }
+            }
+        }
+        if (seg_par) {
+            const int64_t nm = (int64_t)wbase[n];
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) reduction(+ : nnzb)
+            for (int64_t i = 0; i < nm; i++) nnzb += mark[i];
+        }
         // windows in parallel for a batch: the marks of a window are its own stretch of `mark`
 #pragma omp parallel for num_threads(g_host_nt) schedule(dynamic, 4) reduction(+ : n_off, n_diag, nnzb) reduction(max : band) if (n > 8)
-        for (int w = 0; w < n; w++) for (int cls = 0; cls < 2; cls++) {
+        for (int w = 0; w < (seg_par ? 0 : n); w++) for (int cls = 0; cls < 2; cls++) {
             const std::vector<Seg> &sgs = cls ? sg_ls : sg_pt; const std::vector<int> &fps = cls ? fp_ls : fp_pt;
             const std::vector<int> &ptr = cls ? ls_ptr : pt_ptr; const std::vector<int> &operm = cls ? h->lo_perm : h->po_perm;
             const plba_problem &p = probs[w]; const WinInfo &wi = h->wins[w];
