@@ -239,8 +239,11 @@ struct ClassLayout {
     std::vector<int> optr;       // CSR of the caller's order (local)
     std::vector<int> group;      // signature group of each OLD landmark (equal group <=> identical keyframe sequence); empty = not grouped
 };
+static bool g_sig_prof = false;      // PLBA_HOST_PROF: phase times of the signature order of a large window
 static void signature_order(int n_lm, int n_obs, const int32_t *lm, const int32_t *kf, bool permute, ClassLayout &L) {
-    const bool par = n_obs > PAR_OBS;      // one large window: the loops below run in parallel (a region costs more than a small window's whole sort)
+    const bool par = n_obs > PAR_OBS;
+    auto t_sp = std::chrono::steady_clock::now();
+    auto SIGPROF = [&](const char *name) { if (g_sig_prof && par) { const auto t_ = std::chrono::steady_clock::now(); std::fprintf(stderr, "[sigorder] %-10s %.3f ms\n", name, std::chrono::duration<double, std::milli>(t_ - t_sp).count()); t_sp = t_; } };      // one large window: the loops below run in parallel (a region costs more than a small window's whole sort)
     // lm[] is non-decreasing (validated): optr[l] = first observation whose landmark is >= l
     if (par) {
         L.optr.assign(n_lm + 1, n_obs);
@@ -258,9 +261,11 @@ static void signature_order(int n_lm, int n_obs, const int32_t *lm, const int32_
         for (int i = n_obs - 1; i >= 0; i--) L.optr[lm[i]] = i;
         for (int l = n_lm - 1; l >= 0; l--) L.optr[l] = L.optr[l] < 0 ? L.optr[l + 1] : L.optr[l];
     }
+    SIGPROF("optr");
     L.perm.resize(n_lm);
 #pragma omp parallel for num_threads(g_host_nt) schedule(static) if (par)
     for (int l = 0; l < n_lm; l++) L.perm[l] = l;
+    SIGPROF("iota");
     if (!permute || n_lm < 2) return;
     {   // fast path: every track is a contiguous keyframe run (the usual sliding-window case) => the signature IS (first KF, length):
         // one pass over the observations and a counting sort, no hashing
@@ -284,6 +289,7 @@ static void signature_order(int n_lm, int n_obs, const int32_t *lm, const int32_
                 maxkf = std::max(maxkf, b > a ? v : 0);
             }
         }
+        SIGPROF("contig");
         const bool contiguous = broken <= 0;
         if (contiguous && (int64_t)(maxkf + 2) * (maxlen + 1) <= 4 * (int64_t)n_lm + 4096) {
             const int W = maxlen + 1, nkeys = (maxkf + 2) * W;
@@ -302,13 +308,16 @@ static void signature_order(int n_lm, int n_obs, const int32_t *lm, const int32_
                         L.group[l] = key; c[key]++;
                     }
                 }
+                SIGPROF("hist");
                 int running = 0;
                 for (int k = 0; k < nkeys; k++) for (int sidx = 0; sidx < T; sidx++) { int &c = cnt[(size_t)sidx * nkeys + k]; const int v = c; c = running; running += v; }
+                SIGPROF("prefix");
 #pragma omp parallel for num_threads(T) schedule(static, 1)
                 for (int sidx = 0; sidx < T; sidx++) {
                     int *c = cnt.data() + (size_t)sidx * nkeys;
                     for (int l = sidx * per; l < std::min(n_lm, (sidx + 1) * per); l++) L.perm[c[L.group[l]]++] = l;
                 }
+                SIGPROF("scatter");
                 return;
             }
             std::vector<int> cnt(nkeys + 1, 0);
@@ -325,8 +334,7 @@ static void signature_order(int n_lm, int n_obs, const int32_t *lm, const int32_
     // group landmarks by exact signature with an open-addressing table (hash -> group), then order the groups by
     // (first keyframe, first appearance) and counting-sort the landmarks by group: O(n) instead of a comparison sort
     struct Slot { uint64_t hsh; int group, rep; };
-    size_t cap = 1024;
-    std::vector<Slot> table(cap, Slot{0, -1, -1});
+    struct GroupPart { std::vector<Slot> table; std::vector<int> rep, count, first; };
     std::vector<int> group_of(n_lm), g_first, g_rep, g_count;
     auto same_sig = [&](int l, int r) {
         const int a = L.optr[l], b = L.optr[l + 1], c = L.optr[r];
@@ -334,38 +342,77 @@ static void signature_order(int n_lm, int n_obs, const int32_t *lm, const int32_
         for (int i = 0; i < b - a; i++) if (kf[a + i] != kf[c + i]) return false;
         return true;
     };
-    for (int l = 0; l < n_lm; l++) {
+    auto sig_hash = [&](int l) {
         const int a = L.optr[l], b = L.optr[l + 1];
         uint64_t hsh = 1469598103934665603ULL ^ (uint64_t)(b - a);
         for (int i = a; i < b; i++) { hsh ^= (uint64_t)(uint32_t)kf[i] + 0x9e3779b97f4a7c15ULL + (hsh << 6) + (hsh >> 2); hsh *= 1099511628211ULL; }
-        size_t pos = (size_t)(hsh >> 17) & (cap - 1);
-        int g = -1;
-        while (table[pos].group >= 0) {
-            if (table[pos].hsh == hsh && same_sig(l, table[pos].rep)) { g = table[pos].group; break; }
-            pos = (pos + 1) & (cap - 1);
-        }
-        if (g < 0) {
-            g = (int)g_rep.size();
-            g_rep.push_back(l); g_count.push_back(0); g_first.push_back(b > a ? kf[a] : 0x7fffffff);
-            table[pos] = Slot{hsh, g, l};
-            if (2 * g_rep.size() > cap) {      // grow: re-insert the representatives
-                cap *= 4;
-                std::vector<Slot> bigger(cap, Slot{0, -1, -1});
-                for (const Slot &sl : table) if (sl.group >= 0) { size_t q = (size_t)(sl.hsh >> 17) & (cap - 1); while (bigger[q].group >= 0) q = (q + 1) & (cap - 1); bigger[q] = sl; }
-                table.swap(bigger);
+        return hsh;
+    };
+    std::vector<uint64_t> hashes;
+    // the table walk over the landmarks whose hash falls into part `part` of `nparts` (1 = all): group ids in order of first appearance
+    auto walk = [&](int part, int nparts, GroupPart &G) {
+        size_t cap = 1024;
+        G.table.assign(cap, Slot{0, -1, -1});
+        for (int l = 0; l < n_lm; l++) {
+            const uint64_t hsh = hashes.empty() ? sig_hash(l) : hashes[l];
+            if (nparts > 1 && (int)((hsh >> 48) % (uint64_t)nparts) != part) continue;
+            const int a = L.optr[l], b = L.optr[l + 1];
+            size_t pos = (size_t)(hsh >> 17) & (cap - 1);
+            int g = -1;
+            while (G.table[pos].group >= 0) {
+                if (G.table[pos].hsh == hsh && same_sig(l, G.table[pos].rep)) { g = G.table[pos].group; break; }
+                pos = (pos + 1) & (cap - 1);
             }
+            if (g < 0) {
+                g = (int)G.rep.size();
+                G.rep.push_back(l); G.count.push_back(0); G.first.push_back(b > a ? kf[a] : 0x7fffffff);
+                G.table[pos] = Slot{hsh, g, l};
+                if (2 * G.rep.size() > cap) {      // grow: re-insert the representatives
+                    cap *= 4;
+                    std::vector<Slot> bigger(cap, Slot{0, -1, -1});
+                    for (const Slot &sl : G.table) if (sl.group >= 0) { size_t q = (size_t)(sl.hsh >> 17) & (cap - 1); while (bigger[q].group >= 0) q = (q + 1) & (cap - 1); bigger[q] = sl; }
+                    G.table.swap(bigger);
+                }
+            }
+            group_of[l] = g; G.count[g]++;
         }
-        group_of[l] = g; g_count[g]++;
+    };
+    if (par && g_host_nt > 1) {
+        // one large window: the hashes (the pass over every observation) in parallel, then one table per hash partition, each walked by its own
+        // thread over ALL landmarks in order (equal signatures have equal hashes, i.e. meet in one partition); the partitions' groups are
+        // concatenated — the order of the groups below depends on (first keyframe, first landmark of the group) only, not on the group ids
+        const int T = g_host_nt;
+        hashes.resize(n_lm);
+#pragma omp parallel for num_threads(T) schedule(static)
+        for (int l = 0; l < n_lm; l++) hashes[l] = sig_hash(l);
+        SIGPROF("hashes");
+        std::vector<GroupPart> parts(T);
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+        for (int pi = 0; pi < T; pi++) walk(pi, T, parts[pi]);
+        std::vector<int> off(T + 1, 0);
+        for (int pi = 0; pi < T; pi++) off[pi + 1] = off[pi] + (int)parts[pi].rep.size();
+#pragma omp parallel for num_threads(T) schedule(static)
+        for (int l = 0; l < n_lm; l++) group_of[l] += off[(int)((hashes[l] >> 48) % (uint64_t)T)];
+        for (int pi = 0; pi < T; pi++) {
+            g_rep.insert(g_rep.end(), parts[pi].rep.begin(), parts[pi].rep.end()); g_count.insert(g_count.end(), parts[pi].count.begin(), parts[pi].count.end());
+            g_first.insert(g_first.end(), parts[pi].first.begin(), parts[pi].first.end());
+        }
+    } else {
+        GroupPart G;
+        walk(0, 1, G);
+        g_rep.swap(G.rep); g_count.swap(G.count); g_first.swap(G.first);
     }
+    SIGPROF("table");
     const int ng = (int)g_rep.size();
     std::vector<int> order(ng);
     for (int g = 0; g < ng; g++) order[g] = g;
-    std::sort(order.begin(), order.end(), [&](int x, int y) { return g_first[x] != g_first[y] ? g_first[x] < g_first[y] : x < y; });
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return g_first[x] != g_first[y] ? g_first[x] < g_first[y] : g_rep[x] < g_rep[y]; });      // (first keyframe, first appearance)
     std::vector<int> start(ng, 0);
     int acc = 0;
     for (int r = 0; r < ng; r++) { start[order[r]] = acc; acc += g_count[order[r]]; }
     for (int l = 0; l < n_lm; l++) L.perm[start[group_of[l]]++] = l;       // stable inside a group
     L.group.swap(group_of);
+    SIGPROF("groups");
 }
 
 extern "C" {
@@ -947,6 +994,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     if (h->h2d_pending) { CK(cudaEventSynchronize(h->ev_h2d)); h->h2d_pending = false; }   // the previous upload's H2D copies may still be reading h_in / h_P
     const auto t_host0 = std::chrono::steady_clock::now();
     auto t_hp = t_host0; const bool hostprof = std::getenv("PLBA_HOST_PROF") != nullptr;
+    g_sig_prof = hostprof;
 #define HOSTPROF(name) do { if (hostprof) { const auto t_ = std::chrono::steady_clock::now(); std::fprintf(stderr, "[upload] %-10s %.3f ms\n", name, std::chrono::duration<double, std::milli>(t_ - t_hp).count()); t_hp = t_; } } while (0)
     h->uploaded = false;
     h->opt = *opt;

@@ -90,8 +90,8 @@ def test_host_preparation_parallel_equals_serial(emu, path):
     the emulation adds in a fixed order — bit-identical results, chi2 and flags in the caller's order included."""
     from pl_slam_plucker_b200 import abi, scene
     opt = abi.Options(abi.PROFILE_G, 1, iters_stage1=1, iters_stage2=0)
-    big = scene.make_scene(1, n_kf_free=30, n_kf_fixed=2, n_pt=60000, n_ls=4000, seed=77)      # > 200 000 point observations, > 40 000 landmarks: the parallel loops are taken
-    assert big.n_pobs > 200000 and big.n_pt > 40000
+    big = scene.make_scene(1, n_kf_free=30, n_kf_fixed=2, n_pt=60000, n_ls=56000, seed=77)      # > 200 000 observations and > 40 000 landmarks in BOTH classes: the parallel loops are taken (lines: the hash-grouping path)
+    assert big.n_pobs > 200000 and big.n_lobs > 200000
     batch = scene.make_batch(12, 3, n_pt=300, n_ls=60)
     out = {}
     for nt in (1, 4):
