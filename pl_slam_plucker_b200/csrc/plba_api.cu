@@ -1069,8 +1069,11 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
     int max_track = 0;
     for (int w = 0; w < n; w++) for (int cls = 0; cls < 2; cls++) {
         const ClassLayout &L = cls ? Lls[w] : Lps[w];
-        for (size_t l = 0; l + 1 < L.optr.size(); l++) max_track = std::max(max_track, L.optr[l + 1] - L.optr[l]);
+        const int nl1 = (int)L.optr.size() - 1;
+#pragma omp parallel for num_threads(g_host_nt) schedule(static) reduction(max : max_track) if (nl1 > PAR_LM)
+        for (int l = 0; l < nl1; l++) max_track = std::max(max_track, L.optr[l + 1] - L.optr[l]);
     }
+    if (n == 1) HOSTPROF("ch.maxtrk");
     // routing by size, measured (profiles/README.md r01f-h, tools/route_sweep.py): up to ~0.7 M observations the two implementations are
     // within 4 % of each other with the CTA-chunk kernels ahead (a small upload is latency-bound and their warps share one instruction
     // stream); from ~1 M observations on the warp kernels win (config 3: 85 against 119 ms, config 5: assembly 1.9 against 2.8 ms)
@@ -1166,6 +1169,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
             // (the entry after a window's last landmark = ob0 + its observations is the next window's first, written there; the very last one below)
         }
     }
+    if (n == 1 && h->warp_path) HOSTPROF("ch.runs");
     if (h->warp_path) {
         pt_ptr[tot.n_pt] = tot.n_pobs; ls_ptr[tot.n_ls] = tot.n_lobs;
         for (int w = 0; w < n; w++) for (int cls = 0; cls < 2; cls++) {
@@ -1176,6 +1180,7 @@ int plba_upload(plba_handle h, int32_t n, const plba_problem *probs, const plba_
             fps.insert(fps.end(), loc_fp[2 * (size_t)w + cls].begin(), loc_fp[2 * (size_t)w + cls].end());
         }
         seg_begin[0][n] = (int)sg_pt.size(); seg_begin[1][n] = (int)sg_ls.size();
+        if (n == 1) HOSTPROF("ch.concat");
         // cut the runs into items of up to W_ITEM_PASSES_MAX passes (fewer when the upload is small)
         int64_t total_passes = 0;
         for (int cls = 0; cls < 2; cls++) for (const Seg &sg : (cls ? sg_ls : sg_pt)) { const int lpp = sg.nobs ? 32 / sg.nobs : 32; total_passes += (sg.n_lm + lpp - 1) / lpp; }
